@@ -1,0 +1,248 @@
+"""TEST INFRASTRUCTURE ONLY -- freeze golden vectors from the REAL reference.
+
+Run in the build container (needs /root/reference):
+
+    python oracle/make_golden.py
+
+Writes tests/golden/*.npz.  Inputs are seeded; outputs come from the
+reference's own Python code (oracle/ref_harness.py explains the two stubs)
+run in float32 ("as shipped") and in float64 ("truth").  The fixtures travel
+to the GPU box; the reference does not.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+warnings.filterwarnings("ignore")
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_harness as rh  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def _ref64(fn, *tensors, **kw):
+    with rh.float64_mode():
+        return fn(*[t.double() for t in tensors], **kw)
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def make_pairs(R, n, box, seed):
+    """Random pairs + the hard cases the reference's jitters exist for."""
+    D = 4 if box == "bfov" else 5
+    torch.manual_seed(seed)
+    b1 = R.generate_boxes(n, alpha_range=(1, 100), beta_range=(1, 100), dtype="float", box=box)
+    b2 = R.generate_boxes(n, alpha_range=(1, 100), beta_range=(1, 100), dtype="float", box=box)
+    q = n // 8
+    sig = torch.tensor([6, 6, 6, 6, 10.0])[:D]
+    # near-coincident (loss style), three noise scales
+    b2[0:q] = (b1[0:q] + torch.randn(q, D) * sig).clamp(min=1)
+    b2[q:2 * q] = (b1[q:2 * q] + torch.randn(q, D) * sig * 0.1).clamp(min=1)
+    b2[2 * q:2 * q + 64] = (b1[2 * q:2 * q + 64] + torch.randn(64, D) * 1e-3).clamp(min=1)
+    # identical boxes, integer-valued boxes (jitter masks fire), one shared column
+    b2[2 * q + 64:2 * q + 128] = b1[2 * q + 64:2 * q + 128]
+    k = 2 * q + 128
+    bi = R.generate_boxes(128, alpha_range=(1, 100), beta_range=(1, 100), dtype="int", box=box)
+    bj = R.generate_boxes(128, alpha_range=(1, 100), beta_range=(1, 100), dtype="int", box=box)
+    b1[k:k + 128], b2[k:k + 128] = bi, bj
+    k += 128
+    b2[k:k + 64, 2] = b1[k:k + 64, 2]          # same alpha only
+    k += 64
+    b2[k:k + 64, :2] = b1[k:k + 64, :2]        # same centre, different size
+    k += 64
+    # poles, seams, oversize and zero boxes, antipodes
+    special = torch.tensor([
+        [0.0, 0.0, 10, 10, 0], [360.0, 180.0, 10, 10, 0], [0.0, 90.0, 404, 120, 0], [180.0, 90.0, 200, 200, 30],
+        [0.0, 0.0, 0, 0, 0], [359.9999, 0.0001, 1, 1, -90], [10.0, 90.0, 20, 20, 0], [190.0, 90.0, 20, 20, 0],
+        [45.0, 45.0, 30, 60, 45], [45.0, 45.0, 60, 30, -45], [90.0, 1e-3, 50, 50, 10], [270.0, 1e-3, 50, 50, 80],
+    ])[:, :D]
+    m = special.size(0)
+    b1[k:k + m] = special
+    b2[k:k + m] = special.roll(1, dims=0)
+    b1[k + m:k + 2 * m] = special
+    b2[k + m:k + 2 * m] = special
+    return b1.contiguous(), b2.contiguous()
+
+
+def golden_aligned(R):
+    for box in ("bfov", "rbfov"):
+        b1, b2 = make_pairs(R, 4096, box, seed=11 if box == "bfov" else 12)
+        out = dict(b1=_np(b1), b2=_np(b2))
+        for tr in ("efficient", "standard"):
+            fn = getattr(R, "sph2pob_%s_iou" % tr)
+            for mode in ("iou", "iof"):
+                out["%s_%s_f32" % (tr, mode)] = _np(fn(b1, b2, mode=mode, is_aligned=True))
+                out["%s_%s_f64" % (tr, mode)] = _np(_ref64(fn, b1, b2, mode=mode, is_aligned=True))
+            for edge in ("chord", "tangent"):
+                out["%s_%s_f64" % (tr, edge)] = _np(_ref64(fn, b1, b2, is_aligned=True, rbb_edge=edge))
+                out["%s_%s_f32" % (tr, edge)] = _np(fn(b1, b2, is_aligned=True, rbb_edge=edge))
+            out["%s_project_f64" % tr] = _np(_ref64(fn, b1, b2, is_aligned=True, rbb_angle="project"))
+            out["%s_project_f32" % tr] = _np(fn(b1, b2, is_aligned=True, rbb_angle="project"))
+        if box == "bfov":
+            for k in ("sph", "fov"):
+                fn = getattr(R, "%s_iou" % k)
+                out["%s_f32" % k] = _np(fn(b1, b2, is_aligned=True))
+                out["%s_f64" % k] = _np(_ref64(fn, b1, b2, is_aligned=True))
+        # the OBBs after transform + both jitters (first 512 pairs), for unit-level checks
+        for tr, tf in (("efficient", R.eff.sph2pob_efficient), ("standard", R.std.sph2pob_standard)):
+            with rh.float64_mode():
+                j1, j2 = R.jiter_spherical_bboxes(b1[:512].double().clone(), b2[:512].double().clone())
+                o1, o2 = tf(j1, j2, rbb_angle_version="rad")
+                o1, o2 = R.jiter_rotated_bboxes(o1, o2)
+            out["%s_obb1_f64" % tr], out["%s_obb2_f64" % tr] = _np(o1), _np(o2)
+        np.savez_compressed(os.path.join(OUT, "aligned_%s.npz" % box), **out)
+        print("aligned", box, {k: v.shape for k, v in out.items() if k.endswith("iou_f64")})
+
+
+def golden_kat(R):
+    """The 7 hand-picked pairs of tests/test_all_ious.py:243-261 (printed there, frozen here)."""
+    g1 = torch.tensor([[40, 50, 35, 55], [30, 60, 60, 60], [50, -78, 25, 46], [30, 75, 30, 60],
+                       [40, 70, 25, 30], [30, 75, 30, 30], [30, 60, 60, 60]]).float()
+    g2 = torch.tensor([[35, 20, 37, 50], [55, 40, 60, 60], [30, -75, 26, 45], [60, 40, 60, 60],
+                       [60, 85, 30, 30], [60, 55, 40, 50], [60, 60, 60, 60]]).float()
+    b1, b2 = R.box_formator.geo2sph(g1), R.box_formator.geo2sph(g2)
+    out = dict(b1=_np(b1), b2=_np(b2))
+    for name in ("sph2pob_efficient_iou", "sph2pob_standard_iou", "sph_iou", "fov_iou"):
+        out[name] = _np(getattr(R, name)(b1, b2, is_aligned=True))
+    # tests/test_nms.py:6-27 fixture
+    boxes = torch.tensor([[20, 40, 30, 30], [20, 40, 30, 30], [22, 38, 32, 28], [60, 60, 10, 10], [60, 60, 10, 10],
+                          [60, 60, 10, 10], [60, 60, 10, 10], [30, 10, 10, 10], [30, 45, 45, 45], [80, 20, 66, 66]]).float()
+    scores = torch.tensor([0.9, 0.8, 0.7, 0.6, 0.5, 0.85, 0.75, 0.65, 0.4, 0.3])
+    idxs = torch.tensor([1, 1, 1, 1, 1, 2, 2, 2, 3, 3])
+    dets, keep = R.SphNMS("sph2pob_efficient")(boxes, scores, idxs, dict(type="nms", iou_threshold=0.5))
+    out.update(nms_boxes=_np(boxes), nms_scores=_np(scores), nms_idxs=_np(idxs), nms_dets=_np(dets), nms_keep=_np(keep))
+    np.savez_compressed(os.path.join(OUT, "kat.npz"), **out)
+    print("kat", out["sph2pob_efficient_iou"], out["nms_keep"])
+
+
+def anchors_512x1024():
+    """mmdet AnchorGenerator(octave_base_scale=4, scales_per_octave=3, ratios=[.5,1,2],
+    strides=[8..128]) on 512x1024 -> (theta, phi, alpha, beta, 0); SURVEY.md 8(d) config #2
+    (mmdet/core/anchor/anchor_generator.py:98-101,169-192; sphdet/bbox/box_formator.py:85-92)."""
+    H, W = 512, 1024
+    out = []
+    for s in (8, 16, 32, 64, 128):
+        fh, fw = H // s, W // s
+        ys, xs = torch.meshgrid(torch.arange(fh) * s, torch.arange(fw) * s, indexing="ij")
+        base = []
+        for r in (0.5, 1.0, 2.0):
+            for i in range(3):
+                sc = 4 * 2 ** (i / 3)
+                base.append((s * sc / r ** 0.5, s * sc * r ** 0.5))
+        base = torch.tensor(base)                       # [9,2] (w,h): ratio-major like mmdet
+        cx = xs.reshape(-1, 1).float().expand(-1, 9)
+        cy = ys.reshape(-1, 1).float().expand(-1, 9)
+        w = base[:, 0][None, :].expand_as(cx)
+        h = base[:, 1][None, :].expand_as(cx)
+        a = torch.stack([cx / W * 360, cy / H * 180, w / W * 360, h / H * 180, torch.zeros_like(cx)], dim=-1)
+        out.append(a.reshape(-1, 5))
+    return torch.cat(out).float().contiguous()
+
+
+def golden_pairwise(R):
+    out = {}
+    for box in ("bfov", "rbfov"):
+        torch.manual_seed(21)
+        rows = R.generate_boxes(48, alpha_range=(5, 120), beta_range=(5, 120), dtype="float", box=box)
+        cols = R.generate_boxes(160, alpha_range=(5, 120), beta_range=(5, 120), dtype="float", box=box)
+        cols[:16] = rows[:16]                                  # exact duplicates across the two sets
+        cols[16:32] = (rows[16:32] + torch.randn_like(rows[16:32])).clamp(min=1)
+        out["%s_rows" % box], out["%s_cols" % box] = _np(rows), _np(cols)
+        fn = R.sph2pob_efficient_iou
+        out["%s_rc_f32" % box] = _np(fn(rows, cols))
+        out["%s_rc_f64" % box] = _np(_ref64(fn, rows, cols))
+        out["%s_cr_f64" % box] = _np(_ref64(fn, cols, rows))
+        out["%s_cr_f32" % box] = _np(fn(cols, rows))
+    # config #2 orientation through the registry class: GT rows x anchor cols (a strided anchor sample)
+    anc = anchors_512x1024()[::37].contiguous()
+    torch.manual_seed(100)
+    gt = R.generate_boxes(32, alpha_range=(5, 120), beta_range=(5, 120), gamma_range=(-90, 90), dtype="float", box="rbfov")
+    calc = R.SphOverlaps2D("sph2pob_efficient_iou", 5)
+    out["assign_gt"], out["assign_anchors"] = _np(gt), _np(anc)
+    out["assign_f32"] = _np(calc(gt, anc))
+    with rh.float64_mode():
+        out["assign_f64"] = _np(calc(gt.double(), anc.double()))
+    np.savez_compressed(os.path.join(OUT, "pairwise.npz"), **out)
+    print("pairwise", out["assign_f64"].shape, float((out["assign_f64"] > 0).mean()))
+
+
+def golden_loss(R):
+    for box in ("bfov", "rbfov"):
+        D = 4 if box == "bfov" else 5
+        n = 2048
+        torch.manual_seed(31)
+        t = R.generate_boxes(n, alpha_range=(5, 100), beta_range=(5, 100), dtype="float", box=box)
+        p = (t + torch.randn(n, D) * torch.tensor([6, 6, 6, 6, 10.0])[:D]).clamp(min=1)
+        p[:32] = t[:32]                                  # identical rows
+        t[32:64] = 0                                     # negatives carry all-zero targets (sph_retina_head.py:252-265)
+        p[64:96] = (t[64:96] + torch.randn(32, D) * 0.05).clamp(min=1)
+        w1 = (torch.rand(n) > 0.3).float()
+        w2 = torch.rand(n, D)
+        out = dict(pred=_np(p), target=_np(t), w1=_np(w1), w2=_np(w2))
+        for mode in ("iou", "giou", "diou", "ciou"):
+            for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+                L = R.Sph2PobIoULoss(mode=mode, reduction="sum")
+                pp = p.to(dt).clone().requires_grad_(True)
+                tt = t.to(dt).clone().requires_grad_(True)
+                if dt == torch.float64:
+                    with rh.float64_mode():
+                        el = L(pp, tt, reduction_override="none")
+                        el.sum().backward()
+                else:
+                    el = L(pp, tt, reduction_override="none")
+                    el.sum().backward()
+                out["%s_loss_%s" % (mode, tag)] = _np(el)
+                out["%s_gpred_%s" % (mode, tag)] = _np(pp.grad)
+                out["%s_gtarget_%s" % (mode, tag)] = _np(tt.grad)
+        # reduction / weight / avg_factor combinations (float64 scalars)
+        with rh.float64_mode():
+            L = R.Sph2PobIoULoss(mode="iou", loss_weight=2.0)
+            pd, td = p.double(), t.double()
+            out["red_mean"] = _np(L(pd, td))
+            out["red_w1_avg"] = _np(L(pd, td, w1.double(), avg_factor=123.0))
+            out["red_w2"] = _np(L(pd, td, w2.double()))
+            out["red_w1_sum"] = _np(L(pd, td, w1.double(), reduction_override="sum"))
+            out["red_zero_w"] = _np(L(pd, td, torch.zeros(n).double()))
+        np.savez_compressed(os.path.join(OUT, "loss_%s.npz" % box), **out)
+        print("loss", box, float(out["iou_loss_f64"].mean()))
+
+
+def golden_nms(R):
+    out = {}
+    for box in ("bfov", "rbfov"):
+        torch.manual_seed(41)
+        seeds = R.generate_boxes(80, alpha_range=(5, 60), beta_range=(5, 60), dtype="float", box=box)
+        boxes = (seeds.repeat(5, 1) + torch.randn(400, seeds.size(1)) * 2).clamp(min=1)
+        boxes[350:400] = boxes[300:350]                  # exact duplicates
+        scores = torch.rand(400)
+        idxs = torch.randint(0, 6, (400,))
+        for thr in (0.3, 0.5):
+            dets, keep = R.SphNMS("sph2pob_efficient")(boxes, scores, idxs, dict(type="nms", iou_threshold=thr, max_num=150))
+            out["%s_keep_thr%d" % (box, int(thr * 10))] = _np(keep)
+            out["%s_dets_thr%d" % (box, int(thr * 10))] = _np(dets)
+        dets, keep = R.SphNMS("sph2pob_efficient")(boxes, scores, idxs, dict(iou_threshold=0.5), class_agnostic=True)
+        out["%s_keep_agnostic" % box] = _np(keep)
+        # the decision margin: |IoU - thr| of every ordered pair within a label, to know which fixtures are tie-free
+        iou = _ref64(R.sph2pob_efficient_iou, boxes, boxes)
+        out["%s_pair_iou_f64" % box] = _np(iou).astype(np.float32)
+        out["%s_boxes" % box], out["%s_scores" % box], out["%s_idxs" % box] = _np(boxes), _np(scores), _np(idxs)
+    np.savez_compressed(os.path.join(OUT, "nms.npz"), **out)
+    print("nms", {k: v.shape for k, v in out.items() if "keep" in k})
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    R = rh.load_reference()
+    golden_kat(R)
+    golden_aligned(R)
+    golden_pairwise(R)
+    golden_loss(R)
+    golden_nms(R)

@@ -1,0 +1,481 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement (torch, dtype-generic) of the
+reference's spherical-box IoU hot path.  It is the *checker* for the CUDA
+kernels; nothing in the product package imports it.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl
+reference`` legs may call it.
+
+Parity status: PINNED against the reference's own Python code run in this
+container (``oracle/ref_harness.py`` + ``oracle/make_golden.py`` ->
+``tests/golden/*.npz``; ``tests/test_oracle_golden.py`` replays them on any
+box).  The one third-party piece, ``mmcv.ops.box_iou_rotated`` /
+``diff_iou_rotated_2d`` (mmcv-full 1.6.0, not vendored, not installable
+offline), is UNPINNED at the mmcv boundary; it is replaced by a restatement of
+the reference's own vendored ``sphdet/iou/diff_iou_rotated.py`` (which the
+reference's test ``tests/test_sph_iou_loss.py:21-34`` asserts is within 1e-6
+mean of the mmcv kernel).
+
+Run it with float64 inputs for "the truth" and float32 inputs for "the
+reference as shipped" (SURVEY.md section 8c).  Every function cites the
+reference lines it follows (paths relative to the reference root).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+# sph_iou_api.py:223,245  eps = 1e-4 * 1.2345678 ; :232 eps = 1e-3 * 1.2345678
+EPS_SMALL = 1e-4 * 1.2345678
+EPS_ANGLE = 1e-3 * 1.2345678
+# sph2pob_efficient.py:205 / sph2pob_standard.py:214  clamp(-1+1e-7, 1-1e-7)
+COS_LO, COS_HI = -1 + 1e-7, 1 - 1e-7
+
+
+# --------------------------------------------------------------------------- #
+# jitters (sph_iou_api.py:222-260)
+# --------------------------------------------------------------------------- #
+def jitter_spherical(b1: torch.Tensor, b2: torch.Tensor):
+    """sph_iou_api.py:244-260 (jiter_spherical_bboxes), out-of-place.
+
+    Gradient dataflow is the reference's: identity through the masked shift,
+    zero where a clamp is active."""
+    e = EPS_SMALL
+    near = ((b1 - b2).abs() < e).any(dim=1, keepdim=True)
+    b1 = torch.where(near, b1 - 2 * e, b1)
+    b2 = torch.where(near, b2 + e, b2)
+    full, half = 360, 180
+    c1 = [b1[:, 0].clamp(2 * e, full - e)] + [b1[:, k].clamp(2 * e, half - e) for k in (1, 2, 3)]
+    c2 = [b2[:, 0].clamp(e, full - 2 * e)] + [b2[:, k].clamp(e, half - 2 * e) for k in (1, 2, 3)]
+    if b1.size(1) == 5:
+        # :256-258 -- b2's gamma is clamped twice, b1's never (reference quirk, kept)
+        g2 = b2[:, 4].clamp(-full + e, full - 2 * e).clamp(-full + 2 * e, full - e)
+        c1.append(b1[:, 4])
+        c2.append(g2)
+    return torch.stack(c1, dim=1), torch.stack(c2, dim=1)
+
+
+def jitter_rotated(o1: torch.Tensor, o2: torch.Tensor):
+    """sph_iou_api.py:222-242 (jiter_rotated_bboxes), out-of-place."""
+    e = EPS_SMALL
+    cols = [0, 2, 3, 4]
+    near = ((o1[:, cols] - o2[:, cols]).abs() < e).any(dim=1, keepdim=True)
+    add1 = torch.tensor([e, e, 2 * e, 2 * e, e], dtype=o1.dtype)
+    add2 = torch.tensor([2 * e, 2 * e, e, e, 5 * e], dtype=o1.dtype)
+    o1 = torch.where(near, o1 + add1, o1)
+    o2 = torch.where(near, o2 + add2, o2)
+    ea = EPS_ANGLE
+    same_angle = (o1[:, 4] - o2[:, 4]).abs() < ea
+    a1 = torch.where(same_angle, o1[:, 4] + ea, o1[:, 4])
+    a2 = torch.where(same_angle, o2[:, 4] + 2 * ea, o2[:, 4])
+    pi = math.pi
+    w1 = o1[:, 2:4].clamp(min=2 * ea / 10)
+    w2 = o2[:, 2:4].clamp(min=ea / 10)
+    a1 = a1.clamp(-2 * pi + 2 * ea, 2 * pi - ea)
+    a2 = a2.clamp(-2 * pi + ea, 2 * pi - 2 * ea)
+    o1 = torch.cat([o1[:, 0:2], w1, a1[:, None]], dim=1)
+    o2 = torch.cat([o2[:, 0:2], w2, a2[:, None]], dim=1)
+    return o1, o2
+
+
+# --------------------------------------------------------------------------- #
+# small vector helpers shared by both transforms
+# --------------------------------------------------------------------------- #
+def _unit(v):
+    # F.normalize(dim=1): v / max(|v|, 1e-12)
+    return v / v.norm(dim=1, keepdim=True).clamp_min(1e-12)
+
+
+def _angle_between(a, b):
+    """sph2pob_efficient.py:192-208: |acos(clamp(a^ . b^))| in radians."""
+    c = (_unit(a) * _unit(b)).sum(dim=1).clamp(COS_LO, COS_HI)
+    return torch.acos(c).abs()
+
+
+def _turn_sign(a, b, ref):
+    """sph2pob_efficient.py:211-226: +1 where (a x b) . ref < 0 else -1 (zero -> -1)."""
+    crit = (torch.linalg.cross(a, b, dim=1) * ref).sum(dim=1) < 0
+    one = torch.ones((), dtype=a.dtype)
+    return torch.where(crit, one, -one)
+
+
+def _centre_and_tangent(theta, phi):
+    """sph2pob_efficient.py:111-162: unit centre c and the southward tangent d."""
+    st, ct, sp, cp = torch.sin(theta), torch.cos(theta), torch.sin(phi), torch.cos(phi)
+    c = torch.stack([sp * ct, sp * st, cp], dim=1)
+    d = torch.stack([cp * ct, cp * st, -sp], dim=1)
+    return c, d
+
+
+def _edge(fov, mode):
+    """sph2pob_efficient.py:100-108."""
+    if mode == "arc":
+        return fov
+    if mode == "tangent":
+        return 2 * torch.tan(fov / 2)
+    if mode == "chord":
+        return 2 * torch.sin(fov / 2)
+    raise NotImplementedError(mode)
+
+
+# --------------------------------------------------------------------------- #
+# Sph2Pob-efficient (sph2pob_efficient.py:9-73), output angles in radians
+# --------------------------------------------------------------------------- #
+def sph2pob_efficient(b1, b2, rbb_edge="arc", rbb_angle="equator"):
+    assert rbb_edge in ("arc", "chord", "tangent") and rbb_angle in ("equator", "project")
+    r1, r2 = torch.deg2rad(b1), torch.deg2rad(b2)
+    cg, dg = _centre_and_tangent(r1[:, 0], r1[:, 1])
+    cp, dp = _centre_and_tangent(r2[:, 0], r2[:, 1])
+    z = torch.linalg.cross(cg, cp, dim=1)          # :49
+    ref = (cg + cp) / 2                            # :50
+    arc = _angle_between(cg, cp)                   # :51
+
+    def internal(d):                               # :81-97
+        if rbb_angle == "project":
+            d = torch.cat([torch.zeros_like(d[:, :1]), d[:, 1:]], dim=1)
+        return _angle_between(d, z) * _turn_sign(z, d, ref)
+
+    ag, ap = internal(dg), internal(dp)
+    if b1.size(1) == 5 and b2.size(1) == 5:        # :55-57
+        ag = ag - r1[:, 4]
+        ap = ap - r2[:, 4]
+    zero = torch.zeros_like(arc)
+    o1 = torch.stack([zero, zero, _edge(r1[:, 2], rbb_edge), _edge(r1[:, 3], rbb_edge), ag], dim=1)
+    o2 = torch.stack([arc, zero, _edge(r2[:, 2], rbb_edge), _edge(r2[:, 3], rbb_edge), ap], dim=1)
+    return o1, o2
+
+
+# --------------------------------------------------------------------------- #
+# Sph2Pob-standard (sph2pob_standard.py:8-80), output angles in radians
+# --------------------------------------------------------------------------- #
+def _frame_from_angles(theta, phi):
+    """sph2pob_standard.py:238-261: rows (look, down, right)."""
+    st, ct, sp, cp = torch.sin(theta), torch.cos(theta), torch.sin(phi), torch.cos(phi)
+    zero = torch.zeros_like(theta)
+    look = torch.stack([sp * ct, sp * st, cp], dim=1)
+    down = torch.stack([cp * ct, cp * st, -sp], dim=1)
+    right = torch.stack([st, -ct, zero], dim=1)
+    return torch.stack([look, down, right], dim=1)   # [P,3,3], row-major
+
+
+def _pair_frame(cg, cp, theta_mid, phi_mid):
+    """sph2pob_standard.py:264-297 (compute_rotate_matrix_auto)."""
+    look = _unit(cg + cp)
+    right = _unit(cp - cg)
+    up = torch.linalg.cross(look, right, dim=1)
+    R = torch.stack([look, right, up], dim=1)
+    normal = ((cg - cp).abs().sum(dim=1) > 1e-8)[:, None, None]
+    return torch.where(normal, R, _frame_from_angles(theta_mid, phi_mid))
+
+
+def _rotate_tangent_by_gamma(theta, phi, gamma, d):
+    """sph2pob_standard.py:47-54,300-314: T^T Rx(-gamma) T applied to d."""
+    T = _frame_from_angles(theta, phi)
+    g = -gamma
+    sg, cg_ = torch.sin(g), torch.cos(g)
+    one, zero = torch.ones_like(g), torch.zeros_like(g)
+    Rx = torch.stack([torch.stack([one, zero, zero], dim=1),
+                      torch.stack([zero, cg_, -sg], dim=1),
+                      torch.stack([zero, sg, cg_], dim=1)], dim=1)
+    M = T.transpose(1, 2) @ (Rx @ T)
+    return (M @ d[:, :, None]).squeeze(-1)
+
+
+def _angle_between_deg(a, b):
+    # sph2pob_standard.py:202-217: same clamp, but returned in degrees
+    c = (_unit(a) * _unit(b)).sum(dim=1).clamp(COS_LO, COS_HI)
+    return (torch.acos(c) / torch.pi * 180).abs()
+
+
+def sph2pob_standard(b1, b2, rbb_edge="arc", rbb_angle="equator"):
+    r1, r2 = torch.deg2rad(b1), torch.deg2rad(b2)
+    theta_mid, phi_mid = (r1[:, 0] + r2[:, 0]) / 2, (r1[:, 1] + r2[:, 1]) / 2
+    cg, dg = _centre_and_tangent(r1[:, 0], r1[:, 1])
+    cp, dp = _centre_and_tangent(r2[:, 0], r2[:, 1])
+    R = _pair_frame(cg, cp, theta_mid, phi_mid)
+    if b1.size(1) == 5:                               # :47 (tests b1 only, b2 assumed alike)
+        dg = _rotate_tangent_by_gamma(r1[:, 0], r1[:, 1], r1[:, 4], dg)
+        dp = _rotate_tangent_by_gamma(r2[:, 0], r2[:, 1], r2[:, 4], dp)
+    rot = lambda v: (R @ v[:, :, None]).squeeze(-1)
+    cg, cp, dg, dp = rot(cg), rot(cp), rot(dg), rot(dp)
+    ex = torch.tensor([1.0, 0.0, 0.0], dtype=b1.dtype).expand_as(cg)
+    ez = torch.tensor([0.0, 0.0, 1.0], dtype=b1.dtype).expand_as(cg)
+
+    def internal(d):                                  # :88-108, degrees
+        if rbb_angle == "project":
+            d = torch.cat([torch.zeros_like(d[:, :1]), d[:, 1:]], dim=1)
+        return _angle_between_deg(d, ez) * _turn_sign(ez, d, ex)
+
+    def to_sph(c):                                    # :175-199, degrees then deg2rad
+        phi = _angle_between_deg(c, ez)
+        cxy = torch.cat([c[:, :2], torch.zeros_like(c[:, :1])], dim=1)
+        theta = _angle_between_deg(cxy, ex) * _turn_sign(ex, cxy, -ez)
+        return torch.deg2rad(theta), torch.deg2rad(phi)
+
+    ag, ap = torch.deg2rad(internal(dg)), torch.deg2rad(internal(dp))   # :342-364 ('rad')
+    tg, pg = to_sph(cg)
+    tp, pp = to_sph(cp)
+    o1 = torch.stack([tg, pg, _edge(r1[:, 2], rbb_edge), _edge(r1[:, 3], rbb_edge), ag], dim=1)
+    o2 = torch.stack([tp, pp, _edge(r2[:, 2], rbb_edge), _edge(r2[:, 3], rbb_edge), ap], dim=1)
+    return o1, o2
+
+
+# --------------------------------------------------------------------------- #
+# rotated IoU, restating sphdet/iou/diff_iou_rotated.py:20-343
+# --------------------------------------------------------------------------- #
+_TINY = 1e-8   # diff_iou_rotated.py:17 EPSILON
+
+
+def obb_corners(o):
+    """diff_iou_rotated.py:297-322: corners (+,+),(-,+),(-,-),(+,-) rotated CCW by the angle."""
+    sx = torch.tensor([0.5, -0.5, -0.5, 0.5], dtype=o.dtype)
+    sy = torch.tensor([0.5, 0.5, -0.5, -0.5], dtype=o.dtype)
+    lx, ly = sx * o[:, 2:3], sy * o[:, 3:4]
+    s, c = torch.sin(o[:, 4:5]), torch.cos(o[:, 4:5])
+    return torch.stack([lx * c - ly * s + o[:, 0:1], lx * s + ly * c + o[:, 1:2]], dim=-1)  # [P,4,2]
+
+
+def _edge_crossings(q1, q2):
+    """diff_iou_rotated.py:20-60: 4x4 segment crossings, strict interior on both."""
+    a0, a1 = q1[:, :, None, :], q1.roll(-1, dims=1)[:, :, None, :]
+    b0, b1 = q2[:, None, :, :], q2.roll(-1, dims=1)[:, None, :, :]
+    da, db = a0 - a1, b0 - b1
+    den = da[..., 0] * db[..., 1] - da[..., 1] * db[..., 0]
+    ab = a0 - b0
+    tn = ab[..., 0] * db[..., 1] - ab[..., 1] * db[..., 0]
+    un = da[..., 0] * ab[..., 1] - da[..., 1] * ab[..., 0]
+    par = den == 0
+    t = torch.where(par, torch.full_like(den, -1.0), tn / den)
+    u = torch.where(par, torch.full_like(den, -1.0), -un / den)
+    ok = (t > 0) & (t < 1) & (u > 0) & (u < 1)
+    ts = tn / (den + _TINY)
+    pts = a0 + ts[..., None] * (a1 - a0)
+    return pts * ok[..., None].to(pts.dtype), ok
+
+
+def _corners_inside(q, box):
+    """diff_iou_rotated.py:63-89: closed test via projections on two box edges."""
+    a, b, d = box[:, 0:1], box[:, 1:2], box[:, 3:4]
+    ab, ad, am = b - a, d - a, q - a
+    pab, pad = (ab * am).sum(-1), (ad * am).sum(-1)
+    return (pab >= 0) & (pab <= (ab * ab).sum(-1)) & (pad >= 0) & (pad <= (ad * ad).sum(-1))
+
+
+def rotated_intersection_area(q1, q2):
+    """diff_iou_rotated.py:278-295 on corner tensors [P,4,2]."""
+    P = q1.size(0)
+    pts, ok = _edge_crossings(q1, q2)
+    in12, in21 = _corners_inside(q1, q2), _corners_inside(q2, q1)
+    with torch.no_grad():
+        # :196-223 coincident corners: keep box-1's copy only
+        same = (q1[:, :, None, :] == q2[:, None, :, :]).all(-1)   # [P,4(i),4(j)]
+        in12 = in12 | same.any(dim=2)
+        in21 = in21 & ~same.any(dim=1)
+    verts = torch.cat([q1, q2, pts.reshape(P, 16, 2)], dim=1)          # [P,24,2]
+    mask = torch.cat([in12, in21, ok.reshape(P, 16)], dim=1)            # [P,24]
+    with torch.no_grad():
+        n = mask.sum(dim=1)
+        mean = (verts * mask[..., None].to(verts.dtype)).sum(dim=1, keepdim=True) / n[:, None, None]
+        rel = verts - mean
+        x = torch.where(mask, rel[..., 0], torch.full_like(rel[..., 0], -1e6))
+        y = torch.where(mask, rel[..., 1], torch.full_like(rel[..., 1], 1e-6))
+        order = torch.argsort(torch.atan2(y, x), dim=-1)
+        order.scatter_(1, n[:, None].clamp(max=23), order[:, :1].clone())   # close the loop
+        order = order[:, :9]
+        keep = (torch.arange(9)[None, :] < (n[:, None] + 1)) & (n[:, None] >= 3)
+    poly = torch.gather(verts, 1, order[..., None].expand(-1, -1, 2)) * keep[..., None].to(verts.dtype)
+    cross = poly[:, :-1, 0] * poly[:, 1:, 1] - poly[:, :-1, 1] * poly[:, 1:, 0]
+    return cross.sum(dim=1).abs() / 2
+
+
+def rotated_iou(o1, o2, mode="iou"):
+    """diff_iou_rotated.py:325-343 (+ 'iof' as mmcv.ops.box_iou_rotated defines it)."""
+    inter = rotated_intersection_area(obb_corners(o1), obb_corners(o2))
+    a1, a2 = o1[:, 2] * o1[:, 3], o2[:, 2] * o2[:, 3]
+    return inter / (a1 + a2 - inter) if mode == "iou" else inter / a1
+
+
+# --------------------------------------------------------------------------- #
+# public IoU functions (sph_iou_api.py:48-177)
+# --------------------------------------------------------------------------- #
+def _expand(b1, b2, is_aligned):
+    """sph_iou_api.py:59-64: pair p = i*C + j = (b1[i], b2[j])."""
+    if is_aligned:
+        assert b1.size(0) == b2.size(0)
+        return b1, b2
+    R, C = b1.size(0), b2.size(0)
+    return b1.repeat_interleave(C, dim=0), b2.repeat(R, 1)
+
+
+def sph2pob_iou(b1, b2, transform="efficient", mode="iou", is_aligned=False,
+                rbb_edge="arc", rbb_angle="equator", chunk=1 << 18):
+    """sph_iou_api.py:48-98 (_sph2pob_iou_auxiliary with the efficient/standard transform)."""
+    assert mode in ("iou", "iof")
+    R, C = b1.size(0), b2.size(0)
+    if R * C == 0:
+        return b1.new_zeros((R, 1)) if is_aligned else b1.new_zeros((R, C))
+    fn = sph2pob_efficient if transform == "efficient" else sph2pob_standard
+    e1, e2 = _expand(b1, b2, is_aligned)
+    outs = []
+    for s in range(0, e1.size(0), chunk):
+        j1, j2 = jitter_spherical(e1[s:s + chunk], e2[s:s + chunk])
+        o1, o2 = fn(j1, j2, rbb_edge=rbb_edge, rbb_angle=rbb_angle)
+        o1, o2 = jitter_rotated(o1, o2)
+        outs.append(rotated_iou(o1, o2, mode).clamp(0, 1))
+    out = torch.cat(outs)
+    return out if is_aligned else out.view(R, C)
+
+
+def _wrap_far_apart(b1, b2):
+    """approximate_ious.py:60-81: where |dtheta| > 180 shift both thetas by 180 mod 360."""
+    far = (b1[:, 0] - b2[:, 0]).abs() > 180
+    t1 = torch.where(far, (b1[:, 0] + 180) % 360, b1[:, 0])
+    t2 = torch.where(far, (b2[:, 0] + 180) % 360, b2[:, 0])
+    return torch.cat([t1[:, None], b1[:, 1:]], 1), torch.cat([t2[:, None], b2[:, 1:]], 1)
+
+
+def _to_convention(b):
+    """approximate_ious.py:83-100: radians with theta-pi, pi/2-phi."""
+    r = torch.deg2rad(b)
+    return r[:, 0] - torch.pi, torch.pi / 2 - r[:, 1], r[:, 2], r[:, 3]
+
+
+def _approx_iou(b1, b2, kind):
+    """approximate_ious.py:3-55 (sph_iou_aligned / fov_iou_aligned)."""
+    b1, b2 = _wrap_far_apart(b1, b2)
+    tg, pg, ag, bg = _to_convention(b1)
+    tp, pp, ap, bp = _to_convention(b2)
+    if kind == "sph":
+        lo = torch.max(tg - ag / 2, tp - ap / 2)
+        hi = torch.min(tg + ag / 2, tp + ap / 2)
+    else:
+        delta = (tp - tg) * torch.cos((pg + pp) / 2)
+        lo = torch.max(-ag / 2, delta - ap / 2)
+        hi = torch.min(ag / 2, delta + ap / 2)
+    plo = torch.max(pg - bg / 2, pp - bp / 2)
+    phi_ = torch.min(pg + bg / 2, pp + bp / 2)
+    inter = (hi - lo).clamp(min=0) * (phi_ - plo).clamp(min=0)
+    return inter / (ag * bg + ap * bp - inter + 1e-8)
+
+
+def approx_iou(b1, b2, kind="sph", is_aligned=False):
+    """sph_iou_api.py:130-177 (sph_iou / fov_iou wrappers), BFoV only."""
+    assert kind in ("sph", "fov")
+    R, C = b1.size(0), b2.size(0)
+    if R * C == 0:
+        return b1.new_zeros((R, 1)) if is_aligned else b1.new_zeros((R, C))
+    e1, e2 = _expand(b1, b2, is_aligned)
+    j1, j2 = jitter_spherical(e1, e2)
+    out = _approx_iou(j1, j2, kind).clamp(0, 1)
+    return out if is_aligned else out.view(R, C)
+
+
+# --------------------------------------------------------------------------- #
+# Sph2Pob loss (sph2pob_transform.py:24-35 + sph2pob_iou_loss.py:25-58,104-196)
+# --------------------------------------------------------------------------- #
+def obb_to_hbb(o):
+    """sphdet/bbox/box_formator.py obb2hbb_xyxy: enclosing axis-aligned box of an OBB."""
+    c, s = torch.cos(o[:, 4]).abs(), torch.sin(o[:, 4]).abs()
+    w = o[:, 2] * c + o[:, 3] * s
+    h = o[:, 2] * s + o[:, 3] * c
+    return torch.stack([o[:, 0] - w / 2, o[:, 1] - h / 2, o[:, 0] + w / 2, o[:, 1] + h / 2], dim=1)
+
+
+def loss_obbs(pred, target):
+    """sph2pob_transform.py:26-30: jitter -> standard transform -> jitter."""
+    j1, j2 = jitter_spherical(pred, target)
+    o1, o2 = sph2pob_standard(j1, j2)
+    return jitter_rotated(o1, o2)
+
+
+def sph2pob_iou_loss_elementwise(pred, target, mode="iou", eps=1e-6):
+    """sph2pob_iou_loss.py:104-196 on top of the Sph2Pob transform; per-row loss."""
+    o1, o2 = loss_obbs(pred, target)
+    ious = rotated_iou(o1, o2).clamp(0, 1)
+    if mode == "iou":
+        return 1 - ious
+    h1, h2 = obb_to_hbb(o1), obb_to_hbb(o2)
+    enc = (torch.max(h1[:, 2:], h2[:, 2:]) - torch.min(h1[:, :2], h2[:, :2])).clamp(min=0)
+    if mode == "giou":
+        iw = (torch.min(h1[:, 2:], h2[:, 2:]) - torch.max(h1[:, :2], h2[:, :2])).clamp(min=0)
+        a_enc = enc[:, 0] * enc[:, 1]
+        union = o1[:, 2] * o1[:, 3] + o2[:, 2] * o2[:, 3] - iw[:, 0] * iw[:, 1]
+        return 1 - (ious - ((a_enc - union) / (a_enc + eps)).clamp(0, 1))
+    c2 = enc[:, 0] ** 2 + enc[:, 1] ** 2 + eps
+    rho2 = (o2[:, 0] - o1[:, 0]) ** 2 + (o2[:, 1] - o1[:, 1]) ** 2
+    if mode == "diou":
+        return 1 - (ious - (rho2 / c2).clamp(0, 1))
+    v = 4 / math.pi ** 2 * (torch.atan(o2[:, 2] / (o2[:, 3] + eps)) - torch.atan(o1[:, 2] / (o1[:, 3] + eps))) ** 2
+    with torch.no_grad():
+        alpha = (ious > 0.5).to(v.dtype) * v / (1 - ious + v + eps)
+    if mode == "ciou":
+        return 1 - (ious - ((rho2 / c2).clamp(0, 1) + alpha * v))
+    raise NotImplementedError(mode)
+
+
+def sph2pob_iou_loss(pred, target, weight=None, avg_factor=None, mode="iou", eps=1e-6,
+                     reduction="mean", loss_weight=1.0):
+    """Sph2PobIoULoss.forward: sph2pob_transform.py:24-35, sph2pob_iou_loss.py:25-58,
+    mmdet/models/losses/utils.py weight_reduce_loss."""
+    if weight is not None and weight.dim() > 1 and target.size(-1) == 4:
+        weight = torch.cat([weight, weight.mean(-1, keepdim=True)], dim=-1)
+    if weight is not None and not torch.any(weight > 0):
+        o1, _ = loss_obbs(pred, target)
+        w = weight.unsqueeze(1) if o1.dim() == weight.dim() + 1 else weight
+        return (o1 * w).sum()
+    if weight is not None and weight.dim() > 1:
+        weight = weight.mean(-1)
+    loss = sph2pob_iou_loss_elementwise(pred, target, mode=mode, eps=eps)
+    if weight is not None:
+        loss = loss * weight
+    if avg_factor is None:
+        loss = loss.mean() if reduction == "mean" else loss.sum() if reduction == "sum" else loss
+    elif reduction == "mean":
+        loss = loss.sum() / (avg_factor + torch.finfo(torch.float32).eps)
+    elif reduction != "none":
+        raise ValueError('avg_factor can not be used with reduction="sum"')
+    return loss_weight * loss
+
+
+# --------------------------------------------------------------------------- #
+# spherical NMS (sphdet/bbox/nms/sph_nms.py:22-74)
+# --------------------------------------------------------------------------- #
+def nms_single(boxes, scores, thr, iou_fn):
+    """sph_nms.py:62-74: greedy; pivot is bboxes1, the survivors are bboxes2; suppress iff IoU > thr."""
+    order = torch.argsort(scores, descending=True)
+    keep = []
+    while order.numel() > 0:
+        keep.append(int(order[0]))
+        if order.numel() == 1:
+            break
+        iou = iou_fn(boxes[order[0]][None, :], boxes[order[1:]]).reshape(-1)
+        order = order[1:][iou <= thr]
+    return torch.tensor(keep, dtype=torch.long)
+
+
+def nms_batched(boxes, scores, idxs, iou_threshold=0.5, max_num=None, class_agnostic=False, iou_fn=None):
+    """sph_nms.py:22-60: per label greedy NMS, union, sort by score, truncate, append score column."""
+    if iou_fn is None:
+        iou_fn = lambda a, b: sph2pob_iou(a, b, "efficient")
+    max_num = boxes.size(0) if max_num is None else min(max_num, boxes.size(0))
+    kept = torch.zeros(boxes.size(0), dtype=torch.bool)
+    labels = torch.zeros_like(idxs) if class_agnostic else idxs
+    for lab in torch.unique(labels):
+        sel = (labels == lab).nonzero().view(-1)
+        kept[sel[nms_single(boxes[sel], scores[sel], iou_threshold, iou_fn)]] = True
+    keep = kept.nonzero().view(-1)
+    s, o = scores[keep].sort(descending=True)
+    keep = keep[o][:max_num]
+    return torch.cat([boxes[keep], s[:max_num, None]], dim=-1), keep
+
+
+# --------------------------------------------------------------------------- #
+# synthetic inputs (tests/utils/generate_data.py:10-42, dtype='float' branch)
+# --------------------------------------------------------------------------- #
+def generate_boxes(num, theta_range=(0, 360), phi_range=(0, 180), alpha_range=(1, 180),
+                   beta_range=(1, 180), gamma_range=(-90, 90), box="bfov", seed=None):
+    if seed is not None:
+        torch.manual_seed(seed)
+    u = torch.rand((num, 5))
+    rng = [theta_range, phi_range, alpha_range, beta_range, gamma_range]
+    cols = [u[:, k] * (r[1] - r[0]) + r[0] for k, r in enumerate(rng)]
+    return torch.stack(cols[:4] if box == "bfov" else cols, dim=1)
