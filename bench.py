@@ -1,0 +1,475 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the spherical-box IoU hot path (BASELINE.json metric: Sph2Pob-IoU pairs/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload assign|sweep] [--impl reference]
+
+Default workload = BASELINE.json configs[1] ("assign"): RetinaNet label assignment, pairwise
+Sph2Pob-efficient IoU of 32 RBFoV GT x 98,208 FPN anchors for each of 16 images through the
+registry calculator ``SphOverlaps2D('sph2pob_efficient_iou', 5)`` (one "step" = the 16 matrices).
+N>1 (torchrun, one rank per GPU): every rank processes its own 16 images -- weak scaling, no data-path
+collective (images are independent).  ``--workload sweep`` is configs[4]: the
+1,048,576 x 1,024 RBFoV sweep, anchors row-sharded over the ranks, fused max/argmax, NCCL gather of
+the packed per-anchor / per-GT results inside the timed region (strong scaling).
+
+One JSON line on stdout (rank 0).  ``--impl reference`` times the reference's CPU implementation of
+the same call (its PyTorch-eager algorithm as restated in oracle/sph_oracle.py; the reference is
+pure Python that needs mmcv and cannot be installed offline -- DESIGN.md) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "sph2pob_iou_pairs_per_s"
+UNIT = "pairs/s"
+IMAGES, GTS, FLOP_PER_PAIR = 16, 32, 512.0      # W = 512 flop per Sph2Pob-IoU pair
+HBM_FALLBACK_GBS = 6650.0                       # B200_PROFILING.md fallback if MEASURED_PEAKS.json is absent
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# helpers
+# ---------------------------------------------------------------------------------------------------
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        try:
+            return json.load(open(path)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": HBM_FALLBACK_GBS, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index, self.proc, self.path = gpu_index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.path)
+        # the samples under load are the upper half (idle samples before/after pull the clock down)
+        load = sorted(sm)[len(sm) // 2:] if sm else []
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+class L2Flusher:
+    def __init__(self, torch, dev):
+        self.buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)    # 2x the 126 MB L2
+
+    def __call__(self):
+        self.buf.zero_()
+
+
+def time_steps(torch, step, steps, warmup, flush, barrier):
+    """W untimed + K timed steps; each timed step has its own CUDA-event pair on the launching stream, the L2
+    flush between steps sits outside the timed spans.  Returns per-step ms."""
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    barrier()
+    evs = []
+    for _ in range(steps):
+        flush()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step()
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    barrier()
+    return [a.elapsed_time(b) for a, b in evs]
+
+
+def quick(torch, fn, iters=10, warmup=3, flush=None):
+    ms = time_steps(torch, fn, iters, warmup, flush or (lambda: None), lambda: None)
+    return statistics.median(ms)
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU side: the oracle as the reported baseline / the reference arm
+# ---------------------------------------------------------------------------------------------------
+def cpu_port_assign(torch, gts, anchors, images, repeats=1):
+    """The reference's CPU algorithm (PyTorch eager, fp32, all host threads) on `images` images."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import sph_oracle as O
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        for i in range(images):
+            O.sph2pob_iou(gts[i], anchors, "efficient")
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return images * gts.size(1) * anchors.size(0) / best, best
+
+
+def cpu_c_port_assign(gts, anchors):
+    """Second CPU line: float64 C restatement with OpenMP (oracle/sph_oracle.c)."""
+    import ctypes
+    import numpy as np
+    try:
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+        lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_build", "libsph_oracle.so"))
+    except Exception as e:  # pragma: no cover
+        return None
+    fp, dp = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)
+    rows, cols = np.ascontiguousarray(gts[0].numpy()), np.ascontiguousarray(anchors.numpy())
+    out = np.empty((rows.shape[0], cols.shape[0]))
+    best = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        lib.sph_oracle_iou_pairwise(0, rows.ctypes.data_as(fp), ctypes.c_long(rows.shape[0]), cols.ctypes.data_as(fp),
+                                    ctypes.c_long(cols.shape[0]), rows.shape[1], 0, 0, out.ctypes.data_as(dp))
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return out.size / best
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    import torch
+    from sph_retina_b200 import synthetic as S
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    gts, anchors = S.assignment_batch(IMAGES, GTS)
+    # bounded sample per step: one image's matrix; anchors are strided down if K+W would take too long
+    total_steps = args.steps + args.warmup
+    stride = max(1, (total_steps + 29) // 30)
+    anc = anchors[::stride].contiguous()
+    pairs_per_step = GTS * anc.size(0)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import sph_oracle as O
+    for i in range(args.warmup):
+        O.sph2pob_iou(gts[i % IMAGES], anc, "efficient")
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        O.sph2pob_iou(gts[i % IMAGES], anc, "efficient")
+    dt = time.perf_counter() - t0
+    value = pairs_per_step * args.steps / dt
+    sample = "1 image per step: %d GT x %d anchors (anchor stride %d) = %d pairs" % (GTS, anc.size(0), stride, pairs_per_step)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "assign: pairwise Sph2Pob-efficient IoU, 32 RBFoV GT x 98208 anchors (512x1024, 9/loc), batch 16",
+                   "api": "sph2pob_efficient_iou (CPU, PyTorch eager)", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "what": "oracle/sph_oracle.py: the reference's PyTorch-eager algorithm, fp32, torch threads = cores"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU side
+# ---------------------------------------------------------------------------------------------------
+def fp32_peak(torch, native, dev):
+    sm, _, _ = native.device_info()
+    blocks, iters = sm * 16, 1 << 14
+    native.probe_fp32(blocks, 256, dev)
+    torch.cuda.synchronize()
+    best = 0.0
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        flop = native.probe_fp32(blocks, iters, dev)
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, flop / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best
+
+
+def other_configs(torch, native, dev, flush):
+    """The remaining BASELINE.json configurations, timed briefly on one GPU (kernel time, inputs resident)."""
+    from sph_retina_b200 import synthetic as S
+    from sph_retina_b200.sphdet.bbox.nms import sph_batched_nms_images
+    from sph_retina_b200.sphdet.iou import fov_iou, sph2pob_efficient_iou, sph_iou, sph_max_overlaps
+    from sph_retina_b200.sphdet.losses import Sph2PobIoULoss
+    out = {}
+    n = 1_000_000
+    for box in ("bfov", "rbfov"):
+        b1 = S.generate_boxes(n, alpha_range=(1, 100), beta_range=(1, 100), box=box, seed=0).to(dev)
+        b2 = S.generate_boxes(n, alpha_range=(1, 100), beta_range=(1, 100), box=box, seed=1).to(dev)
+        ms = quick(torch, lambda: sph2pob_efficient_iou(b1, b2, is_aligned=True), flush=flush)
+        out["aligned_1M_%s" % box] = {"ms": ms, "pairs_per_s": n / ms * 1e3}
+        if box == "bfov":
+            for name, fn in (("sph_iou", sph_iou), ("fov_iou", fov_iou)):
+                ms = quick(torch, lambda: fn(b1, b2, is_aligned=True), flush=flush)
+                out["aligned_1M_%s" % name] = {"ms": ms, "pairs_per_s": n / ms * 1e3, "hbm_gbs": n * 36 / ms / 1e6}
+    native.set_dense(True)
+    ms = quick(torch, lambda: sph2pob_efficient_iou(b1, b2, is_aligned=True), flush=flush)
+    native.set_dense(False)
+    out["aligned_1M_rbfov_dense"] = {"ms": ms, "pairs_per_s": n / ms * 1e3}
+    pred, target = S.loss_pairs(200_000)
+    pred, target = pred.to(dev), target.to(dev)
+    L = Sph2PobIoULoss(mode="iou", reduction="sum")
+
+    def fwd_bwd():
+        p = pred.detach().requires_grad_(True)
+        L(p, target).backward()
+    with torch.no_grad():
+        ms_f = quick(torch, lambda: L(pred, target), flush=flush)
+    ms_fb = quick(torch, fwd_bwd, flush=flush)
+    out["loss_200k_rbfov"] = {"fwd_ms": ms_f, "fwd_bwd_ms": ms_fb, "pairs_per_s_fwd_bwd": 200_000 / ms_fb * 1e3}
+    boxes, scores, labels, image_ids = (t.to(dev) for t in S.nms_batch(64, 1000, 80))
+    ms = quick(torch, lambda: sph_batched_nms_images(boxes, scores, labels, image_ids, 0.5), iters=5, flush=flush)
+    out["nms_64img_1000box_80cls"] = {"ms": ms, "images_per_s": 64 / ms * 1e3}
+    ms = quick(torch, lambda: sph_batched_nms_images(boxes, scores, torch.zeros_like(labels), image_ids, 0.5), iters=5, flush=flush)
+    out["nms_64img_1000box_class_agnostic"] = {"ms": ms, "images_per_s": 64 / ms * 1e3}
+    A = S.generate_boxes(1 << 20, alpha_range=(1, 100), beta_range=(1, 100), box="rbfov", seed=0).to(dev)
+    G = S.generate_boxes(1024, alpha_range=(1, 100), beta_range=(1, 100), box="rbfov", seed=1).to(dev)
+    ms = quick(torch, lambda: sph_max_overlaps(A, G), iters=3, warmup=1, flush=flush)
+    out["sweep_1Mx1024_fused_max"] = {"ms": ms, "pairs_per_s": (1 << 30) / ms * 1e3}
+    return out
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank, local_rank, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device. The product path is CUDA-only (no CPU fallback); "
+                         "use --impl reference for the CPU arm.")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from sph_retina_b200 import _native as native
+    from sph_retina_b200 import synthetic as S
+    from sph_retina_b200.sphdet.iou import SphOverlaps2D, sph_max_overlaps
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    flush = L2Flusher(torch, dev)
+    peaks, peaks_src = measured_peaks()
+    gts_h, anchors_h = S.assignment_batch(IMAGES, GTS)
+    if world > 1:       # every rank gets its own images (weak scaling)
+        gts_h = torch.stack([S.generate_boxes(GTS, alpha_range=(5, 120), beta_range=(5, 120), box="rbfov",
+                                              seed=100 + rank * IMAGES + i) for i in range(IMAGES)])
+    result = {}
+    if args.workload == "assign":
+        gts, anchors = gts_h.to(dev), anchors_h.to(dev)
+        calc = SphOverlaps2D('sph2pob_efficient_iou', 5)
+        pairs_per_step = IMAGES * GTS * anchors.size(0)
+
+        def step():
+            return [calc(gts[i], anchors) for i in range(IMAGES)]
+        launches_per_step = IMAGES
+        scaling = "weak"
+        total_pairs_per_step = pairs_per_step * world
+        workload = ("assign: pairwise Sph2Pob-efficient IoU, 32 RBFoV GT x 98208 anchors (512x1024, 9/loc), batch 16 "
+                    "per GPU, full [32 x 98208] fp32 matrix written per image")
+    else:
+        from sph_retina_b200.sharded import shard_bounds, sharded_max_overlaps
+        n_a = 1 << 20
+        A = S.generate_boxes(n_a, alpha_range=(1, 100), beta_range=(1, 100), box="rbfov", seed=0)
+        G = S.generate_boxes(1024, alpha_range=(1, 100), beta_range=(1, 100), box="rbfov", seed=1).to(dev)
+        lo, hi = shard_bounds(n_a, world, rank)
+        A_loc = A[lo:hi].contiguous().to(dev)
+        pairs_per_step = (hi - lo) * 1024
+        total_pairs_per_step = n_a * 1024
+
+        def step():
+            return sharded_max_overlaps(A_loc, G, n_a, lo, anchors_are='bboxes1')
+        launches_per_step = 5
+        scaling = "strong"
+        workload = ("sweep: 1,048,576 x 1,024 RBFoV Sph2Pob-efficient IoU, anchors row-sharded over the GPUs, fused "
+                    "per-anchor and per-GT max/argmax, NCCL all_gather + all_reduce(MAX) of packed keys in the timed region")
+
+    # ---- timed region (device time, per-step events, L2 flushed between steps) --------------------
+    sampler = ClockSampler(local_rank)
+    l0 = native.launches
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    l0 = native.launches
+    sampler.start()
+    ms = time_steps(torch, step, args.steps, 0, flush, barrier)
+    clocks = sampler.stop()
+    gpu_launches = native.launches - l0
+    total_ms = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    ms_per_step = total_ms / args.steps
+    value = total_pairs_per_step / (ms_per_step * 1e-3)
+
+    if rank == 0:
+        kernel_ms = statistics.mean(ms) / launches_per_step if args.workload == "assign" else statistics.mean(ms)
+        if args.workload == "assign":
+            bytes_per_launch = GTS * anchors.size(0) * 4 + (GTS + anchors.size(0)) * 5 * 4
+            pairs_per_launch = GTS * anchors.size(0)
+        else:
+            bytes_per_launch = (A_loc.size(0) + 1024) * (5 * 4 + 8)
+            pairs_per_launch = A_loc.size(0) * 1024
+        hbm_achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")     # dram bytes/launch from the committed ncu capture
+        if os.path.isfile(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(args.workload)
+            except Exception:
+                traffic = None
+        roofline = {"bound": "hbm", "achieved": hbm_achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": hbm_achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peaks_src,
+                    "kernel": "k_iou_pairwise", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": bytes_per_launch,
+                    "note": "HBM is NOT what bounds this kernel (4 B written per pair): see roofline_fp32"}
+        result["roofline"] = roofline
+        peak_tf = fp32_peak(torch, native, dev)
+        tf = pairs_per_launch * FLOP_PER_PAIR / (kernel_ms * 1e-3) / 1e12
+        result["roofline_fp32"] = {"bound": "fp32", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
+                                   "peak_source": "FMA-chain probe (sphk_probe_fp32) on this GPU, same run",
+                                   "flop_per_pair": FLOP_PER_PAIR,
+                                   "note": "algorithmic 512 flop/pair (SURVEY.md 8d) counted for ALL pairs, early-outs included"}
+
+    # ---- end to end: host buffers in, host result out, through the public API ----------------------
+    e2e = None
+    if args.workload == "assign":
+        gts_pin, anchors_pin = gts_h.pin_memory(), anchors_h.pin_memory()
+        out_pin = torch.empty((IMAGES, GTS, anchors_h.size(0)), dtype=torch.float32).pin_memory()
+        gts_d, anchors_d = torch.empty_like(gts_pin, device=dev), torch.empty_like(anchors_pin, device=dev)
+
+        def e2e_step():
+            gts_d.copy_(gts_pin, non_blocking=True)
+            anchors_d.copy_(anchors_pin, non_blocking=True)
+            for i in range(IMAGES):
+                out_pin[i].copy_(calc(gts_d[i], anchors_d), non_blocking=True)
+        e2e_ms = time_steps(torch, e2e_step, max(3, args.steps // 2), 2, flush, barrier)
+        t = torch.tensor([statistics.mean(e2e_ms)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": total_pairs_per_step / (float(t.item()) * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": gts_pin.numel() * 4 + anchors_pin.numel() * 4, "d2h_bytes_per_step": out_pin.numel() * 4,
+               "ms_per_step": float(t.item()), "api": "SphOverlaps2D('sph2pob_efficient_iou', 5)(gt, anchors) x 16, pinned host in/out"}
+        # the consumer only needs max/argmax (MaxIoUAssigner): fused variant, result = 12 B per anchor + 12 B per GT
+        amax_pin = torch.empty((IMAGES, anchors_h.size(0)), dtype=torch.float32).pin_memory()
+        aarg_pin = torch.empty((IMAGES, anchors_h.size(0)), dtype=torch.int64).pin_memory()
+        gmax_pin = torch.empty((IMAGES, GTS), dtype=torch.float32).pin_memory()
+        garg_pin = torch.empty((IMAGES, GTS), dtype=torch.int64).pin_memory()
+
+        def e2e_fused_step():
+            gts_d.copy_(gts_pin, non_blocking=True)
+            anchors_d.copy_(anchors_pin, non_blocking=True)
+            for i in range(IMAGES):
+                rmax, rarg, cmax, carg = sph_max_overlaps(gts_d[i], anchors_d)
+                amax_pin[i].copy_(cmax, non_blocking=True); aarg_pin[i].copy_(carg, non_blocking=True)
+                gmax_pin[i].copy_(rmax, non_blocking=True); garg_pin[i].copy_(rarg, non_blocking=True)
+        f_ms = statistics.mean(time_steps(torch, e2e_fused_step, max(3, args.steps // 2), 2, flush, barrier))
+        result["e2e_fused_assign"] = {"value": total_pairs_per_step / (f_ms * 1e-3), "unit": UNIT, "ms_per_step": f_ms,
+                                      "d2h_bytes_per_step": IMAGES * (anchors_h.size(0) + GTS) * 12,
+                                      "api": "sph_max_overlaps(gt, anchors): max/argmax per anchor and per GT, no matrix"}
+    else:
+        e2e = {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+               "note": "sweep inputs are resident by definition of the sharded workload; see the assign workload for e2e"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": workload, "api": "SphOverlaps2D('sph2pob_efficient_iou', box_version=5)",
+                       "pairs_per_step": total_pairs_per_step,
+                       "l2": "256 MB written between timed steps (L2 flush); each step also writes %d MB of output" %
+                             (pairs_per_step * 4 >> 20) if args.workload == "assign" else "256 MB written between timed steps (L2 flush)",
+                       "timing": "CUDA events per step on the launching stream, sum over K steps, max over ranks"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches,
+        }
+        line.update(result)
+        if world == 1 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            v, secs = cpu_port_assign(torch, gts_h, anchors_h, images=2, repeats=2)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "2 of the 16 images (2 x 32 x 98208 = 6.3 M pairs), best of 2, %.1f s" % secs,
+                                    "what": "oracle/sph_oracle.py: the reference's PyTorch-eager CPU algorithm, fp32, all host threads"}
+            c = cpu_c_port_assign(gts_h, anchors_h)
+            if c:
+                line["cpu_baseline_c_openmp"] = {"value": c, "unit": UNIT, "cores": cores, "kind": "port",
+                                                 "sample": "1 image (3.1 M pairs), best of 3",
+                                                 "what": "oracle/sph_oracle.c: float64 scalar restatement, OpenMP"}
+        if world == 1 and not args.no_extras:
+            if True:
+                try:
+                    line["other_configs"] = other_configs(torch, native, dev, flush)
+                except Exception as e:   # the headline line must still be printed
+                    line["other_configs"] = {"error": repr(e)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="assign", choices=["assign", "sweep"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configs and keep the run short (ncu)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,124 @@
+/* sphk.h -- C ABI of the B200 (sm_100a) spherical-box IoU kernels.
+ *
+ * Drop-in boundary for the IoU hot path of ManuelVeras/sph-retina.  Each entry point names
+ * the reference interface (file:line, relative to the reference root) whose arithmetic it
+ * replaces; the Python layer in sph_retina_b200/sphdet keeps the reference's signatures
+ * and calls these through ctypes (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in
+ *     _host; nothing is allocated or freed by the library, the caller owns all buffers;
+ *   - boxes are float32 row-major [n, D], D = 4 (theta, phi, alpha, beta) or 5 (+gamma),
+ *     degrees, exactly the reference layout (sphdet/iou/sph_iou_calculator.py:22-31);
+ *   - inputs are never written (tests/test_all_ious.py:322-331);
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*; 0 = legacy default) and
+ *     the call returns without synchronising;
+ *   - return value: SPHK_OK or a negative error code; sphk_last_error_string() gives the
+ *     reason for the calling thread.  No C++ exception crosses the boundary.
+ */
+#ifndef SPHK_H_
+#define SPHK_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPHK_ABI_VERSION 1
+
+enum sphk_status {
+    SPHK_OK = 0,
+    SPHK_ERR_INVALID_ARGUMENT = -1,
+    SPHK_ERR_CUDA = -2,
+    SPHK_ERR_UNSUPPORTED = -3
+};
+
+/* IoU flavour: reference backend strings of sph_overlaps (sphdet/iou/sph_iou_calculator.py:58-113) */
+enum sphk_kind {
+    SPHK_KIND_SPH2POB_EFFICIENT = 0, /* 'sph2pob_efficient_iou'  sphdet/iou/sph_iou_api.py:97-98   */
+    SPHK_KIND_SPH2POB_STANDARD = 1,  /* 'sph2pob_standard_iou'   sphdet/iou/sph_iou_api.py:94-95   */
+    SPHK_KIND_SPH = 2,               /* 'sph_iou'                sphdet/iou/sph_iou_api.py:130-151 */
+    SPHK_KIND_FOV = 3                /* 'fov_iou'                sphdet/iou/sph_iou_api.py:156-177 */
+};
+enum sphk_mode { SPHK_MODE_IOU = 0, SPHK_MODE_IOF = 1 };                     /* sph_iou_api.py:49     */
+enum sphk_edge { SPHK_EDGE_ARC = 0, SPHK_EDGE_CHORD = 1, SPHK_EDGE_TANGENT = 2 }; /* sph2pob_efficient.py:100-108 */
+
+int sphk_abi_version(void);
+const char* sphk_last_error_string(void);
+/* number of SMs / compute capability of the current device, for grid sizing and sanity checks */
+int sphk_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* Aligned IoU: out[p] = IoU(b1[p], b2[p]), p < P.
+ * Replaces _sph2pob_iou_auxiliary(..., is_aligned=True) (sphdet/iou/sph_iou_api.py:48-86: both
+ * jitters :222-260, transform sph2pob_efficient.py:9-73 | sph2pob_standard.py:8-80, rotated IoU
+ * mmcv.ops.box_iou_rotated at :79, clamp :86) and sph_iou / fov_iou (:130-177 with
+ * approximate_ious.py:3-55; D must be 4, mode must be IOU for those two kinds). */
+int sphk_iou_aligned(int kind, const float* b1, const float* b2, int64_t P, int D, int mode, int edge,
+                     float* out, void* stream);
+
+/* Pairwise IoU of rows[R,D] x cols[C,D]; pair (i,j) = (rows[i] as bboxes1, cols[j] as bboxes2),
+ * the reference's expansion order (sphdet/iou/sph_iou_api.py:59-61).  Any output may be NULL:
+ *   out        [R, ld]  the matrix (ld >= C, in elements)                    (:85 view(rows, cols))
+ *   row_max/row_arg [R] max / argmax over the columns  -- MaxIoUAssigner's overlaps.max(dim=1)
+ *   col_max/col_arg [C] max / argmax over the rows     -- overlaps.max(dim=0)
+ *                       (mmdet/core/bbox/assigners/max_iou_assigner.py:173-176)
+ * Ties resolve to the lowest index.  row_base / col_base are added to the reported indices so a
+ * shard of a larger matrix reports global indices.  `workspace` must hold
+ * sphk_iou_pairwise_workspace_bytes(R, C) bytes when any max/argmax output is requested. */
+int64_t sphk_iou_pairwise_workspace_bytes(int64_t R, int64_t C);
+int sphk_iou_pairwise(int kind, const float* rows, int64_t R, const float* cols, int64_t C, int D, int mode,
+                      int edge, float* out, int64_t ld, float* row_max, int32_t* row_arg, float* col_max,
+                      int32_t* col_arg, int32_t row_base, int32_t col_base, void* workspace, void* stream);
+
+/* Sph2Pob loss, fused forward + backward (Sph2PobIoULoss, mode='iou'):
+ * replaces Sph2PobTransfrom.new_forward (sphdet/losses/sph2pob_transform.py:24-35: jitter_1,
+ * sph2pob_standard, jitter_2) followed by diff_iou_rotated_2d(...).clamp(0,1)
+ * (sphdet/losses/sph2pob_iou_loss.py:122) and its autograd backward.
+ *   iou        [n]      clamped IoU of (pred[i], target[i])
+ *   grad_iou   [n]      upstream d(total)/d(iou[i]) or NULL (then no gradients are produced)
+ *   grad_pred  [n, D]   d(total)/d(pred)   (NULL to skip)
+ *   grad_target[n, D]   d(total)/d(target) (NULL to skip)  */
+int sphk_loss_fwd_bwd(const float* pred, const float* target, int64_t n, int D, float* iou, const float* grad_iou,
+                      float* grad_pred, float* grad_target, void* stream);
+
+/* The same two stages exposed separately so that the GIoU/DIoU/CIoU epilogues
+ * (sphdet/losses/sph2pob_iou_loss.py:142-194) can stay as autograd code on the OBBs:
+ *   sphk_obb_fwd : (pred,target)[n,D] -> obb1, obb2 [n,5] = (x, y, w, h, angle rad) after
+ *                  jitter_1 + transform(kind) + jitter_2
+ *   sphk_obb_bwd : grads of obb1/obb2 -> grads of pred/target (either may be NULL)
+ *   sphk_riou_fwd_bwd : rotated IoU of OBB pairs (diff_iou_rotated_2d, sphdet/iou/diff_iou_rotated.py:325-343)
+ *                  and, when grad_iou != NULL, its gradient w.r.t. both OBBs. */
+int sphk_obb_fwd(int kind, const float* b1, const float* b2, int64_t n, int D, int edge, float* obb1, float* obb2,
+                 void* stream);
+int sphk_obb_bwd(int kind, const float* b1, const float* b2, int64_t n, int D, int edge, const float* grad_obb1,
+                 const float* grad_obb2, float* grad_b1, float* grad_b2, void* stream);
+int sphk_riou_fwd_bwd(const float* obb1, const float* obb2, int64_t n, float* iou, const float* grad_iou,
+                      float* grad_obb1, float* grad_obb2, void* stream);
+
+/* Batched greedy spherical NMS (SphNMS / sph_batched_nms / sph_nms_op,
+ * sphdet/bbox/nms/sph_nms.py:22-74) with Sph2Pob-efficient IoU.
+ *   boxes       [M, D]
+ *   order       [M]    int32 indices into boxes, grouped by segment (one segment = one
+ *                      (image, class) group), score-descending inside a segment (:65)
+ *   seg_offsets [S+1]  int32, segment s covers order[seg_offsets[s] .. seg_offsets[s+1])
+ *   max_seg_len        an upper bound of the segment lengths (sizes the per-CTA shared memory;
+ *                      a longer segment is refused: its keep bytes are set to 0xFF)
+ *   keep        [M]    uint8, keep[q] = 1 iff the box order[q] survives (same positions as `order`)
+ * A box is suppressed iff IoU(pivot as bboxes1, box as bboxes2) > iou_threshold (:70-73). */
+int sphk_nms_batched(const float* boxes, const int32_t* order, const int32_t* seg_offsets, int32_t S,
+                     int32_t max_seg_len, int D, float iou_threshold, uint8_t* keep, void* stream);
+
+/* Measurement helpers (bench.py; no counterpart in the reference).
+ * sphk_probe_fp32: FMA-chain microbenchmark that yields the FP32 CUDA-core peak the Sph2Pob kernels
+ *   are bounded by (SURVEY.md 8d asks for a measured denominator): launches `blocks` x 256 threads,
+ *   each running 8 independent chains of `iters` FMAs, i.e. 2*8*iters*256*blocks flop; sink[blocks*256].
+ * sphk_set_dense: 1 disables the parity-safe "disjoint pair" early-outs of the Sph2Pob kernels so the
+ *   dense throughput can be reported next to the real one; returns the previous setting. */
+int sphk_probe_fp32(int32_t blocks, int32_t iters, float* sink, void* stream);
+int sphk_set_dense(int on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPHK_H_ */

@@ -453,12 +453,14 @@ def nms_single(boxes, scores, thr, iou_fn):
 
 
 def nms_batched(boxes, scores, idxs, iou_threshold=0.5, max_num=None, class_agnostic=False, iou_fn=None):
-    """sph_nms.py:22-60: per label greedy NMS, union, sort by score, truncate, append score column."""
+    """sph_nms.py:22-60: per label greedy NMS, union, sort by score, truncate, append score column.
+    `class_agnostic` is accepted and IGNORED exactly as in the reference (:33 pops it, :44 loops over
+    torch.unique(idxs) regardless)."""
     if iou_fn is None:
         iou_fn = lambda a, b: sph2pob_iou(a, b, "efficient")
     max_num = boxes.size(0) if max_num is None else min(max_num, boxes.size(0))
     kept = torch.zeros(boxes.size(0), dtype=torch.bool)
-    labels = torch.zeros_like(idxs) if class_agnostic else idxs
+    labels = idxs
     for lab in torch.unique(labels):
         sel = (labels == lab).nonzero().view(-1)
         kept[sel[nms_single(boxes[sel], scores[sel], iou_threshold, iou_fn)]] = True

@@ -1,0 +1,244 @@
+"""ctypes binding of the C ABI declared in ``include/sphk.h`` (libsphk.so, sm_100a CUDA).
+
+This is the ONLY compute path of the package.  There is no CPU or eager-PyTorch fallback: a
+missing library raises at import of this module, a non-CUDA tensor raises at the call."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libsphk.so")
+
+KIND = {"sph2pob_efficient": 0, "sph2pob_standard": 1, "sph": 2, "fov": 3}
+MODE = {"iou": 0, "iof": 1}
+EDGE = {"arc": 0, "chord": 1, "tangent": 2}
+
+SPHK_OK = 0
+ABI_VERSION = 1
+
+_c_float_p = ctypes.c_void_p  # raw device addresses
+_i64 = ctypes.c_int64
+_i32 = ctypes.c_int32
+_int = ctypes.c_int
+
+# name -> (restype, argtypes); must list every symbol of include/sphk.h (tests check this)
+SIGNATURES = {
+    "sphk_abi_version": (_int, []),
+    "sphk_last_error_string": (ctypes.c_char_p, []),
+    "sphk_device_info": (_int, [ctypes.POINTER(_int)] * 3),
+    "sphk_iou_aligned": (_int, [_int, _c_float_p, _c_float_p, _i64, _int, _int, _int, _c_float_p, ctypes.c_void_p]),
+    "sphk_iou_pairwise_workspace_bytes": (_i64, [_i64, _i64]),
+    "sphk_iou_pairwise": (_int, [_int, _c_float_p, _i64, _c_float_p, _i64, _int, _int, _int, _c_float_p, _i64,
+                                 _c_float_p, ctypes.c_void_p, _c_float_p, ctypes.c_void_p, _i32, _i32,
+                                 ctypes.c_void_p, ctypes.c_void_p]),
+    "sphk_loss_fwd_bwd": (_int, [_c_float_p, _c_float_p, _i64, _int, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
+                                 ctypes.c_void_p]),
+    "sphk_obb_fwd": (_int, [_int, _c_float_p, _c_float_p, _i64, _int, _int, _c_float_p, _c_float_p, ctypes.c_void_p]),
+    "sphk_obb_bwd": (_int, [_int, _c_float_p, _c_float_p, _i64, _int, _int, _c_float_p, _c_float_p, _c_float_p,
+                            _c_float_p, ctypes.c_void_p]),
+    "sphk_riou_fwd_bwd": (_int, [_c_float_p, _c_float_p, _i64, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
+                                 ctypes.c_void_p]),
+    "sphk_nms_batched": (_int, [_c_float_p, ctypes.c_void_p, ctypes.c_void_p, _i32, _i32, _int, ctypes.c_float,
+                                ctypes.c_void_p, ctypes.c_void_p]),
+    "sphk_probe_fp32": (_int, [_i32, _i32, _c_float_p, ctypes.c_void_p]),
+    "sphk_set_dense": (_int, [_int]),
+}
+
+
+class SphkError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.isfile(LIB_PATH):
+        raise ImportError(
+            "sph_retina_b200: %s is missing. Build it with `python -m sph_retina_b200.build` "
+            "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    got = lib.sphk_abi_version()
+    if got != ABI_VERSION:
+        raise ImportError("libsphk.so ABI version %d, binding expects %d: rebuild" % (got, ABI_VERSION))
+    return lib
+
+
+lib = _load()
+launches = 0  # number of C-ABI compute calls issued by this process (bench.py reports kernel counts from it)
+
+
+def _check(status: int):
+    if status != SPHK_OK:
+        raise SphkError("libsphk: %s (status %d)" % (lib.sphk_last_error_string().decode(), status))
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(t):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _boxes(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise SphkError("%s is on %s: the sm_100a kernels are the only implementation of this path "
+                        "(no CPU fallback); move the boxes to a CUDA device" % (name, t.device))
+    if t.dim() != 2 or t.size(1) not in (4, 5):
+        raise SphkError("%s must have shape [n, 4] (BFoV) or [n, 5] (RBFoV), got %s" % (name, tuple(t.shape)))
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def device_info():
+    sm, major, minor = _int(), _int(), _int()
+    _check(lib.sphk_device_info(ctypes.byref(sm), ctypes.byref(major), ctypes.byref(minor)))
+    return sm.value, major.value, minor.value
+
+
+def iou_aligned(kind: str, b1, b2, mode="iou", edge="arc") -> torch.Tensor:
+    global launches
+    b1, b2 = _boxes(b1, "bboxes1"), _boxes(b2, "bboxes2")
+    if b1.shape != b2.shape:
+        raise SphkError("aligned IoU needs equal shapes, got %s and %s" % (tuple(b1.shape), tuple(b2.shape)))
+    out = torch.empty(b1.size(0), dtype=torch.float32, device=b1.device)
+    with torch.cuda.device(b1.device):
+        _check(lib.sphk_iou_aligned(KIND[kind], _ptr(b1), _ptr(b2), b1.size(0), b1.size(1), MODE[mode], EDGE[edge],
+                                    _ptr(out), _stream(b1)))
+    launches += 1
+    return out
+
+
+def iou_pairwise(kind: str, rows, cols, mode="iou", edge="arc", want_matrix=True, want_row_max=False,
+                 want_col_max=False, row_base=0, col_base=0, out=None):
+    """Returns (matrix|None, (row_max,row_arg)|None, (col_max,col_arg)|None)."""
+    global launches
+    rows, cols = _boxes(rows, "bboxes1"), _boxes(cols, "bboxes2")
+    if rows.size(1) != cols.size(1):
+        raise SphkError("box widths differ: %d vs %d" % (rows.size(1), cols.size(1)))
+    R, C, dev = rows.size(0), cols.size(0), rows.device
+    mat = None
+    if want_matrix:
+        mat = out if out is not None else torch.empty((R, C), dtype=torch.float32, device=dev)
+        assert mat.is_cuda and mat.dtype == torch.float32 and mat.shape == (R, C) and mat.stride(1) == 1
+    ld = mat.stride(0) if (mat is not None and R > 1) else C
+    rmax = rarg = cmax = carg = ws = None
+    if want_row_max:
+        rmax = torch.empty(R, dtype=torch.float32, device=dev)
+        rarg = torch.empty(R, dtype=torch.int32, device=dev)
+    if want_col_max:
+        cmax = torch.empty(C, dtype=torch.float32, device=dev)
+        carg = torch.empty(C, dtype=torch.int32, device=dev)
+    if want_row_max or want_col_max:
+        ws = torch.empty(max(1, lib.sphk_iou_pairwise_workspace_bytes(R, C)), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib.sphk_iou_pairwise(KIND[kind], _ptr(rows), R, _ptr(cols), C, rows.size(1), MODE[mode], EDGE[edge],
+                                     _ptr(mat), ld, _ptr(rmax), _ptr(rarg), _ptr(cmax), _ptr(carg), row_base, col_base,
+                                     _ptr(ws), _stream(rows)))
+    launches += 1 + 2 * int(want_row_max) + 2 * int(want_col_max)
+    return mat, ((rmax, rarg) if want_row_max else None), ((cmax, carg) if want_col_max else None)
+
+
+def loss_fwd_bwd(pred, target, grad_iou=None, want_grad_pred=False, want_grad_target=False):
+    """Fused Sph2Pob (standard transform) IoU of aligned pairs and, if grad_iou is given, its gradients."""
+    global launches
+    pred, target = _boxes(pred, "pred"), _boxes(target, "target")
+    if pred.shape != target.shape:
+        raise SphkError("pred/target shapes differ: %s vs %s" % (tuple(pred.shape), tuple(target.shape)))
+    n, dev = pred.size(0), pred.device
+    iou = torch.empty(n, dtype=torch.float32, device=dev)
+    gp = torch.empty_like(pred) if (grad_iou is not None and want_grad_pred) else None
+    gt = torch.empty_like(target) if (grad_iou is not None and want_grad_target) else None
+    if grad_iou is not None:
+        grad_iou = grad_iou.to(device=dev, dtype=torch.float32).contiguous()
+        assert grad_iou.numel() == n
+    with torch.cuda.device(dev):
+        _check(lib.sphk_loss_fwd_bwd(_ptr(pred), _ptr(target), n, pred.size(1), _ptr(iou), _ptr(grad_iou), _ptr(gp),
+                                     _ptr(gt), _stream(pred)))
+    launches += 1
+    return iou, gp, gt
+
+
+def obb_fwd(kind: str, b1, b2, edge="arc"):
+    global launches
+    b1, b2 = _boxes(b1, "bboxes1"), _boxes(b2, "bboxes2")
+    assert b1.shape == b2.shape
+    n, dev = b1.size(0), b1.device
+    o1 = torch.empty((n, 5), dtype=torch.float32, device=dev)
+    o2 = torch.empty((n, 5), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib.sphk_obb_fwd(KIND[kind], _ptr(b1), _ptr(b2), n, b1.size(1), EDGE[edge], _ptr(o1), _ptr(o2), _stream(b1)))
+    launches += 1
+    return o1, o2
+
+
+def obb_bwd(kind: str, b1, b2, g1, g2, edge="arc", want1=True, want2=True):
+    global launches
+    b1, b2 = _boxes(b1, "bboxes1"), _boxes(b2, "bboxes2")
+    n, dev = b1.size(0), b1.device
+    g1 = None if g1 is None else g1.to(device=dev, dtype=torch.float32).contiguous()
+    g2 = None if g2 is None else g2.to(device=dev, dtype=torch.float32).contiguous()
+    gb1 = torch.empty_like(b1) if want1 else None
+    gb2 = torch.empty_like(b2) if want2 else None
+    with torch.cuda.device(dev):
+        _check(lib.sphk_obb_bwd(KIND[kind], _ptr(b1), _ptr(b2), n, b1.size(1), EDGE[edge], _ptr(g1), _ptr(g2), _ptr(gb1),
+                                _ptr(gb2), _stream(b1)))
+    launches += 1
+    return gb1, gb2
+
+
+def riou_fwd_bwd(o1, o2, grad_iou=None, want1=True, want2=True):
+    global launches
+    if not (o1.is_cuda and o2.is_cuda):
+        raise SphkError("rotated IoU: OBB tensors must be CUDA tensors (no CPU fallback)")
+    o1, o2 = o1.float().contiguous(), o2.float().contiguous()
+    assert o1.shape == o2.shape and o1.dim() == 2 and o1.size(1) == 5
+    n, dev = o1.size(0), o1.device
+    iou = torch.empty(n, dtype=torch.float32, device=dev)
+    g1 = torch.empty_like(o1) if (grad_iou is not None and want1) else None
+    g2 = torch.empty_like(o2) if (grad_iou is not None and want2) else None
+    if grad_iou is not None:
+        grad_iou = grad_iou.to(device=dev, dtype=torch.float32).contiguous()
+    with torch.cuda.device(dev):
+        _check(lib.sphk_riou_fwd_bwd(_ptr(o1), _ptr(o2), n, _ptr(iou), _ptr(grad_iou), _ptr(g1), _ptr(g2), _stream(o1)))
+    launches += 1
+    return iou, g1, g2
+
+
+def nms_batched(boxes, order, seg_offsets, max_seg_len: int, iou_threshold: float) -> torch.Tensor:
+    """keep flags (uint8, aligned with `order`) of the greedy per-segment spherical NMS."""
+    global launches
+    boxes = _boxes(boxes, "boxes")
+    dev = boxes.device
+    order = order.to(device=dev, dtype=torch.int32).contiguous()
+    seg_offsets = seg_offsets.to(device=dev, dtype=torch.int32).contiguous()
+    S = seg_offsets.numel() - 1
+    keep = torch.zeros(order.numel(), dtype=torch.uint8, device=dev)
+    if S <= 0 or order.numel() == 0:
+        return keep
+    with torch.cuda.device(dev):
+        _check(lib.sphk_nms_batched(_ptr(boxes), _ptr(order), _ptr(seg_offsets), S, int(max_seg_len), boxes.size(1),
+                                    float(iou_threshold), _ptr(keep), _stream(boxes)))
+    launches += 1
+    return keep
+
+
+def probe_fp32(blocks: int, iters: int, device) -> float:
+    """Runs the FMA-chain probe once; returns the flop count of the launch (time it with CUDA events)."""
+    sink = torch.empty(blocks * 256, dtype=torch.float32, device=device)
+    with torch.cuda.device(sink.device):
+        _check(lib.sphk_probe_fp32(blocks, iters, _ptr(sink), _stream(sink)))
+    return 2.0 * 8 * iters * 256 * blocks
+
+
+def set_dense(on: bool) -> bool:
+    """Disable (True) / enable (False) the disjoint-pair early-outs; returns the previous setting."""
+    return bool(lib.sphk_set_dense(1 if on else 0))

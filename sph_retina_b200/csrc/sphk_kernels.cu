@@ -1,0 +1,523 @@
+// sphk_kernels.cu -- sm_100a kernels and the C ABI (include/sphk.h) of the spherical-box IoU path.
+//
+// Kernels (all fp32 CUDA-core work; no tensor cores -- nothing here is a contraction):
+//   k_iou_aligned      one thread per aligned pair                      (config #1, Sph/FoV siblings)
+//   k_iou_pairwise     lanes <-> columns (coalesced matrix rows), row tile broadcast from shared
+//                      memory, fused row/column max+argmax              (configs #2, #5)
+//   k_loss_fwd_bwd     one thread per pair, recompute-in-backward        (config #3)
+//   k_obb_fwd/bwd, k_riou_fwd_bwd   the two loss stages exposed separately (GIoU/DIoU/CIoU epilogues)
+//   k_nms              one CTA per (image, class) segment, 32-pivot blocks of warp-ballot
+//                      suppression words + in-warp serial scan            (config #4)
+// The per-pair arithmetic lives in sphk_math.cuh / sphk_grad.cuh.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/sphk.h"
+#include "sphk_grad.cuh"
+#include "sphk_math.cuh"
+
+using namespace sphk;
+
+namespace {
+
+thread_local char g_err[256] = "";
+int g_dense = 0;   // sphk_set_dense: 1 = no disjoint-pair early-outs (measurement only)
+
+int fail(int code, const char* what) {
+    snprintf(g_err, sizeof(g_err), "%s", what);
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* where) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+    return SPHK_ERR_CUDA;
+}
+#define SPHK_LAUNCH_CHECK(where)                                  \
+    do {                                                          \
+        cudaError_t e_ = cudaGetLastError();                      \
+        if (e_ != cudaSuccess) return cuda_fail(e_, where);       \
+    } while (0)
+
+constexpr int kThreads = 256;
+
+// ---- box loads --------------------------------------------------------------------------------
+template <int D>
+__device__ __forceinline__ RawBox load_box(const float* __restrict__ b, int64_t i, bool vec_ok) {
+    RawBox r;
+    if (D == 4) {
+        if (vec_ok) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(b) + i);
+            r.t = v.x; r.p = v.y; r.a = v.z; r.b = v.w;
+        } else {
+            const float* q = b + i * 4;
+            r.t = __ldg(q); r.p = __ldg(q + 1); r.a = __ldg(q + 2); r.b = __ldg(q + 3);
+        }
+        r.g = 0.0f;
+    } else {
+        const float* q = b + i * 5;
+        r.t = __ldg(q); r.p = __ldg(q + 1); r.a = __ldg(q + 2); r.b = __ldg(q + 3); r.g = __ldg(q + 4);
+    }
+    return r;
+}
+
+template <int D>
+__device__ __forceinline__ void store_grad(float* __restrict__ g, int64_t i, const float* v, bool vec_ok) {
+    if (D == 4 && vec_ok) {
+        reinterpret_cast<float4*>(g)[i] = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+        float* q = g + i * D;
+#pragma unroll
+        for (int k = 0; k < D; ++k) q[k] = v[k];
+    }
+}
+
+// ---- aligned -----------------------------------------------------------------------------------
+template <int KIND, int D>
+__global__ void __launch_bounds__(kThreads) k_iou_aligned(const float* __restrict__ b1, const float* __restrict__ b2,
+                                                          int64_t P, int mode, int edge, float* __restrict__ out,
+                                                          bool vec_ok, bool dense) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= P) return;
+    const RawBox x = load_box<D>(b1, i, vec_ok), y = load_box<D>(b2, i, vec_ok);
+    float v;
+    if (KIND == KIND_SPH || KIND == KIND_FOV) v = approx_iou_pair(x, y, KIND);
+    else v = sph2pob_iou_pair(x, y, D, KIND, mode, edge, dense);
+    out[i] = v;
+}
+
+// ---- pairwise ----------------------------------------------------------------------------------
+// key = (float bits << 32) | ~index : u64 max == (max value, lowest index); IoU >= 0 so the bit
+// pattern of the float is monotone.
+__device__ __forceinline__ unsigned long long pack_key(float v, uint32_t idx) {
+    return ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
+}
+
+constexpr int kTileRows = 32;
+
+template <int KIND, int D>
+__global__ void __launch_bounds__(kThreads)
+k_iou_pairwise(const float* __restrict__ rows, int64_t R, const float* __restrict__ cols, int64_t C, int mode, int edge,
+               float* __restrict__ out, int64_t ld, unsigned long long* __restrict__ row_key,
+               unsigned long long* __restrict__ col_key, uint32_t row_base, uint32_t col_base, int64_t col_tiles,
+               bool vec_ok, bool dense) {
+    __shared__ float s_row[kTileRows * 5];
+    __shared__ unsigned long long s_rkey[kTileRows];
+    const int64_t rt = blockIdx.x / col_tiles, ct = blockIdx.x % col_tiles;
+    const int64_t r0 = rt * kTileRows;
+    const int nr = (int)min((int64_t)kTileRows, R - r0);
+    const int64_t col = ct * kThreads + threadIdx.x;
+    const bool col_ok = col < C;
+    for (int k = threadIdx.x; k < nr * D; k += kThreads) s_row[k] = __ldg(rows + r0 * D + k);
+    if (threadIdx.x < kTileRows) s_rkey[threadIdx.x] = 0ull;
+    __syncthreads();
+    RawBox y;
+    y.t = y.p = y.a = y.b = y.g = 0.0f;
+    if (col_ok) y = load_box<D>(cols, col, vec_ok);
+    const int lane = threadIdx.x & 31;
+    float best_v = -1.0f;
+    uint32_t best_r = 0;
+    for (int r = 0; r < nr; ++r) {
+        RawBox x;
+        x.t = s_row[r * D + 0]; x.p = s_row[r * D + 1]; x.a = s_row[r * D + 2]; x.b = s_row[r * D + 3];
+        x.g = (D == 5) ? s_row[r * D + 4] : 0.0f;
+        float v = 0.0f;
+        if (col_ok) {
+            if (KIND == KIND_SPH || KIND == KIND_FOV) v = approx_iou_pair(x, y, KIND);
+            else v = sph2pob_iou_pair(x, y, D, KIND, mode, edge, dense);
+            if (out) out[(r0 + r) * ld + col] = v;
+            if (v > best_v) { best_v = v; best_r = (uint32_t)r; }
+        }
+        if (row_key) {
+            // warp max over the 32 columns of this warp, lowest column on ties
+            const uint32_t bits = col_ok ? __float_as_uint(v) : 0u;
+            const uint32_t mx = __reduce_max_sync(0xFFFFFFFFu, bits);
+            const uint32_t who = __ballot_sync(0xFFFFFFFFu, col_ok && bits == mx);
+            if (who != 0u && lane == __ffs(who) - 1)
+                atomicMax(&s_rkey[r], pack_key(v, col_base + (uint32_t)col));
+        }
+    }
+    if (col_key && col_ok && best_v >= 0.0f) {
+        const unsigned long long key = pack_key(best_v, row_base + (uint32_t)r0 + best_r);
+        if (key > col_key[col]) atomicMax(&col_key[col], key);
+    }
+    if (row_key) {
+        __syncthreads();
+        if (threadIdx.x < nr) {
+            const unsigned long long key = s_rkey[threadIdx.x];
+            if (key > row_key[r0 + threadIdx.x]) atomicMax(&row_key[r0 + threadIdx.x], key);
+        }
+    }
+}
+
+__global__ void k_fill_keys(unsigned long long* keys, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = 0ull;
+}
+
+// unpack (max, argmax); a key that was never raised (no column/row at all) reports (0, base)
+__global__ void k_unpack_keys(const unsigned long long* __restrict__ keys, int64_t n, float* __restrict__ vmax,
+                              int32_t* __restrict__ arg, uint32_t base) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long k = keys[i];
+    if (vmax) vmax[i] = (k == 0ull) ? 0.0f : __uint_as_float((uint32_t)(k >> 32));
+    if (arg) arg[i] = (k == 0ull) ? (int32_t)base : (int32_t)(0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull));
+}
+
+// ---- loss --------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(kThreads)
+k_loss_fwd_bwd(const float* __restrict__ pred, const float* __restrict__ target, int64_t n, float* __restrict__ iou,
+               const float* __restrict__ grad_iou, float* __restrict__ grad_pred, float* __restrict__ grad_target,
+               bool vec_ok) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    const RawBox x = load_box<D>(pred, i, vec_ok), y = load_box<D>(target, i, vec_ok);
+    if (grad_iou == nullptr) {
+        if (iou) iou[i] = sph2pob_iou_pair(x, y, D, KIND_SPH2POB_STANDARD, MODE_IOU, EDGE_ARC);
+        return;
+    }
+    float g1[5], g2[5];
+    const float v = sph2pob_iou_pair_grad(x, y, D, KIND_SPH2POB_STANDARD, EDGE_ARC, __ldg(grad_iou + i), g1, g2);
+    if (iou) iou[i] = v;
+    if (grad_pred) store_grad<D>(grad_pred, i, g1, vec_ok);
+    if (grad_target) store_grad<D>(grad_target, i, g2, vec_ok);
+}
+
+__device__ __forceinline__ void store_obb(float* __restrict__ o, int64_t i, float x, float y, float w, float h, float a) {
+    float* q = o + i * 5;
+    q[0] = x; q[1] = y; q[2] = w; q[3] = h; q[4] = a;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreads)
+k_obb_fwd(int kind, const float* __restrict__ b1, const float* __restrict__ b2, int64_t n, int edge,
+          float* __restrict__ obb1, float* __restrict__ obb2, bool vec_ok) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    const RawBox x = load_box<D>(b1, i, vec_ok), y = load_box<D>(b2, i, vec_ok);
+    const bool m = jitter1_mask(x, y, D);
+    const JitBox g = jitter1_role1(x, m, D), p = jitter1_role2(y, m, D);
+    XformAux aux;
+    ObbPair o = (kind == KIND_SPH2POB_STANDARD) ? sph2pob_standard(g, p, D, edge, &aux)
+                                                : sph2pob_efficient(g, p, D, edge, &aux);
+    jitter2(o);
+    store_obb(obb1, i, o.x1, o.y1, o.w1, o.h1, o.a1);
+    store_obb(obb2, i, o.x2, o.y2, o.w2, o.h2, o.a2);
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreads)
+k_obb_bwd(int kind, const float* __restrict__ b1, const float* __restrict__ b2, int64_t n, int edge,
+          const float* __restrict__ grad_obb1, const float* __restrict__ grad_obb2, float* __restrict__ grad_b1,
+          float* __restrict__ grad_b2, bool vec_ok) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    const RawBox x = load_box<D>(b1, i, vec_ok), y = load_box<D>(b2, i, vec_ok);
+    const bool m = jitter1_mask(x, y, D);
+    const JitBox g = jitter1_role1(x, m, D), p = jitter1_role2(y, m, D);
+    XformAux aux;
+    ObbPair o = (kind == KIND_SPH2POB_STANDARD) ? sph2pob_standard(g, p, D, edge, &aux)
+                                                : sph2pob_efficient(g, p, D, edge, &aux);
+    const uint32_t pass2 = jitter2(o);
+    float go1[5], go2[5], gb1[5], gb2[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        go1[k] = grad_obb1 ? __ldg(grad_obb1 + i * 5 + k) : 0.0f;
+        go2[k] = grad_obb2 ? __ldg(grad_obb2 + i * 5 + k) : 0.0f;
+    }
+    jitter2_grad(pass2, go1, go2);
+    xform_grad(kind, g, p, D, edge, aux, go1, go2, gb1, gb2);
+    if (grad_b1) store_grad<D>(grad_b1, i, gb1, vec_ok);
+    if (grad_b2) store_grad<D>(grad_b2, i, gb2, vec_ok);
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_riou_fwd_bwd(const float* __restrict__ obb1, const float* __restrict__ obb2, int64_t n, float* __restrict__ iou,
+               const float* __restrict__ grad_iou, float* __restrict__ grad_obb1, float* __restrict__ grad_obb2) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    ObbPair o;
+    const float* a = obb1 + i * 5;
+    const float* b = obb2 + i * 5;
+    o.x1 = __ldg(a); o.y1 = __ldg(a + 1); o.w1 = __ldg(a + 2); o.h1 = __ldg(a + 3); o.a1 = __ldg(a + 4);
+    o.x2 = __ldg(b); o.y2 = __ldg(b + 1); o.w2 = __ldg(b + 2); o.h2 = __ldg(b + 3); o.a2 = __ldg(b + 4);
+    if (grad_iou == nullptr) {
+        if (iou) iou[i] = obb_disjoint(o) ? 0.0f : riou_value(o, MODE_IOU);
+        return;
+    }
+    float g1[5], g2[5];
+    float v = 0.0f;
+    if (obb_disjoint(o)) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) { g1[k] = 0.0f; g2[k] = 0.0f; }
+    } else {
+        v = riou_grad(o, MODE_IOU, __ldg(grad_iou + i), g1, g2);
+    }
+    if (iou) iou[i] = v;
+    if (grad_obb1) store_grad<5>(grad_obb1, i, g1, false);
+    if (grad_obb2) store_grad<5>(grad_obb2, i, g2, false);
+}
+
+// ---- NMS ---------------------------------------------------------------------------------------
+// One CTA per segment (the boxes of one (image, class) group, score-descending through `order`).
+// Pivots are taken 32 at a time.  For a block of 32 pivots every warp builds suppression words
+// word(pivot i, column word jw) = ballot_j [ IoU(box_i as bboxes1, box_j as bboxes2) > thr ] for the
+// columns j > i that are still alive; warp 0 then replays the greedy order inside the block with
+// plain register/shared-memory bit operations (no IoU, no block barrier per pivot).  Pivots and
+// columns already removed by earlier blocks are never evaluated.
+template <int D>
+__global__ void __launch_bounds__(kThreads)
+k_nms(const float* __restrict__ boxes, const int32_t* __restrict__ order, const int32_t* __restrict__ seg_offsets,
+      float thr, uint8_t* __restrict__ keep, int max_words, bool vec_ok) {
+    extern __shared__ uint32_t s_mem[];
+    const int seg = blockIdx.x;
+    const int start = seg_offsets[seg];
+    const int k = seg_offsets[seg + 1] - start;
+    if (k <= 0) return;
+    const int W = (k + 31) >> 5;
+    if (W > max_words) {   // caller under-sized max_seg_len: refuse rather than overrun shared memory
+        for (int q = threadIdx.x; q < k; q += kThreads) keep[start + q] = 0xFF;
+        return;
+    }
+    uint32_t* removed = s_mem;             // [W]
+    uint32_t* mask = s_mem + max_words;    // [32][W]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = kThreads >> 5;
+    for (int w = threadIdx.x; w < W; w += kThreads) removed[w] = 0u;
+    __syncthreads();
+    for (int i0 = 0; i0 < k; i0 += 32) {
+        const int nb = min(32, k - i0);
+        const int w0 = i0 >> 5;
+        const int nw = W - w0;
+        const uint32_t dead_pivots = removed[w0];
+        for (int unit = warp; unit < nb * nw; unit += nwarps) {
+            const int pi = unit / nw, jw = w0 + unit % nw;
+            const int i = i0 + pi, j = (jw << 5) + lane;
+            bool sup = false;
+            if (!((dead_pivots >> pi) & 1u) && j < k && j > i && !((removed[jw] >> lane) & 1u)) {
+                const RawBox x = load_box<D>(boxes, order[start + i], vec_ok);
+                const RawBox y = load_box<D>(boxes, order[start + j], vec_ok);
+                sup = sph2pob_iou_pair(x, y, D, KIND_SPH2POB_EFFICIENT, MODE_IOU, EDGE_ARC) > thr;
+            }
+            const uint32_t word = __ballot_sync(0xFFFFFFFFu, sup);
+            if (lane == 0) mask[pi * W + jw] = word;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            for (int pi = 0; pi < nb; ++pi) {
+                const bool alive = !((removed[w0] >> pi) & 1u);
+                __syncwarp();
+                if (alive)
+                    for (int w = w0 + lane; w < W; w += 32) removed[w] |= mask[pi * W + w];
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+    }
+    for (int q = threadIdx.x; q < k; q += kThreads) keep[start + q] = ((removed[q >> 5] >> (q & 31)) & 1u) ? 0 : 1;
+}
+
+__global__ void __launch_bounds__(kThreads) k_probe_fp32(int iters, float* __restrict__ sink) {
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.0f, a2 = a0 + 2.0f, a3 = a0 + 3.0f;
+    float a4 = a0 + 4.0f, a5 = a0 + 5.0f, a6 = a0 + 6.0f, a7 = a0 + 7.0f;
+    const float m = 0.999f + blockIdx.x * 1e-9f, c = 1e-3f;
+#pragma unroll 4
+    for (int i = 0; i < iters; ++i) {
+        a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+        a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+    }
+    sink[(size_t)blockIdx.x * kThreads + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline unsigned blocks_for(int64_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int sphk_abi_version(void) { return SPHK_ABI_VERSION; }
+const char* sphk_last_error_string(void) { return g_err; }
+
+int sphk_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    cudaDeviceProp p;
+    e = cudaGetDeviceProperties(&p, dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    return SPHK_OK;
+}
+
+int sphk_iou_aligned(int kind, const float* b1, const float* b2, int64_t P, int D, int mode, int edge, float* out,
+                     void* stream) {
+    if (P < 0 || (D != 4 && D != 5)) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_aligned: P < 0 or D not in {4,5}");
+    if (kind < 0 || kind > 3) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_aligned: unknown kind");
+    if (mode != SPHK_MODE_IOU && mode != SPHK_MODE_IOF) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_aligned: unknown mode");
+    if (edge < 0 || edge > 2) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_aligned: unknown edge");
+    if ((kind == SPHK_KIND_SPH || kind == SPHK_KIND_FOV) && (D != 4 || mode != SPHK_MODE_IOU))
+        return fail(SPHK_ERR_UNSUPPORTED, "sph_iou / fov_iou take BFoV boxes (D = 4) and mode 'iou' only");
+    if (P == 0) return SPHK_OK;
+    if (!b1 || !b2 || !out) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_aligned: null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool v = aligned16(b1) && aligned16(b2);
+    const unsigned g = blocks_for(P);
+    if (kind == SPHK_KIND_SPH) k_iou_aligned<KIND_SPH, 4><<<g, kThreads, 0, s>>>(b1, b2, P, mode, edge, out, v, g_dense != 0);
+    else if (kind == SPHK_KIND_FOV) k_iou_aligned<KIND_FOV, 4><<<g, kThreads, 0, s>>>(b1, b2, P, mode, edge, out, v, g_dense != 0);
+    else if (kind == SPHK_KIND_SPH2POB_EFFICIENT && D == 4)
+        k_iou_aligned<KIND_SPH2POB_EFFICIENT, 4><<<g, kThreads, 0, s>>>(b1, b2, P, mode, edge, out, v, g_dense != 0);
+    else if (kind == SPHK_KIND_SPH2POB_EFFICIENT)
+        k_iou_aligned<KIND_SPH2POB_EFFICIENT, 5><<<g, kThreads, 0, s>>>(b1, b2, P, mode, edge, out, v, g_dense != 0);
+    else if (D == 4) k_iou_aligned<KIND_SPH2POB_STANDARD, 4><<<g, kThreads, 0, s>>>(b1, b2, P, mode, edge, out, v, g_dense != 0);
+    else k_iou_aligned<KIND_SPH2POB_STANDARD, 5><<<g, kThreads, 0, s>>>(b1, b2, P, mode, edge, out, v, g_dense != 0);
+    SPHK_LAUNCH_CHECK("k_iou_aligned");
+    return SPHK_OK;
+}
+
+int64_t sphk_iou_pairwise_workspace_bytes(int64_t R, int64_t C) {
+    if (R < 0 || C < 0) return 0;
+    return (R + C) * (int64_t)sizeof(unsigned long long);
+}
+
+int sphk_iou_pairwise(int kind, const float* rows, int64_t R, const float* cols, int64_t C, int D, int mode, int edge,
+                      float* out, int64_t ld, float* row_max, int32_t* row_arg, float* col_max, int32_t* col_arg,
+                      int32_t row_base, int32_t col_base, void* workspace, void* stream) {
+    if (R < 0 || C < 0 || (D != 4 && D != 5)) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: bad R, C or D");
+    if (kind < 0 || kind > 3) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: unknown kind");
+    if (mode != SPHK_MODE_IOU && mode != SPHK_MODE_IOF) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: unknown mode");
+    if (edge < 0 || edge > 2) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: unknown edge");
+    if ((kind == SPHK_KIND_SPH || kind == SPHK_KIND_FOV) && (D != 4 || mode != SPHK_MODE_IOU))
+        return fail(SPHK_ERR_UNSUPPORTED, "sph_iou / fov_iou take BFoV boxes (D = 4) and mode 'iou' only");
+    if (out && ld < C) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: ld < C");
+    if (R + (int64_t)(uint32_t)row_base > 0xFFFFFFFFll || C + (int64_t)(uint32_t)col_base > 0xFFFFFFFFll)
+        return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: indices do not fit 32 bits");
+    const bool want_row = row_max || row_arg, want_col = col_max || col_arg;
+    if ((want_row || want_col) && !workspace && (R + C) > 0)
+        return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: workspace required for max/argmax outputs");
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned long long* rkey = want_row ? (unsigned long long*)workspace : nullptr;
+    unsigned long long* ckey = want_col ? (unsigned long long*)workspace + R : nullptr;
+    if (want_row && R > 0) k_fill_keys<<<blocks_for(R), kThreads, 0, s>>>(rkey, R);
+    if (want_col && C > 0) k_fill_keys<<<blocks_for(C), kThreads, 0, s>>>(ckey, C);
+    if (R > 0 && C > 0) {
+        if (!rows || !cols) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: null box pointer");
+        const int64_t col_tiles = (C + kThreads - 1) / kThreads, row_tiles = (R + kTileRows - 1) / kTileRows;
+        if (col_tiles * row_tiles > 0x7FFFFFFFll) return fail(SPHK_ERR_UNSUPPORTED, "sphk_iou_pairwise: grid too large; shard the call");
+        const unsigned g = (unsigned)(col_tiles * row_tiles);
+        const bool v = aligned16(cols);
+#define SPHK_PW(K, DD)                                                                                           \
+    k_iou_pairwise<K, DD><<<g, kThreads, 0, s>>>(rows, R, cols, C, mode, edge, out, ld, rkey, ckey, (uint32_t)row_base, \
+                                                  (uint32_t)col_base, col_tiles, v, g_dense != 0)
+        if (kind == SPHK_KIND_SPH) SPHK_PW(KIND_SPH, 4);
+        else if (kind == SPHK_KIND_FOV) SPHK_PW(KIND_FOV, 4);
+        else if (kind == SPHK_KIND_SPH2POB_EFFICIENT && D == 4) SPHK_PW(KIND_SPH2POB_EFFICIENT, 4);
+        else if (kind == SPHK_KIND_SPH2POB_EFFICIENT) SPHK_PW(KIND_SPH2POB_EFFICIENT, 5);
+        else if (D == 4) SPHK_PW(KIND_SPH2POB_STANDARD, 4);
+        else SPHK_PW(KIND_SPH2POB_STANDARD, 5);
+#undef SPHK_PW
+        SPHK_LAUNCH_CHECK("k_iou_pairwise");
+    }
+    if (want_row && R > 0) k_unpack_keys<<<blocks_for(R), kThreads, 0, s>>>(rkey, R, row_max, row_arg, (uint32_t)col_base);
+    if (want_col && C > 0) k_unpack_keys<<<blocks_for(C), kThreads, 0, s>>>(ckey, C, col_max, col_arg, (uint32_t)row_base);
+    SPHK_LAUNCH_CHECK("k_unpack_keys");
+    return SPHK_OK;
+}
+
+int sphk_loss_fwd_bwd(const float* pred, const float* target, int64_t n, int D, float* iou, const float* grad_iou,
+                      float* grad_pred, float* grad_target, void* stream) {
+    if (n < 0 || (D != 4 && D != 5)) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_loss_fwd_bwd: n < 0 or D not in {4,5}");
+    if (n == 0) return SPHK_OK;
+    if (!pred || !target) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_loss_fwd_bwd: null box pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool v = aligned16(pred) && aligned16(target) && (!grad_pred || aligned16(grad_pred)) &&
+                   (!grad_target || aligned16(grad_target));
+    if (D == 4) k_loss_fwd_bwd<4><<<blocks_for(n), kThreads, 0, s>>>(pred, target, n, iou, grad_iou, grad_pred, grad_target, v);
+    else k_loss_fwd_bwd<5><<<blocks_for(n), kThreads, 0, s>>>(pred, target, n, iou, grad_iou, grad_pred, grad_target, v);
+    SPHK_LAUNCH_CHECK("k_loss_fwd_bwd");
+    return SPHK_OK;
+}
+
+int sphk_obb_fwd(int kind, const float* b1, const float* b2, int64_t n, int D, int edge, float* obb1, float* obb2,
+                 void* stream) {
+    if (n < 0 || (D != 4 && D != 5)) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_obb_fwd: n < 0 or D not in {4,5}");
+    if (kind != SPHK_KIND_SPH2POB_EFFICIENT && kind != SPHK_KIND_SPH2POB_STANDARD)
+        return fail(SPHK_ERR_UNSUPPORTED, "sphk_obb_fwd: kind must be a Sph2Pob transform");
+    if (edge < 0 || edge > 2) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_obb_fwd: unknown edge");
+    if (n == 0) return SPHK_OK;
+    if (!b1 || !b2 || !obb1 || !obb2) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_obb_fwd: null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool v = aligned16(b1) && aligned16(b2);
+    if (D == 4) k_obb_fwd<4><<<blocks_for(n), kThreads, 0, s>>>(kind, b1, b2, n, edge, obb1, obb2, v);
+    else k_obb_fwd<5><<<blocks_for(n), kThreads, 0, s>>>(kind, b1, b2, n, edge, obb1, obb2, v);
+    SPHK_LAUNCH_CHECK("k_obb_fwd");
+    return SPHK_OK;
+}
+
+int sphk_obb_bwd(int kind, const float* b1, const float* b2, int64_t n, int D, int edge, const float* grad_obb1,
+                 const float* grad_obb2, float* grad_b1, float* grad_b2, void* stream) {
+    if (n < 0 || (D != 4 && D != 5)) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_obb_bwd: n < 0 or D not in {4,5}");
+    if (kind != SPHK_KIND_SPH2POB_EFFICIENT && kind != SPHK_KIND_SPH2POB_STANDARD)
+        return fail(SPHK_ERR_UNSUPPORTED, "sphk_obb_bwd: kind must be a Sph2Pob transform");
+    if (edge < 0 || edge > 2) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_obb_bwd: unknown edge");
+    if (n == 0) return SPHK_OK;
+    if (!b1 || !b2) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_obb_bwd: null box pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool v = aligned16(b1) && aligned16(b2) && (!grad_b1 || aligned16(grad_b1)) && (!grad_b2 || aligned16(grad_b2));
+    if (D == 4) k_obb_bwd<4><<<blocks_for(n), kThreads, 0, s>>>(kind, b1, b2, n, edge, grad_obb1, grad_obb2, grad_b1, grad_b2, v);
+    else k_obb_bwd<5><<<blocks_for(n), kThreads, 0, s>>>(kind, b1, b2, n, edge, grad_obb1, grad_obb2, grad_b1, grad_b2, v);
+    SPHK_LAUNCH_CHECK("k_obb_bwd");
+    return SPHK_OK;
+}
+
+int sphk_riou_fwd_bwd(const float* obb1, const float* obb2, int64_t n, float* iou, const float* grad_iou,
+                      float* grad_obb1, float* grad_obb2, void* stream) {
+    if (n < 0) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_riou_fwd_bwd: n < 0");
+    if (n == 0) return SPHK_OK;
+    if (!obb1 || !obb2) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_riou_fwd_bwd: null OBB pointer");
+    k_riou_fwd_bwd<<<blocks_for(n), kThreads, 0, (cudaStream_t)stream>>>(obb1, obb2, n, iou, grad_iou, grad_obb1, grad_obb2);
+    SPHK_LAUNCH_CHECK("k_riou_fwd_bwd");
+    return SPHK_OK;
+}
+
+int sphk_nms_batched(const float* boxes, const int32_t* order, const int32_t* seg_offsets, int32_t S, int32_t max_seg_len,
+                     int D, float iou_threshold, uint8_t* keep, void* stream) {
+    if (S < 0 || max_seg_len < 0 || (D != 4 && D != 5)) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_nms_batched: bad S, max_seg_len or D");
+    if (S == 0 || max_seg_len == 0) return SPHK_OK;
+    if (!boxes || !order || !seg_offsets || !keep) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_nms_batched: null pointer");
+    const int max_words = (max_seg_len + 31) / 32;
+    const size_t smem = (size_t)max_words * 33u * sizeof(uint32_t);
+    if (smem > 200u * 1024u) return fail(SPHK_ERR_UNSUPPORTED, "sphk_nms_batched: segment longer than 49,000 boxes");
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool v = aligned16(boxes);
+    cudaError_t e;
+    if (D == 4) {
+        e = cudaFuncSetAttribute(k_nms<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_nms)");
+        k_nms<4><<<S, kThreads, smem, s>>>(boxes, order, seg_offsets, iou_threshold, keep, max_words, v);
+    } else {
+        e = cudaFuncSetAttribute(k_nms<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_nms)");
+        k_nms<5><<<S, kThreads, smem, s>>>(boxes, order, seg_offsets, iou_threshold, keep, max_words, v);
+    }
+    SPHK_LAUNCH_CHECK("k_nms");
+    return SPHK_OK;
+}
+
+int sphk_probe_fp32(int32_t blocks, int32_t iters, float* sink, void* stream) {
+    if (blocks <= 0 || iters <= 0 || !sink) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_probe_fp32: bad arguments");
+    k_probe_fp32<<<blocks, kThreads, 0, (cudaStream_t)stream>>>(iters, sink);
+    SPHK_LAUNCH_CHECK("k_probe_fp32");
+    return SPHK_OK;
+}
+
+int sphk_set_dense(int on) {
+    const int prev = g_dense;
+    g_dense = on ? 1 : 0;
+    return prev;
+}
+
+}  // extern "C"

@@ -1,0 +1,532 @@
+// sphk_math.cuh -- per-pair arithmetic of the spherical-box IoU hot path (fp32).
+//
+// One box pair is processed entirely in registers:
+//   jitter_1 -> Sph2Pob transform (efficient | standard) -> jitter_2 -> rotated-box IoU
+// following the reference semantics
+//   sphdet/iou/sph_iou_api.py:48-86,222-260      (pair pipeline + both jitters)
+//   sphdet/iou/sph2pob_efficient.py:9-73         (efficient transform)
+//   sphdet/iou/sph2pob_standard.py:8-80          (standard transform, used by the loss)
+//   sphdet/iou/diff_iou_rotated.py:325-343       (rotated IoU = area(A n B) / union)
+//   sphdet/iou/approximate_ious.py:3-55          (Sph-IoU / FoV-IoU)
+//
+// It is NOT a transcription of those files.  The reference builds 3-D vectors, a
+// cross product and acos() of normalised dot products, which is ill-conditioned in
+// fp32 for near-coincident boxes (its own fp32 run is off by up to 4e-3 from its
+// fp64 run there, tests/golden).  Here the same quantities are obtained from
+// closed forms in the angle differences (haversine arc, tangent-plane bearings)
+// and the intersection area from a branch-free boundary integral, so that the fp32
+// kernel tracks the float64 run of the reference to ~1e-6.  DESIGN.md derives the
+// identities.
+//
+// The header compiles with nvcc (device) and with g++ (tests/hostsim, a CPU build of
+// the very same arithmetic used only by the no-GPU unit tests).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SPHK_HD __host__ __device__ __forceinline__
+#else
+#define SPHK_HD inline
+#endif
+
+namespace sphk {
+
+// ---- enums shared with the C ABI (include/sphk.h) -------------------------------------
+enum Kind { KIND_SPH2POB_EFFICIENT = 0, KIND_SPH2POB_STANDARD = 1, KIND_SPH = 2, KIND_FOV = 3 };
+enum Mode { MODE_IOU = 0, MODE_IOF = 1 };
+enum Edge { EDGE_ARC = 0, EDGE_CHORD = 1, EDGE_TANGENT = 2 };
+
+// ---- reference constants (python doubles rounded to fp32 exactly as torch does) -------
+#define SPHK_EPS_D (1e-4 * 1.2345678)   // sph_iou_api.py:223,245
+#define SPHK_EPSA_D (1e-3 * 1.2345678)  // sph_iou_api.py:232
+#define SPHK_PI_D 3.14159265358979323846
+constexpr float kEps = (float)SPHK_EPS_D;
+constexpr float kEps2 = (float)(2 * SPHK_EPS_D);
+constexpr float kEps3 = (float)(3 * SPHK_EPS_D);
+constexpr float kEps5 = (float)(5 * SPHK_EPS_D);
+constexpr float kEpsA = (float)SPHK_EPSA_D;
+constexpr float kEpsA2 = (float)(2 * SPHK_EPSA_D);
+constexpr float kPi = (float)SPHK_PI_D;
+constexpr float kHalfPi = (float)(SPHK_PI_D / 2);
+constexpr float kTwoPi = (float)(2 * SPHK_PI_D);
+constexpr float kDeg2Rad = (float)(SPHK_PI_D / 180.0);
+// acos(clamp(x, -1+1e-7, 1-1e-7)) can never leave [kAcosLo, pi-kAcosLo]
+// (sph2pob_efficient.py:205).  Value of the float64 run: acos(1-1e-7) = 4.47213602e-4.
+constexpr float kAcosLo = 4.47213602e-4f;
+constexpr float kAcosHi = (float)(SPHK_PI_D - 4.47213602e-4);
+// jitter_2 clamps (sph_iou_api.py:237-240)
+constexpr float kMinWh1 = (float)(2 * SPHK_EPSA_D / 10);
+constexpr float kMinWh2 = (float)(SPHK_EPSA_D / 10);
+constexpr float kA1Lo = (float)(-2 * SPHK_PI_D + 2 * SPHK_EPSA_D);
+constexpr float kA1Hi = (float)(2 * SPHK_PI_D - SPHK_EPSA_D);
+constexpr float kA2Lo = (float)(-2 * SPHK_PI_D + SPHK_EPSA_D);
+constexpr float kA2Hi = (float)(2 * SPHK_PI_D - 2 * SPHK_EPSA_D);
+
+SPHK_HD float fmin2(float a, float b) { return fminf(a, b); }
+SPHK_HD float fmax2(float a, float b) { return fmaxf(a, b); }
+SPHK_HD float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+
+// ---- raw box and its jittered, role-specific form -------------------------------------
+struct RawBox {
+    float t, p, a, b, g;  // theta, phi, alpha, beta, gamma in degrees (g = 0 for BFoV)
+};
+
+// A jittered coordinate is kept as hi + lo (hi: the fp32 input or a range end, lo: the
+// jitter offset) so that the angle DIFFERENCES of near-identical boxes stay exact
+// (fl(300 - 2eps) alone is already off by 8% of the 3eps separation jitter_1 creates).
+struct JitBox {
+    float t_hi, t_lo, p_hi, p_lo;  // degrees
+    float a, b, g;                 // degrees
+    uint32_t pass;                 // bit k: column k not clamped (gradient passes)
+};
+
+// sph_iou_api.py:246-247: similar_mask = any_k |b1[k]-b2[k]| < eps over all D columns
+SPHK_HD bool jitter1_mask(const RawBox& x, const RawBox& y, int D) {
+    bool m = (fabsf(x.t - y.t) < kEps) | (fabsf(x.p - y.p) < kEps) | (fabsf(x.a - y.a) < kEps) |
+             (fabsf(x.b - y.b) < kEps);
+    if (D == 5) m = m | (fabsf(x.g - y.g) < kEps);
+    return m;
+}
+
+// one coordinate: value = raw + shift, clamped to [lo_end + lo_off, hi_end + hi_off]
+// (the bounds are "range end + small offset" so they are carried exactly too).
+SPHK_HD void jit_coord(float raw, float shift, float lo_off, float hi_end, float hi_off, float& hi, float& lo,
+                       bool& pass) {
+    const bool below = (raw + shift) < lo_off;                // lower range end is 0
+    const bool above = ((raw - hi_end) + shift) > hi_off;     // raw - hi_end is exact near the end
+    hi = below ? 0.0f : (above ? hi_end : raw);
+    lo = below ? lo_off : (above ? hi_off : shift);
+    pass = !(below | above);
+}
+
+// sph_iou_api.py:249-258, role of bboxes1 (rows / gt / pred / NMS pivot)
+SPHK_HD JitBox jitter1_role1(const RawBox& x, bool m, int D) {
+    const float s = m ? -kEps2 : 0.0f;
+    JitBox o;
+    bool p0, p1, p2, p3;
+    float ah, al, bh, bl;
+    jit_coord(x.t, s, kEps2, 360.0f, -kEps, o.t_hi, o.t_lo, p0);
+    jit_coord(x.p, s, kEps2, 180.0f, -kEps, o.p_hi, o.p_lo, p1);
+    jit_coord(x.a, s, kEps2, 180.0f, -kEps, ah, al, p2);
+    jit_coord(x.b, s, kEps2, 180.0f, -kEps, bh, bl, p3);
+    o.a = ah + al;
+    o.b = bh + bl;
+    o.g = (D == 5) ? x.g + s : 0.0f;  // bboxes1's gamma is never clamped (:256-258)
+    o.pass = (uint32_t)p0 | ((uint32_t)p1 << 1) | ((uint32_t)p2 << 2) | ((uint32_t)p3 << 3) | (1u << 4);
+    return o;
+}
+
+// role of bboxes2 (cols / anchors / target / NMS candidates)
+SPHK_HD JitBox jitter1_role2(const RawBox& x, bool m, int D) {
+    const float s = m ? kEps : 0.0f;
+    JitBox o;
+    bool p0, p1, p2, p3, p4 = true;
+    float ah, al, bh, bl;
+    jit_coord(x.t, s, kEps, 360.0f, -kEps2, o.t_hi, o.t_lo, p0);
+    jit_coord(x.p, s, kEps, 180.0f, -kEps2, o.p_hi, o.p_lo, p1);
+    jit_coord(x.a, s, kEps, 180.0f, -kEps2, ah, al, p2);
+    jit_coord(x.b, s, kEps, 180.0f, -kEps2, bh, bl, p3);
+    o.a = ah + al;
+    o.b = bh + bl;
+    o.g = 0.0f;
+    if (D == 5) {
+        // clamped twice: net [-360+2eps, 360-2eps]
+        const float v = x.g + s;
+        const bool below = v < (-360.0f + kEps2), above = ((x.g - 360.0f) + s) > -kEps2;
+        o.g = below ? (float)(-360.0 + 2 * SPHK_EPS_D) : (above ? (float)(360.0 - 2 * SPHK_EPS_D) : v);
+        p4 = !(below | above);
+    }
+    o.pass = (uint32_t)p0 | ((uint32_t)p1 << 1) | ((uint32_t)p2 << 2) | ((uint32_t)p3 << 3) | ((uint32_t)p4 << 4);
+    return o;
+}
+
+// ---- planar oriented box pair (what the transform hands to the rotated IoU) ----------
+struct ObbPair {
+    float x1, y1, w1, h1, a1;
+    float x2, y2, w2, h2, a2;
+};
+
+// Spherical part shared by both transforms.  With g = box 1 centre, p = box 2 centre,
+// (d, e) = (south, east) unit tangents, dth = theta_p - theta_g, dph = phi_p - phi_g:
+//   hav   = sin^2(arc/2) = sin^2(dph/2) + sin(phi_g) sin(phi_p) sin^2(dth/2)
+//   p.e_g = sin(phi_p) sin(dth)              p.d_g =  sin(dph) - 2 cos(phi_g) sin(phi_p) sin^2(dth/2)
+//   g.e_p = -sin(phi_g) sin(dth)             g.d_p = -sin(dph) - 2 cos(phi_p) sin(phi_g) sin^2(dth/2)
+// and the reference's signed internal angles are (sph2pob_efficient.py:81-97 rewritten
+// in the tangent basis; z = g x p normalised):
+//   a_g = atan2( p.d_g, -p.e_g )             a_p = atan2( -g.d_p,  g.e_p )
+struct SphGeom {
+    float hav;             // sin^2(arc/2), unclamped
+    float ng, mg, np, mp;  // a_g = atan2(ng, mg), a_p = atan2(np, mp)   (|.| ~ sin(arc))
+    float s1, c1, s2, c2;  // sin/cos phi of both boxes
+    float sdt, cdt;        // sin/cos(dth/2)
+    float sdp, cdp;        // sin/cos(dph/2)
+};
+
+SPHK_HD void sincos_f(float x, float* s, float* c) {
+#if defined(__CUDA_ARCH__)
+    sincosf(x, s, c);
+#else
+    *s = sinf(x);
+    *c = cosf(x);
+#endif
+}
+
+// sin/cos of an angle given in DEGREES as hi + lo.  The range reduction to [-45,45] happens in
+// degrees, where it is exact in fp32 (hi - 90k loses no bits), so sin AND cos keep full relative
+// accuracy next to every multiple of 90 degrees -- which radians-based sincosf cannot deliver
+// (fl(pi/2) is already 4e-8 off) and which near-antipodal / near-equator pairs need.
+// Kernels on [-pi/4, pi/4]: single-precision minimax polynomials (cephes sinf/cosf), ~1 ulp.
+SPHK_HD void sincos_deg(float hi, float lo, float* s, float* c) {
+    const float k = rintf(hi * (1.0f / 90.0f));
+    const float y = fmaf(-90.0f, k, hi) + lo;      // exact reduction, then the small offset
+    const float r = y * kDeg2Rad;
+    const float z = r * r;
+    const float ps = fmaf(fmaf(fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f), z, -1.6666654611e-1f) * z, r, r);
+    const float pc = fmaf(fmaf(fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f), z, 4.166664568298827e-2f),
+                          z * z, fmaf(-0.5f, z, 1.0f));
+    const int q = ((int)k) & 3;
+    const float a = (q & 1) ? pc : ps;             // |sin| source
+    const float b = (q & 1) ? ps : pc;             // |cos| source
+    *s = (q & 2) ? -a : a;
+    *c = ((q + 1) & 2) ? -b : b;
+}
+
+// planar edge length of a field-of-view angle (degrees in), sph2pob_efficient.py:100-108.
+// chord/tangent go through the degree-domain sincos so that 2 tan(alpha/2) stays accurate for
+// alpha -> 180 (oversize anchors are clamped to 180 - eps by jitter_1).
+SPHK_HD float edge_len_deg(float fov_deg, int edge) {
+    if (edge == EDGE_ARC) return fov_deg * kDeg2Rad;
+    float s, c;
+    sincos_deg(0.5f * fov_deg, 0.0f, &s, &c);
+    return edge == EDGE_CHORD ? 2.0f * s : 2.0f * s / c;
+}
+// d(edge length)/d(fov in radians)
+SPHK_HD float edge_len_grad_deg(float fov_deg, int edge) {
+    if (edge == EDGE_ARC) return 1.0f;
+    float s, c;
+    sincos_deg(0.5f * fov_deg, 0.0f, &s, &c);
+    return edge == EDGE_CHORD ? c : 1.0f / (c * c);
+}
+
+SPHK_HD SphGeom sph_geom(const JitBox& g, const JitBox& p) {
+    SphGeom q;
+    const float dth_hi = p.t_hi - g.t_hi, dth_lo = p.t_lo - g.t_lo;   // theta_p - theta_g (deg)
+    const float dph_hi = p.p_hi - g.p_hi, dph_lo = p.p_lo - g.p_lo;
+    sincos_deg(g.p_hi, g.p_lo, &q.s1, &q.c1);
+    sincos_deg(p.p_hi, p.p_lo, &q.s2, &q.c2);
+    sincos_deg(0.5f * dth_hi, 0.5f * dth_lo, &q.sdt, &q.cdt);
+    sincos_deg(0.5f * dph_hi, 0.5f * dph_lo, &q.sdp, &q.cdp);
+    const float hth = q.sdt * q.sdt;
+    const float sin_dth = 2.0f * q.sdt * q.cdt;
+    const float sin_dph = 2.0f * q.sdp * q.cdp;
+    q.hav = fmaf(q.s1 * q.s2, hth, q.sdp * q.sdp);
+    q.ng = fmaf(-2.0f * q.c1 * q.s2, hth, sin_dph);        //  p.d_g
+    q.mg = -q.s2 * sin_dth;                                // -p.e_g
+    q.np = fmaf(2.0f * q.c2 * q.s1, hth, sin_dph);         // -g.d_p
+    q.mp = -q.s1 * sin_dth;                                //  g.e_p
+    return q;
+}
+
+// |acos(clamp(.))| * sign with the reference's conventions: magnitude confined to
+// [kAcosLo, kAcosHi]; sign +1 iff the "numerator" is > 0, else -1 (zero -> -1,
+// sph2pob_efficient.py:224-225).
+SPHK_HD float signed_clamped_angle(float n, float m, bool* clamped) {
+    float mag = atan2f(fabsf(n), m);
+    if (n == 0.0f && m == 0.0f) mag = kHalfPi;  // z = 0: F.normalize gives 0 -> acos(0)
+    const float c = clampf(mag, kAcosLo, kAcosHi);
+    *clamped = (c != mag);
+    return n > 0.0f ? c : -c;
+}
+
+SPHK_HD float arc_from_hav(float hav) { return 2.0f * asinf(fminf(sqrtf(hav), 1.0f)); }
+
+struct XformAux {     // what the backward pass needs to know about active clamps
+    bool arc_clamped, ag_clamped, ap_clamped, degenerate;
+};
+
+// Sph2Pob-efficient: sph2pob_efficient.py:9-73 (rbb_angle='equator').
+SPHK_HD ObbPair sph2pob_efficient(const JitBox& g, const JitBox& p, int D, int edge, XformAux* aux) {
+    const SphGeom q = sph_geom(g, p);
+    ObbPair o;
+    const float arc = arc_from_hav(q.hav);
+    const float arc_c = clampf(arc, kAcosLo, kAcosHi);
+    aux->arc_clamped = (arc_c != arc);
+    aux->degenerate = false;
+    o.a1 = signed_clamped_angle(q.ng, q.mg, &aux->ag_clamped);
+    o.a2 = signed_clamped_angle(q.np, q.mp, &aux->ap_clamped);
+    if (D == 5) {  // :55-57  angle -= gamma (unwrapped)
+        o.a1 -= g.g * kDeg2Rad;
+        o.a2 -= p.g * kDeg2Rad;
+    }
+    o.x1 = 0.0f; o.y1 = 0.0f; o.x2 = arc_c; o.y2 = 0.0f;
+    o.w1 = edge_len_deg(g.a, edge); o.h1 = edge_len_deg(g.b, edge);
+    o.w2 = edge_len_deg(p.a, edge); o.h2 = edge_len_deg(p.b, edge);
+    return o;
+}
+
+// wrap to (-pi, pi]
+SPHK_HD float wrap_pi(float a) {
+    if (a > kPi) a -= kTwoPi;
+    if (a < -kPi) a += kTwoPi;
+    return a;
+}
+
+// Sph2Pob-standard: sph2pob_standard.py:8-80.  Geometrically the pair frame
+// (look, right, up) puts both centres on the equator at -/+ arc/2 and `up` equals the
+// efficient transform's z, so the same tangent-plane bearings apply; gamma rotates the
+// tangent BEFORE the clamped acos (sph2pob_standard.py:47-54), hence the wrap here.
+SPHK_HD ObbPair sph2pob_standard(const JitBox& g, const JitBox& p, int D, int edge, XformAux* aux) {
+    const SphGeom q = sph_geom(g, p);
+    ObbPair o;
+    const float half = asinf(fminf(sqrtf(q.hav), 1.0f));   // arc/2 in [0, pi/2]
+    const float half_c = fmaxf(half, kAcosLo);
+    aux->arc_clamped = (half_c != half);
+    // sph2pob_standard.py:291: centres closer than 1e-8 (L1) use the mid-angle frame instead
+    aux->degenerate = q.hav < 2.5e-17f;
+    float ag = atan2f(q.ng, q.mg), ap = atan2f(q.np, q.mp);
+    if (aux->degenerate) { ag = kHalfPi; ap = kHalfPi; }
+    if (D == 5) {
+        ag = wrap_pi(ag - g.g * kDeg2Rad);
+        ap = wrap_pi(ap - p.g * kDeg2Rad);
+    }
+    const float mg = clampf(fabsf(ag), kAcosLo, kAcosHi), mp = clampf(fabsf(ap), kAcosLo, kAcosHi);
+    aux->ag_clamped = (mg != fabsf(ag));
+    aux->ap_clamped = (mp != fabsf(ap));
+    o.a1 = ag > 0.0f ? mg : -mg;
+    o.a2 = ap > 0.0f ? mp : -mp;
+    o.x1 = -half_c; o.x2 = aux->degenerate ? -half_c : half_c;
+    o.y1 = kHalfPi; o.y2 = kHalfPi;
+    o.w1 = edge_len_deg(g.a, edge); o.h1 = edge_len_deg(g.b, edge);
+    o.w2 = edge_len_deg(p.a, edge); o.h2 = edge_len_deg(p.b, edge);
+    return o;
+}
+
+// sph_iou_api.py:222-242 (jiter_rotated_bboxes).  `pass` bits (for the backward): 0 w1, 1 h1,
+// 2 a1, 3 w2, 4 h2, 5 a2 -- set when the corresponding clamp is inactive.
+SPHK_HD uint32_t jitter2(ObbPair& o) {
+    const bool m = (fabsf(o.x1 - o.x2) < kEps) | (fabsf(o.w1 - o.w2) < kEps) | (fabsf(o.h1 - o.h2) < kEps) |
+                   (fabsf(o.a1 - o.a2) < kEps);
+    if (m) {
+        o.x1 += kEps;  o.y1 += kEps;  o.w1 += kEps2; o.h1 += kEps2; o.a1 += kEps;
+        o.x2 += kEps2; o.y2 += kEps2; o.w2 += kEps;  o.h2 += kEps;  o.a2 += kEps5;
+    }
+    if (fabsf(o.a1 - o.a2) < kEpsA) {
+        o.a1 += kEpsA;
+        o.a2 += kEpsA2;
+    }
+    uint32_t pass = 0;
+    pass |= (o.w1 >= kMinWh1) ? 1u : 0u;        pass |= (o.h1 >= kMinWh1) ? 2u : 0u;
+    pass |= (o.a1 >= kA1Lo && o.a1 <= kA1Hi) ? 4u : 0u;
+    pass |= (o.w2 >= kMinWh2) ? 8u : 0u;        pass |= (o.h2 >= kMinWh2) ? 16u : 0u;
+    pass |= (o.a2 >= kA2Lo && o.a2 <= kA2Hi) ? 32u : 0u;
+    o.w1 = fmaxf(o.w1, kMinWh1); o.h1 = fmaxf(o.h1, kMinWh1);
+    o.w2 = fmaxf(o.w2, kMinWh2); o.h2 = fmaxf(o.h2, kMinWh2);
+    o.a1 = clampf(o.a1, kA1Lo, kA1Hi);
+    o.a2 = clampf(o.a2, kA2Lo, kA2Hi);
+    return pass;
+}
+
+// ---- rotated-box intersection: boundary integral, no polygon is ever materialised -----
+//
+// area(A n B) = 1/2 * closed integral of (x - o) x dx over the boundary of A n B, which consists
+// of the parts of B's edges inside A plus the parts of A's sides inside B.  Everything is done
+// in the frame of box 1 (A = [-hw1,hw1] x [-hh1,hh1], o = its centre):
+//   * an edge of B is a segment P + t d, t in [0,1]; Liang-Barsky against A yields the inside
+//     interval [t0,t1] without branches; contribution 1/2 (t1-t0) P x d;
+//   * a side of A (say y = +hh1) is inside B between the largest lower and the smallest upper
+//     bound imposed by B's four edge lines -- and those bounds are the SAME crossing points
+//     P + t d already found for B's edges.  Sharing them is what keeps fp32 accurate for
+//     nearly parallel boxes: a crossing of two almost parallel lines is ill-conditioned along
+//     the lines (error ~ ulp / sin r) but as long as both incident boundary pieces use the
+//     identical point the area error stays O(ulp) (what a polygon clipper gets for free).
+// A division by zero cannot occur: sin/cos of the relative angle are nudged off exact 0.
+//
+// Corner order / rotation convention = diff_iou_rotated.py:297-322 (CCW by the angle,
+// mmcv's clockwise=True in image coordinates).
+struct EdgeClip {
+    float t0[4], t1[4];  // edges of box 2 (order: +v side, -u side, -v side, +u side), parameter interval
+    float lo[4], hi[4];  // sides of box 1 (order: top y=+hh1, left x=-hw1, bottom, right): coordinate interval
+};
+
+SPHK_HD float rcp_f(float x) {
+#if defined(__CUDA_ARCH__)
+    return __frcp_rn(x);
+#else
+    return 1.0f / x;
+#endif
+}
+
+struct RiouGeom {  // everything the forward (and the backward) needs about one OBB pair
+    float px, py;        // centre of box 2 in the frame of box 1
+    float cr, sr;        // cos/sin of r = a2 - a1
+    float c1, s1;        // cos/sin of a1
+};
+
+// one edge of box 2: start corner (Px,Py), direction (dx,dy) with reciprocals (ix,iy).
+// Returns the clipped parameter interval and the four line crossings with the sides of box 1.
+struct EdgeX {
+    float x_top, x_bot, y_left, y_right;
+};
+SPHK_HD EdgeX clip_edge(float Px, float Py, float dx, float dy, float ix, float iy, float hw, float hh, float* t0,
+                        float* t1) {
+    const float txm = (-hw - Px) * ix, txp = (hw - Px) * ix;
+    const float tym = (-hh - Py) * iy, typ = (hh - Py) * iy;
+    const float lo = fmaxf(fmaxf(fminf(txm, txp), fminf(tym, typ)), 0.0f);
+    const float hi = fminf(fminf(fmaxf(txm, txp), fmaxf(tym, typ)), 1.0f);
+    *t0 = lo;
+    *t1 = hi;
+    EdgeX e;
+    e.x_top = fmaf(typ, dx, Px);
+    e.x_bot = fmaf(tym, dx, Px);
+    e.y_left = fmaf(txm, dy, Py);
+    e.y_right = fmaf(txp, dy, Py);
+    return e;
+}
+
+SPHK_HD float riou_intersection(const ObbPair& o, RiouGeom* G, EdgeClip* E) {
+    float s1, c1, sr, cr;
+    sincos_f(o.a1, &s1, &c1);
+    sincos_f(o.a2 - o.a1, &sr, &cr);
+    sr = (sr == 0.0f) ? 1e-30f : sr;
+    cr = (cr == 0.0f) ? 1e-30f : cr;
+    const float dx = o.x2 - o.x1, dy = o.y2 - o.y1;
+    const float px = c1 * dx + s1 * dy, py = -s1 * dx + c1 * dy;      // R(-a1) (dx,dy)
+    G->px = px; G->py = py; G->cr = cr; G->sr = sr; G->c1 = c1; G->s1 = s1;
+    const float hw1 = 0.5f * o.w1, hh1 = 0.5f * o.h1, hw2 = 0.5f * o.w2, hh2 = 0.5f * o.h2;
+    const float icr = rcp_f(cr), isr = rcp_f(sr);
+    const float iw2 = rcp_f(o.w2), ih2 = rcp_f(o.h2);
+
+    // box 2 in frame 1: axes u = (cr, sr), v = (-sr, cr); corners CCW:
+    // c0 = p + hw2 u + hh2 v, c1 = p - hw2 u + hh2 v, c2 = p - hw2 u - hh2 v, c3 = p + hw2 u - hh2 v
+    const float ux = cr * hw2, uy = sr * hw2, vx = -sr * hh2, vy = cr * hh2;
+    const float c0x = px + ux + vx, c0y = py + uy + vy;
+    const float c1x = px - ux + vx, c1y = py - uy + vy;
+    const float c2x = px - ux - vx, c2y = py - uy - vy;
+    const float c3x = px + ux - vx, c3y = py + uy - vy;
+    // edge directions: e0 = -w2 u^ (from c0), e1 = -h2 v^ (from c1), e2 = +w2 u^ (from c2), e3 = +h2 v^ (from c3)
+    const float dux = o.w2 * cr, duy = o.w2 * sr;     // w2 u^
+    const float dvx = -o.h2 * sr, dvy = o.h2 * cr;    // h2 v^
+    const float iux = icr * iw2, iuy = isr * iw2;     // 1/dux, 1/duy
+    const float ivx = -isr * ih2, ivy = icr * ih2;    // 1/dvx, 1/dvy
+    const EdgeX x0 = clip_edge(c0x, c0y, -dux, -duy, -iux, -iuy, hw1, hh1, &E->t0[0], &E->t1[0]);
+    const EdgeX x1 = clip_edge(c1x, c1y, -dvx, -dvy, -ivx, -ivy, hw1, hh1, &E->t0[1], &E->t1[1]);
+    const EdgeX x2 = clip_edge(c2x, c2y, dux, duy, iux, iuy, hw1, hh1, &E->t0[2], &E->t1[2]);
+    const EdgeX x3 = clip_edge(c3x, c3y, dvx, dvy, ivx, ivy, hw1, hh1, &E->t0[3], &E->t1[3]);
+    // P x d of a CCW edge = |d| * (signed distance from o to the edge line along the outward
+    // normal); p.u^ = pxv, p.v^ = -pxu
+    const float pxu = px * sr - py * cr;
+    const float pxv = px * cr + py * sr;
+    const float k0 = o.w2 * (hh2 - pxu);   // edge on the +v side
+    const float k1 = o.h2 * (hw2 - pxv);   // edge on the -u side
+    const float k2 = o.w2 * (hh2 + pxu);   // edge on the -v side
+    const float k3 = o.h2 * (hw2 + pxv);   // edge on the +u side
+    float area2 = 0.0f;  // twice the area
+    area2 = fmaf(fmaxf(E->t1[0] - E->t0[0], 0.0f), k0, area2);
+    area2 = fmaf(fmaxf(E->t1[1] - E->t0[1], 0.0f), k1, area2);
+    area2 = fmaf(fmaxf(E->t1[2] - E->t0[2], 0.0f), k2, area2);
+    area2 = fmaf(fmaxf(E->t1[3] - E->t0[3], 0.0f), k3, area2);
+
+    // sides of box 1.  "inside B" = left of every CCW edge line of B:  d.x (Y - Py) - d.y (X - Px) >= 0.
+    // On a horizontal side (coordinate X) an edge with d.y > 0 gives an upper bound, d.y < 0 a lower one;
+    // on a vertical side (coordinate Y) d.x > 0 gives a lower bound, d.x < 0 an upper one.
+    // e0/e2 have opposite directions, and so have e1/e3: one of each pair bounds from above.
+    const bool up_pos = duy > 0.0f;   // e2 (d = +w2 u^) has d.y > 0
+    const bool vp_pos = dvy > 0.0f;   // e3 (d = +h2 v^) has d.y > 0
+    const bool ux_pos = dux > 0.0f;   // e2 has d.x > 0
+    const bool vx_pos = dvx > 0.0f;   // e3 has d.x > 0
+    {   // top: y = +hh1
+        const float ub = fminf(up_pos ? x2.x_top : x0.x_top, vp_pos ? x3.x_top : x1.x_top);
+        const float lb = fmaxf(up_pos ? x0.x_top : x2.x_top, vp_pos ? x1.x_top : x3.x_top);
+        E->lo[0] = fmaxf(lb, -hw1); E->hi[0] = fminf(ub, hw1);
+    }
+    {   // bottom: y = -hh1
+        const float ub = fminf(up_pos ? x2.x_bot : x0.x_bot, vp_pos ? x3.x_bot : x1.x_bot);
+        const float lb = fmaxf(up_pos ? x0.x_bot : x2.x_bot, vp_pos ? x1.x_bot : x3.x_bot);
+        E->lo[2] = fmaxf(lb, -hw1); E->hi[2] = fminf(ub, hw1);
+    }
+    {   // left: x = -hw1
+        const float lb = fmaxf(ux_pos ? x2.y_left : x0.y_left, vx_pos ? x3.y_left : x1.y_left);
+        const float ub = fminf(ux_pos ? x0.y_left : x2.y_left, vx_pos ? x1.y_left : x3.y_left);
+        E->lo[1] = fmaxf(lb, -hh1); E->hi[1] = fminf(ub, hh1);
+    }
+    {   // right: x = +hw1
+        const float lb = fmaxf(ux_pos ? x2.y_right : x0.y_right, vx_pos ? x3.y_right : x1.y_right);
+        const float ub = fminf(ux_pos ? x0.y_right : x2.y_right, vx_pos ? x1.y_right : x3.y_right);
+        E->lo[3] = fmaxf(lb, -hh1); E->hi[3] = fminf(ub, hh1);
+    }
+    const float lh = fmaxf(E->hi[0] - E->lo[0], 0.0f) + fmaxf(E->hi[2] - E->lo[2], 0.0f);  // horizontal sides
+    const float lv = fmaxf(E->hi[1] - E->lo[1], 0.0f) + fmaxf(E->hi[3] - E->lo[3], 0.0f);  // vertical sides
+    area2 = fmaf(lh, hh1, area2);
+    area2 = fmaf(lv, hw1, area2);
+    return 0.5f * area2;
+}
+
+// IoU / IoF of an oriented box pair + the final clamp(0,1) of sph_iou_api.py:86.
+SPHK_HD float riou_value(const ObbPair& o, int mode) {
+    RiouGeom G;
+    EdgeClip E;
+    const float A1 = o.w1 * o.h1, A2 = o.w2 * o.h2;
+    float I = riou_intersection(o, &G, &E);
+    I = fminf(fmaxf(I, 0.0f), fminf(A1, A2));
+    if (!(I == I)) I = 0.0f;
+    const float den = (mode == MODE_IOF) ? A1 : (A1 + A2 - I);
+    return clampf(I / den, 0.0f, 1.0f);
+}
+
+// Cheap, conservative disjointness test on the jittered OBBs: centres further apart than
+// the sum of the circumradii -> intersection is exactly 0 in the reference too
+// (both mmcv's kernel and diff_iou_rotated return 0 for disjoint rectangles).
+SPHK_HD bool obb_disjoint(const ObbPair& o) {
+    const float dx = o.x2 - o.x1, dy = o.y2 - o.y1;
+    const float r1 = o.w1 * o.w1 + o.h1 * o.h1, r2 = o.w2 * o.w2 + o.h2 * o.h2;
+    // (|c| > (sqrt(r1)+sqrt(r2))/2)  with a 1e-5 relative safety margin
+    const float rs = 0.5f * (sqrtf(r1) + sqrtf(r2));
+    return (dx * dx + dy * dy) > rs * rs * 1.00002f;
+}
+
+// ---- full Sph2Pob IoU of one pair ------------------------------------------------------
+SPHK_HD float sph2pob_iou_pair(const RawBox& b1, const RawBox& b2, int D, int kind, int mode, int edge,
+                               bool dense = false) {
+    const bool m = jitter1_mask(b1, b2, D);
+    const JitBox g = jitter1_role1(b1, m, D), p = jitter1_role2(b2, m, D);
+    XformAux aux;
+    ObbPair o = (kind == KIND_SPH2POB_STANDARD) ? sph2pob_standard(g, p, D, edge, &aux)
+                                                : sph2pob_efficient(g, p, D, edge, &aux);
+    jitter2(o);
+    if (!dense && obb_disjoint(o)) return 0.0f;   // dense: measurement only (sphk_set_dense)
+    return riou_value(o, mode);
+}
+
+// ---- Sph-IoU / FoV-IoU (approximate_ious.py:3-55 behind sph_iou_api.py:130-177) -------
+SPHK_HD float approx_iou_pair(const RawBox& b1, const RawBox& b2, int kind) {
+    const bool m = jitter1_mask(b1, b2, 4);
+    const JitBox g = jitter1_role1(b1, m, 4), p = jitter1_role2(b2, m, 4);
+    const float dlo = p.t_lo - g.t_lo;
+    float dt = (p.t_hi - g.t_hi) + dlo;                     // theta_p - theta_g, exact for close boxes
+    // approximate_ious.py:60-81: where |dtheta| > 180 both thetas become (theta+180) mod 360,
+    // i.e. the difference moves by -/+360.  (360 - hi) is exact, so the small result is too.
+    if (dt > 180.0f) dt = -(g.t_hi + (360.0f - p.t_hi)) + dlo;
+    else if (dt < -180.0f) dt = (p.t_hi + (360.0f - g.t_hi)) + dlo;
+    const float pg = kHalfPi - (g.p_hi + g.p_lo) * kDeg2Rad, pp = kHalfPi - (p.p_hi + p.p_lo) * kDeg2Rad;
+    const float dphi = -((p.p_hi - g.p_hi) + (p.p_lo - g.p_lo)) * kDeg2Rad;   // pp - pg
+    const float ag = g.a * kDeg2Rad, bg = g.b * kDeg2Rad, ap = p.a * kDeg2Rad, bp = p.b * kDeg2Rad;
+    const float dtr = dt * kDeg2Rad;
+    // overlaps are translation invariant: measure everything relative to box 1's centre
+    float lo, hi;
+    if (kind == KIND_SPH) {
+        lo = fmaxf(-0.5f * ag, dtr - 0.5f * ap);
+        hi = fminf(0.5f * ag, dtr + 0.5f * ap);
+    } else {
+        const float delta = dtr * cosf(0.5f * (pg + pp));
+        lo = fmaxf(-0.5f * ag, delta - 0.5f * ap);
+        hi = fminf(0.5f * ag, delta + 0.5f * ap);
+    }
+    const float plo = fmaxf(-0.5f * bg, dphi - 0.5f * bp);
+    const float phi = fminf(0.5f * bg, dphi + 0.5f * bp);
+    const float inter = fmaxf(hi - lo, 0.0f) * fmaxf(phi - plo, 0.0f);
+    const float iou = inter / (ag * bg + ap * bp - inter + 1e-8f);
+    return clampf(iou, 0.0f, 1.0f);
+}
+
+}  // namespace sphk

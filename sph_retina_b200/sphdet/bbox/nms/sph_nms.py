@@ -1,0 +1,104 @@
+"""Spherical NMS with the reference's interface (sphdet/bbox/nms/sph_nms.py:7-74).
+
+The reference runs a Python ``while`` loop per class with one IoU-API call and a ``nonzero`` host
+sync per kept box.  Here all (image, class) segments go through ONE kernel launch
+(``sphk_nms_batched``: warp-ballot suppression words + in-warp greedy scan); the host side only
+sorts and slices."""
+from __future__ import annotations
+
+import torch
+
+from .... import _native
+
+
+def _segments(scores, seg_ids):
+    """order (score-descending inside a segment, segments by ascending id), offsets, longest segment."""
+    order = torch.argsort(scores, descending=True, stable=True)
+    order = order[torch.argsort(seg_ids[order], stable=True)]
+    _, counts = torch.unique_consecutive(seg_ids[order], return_counts=True)
+    offsets = torch.zeros(counts.numel() + 1, dtype=torch.int32, device=scores.device)
+    offsets[1:] = counts.cumsum(0)
+    return order, offsets, int(counts.max().item())
+
+
+def _keep_indices(boxes, scores, seg_ids, iou_threshold):
+    """Indices (into boxes) that survive the per-segment greedy NMS, unordered."""
+    order, offsets, longest = _segments(scores, seg_ids)
+    flags = _native.nms_batched(boxes, order, offsets, longest, iou_threshold)
+    if bool((flags == 0xFF).any()):
+        raise _native.SphkError("sphk_nms_batched refused a segment (max_seg_len too small)")
+    return order[flags.bool()]
+
+
+def sph_batched_nms(boxes, scores, idxs, nms_cfg, iou_calculator='sph2pob_efficient', class_agnostic=False):
+    """sph_nms.py:22-60.  Returns ``(dets[K, D+1], keep[K])``, kept boxes sorted by descending score."""
+    if nms_cfg is None:
+        raise ValueError("nms_cfg is None: the reference aborts the process here (sph_nms.py:24-29)")
+    nms_cfg_ = nms_cfg.copy()
+    # the reference pops these and never uses them (:33-37): NMS is ALWAYS per label
+    nms_cfg_.pop('class_agnostic', class_agnostic)
+    nms_cfg_.pop('type', 'nms')
+    nms_cfg_.pop('split_thr', 10000)
+    iou_threshold = nms_cfg_.pop('iou_threshold', 0.5)
+    max_num = min(nms_cfg_.pop('max_num', boxes.shape[0]), boxes.shape[0])
+    assert boxes.size(1) in [4, 5]
+    if boxes.size(0) == 0:
+        return torch.cat([boxes, scores[:, None]], -1), boxes.new_zeros((0,), dtype=torch.long)
+    keep = _keep_indices(boxes, scores, idxs, iou_threshold)
+    keep = keep.sort()[0]                                   # :49 nonzero() order
+    kept_scores, inds = scores[keep].sort(descending=True)  # :51
+    keep = keep[inds][:max_num]
+    dets = torch.cat([boxes[keep], kept_scores[:max_num, None]], -1)
+    return dets, keep
+
+
+def sph_batched_nms_images(boxes, scores, labels, image_ids, iou_threshold=0.5):
+    """Test-time batch: one launch over every (image, class) segment of a whole batch.
+    Returns the kept indices (into boxes), grouped by image and score-descending inside an image."""
+    num_labels = int(labels.max().item()) + 1 if labels.numel() else 1
+    seg = image_ids.long() * num_labels + labels.long()
+    keep = _keep_indices(boxes, scores, seg, iou_threshold)
+    keep = keep[torch.argsort(scores[keep], descending=True, stable=True)]
+    return keep[torch.argsort(image_ids[keep], stable=True)]
+
+
+class SphNMS:
+    """sph_nms.py:7-19.  ``iou_calculator`` other than 'sph2pob_efficient' select CPU/planar routines
+    of the reference that are outside this path: refused loudly."""
+
+    def __init__(self, iou_calculator='sph2pob_efficient'):
+        if iou_calculator == 'sph2pob_efficient':
+            self.iou_calculator = iou_calculator
+        elif iou_calculator in ('unbiased_iou', 'naive_iou'):
+            raise NotImplementedError("SphNMS(%r): no CUDA kernel on this path (and no fallback)" % iou_calculator)
+        else:
+            raise NotImplementedError('Not supported iou_calculator.')
+
+    def __call__(self, boxes, scores, idxs, nms_cfg, class_agnostic=False):
+        return sph_batched_nms(boxes, scores, idxs, nms_cfg, self.iou_calculator, class_agnostic)
+
+
+def multiclass_nms(multi_bboxes, multi_scores, score_thr, nms_cfg, max_num=-1, score_factors=None,
+                   return_inds=False, nms_op=None, box_version=4):
+    """sphdet/bbox/nms/utils.py:6-95 (R-CNN heads) with ``nms_op`` defaulting to :class:`SphNMS`."""
+    nms_op = SphNMS() if nms_op is None else nms_op
+    num_classes = multi_scores.size(1) - 1
+    if multi_bboxes.shape[1] > box_version:
+        bboxes = multi_bboxes.view(multi_scores.size(0), -1, box_version)
+    else:
+        bboxes = multi_bboxes[:, None].expand(multi_scores.size(0), num_classes, box_version)
+    scores = multi_scores[:, :-1]
+    labels = torch.arange(num_classes, dtype=torch.long, device=scores.device).view(1, -1).expand_as(scores)
+    bboxes, scores, labels = bboxes.reshape(-1, box_version), scores.reshape(-1), labels.reshape(-1)
+    valid_mask = scores > score_thr
+    if score_factors is not None:
+        scores = scores * score_factors.view(-1, 1).expand(multi_scores.size(0), num_classes).reshape(-1)
+    inds = valid_mask.nonzero(as_tuple=False).squeeze(1)
+    bboxes, scores, labels = bboxes[inds], scores[inds], labels[inds]
+    if bboxes.numel() == 0:
+        dets = torch.cat([bboxes, scores[:, None]], -1)
+        return (dets, labels, inds) if return_inds else (dets, labels)
+    dets, keep = nms_op(bboxes, scores, labels, nms_cfg)
+    if max_num > 0:
+        dets, keep = dets[:max_num], keep[:max_num]
+    return (dets, labels[keep], inds[keep]) if return_inds else (dets, labels[keep])

@@ -1,0 +1,66 @@
+"""IoU API with the reference's names and signatures (sphdet/iou/sph_iou_api.py:88-177).
+
+Each function is the whole reference pipeline -- pair expansion, jiter_spherical_bboxes, the
+Sph2Pob transform, jiter_rotated_bboxes, rotated-box IoU, view, clamp (sph_iou_api.py:48-86) --
+executed by ONE CUDA kernel launch (no expansion is materialised, no intermediate reaches HBM).
+Inputs are never modified (tests/test_all_ious.py:322-331)."""
+from __future__ import annotations
+
+import torch
+
+from ... import _native
+
+__all__ = ["sph2pob_standard_iou", "sph2pob_efficient_iou", "fov_iou", "sph_iou"]
+
+
+def _empty(bboxes1, rows, cols, is_aligned):
+    # sph_iou_api.py:56-57 returns an uninitialised tensor of this shape; zeros here
+    return bboxes1.new_zeros((rows, 1)) if is_aligned else bboxes1.new_zeros((rows, cols))
+
+
+def _run(kind, bboxes1, bboxes2, mode, is_aligned, edge):
+    rows, cols = bboxes1.size(0), bboxes2.size(0)
+    if rows * cols == 0:
+        return _empty(bboxes1, rows, cols, is_aligned)
+    with torch.no_grad():
+        if is_aligned:
+            assert rows == cols
+            out = _native.iou_aligned(kind, bboxes1, bboxes2, mode, edge)
+        else:
+            out = _native.iou_pairwise(kind, bboxes1, bboxes2, mode, edge)[0]
+    return out if out.dtype == bboxes1.dtype else out.to(bboxes1.dtype)
+
+
+def _sph2pob_iou(kind, bboxes1, bboxes2, mode, is_aligned, calculator, rbb_edge, rbb_angle):
+    # sph_iou_api.py:49-51
+    assert mode in ['iou', 'iof']
+    assert calculator in ['common', 'diff']
+    assert rbb_edge in ['arc', 'chord', 'tangent']
+    assert rbb_angle in ['equator', 'project']      # sph2pob_efficient.py:27
+    if rbb_angle == 'project':
+        raise NotImplementedError("rbb_angle='project' has no CUDA kernel yet (and no fallback): use 'equator'")
+    return _run(kind, bboxes1, bboxes2, mode, is_aligned, rbb_edge)
+
+
+def sph2pob_standard_iou(bboxes1, bboxes2, mode='iou', is_aligned=False, calculator='common', rbb_edge='arc',
+                         rbb_angle='equator'):
+    """sphdet/iou/sph_iou_api.py:94-95."""
+    return _sph2pob_iou("sph2pob_standard", bboxes1, bboxes2, mode, is_aligned, calculator, rbb_edge, rbb_angle)
+
+
+def sph2pob_efficient_iou(bboxes1, bboxes2, mode='iou', is_aligned=False, calculator='common', rbb_edge='arc',
+                          rbb_angle='equator'):
+    """sphdet/iou/sph_iou_api.py:97-98."""
+    return _sph2pob_iou("sph2pob_efficient", bboxes1, bboxes2, mode, is_aligned, calculator, rbb_edge, rbb_angle)
+
+
+def sph_iou(bboxes1, bboxes2, mode='iou', is_aligned=False, calculator='diff'):
+    """sphdet/iou/sph_iou_api.py:130-151 (+ approximate_ious.py:3-25).  BFoV only."""
+    assert mode in ['iou']
+    return _run("sph", bboxes1, bboxes2, mode, is_aligned, "arc")
+
+
+def fov_iou(bboxes1, bboxes2, mode='iou', is_aligned=False, calculator='diff'):
+    """sphdet/iou/sph_iou_api.py:156-177 (+ approximate_ious.py:28-55).  BFoV only."""
+    assert mode in ['iou']
+    return _run("fov", bboxes1, bboxes2, mode, is_aligned, "arc")

@@ -1,0 +1,225 @@
+"""Sph2Pob IoU losses with the reference's class names, constructor arguments and forward signature
+(sphdet/losses/sph2pob_iou_loss.py:16-58,199-296; sphdet/losses/sph2pob_transform.py:11-37).
+
+Reference dataflow: clone -> jiter_spherical_bboxes -> sph2pob_standard -> jiter_rotated_bboxes ->
+diff_iou_rotated_2d -> clamp -> 1 - iou [-> GIoU/DIoU/CIoU epilogue] -> weight_reduce_loss, all as
+eager autograd ops.  Here:
+  * mode 'iou': ONE kernel launch computes the IoU of every pair AND d(iou)/d(pred), d(iou)/d(target)
+    in registers (recompute-free: the backward pass only scales the stored per-row gradients by the
+    incoming d(loss)/d(iou));
+  * modes 'giou'/'diou'/'ciou': the OBBs come from sphk_obb_fwd (backward sphk_obb_bwd), the rotated
+    IoU from sphk_riou_fwd_bwd, and the cheap enclosing-box epilogue stays torch autograd on the OBBs
+    exactly as sph2pob_iou_loss.py:142-194."""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+from ... import _native
+from ..registry import LOSSES
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd bridges to the kernels
+# ------------------------------------------------------------------------------------------------
+class _Sph2PobIoU(torch.autograd.Function):
+    """iou[n] = clamp(rotated_iou(sph2pob_standard(jitter(pred, target)))) with analytic gradients."""
+
+    @staticmethod
+    def forward(ctx, pred, target):
+        need_p, need_t = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if need_p or need_t:
+            ones = torch.ones(pred.size(0), dtype=torch.float32, device=pred.device)
+            iou, gp, gt = _native.loss_fwd_bwd(pred.detach(), target.detach(), ones, need_p, need_t)
+            ctx.save_for_backward(*[g for g in (gp, gt) if g is not None])
+            ctx.have = (need_p, need_t)
+        else:
+            iou, _, _ = _native.loss_fwd_bwd(pred.detach(), target.detach())
+            ctx.have = (False, False)
+        ctx.in_dtypes = (pred.dtype, target.dtype)
+        return iou.to(pred.dtype)
+
+    @staticmethod
+    def backward(ctx, grad_iou):
+        saved = list(ctx.saved_tensors)
+        gp = saved.pop(0) if ctx.have[0] else None
+        gt = saved.pop(0) if ctx.have[1] else None
+        g = grad_iou.float().unsqueeze(1)
+        return (None if gp is None else (gp * g).to(ctx.in_dtypes[0]),
+                None if gt is None else (gt * g).to(ctx.in_dtypes[1]))
+
+
+class _Sph2PobObbs(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target, kind):
+        o1, o2 = _native.obb_fwd(kind, pred.detach(), target.detach())
+        ctx.save_for_backward(pred.detach(), target.detach())
+        ctx.kind = kind
+        ctx.in_dtypes = (pred.dtype, target.dtype)
+        return o1.to(pred.dtype), o2.to(pred.dtype)
+
+    @staticmethod
+    def backward(ctx, g1, g2):
+        pred, target = ctx.saved_tensors
+        gb1, gb2 = _native.obb_bwd(ctx.kind, pred, target, g1, g2, want1=ctx.needs_input_grad[0],
+                                   want2=ctx.needs_input_grad[1])
+        return (None if gb1 is None else gb1.to(ctx.in_dtypes[0]),
+                None if gb2 is None else gb2.to(ctx.in_dtypes[1]), None)
+
+
+class _RotatedIoU(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, o1, o2):
+        need1, need2 = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if need1 or need2:
+            ones = torch.ones(o1.size(0), dtype=torch.float32, device=o1.device)
+            iou, g1, g2 = _native.riou_fwd_bwd(o1.detach(), o2.detach(), ones, need1, need2)
+            ctx.save_for_backward(*[g for g in (g1, g2) if g is not None])
+        else:
+            iou, _, _ = _native.riou_fwd_bwd(o1.detach(), o2.detach())
+        ctx.have = (need1, need2)
+        ctx.in_dtype = o1.dtype
+        return iou.to(o1.dtype)
+
+    @staticmethod
+    def backward(ctx, grad_iou):
+        saved = list(ctx.saved_tensors)
+        g1 = saved.pop(0) if ctx.have[0] else None
+        g2 = saved.pop(0) if ctx.have[1] else None
+        g = grad_iou.float().unsqueeze(1)
+        return (None if g1 is None else (g1 * g).to(ctx.in_dtype), None if g2 is None else (g2 * g).to(ctx.in_dtype))
+
+
+def sph2pob_iou(pred, target):
+    """Differentiable clamped Sph2Pob-standard IoU of aligned spherical boxes [n, 4|5] (degrees)."""
+    return _Sph2PobIoU.apply(pred, target)
+
+
+def sph2pob_obbs(pred, target, transform='sph2pob_standard'):
+    """The planar OBBs (x, y, w, h, angle rad) after jitter -> transform -> jitter
+    (sph2pob_transform.py:26-30), differentiable."""
+    return _Sph2PobObbs.apply(pred, target, transform)
+
+
+def rotated_iou(obb1, obb2):
+    """Differentiable rotated-box IoU of aligned OBBs [n, 5] (diff_iou_rotated_2d semantics), clamped to [0, 1]."""
+    return _RotatedIoU.apply(obb1, obb2)
+
+
+# ------------------------------------------------------------------------------------------------
+# reduction: mmdet/models/losses/utils.py (weight_reduce_loss)
+# ------------------------------------------------------------------------------------------------
+def _weight_reduce_loss(loss, weight=None, reduction='mean', avg_factor=None):
+    if weight is not None:
+        loss = loss * weight
+    if avg_factor is None:
+        if reduction == 'mean':
+            return loss.mean()
+        if reduction == 'sum':
+            return loss.sum()
+        return loss
+    if reduction == 'mean':
+        return loss.sum() / (avg_factor + torch.finfo(torch.float32).eps)
+    if reduction != 'none':
+        raise ValueError('avg_factor can not be used with reduction="sum"')
+    return loss
+
+
+def _obb2hbb_xyxy(obb):
+    """sphdet/bbox/box_formator.py:34-54."""
+    w, h, a = obb[:, 2], obb[:, 3], obb[:, 4]
+    cosa, sina = torch.cos(a).abs(), torch.sin(a).abs()
+    hw, hh = (cosa * w + sina * h) / 2, (sina * w + cosa * h) / 2
+    return torch.stack((obb[:, 0] - hw, obb[:, 1] - hh, obb[:, 0] + hw, obb[:, 1] + hh), -1)
+
+
+def _obb_epilogue(ious, pred, target, mode, eps):
+    """sph2pob_iou_loss.py:142-194 on the transformed OBBs."""
+    hbb_pred, hbb_target = _obb2hbb_xyxy(pred), _obb2hbb_xyxy(target)
+    enclose_wh = (torch.max(hbb_pred[:, 2:], hbb_target[:, 2:]) -
+                  torch.min(hbb_pred[:, :2], hbb_target[:, :2])).clamp(min=0)
+    if mode == 'giou':
+        inter_wh = (torch.min(hbb_pred[:, 2:], hbb_target[:, 2:]) -
+                    torch.max(hbb_pred[:, :2], hbb_target[:, :2])).clamp(min=0)
+        area_enclose = enclose_wh[:, 0] * enclose_wh[:, 1]
+        area_union = pred[:, 2] * pred[:, 3] + target[:, 2] * target[:, 3] - inter_wh[:, 0] * inter_wh[:, 1]
+        area_ratio = (area_enclose - area_union) / (area_enclose + eps)
+        return 1 - (ious - area_ratio.clamp(min=0, max=1.0))
+    c2 = enclose_wh[:, 0] ** 2 + enclose_wh[:, 1] ** 2 + eps
+    rho2 = (target[:, 0] - pred[:, 0]) ** 2 + (target[:, 1] - pred[:, 1]) ** 2
+    if mode == 'diou':
+        return 1 - (ious - (rho2 / c2).clamp(min=0, max=1.0))
+    factor = 4 / math.pi ** 2
+    v = factor * torch.pow(torch.atan(target[:, 2] / (target[:, 3] + eps)) - torch.atan(pred[:, 2] / (pred[:, 3] + eps)), 2)
+    with torch.no_grad():
+        alpha = (ious > 0.5).float() * v / (1 - ious + v + eps)
+    if mode == 'ciou':
+        return 1 - (ious - ((rho2 / c2).clamp(min=0, max=1.0) + alpha * v))
+    raise NotImplementedError('Not supported version of iou-based loss.')
+
+
+def _elementwise_loss(pred, target, mode, eps, transform='sph2pob_standard'):
+    if mode == 'iou' and transform == 'sph2pob_standard':
+        return 1 - sph2pob_iou(pred, target)
+    o1, o2 = sph2pob_obbs(pred, target, transform)
+    ious = rotated_iou(o1, o2)
+    if mode == 'iou':
+        return 1 - ious
+    return _obb_epilogue(ious, o1, o2, mode, eps)
+
+
+class _SphLossBase(nn.Module):
+    _transform = 'sph2pob_standard'
+
+    def __init__(self, mode='iou', eps=1e-6, reduction='mean', loss_weight=1.0):
+        super().__init__()
+        assert mode in ['iou', 'giou', 'diou', 'ciou']
+        self.mode = mode
+        self.eps = eps
+        self.reduction = reduction
+        self.loss_weight = loss_weight
+
+    def forward(self, pred, target, weight=None, avg_factor=None, reduction_override=None, **kwargs):
+        box_version = target.size(-1)
+        # sph2pob_transform.py:32-34: a 2-D BFoV weight gains the column the OBB angle would use
+        if weight is not None and weight.dim() > 1 and box_version == 4:
+            weight = torch.cat([weight, weight.mean(-1, keepdim=True)], dim=-1)
+        # sph2pob_iou_loss.py:36-39: nothing positive -> a zero that still hangs off `pred`
+        if weight is not None and not torch.any(weight > 0):
+            return pred.sum() * 0
+        assert reduction_override in (None, 'none', 'mean', 'sum')
+        reduction = reduction_override if reduction_override else self.reduction
+        if weight is not None and weight.dim() > 1:
+            assert weight.shape == (pred.size(0), 5)    # :46 weight.shape == obb pred.shape
+            weight = weight.mean(-1)
+        loss = _elementwise_loss(pred, target, self.mode, self.eps, self._transform)
+        return self.loss_weight * _weight_reduce_loss(loss, weight, reduction, avg_factor)
+
+
+class OBBIoULoss(_SphLossBase):
+    """Name kept for parity with sph2pob_iou_loss.py:16; here it already includes the Sph2Pob transform
+    (the reference applies it through the ``Sph2PobTransfrom`` class decorator)."""
+
+
+@LOSSES.register_module()
+class Sph2PobIoULoss(_SphLossBase):
+    """sphdet/losses/sph2pob_iou_loss.py:220-236 -- ``Sph2PobTransfrom()(OBBIoULoss)``.
+
+    pred / target: spherical boxes [n, 4|5] in degrees; weight: None, [n] or [n, box_version]."""
+
+
+@LOSSES.register_module()
+class SphIoULoss(_SphLossBase):
+    """sphdet/losses/sph2pob_iou_loss.py:239-296.  The reference class is non-functional as shipped
+    (its calculator='diff' branch is dead code); this one computes what it was written to compute for
+    iou_calculator='sph2pob_standard', mode='iou'."""
+
+    def __init__(self, mode='iou', iou_calculator='sph2pob_standard', eps=1e-6, reduction='mean', loss_weight=1.0):
+        assert iou_calculator in ['sph2pob_standard', 'sph', 'fov']
+        if iou_calculator != 'sph2pob_standard':
+            raise NotImplementedError("SphIoULoss: only 'sph2pob_standard' is differentiable on this path")
+        if mode != 'iou':
+            raise NotImplementedError("SphIoULoss: the reference returns None for mode != 'iou'")
+        super().__init__(mode, eps, reduction, loss_weight)

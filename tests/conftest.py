@@ -1,0 +1,74 @@
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def load_golden(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+@pytest.fixture(scope="session")
+def golden():
+    return load_golden
+
+
+def _system_gxx():
+    for c in ("/usr/bin/g++", "g++"):
+        if os.path.isfile(c) or c == "g++":
+            return c
+
+
+@pytest.fixture(scope="session")
+def hostsim():
+    """g++ build of the DEVICE arithmetic headers (csrc/sphk_math.cuh, sphk_grad.cuh): lets the no-GPU
+    suite check the kernels' maths.  Test infrastructure only; the product never loads it."""
+    src = os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")
+    out_dir = os.path.join(ROOT, "tests", "hostsim", "_build")
+    out = os.path.join(out_dir, "libhostsim.so")
+    deps = [src] + [os.path.join(ROOT, "sph_retina_b200", "csrc", f) for f in ("sphk_math.cuh", "sphk_grad.cuh")]
+    if not os.path.isfile(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        os.makedirs(out_dir, exist_ok=True)
+        subprocess.check_call([_system_gxx(), "-O2", "-fPIC", "-shared", "-DSPHK_WITH_GRAD", "-ffp-contract=fast",
+                               "-mfma", "-o", out, src, "-lm"])
+    lib = ctypes.CDLL(out)
+    return lib
+
+
+@pytest.fixture(scope="session")
+def c_oracle():
+    """oracle/_build/libsph_oracle.so (float64 C restatement, OpenMP)."""
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_build", "libsph_oracle.so"))
+    return lib
+
+
+def within(kernel, truth64, ref32=None, tol=1e-5, slack=1.0):
+    """The parity criterion of SURVEY.md 8(c): |kernel - fp64 reference| <= tol, OR the kernel is at
+    least as close to the fp64 run as the reference's own fp32 run is on that element."""
+    err = np.abs(np.asarray(kernel, np.float64) - np.asarray(truth64, np.float64))
+    ok = err <= tol
+    if ref32 is not None:
+        ref_err = np.abs(np.asarray(ref32, np.float64) - np.asarray(truth64, np.float64))
+        ok |= err <= slack * ref_err
+    return ok, err
+
+
+def degenerate_pairs(b1, b2, min_fov_deg=0.06):
+    """Pairs with a (near) zero-size box: jitter_2 inflates it to a ~2.5e-4 rad square, and whether that
+    speck straddles the other box's edge is decided below fp32 resolution of the O(1) coordinates.
+    IoF of such a pair is ill-conditioned in ANY fp32 evaluation; these rows are checked at 1e-3."""
+    b1, b2 = np.asarray(b1), np.asarray(b2)
+    return (np.minimum(b1[:, 2:4].min(axis=1), b2[:, 2:4].min(axis=1)) < min_fov_deg)

@@ -1,0 +1,58 @@
+// TEST INFRASTRUCTURE ONLY.  A g++ build of sph_retina_b200/csrc/sphk_math.cuh so that the
+// no-GPU test-suite can check the *device arithmetic* (same source, host libm) against the
+// golden vectors.  The product package never loads this library: the product path is the CUDA
+// C-ABI library and fails loudly without a GPU.
+#include "../../sph_retina_b200/csrc/sphk_math.cuh"
+#ifdef SPHK_WITH_GRAD
+#include "../../sph_retina_b200/csrc/sphk_grad.cuh"
+#endif
+
+using namespace sphk;
+
+static inline RawBox load_box(const float* b, long i, int D) {
+    RawBox r;
+    r.t = b[i * D + 0]; r.p = b[i * D + 1]; r.a = b[i * D + 2]; r.b = b[i * D + 3];
+    r.g = (D == 5) ? b[i * D + 4] : 0.0f;
+    return r;
+}
+
+extern "C" {
+
+void hostsim_iou_aligned(int kind, const float* b1, const float* b2, long P, int D, int mode, int edge, float* out) {
+    for (long i = 0; i < P; ++i) {
+        const RawBox x = load_box(b1, i, D), y = load_box(b2, i, D);
+        out[i] = (kind == KIND_SPH || kind == KIND_FOV) ? approx_iou_pair(x, y, kind)
+                                                        : sph2pob_iou_pair(x, y, D, kind, mode, edge);
+    }
+}
+
+// OBBs after transform + both jitters: out [P,10] = (x1,y1,w1,h1,a1,x2,y2,w2,h2,a2)
+void hostsim_obbs(int kind, const float* b1, const float* b2, long P, int D, int edge, float* out) {
+    for (long i = 0; i < P; ++i) {
+        const RawBox x = load_box(b1, i, D), y = load_box(b2, i, D);
+        const bool m = jitter1_mask(x, y, D);
+        const JitBox g = jitter1_role1(x, m, D), p = jitter1_role2(y, m, D);
+        XformAux aux;
+        ObbPair o = (kind == KIND_SPH2POB_STANDARD) ? sph2pob_standard(g, p, D, edge, &aux)
+                                                    : sph2pob_efficient(g, p, D, edge, &aux);
+        jitter2(o);
+        float* r = out + i * 10;
+        r[0] = o.x1; r[1] = o.y1; r[2] = o.w1; r[3] = o.h1; r[4] = o.a1;
+        r[5] = o.x2; r[6] = o.y2; r[7] = o.w2; r[8] = o.h2; r[9] = o.a2;
+    }
+}
+
+#ifdef SPHK_WITH_GRAD
+// fused loss forward/backward (standard transform): iou[P], g1[P,D], g2[P,D] for upstream grad_iou[P]
+void hostsim_loss_fwd_bwd(const float* b1, const float* b2, const float* grad_iou, long P, int D, float* iou,
+                          float* g1, float* g2) {
+    for (long i = 0; i < P; ++i) {
+        const RawBox x = load_box(b1, i, D), y = load_box(b2, i, D);
+        float ga[5], gb[5];
+        iou[i] = sph2pob_iou_pair_grad(x, y, D, KIND_SPH2POB_STANDARD, EDGE_ARC, grad_iou[i], ga, gb);
+        for (int k = 0; k < D; ++k) { g1[i * D + k] = ga[k]; g2[i * D + k] = gb[k]; }
+    }
+}
+
+#endif
+}  // extern "C"

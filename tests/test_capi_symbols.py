@@ -1,0 +1,65 @@
+"""The C-ABI library loads on a machine without a GPU and exports every symbol include/sphk.h
+declares; the ctypes binding covers all of them.  No compute call is made here."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "sphk.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sphk_[a-z0-9_]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    from sph_retina_b200 import build
+    return build.build()
+
+
+def test_header_declares_the_expected_entry_points():
+    names = declared_symbols()
+    for must in ("sphk_iou_aligned", "sphk_iou_pairwise", "sphk_loss_fwd_bwd", "sphk_nms_batched", "sphk_obb_fwd",
+                 "sphk_obb_bwd", "sphk_riou_fwd_bwd", "sphk_last_error_string", "sphk_abi_version"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    lib = ctypes.CDLL(built_lib)
+    for name in declared_symbols():
+        assert hasattr(lib, name), "libsphk.so does not export %s" % name
+    lib.sphk_abi_version.restype = ctypes.c_int
+    assert lib.sphk_abi_version() == 1
+
+
+def test_binding_covers_the_header(built_lib):
+    from sph_retina_b200 import _native
+    assert sorted(_native.SIGNATURES) == declared_symbols()
+
+
+def test_argument_validation_needs_no_gpu(built_lib):
+    """Invalid arguments are rejected before any CUDA call, with a message."""
+    from sph_retina_b200 import _native
+    lib = _native.lib
+    assert lib.sphk_iou_aligned(0, None, None, 10, 3, 0, 0, None, None) == -1          # D = 3
+    assert b"D not in" in lib.sphk_last_error_string()
+    assert lib.sphk_iou_aligned(2, None, None, 10, 5, 0, 0, None, None) == -3          # sph_iou on RBFoV
+    assert lib.sphk_iou_aligned(7, None, None, 10, 4, 0, 0, None, None) == -1          # unknown kind
+    assert lib.sphk_iou_aligned(0, None, None, 0, 4, 0, 0, None, None) == 0            # empty is fine
+    assert lib.sphk_iou_pairwise_workspace_bytes(10, 20) == 240
+    assert lib.sphk_nms_batched(None, None, None, 0, 0, 4, 0.5, None, None) == 0
+    assert lib.sphk_loss_fwd_bwd(None, None, 5, 4, None, None, None, None, None) == -1  # null boxes
+
+
+def test_sass_is_sm100a(built_lib):
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.isfile(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-lelf", built_lib], capture_output=True, text=True).stdout
+    assert "sm_100a" in out

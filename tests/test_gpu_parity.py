@@ -1,0 +1,383 @@
+"""Parity of the CUDA path (Python API -> ctypes -> C ABI -> sm_100a kernels) against the golden
+vectors of the reference and against the oracle on seeded inputs.  Run on the B200: pytest -m gpu.
+
+Tolerances (BASELINE.json north_star): IoU 1e-5 absolute, gradients 1e-4 relative, NMS keep sets
+exact.  The reference's OWN fp32 run misses those against its fp64 run on part of the workload
+(SURVEY.md 8c), so an element passes if it is within tolerance of the fp64 reference OR at least as
+close to it as the fp32 reference is."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, degenerate_pairs, load_golden, within
+
+pytestmark = pytest.mark.gpu
+
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import sph_oracle as O  # noqa: E402  (the checker)
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def api():
+    import sph_retina_b200  # noqa: F401
+    from sph_retina_b200 import _native
+    from sph_retina_b200.sphdet import iou, losses
+    from sph_retina_b200.sphdet.bbox import nms
+    sm, major, minor = _native.device_info()
+    assert major >= 10, "these kernels are built for sm_100a only"
+    import types
+    return types.SimpleNamespace(native=_native, iou=iou, losses=losses, nms=nms)
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def c_oracle_aligned(lib, kind, b1, b2, mode=0, edge=0):
+    b1, b2 = np.ascontiguousarray(b1, np.float32), np.ascontiguousarray(b2, np.float32)
+    P, D = b1.shape
+    out = np.empty(P, np.float64)
+    fp, dp = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)
+    lib.sph_oracle_iou_aligned(kind, b1.ctypes.data_as(fp), b2.ctypes.data_as(fp), ctypes.c_long(P), D, mode, edge,
+                               out.ctypes.data_as(dp), None)
+    return out
+
+
+# ---- aligned -----------------------------------------------------------------------------------
+@pytest.mark.parametrize("box", ["bfov", "rbfov"])
+@pytest.mark.parametrize("tr", ["efficient", "standard"])
+def test_aligned_golden(api, box, tr):
+    g = load_golden("aligned_" + box)
+    b1, b2 = cu(g["b1"]), cu(g["b2"])
+    fn = getattr(api.iou, "sph2pob_%s_iou" % tr)
+    keep1, keep2 = b1.clone(), b2.clone()
+    for key, kw in (("iou", {}), ("iof", dict(mode="iof")), ("chord", dict(rbb_edge="chord")),
+                    ("tangent", dict(rbb_edge="tangent"))):
+        got = fn(b1, b2, is_aligned=True, **kw)
+        assert got.shape == (len(g["b1"]),) and got.dtype == torch.float32 and got.device == b1.device
+        got = got.cpu().numpy()
+        ok, err = within(got, g["%s_%s_f64" % (tr, key)], g["%s_%s_f32" % (tr, key)])
+        ok |= degenerate_pairs(g["b1"], g["b2"]) & (err < 1e-3)
+        assert ok.all(), (box, tr, key, np.where(~ok)[0], err[~ok])
+        assert (err > 1e-5).sum() <= 2 and np.median(err) < 2e-7
+        assert got.min() >= 0.0 and got.max() <= 1.0
+    assert torch.equal(b1, keep1) and torch.equal(b2, keep2)        # tests/test_all_ious.py:322-331
+
+
+def test_sph_fov_golden_and_known_answers(api):
+    g = load_golden("aligned_bfov")
+    b1, b2 = cu(g["b1"]), cu(g["b2"])
+    for k in ("sph", "fov"):
+        got = getattr(api.iou, k + "_iou")(b1, b2, is_aligned=True).cpu().numpy()
+        assert np.abs(got - g[k + "_f64"]).max() < 2e-6
+    g = load_golden("kat")
+    b1, b2 = cu(g["b1"]), cu(g["b2"])
+    for name in ("sph2pob_efficient_iou", "sph2pob_standard_iou", "sph_iou", "fov_iou"):
+        got = getattr(api.iou, name)(b1, b2, is_aligned=True).cpu().numpy()
+        np.testing.assert_allclose(got, g[name], atol=5e-6)
+    calc = api.iou.SphOverlaps2D('sph2pob_efficient_iou', 4)
+    np.testing.assert_allclose(calc(b1, b2, is_aligned=True).cpu().numpy(), g["sph2pob_efficient_iou"], atol=5e-6)
+
+
+@pytest.mark.parametrize("box,D", [("bfov", 4), ("rbfov", 5)])
+def test_aligned_fresh_seed_vs_c_oracle(api, c_oracle, box, D):
+    """200k seeded pairs (config #1 generator) against the exact-clipping float64 C oracle."""
+    b1 = O.generate_boxes(200_000, alpha_range=(1, 100), beta_range=(1, 100), box=box, seed=5)
+    b2 = O.generate_boxes(200_000, alpha_range=(1, 100), beta_range=(1, 100), box=box, seed=6)
+    for kind, tr in ((0, "efficient"), (1, "standard")):
+        got = getattr(api.iou, "sph2pob_%s_iou" % tr)(b1.to(DEV), b2.to(DEV), is_aligned=True).cpu().numpy()
+        want = c_oracle_aligned(c_oracle, kind, b1.numpy(), b2.numpy())
+        err = np.abs(got - want)
+        assert err.max() < 1e-5, (tr, err.max(), np.argmax(err))
+        assert ((got > 0) == (want > 1e-9)).mean() > 0.9999
+
+
+def test_aligned_odd_sizes_views_and_streams(api):
+    b1 = O.generate_boxes(1000, alpha_range=(1, 100), beta_range=(1, 100), box="rbfov", seed=7).to(DEV)
+    b2 = O.generate_boxes(1000, alpha_range=(1, 100), beta_range=(1, 100), box="rbfov", seed=8).to(DEV)
+    full = api.iou.sph2pob_efficient_iou(b1, b2, is_aligned=True)
+    for n in (1, 31, 33, 255, 257, 999):
+        assert torch.equal(api.iou.sph2pob_efficient_iou(b1[:n], b2[:n], is_aligned=True), full[:n])
+    # non-contiguous views, unaligned BFoV slices of a wider tensor, a trailing score column
+    wide1, wide2 = torch.cat([b1, b1[:, :1]], 1), torch.cat([b2, b2[:, :1]], 1)
+    calc = api.iou.SphOverlaps2D('sph2pob_efficient_iou', 5)
+    assert torch.equal(calc(wide1, wide2, is_aligned=True), full)
+    bf = api.iou.sph2pob_efficient_iou(b1[:, :4].contiguous(), b2[:, :4].contiguous(), is_aligned=True)
+    assert torch.equal(api.iou.sph2pob_efficient_iou(b1[:, :4], b2[:, :4], is_aligned=True), bf)
+    assert torch.equal(api.iou.sph2pob_efficient_iou(b1[1:, :4], b2[1:, :4], is_aligned=True), bf[1:])
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        on_side = api.iou.sph2pob_efficient_iou(b1, b2, is_aligned=True)
+    s.synchronize()
+    assert torch.equal(on_side, full)
+    # float64 inputs are computed in fp32 and returned in the input dtype
+    assert api.iou.sph2pob_efficient_iou(b1.double(), b2.double(), is_aligned=True).dtype == torch.float64
+
+
+# ---- pairwise ----------------------------------------------------------------------------------
+def test_pairwise_golden_both_orientations(api):
+    g = load_golden("pairwise")
+    for box in ("bfov", "rbfov"):
+        rows, cols = cu(g[box + "_rows"]), cu(g[box + "_cols"])
+        got = api.iou.sph2pob_efficient_iou(rows, cols)
+        assert got.shape == (rows.size(0), cols.size(0))
+        ok, err = within(got.cpu().numpy(), g[box + "_rc_f64"], g[box + "_rc_f32"])
+        assert ok.all(), err[~ok]
+        ok, err = within(api.iou.sph2pob_efficient_iou(cols, rows).cpu().numpy(), g[box + "_cr_f64"], g[box + "_cr_f32"])
+        assert ok.all(), err[~ok]
+    gt, anc = cu(g["assign_gt"]), cu(g["assign_anchors"])
+    got = api.iou.SphOverlaps2D('sph2pob_efficient_iou', 5)(gt, anc).cpu().numpy()
+    ok, err = within(got, g["assign_f64"], g["assign_f32"])
+    assert ok.all(), err[~ok]
+    assert ((got > 0) == (g["assign_f64"] > 1e-9)).mean() > 0.9999     # exact zeros stay exact zeros
+
+
+@pytest.mark.parametrize("kind", ["sph2pob_efficient_iou", "sph2pob_standard_iou", "sph_iou", "fov_iou"])
+@pytest.mark.parametrize("R,C", [(1, 1), (3, 700), (33, 257), (100, 31), (257, 5)])
+def test_pairwise_equals_aligned_on_the_expansion(api, kind, R, C):
+    """sph_iou_api.py:59-61: pair p = i*C + j is (bboxes1[i], bboxes2[j])."""
+    box = "bfov" if kind in ("sph_iou", "fov_iou") else "rbfov"
+    rows = O.generate_boxes(R, alpha_range=(5, 120), beta_range=(5, 120), box=box, seed=R).to(DEV)
+    cols = O.generate_boxes(C, alpha_range=(5, 120), beta_range=(5, 120), box=box, seed=C + 1000).to(DEV)
+    if R > 2 and C > 2:
+        cols[1] = rows[2]
+    fn = getattr(api.iou, kind)
+    mat = fn(rows, cols)
+    flat = fn(rows.repeat_interleave(C, 0), cols.repeat(R, 1), is_aligned=True)
+    assert torch.equal(mat.reshape(-1), flat)
+
+
+def test_fused_max_argmax(api):
+    rows = O.generate_boxes(70, alpha_range=(5, 120), beta_range=(5, 120), box="rbfov", seed=1).to(DEV)
+    cols = O.generate_boxes(3000, alpha_range=(5, 120), beta_range=(5, 120), box="rbfov", seed=2).to(DEV)
+    cols[10] = cols[2000] = rows[3]                     # tie: lowest index must win
+    rows[60] = torch.tensor([0.0, 0.0, 1.0, 1.0, 0.0])  # a row that overlaps (almost) nothing
+    for r, c in ((rows, cols), (cols, rows)):
+        mat = api.iou.sph2pob_efficient_iou(r, c)
+        rmax, rarg, cmax, carg, mat2 = api.iou.sph_max_overlaps(r, c, return_matrix=True)
+        assert torch.equal(mat, mat2)
+        assert torch.equal(rmax, mat.max(dim=1)[0]) and torch.equal(cmax, mat.max(dim=0)[0])
+        m = mat.cpu().numpy()
+        assert rarg.cpu().tolist() == [int(np.flatnonzero(m[i] == m[i].max())[0]) for i in range(m.shape[0])]
+        assert carg.cpu().tolist() == [int(np.flatnonzero(m[:, j] == m[:, j].max())[0]) for j in range(m.shape[1])]
+        # no matrix: same numbers
+        rmax2, rarg2, cmax2, carg2 = api.iou.sph_max_overlaps(r, c)
+        assert torch.equal(rmax, rmax2) and torch.equal(rarg, rarg2) and torch.equal(cmax, cmax2) and torch.equal(carg, carg2)
+        # shard offsets are added to the reported indices
+        _, rarg3, _, carg3 = api.iou.sph_max_overlaps(r, c, row_base=1000, col_base=5000)
+        assert torch.equal(rarg3, rarg + 5000) and torch.equal(carg3, carg + 1000)
+
+
+def test_sharding_emulated_on_one_gpu(api):
+    """Two 'ranks' processed one after the other on one GPU; merging their packed keys with max() is what
+    all_reduce(MAX)/all_gather do (the collective itself is covered by tests/test_sharded_gloo.py)."""
+    from sph_retina_b200.sharded import pack_keys, shard_bounds, sharded_max_overlaps, unpack_keys
+    A = O.generate_boxes(5001, alpha_range=(1, 100), beta_range=(1, 100), box="rbfov", seed=0).to(DEV)
+    G = O.generate_boxes(300, alpha_range=(1, 100), beta_range=(1, 100), box="rbfov", seed=1).to(DEV)
+    A[4000] = A[17] = G[5]
+    for orient in ("bboxes1", "bboxes2"):
+        a_max, a_arg, g_max, g_arg = sharded_max_overlaps(A, G, A.size(0), 0, anchors_are=orient)   # world = 1
+        parts, gkeys = [], []
+        for rank in range(3):
+            lo, hi = shard_bounds(A.size(0), 3, rank)
+            if orient == "bboxes1":
+                rm, ra, cm, ca = api.iou.sph_max_overlaps(A[lo:hi], G, row_base=lo)
+                parts.append(pack_keys(rm, ra)); gkeys.append(pack_keys(cm, ca))
+            else:
+                rm, ra, cm, ca = api.iou.sph_max_overlaps(G, A[lo:hi], col_base=lo)
+                parts.append(pack_keys(cm, ca)); gkeys.append(pack_keys(rm, ra))
+        sa_max, sa_arg = unpack_keys(torch.cat(parts))
+        sg_max, sg_arg = unpack_keys(torch.stack(gkeys).max(dim=0)[0])
+        assert torch.equal(sa_max, a_max) and torch.equal(sa_arg, a_arg)
+        assert torch.equal(sg_max, g_max) and torch.equal(sg_arg, g_arg)
+        assert int(g_arg[5]) == 17
+
+
+def test_config2_slice_vs_c_oracle(api, c_oracle):
+    """Assignment orientation (GT rows x anchor cols) on a strided sample of the real 512x1024 anchor grid."""
+    g = load_golden("pairwise")
+    gt, anc = g["assign_gt"], g["assign_anchors"]
+    R, C = len(gt), len(anc)
+    want = c_oracle_aligned(c_oracle, 0, np.repeat(gt, C, axis=0), np.tile(anc, (R, 1))).reshape(R, C)
+    got = api.iou.sph2pob_efficient_iou(cu(gt), cu(anc)).cpu().numpy()
+    assert np.abs(got - want).max() < 1e-5
+
+
+# ---- loss --------------------------------------------------------------------------------------
+def grad_row_error(got, truth):
+    den = np.linalg.norm(truth, axis=1)
+    return np.linalg.norm(got - truth, axis=1) / np.maximum(den, 1e-12), den
+
+
+@pytest.mark.parametrize("box", ["bfov", "rbfov"])
+@pytest.mark.parametrize("mode", ["iou", "giou", "diou", "ciou"])
+def test_loss_forward_backward_golden(api, box, mode):
+    g = load_golden("loss_" + box)
+    p = cu(g["pred"]).requires_grad_(True)
+    t = cu(g["target"]).requires_grad_(True)
+    L = api.losses.Sph2PobIoULoss(mode=mode, reduction="sum")
+    el = L(p, t, reduction_override="none")
+    assert el.shape == (p.size(0),)
+    el.sum().backward()
+    ok, err = within(el.detach().cpu().numpy(), g[mode + "_loss_f64"], g[mode + "_loss_f32"], tol=2e-5 if mode != "iou" else 1e-5)
+    assert ok.all(), (np.where(~ok)[0], err[~ok])
+    for got, key in ((p.grad, "gpred"), (t.grad, "gtarget")):
+        truth, ref32 = g["%s_%s_f64" % (mode, key)], g["%s_%s_f32" % (mode, key)]
+        rel, den = grad_row_error(got.cpu().numpy(), truth)
+        rel32, _ = grad_row_error(ref32, truth)
+        live = den > 1e-9
+        assert np.abs(got.cpu().numpy()[~live]).max(initial=0.0) < 1e-6
+        good = (rel <= 1e-4) | (rel <= rel32)
+        assert good[live].mean() > 0.995, (key, (~good & live).sum())
+        assert np.median(rel[live]) < 3e-6
+        assert (rel[live] > 1e-4).sum() < 0.5 * (rel32[live] > 1e-4).sum()
+
+
+@pytest.mark.parametrize("box", ["bfov", "rbfov"])
+def test_loss_reductions_weights_avg_factor(api, box):
+    g = load_golden("loss_" + box)
+    p, t, w1, w2 = cu(g["pred"]), cu(g["target"]), cu(g["w1"]), cu(g["w2"])
+    L = api.losses.Sph2PobIoULoss(mode="iou", loss_weight=2.0)
+    np.testing.assert_allclose(L(p, t).item(), g["red_mean"], rtol=2e-5)
+    np.testing.assert_allclose(L(p, t, w1, avg_factor=123.0).item(), g["red_w1_avg"], rtol=2e-5)
+    np.testing.assert_allclose(L(p, t, w2).item(), g["red_w2"], rtol=2e-5)
+    np.testing.assert_allclose(L(p, t, w1, reduction_override="sum").item(), g["red_w1_sum"], rtol=2e-5)
+    pz = p.clone().requires_grad_(True)
+    z = L(pz, t, torch.zeros_like(w1))
+    assert z.item() == 0.0
+    z.backward()
+    assert float(pz.grad.abs().max()) == 0.0
+    with pytest.raises(ValueError):
+        L(p, t, w1, avg_factor=3.0, reduction_override="sum")
+    # weighted rows with weight 0 receive exactly zero gradient; no-grad call works
+    pw = p.clone().requires_grad_(True)
+    L(pw, t, w1, avg_factor=50.0).backward()
+    assert float(pw.grad[w1 == 0].abs().max()) == 0.0 and torch.isfinite(pw.grad).all()
+    with torch.no_grad():
+        assert torch.isfinite(L(p, t))
+
+
+def test_loss_gradcheck_against_finite_differences(api):
+    """Independent of the reference: central differences of the kernel's own forward (fp32, so loose)."""
+    t = O.generate_boxes(512, alpha_range=(20, 80), beta_range=(20, 80), box="rbfov", seed=2)
+    p = (t + torch.randn(512, 5) * torch.tensor([4, 4, 4, 4, 8.0])).clamp(min=5)
+    p, t = p.to(DEV), t.to(DEV)
+    pr = p.clone().requires_grad_(True)
+    iou = api.losses.sph2pob_iou(pr, t)
+    iou.sum().backward()
+    h = 0.05
+    num = torch.zeros_like(p)
+    for k in range(5):
+        d = torch.zeros_like(p); d[:, k] = h
+        num[:, k] = (api.losses.sph2pob_iou(p + d, t) - api.losses.sph2pob_iou(p - d, t)) / (2 * h)
+    err = (pr.grad - num).norm(dim=1) / num.norm(dim=1).clamp(min=1e-3)
+    assert float(err.median()) < 5e-3 and float((err < 5e-2).float().mean()) > 0.97
+
+
+# ---- NMS ---------------------------------------------------------------------------------------
+def test_nms_known_answer(api):
+    g = load_golden("kat")
+    dets, keep = api.nms.SphNMS('sph2pob_efficient')(cu(g["nms_boxes"]), cu(g["nms_scores"]), cu(g["nms_idxs"]),
+                                                      dict(type="nms", iou_threshold=0.5))
+    assert keep.dtype == torch.int64 and keep.cpu().tolist() == [0, 5, 7, 3, 8, 9]
+    np.testing.assert_allclose(dets.cpu().numpy(), g["nms_dets"], atol=1e-6)
+
+
+@pytest.mark.parametrize("box", ["bfov", "rbfov"])
+def test_nms_golden_keep_sets(api, box):
+    g = load_golden("nms")
+    boxes, scores, idxs = cu(g[box + "_boxes"]), cu(g[box + "_scores"]), cu(g[box + "_idxs"])
+    nms = api.nms.SphNMS()
+    for thr, tag in ((0.3, "thr3"), (0.5, "thr5")):
+        dets, keep = nms(boxes, scores, idxs, dict(type="nms", iou_threshold=thr, max_num=150))
+        assert keep.cpu().tolist() == g["%s_keep_%s" % (box, tag)].tolist()
+        np.testing.assert_allclose(dets.cpu().numpy(), g["%s_dets_%s" % (box, tag)], atol=1e-6)
+    _, keep = nms(boxes, scores, idxs, dict(iou_threshold=0.5), class_agnostic=True)
+    assert keep.cpu().tolist() == g[box + "_keep_agnostic"].tolist()
+
+
+def greedy_from_matrix(iou, order, thr):
+    alive = np.ones(len(order), bool)
+    keep = []
+    for a, i in enumerate(order):
+        if not alive[a]:
+            continue
+        keep.append(int(i))
+        alive[a + 1:] &= ~(iou[i, order[a + 1:]] > thr)
+    return keep
+
+
+@pytest.mark.parametrize("box,k", [("bfov", 1000), ("rbfov", 1537), ("rbfov", 33), ("bfov", 1)])
+def test_nms_long_segment_equals_greedy_on_the_iou_matrix(api, box, k):
+    """One segment of k boxes (class-agnostic stress shape): the kernel's blocked bitmask scan must equal
+    the textbook greedy loop run on the kernel's own pairwise IoU (pivot = bboxes1)."""
+    seeds = O.generate_boxes(max(1, k // 5), alpha_range=(5, 60), beta_range=(5, 60), box=box, seed=9)
+    boxes = (seeds.repeat(6, 1)[:k] + torch.randn(k, seeds.size(1)) * 2).clamp(min=1).to(DEV)
+    scores = torch.rand(k, device=DEV)
+    dets, keep = api.nms.SphNMS()(boxes, scores, torch.zeros(k, dtype=torch.long, device=DEV), dict(iou_threshold=0.5))
+    iou = api.iou.sph2pob_efficient_iou(boxes, boxes).cpu().numpy()
+    order = torch.argsort(scores, descending=True, stable=True).cpu().numpy()
+    want = greedy_from_matrix(iou, order, 0.5)
+    assert keep.cpu().tolist() == want
+    assert torch.equal(dets[:, -1], scores[keep]) and torch.equal(dets[:, :-1], boxes[keep])
+
+
+def test_nms_batch_of_images_equals_per_image(api):
+    B, n = 6, 400
+    boxes = O.generate_boxes(B * n, alpha_range=(5, 60), beta_range=(5, 60), box="bfov", seed=10)
+    boxes[1::2] = (boxes[0::2] + torch.randn(B * n // 2, 4)).clamp(min=1)
+    boxes = boxes.to(DEV)
+    scores = torch.rand(B * n, device=DEV)
+    labels = torch.randint(0, 7, (B * n,), device=DEV)
+    image_ids = torch.arange(B, device=DEV).repeat_interleave(n)
+    keep = api.nms.sph_batched_nms_images(boxes, scores, labels, image_ids, 0.5)
+    for b in range(B):
+        sel = (image_ids == b).nonzero().view(-1)
+        _, k1 = api.nms.SphNMS()(boxes[sel], scores[sel], labels[sel], dict(iou_threshold=0.5))
+        assert sorted(sel[k1].cpu().tolist()) == sorted(keep[image_ids[keep] == b].cpu().tolist())
+
+
+def test_multiclass_nms_wrapper(api):
+    n, C = 300, 5
+    bboxes = O.generate_boxes(n * C, alpha_range=(5, 60), beta_range=(5, 60), box="bfov", seed=12).view(n, C * 4).to(DEV)
+    scores = torch.rand(n, C + 1, device=DEV)
+    dets, labels, inds = api.nms.multiclass_nms(bboxes, scores, 0.3, dict(iou_threshold=0.5), max_num=100,
+                                                return_inds=True, box_version=4)
+    assert dets.shape[1] == 5 and dets.shape[0] <= 100 and labels.shape[0] == dets.shape[0]
+    assert bool((dets[:-1, -1] >= dets[1:, -1]).all()) and float(dets[:, -1].min()) > 0.3
+
+
+# ---- full-size property checks (BASELINE.json configs) --------------------------------------------
+def test_config1_one_million_pairs(api, c_oracle):
+    b1 = O.generate_boxes(1_000_000, alpha_range=(1, 100), beta_range=(1, 100), box="bfov", seed=0)
+    b2 = O.generate_boxes(1_000_000, alpha_range=(1, 100), beta_range=(1, 100), box="bfov", seed=1)
+    got = api.iou.sph2pob_efficient_iou(b1.to(DEV), b2.to(DEV), is_aligned=True).cpu().numpy()
+    assert got.shape == (1_000_000,) and np.isfinite(got).all() and got.min() >= 0 and got.max() <= 1
+    sel = np.arange(0, 1_000_000, 37)
+    want = c_oracle_aligned(c_oracle, 0, b1.numpy()[sel], b2.numpy()[sel])
+    assert np.abs(got[sel] - want).max() < 1e-5
+    assert abs((got > 0).mean() - 0.26) < 0.03                # ~26 % of random pairs overlap
+
+
+def test_config5_sweep_slice(api, c_oracle):
+    """1M x 1024 is checked through size-independent properties: a row block of the matrix equals the
+    oracle, and the fused max/argmax over the full sweep equals the max over matrix blocks."""
+    A = O.generate_boxes(1 << 20, alpha_range=(1, 100), beta_range=(1, 100), box="rbfov", seed=0).to(DEV)
+    G = O.generate_boxes(1024, alpha_range=(1, 100), beta_range=(1, 100), box="rbfov", seed=1).to(DEV)
+    rmax, rarg, cmax, carg = api.iou.sph_max_overlaps(A, G)
+    best = torch.zeros(1024, device=DEV)
+    for lo in range(0, 1 << 20, 1 << 16):
+        blk = api.iou.sph2pob_efficient_iou(A[lo:lo + (1 << 16)], G)
+        assert torch.equal(blk.max(dim=1)[0], rmax[lo:lo + (1 << 16)])
+        best = torch.maximum(best, blk.max(dim=0)[0])
+    assert torch.equal(best, cmax)
+    rows = A[12345:12345 + 64].cpu().numpy()
+    want = c_oracle_aligned(c_oracle, 0, np.repeat(rows, 1024, axis=0), np.tile(G.cpu().numpy(), (64, 1))).reshape(64, 1024)
+    got = api.iou.sph2pob_efficient_iou(A[12345:12345 + 64], G).cpu().numpy()
+    assert np.abs(got - want).max() < 1e-5

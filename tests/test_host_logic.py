@@ -1,0 +1,129 @@
+"""Host-side logic that needs no GPU: registries, the drop-in signatures, loud failure on CPU tensors,
+key packing and shard arithmetic of the multi-GPU path."""
+import inspect
+
+import numpy as np
+import pytest
+import torch
+
+
+def test_registry_drop_in_names():
+    from sph_retina_b200.sphdet import registry
+    from sph_retina_b200.sphdet.iou import SphOverlaps2D
+    from sph_retina_b200.sphdet.losses import Sph2PobIoULoss
+    calc = registry.build_iou_calculator(dict(type='SphOverlaps2D', backend='sph2pob_efficient_iou', box_version=5))
+    assert isinstance(calc, SphOverlaps2D) and calc.backend == 'sph2pob_efficient_iou' and calc.box_version == 5
+    loss = registry.build_loss(dict(type='Sph2PobIoULoss', mode='ciou', loss_weight=2.0))
+    assert isinstance(loss, Sph2PobIoULoss) and loss.mode == 'ciou' and loss.loss_weight == 2.0
+    assert repr(calc) == 'SphOverlaps2D()'
+
+
+def test_signatures_match_the_reference():
+    """Argument names/defaults of sphdet/iou/sph_iou_api.py:94-98,130,156, sph_iou_calculator.py:12-20,58,
+    sph2pob_iou_loss.py:17-31 and sph_nms.py:8,18."""
+    from sph_retina_b200.sphdet.bbox.nms import SphNMS
+    from sph_retina_b200.sphdet.iou import (SphOverlaps2D, fov_iou, sph2pob_efficient_iou, sph2pob_standard_iou,
+                                            sph_iou, sph_overlaps)
+    from sph_retina_b200.sphdet.losses import Sph2PobIoULoss
+
+    def sig(f):
+        return [(p.name, p.default) for p in inspect.signature(f).parameters.values()]
+    E = inspect.Parameter.empty
+    want = [('bboxes1', E), ('bboxes2', E), ('mode', 'iou'), ('is_aligned', False), ('calculator', 'common'),
+            ('rbb_edge', 'arc'), ('rbb_angle', 'equator')]
+    assert sig(sph2pob_efficient_iou) == want and sig(sph2pob_standard_iou) == want
+    want = [('bboxes1', E), ('bboxes2', E), ('mode', 'iou'), ('is_aligned', False), ('calculator', 'diff')]
+    assert sig(sph_iou) == want and sig(fov_iou) == want
+    assert sig(sph_overlaps) == [('bboxes1', E), ('bboxes2', E), ('mode', 'iou'), ('is_aligned', False),
+                                 ('backend', 'unbiased_iou')]
+    assert sig(SphOverlaps2D.__init__)[1:] == [('backend', 'unbiased_iou'), ('box_version', 4)]
+    assert sig(SphOverlaps2D.__call__)[1:] == [('bboxes1', E), ('bboxes2', E), ('mode', 'iou'), ('is_aligned', False)]
+    assert sig(Sph2PobIoULoss.__init__)[1:] == [('mode', 'iou'), ('eps', 1e-6), ('reduction', 'mean'), ('loss_weight', 1.0)]
+    assert [n for n, _ in sig(Sph2PobIoULoss.forward)][1:6] == ['pred', 'target', 'weight', 'avg_factor', 'reduction_override']
+    assert sig(SphNMS.__init__)[1:] == [('iou_calculator', 'sph2pob_efficient')]
+    assert sig(SphNMS.__call__)[1:] == [('boxes', E), ('scores', E), ('idxs', E), ('nms_cfg', E), ('class_agnostic', False)]
+
+
+def test_empty_inputs_and_errors_follow_the_reference():
+    from sph_retina_b200.sphdet.iou import SphOverlaps2D, sph2pob_efficient_iou, sph_overlaps
+    e, b = torch.zeros(0, 4), torch.rand(3, 4)
+    assert sph2pob_efficient_iou(e, b).shape == (0, 3)                  # sph_iou_api.py:56-57
+    assert sph2pob_efficient_iou(b, e).shape == (3, 0)
+    assert sph2pob_efficient_iou(e, e, is_aligned=True).shape == (0, 1)
+    assert SphOverlaps2D('sph2pob_efficient_iou')(e, b).shape == (0, 3)
+    with pytest.raises(AssertionError):
+        sph_overlaps(b, b, mode='giou', backend='sph2pob_efficient_iou')   # :75
+    with pytest.raises(AssertionError):
+        sph_overlaps(b, b, backend='no_such_iou')                          # :76
+    with pytest.raises(AssertionError):
+        SphOverlaps2D('sph2pob_efficient_iou')(torch.rand(3, 7), b)        # :41
+    with pytest.raises(AssertionError):
+        sph2pob_efficient_iou(b, b, rbb_edge='diagonal')                   # sph_iou_api.py:51
+    with pytest.raises(NotImplementedError):
+        sph_overlaps(b, b, backend='unbiased_iou')                         # outside the path: refused, not faked
+
+
+def test_no_cpu_fallback():
+    """A CPU tensor must raise -- never silently compute somewhere else."""
+    from sph_retina_b200 import _native
+    from sph_retina_b200.sphdet.bbox.nms import SphNMS
+    from sph_retina_b200.sphdet.iou import sph2pob_efficient_iou, sph_iou
+    from sph_retina_b200.sphdet.losses import Sph2PobIoULoss
+    b = torch.rand(8, 4) * 50 + 10
+    with pytest.raises(_native.SphkError):
+        sph2pob_efficient_iou(b, b)
+    with pytest.raises(_native.SphkError):
+        sph_iou(b, b, is_aligned=True)
+    with pytest.raises(_native.SphkError):
+        Sph2PobIoULoss()(b.clone().requires_grad_(True), b)
+    with pytest.raises(_native.SphkError):
+        SphNMS()(b, torch.rand(8), torch.zeros(8, dtype=torch.long), dict(iou_threshold=0.5))
+
+
+def test_product_never_imports_the_oracle():
+    import os
+    import re
+    from conftest import ROOT
+    pkg = os.path.join(ROOT, "sph_retina_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+(oracle|sph_oracle|ref_harness)", text, flags=re.M), f
+                assert "oracle/" not in text.replace("the oracle", ""), f
+
+
+def test_key_packing_orders_by_value_then_lowest_index():
+    from sph_retina_b200.sharded import pack_keys, unpack_keys
+    v = torch.tensor([0.0, 0.5, 0.5, 1.0, 0.25])
+    i = torch.tensor([7, 9, 3, 4000000000, 0])
+    k = pack_keys(v, i)
+    assert k.dtype == torch.int64 and bool((k >= 0).all())
+    vv, ii = unpack_keys(k)
+    assert torch.equal(vv, v) and ii.tolist() == i.tolist()
+    assert k[2] > k[1] > k[4] > k[0] and k[3] == k.max()      # ties -> lowest index wins
+    vals, idx = unpack_keys(torch.stack([k[1], k[2]]).max(dim=0, keepdim=True)[0])
+    assert idx.item() == 3
+
+
+def test_shard_bounds_cover_and_balance():
+    from sph_retina_b200.sharded import shard_bounds
+    for n in (0, 1, 7, 8, 1000003):
+        for w in (1, 2, 3, 8):
+            b = [shard_bounds(n, w, r) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[r][1] == b[r + 1][0] for r in range(w - 1))
+            sizes = [hi - lo for lo, hi in b]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_weight_reduce_matches_mmdet_rules():
+    from sph_retina_b200.sphdet.losses.sph2pob_iou_loss import _weight_reduce_loss
+    loss, w = torch.tensor([1.0, 2.0, 3.0]), torch.tensor([1.0, 0.0, 1.0])
+    assert _weight_reduce_loss(loss).item() == 2.0
+    assert _weight_reduce_loss(loss, w).item() == pytest.approx(4 / 3)
+    assert _weight_reduce_loss(loss, w, 'sum').item() == 4.0
+    assert _weight_reduce_loss(loss, w, 'mean', avg_factor=2).item() == pytest.approx(2.0, rel=1e-6)
+    assert _weight_reduce_loss(loss, w, 'none', avg_factor=2).tolist() == [1.0, 0.0, 3.0]
+    with pytest.raises(ValueError):
+        _weight_reduce_loss(loss, w, 'sum', avg_factor=2)

@@ -1,0 +1,99 @@
+"""The DEVICE arithmetic (sph_retina_b200/csrc/sphk_math.cuh, sphk_grad.cuh) compiled for the host
+by g++ (tests/hostsim) against the golden vectors of the reference.  Lets the no-GPU suite catch
+maths regressions; the GPU suite (tests/test_gpu_parity.py) repeats the checks through the C ABI.
+
+Parity criterion: |kernel - reference fp64| <= 1e-5, or the kernel is at least as
+close to the fp64 run as the reference's own fp32 run on that element."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import degenerate_pairs, load_golden, within
+
+fp = ctypes.POINTER(ctypes.c_float)
+
+
+def hs_aligned(lib, kind, b1, b2, mode=0, edge=0):
+    b1, b2 = np.ascontiguousarray(b1, np.float32), np.ascontiguousarray(b2, np.float32)
+    P, D = b1.shape
+    out = np.empty(P, np.float32)
+    lib.hostsim_iou_aligned(kind, b1.ctypes.data_as(fp), b2.ctypes.data_as(fp), ctypes.c_long(P), D, mode, edge,
+                            out.ctypes.data_as(fp))
+    return out
+
+
+def hs_loss(lib, pred, target, grad_iou):
+    p, t = np.ascontiguousarray(pred, np.float32), np.ascontiguousarray(target, np.float32)
+    n, D = p.shape
+    gi = np.ascontiguousarray(grad_iou, np.float32)
+    iou, g1, g2 = np.empty(n, np.float32), np.empty((n, D), np.float32), np.empty((n, D), np.float32)
+    lib.hostsim_loss_fwd_bwd(p.ctypes.data_as(fp), t.ctypes.data_as(fp), gi.ctypes.data_as(fp), ctypes.c_long(n), D,
+                             iou.ctypes.data_as(fp), g1.ctypes.data_as(fp), g2.ctypes.data_as(fp))
+    return iou, g1, g2
+
+
+@pytest.mark.parametrize("box", ["bfov", "rbfov"])
+@pytest.mark.parametrize("kind,tr", [(0, "efficient"), (1, "standard")])
+def test_aligned_iou(hostsim, box, kind, tr):
+    g = load_golden("aligned_" + box)
+    for key, mode, edge in (("iou", 0, 0), ("iof", 1, 0), ("chord", 0, 1), ("tangent", 0, 2)):
+        got = hs_aligned(hostsim, kind, g["b1"], g["b2"], mode, edge)
+        ok, err = within(got, g["%s_%s_f64" % (tr, key)], g["%s_%s_f32" % (tr, key)])
+        ok |= degenerate_pairs(g["b1"], g["b2"]) & (err < 1e-3)
+        assert ok.all(), (box, tr, key, np.where(~ok)[0], err[~ok])
+        assert (err > 1e-5).sum() <= 2 and np.median(err) < 2e-7
+        assert got.min() >= 0.0 and got.max() <= 1.0
+
+
+def test_sph_fov(hostsim):
+    g = load_golden("aligned_bfov")
+    for kind, k in ((2, "sph"), (3, "fov")):
+        got = hs_aligned(hostsim, kind, g["b1"], g["b2"])
+        assert np.abs(got - g[k + "_f64"]).max() < 2e-6
+
+
+def test_known_answers(hostsim):
+    g = load_golden("kat")
+    for kind, name in ((0, "sph2pob_efficient_iou"), (1, "sph2pob_standard_iou"), (2, "sph_iou"), (3, "fov_iou")):
+        np.testing.assert_allclose(hs_aligned(hostsim, kind, g["b1"], g["b2"]), g[name], atol=5e-6)
+
+
+def test_pairwise_orientation(hostsim):
+    """IoU(b1, b2) != IoU(b2, b1) at the 1e-4 level (role-asymmetric jitters): both orders are pinned."""
+    g = load_golden("pairwise")
+    for box in ("bfov", "rbfov"):
+        rows, cols = g[box + "_rows"], g[box + "_cols"]
+        R, C = len(rows), len(cols)
+        b1, b2 = np.repeat(rows, C, axis=0), np.tile(cols, (R, 1))
+        ok, err = within(hs_aligned(hostsim, 0, b1, b2).reshape(R, C), g[box + "_rc_f64"], g[box + "_rc_f32"])
+        assert ok.all(), err[~ok]
+        ok, err = within(hs_aligned(hostsim, 0, b2, b1).reshape(R, C).T, g[box + "_cr_f64"], g[box + "_cr_f32"])
+        assert ok.all(), err[~ok]
+
+
+def grad_row_error(got, truth):
+    den = np.linalg.norm(truth, axis=1)
+    return np.linalg.norm(got - truth, axis=1) / np.maximum(den, 1e-12), den
+
+
+@pytest.mark.parametrize("box", ["bfov", "rbfov"])
+def test_loss_gradients(hostsim, box):
+    """Gradients: 1e-4 relative (row-wise L2) against the reference's fp64 autograd, or no worse than
+    the reference's own fp32 autograd on that row (4-6 % of its rows are beyond 1e-4)."""
+    g = load_golden("loss_" + box)
+    n = len(g["pred"])
+    iou, g1, g2 = hs_loss(hostsim, g["pred"], g["target"], -np.ones(n, np.float32))   # loss = 1 - iou
+    ok, err = within(1 - iou, g["iou_loss_f64"], g["iou_loss_f32"])
+    assert ok.all(), err[~ok]
+    for got, key in ((g1, "gpred"), (g2, "gtarget")):
+        truth, ref32 = g["iou_%s_f64" % key], g["iou_%s_f32" % key]
+        rel, den = grad_row_error(got, truth)
+        rel32, _ = grad_row_error(ref32, truth)
+        live = den > 1e-9
+        assert np.abs(got[~live]).max(initial=0.0) < 1e-6          # zero rows stay zero
+        good = (rel <= 1e-4) | (rel <= rel32)
+        assert good[live].mean() > 0.995, (key, (~good & live).sum())
+        assert np.median(rel[live]) < 2e-6
+        # the kernel is (much) closer to the fp64 truth than the fp32 reference is
+        assert (rel[live] > 1e-4).sum() < 0.5 * (rel32[live] > 1e-4).sum()

@@ -1,0 +1,143 @@
+"""The oracle (oracle/sph_oracle.py torch restatement, oracle/sph_oracle.c float64 C restatement)
+against the golden vectors frozen from the REAL reference (oracle/make_golden.py)."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import sph_oracle as O  # noqa: E402
+
+
+@pytest.mark.parametrize("box", ["bfov", "rbfov"])
+@pytest.mark.parametrize("tr", ["efficient", "standard"])
+def test_restatement_aligned_f64(box, tr):
+    g = load_golden("aligned_" + box)
+    b1, b2 = torch.from_numpy(g["b1"]).double(), torch.from_numpy(g["b2"]).double()
+    for key, kw in (("iou", {}), ("iof", dict(mode="iof")), ("chord", dict(rbb_edge="chord")),
+                    ("tangent", dict(rbb_edge="tangent")), ("project", dict(rbb_angle="project"))):
+        got = O.sph2pob_iou(b1, b2, tr, is_aligned=True, **kw).numpy()
+        want = g["%s_%s_f64" % (tr, key)]
+        assert np.abs(got - want).max() < 1e-9, (box, tr, key)
+
+
+@pytest.mark.parametrize("box", ["bfov", "rbfov"])
+def test_restatement_aligned_f32_is_the_shipped_reference(box):
+    g = load_golden("aligned_" + box)
+    b1, b2 = torch.from_numpy(g["b1"]), torch.from_numpy(g["b2"])
+    for tr in ("efficient", "standard"):
+        got = O.sph2pob_iou(b1, b2, tr, is_aligned=True).numpy()
+        want = g["%s_iou_f32" % tr]
+        # fp32 runs differ in op order (bmm vs matmul); the bulk must agree tightly
+        assert np.median(np.abs(got - want)) < 1e-6
+        assert (np.abs(got - want) > 1e-3).mean() < 0.03
+
+
+def test_restatement_obbs():
+    for box in ("bfov", "rbfov"):
+        g = load_golden("aligned_" + box)
+        b1, b2 = torch.from_numpy(g["b1"][:512]).double(), torch.from_numpy(g["b2"][:512]).double()
+        for tr, fn in (("efficient", O.sph2pob_efficient), ("standard", O.sph2pob_standard)):
+            j1, j2 = O.jitter_spherical(b1, b2)
+            o1, o2 = O.jitter_rotated(*fn(j1, j2))
+            assert np.abs(o1.numpy() - g["%s_obb1_f64" % tr]).max() < 1e-9
+            assert np.abs(o2.numpy() - g["%s_obb2_f64" % tr]).max() < 1e-9
+
+
+def test_restatement_sph_fov():
+    g = load_golden("aligned_bfov")
+    b1, b2 = torch.from_numpy(g["b1"]).double(), torch.from_numpy(g["b2"]).double()
+    for k in ("sph", "fov"):
+        got = O.approx_iou(b1, b2, k, is_aligned=True).numpy()
+        assert np.abs(got - g[k + "_f64"]).max() < 1e-9
+
+
+def test_known_answers():
+    """The 7 pairs printed by the reference's tests/test_all_ious.py:243-284 and the NMS fixture of
+    tests/test_nms.py:6-27 (values frozen from the reference; SURVEY.md 8c lists them)."""
+    g = load_golden("kat")
+    b1, b2 = torch.from_numpy(g["b1"]), torch.from_numpy(g["b2"])
+    want = [0.233804, 0.334934, 0.617307, 0.135759, 0.283414, 0.203681, 0.554219]
+    np.testing.assert_allclose(g["sph2pob_efficient_iou"], want, atol=2e-6)
+    np.testing.assert_allclose(O.sph2pob_iou(b1, b2, "efficient", is_aligned=True).numpy(), want, atol=5e-6)
+    np.testing.assert_allclose(O.sph2pob_iou(b1, b2, "standard", is_aligned=True).numpy(), g["sph2pob_standard_iou"], atol=5e-6)
+    np.testing.assert_allclose(O.approx_iou(b1, b2, "sph", is_aligned=True).numpy(), g["sph_iou"], atol=2e-6)
+    np.testing.assert_allclose(O.approx_iou(b1, b2, "fov", is_aligned=True).numpy(), g["fov_iou"], atol=2e-6)
+    dets, keep = O.nms_batched(torch.from_numpy(g["nms_boxes"]), torch.from_numpy(g["nms_scores"]),
+                               torch.from_numpy(g["nms_idxs"]), 0.5)
+    assert keep.tolist() == g["nms_keep"].tolist() == [0, 5, 7, 3, 8, 9]
+    np.testing.assert_allclose(dets.numpy(), g["nms_dets"], atol=1e-6)
+
+
+def test_restatement_pairwise():
+    g = load_golden("pairwise")
+    for box in ("bfov", "rbfov"):
+        rows, cols = torch.from_numpy(g[box + "_rows"]).double(), torch.from_numpy(g[box + "_cols"]).double()
+        assert np.abs(O.sph2pob_iou(rows, cols, "efficient").numpy() - g[box + "_rc_f64"]).max() < 1e-9
+        assert np.abs(O.sph2pob_iou(cols, rows, "efficient").numpy() - g[box + "_cr_f64"]).max() < 1e-9
+    gt, anc = torch.from_numpy(g["assign_gt"]).double(), torch.from_numpy(g["assign_anchors"]).double()
+    assert np.abs(O.sph2pob_iou(gt, anc, "efficient").numpy() - g["assign_f64"]).max() < 1e-9
+
+
+@pytest.mark.parametrize("box", ["bfov", "rbfov"])
+def test_restatement_loss_and_grads(box):
+    g = load_golden("loss_" + box)
+    for mode in ("iou", "giou", "diou", "ciou"):
+        p = torch.from_numpy(g["pred"]).double().requires_grad_(True)
+        t = torch.from_numpy(g["target"]).double().requires_grad_(True)
+        el = O.sph2pob_iou_loss_elementwise(p, t, mode=mode)
+        el.sum().backward()
+        assert np.abs(el.detach().numpy() - g[mode + "_loss_f64"]).max() < 1e-9, mode
+        for got, key in ((p.grad, "gpred"), (t.grad, "gtarget")):
+            want = g["%s_%s_f64" % (mode, key)]
+            assert np.abs(got.numpy() - want).max() <= 1e-7 * max(1.0, np.abs(want).max()), (mode, key)
+    p, t = torch.from_numpy(g["pred"]).double(), torch.from_numpy(g["target"]).double()
+    w1, w2 = torch.from_numpy(g["w1"]).double(), torch.from_numpy(g["w2"]).double()
+    n = p.size(0)
+    np.testing.assert_allclose(O.sph2pob_iou_loss(p, t, loss_weight=2.0).item(), g["red_mean"], rtol=1e-10)
+    np.testing.assert_allclose(O.sph2pob_iou_loss(p, t, w1, avg_factor=123.0, loss_weight=2.0).item(), g["red_w1_avg"], rtol=1e-10)
+    np.testing.assert_allclose(O.sph2pob_iou_loss(p, t, w2, loss_weight=2.0).item(), g["red_w2"], rtol=1e-10)
+    np.testing.assert_allclose(O.sph2pob_iou_loss(p, t, w1, reduction="sum", loss_weight=2.0).item(), g["red_w1_sum"], rtol=1e-10)
+    np.testing.assert_allclose(O.sph2pob_iou_loss(p, t, torch.zeros(n).double(), loss_weight=2.0).item(), g["red_zero_w"], atol=1e-12)
+
+
+@pytest.mark.parametrize("box", ["bfov", "rbfov"])
+def test_restatement_nms(box):
+    g = load_golden("nms")
+    boxes, scores, idxs = (torch.from_numpy(g["%s_%s" % (box, k)]) for k in ("boxes", "scores", "idxs"))
+    for thr, tag in ((0.3, "thr3"), (0.5, "thr5")):
+        dets, keep = O.nms_batched(boxes, scores, idxs, thr, max_num=150)
+        assert keep.tolist() == g["%s_keep_%s" % (box, tag)].tolist()
+        np.testing.assert_allclose(dets.numpy(), g["%s_dets_%s" % (box, tag)], atol=1e-6)
+    # the reference pops `class_agnostic` and ignores it (sph_nms.py:33): still per label
+    _, keep = O.nms_batched(boxes, scores, idxs, 0.5, class_agnostic=True)
+    assert keep.tolist() == g[box + "_keep_agnostic"].tolist()
+
+
+# ---- the float64 C restatement (exact polygon clipping) ----------------------------------------
+def _c_aligned(lib, kind, b1, b2, mode=0, edge=0):
+    b1, b2 = np.ascontiguousarray(b1, np.float32), np.ascontiguousarray(b2, np.float32)
+    P, D = b1.shape
+    out = np.empty(P, np.float64)
+    fp, dp = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)
+    lib.sph_oracle_iou_aligned(kind, b1.ctypes.data_as(fp), b2.ctypes.data_as(fp), ctypes.c_long(P), D, mode, edge,
+                               out.ctypes.data_as(dp), None)
+    return out
+
+
+@pytest.mark.parametrize("box", ["bfov", "rbfov"])
+def test_c_oracle_aligned(c_oracle, box):
+    """Exact clipping vs the reference's vertex-sort rotated IoU: they agree to 1e-6 except on the few
+    degenerate pairs where the vendored algorithm itself is inexact (coincident edges)."""
+    g = load_golden("aligned_" + box)
+    for kind, tr in ((0, "efficient"), (1, "standard")):
+        for key, mode, edge in (("iou", 0, 0), ("iof", 1, 0), ("chord", 0, 1), ("tangent", 0, 2)):
+            got = _c_aligned(c_oracle, kind, g["b1"], g["b2"], mode, edge)
+            err = np.abs(got - g["%s_%s_f64" % (tr, key)])
+            assert np.median(err) < 1e-9
+            assert (err > 1e-6).mean() < 5e-3, (box, tr, key, (err > 1e-6).sum())

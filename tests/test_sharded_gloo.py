@@ -1,0 +1,78 @@
+"""The N>1 host logic of the row-sharded overlaps (sph_retina_b200/sharded.py) on CPU: world_size 2
+and 3 over gloo.  The per-shard IoU here comes from the oracle (test infrastructure); on the GPU box
+tests/test_gpu_parity.py runs the same sharding with the CUDA kernel producing the keys."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _plant_ties(anchors, gts):
+    """exact duplicates in different shards: the gathered argmax must be the LOWEST global index"""
+    if anchors.size(0) > 8:
+        anchors[5] = gts[2]
+        anchors[anchors.size(0) - 3] = gts[2]
+
+
+def _worker(rank, world, port, n_anchors, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import sph_oracle as O
+    from test_sharded_gloo import _plant_ties
+    from sph_retina_b200.sharded import gather_assignment, pack_keys, shard_bounds
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        anchors = O.generate_boxes(n_anchors, alpha_range=(5, 100), beta_range=(5, 100), box="rbfov", seed=3)
+        gts = O.generate_boxes(24, alpha_range=(5, 100), beta_range=(5, 100), box="rbfov", seed=4)
+        _plant_ties(anchors, gts)
+        lo, hi = shard_bounds(n_anchors, world, rank)
+        iou = O.sph2pob_iou(anchors[lo:hi], gts, "efficient").float()            # [n_local, G]
+        if hi > lo:
+            a_max, a_arg = iou.max(dim=1)
+            g_max, g_arg = iou.max(dim=0)
+            a_keys, g_keys = pack_keys(a_max, a_arg), pack_keys(g_max, g_arg + lo)
+        else:
+            a_keys = torch.zeros(0, dtype=torch.int64)
+            g_keys = pack_keys(torch.zeros(gts.size(0)), torch.full((gts.size(0),), lo))
+        res = gather_assignment(a_keys, g_keys, n_anchors)
+        torch.save([r.clone() for r in res], os.path.join(out_dir, "rank%d.pt" % rank))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_anchors", [(2, 301), (3, 2)])
+def test_sharded_assignment_equals_single_process(tmp_path, world, n_anchors):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import sph_oracle as O
+    mp.spawn(_worker, args=(world, _free_port(), n_anchors, str(tmp_path)), nprocs=world, join=True)
+    anchors = O.generate_boxes(n_anchors, alpha_range=(5, 100), beta_range=(5, 100), box="rbfov", seed=3)
+    gts = O.generate_boxes(24, alpha_range=(5, 100), beta_range=(5, 100), box="rbfov", seed=4)
+    _plant_ties(anchors, gts)
+    iou = O.sph2pob_iou(anchors, gts, "efficient").float()
+    a_max, a_arg = iou.max(dim=1)
+    g_max = iou.max(dim=0)[0]
+    # lowest-index tie rule, computed independently of torch.max's convention
+    g_arg = torch.tensor([int(torch.nonzero(iou[:, j] == g_max[j])[0]) for j in range(gts.size(0))])
+    a_arg_low = torch.tensor([int(torch.nonzero(iou[i] == a_max[i])[0]) for i in range(n_anchors)])
+    for rank in range(world):
+        ra_max, ra_arg, rg_max, rg_arg = torch.load(os.path.join(str(tmp_path), "rank%d.pt" % rank))
+        assert torch.equal(ra_max, a_max) and torch.equal(ra_arg, a_arg_low)
+        assert torch.equal(rg_max, g_max) and torch.equal(rg_arg, g_arg)
