@@ -1,0 +1,50 @@
+#!/usr/bin/env python
+"""Launches one hot-path kernel a few times on BASELINE-shaped synthetic input (for ncu captures).
+    python tools/run_kernel.py aligned|aligned5|loss|nms|nms_agnostic|sweep|assign [--iters 5]"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from sph_retina_b200 import synthetic as S  # noqa: E402
+from sph_retina_b200.sphdet.bbox.nms import sph_batched_nms_images  # noqa: E402
+from sph_retina_b200.sphdet.iou import SphOverlaps2D, sph2pob_efficient_iou, sph_max_overlaps  # noqa: E402
+from sph_retina_b200.sphdet.losses import Sph2PobIoULoss  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("which")
+ap.add_argument("--iters", type=int, default=5)
+a = ap.parse_args()
+dev = "cuda:0"
+if a.which in ("aligned", "aligned5"):
+    box = "bfov" if a.which == "aligned" else "rbfov"
+    b1 = S.generate_boxes(1_000_000, alpha_range=(1, 100), beta_range=(1, 100), box=box, seed=0).to(dev)
+    b2 = S.generate_boxes(1_000_000, alpha_range=(1, 100), beta_range=(1, 100), box=box, seed=1).to(dev)
+    fn = lambda: sph2pob_efficient_iou(b1, b2, is_aligned=True)
+elif a.which == "loss":
+    p, t = (x.to(dev) for x in S.loss_pairs(200_000))
+    L = Sph2PobIoULoss(reduction="sum")
+
+    def fn():
+        q = p.detach().requires_grad_(True)
+        L(q, t).backward()
+elif a.which in ("nms", "nms_agnostic"):
+    boxes, scores, labels, image_ids = (x.to(dev) for x in S.nms_batch(64, 1000, 80))
+    if a.which == "nms_agnostic":
+        labels = torch.zeros_like(labels)
+    fn = lambda: sph_batched_nms_images(boxes, scores, labels, image_ids, 0.5)
+elif a.which == "sweep":
+    A = S.generate_boxes(1 << 20, alpha_range=(1, 100), beta_range=(1, 100), box="rbfov", seed=0).to(dev)
+    G = S.generate_boxes(1024, alpha_range=(1, 100), beta_range=(1, 100), box="rbfov", seed=1).to(dev)
+    fn = lambda: sph_max_overlaps(A, G)
+else:
+    gts, anchors = S.assignment_batch()
+    gts, anchors = gts.to(dev), anchors.to(dev)
+    calc = SphOverlaps2D('sph2pob_efficient_iou', 5)
+    fn = lambda: [calc(gts[i], anchors) for i in range(16)]
+for _ in range(a.iters):
+    fn()
+torch.cuda.synchronize()
+print("ok", a.which)
