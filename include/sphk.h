@@ -64,8 +64,9 @@ int sphk_iou_aligned(int kind, const float* b1, const float* b2, int64_t P, int 
  *   col_max/col_arg [C] max / argmax over the rows     -- overlaps.max(dim=0)
  *                       (mmdet/core/bbox/assigners/max_iou_assigner.py:173-176)
  * Ties resolve to the lowest index.  row_base / col_base are added to the reported indices so a
- * shard of a larger matrix reports global indices.  `workspace` must hold
- * sphk_iou_pairwise_workspace_bytes(R, C) bytes when any max/argmax output is requested. */
+ * shard of a larger matrix reports global indices.  `workspace` (16-byte aligned device memory of
+ * sphk_iou_pairwise_workspace_bytes(R, C) bytes) holds the per-box precompute of the Sph2Pob kinds and
+ * the packed max/argmax keys; it may be NULL only for the sph/fov kinds without max outputs. */
 int64_t sphk_iou_pairwise_workspace_bytes(int64_t R, int64_t C);
 int sphk_iou_pairwise(int kind, const float* rows, int64_t R, const float* cols, int64_t C, int D, int mode,
                       int edge, float* out, int64_t ld, float* row_max, int32_t* row_arg, float* col_max,

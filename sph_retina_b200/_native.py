@@ -78,11 +78,49 @@ def _check(status: int):
 
 
 def _ptr(t):
-    return None if t is None else ctypes.c_void_p(t.data_ptr())
+    return None if t is None else t.data_ptr()
+
+
+try:
+    _raw_stream = torch._C._cuda_getCurrentRawStream
+except AttributeError:  # pragma: no cover
+    def _raw_stream(index):
+        return torch.cuda.current_stream(index).cuda_stream
 
 
 def _stream(t):
-    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+    return _raw_stream(t.device.index)
+
+
+class _on_device:
+    """`with torch.cuda.device(dev)` only when dev is not already current (the context manager costs ~10 us)."""
+    __slots__ = ("ctx",)
+
+    def __init__(self, dev):
+        self.ctx = None if dev.index == torch.cuda.current_device() else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+
+_workspaces = {}
+
+
+def _workspace(dev, nbytes):
+    """Per (device, stream) scratch buffer, grown geometrically.  Re-use across calls is safe because every
+    consumer is enqueued on that same stream."""
+    key = (dev.index, _raw_stream(dev.index))
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes + nbytes // 2, 1 << 16), dtype=torch.uint8, device=dev)
+        _workspaces[key] = ws
+    return ws
 
 
 def _boxes(t: torch.Tensor, name: str) -> torch.Tensor:
@@ -110,7 +148,7 @@ def iou_aligned(kind: str, b1, b2, mode="iou", edge="arc") -> torch.Tensor:
     if b1.shape != b2.shape:
         raise SphkError("aligned IoU needs equal shapes, got %s and %s" % (tuple(b1.shape), tuple(b2.shape)))
     out = torch.empty(b1.size(0), dtype=torch.float32, device=b1.device)
-    with torch.cuda.device(b1.device):
+    with _on_device(b1.device):
         _check(lib.sphk_iou_aligned(KIND[kind], _ptr(b1), _ptr(b2), b1.size(0), b1.size(1), MODE[mode], EDGE[edge],
                                     _ptr(out), _stream(b1)))
     launches += 1
@@ -137,13 +175,13 @@ def iou_pairwise(kind: str, rows, cols, mode="iou", edge="arc", want_matrix=True
     if want_col_max:
         cmax = torch.empty(C, dtype=torch.float32, device=dev)
         carg = torch.empty(C, dtype=torch.int32, device=dev)
-    if want_row_max or want_col_max:
-        ws = torch.empty(max(1, lib.sphk_iou_pairwise_workspace_bytes(R, C)), dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
+    if want_row_max or want_col_max or kind in ("sph2pob_efficient", "sph2pob_standard"):
+        ws = _workspace(dev, 104 * (R + C) + 32)     # >= sphk_iou_pairwise_workspace_bytes(R, C)
+    with _on_device(dev):
         _check(lib.sphk_iou_pairwise(KIND[kind], _ptr(rows), R, _ptr(cols), C, rows.size(1), MODE[mode], EDGE[edge],
                                      _ptr(mat), ld, _ptr(rmax), _ptr(rarg), _ptr(cmax), _ptr(carg), row_base, col_base,
                                      _ptr(ws), _stream(rows)))
-    launches += 1 + 2 * int(want_row_max) + 2 * int(want_col_max)
+    launches += 1 + int(kind in ("sph2pob_efficient", "sph2pob_standard")) + 2 * int(want_row_max) + 2 * int(want_col_max)
     return mat, ((rmax, rarg) if want_row_max else None), ((cmax, carg) if want_col_max else None)
 
 
@@ -160,7 +198,7 @@ def loss_fwd_bwd(pred, target, grad_iou=None, want_grad_pred=False, want_grad_ta
     if grad_iou is not None:
         grad_iou = grad_iou.to(device=dev, dtype=torch.float32).contiguous()
         assert grad_iou.numel() == n
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         _check(lib.sphk_loss_fwd_bwd(_ptr(pred), _ptr(target), n, pred.size(1), _ptr(iou), _ptr(grad_iou), _ptr(gp),
                                      _ptr(gt), _stream(pred)))
     launches += 1
@@ -174,7 +212,7 @@ def obb_fwd(kind: str, b1, b2, edge="arc"):
     n, dev = b1.size(0), b1.device
     o1 = torch.empty((n, 5), dtype=torch.float32, device=dev)
     o2 = torch.empty((n, 5), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         _check(lib.sphk_obb_fwd(KIND[kind], _ptr(b1), _ptr(b2), n, b1.size(1), EDGE[edge], _ptr(o1), _ptr(o2), _stream(b1)))
     launches += 1
     return o1, o2
@@ -188,7 +226,7 @@ def obb_bwd(kind: str, b1, b2, g1, g2, edge="arc", want1=True, want2=True):
     g2 = None if g2 is None else g2.to(device=dev, dtype=torch.float32).contiguous()
     gb1 = torch.empty_like(b1) if want1 else None
     gb2 = torch.empty_like(b2) if want2 else None
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         _check(lib.sphk_obb_bwd(KIND[kind], _ptr(b1), _ptr(b2), n, b1.size(1), EDGE[edge], _ptr(g1), _ptr(g2), _ptr(gb1),
                                 _ptr(gb2), _stream(b1)))
     launches += 1
@@ -207,7 +245,7 @@ def riou_fwd_bwd(o1, o2, grad_iou=None, want1=True, want2=True):
     g2 = torch.empty_like(o2) if (grad_iou is not None and want2) else None
     if grad_iou is not None:
         grad_iou = grad_iou.to(device=dev, dtype=torch.float32).contiguous()
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         _check(lib.sphk_riou_fwd_bwd(_ptr(o1), _ptr(o2), n, _ptr(iou), _ptr(grad_iou), _ptr(g1), _ptr(g2), _stream(o1)))
     launches += 1
     return iou, g1, g2
@@ -224,7 +262,7 @@ def nms_batched(boxes, order, seg_offsets, max_seg_len: int, iou_threshold: floa
     keep = torch.zeros(order.numel(), dtype=torch.uint8, device=dev)
     if S <= 0 or order.numel() == 0:
         return keep
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         _check(lib.sphk_nms_batched(_ptr(boxes), _ptr(order), _ptr(seg_offsets), S, int(max_seg_len), boxes.size(1),
                                     float(iou_threshold), _ptr(keep), _stream(boxes)))
     launches += 1
@@ -234,7 +272,7 @@ def nms_batched(boxes, order, seg_offsets, max_seg_len: int, iou_threshold: floa
 def probe_fp32(blocks: int, iters: int, device) -> float:
     """Runs the FMA-chain probe once; returns the flop count of the launch (time it with CUDA events)."""
     sink = torch.empty(blocks * 256, dtype=torch.float32, device=device)
-    with torch.cuda.device(sink.device):
+    with _on_device(sink.device):
         _check(lib.sphk_probe_fp32(blocks, iters, _ptr(sink), _stream(sink)))
     return 2.0 * 8 * iters * 256 * blocks
 

@@ -1,0 +1,168 @@
+// sphk_fast.cuh -- the N x M formulation of the Sph2Pob IoU pair: per-box precompute, a conservative
+// "cannot touch" prefilter, and a trig-free fast path for the pairs that survive it.
+//
+// Why: in the reference every pair pays the whole pipeline (sph_iou_api.py:48-86).  In the N x M
+// workloads 70-80 % of the pairs are far apart and their IoU is exactly 0, and most of
+// the per-pair transcendental work depends on one box only.  So
+//   * BoxRec / BoxCull hold, per box and per role, everything that does not depend on the partner, for
+//     the case that jitter_1's similarity mask is false (sph_iou_api.py:246-251: the mask is the only
+//     pair-dependent part of jitter_1; with it false each box is merely clamped);
+//   * pre_disjoint() proves from 7 FMAs that the two planar boxes cannot touch whatever the jitters
+//     do (centre distance > sum of circumradii + margin), in which case both rotated-IoU
+//     implementations of the reference return exactly 0;
+//   * pair_fast() evaluates a surviving pair without atan2/sincos: the internal angles are only ever
+//     used through their sine and cosine, which are the normalised (n, m) components themselves.
+// Whenever a reference quirk could be active (similarity mask, acos clamp zone, jitter_2, size
+// clamps, gamma beyond +-179 deg) pair_fast() declines and the caller runs the reference-order code of
+// sphk_math.cuh (sph2pob_iou_pair).  Both paths share riou_core().
+#pragma once
+#include "sphk_math.cuh"
+
+namespace sphk {
+
+// What the fast path needs about one box (valid when jitter_1's mask is false for the pair).
+// 64 bytes = 4 x float4.
+struct BoxRec {
+    float t, p, tj, pj;   // raw theta, phi (deg) for the similarity mask; jittered (clamped) theta, phi for the geometry
+    float sp, cp, w, h;   // sin / cos phi; planar edge lengths (rad) before jitter_2
+    float sg, cg, a, b;   // sin / cos gamma (0, 1 for BFoV); raw alpha, beta (deg) for the similarity mask
+    float g, flag, pad0, pad1;  // raw gamma (deg); flag != 0: reference-order path only
+};
+// Prefilter operands of one box.  32 bytes = 2 x float4.
+struct BoxCull {
+    float ux, uy, uz, rc;  // centre unit vector; cos(r), r = circumradius of the planar box + jitter margin
+    float rs, bias, pad0, pad1;  // sin(r); bias: -1e-6 (rounding margin) or -10 (box too large to ever be culled)
+};
+constexpr int kBoxRecFloats = 16, kBoxCullFloats = 8;
+
+// Record of one box in its role (1 = bboxes1 / rows, 2 = bboxes2 / columns); the jittered box is returned too.
+SPHK_HD JitBox box_rec(const RawBox& x, int role, int D, int edge, BoxRec* rec) {
+    const JitBox j = (role == 1) ? jitter1_role1(x, false, D) : jitter1_role2(x, false, D);
+    sincos_deg(j.p_hi, j.p_lo, &rec->sp, &rec->cp);
+    rec->t = x.t; rec->p = x.p; rec->a = x.a; rec->b = x.b; rec->g = (D == 5) ? x.g : 0.0f;
+    rec->tj = j.t_hi + j.t_lo; rec->pj = j.p_hi + j.p_lo;   // exact unless clamped at the upper end (flagged below)
+    rec->pad0 = 0.0f; rec->pad1 = 0.0f;
+    rec->w = edge_len_deg(j.a, edge);
+    rec->h = edge_len_deg(j.b, edge);
+    rec->sg = 0.0f; rec->cg = 1.0f;
+    // slow-path-only boxes: theta or phi clamped at the UPPER end (360 - eps is not a float: the hi + lo
+    // pair of the reference-order path is needed; a clamp at the lower end gives tj = the offset,
+    // exactly), sizes in reach of jitter_2's minimum, gamma in reach of jitter_2's +-2 pi clamp, NaNs.
+    // A clamped alpha / beta is fine: a, b stay raw, w, h come from the clamped values.
+    bool slow = (j.t_hi != x.t && j.t_hi != 0.0f) || (j.p_hi != x.p && j.p_hi != 0.0f) || !(x.t == x.t) || !(x.p == x.p);
+    slow = slow || !(rec->w >= 2.0f * kMinWh1) || !(rec->h >= 2.0f * kMinWh1);
+    if (D == 5) {
+        sincos_deg(j.g, 0.0f, &rec->sg, &rec->cg);
+        slow = slow || !(fabsf(x.g) <= 179.0f);
+    }
+    rec->flag = slow ? 1.0f : 0.0f;
+    return j;
+}
+
+// circumradius of the planar box plus the jitter margin: jitter_1 moves w, h by <= 4.3e-6 rad, jitter_2 by
+// <= 2.5e-4 rad and the centre distance by <= 1.3e-4 rad: 4e-4 per box covers all of it
+SPHK_HD float cull_radius(float w, float h) { return fmaf(0.5f * sqrtf(fmaf(w, w, h * h)), 1.0001f, 4e-4f); }
+
+SPHK_HD void box_pre(const RawBox& x, int role, int D, int edge, BoxRec* rec, BoxCull* cull) {
+    const JitBox j = box_rec(x, role, D, edge, rec);
+    float st, ct;
+    sincos_deg(j.t_hi, j.t_lo, &st, &ct);
+    cull->ux = rec->sp * ct; cull->uy = rec->sp * st; cull->uz = rec->cp;
+    const float r = cull_radius(rec->w, rec->h);
+    if (r < 1.55f) {               // r_g + r_p < pi: cos is monotone over [0, r_g + r_p]
+        sincos_f(r, &cull->rs, &cull->rc);
+        cull->bias = -1e-6f;
+    } else {
+        cull->rs = 0.0f; cull->rc = 0.0f; cull->bias = -10.0f;
+    }
+    cull->pad0 = 0.0f; cull->pad1 = 0.0f;
+}
+
+// true: the planar boxes are disjoint for every jitter outcome (centre distance > sum of the circumradii
+// + margins) -> IoU is exactly 0 in the reference.  cos(arc) < cos(r_g + r_p), 7 FMA-class instructions.
+SPHK_HD bool pre_disjoint(const BoxCull& g, const BoxCull& p) {
+    const float dot = fmaf(g.ux, p.ux, fmaf(g.uy, p.uy, g.uz * p.uz));
+    const float thr = fmaf(g.rc, p.rc, fmaf(-g.rs, p.rs, g.bias + p.bias));
+    return dot < thr;
+}
+
+SPHK_HD float rsqrt_f(float x) {
+#if defined(__CUDA_ARCH__)
+    return rsqrtf(x);
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
+
+// The clipping job a pair boils down to: box 2 (w2 x h2, centre (px, py), rotated by r) against the
+// axis-aligned box 1 (w1 x h1) at the origin.
+struct ClipJob {
+    float px, py, cr, sr, w1, h1, w2, h2;
+};
+enum { JOB_READY = 0, JOB_DEAD = 1, JOB_SLOW = 2 };
+
+// Transform stage of the fast path.  JOB_READY: *job is set.  JOB_DEAD (only with cull = true): the planar
+// boxes cannot touch, IoU is exactly 0.  JOB_SLOW: a reference quirk may be active, run sph2pob_iou_pair.
+SPHK_HD int pair_job(const BoxRec& g, const BoxRec& p, int D, int kind, bool cull, ClipJob* job) {
+    if (g.flag != 0.0f || p.flag != 0.0f) return JOB_SLOW;
+    // jitter_1's similarity mask (sph_iou_api.py:246-247) on the raw coordinates
+    bool sim = (fabsf(g.t - p.t) < kEps) | (fabsf(g.p - p.p) < kEps) | (fabsf(g.a - p.a) < kEps) | (fabsf(g.b - p.b) < kEps);
+    if (D == 5) sim = sim | (fabsf(g.g - p.g) < kEps);
+    if (sim) return JOB_SLOW;
+    float sdt, cdt, sdp, cdp;
+    sincos_deg(0.5f * (p.tj - g.tj), 0.0f, &sdt, &cdt);
+    sincos_deg(0.5f * (p.pj - g.pj), 0.0f, &sdp, &cdp);
+    const float hth = sdt * sdt;
+    const float sin_dth = 2.0f * sdt * cdt, sin_dph = 2.0f * sdp * cdp;
+    const float hav = fmaf(g.sp * p.sp, hth, sdp * sdp);
+    const float arc = arc_from_hav(hav);
+    // outside: the acos clamp zone of the arc and jitter_2's |x1 - x2| < eps
+    if (!(arc > 2e-3f && arc < 3.14f)) return JOB_SLOW;
+    if (cull && arc > cull_radius(g.w, g.h) + cull_radius(p.w, p.h)) return JOB_DEAD;
+    const float ng = fmaf(-2.0f * g.cp * p.sp, hth, sin_dph), mg = -p.sp * sin_dth;
+    const float np = fmaf(2.0f * p.cp * g.sp, hth, sin_dph), mp = -g.sp * sin_dth;
+    const float S2g = fmaf(ng, ng, mg * mg), S2p = fmaf(np, np, mp * mp);   // both sin^2(arc)
+    if (!(S2g > 1e-30f && S2p > 1e-30f)) return JOB_SLOW;
+    const float ig = rsqrt_f(S2g), ip = rsqrt_f(S2p);
+    // a_g = atan2(ng, mg), a_p = atan2(np, mp): only their sine and cosine are ever used
+    const float sag = ng * ig, cag = mg * ig, sap = np * ip, cap = mp * ip;
+    // a1 = a_g - gamma_g, a2 = a_p - gamma_p
+    const float c1 = fmaf(cag, g.cg, sag * g.sg), s1 = fmaf(sag, g.cg, -cag * g.sg);
+    const float c2 = fmaf(cap, p.cg, sap * p.sg), s2 = fmaf(sap, p.cg, -cap * p.sg);
+    // the reference clamps |angle| into [4.47e-4, pi - 4.47e-4] (before gamma in 'efficient', after
+    // it in 'standard') and gives angle == 0 the sign -1: stay clear of both ends
+    const bool near_axis = (kind == KIND_SPH2POB_STANDARD) ? (fabsf(s1) < 1e-3f || fabsf(s2) < 1e-3f)
+                                                           : (fabsf(sag) < 1e-3f || fabsf(sap) < 1e-3f);
+    if (near_axis) return JOB_SLOW;
+    float cr = fmaf(c2, c1, s2 * s1), sr = fmaf(s2, c1, -c2 * s1);         // r = a2 - a1
+    // jitter_2 (sph_iou_api.py:222-242) must be inactive: sizes differ by > eps, angles by > eps'
+    if (fabsf(g.w - p.w) < 2e-4f || fabsf(g.h - p.h) < 2e-4f) return JOB_SLOW;
+    if (cr > 0.0f && fabsf(sr) < 2e-3f) return JOB_SLOW;
+    job->sr = (sr == 0.0f) ? 1e-30f : sr;
+    job->cr = (cr == 0.0f) ? 1e-30f : cr;
+    // centre of box 2 in the frame of box 1: R(-a1) (arc, 0)   (same for both transforms)
+    job->px = c1 * arc; job->py = -s1 * arc;
+    job->w1 = g.w; job->h1 = g.h; job->w2 = p.w; job->h2 = p.h;
+    return JOB_READY;
+}
+
+// Clipping stage: IoU / IoF of a job, with the final clamp(0, 1) of sph_iou_api.py:86.
+SPHK_HD float clip_job_iou(const ClipJob& j, int mode) {
+    EdgeClip E;
+    const float A1 = j.w1 * j.h1, A2 = j.w2 * j.h2;
+    float I = riou_core(j.px, j.py, j.cr, j.sr, j.w1, j.h1, j.w2, j.h2, &E);
+    I = fminf(fmaxf(I, 0.0f), fminf(A1, A2));
+    if (!(I == I)) I = 0.0f;
+    const float den = (mode == MODE_IOF) ? A1 : (A1 + A2 - I);
+    return clampf(I / den, 0.0f, 1.0f);
+}
+
+// Fast path of one pair.  Returns true and sets *out when it applies; false = run the reference-order path.
+SPHK_HD bool pair_fast(const BoxRec& g, const BoxRec& p, int D, int kind, int mode, float* out) {
+    ClipJob job;
+    if (pair_job(g, p, D, kind, false, &job) != JOB_READY) return false;
+    *out = clip_job_iou(job, mode);
+    return true;
+}
+
+}  // namespace sphk

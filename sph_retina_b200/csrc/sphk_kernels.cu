@@ -11,9 +11,11 @@
 // The per-pair arithmetic lives in sphk_math.cuh / sphk_grad.cuh.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/sphk.h"
+#include "sphk_fast.cuh"
 #include "sphk_grad.cuh"
 #include "sphk_math.cuh"
 
@@ -23,6 +25,7 @@ namespace {
 
 thread_local char g_err[256] = "";
 int g_dense = 0;   // sphk_set_dense: 1 = no disjoint-pair early-outs (measurement only)
+const int g_force_tr = [] { const char* e = getenv("SPHK_TR"); return e ? atoi(e) : 0; }();
 
 int fail(int code, const char* what) {
     snprintf(g_err, sizeof(g_err), "%s", what);
@@ -71,6 +74,18 @@ __device__ __forceinline__ void store_grad(float* __restrict__ g, int64_t i, con
     }
 }
 
+// The reference-order path of one pair, out of line: it is rare on the N x M / aligned workloads, and
+// keeping ONE copy of its ~1300 instructions per library keeps the hot kernels inside the instruction cache.
+__device__ __noinline__ float slow_pair_iou(const float* __restrict__ b1, int64_t i1, const float* __restrict__ b2,
+                                            int64_t i2, int D, int kind, int mode, int edge, bool dense) {
+    RawBox x, y;
+    const float* q = b1 + i1 * D;
+    x.t = __ldg(q); x.p = __ldg(q + 1); x.a = __ldg(q + 2); x.b = __ldg(q + 3); x.g = (D == 5) ? __ldg(q + 4) : 0.0f;
+    q = b2 + i2 * D;
+    y.t = __ldg(q); y.p = __ldg(q + 1); y.a = __ldg(q + 2); y.b = __ldg(q + 3); y.g = (D == 5) ? __ldg(q + 4) : 0.0f;
+    return sph2pob_iou_pair(x, y, D, kind, mode, edge, dense);
+}
+
 // ---- aligned -----------------------------------------------------------------------------------
 template <int KIND, int D>
 __global__ void __launch_bounds__(kThreads) k_iou_aligned(const float* __restrict__ b1, const float* __restrict__ b2,
@@ -83,6 +98,80 @@ __global__ void __launch_bounds__(kThreads) k_iou_aligned(const float* __restric
     if (KIND == KIND_SPH || KIND == KIND_FOV) v = approx_iou_pair(x, y, KIND);
     else v = sph2pob_iou_pair(x, y, D, KIND, mode, edge, dense);
     out[i] = v;
+}
+
+// ---- aligned, Sph2Pob kinds: transform stage per pair, clipping stage warp-compacted -----------------
+// Every pair pays the transform stage (pair_job: jitter clamps, four degree-domain sincos, arc, dead
+// test); only the pairs whose planar boxes can touch (26-40 % of random pairs) go on to the clipper,
+// and they do so compacted through a per-warp ring of ClipJobs in shared memory, 32 at a time.
+// Pairs on which a reference quirk may be active are queued for the reference-order path.
+constexpr int kJobRing = 64;
+
+struct AlignedTile {
+    float job[kThreads / 32][8][kJobRing];
+    unsigned short jidx[kThreads / 32][kJobRing];
+    unsigned short sidx[kThreads / 32][kJobRing];
+};
+
+template <int D>
+__global__ void __launch_bounds__(kThreads)
+k_iou_aligned2(const float* __restrict__ b1, const float* __restrict__ b2, int64_t P, int kind, int mode, int edge,
+               float* __restrict__ out, int iters, bool vec_ok, bool dense) {
+    __shared__ AlignedTile T;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t base = ((int64_t)blockIdx.x * (kThreads / 32) + warp) * iters * 32;
+    if (base >= P) return;
+    int hj = 0, tj = 0, hs = 0, ts = 0;
+    const unsigned lt = (1u << lane) - 1u;
+    // one extra iteration (it == iters) drains the rings, so that each batch body exists once in the code
+#pragma unroll 1
+    for (int it = 0; it <= iters; ++it) {
+        const bool last = it == iters;
+        const int off = it * 32 + lane;
+        const int64_t i = base + off;
+        int st = JOB_DEAD;
+        ClipJob j;
+        j.px = j.py = j.cr = j.sr = j.w1 = j.h1 = j.w2 = j.h2 = 0.0f;
+        if (!last && i < P) {
+            const RawBox x = load_box<D>(b1, i, vec_ok), y = load_box<D>(b2, i, vec_ok);
+            BoxRec g, p;
+            box_rec(x, 1, D, edge, &g);
+            box_rec(y, 2, D, edge, &p);
+            st = pair_job(g, p, D, kind, !dense, &j);
+            if (st == JOB_DEAD) out[i] = 0.0f;
+        }
+        const unsigned mj = __ballot_sync(0xFFFFFFFFu, st == JOB_READY);
+        if (st == JOB_READY) {
+            const int slot = (tj + __popc(mj & lt)) & (kJobRing - 1);
+            T.job[warp][0][slot] = j.px; T.job[warp][1][slot] = j.py; T.job[warp][2][slot] = j.cr; T.job[warp][3][slot] = j.sr;
+            T.job[warp][4][slot] = j.w1; T.job[warp][5][slot] = j.h1; T.job[warp][6][slot] = j.w2; T.job[warp][7][slot] = j.h2;
+            T.jidx[warp][slot] = (unsigned short)off;
+        }
+        tj += __popc(mj);
+        const unsigned ms = __ballot_sync(0xFFFFFFFFu, st == JOB_SLOW);
+        if (st == JOB_SLOW) T.sidx[warp][(ts + __popc(ms & lt)) & (kJobRing - 1)] = (unsigned short)off;
+        ts += __popc(ms);
+        if (tj - hj >= 32 || (last && tj > hj)) {
+            const int cnt = min(tj - hj, 32);
+            __syncwarp();
+            const int slot = (hj + lane) & (kJobRing - 1);
+            ClipJob c;
+            c.px = T.job[warp][0][slot]; c.py = T.job[warp][1][slot]; c.cr = T.job[warp][2][slot]; c.sr = T.job[warp][3][slot];
+            c.w1 = T.job[warp][4][slot]; c.h1 = T.job[warp][5][slot]; c.w2 = T.job[warp][6][slot]; c.h2 = T.job[warp][7][slot];
+            const int o2 = T.jidx[warp][slot];
+            __syncwarp();
+            if (lane < cnt) out[base + o2] = clip_job_iou(c, mode);
+            hj += cnt;
+        }
+        if (ts - hs >= 32 || (last && ts > hs)) {
+            const int cnt = min(ts - hs, 32);
+            __syncwarp();
+            const int o2 = T.sidx[warp][(hs + lane) & (kJobRing - 1)];
+            __syncwarp();
+            if (lane < cnt) out[base + o2] = slow_pair_iou(b1, base + o2, b2, base + o2, D, kind, mode, edge, dense);
+            hs += cnt;
+        }
+    }
 }
 
 // ---- pairwise ----------------------------------------------------------------------------------
@@ -145,6 +234,202 @@ k_iou_pairwise(const float* __restrict__ rows, int64_t R, const float* __restric
         if (threadIdx.x < nr) {
             const unsigned long long key = s_rkey[threadIdx.x];
             if (key > row_key[r0 + threadIdx.x]) atomicMax(&row_key[r0 + threadIdx.x], key);
+        }
+    }
+}
+
+// ---- pairwise, Sph2Pob kinds: precompute + prefilter + warp-compacted evaluation -------------------
+// k_box_pre: BoxRec (64 B) + BoxCull (32 B) of every row and column box, once per call, into the workspace.
+// k_iou_pairwise2: CTA tile = TR rows x 256 columns, lane <-> column.  For each row the 7-FMA prefilter
+// decides "exactly 0" (written straight away, coalesced) or "live"; live (row, column) pairs are
+// ballot-compacted into a per-warp ring buffer in shared memory and evaluated 32 at a time, so the
+// expensive clipping code always runs with full warps although only ~20-30 % of the pairs need it.
+// Pairs that need the reference-order path (rare) are compacted once more into a second ring.
+// Row / column max+argmax are reduced in shared memory and merged into the global packed keys with
+// one atomicMax per row / column and CTA.
+constexpr int kTC = 256, kRing = 64, kRecStride = 20;   // record stride 20 words: conflict-free LDS.128 across lanes
+
+template <int TR>
+struct PairTile {
+    float crec[kTC * kRecStride];
+    float rrec[TR * kRecStride];
+    float4 rcull[TR][2];
+    unsigned long long rkey[TR];
+    unsigned long long ckey[kTC];
+    unsigned short ring[kThreads / 32][2][kRing];
+};
+
+template <int D>
+__global__ void __launch_bounds__(kThreads)
+k_box_pre(const float* __restrict__ rows, int64_t R, const float* __restrict__ cols, int64_t C, int edge,
+          float4* __restrict__ rec, float4* __restrict__ cull, bool rows_vec, bool cols_vec) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= R + C) return;
+    const bool is_row = i < R;
+    const RawBox x = is_row ? load_box<D>(rows, i, rows_vec) : load_box<D>(cols, i - R, cols_vec);
+    BoxRec b;
+    BoxCull c;
+    box_pre(x, is_row ? 1 : 2, D, edge, &b, &c);
+    float4* q = rec + i * 4;
+    q[0] = make_float4(b.t, b.p, b.tj, b.pj);
+    q[1] = make_float4(b.sp, b.cp, b.w, b.h);
+    q[2] = make_float4(b.sg, b.cg, b.a, b.b);
+    q[3] = make_float4(b.g, b.flag, 0.0f, 0.0f);
+    float4* u = cull + i * 2;
+    u[0] = make_float4(c.ux, c.uy, c.uz, c.rc);
+    u[1] = make_float4(c.rs, c.bias, 0.0f, 0.0f);
+}
+
+__device__ __forceinline__ BoxRec load_rec(const float* base, int i) {
+    const float4* q = reinterpret_cast<const float4*>(base + i * kRecStride);
+    const float4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
+    BoxRec b;
+    b.t = q0.x; b.p = q0.y; b.tj = q0.z; b.pj = q0.w;
+    b.sp = q1.x; b.cp = q1.y; b.w = q1.z; b.h = q1.w;
+    b.sg = q2.x; b.cg = q2.y; b.a = q2.z; b.b = q2.w;
+    b.g = q3.x; b.flag = q3.y; b.pad0 = 0.0f; b.pad1 = 0.0f;
+    return b;
+}
+__device__ __forceinline__ void stage_rec(float* base, int i, const float4* __restrict__ rec, int64_t idx, bool ok) {
+    // out-of-range slots get a flagged record (never evaluated anyway)
+    float4 q0 = make_float4(0.f, 90.f, 0.f, 90.f), q1 = make_float4(1.f, 0.f, 1e-2f, 1e-2f);
+    float4 q2 = make_float4(0.f, 1.f, 1.f, 1.f), q3 = make_float4(0.f, 1.f, 0.f, 0.f);
+    if (ok) {
+        const float4* q = rec + idx * 4;
+        q0 = __ldg(q); q1 = __ldg(q + 1); q2 = __ldg(q + 2); q3 = __ldg(q + 3);
+    }
+    float4* d = reinterpret_cast<float4*>(base + i * kRecStride);
+    d[0] = q0; d[1] = q1; d[2] = q2; d[3] = q3;
+}
+
+struct PairOut {
+    float* out;
+    int64_t ld, r0, c0;
+    bool want_row, want_col;
+    uint32_t row_base, col_base;
+};
+
+template <int TR>
+__device__ __forceinline__ void emit_pair(PairTile<TR>& T, const PairOut& o, int r, int c, float v) {
+    if (o.out) o.out[(o.r0 + r) * o.ld + o.c0 + c] = v;
+    if (v > 0.0f) {
+        if (o.want_row) atomicMax(&T.rkey[r], pack_key(v, o.col_base + (uint32_t)(o.c0 + c)));
+        if (o.want_col) atomicMax(&T.ckey[c], pack_key(v, o.row_base + (uint32_t)(o.r0 + r)));
+    }
+}
+
+template <int D, int TR>
+__global__ void __launch_bounds__(kThreads)
+k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restrict__ cols, int64_t C,
+                const float4* __restrict__ rec, const float4* __restrict__ cull, int kind, int mode, int edge,
+                float* __restrict__ out, int64_t ld, unsigned long long* __restrict__ row_key,
+                unsigned long long* __restrict__ col_key, uint32_t row_base, uint32_t col_base, uint32_t col_tiles,
+                bool dense) {
+    __shared__ __align__(16) PairTile<TR> T;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // heaviest tiles first: RetinaNet-style anchor lists end with the coarse pyramid levels, whose huge anchors
+    // overlap every GT, so the tail of the launch is made of the light tiles
+    const uint32_t bid = gridDim.x - 1u - blockIdx.x;
+    const uint32_t rt = bid / col_tiles, ct = bid - rt * col_tiles;
+    PairOut o;
+    o.out = out; o.ld = ld; o.r0 = (int64_t)rt * TR; o.c0 = (int64_t)ct * kTC;
+    o.want_row = row_key != nullptr; o.want_col = col_key != nullptr;
+    o.row_base = row_base; o.col_base = col_base;
+    const int nr = (int)min((int64_t)TR, R - o.r0);
+    const bool col_ok = o.c0 + tid < C;
+    // ---- phase 0: stage the tile's records (columns: records -> shared memory, cull operands -> registers)
+    stage_rec(T.crec, tid, rec + R * 4, o.c0 + tid, col_ok);
+    T.ckey[tid] = 0ull;
+    float4 pc0 = make_float4(0.f, 0.f, 1.f, 0.f), pc1 = make_float4(0.f, -10.f, 0.f, 0.f);
+    if (col_ok) {
+        const float4* u = cull + (R + o.c0 + tid) * 2;
+        pc0 = __ldg(u); pc1 = __ldg(u + 1);
+    }
+    if (tid < TR) {
+        const bool ok = tid < nr;
+        stage_rec(T.rrec, tid, rec, o.r0 + tid, ok);
+        float4 u0 = make_float4(0.f, 0.f, 1.f, 0.f), u1 = make_float4(0.f, -10.f, 0.f, 0.f);
+        if (ok) {
+            const float4* u = cull + (o.r0 + tid) * 2;
+            u0 = __ldg(u); u1 = __ldg(u + 1);
+        }
+        T.rcull[tid][0] = u0; T.rcull[tid][1] = u1;
+        T.rkey[tid] = 0ull;
+    }
+    __syncthreads();
+    // ---- phase 1: prefilter + compaction.  This thread's column is tid (= warp * 32 + lane).
+    // Out-of-range columns and the dense (measurement) mode are folded into the bias term of the test.
+    const float pbias = col_ok ? (dense ? -1e30f : pc1.y) : 1e30f;
+    int hf = 0, tf = 0, hs = 0, ts = 0;          // ring head / tail counters (fast, slow)
+    const unsigned lt = (1u << lane) - 1u;
+    if (out) {
+        // zero-fill this warp's [nr x 32] part of the matrix; live pairs overwrite their entry later
+        // (ordered by the __syncwarp() in front of every batch)
+        float* base = out + o.r0 * ld + o.c0 + warp * 32;
+        const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0) && (o.c0 + warp * 32 + 32 <= C);
+        if (vec) {
+            for (int rr = lane >> 3; rr < nr; rr += 4)
+                *reinterpret_cast<float4*>(base + rr * ld + (lane & 7) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else if (col_ok) {
+            for (int rr = 0; rr < nr; ++rr) base[rr * ld + lane] = 0.0f;
+        }
+    }
+
+    // one extra iteration (r == nr) drains the rings, so that each batch body exists once in the code
+#pragma unroll 1
+    for (int r = 0; r <= nr; ++r) {
+        const bool last = r == nr;
+        bool live = false;
+        if (!last) {
+            const float4 g0 = T.rcull[r][0];
+            const float2 g1 = *reinterpret_cast<const float2*>(&T.rcull[r][1]);
+            // cos(arc) < cos(r_g + r_p) - margin  <=>  the planar boxes cannot touch  (sphk_fast.cuh: pre_disjoint)
+            const float dot = fmaf(g0.x, pc0.x, fmaf(g0.y, pc0.y, g0.z * pc0.z));
+            const float thr = fmaf(g0.w, pc0.w, fmaf(-g1.x, pc1.x, g1.y + pbias));
+            live = !(dot < thr);
+        }
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, live);
+        if (live) T.ring[warp][0][(tf + __popc(m & lt)) & (kRing - 1)] = (unsigned short)((r << 5) | lane);
+        tf += __popc(m);
+        if (tf - hf >= 32 || (last && tf > hf)) {
+            const int cnt = min(tf - hf, 32);
+            __syncwarp();
+            const int e = T.ring[warp][0][(hf + lane) & (kRing - 1)];
+            __syncwarp();
+            bool slow = false;
+            if (lane < cnt) {
+                const int rr = e >> 5, c = warp * 32 + (e & 31);
+                float v;
+                slow = !pair_fast(load_rec(T.rrec, rr), load_rec(T.crec, c), D, kind, mode, &v);
+                if (!slow) emit_pair(T, o, rr, c, v);
+            }
+            const unsigned ms = __ballot_sync(0xFFFFFFFFu, slow);
+            if (slow) T.ring[warp][1][(ts + __popc(ms & lt)) & (kRing - 1)] = (unsigned short)e;
+            ts += __popc(ms);
+            hf += cnt;
+        }
+        while (ts - hs >= 32 || (last && ts > hs)) {
+            const int cnt = min(ts - hs, 32);
+            __syncwarp();
+            const int e = T.ring[warp][1][(hs + lane) & (kRing - 1)];
+            __syncwarp();
+            if (lane < cnt) {
+                const int rr = e >> 5, c = warp * 32 + (e & 31);
+                emit_pair(T, o, rr, c, slow_pair_iou(rows, o.r0 + rr, cols, o.c0 + c, D, kind, mode, edge, dense));
+            }
+            hs += cnt;
+        }
+    }
+    // ---- merge the tile's max/argmax into the global keys
+    if (o.want_row || o.want_col) {
+        __syncthreads();
+        if (o.want_row && tid < nr) {
+            const unsigned long long key = T.rkey[tid];
+            if (key != 0ull && key > row_key[o.r0 + tid]) atomicMax(&row_key[o.r0 + tid], key);
+        }
+        if (o.want_col && col_ok) {
+            const unsigned long long key = T.ckey[tid];
+            if (key != 0ull && key > col_key[o.c0 + tid]) atomicMax(&col_key[o.c0 + tid], key);
         }
     }
 }
@@ -329,6 +614,16 @@ __global__ void __launch_bounds__(kThreads) k_probe_fp32(int iters, float* __res
     sink[(size_t)blockIdx.x * kThreads + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 
+inline int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline unsigned blocks_for(int64_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
 
@@ -365,22 +660,32 @@ int sphk_iou_aligned(int kind, const float* b1, const float* b2, int64_t P, int 
     if (!b1 || !b2 || !out) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_aligned: null pointer");
     cudaStream_t s = (cudaStream_t)stream;
     const bool v = aligned16(b1) && aligned16(b2);
-    const unsigned g = blocks_for(P);
-    if (kind == SPHK_KIND_SPH) k_iou_aligned<KIND_SPH, 4><<<g, kThreads, 0, s>>>(b1, b2, P, mode, edge, out, v, g_dense != 0);
-    else if (kind == SPHK_KIND_FOV) k_iou_aligned<KIND_FOV, 4><<<g, kThreads, 0, s>>>(b1, b2, P, mode, edge, out, v, g_dense != 0);
-    else if (kind == SPHK_KIND_SPH2POB_EFFICIENT && D == 4)
-        k_iou_aligned<KIND_SPH2POB_EFFICIENT, 4><<<g, kThreads, 0, s>>>(b1, b2, P, mode, edge, out, v, g_dense != 0);
-    else if (kind == SPHK_KIND_SPH2POB_EFFICIENT)
-        k_iou_aligned<KIND_SPH2POB_EFFICIENT, 5><<<g, kThreads, 0, s>>>(b1, b2, P, mode, edge, out, v, g_dense != 0);
-    else if (D == 4) k_iou_aligned<KIND_SPH2POB_STANDARD, 4><<<g, kThreads, 0, s>>>(b1, b2, P, mode, edge, out, v, g_dense != 0);
-    else k_iou_aligned<KIND_SPH2POB_STANDARD, 5><<<g, kThreads, 0, s>>>(b1, b2, P, mode, edge, out, v, g_dense != 0);
+    if (kind == SPHK_KIND_SPH || kind == SPHK_KIND_FOV) {
+        const unsigned g = blocks_for(P);
+        if (kind == SPHK_KIND_SPH) k_iou_aligned<KIND_SPH, 4><<<g, kThreads, 0, s>>>(b1, b2, P, mode, edge, out, v, g_dense != 0);
+        else k_iou_aligned<KIND_FOV, 4><<<g, kThreads, 0, s>>>(b1, b2, P, mode, edge, out, v, g_dense != 0);
+    } else {
+        // pairs per warp = 32 * iters: enough warps for ~2 waves of 4 CTAs per SM, at most 512 pairs per warp
+        const int sms = sm_count();
+        int64_t iters = (P + (int64_t)kThreads * 8 * sms - 1) / ((int64_t)kThreads * 8 * sms);
+        iters = iters < 1 ? 1 : (iters > 16 ? 16 : iters);
+        const int64_t per_cta = (int64_t)kThreads * iters;
+        const int64_t g64 = (P + per_cta - 1) / per_cta;
+        if (g64 > 0x7FFFFFFFll) return fail(SPHK_ERR_UNSUPPORTED, "sphk_iou_aligned: P too large; split the call");
+        const unsigned g = (unsigned)g64;
+        if (D == 4) k_iou_aligned2<4><<<g, kThreads, 0, s>>>(b1, b2, P, kind, mode, edge, out, (int)iters, v, g_dense != 0);
+        else k_iou_aligned2<5><<<g, kThreads, 0, s>>>(b1, b2, P, kind, mode, edge, out, (int)iters, false, g_dense != 0);
+    }
     SPHK_LAUNCH_CHECK("k_iou_aligned");
     return SPHK_OK;
 }
 
+static inline int64_t keys_bytes(int64_t R, int64_t C) { return ((R + C) * (int64_t)sizeof(unsigned long long) + 15) & ~15ll; }
+
 int64_t sphk_iou_pairwise_workspace_bytes(int64_t R, int64_t C) {
     if (R < 0 || C < 0) return 0;
-    return (R + C) * (int64_t)sizeof(unsigned long long);
+    // packed max/argmax keys of rows and columns, then the per-box precompute (BoxRec + BoxCull per box)
+    return keys_bytes(R, C) + (R + C) * (int64_t)((kBoxRecFloats + kBoxCullFloats) * sizeof(float));
 }
 
 int sphk_iou_pairwise(int kind, const float* rows, int64_t R, const float* cols, int64_t C, int D, int mode, int edge,
@@ -390,14 +695,16 @@ int sphk_iou_pairwise(int kind, const float* rows, int64_t R, const float* cols,
     if (kind < 0 || kind > 3) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: unknown kind");
     if (mode != SPHK_MODE_IOU && mode != SPHK_MODE_IOF) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: unknown mode");
     if (edge < 0 || edge > 2) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: unknown edge");
-    if ((kind == SPHK_KIND_SPH || kind == SPHK_KIND_FOV) && (D != 4 || mode != SPHK_MODE_IOU))
+    const bool approx = (kind == SPHK_KIND_SPH || kind == SPHK_KIND_FOV);
+    if (approx && (D != 4 || mode != SPHK_MODE_IOU))
         return fail(SPHK_ERR_UNSUPPORTED, "sph_iou / fov_iou take BFoV boxes (D = 4) and mode 'iou' only");
     if (out && ld < C) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: ld < C");
     if (R + (int64_t)(uint32_t)row_base > 0xFFFFFFFFll || C + (int64_t)(uint32_t)col_base > 0xFFFFFFFFll)
         return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: indices do not fit 32 bits");
     const bool want_row = row_max || row_arg, want_col = col_max || col_arg;
-    if ((want_row || want_col) && !workspace && (R + C) > 0)
-        return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: workspace required for max/argmax outputs");
+    if ((want_row || want_col || !approx) && !workspace && (R + C) > 0)
+        return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: workspace of sphk_iou_pairwise_workspace_bytes(R, C) required");
+    if (workspace && !aligned16(workspace)) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: workspace must be 16-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
     unsigned long long* rkey = want_row ? (unsigned long long*)workspace : nullptr;
     unsigned long long* ckey = want_col ? (unsigned long long*)workspace + R : nullptr;
@@ -405,20 +712,42 @@ int sphk_iou_pairwise(int kind, const float* rows, int64_t R, const float* cols,
     if (want_col && C > 0) k_fill_keys<<<blocks_for(C), kThreads, 0, s>>>(ckey, C);
     if (R > 0 && C > 0) {
         if (!rows || !cols) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: null box pointer");
-        const int64_t col_tiles = (C + kThreads - 1) / kThreads, row_tiles = (R + kTileRows - 1) / kTileRows;
-        if (col_tiles * row_tiles > 0x7FFFFFFFll) return fail(SPHK_ERR_UNSUPPORTED, "sphk_iou_pairwise: grid too large; shard the call");
-        const unsigned g = (unsigned)(col_tiles * row_tiles);
+        const int64_t col_tiles = (C + kThreads - 1) / kThreads;
         const bool v = aligned16(cols);
-#define SPHK_PW(K, DD)                                                                                           \
-    k_iou_pairwise<K, DD><<<g, kThreads, 0, s>>>(rows, R, cols, C, mode, edge, out, ld, rkey, ckey, (uint32_t)row_base, \
-                                                  (uint32_t)col_base, col_tiles, v, g_dense != 0)
-        if (kind == SPHK_KIND_SPH) SPHK_PW(KIND_SPH, 4);
-        else if (kind == SPHK_KIND_FOV) SPHK_PW(KIND_FOV, 4);
-        else if (kind == SPHK_KIND_SPH2POB_EFFICIENT && D == 4) SPHK_PW(KIND_SPH2POB_EFFICIENT, 4);
-        else if (kind == SPHK_KIND_SPH2POB_EFFICIENT) SPHK_PW(KIND_SPH2POB_EFFICIENT, 5);
-        else if (D == 4) SPHK_PW(KIND_SPH2POB_STANDARD, 4);
-        else SPHK_PW(KIND_SPH2POB_STANDARD, 5);
-#undef SPHK_PW
+        if (approx) {
+            const int64_t row_tiles = (R + kTileRows - 1) / kTileRows;
+            if (col_tiles * row_tiles > 0x7FFFFFFFll) return fail(SPHK_ERR_UNSUPPORTED, "sphk_iou_pairwise: grid too large; shard the call");
+            const unsigned g = (unsigned)(col_tiles * row_tiles);
+            if (kind == SPHK_KIND_SPH)
+                k_iou_pairwise<KIND_SPH, 4><<<g, kThreads, 0, s>>>(rows, R, cols, C, mode, edge, out, ld, rkey, ckey, (uint32_t)row_base,
+                                                                    (uint32_t)col_base, col_tiles, v, g_dense != 0);
+            else
+                k_iou_pairwise<KIND_FOV, 4><<<g, kThreads, 0, s>>>(rows, R, cols, C, mode, edge, out, ld, rkey, ckey, (uint32_t)row_base,
+                                                                    (uint32_t)col_base, col_tiles, v, g_dense != 0);
+        } else {
+            float4* rec = (float4*)((char*)workspace + keys_bytes(R, C));       // [R + C][4] rows first
+            float4* cull = rec + (R + C) * 4;                                    // [R + C][2]
+            if (D == 4) k_box_pre<4><<<blocks_for(R + C), kThreads, 0, s>>>(rows, R, cols, C, edge, rec, cull, aligned16(rows), v);
+            else k_box_pre<5><<<blocks_for(R + C), kThreads, 0, s>>>(rows, R, cols, C, edge, rec, cull, false, false);
+            // row-tile height: 32 when that already yields many CTAs per SM, else 8 so that the heavy
+            // (mostly-live) tiles are spread over more warps and the tail of the launch stays short
+            const int64_t tiles32 = col_tiles * ((R + 31) / 32);
+            int tr = (tiles32 >= 16ll * sm_count()) ? 32 : 8;
+            if (g_force_tr == 8 || g_force_tr == 16 || g_force_tr == 32) tr = g_force_tr;   // tuning hook (SPHK_TR)
+            const int64_t row_tiles = (R + tr - 1) / tr;
+            if (col_tiles * row_tiles > 0x7FFFFFFFll) return fail(SPHK_ERR_UNSUPPORTED, "sphk_iou_pairwise: grid too large; shard the call");
+            const unsigned g = (unsigned)(col_tiles * row_tiles);
+#define SPHK_PW2(DD, TR)                                                                                             \
+    k_iou_pairwise2<DD, TR><<<g, kThreads, 0, s>>>(rows, R, cols, C, rec, cull, kind, mode, edge, out, ld, rkey, ckey, \
+                                                    (uint32_t)row_base, (uint32_t)col_base, (uint32_t)col_tiles, g_dense != 0)
+            if (D == 4 && tr == 32) SPHK_PW2(4, 32);
+            else if (D == 4 && tr == 16) SPHK_PW2(4, 16);
+            else if (D == 4) SPHK_PW2(4, 8);
+            else if (tr == 32) SPHK_PW2(5, 32);
+            else if (tr == 16) SPHK_PW2(5, 16);
+            else SPHK_PW2(5, 8);
+#undef SPHK_PW2
+        }
         SPHK_LAUNCH_CHECK("k_iou_pairwise");
     }
     if (want_row && R > 0) k_unpack_keys<<<blocks_for(R), kThreads, 0, s>>>(rkey, R, row_max, row_arg, (uint32_t)col_base);

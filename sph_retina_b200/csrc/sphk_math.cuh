@@ -349,9 +349,13 @@ struct EdgeClip {
     float lo[4], hi[4];  // sides of box 1 (order: top y=+hh1, left x=-hw1, bottom, right): coordinate interval
 };
 
+// reciprocal to ~1 ulp: MUFU.RCP + one Newton step (the IEEE-rounded __frcp_rn costs 4x as much and the
+// clipper only needs the crossing parameters to fp32 rounding accuracy)
 SPHK_HD float rcp_f(float x) {
 #if defined(__CUDA_ARCH__)
-    return __frcp_rn(x);
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return fmaf(r, fmaf(-x, r, 1.0f), r);
 #else
     return 1.0f / x;
 #endif
@@ -384,15 +388,10 @@ SPHK_HD EdgeX clip_edge(float Px, float Py, float dx, float dy, float ix, float 
     return e;
 }
 
-SPHK_HD float riou_intersection(const ObbPair& o, RiouGeom* G, EdgeClip* E) {
-    float s1, c1, sr, cr;
-    sincos_f(o.a1, &s1, &c1);
-    sincos_f(o.a2 - o.a1, &sr, &cr);
-    sr = (sr == 0.0f) ? 1e-30f : sr;
-    cr = (cr == 0.0f) ? 1e-30f : cr;
-    const float dx = o.x2 - o.x1, dy = o.y2 - o.y1;
-    const float px = c1 * dx + s1 * dy, py = -s1 * dx + c1 * dy;      // R(-a1) (dx,dy)
-    G->px = px; G->py = py; G->cr = cr; G->sr = sr; G->c1 = c1; G->s1 = s1;
+// Intersection area of A = [-w1/2,w1/2] x [-h1/2,h1/2] with the box of size (w2,h2) centred at
+// (px,py) and rotated by r (cr = cos r, sr = sin r, neither exactly 0), everything in A's frame.
+SPHK_HD float riou_core(float px, float py, float cr, float sr, float w1, float h1, float w2, float h2, EdgeClip* E) {
+    struct { float w1, h1, w2, h2; } o = {w1, h1, w2, h2};
     const float hw1 = 0.5f * o.w1, hh1 = 0.5f * o.h1, hw2 = 0.5f * o.w2, hh2 = 0.5f * o.h2;
     const float icr = rcp_f(cr), isr = rcp_f(sr);
     const float iw2 = rcp_f(o.w2), ih2 = rcp_f(o.h2);
@@ -460,6 +459,18 @@ SPHK_HD float riou_intersection(const ObbPair& o, RiouGeom* G, EdgeClip* E) {
     area2 = fmaf(lh, hh1, area2);
     area2 = fmaf(lv, hw1, area2);
     return 0.5f * area2;
+}
+
+SPHK_HD float riou_intersection(const ObbPair& o, RiouGeom* G, EdgeClip* E) {
+    float s1, c1, sr, cr;
+    sincos_f(o.a1, &s1, &c1);
+    sincos_f(o.a2 - o.a1, &sr, &cr);
+    sr = (sr == 0.0f) ? 1e-30f : sr;
+    cr = (cr == 0.0f) ? 1e-30f : cr;
+    const float dx = o.x2 - o.x1, dy = o.y2 - o.y1;
+    const float px = c1 * dx + s1 * dy, py = -s1 * dx + c1 * dy;      // R(-a1) (dx,dy)
+    G->px = px; G->py = py; G->cr = cr; G->sr = sr; G->c1 = c1; G->s1 = s1;
+    return riou_core(px, py, cr, sr, o.w1, o.h1, o.w2, o.h2, E);
 }
 
 // IoU / IoF of an oriented box pair + the final clamp(0,1) of sph_iou_api.py:86.

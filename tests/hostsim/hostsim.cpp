@@ -3,6 +3,7 @@
 // golden vectors.  The product package never loads this library: the product path is the CUDA
 // C-ABI library and fails loudly without a GPU.
 #include "../../sph_retina_b200/csrc/sphk_math.cuh"
+#include "../../sph_retina_b200/csrc/sphk_fast.cuh"
 #ifdef SPHK_WITH_GRAD
 #include "../../sph_retina_b200/csrc/sphk_grad.cuh"
 #endif
@@ -23,6 +24,39 @@ void hostsim_iou_aligned(int kind, const float* b1, const float* b2, long P, int
         const RawBox x = load_box(b1, i, D), y = load_box(b2, i, D);
         out[i] = (kind == KIND_SPH || kind == KIND_FOV) ? approx_iou_pair(x, y, kind)
                                                         : sph2pob_iou_pair(x, y, D, kind, mode, edge);
+    }
+}
+
+// The N x M formulation (csrc/sphk_fast.cuh): per-box precompute, prefilter, fast path with fallback.
+// path[i] (optional): 0 = prefilter said disjoint, 1 = fast path, 2 = reference-order path.
+void hostsim_iou_aligned_v2(int kind, const float* b1, const float* b2, long P, int D, int mode, int edge, float* out,
+                            unsigned char* path) {
+    for (long i = 0; i < P; ++i) {
+        const RawBox x = load_box(b1, i, D), y = load_box(b2, i, D);
+        BoxRec gr, pr;
+        BoxCull gc, pc;
+        box_pre(x, 1, D, edge, &gr, &gc);
+        box_pre(y, 2, D, edge, &pr, &pc);
+        if (pre_disjoint(gc, pc)) { out[i] = 0.0f; if (path) path[i] = 0; continue; }
+        float v;
+        if (pair_fast(gr, pr, D, kind, mode, &v)) { out[i] = v; if (path) path[i] = 1; continue; }
+        out[i] = sph2pob_iou_pair(x, y, D, kind, mode, edge);
+        if (path) path[i] = 2;
+    }
+}
+
+// The aligned formulation: per-pair records, dead test on the exact arc, job + clip stages.
+void hostsim_iou_aligned_v3(int kind, const float* b1, const float* b2, long P, int D, int mode, int edge, float* out,
+                            unsigned char* path) {
+    for (long i = 0; i < P; ++i) {
+        const RawBox x = load_box(b1, i, D), y = load_box(b2, i, D);
+        BoxRec gr, pr;
+        box_rec(x, 1, D, edge, &gr);
+        box_rec(y, 2, D, edge, &pr);
+        ClipJob job;
+        const int st = pair_job(gr, pr, D, kind, true, &job);
+        if (path) path[i] = (st == JOB_DEAD) ? 0 : (st == JOB_READY ? 1 : 2);
+        out[i] = (st == JOB_DEAD) ? 0.0f : (st == JOB_READY ? clip_job_iou(job, mode) : sph2pob_iou_pair(x, y, D, kind, mode, edge));
     }
 }
 

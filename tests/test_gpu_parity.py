@@ -150,7 +150,13 @@ def test_pairwise_equals_aligned_on_the_expansion(api, kind, R, C):
     fn = getattr(api.iou, kind)
     mat = fn(rows, cols)
     flat = fn(rows.repeat_interleave(C, 0), cols.repeat(R, 1), is_aligned=True)
-    assert torch.equal(mat.reshape(-1), flat)
+    if kind in ("sph_iou", "fov_iou"):
+        assert torch.equal(mat.reshape(-1), flat)
+    else:
+        # the N x M kernel evaluates far-apart pairs through its precompute/fast path, the aligned kernel
+        # through the reference-order path: equal up to fp32 rounding, and exact zeros agree
+        assert float((mat.reshape(-1) - flat).abs().max()) < 2e-6
+        assert torch.equal(mat.reshape(-1) == 0, flat == 0)
 
 
 def test_fused_max_argmax(api):

@@ -23,6 +23,18 @@ def hs_aligned(lib, kind, b1, b2, mode=0, edge=0):
     return out
 
 
+def hs_fast(lib, fn, kind, b1, b2, mode=0, edge=0):
+    """csrc/sphk_fast.cuh on the host: fn = hostsim_iou_aligned_v2 (N x M formulation: precompute, prefilter, fast
+    path) or hostsim_iou_aligned_v3 (aligned formulation: job + clip stages).  Returns (iou, path) with
+    path 0 = culled as disjoint, 1 = fast path, 2 = reference-order path."""
+    b1, b2 = np.ascontiguousarray(b1, np.float32), np.ascontiguousarray(b2, np.float32)
+    P, D = b1.shape
+    out, path = np.empty(P, np.float32), np.empty(P, np.uint8)
+    getattr(lib, fn)(kind, b1.ctypes.data_as(fp), b2.ctypes.data_as(fp), ctypes.c_long(P), D, mode, edge,
+                     out.ctypes.data_as(fp), path.ctypes.data_as(ctypes.POINTER(ctypes.c_ubyte)))
+    return out, path
+
+
 def hs_loss(lib, pred, target, grad_iou):
     p, t = np.ascontiguousarray(pred, np.float32), np.ascontiguousarray(target, np.float32)
     n, D = p.shape
@@ -97,3 +109,41 @@ def test_loss_gradients(hostsim, box):
         assert np.median(rel[live]) < 2e-6
         # the kernel is (much) closer to the fp64 truth than the fp32 reference is
         assert (rel[live] > 1e-4).sum() < 0.5 * (rel32[live] > 1e-4).sum()
+
+
+@pytest.mark.parametrize("fn", ["hostsim_iou_aligned_v2", "hostsim_iou_aligned_v3"])
+@pytest.mark.parametrize("box", ["bfov", "rbfov"])
+def test_fast_formulations_golden(hostsim, fn, box):
+    """The precompute / prefilter / fast-path formulation used by the N x M and aligned kernels."""
+    g = load_golden("aligned_" + box)
+    for kind, tr in ((0, "efficient"), (1, "standard")):
+        for key, mode, edge in (("iou", 0, 0), ("iof", 1, 0), ("chord", 0, 1), ("tangent", 0, 2)):
+            got, path = hs_fast(hostsim, fn, kind, g["b1"], g["b2"], mode, edge)
+            truth = g["%s_%s_f64" % (tr, key)]
+            ok, err = within(got, truth, g["%s_%s_f32" % (tr, key)])
+            ok |= degenerate_pairs(g["b1"], g["b2"]) & (err < 1e-3)
+            assert ok.all(), (fn, box, tr, key, np.where(~ok)[0], err[~ok])
+            assert not ((path == 0) & (truth > 0)).any()        # a culled pair is exactly 0 in the reference
+            assert (path == 1).sum() > 1000                       # the fast path is what is being tested
+
+
+@pytest.mark.parametrize("fn", ["hostsim_iou_aligned_v2", "hostsim_iou_aligned_v3"])
+def test_fast_formulations_equal_reference_order_path(hostsim, fn):
+    """Fast path vs the reference-order path of the same header on random, thin and huge boxes."""
+    rng = np.random.RandomState(3)
+    n = 200_000
+    def boxes():
+        b = np.stack([rng.uniform(0, 360, n), rng.uniform(0, 180, n), rng.uniform(0.5, 179, n), rng.uniform(0.5, 179, n),
+                      rng.uniform(-90, 90, n)], axis=1).astype(np.float32)
+        b[::3, 3] = rng.uniform(0.3, 3, len(b[::3]))         # thin boxes
+        b[::7, 2] = rng.uniform(170, 400, len(b[::7]))       # oversize (clamped to 180 - eps)
+        b[::11, 0] = 0.0                                     # on the seam (clamped to eps / 2 eps)
+        b[::13, 1] = 0.0
+        return b
+    b1, b2 = boxes(), boxes()
+    for kind in (0, 1):
+        want = hs_aligned(hostsim, kind, b1, b2)
+        got, path = hs_fast(hostsim, fn, kind, b1, b2)
+        assert np.abs(got - want).max() < 5e-6
+        assert not ((path == 0) & (want > 0)).any()
+        assert (path == 1).mean() > 0.3
