@@ -39,6 +39,17 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# stdout carries exactly ONE line (the JSON).  Libraries print there too (NCCL's version banner):
+# route fd 1 to stderr for the whole run and keep the real stdout for the final line.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 # ---------------------------------------------------------------------------------------------------
 # helpers
 # ---------------------------------------------------------------------------------------------------
@@ -212,7 +223,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -238,7 +249,7 @@ def other_configs(torch, native, dev, flush):
     """The remaining BASELINE.json configurations, timed briefly on one GPU (kernel time, inputs resident)."""
     from sph_retina_b200 import synthetic as S
     from sph_retina_b200.sphdet.bbox.nms import sph_batched_nms_images
-    from sph_retina_b200.sphdet.iou import fov_iou, sph2pob_efficient_iou, sph_iou, sph_max_overlaps
+    from sph_retina_b200.sphdet.iou import SphOverlaps2D, fov_iou, sph2pob_efficient_iou, sph_iou, sph_max_overlaps
     from sph_retina_b200.sphdet.losses import Sph2PobIoULoss
     out = {}
     n = 1_000_000
@@ -271,6 +282,13 @@ def other_configs(torch, native, dev, flush):
     out["nms_64img_1000box_80cls"] = {"ms": ms, "images_per_s": 64 / ms * 1e3}
     ms = quick(torch, lambda: sph_batched_nms_images(boxes, scores, torch.zeros_like(labels), image_ids, 0.5), iters=5, flush=flush)
     out["nms_64img_1000box_class_agnostic"] = {"ms": ms, "images_per_s": 64 / ms * 1e3}
+    # configs[1] again, but all 16 images' GT in ONE call (legal whenever the anchors are shared by the images, as in
+    # RetinaNet: SURVEY.md 3.1 "same anchors for every image"): [16*32, 98208] in two launches instead of 32
+    gts, anchors = S.assignment_batch(IMAGES, GTS)
+    gts, anchors = gts.to(dev), anchors.to(dev)
+    calc = SphOverlaps2D('sph2pob_efficient_iou', 5)
+    ms = quick(torch, lambda: calc(gts.view(-1, 5), anchors).view(IMAGES, GTS, -1), flush=flush)
+    out["assign_16img_one_call"] = {"ms": ms, "pairs_per_s": IMAGES * GTS * anchors.size(0) / ms * 1e3}
     A = S.generate_boxes(1 << 20, alpha_range=(1, 100), beta_range=(1, 100), box="rbfov", seed=0).to(dev)
     G = S.generate_boxes(1024, alpha_range=(1, 100), beta_range=(1, 100), box="rbfov", seed=1).to(dev)
     ms = quick(torch, lambda: sph_max_overlaps(A, G), iters=3, warmup=1, flush=flush)
@@ -452,7 +470,7 @@ def run_ours(args):
                     line["other_configs"] = other_configs(torch, native, dev, flush)
                 except Exception as e:   # the headline line must still be printed
                     line["other_configs"] = {"error": repr(e)}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

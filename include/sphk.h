@@ -77,9 +77,10 @@ int sphk_iou_pairwise(int kind, const float* rows, int64_t R, const float* cols,
  * sph2pob_standard, jitter_2) followed by diff_iou_rotated_2d(...).clamp(0,1)
  * (sphdet/losses/sph2pob_iou_loss.py:122) and its autograd backward.
  *   iou        [n]      clamped IoU of (pred[i], target[i])
- *   grad_iou   [n]      upstream d(total)/d(iou[i]) or NULL (then no gradients are produced)
+ *   grad_iou   [n]      upstream d(total)/d(iou[i]); NULL = 1 for every row (the outputs are then
+ *                       d(iou[i])/d(box) itself)
  *   grad_pred  [n, D]   d(total)/d(pred)   (NULL to skip)
- *   grad_target[n, D]   d(total)/d(target) (NULL to skip)  */
+ *   grad_target[n, D]   d(total)/d(target) (NULL to skip); both NULL = forward only  */
 int sphk_loss_fwd_bwd(const float* pred, const float* target, int64_t n, int D, float* iou, const float* grad_iou,
                       float* grad_pred, float* grad_target, void* stream);
 

@@ -186,15 +186,16 @@ def iou_pairwise(kind: str, rows, cols, mode="iou", edge="arc", want_matrix=True
 
 
 def loss_fwd_bwd(pred, target, grad_iou=None, want_grad_pred=False, want_grad_target=False):
-    """Fused Sph2Pob (standard transform) IoU of aligned pairs and, if grad_iou is given, its gradients."""
+    """Fused Sph2Pob (standard transform) IoU of aligned pairs and its gradients w.r.t. pred / target
+    (scaled by grad_iou if given, else d(iou)/d(box) itself)."""
     global launches
     pred, target = _boxes(pred, "pred"), _boxes(target, "target")
     if pred.shape != target.shape:
         raise SphkError("pred/target shapes differ: %s vs %s" % (tuple(pred.shape), tuple(target.shape)))
     n, dev = pred.size(0), pred.device
     iou = torch.empty(n, dtype=torch.float32, device=dev)
-    gp = torch.empty_like(pred) if (grad_iou is not None and want_grad_pred) else None
-    gt = torch.empty_like(target) if (grad_iou is not None and want_grad_target) else None
+    gp = torch.empty_like(pred) if want_grad_pred else None
+    gt = torch.empty_like(target) if want_grad_target else None
     if grad_iou is not None:
         grad_iou = grad_iou.to(device=dev, dtype=torch.float32).contiguous()
         assert grad_iou.numel() == n
@@ -233,7 +234,7 @@ def obb_bwd(kind: str, b1, b2, g1, g2, edge="arc", want1=True, want2=True):
     return gb1, gb2
 
 
-def riou_fwd_bwd(o1, o2, grad_iou=None, want1=True, want2=True):
+def riou_fwd_bwd(o1, o2, grad_iou=None, want1=False, want2=False):
     global launches
     if not (o1.is_cuda and o2.is_cuda):
         raise SphkError("rotated IoU: OBB tensors must be CUDA tensors (no CPU fallback)")
@@ -241,8 +242,8 @@ def riou_fwd_bwd(o1, o2, grad_iou=None, want1=True, want2=True):
     assert o1.shape == o2.shape and o1.dim() == 2 and o1.size(1) == 5
     n, dev = o1.size(0), o1.device
     iou = torch.empty(n, dtype=torch.float32, device=dev)
-    g1 = torch.empty_like(o1) if (grad_iou is not None and want1) else None
-    g2 = torch.empty_like(o2) if (grad_iou is not None and want2) else None
+    g1 = torch.empty_like(o1) if want1 else None
+    g2 = torch.empty_like(o2) if want2 else None
     if grad_iou is not None:
         grad_iou = grad_iou.to(device=dev, dtype=torch.float32).contiguous()
     with _on_device(dev):

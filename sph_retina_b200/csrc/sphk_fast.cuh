@@ -165,4 +165,86 @@ SPHK_HD bool pair_fast(const BoxRec& g, const BoxRec& p, int D, int kind, int mo
     return true;
 }
 
+// ---- aligned pairs: two-stage evaluation (no per-box reuse, so nothing is precomputed) ---------------
+// Stage 1 runs for every pair: jitter_1 (similarity mask + clamps), three degree-domain sincos, hav, and a
+// conservative dead test that needs neither asin nor sqrt of hav: a series lower bound of
+// arc = 2 asin(sqrt(hav)) is compared with r_g + r_p in squared form.  Stage 2 (survivors only, warp-compacted by the kernel)
+// finishes the transform (arc, internal angles as sin/cos, gamma, jitter_2 checks) into a ClipJob.
+struct PairS1 {
+    float hav, sdt, cdt, sdp, cdp;   // sin^2(arc/2); sin/cos(dtheta/2); sin/cos(dphi/2)
+    float s1, c1, s2, c2;            // sin/cos phi of box 1 and box 2
+    float w1, h1, w2, h2;            // planar edges (rad)
+    float g1, g2;                    // gamma (deg)
+};
+
+SPHK_HD int pair_stage1(const RawBox& x, const RawBox& y, int D, int edge, bool cull, PairS1* s) {
+    bool sim = (fabsf(x.t - y.t) < kEps) | (fabsf(x.p - y.p) < kEps) | (fabsf(x.a - y.a) < kEps) | (fabsf(x.b - y.b) < kEps);
+    if (D == 5) sim = sim | (fabsf(x.g - y.g) < kEps);
+    // jitter_1 clamps of the unshifted boxes (sph_iou_api.py:249-258).  A centre within 1e-3 deg of the upper
+    // range end needs the hi + lo arithmetic of the reference-order path: flagged slow (as are NaNs).
+    bool slow = sim | !(x.t <= 359.999f) | !(y.t <= 359.999f) | !(x.p <= 179.999f) | !(y.p <= 179.999f);
+    const float t1 = fmaxf(x.t, kEps2), p1 = fmaxf(x.p, kEps2);
+    const float t2 = fmaxf(y.t, kEps), p2 = fmaxf(y.p, kEps);
+    const float a1 = clampf(x.a, kEps2, (float)(180.0 - SPHK_EPS_D)), b1 = clampf(x.b, kEps2, (float)(180.0 - SPHK_EPS_D));
+    const float a2 = clampf(y.a, kEps, (float)(180.0 - 2 * SPHK_EPS_D)), b2 = clampf(y.b, kEps, (float)(180.0 - 2 * SPHK_EPS_D));
+    s->w1 = edge_len_deg(a1, edge); s->h1 = edge_len_deg(b1, edge);
+    s->w2 = edge_len_deg(a2, edge); s->h2 = edge_len_deg(b2, edge);
+    slow = slow | !(s->w1 >= 2.0f * kMinWh1) | !(s->h1 >= 2.0f * kMinWh1) | !(s->w2 >= 2.0f * kMinWh1) | !(s->h2 >= 2.0f * kMinWh1);
+    s->g1 = 0.0f; s->g2 = 0.0f;
+    if (D == 5) {
+        s->g1 = x.g; s->g2 = y.g;
+        slow = slow | !(fabsf(x.g) <= 179.0f) | !(fabsf(y.g) <= 179.0f);
+    }
+    if (slow) return JOB_SLOW;
+    sincos_deg(0.5f * (t2 - t1), 0.0f, &s->sdt, &s->cdt);
+    sincos_deg(0.5f * (p2 - p1), 0.0f, &s->sdp, &s->cdp);
+    sincos_deg(p1, 0.0f, &s->s1, &s->c1);
+    // phi_2 = phi_1 + dphi: angle addition instead of a fourth sincos
+    const float sd = 2.0f * s->sdp * s->cdp, cd = fmaf(-2.0f * s->sdp, s->sdp, 1.0f);
+    s->s2 = fmaf(s->s1, cd, s->c1 * sd);
+    s->c2 = fmaf(s->c1, cd, -s->s1 * sd);
+    s->hav = fmaf(s->s1 * s->s2, s->sdt * s->sdt, s->sdp * s->sdp);
+    if (cull) {
+        // (r_g + r_p)^2 with r = circumradius + margin; the rsqrt-based sqrt is within 2 ulp, far inside the margin
+        const float q1 = fmaf(s->w1, s->w1, s->h1 * s->h1), q2 = fmaf(s->w2, s->w2, s->h2 * s->h2);
+        const float R = fmaf(0.5f * (q1 * rsqrt_f(q1) + q2 * rsqrt_f(q2)), 1.0002f, 8e-4f);
+        // asin(x) >= x (1 + x^2/6 + 3 x^4/40) on [0, 1]: a lower bound of arc/2 from hav = x^2 alone
+        const float k = fmaf(s->hav, fmaf(s->hav, 0.075f, 0.16666667f), 1.0f);
+        if (4.0f * s->hav * k * k > R * R) return JOB_DEAD;
+    }
+    return JOB_READY;
+}
+
+SPHK_HD int pair_stage2(const PairS1& s, int D, int kind, ClipJob* job) {
+    const float hth = s.sdt * s.sdt;
+    const float sin_dth = 2.0f * s.sdt * s.cdt, sin_dph = 2.0f * s.sdp * s.cdp;
+    const float arc = arc_from_hav(s.hav);
+    if (!(arc > 2e-3f && arc < 3.14f)) return JOB_SLOW;
+    const float ng = fmaf(-2.0f * s.c1 * s.s2, hth, sin_dph), mg = -s.s2 * sin_dth;
+    const float np = fmaf(2.0f * s.c2 * s.s1, hth, sin_dph), mp = -s.s1 * sin_dth;
+    const float S2g = fmaf(ng, ng, mg * mg), S2p = fmaf(np, np, mp * mp);
+    if (!(S2g > 1e-30f && S2p > 1e-30f)) return JOB_SLOW;
+    const float ig = rsqrt_f(S2g), ip = rsqrt_f(S2p);
+    const float sag = ng * ig, cag = mg * ig, sap = np * ip, cap = mp * ip;
+    float c1 = cag, s1 = sag, c2 = cap, s2 = sap;
+    if (D == 5) {
+        float sg1, cg1, sg2, cg2;
+        sincos_deg(s.g1, 0.0f, &sg1, &cg1);
+        sincos_deg(s.g2, 0.0f, &sg2, &cg2);
+        c1 = fmaf(cag, cg1, sag * sg1); s1 = fmaf(sag, cg1, -cag * sg1);
+        c2 = fmaf(cap, cg2, sap * sg2); s2 = fmaf(sap, cg2, -cap * sg2);
+    }
+    const bool near_axis = (kind == KIND_SPH2POB_STANDARD) ? (fabsf(s1) < 1e-3f || fabsf(s2) < 1e-3f)
+                                                           : (fabsf(sag) < 1e-3f || fabsf(sap) < 1e-3f);
+    if (near_axis) return JOB_SLOW;
+    const float cr = fmaf(c2, c1, s2 * s1), sr = fmaf(s2, c1, -c2 * s1);
+    if (fabsf(s.w1 - s.w2) < 2e-4f || fabsf(s.h1 - s.h2) < 2e-4f) return JOB_SLOW;
+    if (cr > 0.0f && fabsf(sr) < 2e-3f) return JOB_SLOW;
+    job->sr = (sr == 0.0f) ? 1e-30f : sr;
+    job->cr = (cr == 0.0f) ? 1e-30f : cr;
+    job->px = c1 * arc; job->py = -s1 * arc;
+    job->w1 = s.w1; job->h1 = s.h1; job->w2 = s.w2; job->h2 = s.h2;
+    return JOB_READY;
+}
+
 }  // namespace sphk

@@ -86,6 +86,20 @@ __device__ __noinline__ float slow_pair_iou(const float* __restrict__ b1, int64_
     return sph2pob_iou_pair(x, y, D, kind, mode, edge, dense);
 }
 
+// One pair, cheapest applicable route: exact 0 if provably disjoint, the two-stage fast path, else the
+// out-of-line reference-order path (indices i1 / i2 into b1 / b2).
+__device__ __forceinline__ float pair_iou_any(const float* __restrict__ b1, int64_t i1, const float* __restrict__ b2,
+                                              int64_t i2, const RawBox& x, const RawBox& y, int D, int kind, int mode,
+                                              int edge) {
+    PairS1 s;
+    ClipJob j;
+    int st = pair_stage1(x, y, D, edge, true, &s);
+    if (st == JOB_READY) st = pair_stage2(s, D, kind, &j);
+    if (st == JOB_DEAD) return 0.0f;
+    if (st == JOB_READY) return clip_job_iou(j, mode);
+    return slow_pair_iou(b1, i1, b2, i2, D, kind, mode, edge, false);
+}
+
 // ---- aligned -----------------------------------------------------------------------------------
 template <int KIND, int D>
 __global__ void __launch_bounds__(kThreads) k_iou_aligned(const float* __restrict__ b1, const float* __restrict__ b2,
@@ -100,15 +114,16 @@ __global__ void __launch_bounds__(kThreads) k_iou_aligned(const float* __restric
     out[i] = v;
 }
 
-// ---- aligned, Sph2Pob kinds: transform stage per pair, clipping stage warp-compacted -----------------
-// Every pair pays the transform stage (pair_job: jitter clamps, four degree-domain sincos, arc, dead
-// test); only the pairs whose planar boxes can touch (26-40 % of random pairs) go on to the clipper,
-// and they do so compacted through a per-warp ring of ClipJobs in shared memory, 32 at a time.
-// Pairs on which a reference quirk may be active are queued for the reference-order path.
-constexpr int kJobRing = 64;
+// ---- aligned, Sph2Pob kinds: two stages, the second one warp-compacted ------------------------------
+// Stage 1 (pair_stage1) runs for every pair: jitter_1, three degree-domain sincos, hav, conservative dead
+// test -- about half of random pairs end here with an exact 0.  Survivors are ballot-compacted into a
+// per-warp ring of PairS1 records in shared memory; stage 2 (arc, internal angles, gamma, jitter_2 checks)
+// and the clipper then run 32 survivors at a time with full warps.  Pairs on which a reference quirk may be
+// active are queued for the out-of-line reference-order path.
+constexpr int kJobRing = 64, kS1Floats = 15;
 
 struct AlignedTile {
-    float job[kThreads / 32][8][kJobRing];
+    float s1[kThreads / 32][kS1Floats][kJobRing];
     unsigned short jidx[kThreads / 32][kJobRing];
     unsigned short sidx[kThreads / 32][kJobRing];
 };
@@ -127,43 +142,54 @@ k_iou_aligned2(const float* __restrict__ b1, const float* __restrict__ b2, int64
 #pragma unroll 1
     for (int it = 0; it <= iters; ++it) {
         const bool last = it == iters;
+        const int need = last ? 1 : 32;
         const int off = it * 32 + lane;
         const int64_t i = base + off;
         int st = JOB_DEAD;
-        ClipJob j;
-        j.px = j.py = j.cr = j.sr = j.w1 = j.h1 = j.w2 = j.h2 = 0.0f;
+        PairS1 q;
         if (!last && i < P) {
             const RawBox x = load_box<D>(b1, i, vec_ok), y = load_box<D>(b2, i, vec_ok);
-            BoxRec g, p;
-            box_rec(x, 1, D, edge, &g);
-            box_rec(y, 2, D, edge, &p);
-            st = pair_job(g, p, D, kind, !dense, &j);
+            st = pair_stage1(x, y, D, edge, !dense, &q);
             if (st == JOB_DEAD) out[i] = 0.0f;
         }
         const unsigned mj = __ballot_sync(0xFFFFFFFFu, st == JOB_READY);
         if (st == JOB_READY) {
             const int slot = (tj + __popc(mj & lt)) & (kJobRing - 1);
-            T.job[warp][0][slot] = j.px; T.job[warp][1][slot] = j.py; T.job[warp][2][slot] = j.cr; T.job[warp][3][slot] = j.sr;
-            T.job[warp][4][slot] = j.w1; T.job[warp][5][slot] = j.h1; T.job[warp][6][slot] = j.w2; T.job[warp][7][slot] = j.h2;
+            float (*r)[kJobRing] = T.s1[warp];
+            r[0][slot] = q.hav; r[1][slot] = q.sdt; r[2][slot] = q.cdt; r[3][slot] = q.sdp; r[4][slot] = q.cdp;
+            r[5][slot] = q.s1; r[6][slot] = q.c1; r[7][slot] = q.s2; r[8][slot] = q.c2;
+            r[9][slot] = q.w1; r[10][slot] = q.h1; r[11][slot] = q.w2; r[12][slot] = q.h2;
+            if (D == 5) { r[13][slot] = q.g1; r[14][slot] = q.g2; }
             T.jidx[warp][slot] = (unsigned short)off;
         }
         tj += __popc(mj);
-        const unsigned ms = __ballot_sync(0xFFFFFFFFu, st == JOB_SLOW);
+        unsigned ms = __ballot_sync(0xFFFFFFFFu, st == JOB_SLOW);
         if (st == JOB_SLOW) T.sidx[warp][(ts + __popc(ms & lt)) & (kJobRing - 1)] = (unsigned short)off;
         ts += __popc(ms);
-        if (tj - hj >= 32 || (last && tj > hj)) {
+        if (tj - hj >= need) {
             const int cnt = min(tj - hj, 32);
             __syncwarp();
             const int slot = (hj + lane) & (kJobRing - 1);
-            ClipJob c;
-            c.px = T.job[warp][0][slot]; c.py = T.job[warp][1][slot]; c.cr = T.job[warp][2][slot]; c.sr = T.job[warp][3][slot];
-            c.w1 = T.job[warp][4][slot]; c.h1 = T.job[warp][5][slot]; c.w2 = T.job[warp][6][slot]; c.h2 = T.job[warp][7][slot];
+            const float (*r)[kJobRing] = T.s1[warp];
+            PairS1 c;
+            c.hav = r[0][slot]; c.sdt = r[1][slot]; c.cdt = r[2][slot]; c.sdp = r[3][slot]; c.cdp = r[4][slot];
+            c.s1 = r[5][slot]; c.c1 = r[6][slot]; c.s2 = r[7][slot]; c.c2 = r[8][slot];
+            c.w1 = r[9][slot]; c.h1 = r[10][slot]; c.w2 = r[11][slot]; c.h2 = r[12][slot];
+            c.g1 = (D == 5) ? r[13][slot] : 0.0f; c.g2 = (D == 5) ? r[14][slot] : 0.0f;
             const int o2 = T.jidx[warp][slot];
             __syncwarp();
-            if (lane < cnt) out[base + o2] = clip_job_iou(c, mode);
+            bool slow = false;
+            if (lane < cnt) {
+                ClipJob job;
+                slow = pair_stage2(c, D, kind, &job) != JOB_READY;
+                if (!slow) out[base + o2] = clip_job_iou(job, mode);
+            }
+            ms = __ballot_sync(0xFFFFFFFFu, slow);
+            if (slow) T.sidx[warp][(ts + __popc(ms & lt)) & (kJobRing - 1)] = (unsigned short)o2;
+            ts += __popc(ms);
             hj += cnt;
         }
-        if (ts - hs >= 32 || (last && ts > hs)) {
+        while (ts - hs >= need) {
             const int cnt = min(ts - hs, 32);
             __syncwarp();
             const int o2 = T.sidx[warp][(hs + lane) & (kJobRing - 1)];
@@ -263,6 +289,7 @@ template <int D>
 __global__ void __launch_bounds__(kThreads)
 k_box_pre(const float* __restrict__ rows, int64_t R, const float* __restrict__ cols, int64_t C, int edge,
           float4* __restrict__ rec, float4* __restrict__ cull, bool rows_vec, bool cols_vec) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // k_iou_pairwise2 may start its prologue
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (i >= R + C) return;
     const bool is_row = i < R;
@@ -323,20 +350,34 @@ __global__ void __launch_bounds__(kThreads)
 k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restrict__ cols, int64_t C,
                 const float4* __restrict__ rec, const float4* __restrict__ cull, int kind, int mode, int edge,
                 float* __restrict__ out, int64_t ld, unsigned long long* __restrict__ row_key,
-                unsigned long long* __restrict__ col_key, uint32_t row_base, uint32_t col_base, uint32_t col_tiles,
-                bool dense) {
+                unsigned long long* __restrict__ col_key, uint32_t row_base, uint32_t col_base, bool dense) {
     __shared__ __align__(16) PairTile<TR> T;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // heaviest tiles first: RetinaNet-style anchor lists end with the coarse pyramid levels, whose huge anchors
-    // overlap every GT, so the tail of the launch is made of the light tiles
-    const uint32_t bid = gridDim.x - 1u - blockIdx.x;
-    const uint32_t rt = bid / col_tiles, ct = bid - rt * col_tiles;
+    // grid = (row tiles, column tiles).  Column tiles are taken heaviest-first: RetinaNet-style anchor lists
+    // end with the coarse pyramid levels, whose huge anchors overlap every GT, so the tail of the launch is
+    // made of the light tiles.
+    const uint32_t rt = blockIdx.x, ct = gridDim.y - 1u - blockIdx.y;
     PairOut o;
     o.out = out; o.ld = ld; o.r0 = (int64_t)rt * TR; o.c0 = (int64_t)ct * kTC;
     o.want_row = row_key != nullptr; o.want_col = col_key != nullptr;
     o.row_base = row_base; o.col_base = col_base;
     const int nr = (int)min((int64_t)TR, R - o.r0);
     const bool col_ok = o.c0 + tid < C;
+    if (out) {
+        // zero-fill this warp's [nr x 32] part of the matrix; live pairs overwrite their entry later
+        // (ordered by the __syncthreads() below and the __syncwarp() in front of every batch)
+        float* base = out + o.r0 * ld + o.c0 + warp * 32;
+        const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0) && (o.c0 + warp * 32 + 32 <= C);
+        if (vec) {
+            for (int rr = lane >> 3; rr < nr; rr += 4)
+                *reinterpret_cast<float4*>(base + rr * ld + (lane & 7) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else if (col_ok) {
+            for (int rr = 0; rr < nr; ++rr) base[rr * ld + lane] = 0.0f;
+        }
+    }
+    // Programmatic dependent launch: everything above overlaps the tail of k_box_pre; its records are
+    // needed from here on.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     // ---- phase 0: stage the tile's records (columns: records -> shared memory, cull operands -> registers)
     stage_rec(T.crec, tid, rec + R * 4, o.c0 + tid, col_ok);
     T.ckey[tid] = 0ull;
@@ -362,19 +403,6 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
     const float pbias = col_ok ? (dense ? -1e30f : pc1.y) : 1e30f;
     int hf = 0, tf = 0, hs = 0, ts = 0;          // ring head / tail counters (fast, slow)
     const unsigned lt = (1u << lane) - 1u;
-    if (out) {
-        // zero-fill this warp's [nr x 32] part of the matrix; live pairs overwrite their entry later
-        // (ordered by the __syncwarp() in front of every batch)
-        float* base = out + o.r0 * ld + o.c0 + warp * 32;
-        const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0) && (o.c0 + warp * 32 + 32 <= C);
-        if (vec) {
-            for (int rr = lane >> 3; rr < nr; rr += 4)
-                *reinterpret_cast<float4*>(base + rr * ld + (lane & 7) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-        } else if (col_ok) {
-            for (int rr = 0; rr < nr; ++rr) base[rr * ld + lane] = 0.0f;
-        }
-    }
-
     // one extra iteration (r == nr) drains the rings, so that each batch body exists once in the code
 #pragma unroll 1
     for (int r = 0; r <= nr; ++r) {
@@ -391,7 +419,8 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
         const unsigned m = __ballot_sync(0xFFFFFFFFu, live);
         if (live) T.ring[warp][0][(tf + __popc(m & lt)) & (kRing - 1)] = (unsigned short)((r << 5) | lane);
         tf += __popc(m);
-        if (tf - hf >= 32 || (last && tf > hf)) {
+        const int need = last ? 1 : 32;           // the last iteration flushes whatever is pending
+        if (tf - hf >= need) {
             const int cnt = min(tf - hf, 32);
             __syncwarp();
             const int e = T.ring[warp][0][(hf + lane) & (kRing - 1)];
@@ -408,7 +437,7 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
             ts += __popc(ms);
             hf += cnt;
         }
-        while (ts - hs >= 32 || (last && ts > hs)) {
+        while (ts - hs >= need) {
             const int cnt = min(ts - hs, 32);
             __syncwarp();
             const int e = T.ring[warp][1][(hs + lane) & (kRing - 1)];
@@ -458,12 +487,13 @@ k_loss_fwd_bwd(const float* __restrict__ pred, const float* __restrict__ target,
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (i >= n) return;
     const RawBox x = load_box<D>(pred, i, vec_ok), y = load_box<D>(target, i, vec_ok);
-    if (grad_iou == nullptr) {
+    if (grad_pred == nullptr && grad_target == nullptr) {
         if (iou) iou[i] = sph2pob_iou_pair(x, y, D, KIND_SPH2POB_STANDARD, MODE_IOU, EDGE_ARC);
         return;
     }
     float g1[5], g2[5];
-    const float v = sph2pob_iou_pair_grad(x, y, D, KIND_SPH2POB_STANDARD, EDGE_ARC, __ldg(grad_iou + i), g1, g2);
+    const float up = grad_iou ? __ldg(grad_iou + i) : 1.0f;     // no upstream gradient given: d(iou)/d(box) itself
+    const float v = sph2pob_iou_pair_grad(x, y, D, KIND_SPH2POB_STANDARD, EDGE_ARC, up, g1, g2);
     if (iou) iou[i] = v;
     if (grad_pred) store_grad<D>(grad_pred, i, g1, vec_ok);
     if (grad_target) store_grad<D>(grad_target, i, g2, vec_ok);
@@ -527,7 +557,7 @@ k_riou_fwd_bwd(const float* __restrict__ obb1, const float* __restrict__ obb2, i
     const float* b = obb2 + i * 5;
     o.x1 = __ldg(a); o.y1 = __ldg(a + 1); o.w1 = __ldg(a + 2); o.h1 = __ldg(a + 3); o.a1 = __ldg(a + 4);
     o.x2 = __ldg(b); o.y2 = __ldg(b + 1); o.w2 = __ldg(b + 2); o.h2 = __ldg(b + 3); o.a2 = __ldg(b + 4);
-    if (grad_iou == nullptr) {
+    if (grad_obb1 == nullptr && grad_obb2 == nullptr) {
         if (iou) iou[i] = obb_disjoint(o) ? 0.0f : riou_value(o, MODE_IOU);
         return;
     }
@@ -537,7 +567,7 @@ k_riou_fwd_bwd(const float* __restrict__ obb1, const float* __restrict__ obb2, i
 #pragma unroll
         for (int k = 0; k < 5; ++k) { g1[k] = 0.0f; g2[k] = 0.0f; }
     } else {
-        v = riou_grad(o, MODE_IOU, __ldg(grad_iou + i), g1, g2);
+        v = riou_grad(o, MODE_IOU, grad_iou ? __ldg(grad_iou + i) : 1.0f, g1, g2);
     }
     if (iou) iou[i] = v;
     if (grad_obb1) store_grad<5>(grad_obb1, i, g1, false);
@@ -580,9 +610,9 @@ k_nms(const float* __restrict__ boxes, const int32_t* __restrict__ order, const 
             const int i = i0 + pi, j = (jw << 5) + lane;
             bool sup = false;
             if (!((dead_pivots >> pi) & 1u) && j < k && j > i && !((removed[jw] >> lane) & 1u)) {
-                const RawBox x = load_box<D>(boxes, order[start + i], vec_ok);
-                const RawBox y = load_box<D>(boxes, order[start + j], vec_ok);
-                sup = sph2pob_iou_pair(x, y, D, KIND_SPH2POB_EFFICIENT, MODE_IOU, EDGE_ARC) > thr;
+                const int bi = order[start + i], bj = order[start + j];
+                const RawBox x = load_box<D>(boxes, bi, vec_ok), y = load_box<D>(boxes, bj, vec_ok);
+                sup = pair_iou_any(boxes, bi, boxes, bj, x, y, D, KIND_SPH2POB_EFFICIENT, MODE_IOU, EDGE_ARC) > thr;
             }
             const uint32_t word = __ballot_sync(0xFFFFFFFFu, sup);
             if (lane == 0) mask[pi * W + jw] = word;
@@ -735,17 +765,34 @@ int sphk_iou_pairwise(int kind, const float* rows, int64_t R, const float* cols,
             int tr = (tiles32 >= 16ll * sm_count()) ? 32 : 8;
             if (g_force_tr == 8 || g_force_tr == 16 || g_force_tr == 32) tr = g_force_tr;   // tuning hook (SPHK_TR)
             const int64_t row_tiles = (R + tr - 1) / tr;
-            if (col_tiles * row_tiles > 0x7FFFFFFFll) return fail(SPHK_ERR_UNSUPPORTED, "sphk_iou_pairwise: grid too large; shard the call");
-            const unsigned g = (unsigned)(col_tiles * row_tiles);
-#define SPHK_PW2(DD, TR)                                                                                             \
-    k_iou_pairwise2<DD, TR><<<g, kThreads, 0, s>>>(rows, R, cols, C, rec, cull, kind, mode, edge, out, ld, rkey, ckey, \
-                                                    (uint32_t)row_base, (uint32_t)col_base, (uint32_t)col_tiles, g_dense != 0)
+            if (row_tiles > 0x7FFFFFFFll || col_tiles > 65535)
+                return fail(SPHK_ERR_UNSUPPORTED, "sphk_iou_pairwise: more than 16.7 M columns or 2^31 row tiles; shard the call");
+            // launched with programmatic stream serialization: the prologue (zero-fill of the matrix) overlaps
+            // k_box_pre, the kernel itself waits (griddepcontrol.wait) before it reads the records
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)row_tiles, (unsigned)col_tiles, 1);
+            cfg.blockDim = dim3(kThreads, 1, 1);
+            cfg.dynamicSmemBytes = 0;
+            cfg.stream = s;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            const float4* crec = rec;
+            const float4* ccull = cull;
+            const bool dn = g_dense != 0;
+            cudaError_t le;
+#define SPHK_PW2(DD, TR)                                                                                               \
+    le = cudaLaunchKernelEx(&cfg, k_iou_pairwise2<DD, TR>, rows, R, cols, C, crec, ccull, kind, mode, edge, out, ld, rkey, \
+                            ckey, (uint32_t)row_base, (uint32_t)col_base, dn)
             if (D == 4 && tr == 32) SPHK_PW2(4, 32);
             else if (D == 4 && tr == 16) SPHK_PW2(4, 16);
             else if (D == 4) SPHK_PW2(4, 8);
             else if (tr == 32) SPHK_PW2(5, 32);
             else if (tr == 16) SPHK_PW2(5, 16);
             else SPHK_PW2(5, 8);
+            if (le != cudaSuccess) return cuda_fail(le, "cudaLaunchKernelEx(k_iou_pairwise2)");
 #undef SPHK_PW2
         }
         SPHK_LAUNCH_CHECK("k_iou_pairwise");

@@ -31,8 +31,7 @@ class _Sph2PobIoU(torch.autograd.Function):
     def forward(ctx, pred, target):
         need_p, need_t = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         if need_p or need_t:
-            ones = torch.ones(pred.size(0), dtype=torch.float32, device=pred.device)
-            iou, gp, gt = _native.loss_fwd_bwd(pred.detach(), target.detach(), ones, need_p, need_t)
+            iou, gp, gt = _native.loss_fwd_bwd(pred.detach(), target.detach(), None, need_p, need_t)
             ctx.save_for_backward(*[g for g in (gp, gt) if g is not None])
             ctx.have = (need_p, need_t)
         else:
@@ -74,8 +73,7 @@ class _RotatedIoU(torch.autograd.Function):
     def forward(ctx, o1, o2):
         need1, need2 = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         if need1 or need2:
-            ones = torch.ones(o1.size(0), dtype=torch.float32, device=o1.device)
-            iou, g1, g2 = _native.riou_fwd_bwd(o1.detach(), o2.detach(), ones, need1, need2)
+            iou, g1, g2 = _native.riou_fwd_bwd(o1.detach(), o2.detach(), None, need1, need2)
             ctx.save_for_backward(*[g for g in (g1, g2) if g is not None])
         else:
             iou, _, _ = _native.riou_fwd_bwd(o1.detach(), o2.detach())

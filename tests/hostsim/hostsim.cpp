@@ -45,16 +45,15 @@ void hostsim_iou_aligned_v2(int kind, const float* b1, const float* b2, long P, 
     }
 }
 
-// The aligned formulation: per-pair records, dead test on the exact arc, job + clip stages.
+// The aligned formulation (k_iou_aligned2): stage 1 for every pair, stage 2 + clipper for the survivors.
 void hostsim_iou_aligned_v3(int kind, const float* b1, const float* b2, long P, int D, int mode, int edge, float* out,
                             unsigned char* path) {
     for (long i = 0; i < P; ++i) {
         const RawBox x = load_box(b1, i, D), y = load_box(b2, i, D);
-        BoxRec gr, pr;
-        box_rec(x, 1, D, edge, &gr);
-        box_rec(y, 2, D, edge, &pr);
+        PairS1 s1;
         ClipJob job;
-        const int st = pair_job(gr, pr, D, kind, true, &job);
+        int st = pair_stage1(x, y, D, edge, true, &s1);
+        if (st == JOB_READY) st = pair_stage2(s1, D, kind, &job);
         if (path) path[i] = (st == JOB_DEAD) ? 0 : (st == JOB_READY ? 1 : 2);
         out[i] = (st == JOB_DEAD) ? 0.0f : (st == JOB_READY ? clip_job_iou(job, mode) : sph2pob_iou_pair(x, y, D, kind, mode, edge));
     }

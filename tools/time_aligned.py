@@ -1,0 +1,22 @@
+#!/usr/bin/env python
+"""Device time of the aligned Sph2Pob IoU at several sizes (fixed launch cost vs throughput)."""
+import os, sys, statistics
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from sph_retina_b200 import synthetic as S
+from sph_retina_b200.sphdet.iou import sph2pob_efficient_iou
+flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+def run(fn, n=10):
+    for _ in range(3): fn()
+    torch.cuda.synchronize(); ms = []
+    for _ in range(n):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ms.append(e0.elapsed_time(e1))
+    return statistics.median(ms)
+for box in ("bfov", "rbfov"):
+    for n in (250_000, 1_000_000, 4_000_000, 16_000_000):
+        b1 = S.generate_boxes(n, alpha_range=(1, 100), beta_range=(1, 100), box=box, seed=0).cuda()
+        b2 = S.generate_boxes(n, alpha_range=(1, 100), beta_range=(1, 100), box=box, seed=1).cuda()
+        ms = run(lambda: sph2pob_efficient_iou(b1, b2, is_aligned=True))
+        print("%s %9d pairs: %8.1f us  %6.1f Gpairs/s" % (box, n, ms * 1e3, n / ms / 1e6))
