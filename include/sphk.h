@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SPHK_ABI_VERSION 1
+#define SPHK_ABI_VERSION 2
 
 enum sphk_status {
     SPHK_OK = 0,
@@ -43,6 +43,7 @@ enum sphk_kind {
 };
 enum sphk_mode { SPHK_MODE_IOU = 0, SPHK_MODE_IOF = 1 };                     /* sph_iou_api.py:49     */
 enum sphk_edge { SPHK_EDGE_ARC = 0, SPHK_EDGE_CHORD = 1, SPHK_EDGE_TANGENT = 2 }; /* sph2pob_efficient.py:100-108 */
+enum sphk_angle { SPHK_ANGLE_EQUATOR = 0, SPHK_ANGLE_PROJECT = 1 };                /* sph2pob_efficient.py:81-97    */
 
 int sphk_abi_version(void);
 const char* sphk_last_error_string(void);
@@ -53,8 +54,10 @@ int sphk_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * Replaces _sph2pob_iou_auxiliary(..., is_aligned=True) (sphdet/iou/sph_iou_api.py:48-86: both
  * jitters :222-260, transform sph2pob_efficient.py:9-73 | sph2pob_standard.py:8-80, rotated IoU
  * mmcv.ops.box_iou_rotated at :79, clamp :86) and sph_iou / fov_iou (:130-177 with
- * approximate_ious.py:3-55; D must be 4, mode must be IOU for those two kinds). */
-int sphk_iou_aligned(int kind, const float* b1, const float* b2, int64_t P, int D, int mode, int edge,
+ * approximate_ious.py:3-55; D must be 4, mode must be IOU for those two kinds).
+ * angle = SPHK_ANGLE_PROJECT (the reference's ablation option rbb_angle='project') runs a plain
+ * double-precision kernel: correct, not tuned. */
+int sphk_iou_aligned(int kind, const float* b1, const float* b2, int64_t P, int D, int mode, int edge, int angle,
                      float* out, void* stream);
 
 /* Pairwise IoU of rows[R,D] x cols[C,D]; pair (i,j) = (rows[i] as bboxes1, cols[j] as bboxes2),
@@ -66,10 +69,11 @@ int sphk_iou_aligned(int kind, const float* b1, const float* b2, int64_t P, int 
  * Ties resolve to the lowest index.  row_base / col_base are added to the reported indices so a
  * shard of a larger matrix reports global indices.  `workspace` (16-byte aligned device memory of
  * sphk_iou_pairwise_workspace_bytes(R, C) bytes) holds the per-box precompute of the Sph2Pob kinds and
- * the packed max/argmax keys; it may be NULL only for the sph/fov kinds without max outputs. */
+ * the packed max/argmax keys; it may be NULL only for the sph/fov kinds without max outputs.
+ * With angle = SPHK_ANGLE_PROJECT only the matrix output is supported. */
 int64_t sphk_iou_pairwise_workspace_bytes(int64_t R, int64_t C);
 int sphk_iou_pairwise(int kind, const float* rows, int64_t R, const float* cols, int64_t C, int D, int mode,
-                      int edge, float* out, int64_t ld, float* row_max, int32_t* row_arg, float* col_max,
+                      int edge, int angle, float* out, int64_t ld, float* row_max, int32_t* row_arg, float* col_max,
                       int32_t* col_arg, int32_t row_base, int32_t col_base, void* workspace, void* stream);
 
 /* Sph2Pob loss, fused forward + backward (Sph2PobIoULoss, mode='iou'):

@@ -15,9 +15,10 @@ LIB_PATH = os.path.join(_HERE, "_lib", "libsphk.so")
 KIND = {"sph2pob_efficient": 0, "sph2pob_standard": 1, "sph": 2, "fov": 3}
 MODE = {"iou": 0, "iof": 1}
 EDGE = {"arc": 0, "chord": 1, "tangent": 2}
+ANGLE = {"equator": 0, "project": 1}
 
 SPHK_OK = 0
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _c_float_p = ctypes.c_void_p  # raw device addresses
 _i64 = ctypes.c_int64
@@ -29,9 +30,9 @@ SIGNATURES = {
     "sphk_abi_version": (_int, []),
     "sphk_last_error_string": (ctypes.c_char_p, []),
     "sphk_device_info": (_int, [ctypes.POINTER(_int)] * 3),
-    "sphk_iou_aligned": (_int, [_int, _c_float_p, _c_float_p, _i64, _int, _int, _int, _c_float_p, ctypes.c_void_p]),
+    "sphk_iou_aligned": (_int, [_int, _c_float_p, _c_float_p, _i64, _int, _int, _int, _int, _c_float_p, ctypes.c_void_p]),
     "sphk_iou_pairwise_workspace_bytes": (_i64, [_i64, _i64]),
-    "sphk_iou_pairwise": (_int, [_int, _c_float_p, _i64, _c_float_p, _i64, _int, _int, _int, _c_float_p, _i64,
+    "sphk_iou_pairwise": (_int, [_int, _c_float_p, _i64, _c_float_p, _i64, _int, _int, _int, _int, _c_float_p, _i64,
                                  _c_float_p, ctypes.c_void_p, _c_float_p, ctypes.c_void_p, _i32, _i32,
                                  ctypes.c_void_p, ctypes.c_void_p]),
     "sphk_loss_fwd_bwd": (_int, [_c_float_p, _c_float_p, _i64, _int, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
@@ -142,7 +143,7 @@ def device_info():
     return sm.value, major.value, minor.value
 
 
-def iou_aligned(kind: str, b1, b2, mode="iou", edge="arc") -> torch.Tensor:
+def iou_aligned(kind: str, b1, b2, mode="iou", edge="arc", angle="equator") -> torch.Tensor:
     global launches
     b1, b2 = _boxes(b1, "bboxes1"), _boxes(b2, "bboxes2")
     if b1.shape != b2.shape:
@@ -150,13 +151,13 @@ def iou_aligned(kind: str, b1, b2, mode="iou", edge="arc") -> torch.Tensor:
     out = torch.empty(b1.size(0), dtype=torch.float32, device=b1.device)
     with _on_device(b1.device):
         _check(lib.sphk_iou_aligned(KIND[kind], _ptr(b1), _ptr(b2), b1.size(0), b1.size(1), MODE[mode], EDGE[edge],
-                                    _ptr(out), _stream(b1)))
+                                    ANGLE[angle], _ptr(out), _stream(b1)))
     launches += 1
     return out
 
 
 def iou_pairwise(kind: str, rows, cols, mode="iou", edge="arc", want_matrix=True, want_row_max=False,
-                 want_col_max=False, row_base=0, col_base=0, out=None):
+                 want_col_max=False, row_base=0, col_base=0, out=None, angle="equator"):
     """Returns (matrix|None, (row_max,row_arg)|None, (col_max,col_arg)|None)."""
     global launches
     rows, cols = _boxes(rows, "bboxes1"), _boxes(cols, "bboxes2")
@@ -179,7 +180,7 @@ def iou_pairwise(kind: str, rows, cols, mode="iou", edge="arc", want_matrix=True
         ws = _workspace(dev, 104 * (R + C) + 32)     # >= sphk_iou_pairwise_workspace_bytes(R, C)
     with _on_device(dev):
         _check(lib.sphk_iou_pairwise(KIND[kind], _ptr(rows), R, _ptr(cols), C, rows.size(1), MODE[mode], EDGE[edge],
-                                     _ptr(mat), ld, _ptr(rmax), _ptr(rarg), _ptr(cmax), _ptr(carg), row_base, col_base,
+                                     ANGLE[angle], _ptr(mat), ld, _ptr(rmax), _ptr(rarg), _ptr(cmax), _ptr(carg), row_base, col_base,
                                      _ptr(ws), _stream(rows)))
     launches += 1 + int(kind in ("sph2pob_efficient", "sph2pob_standard")) + 2 * int(want_row_max) + 2 * int(want_col_max)
     return mat, ((rmax, rarg) if want_row_max else None), ((cmax, carg) if want_col_max else None)

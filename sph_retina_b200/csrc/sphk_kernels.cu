@@ -25,6 +25,7 @@ namespace {
 
 thread_local char g_err[256] = "";
 int g_dense = 0;   // sphk_set_dense: 1 = no disjoint-pair early-outs (measurement only)
+const int g_force_iters = [] { const char* e = getenv("SPHK_ALIGNED_ITERS"); return e ? atoi(e) : 0; }();
 const int g_force_tr = [] { const char* e = getenv("SPHK_TR"); return e ? atoi(e) : 0; }();
 
 int fail(int code, const char* what) {
@@ -198,6 +199,19 @@ k_iou_aligned2(const float* __restrict__ b1, const float* __restrict__ b2, int64
             hs += cnt;
         }
     }
+}
+
+// ---- rbb_angle = 'project': one thread per pair, double-precision transform (sphk_math.cuh) ------------
+template <int D>
+__global__ void __launch_bounds__(kThreads)
+k_iou_project(const float* __restrict__ b1, int64_t n1, const float* __restrict__ b2, int64_t n2, bool aligned, int kind,
+              int mode, int edge, float* __restrict__ out, int64_t ld) {
+    const int64_t p = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int64_t total = aligned ? n1 : n1 * n2;
+    if (p >= total) return;
+    const int64_t i = aligned ? p : p / n2, j = aligned ? p : p - i * n2;
+    const RawBox x = load_box<D>(b1, i, false), y = load_box<D>(b2, j, false);
+    out[aligned ? p : i * ld + j] = sph2pob_iou_pair_project(x, y, D, kind, mode, edge);
 }
 
 // ---- pairwise ----------------------------------------------------------------------------------
@@ -678,19 +692,23 @@ int sphk_device_info(int* sm_count, int* cc_major, int* cc_minor) {
     return SPHK_OK;
 }
 
-int sphk_iou_aligned(int kind, const float* b1, const float* b2, int64_t P, int D, int mode, int edge, float* out,
-                     void* stream) {
+int sphk_iou_aligned(int kind, const float* b1, const float* b2, int64_t P, int D, int mode, int edge, int angle,
+                     float* out, void* stream) {
     if (P < 0 || (D != 4 && D != 5)) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_aligned: P < 0 or D not in {4,5}");
     if (kind < 0 || kind > 3) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_aligned: unknown kind");
     if (mode != SPHK_MODE_IOU && mode != SPHK_MODE_IOF) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_aligned: unknown mode");
     if (edge < 0 || edge > 2) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_aligned: unknown edge");
+    if (angle != SPHK_ANGLE_EQUATOR && angle != SPHK_ANGLE_PROJECT) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_aligned: unknown angle");
     if ((kind == SPHK_KIND_SPH || kind == SPHK_KIND_FOV) && (D != 4 || mode != SPHK_MODE_IOU))
         return fail(SPHK_ERR_UNSUPPORTED, "sph_iou / fov_iou take BFoV boxes (D = 4) and mode 'iou' only");
     if (P == 0) return SPHK_OK;
     if (!b1 || !b2 || !out) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_aligned: null pointer");
     cudaStream_t s = (cudaStream_t)stream;
     const bool v = aligned16(b1) && aligned16(b2);
-    if (kind == SPHK_KIND_SPH || kind == SPHK_KIND_FOV) {
+    if (angle == SPHK_ANGLE_PROJECT && kind <= SPHK_KIND_SPH2POB_STANDARD) {
+        if (D == 4) k_iou_project<4><<<blocks_for(P), kThreads, 0, s>>>(b1, P, b2, P, true, kind, mode, edge, out, 0);
+        else k_iou_project<5><<<blocks_for(P), kThreads, 0, s>>>(b1, P, b2, P, true, kind, mode, edge, out, 0);
+    } else if (kind == SPHK_KIND_SPH || kind == SPHK_KIND_FOV) {
         const unsigned g = blocks_for(P);
         if (kind == SPHK_KIND_SPH) k_iou_aligned<KIND_SPH, 4><<<g, kThreads, 0, s>>>(b1, b2, P, mode, edge, out, v, g_dense != 0);
         else k_iou_aligned<KIND_FOV, 4><<<g, kThreads, 0, s>>>(b1, b2, P, mode, edge, out, v, g_dense != 0);
@@ -699,6 +717,7 @@ int sphk_iou_aligned(int kind, const float* b1, const float* b2, int64_t P, int 
         const int sms = sm_count();
         int64_t iters = (P + (int64_t)kThreads * 8 * sms - 1) / ((int64_t)kThreads * 8 * sms);
         iters = iters < 1 ? 1 : (iters > 16 ? 16 : iters);
+        if (g_force_iters >= 1 && g_force_iters <= 16) iters = g_force_iters;   // tuning hook (SPHK_ALIGNED_ITERS)
         const int64_t per_cta = (int64_t)kThreads * iters;
         const int64_t g64 = (P + per_cta - 1) / per_cta;
         if (g64 > 0x7FFFFFFFll) return fail(SPHK_ERR_UNSUPPORTED, "sphk_iou_aligned: P too large; split the call");
@@ -719,12 +738,13 @@ int64_t sphk_iou_pairwise_workspace_bytes(int64_t R, int64_t C) {
 }
 
 int sphk_iou_pairwise(int kind, const float* rows, int64_t R, const float* cols, int64_t C, int D, int mode, int edge,
-                      float* out, int64_t ld, float* row_max, int32_t* row_arg, float* col_max, int32_t* col_arg,
-                      int32_t row_base, int32_t col_base, void* workspace, void* stream) {
+                      int angle, float* out, int64_t ld, float* row_max, int32_t* row_arg, float* col_max,
+                      int32_t* col_arg, int32_t row_base, int32_t col_base, void* workspace, void* stream) {
     if (R < 0 || C < 0 || (D != 4 && D != 5)) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: bad R, C or D");
     if (kind < 0 || kind > 3) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: unknown kind");
     if (mode != SPHK_MODE_IOU && mode != SPHK_MODE_IOF) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: unknown mode");
     if (edge < 0 || edge > 2) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: unknown edge");
+    if (angle != SPHK_ANGLE_EQUATOR && angle != SPHK_ANGLE_PROJECT) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: unknown angle");
     const bool approx = (kind == SPHK_KIND_SPH || kind == SPHK_KIND_FOV);
     if (approx && (D != 4 || mode != SPHK_MODE_IOU))
         return fail(SPHK_ERR_UNSUPPORTED, "sph_iou / fov_iou take BFoV boxes (D = 4) and mode 'iou' only");
@@ -732,6 +752,16 @@ int sphk_iou_pairwise(int kind, const float* rows, int64_t R, const float* cols,
     if (R + (int64_t)(uint32_t)row_base > 0xFFFFFFFFll || C + (int64_t)(uint32_t)col_base > 0xFFFFFFFFll)
         return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: indices do not fit 32 bits");
     const bool want_row = row_max || row_arg, want_col = col_max || col_arg;
+    if (angle == SPHK_ANGLE_PROJECT && !approx) {
+        if (want_row || want_col) return fail(SPHK_ERR_UNSUPPORTED, "sphk_iou_pairwise: rbb_angle='project' supports the matrix output only");
+        if (R == 0 || C == 0 || !out) return SPHK_OK;
+        if (!rows || !cols) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: null box pointer");
+        if (R * C > 0x7FFFFFFFll * (int64_t)kThreads) return fail(SPHK_ERR_UNSUPPORTED, "sphk_iou_pairwise: grid too large; shard the call");
+        if (D == 4) k_iou_project<4><<<blocks_for(R * C), kThreads, 0, (cudaStream_t)stream>>>(rows, R, cols, C, false, kind, mode, edge, out, ld);
+        else k_iou_project<5><<<blocks_for(R * C), kThreads, 0, (cudaStream_t)stream>>>(rows, R, cols, C, false, kind, mode, edge, out, ld);
+        SPHK_LAUNCH_CHECK("k_iou_project");
+        return SPHK_OK;
+    }
     if ((want_row || want_col || !approx) && !workspace && (R + C) > 0)
         return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: workspace of sphk_iou_pairwise_workspace_bytes(R, C) required");
     if (workspace && !aligned16(workspace)) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: workspace must be 16-byte aligned");

@@ -509,6 +509,85 @@ SPHK_HD float sph2pob_iou_pair(const RawBox& b1, const RawBox& b2, int D, int ki
     return riou_value(o, mode);
 }
 
+// ---- rbb_angle = 'project' (sph2pob_efficient.py:92-93, sph2pob_standard.py:99-100) -----------------------
+// The ablation variant that zeroes the x component of the box tangent before measuring the internal angle.
+// It has no closed form in the tangent basis, so it is evaluated with explicit 3-D vectors, in double
+// precision (the option is rare; correctness over speed), then handed to the same jitter_2 + clipper.
+struct V3 { double x, y, z; };
+SPHK_HD V3 v3(double x, double y, double z) { V3 v; v.x = x; v.y = y; v.z = z; return v; }
+SPHK_HD V3 cross3(const V3& a, const V3& b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+SPHK_HD double dot3(const V3& a, const V3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+SPHK_HD V3 unit3(const V3& a) {                 // F.normalize: v / max(|v|, 1e-12)
+    double n = sqrt(dot3(a, a));
+    n = n < 1e-12 ? 1e-12 : n;
+    return v3(a.x / n, a.y / n, a.z / n);
+}
+SPHK_HD double clamped_angle(const V3& a, const V3& b) {   // |acos(clamp(a^ . b^, -1 + 1e-7, 1 - 1e-7))|
+    double c = dot3(unit3(a), unit3(b));
+    c = c < -1.0 + 1e-7 ? -1.0 + 1e-7 : (c > 1.0 - 1e-7 ? 1.0 - 1e-7 : c);
+    return fabs(acos(c));
+}
+SPHK_HD double turn_sign(const V3& a, const V3& b, const V3& ref) { return dot3(cross3(a, b), ref) < 0.0 ? 1.0 : -1.0; }
+SPHK_HD V3 rot3(const V3 R[3], const V3& v) { return v3(dot3(R[0], v), dot3(R[1], v), dot3(R[2], v)); }
+
+SPHK_HD ObbPair sph2pob_project(const JitBox& g, const JitBox& p, int D, int kind, int edge) {
+    const double k = SPHK_PI_D / 180.0;
+    const double tg = ((double)g.t_hi + (double)g.t_lo) * k, pg = ((double)g.p_hi + (double)g.p_lo) * k;
+    const double tp = ((double)p.t_hi + (double)p.t_lo) * k, pp = ((double)p.p_hi + (double)p.p_lo) * k;
+    V3 cg = v3(sin(pg) * cos(tg), sin(pg) * sin(tg), cos(pg)), dg = v3(cos(pg) * cos(tg), cos(pg) * sin(tg), -sin(pg));
+    V3 cp = v3(sin(pp) * cos(tp), sin(pp) * sin(tp), cos(pp)), dp = v3(cos(pp) * cos(tp), cos(pp) * sin(tp), -sin(pp));
+    ObbPair o;
+    double a1, a2;
+    if (kind == KIND_SPH2POB_STANDARD) {
+        V3 R[3];
+        if (fabs(cg.x - cp.x) + fabs(cg.y - cp.y) + fabs(cg.z - cp.z) > 1e-8) {          // sph2pob_standard.py:264-297
+            R[0] = unit3(v3(cg.x + cp.x, cg.y + cp.y, cg.z + cp.z));
+            R[1] = unit3(v3(cp.x - cg.x, cp.y - cg.y, cp.z - cg.z));
+            R[2] = cross3(R[0], R[1]);
+        } else {
+            const double tm = 0.5 * (tg + tp), pm = 0.5 * (pg + pp);
+            R[0] = v3(sin(pm) * cos(tm), sin(pm) * sin(tm), cos(pm));
+            R[1] = v3(cos(pm) * cos(tm), cos(pm) * sin(tm), -sin(pm));
+            R[2] = v3(sin(tm), -cos(tm), 0.0);
+        }
+        if (D == 5) {   // :47-54 rotate the tangent about the centre by -gamma: d cos(gamma) + e sin(gamma) in the local frame
+            const double gg = (double)g.g * k, gp = (double)p.g * k;
+            const V3 eg = v3(sin(tg), -cos(tg), 0.0), ep = v3(sin(tp), -cos(tp), 0.0);   // third row of the local frame
+            dg = v3(dg.x * cos(gg) - eg.x * sin(gg), dg.y * cos(gg) - eg.y * sin(gg), dg.z * cos(gg) - eg.z * sin(gg));
+            dp = v3(dp.x * cos(gp) - ep.x * sin(gp), dp.y * cos(gp) - ep.y * sin(gp), dp.z * cos(gp) - ep.z * sin(gp));
+        }
+        const V3 ex = v3(1, 0, 0), ez = v3(0, 0, 1), nez = v3(0, 0, -1);
+        const V3 c1 = rot3(R, cg), c2 = rot3(R, cp);
+        V3 d1 = rot3(R, dg), d2 = rot3(R, dp);
+        d1.x = 0.0; d2.x = 0.0;                                                          // 'project'
+        a1 = clamped_angle(d1, ez) * turn_sign(ez, d1, ex);
+        a2 = clamped_angle(d2, ez) * turn_sign(ez, d2, ex);
+        const V3 c1xy = v3(c1.x, c1.y, 0.0), c2xy = v3(c2.x, c2.y, 0.0);
+        o.x1 = (float)(clamped_angle(c1xy, ex) * turn_sign(ex, c1xy, nez)); o.y1 = (float)clamped_angle(c1, ez);
+        o.x2 = (float)(clamped_angle(c2xy, ex) * turn_sign(ex, c2xy, nez)); o.y2 = (float)clamped_angle(c2, ez);
+    } else {
+        const V3 z = cross3(cg, cp), ref = v3(0.5 * (cg.x + cp.x), 0.5 * (cg.y + cp.y), 0.5 * (cg.z + cp.z));
+        dg.x = 0.0; dp.x = 0.0;                                                          // 'project'
+        a1 = clamped_angle(dg, z) * turn_sign(z, dg, ref);
+        a2 = clamped_angle(dp, z) * turn_sign(z, dp, ref);
+        if (D == 5) { a1 -= (double)g.g * k; a2 -= (double)p.g * k; }
+        o.x1 = 0.0f; o.y1 = 0.0f; o.x2 = (float)clamped_angle(cg, cp); o.y2 = 0.0f;
+    }
+    o.a1 = (float)a1; o.a2 = (float)a2;
+    o.w1 = edge_len_deg(g.a, edge); o.h1 = edge_len_deg(g.b, edge);
+    o.w2 = edge_len_deg(p.a, edge); o.h2 = edge_len_deg(p.b, edge);
+    return o;
+}
+
+SPHK_HD float sph2pob_iou_pair_project(const RawBox& b1, const RawBox& b2, int D, int kind, int mode, int edge) {
+    const bool m = jitter1_mask(b1, b2, D);
+    const JitBox g = jitter1_role1(b1, m, D), p = jitter1_role2(b2, m, D);
+    ObbPair o = sph2pob_project(g, p, D, kind, edge);
+    jitter2(o);
+    if (obb_disjoint(o)) return 0.0f;
+    return riou_value(o, mode);
+}
+
 // ---- Sph-IoU / FoV-IoU (approximate_ious.py:3-55 behind sph_iou_api.py:130-177) -------
 SPHK_HD float approx_iou_pair(const RawBox& b1, const RawBox& b2, int kind) {
     const bool m = jitter1_mask(b1, b2, 4);

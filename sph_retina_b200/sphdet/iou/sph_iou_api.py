@@ -18,16 +18,16 @@ def _empty(bboxes1, rows, cols, is_aligned):
     return bboxes1.new_zeros((rows, 1)) if is_aligned else bboxes1.new_zeros((rows, cols))
 
 
-def _run(kind, bboxes1, bboxes2, mode, is_aligned, edge):
+def _run(kind, bboxes1, bboxes2, mode, is_aligned, edge, angle="equator"):
     rows, cols = bboxes1.size(0), bboxes2.size(0)
     if rows * cols == 0:
         return _empty(bboxes1, rows, cols, is_aligned)
     with torch.no_grad():
         if is_aligned:
             assert rows == cols
-            out = _native.iou_aligned(kind, bboxes1, bboxes2, mode, edge)
+            out = _native.iou_aligned(kind, bboxes1, bboxes2, mode, edge, angle)
         else:
-            out = _native.iou_pairwise(kind, bboxes1, bboxes2, mode, edge)[0]
+            out = _native.iou_pairwise(kind, bboxes1, bboxes2, mode, edge, angle=angle)[0]
     return out if out.dtype == bboxes1.dtype else out.to(bboxes1.dtype)
 
 
@@ -37,9 +37,7 @@ def _sph2pob_iou(kind, bboxes1, bboxes2, mode, is_aligned, calculator, rbb_edge,
     assert calculator in ['common', 'diff']
     assert rbb_edge in ['arc', 'chord', 'tangent']
     assert rbb_angle in ['equator', 'project']      # sph2pob_efficient.py:27
-    if rbb_angle == 'project':
-        raise NotImplementedError("rbb_angle='project' has no CUDA kernel yet (and no fallback): use 'equator'")
-    return _run(kind, bboxes1, bboxes2, mode, is_aligned, rbb_edge)
+    return _run(kind, bboxes1, bboxes2, mode, is_aligned, rbb_edge, rbb_angle)
 
 
 def sph2pob_standard_iou(bboxes1, bboxes2, mode='iou', is_aligned=False, calculator='common', rbb_edge='arc',

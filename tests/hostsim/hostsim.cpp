@@ -59,6 +59,11 @@ void hostsim_iou_aligned_v3(int kind, const float* b1, const float* b2, long P, 
     }
 }
 
+void hostsim_iou_aligned_project(int kind, const float* b1, const float* b2, long P, int D, int mode, int edge, float* out) {
+    for (long i = 0; i < P; ++i)
+        out[i] = sph2pob_iou_pair_project(load_box(b1, i, D), load_box(b2, i, D), D, kind, mode, edge);
+}
+
 // OBBs after transform + both jitters: out [P,10] = (x1,y1,w1,h1,a1,x2,y2,w2,h2,a2)
 void hostsim_obbs(int kind, const float* b1, const float* b2, long P, int D, int edge, float* out) {
     for (long i = 0; i < P; ++i) {

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol(built_lib):
     for name in declared_symbols():
         assert hasattr(lib, name), "libsphk.so does not export %s" % name
     lib.sphk_abi_version.restype = ctypes.c_int
-    assert lib.sphk_abi_version() == 1
+    assert lib.sphk_abi_version() == 2
 
 
 def test_binding_covers_the_header(built_lib):
@@ -45,11 +45,11 @@ def test_argument_validation_needs_no_gpu(built_lib):
     """Invalid arguments are rejected before any CUDA call, with a message."""
     from sph_retina_b200 import _native
     lib = _native.lib
-    assert lib.sphk_iou_aligned(0, None, None, 10, 3, 0, 0, None, None) == -1          # D = 3
+    assert lib.sphk_iou_aligned(0, None, None, 10, 3, 0, 0, 0, None, None) == -1          # D = 3
     assert b"D not in" in lib.sphk_last_error_string()
-    assert lib.sphk_iou_aligned(2, None, None, 10, 5, 0, 0, None, None) == -3          # sph_iou on RBFoV
-    assert lib.sphk_iou_aligned(7, None, None, 10, 4, 0, 0, None, None) == -1          # unknown kind
-    assert lib.sphk_iou_aligned(0, None, None, 0, 4, 0, 0, None, None) == 0            # empty is fine
+    assert lib.sphk_iou_aligned(2, None, None, 10, 5, 0, 0, 0, None, None) == -3          # sph_iou on RBFoV
+    assert lib.sphk_iou_aligned(7, None, None, 10, 4, 0, 0, 0, None, None) == -1          # unknown kind
+    assert lib.sphk_iou_aligned(0, None, None, 0, 4, 0, 0, 0, None, None) == 0            # empty is fine
     assert lib.sphk_iou_pairwise_workspace_bytes(10, 20) == 240 + 30 * 96
     assert lib.sphk_nms_batched(None, None, None, 0, 0, 4, 0.5, None, None) == 0
     assert lib.sphk_loss_fwd_bwd(None, None, 5, 4, None, None, None, None, None) == -1  # null boxes

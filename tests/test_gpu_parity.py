@@ -70,6 +70,21 @@ def test_aligned_golden(api, box, tr):
     assert torch.equal(b1, keep1) and torch.equal(b2, keep2)        # tests/test_all_ious.py:322-331
 
 
+@pytest.mark.parametrize("box", ["bfov", "rbfov"])
+def test_project_angle_variant(api, box):
+    """rbb_angle='project': aligned and N x M (plain double-precision kernel)."""
+    g = load_golden("aligned_" + box)
+    b1, b2 = cu(g["b1"]), cu(g["b2"])
+    for tr in ("efficient", "standard"):
+        fn = getattr(api.iou, "sph2pob_%s_iou" % tr)
+        got = fn(b1, b2, is_aligned=True, rbb_angle="project")
+        ok, err = within(got.cpu().numpy(), g[tr + "_project_f64"], g[tr + "_project_f32"])
+        assert ok.all(), (box, tr, np.where(~ok)[0], err[~ok])
+        mat = fn(b1[:40], b2[:70], rbb_angle="project")
+        flat = fn(b1[:40].repeat_interleave(70, 0), b2[:70].repeat(40, 1), is_aligned=True, rbb_angle="project")
+        assert torch.equal(mat.reshape(-1), flat)
+
+
 def test_sph_fov_golden_and_known_answers(api):
     g = load_golden("aligned_bfov")
     b1, b2 = cu(g["b1"]), cu(g["b2"])

@@ -147,3 +147,18 @@ def test_fast_formulations_equal_reference_order_path(hostsim, fn):
         assert np.abs(got - want).max() < 5e-6
         assert not ((path == 0) & (want > 0)).any()
         assert (path == 1).mean() > 0.3
+
+
+@pytest.mark.parametrize("box", ["bfov", "rbfov"])
+def test_project_angle_variant(hostsim, box):
+    """rbb_angle='project' (sph2pob_efficient.py:92-93, sph2pob_standard.py:99-100)."""
+    g = load_golden("aligned_" + box)
+    b1, b2 = np.ascontiguousarray(g["b1"], np.float32), np.ascontiguousarray(g["b2"], np.float32)
+    P, D = b1.shape
+    for kind, tr in ((0, "efficient"), (1, "standard")):
+        out = np.empty(P, np.float32)
+        hostsim.hostsim_iou_aligned_project(kind, b1.ctypes.data_as(fp), b2.ctypes.data_as(fp), ctypes.c_long(P), D, 0, 0,
+                                            out.ctypes.data_as(fp))
+        ok, err = within(out, g[tr + "_project_f64"], g[tr + "_project_f32"])
+        assert ok.all(), (box, tr, np.where(~ok)[0], err[~ok])
+        assert (err > 1e-5).sum() <= 2

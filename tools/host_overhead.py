@@ -32,7 +32,7 @@ def bench(name, fn, n=2000):
 small = anchors[:256].contiguous()
 bench("ctypes: sphk_abi_version()", lambda: N.lib.sphk_abi_version())
 bench("ctypes: sphk_iou_pairwise with R = 0 (18 args, no launch)",
-      lambda: N.lib.sphk_iou_pairwise(0, g0.data_ptr(), 0, small.data_ptr(), 256, 5, 0, 0, None, 256, None, None, None, None, 0, 0, None, 0))
+      lambda: N.lib.sphk_iou_pairwise(0, g0.data_ptr(), 0, small.data_ptr(), 256, 5, 0, 0, 0, None, 256, None, None, None, None, 0, 0, None, 0))
 bench("torch.empty((32, 98208))", lambda: torch.empty((32, 98208), dtype=torch.float32, device="cuda"))
 bench("gts[i]", lambda: gts[3])
 bench("slice [..., :5] x2", lambda: (g0[..., :5], anchors[..., :5]))

@@ -15,7 +15,7 @@ def run(fn, n=10):
         e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ms.append(e0.elapsed_time(e1))
     return statistics.median(ms)
 for box in ("bfov", "rbfov"):
-    for n in (250_000, 1_000_000, 4_000_000, 16_000_000):
+    for n in [int(v) for v in os.environ.get("SIZES", "250000,1000000,4000000,16000000").split(",")]:
         b1 = S.generate_boxes(n, alpha_range=(1, 100), beta_range=(1, 100), box=box, seed=0).cuda()
         b2 = S.generate_boxes(n, alpha_range=(1, 100), beta_range=(1, 100), box=box, seed=1).cuda()
         ms = run(lambda: sph2pob_efficient_iou(b1, b2, is_aligned=True))
