@@ -76,6 +76,16 @@ int sphk_iou_pairwise(int kind, const float* rows, int64_t R, const float* cols,
                       int edge, int angle, float* out, int64_t ld, float* row_max, int32_t* row_arg, float* col_max,
                       int32_t* col_arg, int32_t row_base, int32_t col_base, void* workspace, void* stream);
 
+/* Second pass of MaxIoUAssigner's low-quality matching with gt_max_assign_all=True
+ * (mmdet/core/bbox/assigners/max_iou_assigner.py:201-205: for each GT i in ascending order,
+ * `assigned[overlaps[i, :] == gt_max_overlaps[i]] = i + 1`) without the K x N matrix:
+ *   row_target [R]  the row maxima of a previous sphk_iou_pairwise call on the SAME operands (same kernel,
+ *                   bit-identical values); a negative entry disables that row (gt_max < min_pos_iou)
+ *   col_tie    [C]  out: the largest row_base + i + 1 over the rows i with IoU(i, j) == row_target[i] > 0,
+ *                   0 if none.  Rows whose target is exactly 0 must be handled by the caller. */
+int sphk_iou_pairwise_ties(int kind, const float* rows, int64_t R, const float* cols, int64_t C, int D, int mode, int edge,
+                           const float* row_target, int32_t* col_tie, int32_t row_base, void* workspace, void* stream);
+
 /* Sph2Pob loss, fused forward + backward (Sph2PobIoULoss, mode='iou'):
  * replaces Sph2PobTransfrom.new_forward (sphdet/losses/sph2pob_transform.py:24-35: jitter_1,
  * sph2pob_standard, jitter_2) followed by diff_iou_rotated_2d(...).clamp(0,1)

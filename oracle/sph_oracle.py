@@ -471,6 +471,42 @@ def nms_batched(boxes, scores, idxs, iou_threshold=0.5, max_num=None, class_agno
 
 
 # --------------------------------------------------------------------------- #
+# MaxIoUAssigner.assign_wrt_overlaps (mmdet/core/bbox/assigners/max_iou_assigner.py:135-220)
+# --------------------------------------------------------------------------- #
+def assign_wrt_overlaps(overlaps, gt_labels=None, pos_iou_thr=0.5, neg_iou_thr=0.4, min_pos_iou=0.0,
+                        gt_max_assign_all=True, match_low_quality=True):
+    """Literal restatement, Python loop over the GTs included.  Returns (gt_inds, max_overlaps, labels)."""
+    num_gts, num_bboxes = overlaps.size(0), overlaps.size(1)
+    assigned = overlaps.new_full((num_bboxes,), -1, dtype=torch.long)
+    if num_gts == 0 or num_bboxes == 0:
+        if num_gts == 0:
+            assigned[:] = 0
+        labels = None if gt_labels is None else overlaps.new_full((num_bboxes,), -1, dtype=torch.long)
+        return assigned, overlaps.new_zeros((num_bboxes,)), labels
+    max_overlaps, argmax_overlaps = overlaps.max(dim=0)
+    gt_max_overlaps, gt_argmax_overlaps = overlaps.max(dim=1)
+    if isinstance(neg_iou_thr, float):
+        assigned[(max_overlaps >= 0) & (max_overlaps < neg_iou_thr)] = 0
+    else:
+        assigned[(max_overlaps >= neg_iou_thr[0]) & (max_overlaps < neg_iou_thr[1])] = 0
+    pos = max_overlaps >= pos_iou_thr
+    assigned[pos] = argmax_overlaps[pos] + 1
+    if match_low_quality:
+        for i in range(num_gts):
+            if gt_max_overlaps[i] >= min_pos_iou:
+                if gt_max_assign_all:
+                    assigned[overlaps[i, :] == gt_max_overlaps[i]] = i + 1
+                else:
+                    assigned[gt_argmax_overlaps[i]] = i + 1
+    labels = None
+    if gt_labels is not None:
+        labels = assigned.new_full((num_bboxes,), -1)
+        p = assigned > 0
+        labels[p] = gt_labels[assigned[p] - 1]
+    return assigned, max_overlaps, labels
+
+
+# --------------------------------------------------------------------------- #
 # synthetic inputs (tests/utils/generate_data.py:10-42, dtype='float' branch)
 # --------------------------------------------------------------------------- #
 def generate_boxes(num, theta_range=(0, 360), phi_range=(0, 180), alpha_range=(1, 180),

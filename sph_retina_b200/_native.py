@@ -35,6 +35,8 @@ SIGNATURES = {
     "sphk_iou_pairwise": (_int, [_int, _c_float_p, _i64, _c_float_p, _i64, _int, _int, _int, _int, _c_float_p, _i64,
                                  _c_float_p, ctypes.c_void_p, _c_float_p, ctypes.c_void_p, _i32, _i32,
                                  ctypes.c_void_p, ctypes.c_void_p]),
+    "sphk_iou_pairwise_ties": (_int, [_int, _c_float_p, _i64, _c_float_p, _i64, _int, _int, _int, _c_float_p, ctypes.c_void_p,
+                                      _i32, ctypes.c_void_p, ctypes.c_void_p]),
     "sphk_loss_fwd_bwd": (_int, [_c_float_p, _c_float_p, _i64, _int, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
                                  ctypes.c_void_p]),
     "sphk_obb_fwd": (_int, [_int, _c_float_p, _c_float_p, _i64, _int, _int, _c_float_p, _c_float_p, ctypes.c_void_p]),
@@ -184,6 +186,22 @@ def iou_pairwise(kind: str, rows, cols, mode="iou", edge="arc", want_matrix=True
                                      _ptr(ws), _stream(rows)))
     launches += 1 + int(kind in ("sph2pob_efficient", "sph2pob_standard")) + 2 * int(want_row_max) + 2 * int(want_col_max)
     return mat, ((rmax, rarg) if want_row_max else None), ((cmax, carg) if want_col_max else None)
+
+
+def iou_pairwise_ties(kind: str, rows, cols, row_target, mode="iou", edge="arc", row_base=0):
+    """col_tie[j] = max over rows i with IoU(rows[i], cols[j]) == row_target[i] > 0 of (row_base + i + 1), else 0."""
+    global launches
+    rows, cols = _boxes(rows, "bboxes1"), _boxes(cols, "bboxes2")
+    R, C, dev = rows.size(0), cols.size(0), rows.device
+    row_target = row_target.to(device=dev, dtype=torch.float32).contiguous()
+    assert row_target.numel() == R
+    tie = torch.empty(C, dtype=torch.int32, device=dev)
+    ws = _workspace(dev, 104 * (R + C) + 32)
+    with _on_device(dev):
+        _check(lib.sphk_iou_pairwise_ties(KIND[kind], _ptr(rows), R, _ptr(cols), C, rows.size(1), MODE[mode], EDGE[edge],
+                                          _ptr(row_target), _ptr(tie), row_base, _ptr(ws), _stream(rows)))
+    launches += 2
+    return tie
 
 
 def loss_fwd_bwd(pred, target, grad_iou=None, want_grad_pred=False, want_grad_target=False):

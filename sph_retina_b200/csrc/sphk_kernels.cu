@@ -297,6 +297,8 @@ struct PairTile {
     unsigned long long rkey[TR];
     unsigned long long ckey[kTC];
     unsigned short ring[kThreads / 32][2][kRing];
+    float rtgt[TR];      // tie pass: the row maxima to compare with
+    int ctie[kTC];       // tie pass: per column, the largest (row index + 1) that ties its row maximum
 };
 
 template <int D>
@@ -346,7 +348,7 @@ __device__ __forceinline__ void stage_rec(float* base, int i, const float4* __re
 struct PairOut {
     float* out;
     int64_t ld, r0, c0;
-    bool want_row, want_col;
+    bool want_row, want_col, tie;
     uint32_t row_base, col_base;
 };
 
@@ -356,6 +358,8 @@ __device__ __forceinline__ void emit_pair(PairTile<TR>& T, const PairOut& o, int
     if (v > 0.0f) {
         if (o.want_row) atomicMax(&T.rkey[r], pack_key(v, o.col_base + (uint32_t)(o.c0 + c)));
         if (o.want_col) atomicMax(&T.ckey[c], pack_key(v, o.row_base + (uint32_t)(o.r0 + r)));
+        // MaxIoUAssigner's gt_max_assign_all scan (max_iou_assigner.py:203-205): overlaps[i, :] == gt_max[i]
+        if (o.tie && v == T.rtgt[r]) atomicMax(&T.ctie[c], (int)(o.row_base + (uint32_t)(o.r0 + r)) + 1);
     }
 }
 
@@ -364,7 +368,8 @@ __global__ void __launch_bounds__(kThreads)
 k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restrict__ cols, int64_t C,
                 const float4* __restrict__ rec, const float4* __restrict__ cull, int kind, int mode, int edge,
                 float* __restrict__ out, int64_t ld, unsigned long long* __restrict__ row_key,
-                unsigned long long* __restrict__ col_key, uint32_t row_base, uint32_t col_base, bool dense) {
+                unsigned long long* __restrict__ col_key, uint32_t row_base, uint32_t col_base, bool dense,
+                const float* __restrict__ row_target, int* __restrict__ col_tie) {
     __shared__ __align__(16) PairTile<TR> T;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // grid = (row tiles, column tiles).  Column tiles are taken heaviest-first: RetinaNet-style anchor lists
@@ -373,7 +378,7 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
     const uint32_t rt = blockIdx.x, ct = gridDim.y - 1u - blockIdx.y;
     PairOut o;
     o.out = out; o.ld = ld; o.r0 = (int64_t)rt * TR; o.c0 = (int64_t)ct * kTC;
-    o.want_row = row_key != nullptr; o.want_col = col_key != nullptr;
+    o.want_row = row_key != nullptr; o.want_col = col_key != nullptr; o.tie = col_tie != nullptr;
     o.row_base = row_base; o.col_base = col_base;
     const int nr = (int)min((int64_t)TR, R - o.r0);
     const bool col_ok = o.c0 + tid < C;
@@ -410,7 +415,9 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
         }
         T.rcull[tid][0] = u0; T.rcull[tid][1] = u1;
         T.rkey[tid] = 0ull;
+        T.rtgt[tid] = (o.tie && ok) ? __ldg(row_target + o.r0 + tid) : -1.0f;
     }
+    T.ctie[tid] = 0;
     __syncthreads();
     // ---- phase 1: prefilter + compaction.  This thread's column is tid (= warp * 32 + lane).
     // Out-of-range columns and the dense (measurement) mode are folded into the bias term of the test.
@@ -464,8 +471,9 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
         }
     }
     // ---- merge the tile's max/argmax into the global keys
-    if (o.want_row || o.want_col) {
+    if (o.want_row || o.want_col || o.tie) {
         __syncthreads();
+        if (o.tie && col_ok && T.ctie[tid] > 0) atomicMax(&col_tie[o.c0 + tid], T.ctie[tid]);
         if (o.want_row && tid < nr) {
             const unsigned long long key = T.rkey[tid];
             if (key != 0ull && key > row_key[o.r0 + tid]) atomicMax(&row_key[o.r0 + tid], key);
@@ -737,9 +745,10 @@ int64_t sphk_iou_pairwise_workspace_bytes(int64_t R, int64_t C) {
     return keys_bytes(R, C) + (R + C) * (int64_t)((kBoxRecFloats + kBoxCullFloats) * sizeof(float));
 }
 
-int sphk_iou_pairwise(int kind, const float* rows, int64_t R, const float* cols, int64_t C, int D, int mode, int edge,
-                      int angle, float* out, int64_t ld, float* row_max, int32_t* row_arg, float* col_max,
-                      int32_t* col_arg, int32_t row_base, int32_t col_base, void* workspace, void* stream) {
+static int pairwise_impl(int kind, const float* rows, int64_t R, const float* cols, int64_t C, int D, int mode, int edge,
+                         int angle, float* out, int64_t ld, float* row_max, int32_t* row_arg, float* col_max,
+                         int32_t* col_arg, int32_t row_base, int32_t col_base, void* workspace, void* stream,
+                         const float* row_target, int* col_tie) {
     if (R < 0 || C < 0 || (D != 4 && D != 5)) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: bad R, C or D");
     if (kind < 0 || kind > 3) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: unknown kind");
     if (mode != SPHK_MODE_IOU && mode != SPHK_MODE_IOF) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: unknown mode");
@@ -815,7 +824,7 @@ int sphk_iou_pairwise(int kind, const float* rows, int64_t R, const float* cols,
             cudaError_t le;
 #define SPHK_PW2(DD, TR)                                                                                               \
     le = cudaLaunchKernelEx(&cfg, k_iou_pairwise2<DD, TR>, rows, R, cols, C, crec, ccull, kind, mode, edge, out, ld, rkey, \
-                            ckey, (uint32_t)row_base, (uint32_t)col_base, dn)
+                            ckey, (uint32_t)row_base, (uint32_t)col_base, dn, row_target, col_tie)
             if (D == 4 && tr == 32) SPHK_PW2(4, 32);
             else if (D == 4 && tr == 16) SPHK_PW2(4, 16);
             else if (D == 4) SPHK_PW2(4, 8);
@@ -831,6 +840,27 @@ int sphk_iou_pairwise(int kind, const float* rows, int64_t R, const float* cols,
     if (want_col && C > 0) k_unpack_keys<<<blocks_for(C), kThreads, 0, s>>>(ckey, C, col_max, col_arg, (uint32_t)row_base);
     SPHK_LAUNCH_CHECK("k_unpack_keys");
     return SPHK_OK;
+}
+
+int sphk_iou_pairwise(int kind, const float* rows, int64_t R, const float* cols, int64_t C, int D, int mode, int edge,
+                      int angle, float* out, int64_t ld, float* row_max, int32_t* row_arg, float* col_max,
+                      int32_t* col_arg, int32_t row_base, int32_t col_base, void* workspace, void* stream) {
+    return pairwise_impl(kind, rows, R, cols, C, D, mode, edge, angle, out, ld, row_max, row_arg, col_max, col_arg, row_base,
+                         col_base, workspace, stream, nullptr, nullptr);
+}
+
+int sphk_iou_pairwise_ties(int kind, const float* rows, int64_t R, const float* cols, int64_t C, int D, int mode, int edge,
+                           const float* row_target, int32_t* col_tie, int32_t row_base, void* workspace, void* stream) {
+    if (kind != SPHK_KIND_SPH2POB_EFFICIENT && kind != SPHK_KIND_SPH2POB_STANDARD)
+        return fail(SPHK_ERR_UNSUPPORTED, "sphk_iou_pairwise_ties: kind must be a Sph2Pob transform");
+    if (R < 0 || C < 0) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise_ties: bad R or C");
+    if (C == 0) return SPHK_OK;
+    if (!col_tie || (R > 0 && !row_target)) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise_ties: null pointer");
+    cudaError_t e = cudaMemsetAsync(col_tie, 0, (size_t)C * sizeof(int32_t), (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(col_tie)");
+    if (R == 0) return SPHK_OK;
+    return pairwise_impl(kind, rows, R, cols, C, D, mode, edge, SPHK_ANGLE_EQUATOR, nullptr, C, nullptr, nullptr, nullptr, nullptr,
+                         row_base, 0, workspace, stream, row_target, col_tie);
 }
 
 int sphk_loss_fwd_bwd(const float* pred, const float* target, int64_t n, int D, float* iou, const float* grad_iou,

@@ -230,6 +230,63 @@ def test_config2_slice_vs_c_oracle(api, c_oracle):
     assert np.abs(got - want).max() < 1e-5
 
 
+# ---- fused assignment -------------------------------------------------------
+@pytest.mark.parametrize("assign_all", [True, False])
+@pytest.mark.parametrize("min_pos_iou", [0.0, 0.3])
+def test_fused_assigner_equals_reference_on_the_matrix(api, assign_all, min_pos_iou):
+    """SphMaxIoUAssigner (no matrix) == the reference's assign_wrt_overlaps loop run on the matrix."""
+    from sph_retina_b200 import synthetic as S
+    from sph_retina_b200.sphdet.assigners import SphMaxIoUAssigner
+    anchors = S.retina_anchors()[::3].contiguous()
+    anchors[100] = anchors[5000] = anchors[7]           # duplicated anchors: ties on the row maxima
+    gts = S.generate_boxes(32, alpha_range=(5, 120), beta_range=(5, 120), box="rbfov", seed=100)
+    gts[3] = torch.tensor([10.0, 90.0, 0.5, 0.5, 0.0])   # a tiny GT no anchor reaches 0.3 with
+    labels = torch.randint(0, 37, (32,))
+    anchors, gts, labels = anchors.to(DEV), gts.to(DEV), labels.to(DEV)
+    calc = api.iou.SphOverlaps2D('sph2pob_efficient_iou', 5)
+    a = SphMaxIoUAssigner(0.5, 0.3, min_pos_iou=min_pos_iou, gt_max_assign_all=assign_all, iou_calculator=calc)
+    res = a.assign(anchors, gts, gt_labels=labels)
+    overlaps = calc(gts, anchors)
+    g, m, l = O.assign_wrt_overlaps(overlaps.cpu(), labels.cpu(), 0.5, 0.3, min_pos_iou, assign_all, True)
+    assert res.num_gts == 32 and res.gt_inds.dtype == torch.int64
+    assert torch.equal(res.max_overlaps.cpu(), m)
+    if assign_all:
+        assert torch.equal(res.gt_inds.cpu(), g) and torch.equal(res.labels.cpu(), l)
+    else:
+        # argmax ties are resolved to the lowest index here; torch.max documents no rule: compare where the row max is unique
+        uniq = (overlaps == overlaps.max(dim=1, keepdim=True)[0]).sum(dim=1).cpu() == 1
+        same = res.gt_inds.cpu() == g
+        assert same.float().mean() > 0.999 and bool(uniq.float().mean() > 0.8)
+    assert int((res.gt_inds > 0).sum()) > 100 and int((res.gt_inds == 0).sum()) > 1000 and int((res.gt_inds == -1).sum()) > 10
+
+
+def test_fused_assigner_corner_cases(api):
+    from sph_retina_b200.sphdet.assigners import SphMaxIoUAssigner
+    calc = api.iou.SphOverlaps2D('sph2pob_efficient_iou', 4)
+    a = SphMaxIoUAssigner(0.5, 0.4, iou_calculator=calc)
+    boxes = O.generate_boxes(500, alpha_range=(5, 60), beta_range=(5, 60), seed=1).to(DEV)
+    gts = O.generate_boxes(6, alpha_range=(5, 60), beta_range=(5, 60), seed=2).to(DEV)
+    # no GT -> everything background; no boxes -> empty
+    r = a.assign(boxes, gts[:0])
+    assert r.num_gts == 0 and bool((r.gt_inds == 0).all())
+    assert a.assign(boxes[:0], gts).gt_inds.numel() == 0
+    # a GT far from every box (best overlap exactly 0, min_pos_iou = 0): mmdet assigns every zero-overlap box to it
+    far = torch.tensor([[0.5, 0.5, 1.0, 1.0]], device=DEV)
+    near = boxes[:50].clone(); near[:, 1] = near[:, 1].clamp(min=60)
+    r = a.assign(near, torch.cat([gts[:2], far]))
+    ov = calc(torch.cat([gts[:2], far]), near)
+    g, m, _ = O.assign_wrt_overlaps(ov.cpu(), None, 0.5, 0.4, 0.0, True, True)
+    assert torch.equal(r.gt_inds.cpu(), g) and torch.equal(r.max_overlaps.cpu(), m)
+    # ignore region (matrix path)
+    ai = SphMaxIoUAssigner(0.5, 0.4, ignore_iof_thr=0.5, iou_calculator=calc)
+    r = ai.assign(boxes, gts, gt_bboxes_ignore=boxes[:3])
+    ov = calc(gts, boxes)
+    ign = calc(boxes, boxes[:3], mode='iof').max(dim=1)[0]
+    ov[:, ign > 0.5] = -1
+    g, m, _ = O.assign_wrt_overlaps(ov.cpu(), None, 0.5, 0.4, 0.0, True, True)
+    assert torch.equal(r.gt_inds.cpu(), g) and bool((r.gt_inds[:3] == -1).all())
+
+
 # ---- loss --------------------------------------------------------------------------------------
 def grad_row_error(got, truth):
     den = np.linalg.norm(truth, axis=1)

@@ -127,3 +127,31 @@ def test_weight_reduce_matches_mmdet_rules():
     assert _weight_reduce_loss(loss, w, 'none', avg_factor=2).tolist() == [1.0, 0.0, 3.0]
     with pytest.raises(ValueError):
         _weight_reduce_loss(loss, w, 'sum', avg_factor=2)
+
+
+def test_vectorised_assign_wrt_overlaps_equals_the_reference_loop():
+    """SphMaxIoUAssigner.assign_wrt_overlaps (no Python loop) against the literal restatement of
+    mmdet/core/bbox/assigners/max_iou_assigner.py:135-220, on matrices full of ties and zeros."""
+    import os
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import sph_oracle as O
+    from sph_retina_b200.sphdet.assigners import SphMaxIoUAssigner
+    torch.manual_seed(0)
+    for trial in range(40):
+        K, N = int(torch.randint(0, 12, (1,))), int(torch.randint(0, 300, (1,)))
+        ov = (torch.rand(K, N) * torch.rand(K, N)).round(decimals=2)
+        ov[torch.rand(K, N) < 0.5] = 0
+        if trial % 5 == 0 and N:
+            ov[:, torch.rand(N) < 0.2] = -1          # an ignore region
+        lab = torch.randint(0, 5, (K,))
+        for all_ in (True, False):
+            for mlq in (True, False):
+                for neg in (0.4, (0.1, 0.4)):
+                    a = SphMaxIoUAssigner(0.5, neg, min_pos_iou=0.0 if trial % 2 else 0.2, gt_max_assign_all=all_,
+                                          match_low_quality=mlq)
+                    r = a.assign_wrt_overlaps(ov, lab)
+                    g, m, l = O.assign_wrt_overlaps(ov, lab, 0.5, neg, a.min_pos_iou, all_, mlq)
+                    assert r.num_gts == K and torch.equal(r.gt_inds, g) and torch.equal(r.max_overlaps, m)
+                    assert torch.equal(r.labels, l)
