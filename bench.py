@@ -289,6 +289,17 @@ def other_configs(torch, native, dev, flush):
     calc = SphOverlaps2D('sph2pob_efficient_iou', 5)
     ms = quick(torch, lambda: calc(gts.view(-1, 5), anchors).view(IMAGES, GTS, -1), flush=flush)
     out["assign_16img_one_call"] = {"ms": ms, "pairs_per_s": IMAGES * GTS * anchors.size(0) / ms * 1e3}
+    # the consumer of configs[1]: MaxIoUAssigner(pos 0.5, neg 0.3, min_pos 0) per image.  (a) the drop-in way:
+    # matrix from the calculator + assign_wrt_overlaps on it; (b) SphMaxIoUAssigner: no matrix, two fused passes
+    from sph_retina_b200.sphdet.assigners import SphMaxIoUAssigner
+    asg = SphMaxIoUAssigner(0.5, 0.3, min_pos_iou=0.0, iou_calculator=calc)
+    labels = torch.randint(0, 37, (IMAGES, GTS), device=dev)
+    ms_a = quick(torch, lambda: [asg.assign_wrt_overlaps(calc(gts[i], anchors), labels[i]) for i in range(IMAGES)], iters=5, flush=flush)
+    ms_b = quick(torch, lambda: [asg.assign(anchors, gts[i], gt_labels=labels[i]) for i in range(IMAGES)], iters=5, flush=flush)
+    gl, ll = [gts[i] for i in range(IMAGES)], [labels[i] for i in range(IMAGES)]
+    ms_c = quick(torch, lambda: asg.assign_batch(anchors, gl, ll), iters=5, flush=flush)
+    out["assigner_16img"] = {"matrix_then_assign_ms": ms_a, "fused_per_image_ms": ms_b, "fused_batch_ms": ms_c,
+                             "pairs_per_s_fused_batch": IMAGES * GTS * anchors.size(0) / ms_c * 1e3}
     A = S.generate_boxes(1 << 20, alpha_range=(1, 100), beta_range=(1, 100), box="rbfov", seed=0).to(dev)
     G = S.generate_boxes(1024, alpha_range=(1, 100), beta_range=(1, 100), box="rbfov", seed=1).to(dev)
     ms = quick(torch, lambda: sph_max_overlaps(A, G), iters=3, warmup=1, flush=flush)

@@ -86,6 +86,21 @@ int sphk_iou_pairwise(int kind, const float* rows, int64_t R, const float* cols,
 int sphk_iou_pairwise_ties(int kind, const float* rows, int64_t R, const float* cols, int64_t C, int D, int mode, int edge,
                            const float* row_target, int32_t* col_tie, int32_t row_base, void* workspace, void* stream);
 
+/* MaxIoUAssigner.assign for a batch of images that share one anchor list, without the K x N matrices
+ * (mmdet/core/bbox/assigners/max_iou_assigner.py:67-220; per-image loop mmdet/models/dense_heads/anchor_head.py:368-377):
+ *   gts             [sumK, D]   ground truths of all images, concatenated (bboxes1 role, as :113 calls the calculator)
+ *   gt_offsets_host [batch+1]   HOST array, image b owns gts[gt_offsets[b] .. gt_offsets[b+1])
+ *   boxes           [N, D]      anchors / proposals (bboxes2 role), shared by the images
+ *   neg_iou_lo/hi               the negative range [lo, hi): (0, neg_iou_thr) for a float threshold (:178-184)
+ *   gt_labels       [sumK] int64 or NULL;  labels [batch, N] int64 or NULL
+ *   gt_inds [batch, N] int64: -1 ignore, 0 background, i+1 = assigned to the image's GT i;  max_overlaps [batch, N]
+ * Launches: records, pass 1 (fused max/argmax), targets, pass 2 (ties, only for gt_max_assign_all), epilogue. */
+int64_t sphk_max_iou_assign_workspace_bytes(int64_t sumK, int64_t N, int32_t batch);
+int sphk_max_iou_assign(int kind, const float* gts, const int32_t* gt_offsets_host, int32_t batch, const float* boxes,
+                        int64_t N, int D, float pos_iou_thr, float neg_iou_lo, float neg_iou_hi, float min_pos_iou,
+                        int gt_max_assign_all, int match_low_quality, const int64_t* gt_labels, int64_t* gt_inds,
+                        float* max_overlaps, int64_t* labels, void* workspace, void* stream);
+
 /* Sph2Pob loss, fused forward + backward (Sph2PobIoULoss, mode='iou'):
  * replaces Sph2PobTransfrom.new_forward (sphdet/losses/sph2pob_transform.py:24-35: jitter_1,
  * sph2pob_standard, jitter_2) followed by diff_iou_rotated_2d(...).clamp(0,1)

@@ -37,6 +37,10 @@ SIGNATURES = {
                                  ctypes.c_void_p, ctypes.c_void_p]),
     "sphk_iou_pairwise_ties": (_int, [_int, _c_float_p, _i64, _c_float_p, _i64, _int, _int, _int, _c_float_p, ctypes.c_void_p,
                                       _i32, ctypes.c_void_p, ctypes.c_void_p]),
+    "sphk_max_iou_assign_workspace_bytes": (_i64, [_i64, _i64, _i32]),
+    "sphk_max_iou_assign": (_int, [_int, _c_float_p, ctypes.POINTER(_i32), _i32, _c_float_p, _i64, _int, ctypes.c_float,
+                                   ctypes.c_float, ctypes.c_float, ctypes.c_float, _int, _int, ctypes.c_void_p, ctypes.c_void_p,
+                                   _c_float_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "sphk_loss_fwd_bwd": (_int, [_c_float_p, _c_float_p, _i64, _int, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
                                  ctypes.c_void_p]),
     "sphk_obb_fwd": (_int, [_int, _c_float_p, _c_float_p, _i64, _int, _int, _c_float_p, _c_float_p, ctypes.c_void_p]),
@@ -202,6 +206,37 @@ def iou_pairwise_ties(kind: str, rows, cols, row_target, mode="iou", edge="arc",
                                           _ptr(row_target), _ptr(tie), row_base, _ptr(ws), _stream(rows)))
     launches += 2
     return tie
+
+
+def max_iou_assign(kind: str, gts, gt_offsets, boxes, pos_iou_thr, neg_lo, neg_hi, min_pos_iou, gt_max_assign_all,
+                   match_low_quality, gt_labels=None):
+    """Batched MaxIoUAssigner.  gts [sumK, D] (all images), gt_offsets: python list of batch+1 ints, boxes [N, D] shared.
+    Returns (gt_inds [B, N] int64, max_overlaps [B, N] float32, labels [B, N] int64 | None)."""
+    global launches
+    boxes = _boxes(boxes, "bboxes")
+    dev, N, B = boxes.device, boxes.size(0), len(gt_offsets) - 1
+    sumK = int(gt_offsets[-1])
+    if sumK > 0:
+        gts = _boxes(gts, "gt_bboxes")
+        assert gts.size(0) == sumK and gts.size(1) == boxes.size(1)
+    gt_inds = torch.empty((B, N), dtype=torch.int64, device=dev)
+    max_overlaps = torch.empty((B, N), dtype=torch.float32, device=dev)
+    labels = None
+    if gt_labels is not None:
+        gt_labels = gt_labels.to(device=dev, dtype=torch.int64).contiguous()
+        assert gt_labels.numel() == sumK
+        labels = torch.empty((B, N), dtype=torch.int64, device=dev)
+    if B == 0 or N == 0:
+        return gt_inds, max_overlaps, labels
+    offs = (_i32 * (B + 1))(*[int(v) for v in gt_offsets])
+    ws = _workspace(dev, lib.sphk_max_iou_assign_workspace_bytes(sumK, N, B))
+    with _on_device(dev):
+        _check(lib.sphk_max_iou_assign(KIND[kind], _ptr(gts) if sumK > 0 else None, offs, B, _ptr(boxes), N, boxes.size(1),
+                                       float(pos_iou_thr), float(neg_lo), float(neg_hi), float(min_pos_iou),
+                                       int(bool(gt_max_assign_all)), int(bool(match_low_quality)), _ptr(gt_labels), _ptr(gt_inds),
+                                       _ptr(max_overlaps), _ptr(labels), _ptr(ws), _stream(boxes)))
+    launches += 6
+    return gt_inds, max_overlaps, labels
 
 
 def loss_fwd_bwd(pred, target, grad_iou=None, want_grad_pred=False, want_grad_target=False):

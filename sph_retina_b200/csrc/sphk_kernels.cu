@@ -369,18 +369,31 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
                 const float4* __restrict__ rec, const float4* __restrict__ cull, int kind, int mode, int edge,
                 float* __restrict__ out, int64_t ld, unsigned long long* __restrict__ row_key,
                 unsigned long long* __restrict__ col_key, uint32_t row_base, uint32_t col_base, bool dense,
-                const float* __restrict__ row_target, int* __restrict__ col_tie) {
+                const float* __restrict__ row_target, int* __restrict__ col_tie,
+                const int32_t* __restrict__ row_offsets, int64_t col_stride) {
     __shared__ __align__(16) PairTile<TR> T;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // grid = (row tiles, column tiles).  Column tiles are taken heaviest-first: RetinaNet-style anchor lists
     // end with the coarse pyramid levels, whose huge anchors overlap every GT, so the tail of the launch is
     // made of the light tiles.
     const uint32_t rt = blockIdx.x, ct = gridDim.y - 1u - blockIdx.y;
+    // Batch mode (blockIdx.z = image): the rows are the concatenated GT lists of all images, image b owning rows
+    // [row_offsets[b], row_offsets[b+1]); row tiles never straddle images, every column-side result (max/argmax
+    // keys, ties) is per image at offset b * col_stride, and reported row indices are local to the image.
+    int64_t r_begin = 0, r_end = R;
+    if (row_offsets) {
+        r_begin = row_offsets[blockIdx.z];
+        r_end = row_offsets[blockIdx.z + 1];
+        if ((int64_t)rt * TR >= r_end - r_begin) return;
+        if (col_key) col_key += blockIdx.z * col_stride;
+        if (col_tie) col_tie += blockIdx.z * col_stride;
+        row_base -= (uint32_t)r_begin;
+    }
     PairOut o;
-    o.out = out; o.ld = ld; o.r0 = (int64_t)rt * TR; o.c0 = (int64_t)ct * kTC;
+    o.out = out; o.ld = ld; o.r0 = r_begin + (int64_t)rt * TR; o.c0 = (int64_t)ct * kTC;
     o.want_row = row_key != nullptr; o.want_col = col_key != nullptr; o.tie = col_tie != nullptr;
     o.row_base = row_base; o.col_base = col_base;
-    const int nr = (int)min((int64_t)TR, R - o.r0);
+    const int nr = (int)min((int64_t)TR, r_end - o.r0);
     const bool col_ok = o.c0 + tid < C;
     if (out) {
         // zero-fill this warp's [nr x 32] part of the matrix; live pairs overwrite their entry later
@@ -483,6 +496,62 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
             if (key != 0ull && key > col_key[o.c0 + tid]) atomicMax(&col_key[o.c0 + tid], key);
         }
     }
+}
+
+// ---- MaxIoUAssigner without the matrix (mmdet/core/bbox/assigners/max_iou_assigner.py:135-220) ------------
+// k_assign_targets: per GT, from the packed row key: its best overlap; for gt_max_assign_all the value the
+//   tie pass compares with (-1 disables the row) and, for a GT whose best overlap is exactly 0, its claim on
+//   every anchor of the image; otherwise its claim on its argmax anchor.  Later GTs override earlier ones.
+__global__ void __launch_bounds__(kThreads)
+k_assign_targets(const unsigned long long* __restrict__ row_key, int64_t sumK, const int32_t* __restrict__ offsets,
+                 int batch, int64_t N, float min_pos_iou, bool assign_all, float* __restrict__ target,
+                 int* __restrict__ zero_row, int* __restrict__ last) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= sumK) return;
+    int b = 0;
+    while (b + 1 < batch && i >= offsets[b + 1]) ++b;
+    const int local = (int)(i - offsets[b]);
+    const unsigned long long k = row_key[i];
+    const float gmax = (k == 0ull) ? 0.0f : __uint_as_float((uint32_t)(k >> 32));
+    const int64_t garg = (k == 0ull) ? 0 : (int64_t)(0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull));
+    const bool valid = gmax >= min_pos_iou;
+    if (assign_all) {
+        target[i] = (valid && gmax > 0.0f) ? gmax : -1.0f;
+        if (valid && !(gmax > 0.0f)) atomicMax(&zero_row[b], local + 1);
+    } else if (valid) {
+        atomicMax(&last[(int64_t)b * N + garg], local + 1);
+    }
+}
+
+// k_assign_epilogue: per (image, anchor): thresholds, low-quality override, labels.
+__global__ void __launch_bounds__(kThreads)
+k_assign_epilogue(const unsigned long long* __restrict__ col_key, const int* __restrict__ last,
+                  const int* __restrict__ zero_row, const int32_t* __restrict__ offsets, int batch, int64_t N,
+                  float pos_thr, float neg_lo, float neg_hi, bool match_low_quality, bool assign_all,
+                  const int64_t* __restrict__ gt_labels, int64_t* __restrict__ gt_inds, float* __restrict__ max_overlaps,
+                  int64_t* __restrict__ labels) {
+    const int64_t p = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (p >= (int64_t)batch * N) return;
+    const int b = (int)(p / N);
+    const int num_gts = offsets[b + 1] - offsets[b];
+    const unsigned long long k = col_key[p];
+    const float m = (k == 0ull) ? 0.0f : __uint_as_float((uint32_t)(k >> 32));
+    const int arg = (k == 0ull) ? 0 : (int)(0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull));
+    int64_t a = -1;
+    if (num_gts == 0) {
+        a = 0;                                            // :158-160 no ground truth: everything is background
+    } else {
+        if (m >= neg_lo && m < neg_hi) a = 0;             // :178-184
+        if (m >= pos_thr) a = arg + 1;                    // :187-188
+        if (match_low_quality) {                          // :190-207
+            int l = last[p];
+            if (assign_all) l = max(l, zero_row[b]);
+            if (l > 0) a = l;
+        }
+    }
+    gt_inds[p] = a;
+    max_overlaps[p] = m;
+    if (labels) labels[p] = (a > 0 && gt_labels) ? gt_labels[offsets[b] + a - 1] : -1;
 }
 
 __global__ void k_fill_keys(unsigned long long* keys, int64_t n) {
@@ -745,6 +814,54 @@ int64_t sphk_iou_pairwise_workspace_bytes(int64_t R, int64_t C) {
     return keys_bytes(R, C) + (R + C) * (int64_t)((kBoxRecFloats + kBoxCullFloats) * sizeof(float));
 }
 
+// k_box_pre + k_iou_pairwise2 for rows[R] x cols[C] (rows = concatenation of `batch` GT lists when row_offsets is
+// given; max_rows = the longest list).  rec / cull: [R + C] records in the workspace.
+static int launch_pairwise2(int kind, const float* rows, int64_t R, const float* cols, int64_t C, int D, int mode, int edge,
+                            float4* rec, float4* cull, float* out, int64_t ld, unsigned long long* rkey,
+                            unsigned long long* ckey, int32_t row_base, int32_t col_base, const float* row_target,
+                            int* col_tie, const int32_t* row_offsets, int64_t col_stride, int batch, int64_t max_rows,
+                            cudaStream_t s) {
+    const int64_t col_tiles = (C + kThreads - 1) / kThreads;
+    if (D == 4) k_box_pre<4><<<blocks_for(R + C), kThreads, 0, s>>>(rows, R, cols, C, edge, rec, cull, aligned16(rows), aligned16(cols));
+    else k_box_pre<5><<<blocks_for(R + C), kThreads, 0, s>>>(rows, R, cols, C, edge, rec, cull, false, false);
+    // row-tile height: 32 when that already yields many CTAs per SM, else 8 so that the heavy
+    // (mostly-live) tiles are spread over more warps and the tail of the launch stays short
+    const int64_t tiles32 = col_tiles * ((max_rows + 31) / 32) * batch;
+    int tr = (tiles32 >= 16ll * sm_count()) ? 32 : 8;
+    if (g_force_tr == 8 || g_force_tr == 16 || g_force_tr == 32) tr = g_force_tr;   // tuning hook (SPHK_TR)
+    const int64_t row_tiles = (max_rows + tr - 1) / tr;
+    if (row_tiles > 0x7FFFFFFFll || col_tiles > 65535 || batch > 65535)
+        return fail(SPHK_ERR_UNSUPPORTED, "pairwise: more than 16.7 M columns, 2^31 row tiles or 65535 images; shard the call");
+    // launched with programmatic stream serialization: the prologue (zero-fill of the matrix) overlaps
+    // k_box_pre, the kernel itself waits (griddepcontrol.wait) before it reads the records
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)row_tiles, (unsigned)col_tiles, (unsigned)batch);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const float4* crec = rec;
+    const float4* ccull = cull;
+    const bool dn = g_dense != 0;
+    cudaError_t le;
+#define SPHK_PW2(DD, TR)                                                                                               \
+    le = cudaLaunchKernelEx(&cfg, k_iou_pairwise2<DD, TR>, rows, R, cols, C, crec, ccull, kind, mode, edge, out, ld, rkey, \
+                            ckey, (uint32_t)row_base, (uint32_t)col_base, dn, row_target, col_tie, row_offsets, col_stride)
+    if (D == 4 && tr == 32) SPHK_PW2(4, 32);
+    else if (D == 4 && tr == 16) SPHK_PW2(4, 16);
+    else if (D == 4) SPHK_PW2(4, 8);
+    else if (tr == 32) SPHK_PW2(5, 32);
+    else if (tr == 16) SPHK_PW2(5, 16);
+    else SPHK_PW2(5, 8);
+#undef SPHK_PW2
+    if (le != cudaSuccess) return cuda_fail(le, "cudaLaunchKernelEx(k_iou_pairwise2)");
+    return SPHK_OK;
+}
+
 static int pairwise_impl(int kind, const float* rows, int64_t R, const float* cols, int64_t C, int D, int mode, int edge,
                          int angle, float* out, int64_t ld, float* row_max, int32_t* row_arg, float* col_max,
                          int32_t* col_arg, int32_t row_base, int32_t col_base, void* workspace, void* stream,
@@ -796,43 +913,9 @@ static int pairwise_impl(int kind, const float* rows, int64_t R, const float* co
         } else {
             float4* rec = (float4*)((char*)workspace + keys_bytes(R, C));       // [R + C][4] rows first
             float4* cull = rec + (R + C) * 4;                                    // [R + C][2]
-            if (D == 4) k_box_pre<4><<<blocks_for(R + C), kThreads, 0, s>>>(rows, R, cols, C, edge, rec, cull, aligned16(rows), v);
-            else k_box_pre<5><<<blocks_for(R + C), kThreads, 0, s>>>(rows, R, cols, C, edge, rec, cull, false, false);
-            // row-tile height: 32 when that already yields many CTAs per SM, else 8 so that the heavy
-            // (mostly-live) tiles are spread over more warps and the tail of the launch stays short
-            const int64_t tiles32 = col_tiles * ((R + 31) / 32);
-            int tr = (tiles32 >= 16ll * sm_count()) ? 32 : 8;
-            if (g_force_tr == 8 || g_force_tr == 16 || g_force_tr == 32) tr = g_force_tr;   // tuning hook (SPHK_TR)
-            const int64_t row_tiles = (R + tr - 1) / tr;
-            if (row_tiles > 0x7FFFFFFFll || col_tiles > 65535)
-                return fail(SPHK_ERR_UNSUPPORTED, "sphk_iou_pairwise: more than 16.7 M columns or 2^31 row tiles; shard the call");
-            // launched with programmatic stream serialization: the prologue (zero-fill of the matrix) overlaps
-            // k_box_pre, the kernel itself waits (griddepcontrol.wait) before it reads the records
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3((unsigned)row_tiles, (unsigned)col_tiles, 1);
-            cfg.blockDim = dim3(kThreads, 1, 1);
-            cfg.dynamicSmemBytes = 0;
-            cfg.stream = s;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-            attr[0].val.programmaticStreamSerializationAllowed = 1;
-            cfg.attrs = attr;
-            cfg.numAttrs = 1;
-            const float4* crec = rec;
-            const float4* ccull = cull;
-            const bool dn = g_dense != 0;
-            cudaError_t le;
-#define SPHK_PW2(DD, TR)                                                                                               \
-    le = cudaLaunchKernelEx(&cfg, k_iou_pairwise2<DD, TR>, rows, R, cols, C, crec, ccull, kind, mode, edge, out, ld, rkey, \
-                            ckey, (uint32_t)row_base, (uint32_t)col_base, dn, row_target, col_tie)
-            if (D == 4 && tr == 32) SPHK_PW2(4, 32);
-            else if (D == 4 && tr == 16) SPHK_PW2(4, 16);
-            else if (D == 4) SPHK_PW2(4, 8);
-            else if (tr == 32) SPHK_PW2(5, 32);
-            else if (tr == 16) SPHK_PW2(5, 16);
-            else SPHK_PW2(5, 8);
-            if (le != cudaSuccess) return cuda_fail(le, "cudaLaunchKernelEx(k_iou_pairwise2)");
-#undef SPHK_PW2
+            const int rc = launch_pairwise2(kind, rows, R, cols, C, D, mode, edge, rec, cull, out, ld, rkey, ckey, row_base,
+                                            col_base, row_target, col_tie, nullptr, 0, 1, R, s);
+            if (rc != SPHK_OK) return rc;
         }
         SPHK_LAUNCH_CHECK("k_iou_pairwise");
     }
@@ -861,6 +944,73 @@ int sphk_iou_pairwise_ties(int kind, const float* rows, int64_t R, const float* 
     if (R == 0) return SPHK_OK;
     return pairwise_impl(kind, rows, R, cols, C, D, mode, edge, SPHK_ANGLE_EQUATOR, nullptr, C, nullptr, nullptr, nullptr, nullptr,
                          row_base, 0, workspace, stream, row_target, col_tie);
+}
+
+static inline int64_t align16(int64_t x) { return (x + 15) & ~15ll; }
+
+int64_t sphk_max_iou_assign_workspace_bytes(int64_t sumK, int64_t N, int32_t batch) {
+    if (sumK < 0 || N < 0 || batch < 0) return 0;
+    // row keys, column keys per image, records, tie targets, per-image zero rows, per (image, anchor) claims, offsets
+    return align16(sumK * 8) + align16((int64_t)batch * N * 8) + (sumK + N) * (int64_t)((kBoxRecFloats + kBoxCullFloats) * sizeof(float)) +
+           align16(sumK * 4) + align16((int64_t)batch * 4) + align16((int64_t)batch * N * 4) + align16(((int64_t)batch + 1) * 4);
+}
+
+int sphk_max_iou_assign(int kind, const float* gts, const int32_t* gt_offsets_host, int32_t batch, const float* boxes,
+                        int64_t N, int D, float pos_iou_thr, float neg_iou_lo, float neg_iou_hi, float min_pos_iou,
+                        int gt_max_assign_all, int match_low_quality, const int64_t* gt_labels, int64_t* gt_inds,
+                        float* max_overlaps, int64_t* labels, void* workspace, void* stream) {
+    if (kind != SPHK_KIND_SPH2POB_EFFICIENT && kind != SPHK_KIND_SPH2POB_STANDARD)
+        return fail(SPHK_ERR_UNSUPPORTED, "sphk_max_iou_assign: kind must be a Sph2Pob transform");
+    if (batch < 0 || N < 0 || (D != 4 && D != 5) || !gt_offsets_host) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_max_iou_assign: bad batch, N, D or offsets");
+    if (batch == 0 || N == 0) return SPHK_OK;
+    if (gt_offsets_host[0] != 0) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_max_iou_assign: gt_offsets[0] must be 0");
+    int64_t max_rows = 0;
+    for (int b = 0; b < batch; ++b) {
+        const int64_t k = (int64_t)gt_offsets_host[b + 1] - gt_offsets_host[b];
+        if (k < 0) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_max_iou_assign: gt_offsets must be non-decreasing");
+        max_rows = k > max_rows ? k : max_rows;
+    }
+    const int64_t sumK = gt_offsets_host[batch];
+    if (!boxes || !gt_inds || !max_overlaps || !workspace || (sumK > 0 && !gts)) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_max_iou_assign: null pointer");
+    if (!aligned16(workspace)) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_max_iou_assign: workspace must be 16-byte aligned");
+    if ((int64_t)batch * N > 0x7FFFFFFFll * (int64_t)kThreads) return fail(SPHK_ERR_UNSUPPORTED, "sphk_max_iou_assign: batch * N too large");
+    cudaStream_t s = (cudaStream_t)stream;
+    char* w = (char*)workspace;
+    unsigned long long* rkey = (unsigned long long*)w;            w += align16(sumK * 8);
+    unsigned long long* ckey = (unsigned long long*)w;            w += align16((int64_t)batch * N * 8);
+    float4* rec = (float4*)w;                                      w += (sumK + N) * (int64_t)(kBoxRecFloats * sizeof(float));
+    float4* cull = (float4*)w;                                     w += (sumK + N) * (int64_t)(kBoxCullFloats * sizeof(float));
+    float* target = (float*)w;                                     w += align16(sumK * 4);
+    int* zero_row = (int*)w;                                       w += align16((int64_t)batch * 4);
+    int* last = (int*)w;                                           w += align16((int64_t)batch * N * 4);
+    int32_t* offsets = (int32_t*)w;
+    cudaError_t e = cudaMemcpyAsync(offsets, gt_offsets_host, ((size_t)batch + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(gt_offsets)");
+    // one memset covers row keys + column keys; another one the zero rows + claims
+    e = cudaMemsetAsync(rkey, 0, (size_t)(align16(sumK * 8) + align16((int64_t)batch * N * 8)), s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(zero_row, 0, (size_t)(align16((int64_t)batch * 4) + align16((int64_t)batch * N * 4)), s);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(assign workspace)");
+    if (sumK > 0) {
+        // pass 1: per-GT and per-(image, anchor) max / argmax
+        int rc = launch_pairwise2(kind, gts, sumK, boxes, N, D, SPHK_MODE_IOU, SPHK_EDGE_ARC, rec, cull, nullptr, N, rkey, ckey, 0, 0,
+                                  nullptr, nullptr, offsets, N, batch, max_rows, s);
+        if (rc != SPHK_OK) return rc;
+        if (match_low_quality) {
+            k_assign_targets<<<blocks_for(sumK), kThreads, 0, s>>>(rkey, sumK, offsets, batch, N, min_pos_iou, gt_max_assign_all != 0,
+                                                                   target, zero_row, last);
+            if (gt_max_assign_all) {
+                // pass 2: which anchors tie the row maxima (same kernel, same operands: bit-identical overlaps)
+                rc = launch_pairwise2(kind, gts, sumK, boxes, N, D, SPHK_MODE_IOU, SPHK_EDGE_ARC, rec, cull, nullptr, N, nullptr, nullptr,
+                                      0, 0, target, last, offsets, N, batch, max_rows, s);
+                if (rc != SPHK_OK) return rc;
+            }
+        }
+    }
+    k_assign_epilogue<<<blocks_for((int64_t)batch * N), kThreads, 0, s>>>(ckey, last, zero_row, offsets, batch, N, pos_iou_thr, neg_iou_lo,
+                                                                         neg_iou_hi, match_low_quality != 0, gt_max_assign_all != 0,
+                                                                         gt_labels, gt_inds, max_overlaps, labels);
+    SPHK_LAUNCH_CHECK("k_assign_epilogue");
+    return SPHK_OK;
 }
 
 int sphk_loss_fwd_bwd(const float* pred, const float* target, int64_t n, int D, float* iou, const float* grad_iou,

@@ -7,14 +7,16 @@ Same constructor, ``assign`` signature, thresholds and result as
 ``max(dim=1)`` and a Python loop over the K ground truths with one N-wide equality scan each.
 Here:
 
-  pass 1  ``sphk_iou_pairwise`` with fused row/column max+argmax     -> per-GT and per-anchor (max, argmax)
-  pass 2  ``sphk_iou_pairwise_ties`` (only for ``gt_max_assign_all``) -> per anchor, the last GT whose
+  pass 1  the N x M kernel with fused row/column max+argmax          -> per-GT and per-anchor (max, argmax)
+  pass 2  the same kernel in tie mode (only for ``gt_max_assign_all``) -> per anchor, the last GT whose
           row maximum it ties (the result of the reference's ascending ``for i in range(num_gts)`` loop)
+  epilogue kernel: thresholds, low-quality override, labels
 
-plus a handful of N-long elementwise torch ops for the thresholds.  The matrix is never written.
-Corner cases that need the matrix semantics exactly (an ignore region, or a GT whose best overlap is
-exactly 0 while ``min_pos_iou <= 0`` -- mmdet then assigns *every* zero-overlap anchor to it) take the
-matrix path, still on the GPU through the same calculator."""
+all inside ONE C-ABI call (``sphk_max_iou_assign``), for one image (``assign``) or for all images of a step
+that share the anchor list (``assign_batch``).  The matrix is never written.
+No host synchronisation happens anywhere in ``assign``.  An ignore region (``ignore_iof_thr > 0`` with
+``gt_bboxes_ignore``) takes the matrix path, still on the GPU through the same calculator.  The mmdet quirk
+that a GT whose best overlap is exactly 0 (with ``min_pos_iou <= 0``) grabs *every* anchor is reproduced."""
 from __future__ import annotations
 
 import torch
@@ -37,12 +39,14 @@ class AssignResult:
         return len(self.gt_inds)
 
 
+try:
+    from mmdet.core.bbox.assigners.assign_result import AssignResult as _ResultClass
+except Exception:
+    _ResultClass = AssignResult
+
+
 def _result(num_gts, gt_inds, max_overlaps, labels):
-    try:
-        from mmdet.core.bbox.assigners.assign_result import AssignResult as MM
-        return MM(num_gts, gt_inds, max_overlaps, labels=labels)
-    except Exception:
-        return AssignResult(num_gts, gt_inds, max_overlaps, labels)
+    return _ResultClass(num_gts, gt_inds, max_overlaps, labels=labels)
 
 
 class SphMaxIoUAssigner:
@@ -65,10 +69,8 @@ class SphMaxIoUAssigner:
         has_ignore = (self.ignore_iof_thr > 0 and gt_bboxes_ignore is not None and gt_bboxes_ignore.numel() > 0
                       and bboxes.numel() > 0)
         fused_ok = isinstance(calc, SphOverlaps2D) and calc.backend in _KINDS and not has_ignore
-        if fused_ok and gt_bboxes.size(0) > 0 and bboxes.size(0) > 0:
-            res = self._assign_fused(bboxes, gt_bboxes, gt_labels)
-            if res is not None:
-                return res
+        if fused_ok and bboxes.size(0) > 0:
+            return self._assign_fused(bboxes, gt_bboxes, gt_labels)
         overlaps = calc(gt_bboxes, bboxes)
         if has_ignore:
             if self.ignore_wrt_candidates:
@@ -79,51 +81,64 @@ class SphMaxIoUAssigner:
         return self.assign_wrt_overlaps(overlaps, gt_labels)
 
     # ------------------------------------------------------------------------------------------
-    def _thresholds(self, assigned, max_overlaps, argmax_overlaps):
-        """Steps 2 and 3 of max_iou_assigner.py:178-190."""
+    def _thresholds(self, max_overlaps, argmax_overlaps):
+        """Steps 1-3 of max_iou_assigner.py:147-190 as select ops (no boolean-mask indexing, hence no host sync)."""
+        assigned = torch.full_like(argmax_overlaps, -1)
         if isinstance(self.neg_iou_thr, float):
-            assigned[(max_overlaps >= 0) & (max_overlaps < self.neg_iou_thr)] = 0
-        elif isinstance(self.neg_iou_thr, tuple):
-            assert len(self.neg_iou_thr) == 2
-            assigned[(max_overlaps >= self.neg_iou_thr[0]) & (max_overlaps < self.neg_iou_thr[1])] = 0
-        pos = max_overlaps >= self.pos_iou_thr
-        assigned[pos] = argmax_overlaps[pos] + 1
+            neg = (max_overlaps >= 0) & (max_overlaps < self.neg_iou_thr)
+        else:
+            assert isinstance(self.neg_iou_thr, tuple) and len(self.neg_iou_thr) == 2
+            neg = (max_overlaps >= self.neg_iou_thr[0]) & (max_overlaps < self.neg_iou_thr[1])
+        assigned = torch.where(neg, torch.zeros_like(assigned), assigned)
+        return torch.where(max_overlaps >= self.pos_iou_thr, argmax_overlaps + 1, assigned)
 
     @staticmethod
     def _labels(assigned, gt_labels):
         if gt_labels is None:
             return None
-        labels = assigned.new_full((assigned.numel(),), -1)
-        pos = assigned > 0
-        labels[pos] = gt_labels[assigned[pos] - 1]
-        return labels
+        picked = gt_labels.to(assigned.dtype)[(assigned - 1).clamp(min=0)]
+        return torch.where(assigned > 0, picked, torch.full_like(assigned, -1))
+
+    def _neg_range(self):
+        if isinstance(self.neg_iou_thr, float):
+            return 0.0, self.neg_iou_thr
+        assert isinstance(self.neg_iou_thr, tuple) and len(self.neg_iou_thr) == 2
+        return float(self.neg_iou_thr[0]), float(self.neg_iou_thr[1])
 
     def _assign_fused(self, bboxes, gt_bboxes, gt_labels):
+        return self.assign_batch(bboxes, [gt_bboxes], None if gt_labels is None else [gt_labels])[0]
+
+    def assign_batch(self, bboxes, gt_bboxes_list, gt_labels_list=None):
+        """All images of a step in one go when they share the anchor list (RetinaNet: SURVEY.md 3.1, the reference
+        loops over the images in Python, mmdet/models/dense_heads/anchor_head.py:368-377).  One C-ABI call
+        (``sphk_max_iou_assign``: 5-6 kernel launches for the whole batch), no K x N matrix, no host sync.
+        Returns a list of AssignResult, one per image."""
         calc = self.iou_calculator
-        kind = _KINDS[calc.backend]
-        gts, boxes = gt_bboxes[..., :calc.box_version], bboxes[..., :calc.box_version]
+        assert isinstance(calc, SphOverlaps2D) and calc.backend in _KINDS, "fused assignment needs a Sph2Pob calculator"
+        bv = calc.box_version
+        boxes = bboxes[..., :bv]
+        counts = [int(g.size(0)) for g in gt_bboxes_list]
+        offsets = [0]
+        for c in counts:
+            offsets.append(offsets[-1] + c)
+        nonempty = [g[..., :bv] for g in gt_bboxes_list if g.size(0) > 0]
+        gts = torch.cat(nonempty) if len(nonempty) > 1 else (nonempty[0] if nonempty else None)
+        labels = None
+        if gt_labels_list is not None and offsets[-1] > 0:
+            ll = [l for l, c in zip(gt_labels_list, counts) if c > 0]
+            labels = torch.cat(ll) if len(ll) > 1 else ll[0]
+        lo, hi = self._neg_range()
         with torch.no_grad():
-            _, (gt_max, gt_arg), (max_overlaps, argmax) = _native.iou_pairwise(
-                kind, gts, boxes, want_matrix=False, want_row_max=True, want_col_max=True)
-            assigned = torch.full((boxes.size(0),), -1, dtype=torch.long, device=boxes.device)
-            self._thresholds(assigned, max_overlaps, argmax.long())
-            if self.match_low_quality:
-                valid = gt_max >= self.min_pos_iou
-                if self.gt_max_assign_all:
-                    # a GT whose best overlap is exactly 0 ties with every zero entry of its row: matrix semantics
-                    if bool((valid & (gt_max <= 0)).any()):
-                        return None
-                    target = torch.where(valid, gt_max, torch.full_like(gt_max, -1.0))
-                    tie = _native.iou_pairwise_ties(kind, gts, boxes, target).long()
-                    assigned = torch.where(tie > 0, tie, assigned)
-                else:
-                    # assigned[gt_argmax[i]] = i + 1 for ascending i: the largest i wins on duplicates
-                    idx = torch.arange(1, gts.size(0) + 1, device=boxes.device)
-                    idx = torch.where(valid, idx, torch.zeros_like(idx))
-                    last = torch.zeros(boxes.size(0), dtype=torch.long, device=boxes.device)
-                    last.scatter_reduce_(0, gt_arg.long(), idx, reduce='amax', include_self=True)
-                    assigned = torch.where(last > 0, last, assigned)
-        return _result(gts.size(0), assigned, max_overlaps, self._labels(assigned, gt_labels))
+            gt_inds, max_overlaps, out_labels = _native.max_iou_assign(
+                _KINDS[calc.backend], gts, offsets, boxes, self.pos_iou_thr, lo, hi, self.min_pos_iou,
+                self.gt_max_assign_all, self.match_low_quality, labels)
+        res = []
+        for b, k in enumerate(counts):
+            lab = None
+            if gt_labels_list is not None:
+                lab = out_labels[b] if out_labels is not None else gt_inds.new_full((gt_inds.size(1),), -1)
+            res.append(_result(k, gt_inds[b], max_overlaps[b], lab))
+        return res
 
     # ------------------------------------------------------------------------------------------
     def assign_wrt_overlaps(self, overlaps, gt_labels=None):
@@ -138,7 +153,7 @@ class SphMaxIoUAssigner:
             return _result(num_gts, assigned, max_overlaps, labels)
         max_overlaps, argmax_overlaps = overlaps.max(dim=0)
         gt_max, gt_arg = overlaps.max(dim=1)
-        self._thresholds(assigned, max_overlaps, argmax_overlaps)
+        assigned = self._thresholds(max_overlaps, argmax_overlaps)
         if self.match_low_quality:
             valid = gt_max >= self.min_pos_iou
             idx = torch.arange(1, num_gts + 1, device=overlaps.device)

@@ -260,6 +260,30 @@ def test_fused_assigner_equals_reference_on_the_matrix(api, assign_all, min_pos_
     assert int((res.gt_inds > 0).sum()) > 100 and int((res.gt_inds == 0).sum()) > 1000 and int((res.gt_inds == -1).sum()) > 10
 
 
+def test_fused_assigner_batch_equals_per_image(api):
+    from sph_retina_b200 import synthetic as S
+    from sph_retina_b200.sphdet.assigners import SphMaxIoUAssigner
+    anchors = S.retina_anchors()[::5].contiguous().to(DEV)
+    calc = api.iou.SphOverlaps2D('sph2pob_efficient_iou', 5)
+    counts = [32, 0, 7, 1, 33, 64]
+    gts = [S.generate_boxes(k, alpha_range=(5, 120), beta_range=(5, 120), box="rbfov", seed=200 + i).to(DEV) for i, k in enumerate(counts)]
+    labels = [torch.randint(0, 37, (k,), device=DEV) for k in counts]
+    for assign_all in (True, False):
+        a = SphMaxIoUAssigner(0.5, (0.05, 0.3), min_pos_iou=0.1, gt_max_assign_all=assign_all, iou_calculator=calc)
+        batch = a.assign_batch(anchors, gts, labels)
+        assert len(batch) == len(counts)
+        for b, k in enumerate(counts):
+            ov = calc(gts[b], anchors) if k else anchors.new_zeros((0, anchors.size(0)))
+            g, m, l = O.assign_wrt_overlaps(ov.cpu(), labels[b].cpu(), 0.5, (0.05, 0.3), 0.1, assign_all, True)
+            assert batch[b].num_gts == k and torch.equal(batch[b].max_overlaps.cpu(), m)
+            if assign_all or k == 0:
+                assert torch.equal(batch[b].gt_inds.cpu(), g) and torch.equal(batch[b].labels.cpu(), l)
+            else:
+                assert (batch[b].gt_inds.cpu() == g).float().mean() > 0.999
+            one = a.assign(anchors, gts[b], gt_labels=labels[b])
+            assert torch.equal(one.gt_inds, batch[b].gt_inds) and torch.equal(one.max_overlaps, batch[b].max_overlaps)
+
+
 def test_fused_assigner_corner_cases(api):
     from sph_retina_b200.sphdet.assigners import SphMaxIoUAssigner
     calc = api.iou.SphOverlaps2D('sph2pob_efficient_iou', 4)
