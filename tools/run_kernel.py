@@ -39,6 +39,13 @@ elif a.which == "sweep":
     A = S.generate_boxes(1 << 20, alpha_range=(1, 100), beta_range=(1, 100), box="rbfov", seed=0).to(dev)
     G = S.generate_boxes(1024, alpha_range=(1, 100), beta_range=(1, 100), box="rbfov", seed=1).to(dev)
     fn = lambda: sph_max_overlaps(A, G)
+elif a.which == "assigner":
+    from sph_retina_b200.sphdet.assigners import SphMaxIoUAssigner
+    gts, anchors = S.assignment_batch()
+    gts, anchors = gts.to(dev), anchors.to(dev)
+    asg = SphMaxIoUAssigner(0.5, 0.3, min_pos_iou=0.0, iou_calculator=SphOverlaps2D('sph2pob_efficient_iou', 5))
+    gl = [gts[i] for i in range(16)]
+    fn = lambda: asg.assign_batch(anchors, gl)
 else:
     gts, anchors = S.assignment_batch()
     gts, anchors = gts.to(dev), anchors.to(dev)
