@@ -418,6 +418,9 @@ def run_ours(args):
         gts_d, anchors_d = torch.empty_like(gts_pin, device=dev), torch.empty_like(anchors_pin, device=dev)
 
         def e2e_step():
+            # H2D of this step's inputs, 16 calculator calls, D2H of every matrix, all on the launching stream.
+            # (A side stream for the copies was tried: the per-call output allocation then has to be held across
+            # streams, which costs more than the overlap gains.  The step is bound by the 201 MB D2H over PCIe.)
             gts_d.copy_(gts_pin, non_blocking=True)
             anchors_d.copy_(anchors_pin, non_blocking=True)
             for i in range(IMAGES):

@@ -673,7 +673,7 @@ k_riou_fwd_bwd(const float* __restrict__ obb1, const float* __restrict__ obb2, i
 // plain register/shared-memory bit operations (no IoU, no block barrier per pivot).  Pivots and
 // columns already removed by earlier blocks are never evaluated.
 template <int D>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(1024)
 k_nms(const float* __restrict__ boxes, const int32_t* __restrict__ order, const int32_t* __restrict__ seg_offsets,
       float thr, uint8_t* __restrict__ keep, int max_words, bool vec_ok) {
     extern __shared__ uint32_t s_mem[];
@@ -683,13 +683,13 @@ k_nms(const float* __restrict__ boxes, const int32_t* __restrict__ order, const 
     if (k <= 0) return;
     const int W = (k + 31) >> 5;
     if (W > max_words) {   // caller under-sized max_seg_len: refuse rather than overrun shared memory
-        for (int q = threadIdx.x; q < k; q += kThreads) keep[start + q] = 0xFF;
+        for (int q = threadIdx.x; q < k; q += blockDim.x) keep[start + q] = 0xFF;
         return;
     }
     uint32_t* removed = s_mem;             // [W]
     uint32_t* mask = s_mem + max_words;    // [32][W]
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = kThreads >> 5;
-    for (int w = threadIdx.x; w < W; w += kThreads) removed[w] = 0u;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int w = threadIdx.x; w < W; w += blockDim.x) removed[w] = 0u;
     __syncthreads();
     for (int i0 = 0; i0 < k; i0 += 32) {
         const int nb = min(32, k - i0);
@@ -720,7 +720,7 @@ k_nms(const float* __restrict__ boxes, const int32_t* __restrict__ order, const 
         }
         __syncthreads();
     }
-    for (int q = threadIdx.x; q < k; q += kThreads) keep[start + q] = ((removed[q >> 5] >> (q & 31)) & 1u) ? 0 : 1;
+    for (int q = threadIdx.x; q < k; q += blockDim.x) keep[start + q] = ((removed[q >> 5] >> (q & 31)) & 1u) ? 0 : 1;
 }
 
 __global__ void __launch_bounds__(kThreads) k_probe_fp32(int iters, float* __restrict__ sink) {
@@ -1079,15 +1079,18 @@ int sphk_nms_batched(const float* boxes, const int32_t* order, const int32_t* se
     if (smem > 200u * 1024u) return fail(SPHK_ERR_UNSUPPORTED, "sphk_nms_batched: segment longer than 49,000 boxes");
     cudaStream_t s = (cudaStream_t)stream;
     const bool v = aligned16(boxes);
+    // one CTA per segment; its width follows the longest segment: a 32-pivot round has up to 32 * k/32 (pivot, word)
+    // units, one warp each
+    const int nt = max_seg_len <= 64 ? 128 : (max_seg_len <= 256 ? 256 : (max_seg_len <= 512 ? 512 : 1024));
     cudaError_t e;
     if (D == 4) {
         e = cudaFuncSetAttribute(k_nms<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_nms)");
-        k_nms<4><<<S, kThreads, smem, s>>>(boxes, order, seg_offsets, iou_threshold, keep, max_words, v);
+        k_nms<4><<<S, nt, smem, s>>>(boxes, order, seg_offsets, iou_threshold, keep, max_words, v);
     } else {
         e = cudaFuncSetAttribute(k_nms<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_nms)");
-        k_nms<5><<<S, kThreads, smem, s>>>(boxes, order, seg_offsets, iou_threshold, keep, max_words, v);
+        k_nms<5><<<S, nt, smem, s>>>(boxes, order, seg_offsets, iou_threshold, keep, max_words, v);
     }
     SPHK_LAUNCH_CHECK("k_nms");
     return SPHK_OK;
