@@ -76,6 +76,14 @@ int sphk_iou_pairwise(int kind, const float* rows, int64_t R, const float* cols,
                       int edge, int angle, float* out, int64_t ld, float* row_max, int32_t* row_arg, float* col_max,
                       int32_t* col_arg, int32_t row_base, int32_t col_base, void* workspace, void* stream);
 
+/* The fused max/argmax of sphk_iou_pairwise as PACKED keys (no matrix, no unpacking), for reductions across
+ * shards: key = float32 bits << 32 | (0xFFFFFFFF - index), 0 = "no positive overlap".  The integer maximum of
+ * such keys over shards is (max value, lowest index) -- the single-device tie rule.
+ *   row_keys [R]: max over the columns (index = col_base + j);  col_keys [C]: max over the rows (row_base + i) */
+int sphk_iou_pairwise_keys(int kind, const float* rows, int64_t R, const float* cols, int64_t C, int D, int mode, int edge,
+                           uint64_t* row_keys, uint64_t* col_keys, int32_t row_base, int32_t col_base, void* workspace,
+                           void* stream);
+
 /* Second pass of MaxIoUAssigner's low-quality matching with gt_max_assign_all=True
  * (mmdet/core/bbox/assigners/max_iou_assigner.py:201-205: for each GT i in ascending order,
  * `assigned[overlaps[i, :] == gt_max_overlaps[i]] = i + 1`) without the K x N matrix:

@@ -35,6 +35,8 @@ SIGNATURES = {
     "sphk_iou_pairwise": (_int, [_int, _c_float_p, _i64, _c_float_p, _i64, _int, _int, _int, _int, _c_float_p, _i64,
                                  _c_float_p, ctypes.c_void_p, _c_float_p, ctypes.c_void_p, _i32, _i32,
                                  ctypes.c_void_p, ctypes.c_void_p]),
+    "sphk_iou_pairwise_keys": (_int, [_int, _c_float_p, _i64, _c_float_p, _i64, _int, _int, _int, ctypes.c_void_p, ctypes.c_void_p,
+                                      _i32, _i32, ctypes.c_void_p, ctypes.c_void_p]),
     "sphk_iou_pairwise_ties": (_int, [_int, _c_float_p, _i64, _c_float_p, _i64, _int, _int, _int, _c_float_p, ctypes.c_void_p,
                                       _i32, ctypes.c_void_p, ctypes.c_void_p]),
     "sphk_max_iou_assign_workspace_bytes": (_i64, [_i64, _i64, _i32]),
@@ -190,6 +192,23 @@ def iou_pairwise(kind: str, rows, cols, mode="iou", edge="arc", want_matrix=True
                                      _ptr(ws), _stream(rows)))
     launches += 1 + int(kind in ("sph2pob_efficient", "sph2pob_standard")) + 2 * int(want_row_max) + 2 * int(want_col_max)
     return mat, ((rmax, rarg) if want_row_max else None), ((cmax, carg) if want_col_max else None)
+
+
+def iou_pairwise_keys(kind: str, rows, cols, mode="iou", edge="arc", row_base=0, col_base=0):
+    """Fused max/argmax of the N x M overlaps as the kernel's packed keys, without unpacking:
+    (row_keys[R], col_keys[C]) int64 = float32 bits << 32 | (0xFFFFFFFF - index); 0 = no positive overlap.
+    Integer MAX over shards of such keys = (max value, lowest index): what the multi-GPU sweep reduces."""
+    global launches
+    rows, cols = _boxes(rows, "bboxes1"), _boxes(cols, "bboxes2")
+    R, C, dev = rows.size(0), cols.size(0), rows.device
+    rk = torch.empty(R, dtype=torch.int64, device=dev)
+    ck = torch.empty(C, dtype=torch.int64, device=dev)
+    ws = _workspace(dev, 104 * (R + C) + 32)
+    with _on_device(dev):
+        _check(lib.sphk_iou_pairwise_keys(KIND[kind], _ptr(rows), R, _ptr(cols), C, rows.size(1), MODE[mode], EDGE[edge],
+                                          _ptr(rk), _ptr(ck), row_base, col_base, _ptr(ws), _stream(rows)))
+    launches += 4
+    return rk, ck
 
 
 def iou_pairwise_ties(kind: str, rows, cols, row_target, mode="iou", edge="arc", row_base=0):

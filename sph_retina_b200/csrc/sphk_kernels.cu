@@ -865,7 +865,8 @@ static int launch_pairwise2(int kind, const float* rows, int64_t R, const float*
 static int pairwise_impl(int kind, const float* rows, int64_t R, const float* cols, int64_t C, int D, int mode, int edge,
                          int angle, float* out, int64_t ld, float* row_max, int32_t* row_arg, float* col_max,
                          int32_t* col_arg, int32_t row_base, int32_t col_base, void* workspace, void* stream,
-                         const float* row_target, int* col_tie) {
+                         const float* row_target, int* col_tie, unsigned long long* ext_rkey = nullptr,
+                         unsigned long long* ext_ckey = nullptr) {
     if (R < 0 || C < 0 || (D != 4 && D != 5)) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: bad R, C or D");
     if (kind < 0 || kind > 3) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: unknown kind");
     if (mode != SPHK_MODE_IOU && mode != SPHK_MODE_IOF) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: unknown mode");
@@ -877,7 +878,7 @@ static int pairwise_impl(int kind, const float* rows, int64_t R, const float* co
     if (out && ld < C) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: ld < C");
     if (R + (int64_t)(uint32_t)row_base > 0xFFFFFFFFll || C + (int64_t)(uint32_t)col_base > 0xFFFFFFFFll)
         return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: indices do not fit 32 bits");
-    const bool want_row = row_max || row_arg, want_col = col_max || col_arg;
+    const bool want_row = row_max || row_arg || ext_rkey, want_col = col_max || col_arg || ext_ckey;
     if (angle == SPHK_ANGLE_PROJECT && !approx) {
         if (want_row || want_col) return fail(SPHK_ERR_UNSUPPORTED, "sphk_iou_pairwise: rbb_angle='project' supports the matrix output only");
         if (R == 0 || C == 0 || !out) return SPHK_OK;
@@ -892,8 +893,8 @@ static int pairwise_impl(int kind, const float* rows, int64_t R, const float* co
         return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: workspace of sphk_iou_pairwise_workspace_bytes(R, C) required");
     if (workspace && !aligned16(workspace)) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: workspace must be 16-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
-    unsigned long long* rkey = want_row ? (unsigned long long*)workspace : nullptr;
-    unsigned long long* ckey = want_col ? (unsigned long long*)workspace + R : nullptr;
+    unsigned long long* rkey = ext_rkey ? ext_rkey : (want_row ? (unsigned long long*)workspace : nullptr);
+    unsigned long long* ckey = ext_ckey ? ext_ckey : (want_col ? (unsigned long long*)workspace + R : nullptr);
     if (want_row && R > 0) k_fill_keys<<<blocks_for(R), kThreads, 0, s>>>(rkey, R);
     if (want_col && C > 0) k_fill_keys<<<blocks_for(C), kThreads, 0, s>>>(ckey, C);
     if (R > 0 && C > 0) {
@@ -919,8 +920,8 @@ static int pairwise_impl(int kind, const float* rows, int64_t R, const float* co
         }
         SPHK_LAUNCH_CHECK("k_iou_pairwise");
     }
-    if (want_row && R > 0) k_unpack_keys<<<blocks_for(R), kThreads, 0, s>>>(rkey, R, row_max, row_arg, (uint32_t)col_base);
-    if (want_col && C > 0) k_unpack_keys<<<blocks_for(C), kThreads, 0, s>>>(ckey, C, col_max, col_arg, (uint32_t)row_base);
+    if ((row_max || row_arg) && R > 0) k_unpack_keys<<<blocks_for(R), kThreads, 0, s>>>(rkey, R, row_max, row_arg, (uint32_t)col_base);
+    if ((col_max || col_arg) && C > 0) k_unpack_keys<<<blocks_for(C), kThreads, 0, s>>>(ckey, C, col_max, col_arg, (uint32_t)row_base);
     SPHK_LAUNCH_CHECK("k_unpack_keys");
     return SPHK_OK;
 }
@@ -930,6 +931,17 @@ int sphk_iou_pairwise(int kind, const float* rows, int64_t R, const float* cols,
                       int32_t* col_arg, int32_t row_base, int32_t col_base, void* workspace, void* stream) {
     return pairwise_impl(kind, rows, R, cols, C, D, mode, edge, angle, out, ld, row_max, row_arg, col_max, col_arg, row_base,
                          col_base, workspace, stream, nullptr, nullptr);
+}
+
+int sphk_iou_pairwise_keys(int kind, const float* rows, int64_t R, const float* cols, int64_t C, int D, int mode, int edge,
+                           uint64_t* row_keys, uint64_t* col_keys, int32_t row_base, int32_t col_base, void* workspace,
+                           void* stream) {
+    if (kind != SPHK_KIND_SPH2POB_EFFICIENT && kind != SPHK_KIND_SPH2POB_STANDARD)
+        return fail(SPHK_ERR_UNSUPPORTED, "sphk_iou_pairwise_keys: kind must be a Sph2Pob transform");
+    if (!row_keys || !col_keys) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise_keys: null key pointer");
+    return pairwise_impl(kind, rows, R, cols, C, D, mode, edge, SPHK_ANGLE_EQUATOR, nullptr, C, nullptr, nullptr, nullptr, nullptr,
+                         row_base, col_base, workspace, stream, nullptr, nullptr, (unsigned long long*)row_keys,
+                         (unsigned long long*)col_keys);
 }
 
 int sphk_iou_pairwise_ties(int kind, const float* rows, int64_t R, const float* cols, int64_t C, int D, int mode, int edge,

@@ -26,8 +26,9 @@ def pack_keys(values: torch.Tensor, indices: torch.Tensor) -> torch.Tensor:
 
 
 def unpack_keys(keys: torch.Tensor):
+    """keys -> (values, indices); the kernel's 0 key ("no positive overlap") reads as (0.0, index 0)."""
     vals = (keys >> 32).to(torch.int32).view(torch.float32)
-    idx = _IDX_MASK - (keys & _IDX_MASK)
+    idx = torch.where(keys == 0, torch.zeros_like(keys), _IDX_MASK - (keys & _IDX_MASK))
     return vals, idx
 
 
@@ -69,11 +70,12 @@ def sharded_max_overlaps(anchors_local, gts, n_anchors, anchor_offset, backend='
     anchors_are   : 'bboxes1' -> IoU(anchor, gt) (config #5 call), 'bboxes2' -> IoU(gt, anchor)
                     (the assigner's orientation); the jitters are role-asymmetric, so this matters.
     Returns (anchor_max[n_anchors], anchor_arg -> gt index, gt_max[G], gt_arg -> global anchor index)."""
-    from .sphdet.iou.assign import sph_max_overlaps
-    if anchors_are == 'bboxes1':
-        rmax, rarg, cmax, carg = sph_max_overlaps(anchors_local, gts, backend, mode, row_base=anchor_offset)
-        a_keys, g_keys = pack_keys(rmax, rarg), pack_keys(cmax, carg)
-    else:
-        rmax, rarg, cmax, carg = sph_max_overlaps(gts, anchors_local, backend, mode, col_base=anchor_offset)
-        a_keys, g_keys = pack_keys(cmax, carg), pack_keys(rmax, rarg)
+    from . import _native
+    kind = {'sph2pob_standard_iou': 'sph2pob_standard', 'sph2pob_efficient_iou': 'sph2pob_efficient'}[backend]
+    # the kernel's packed keys go straight into the collectives: no unpack / repack round trip
+    with torch.no_grad():
+        if anchors_are == 'bboxes1':
+            a_keys, g_keys = _native.iou_pairwise_keys(kind, anchors_local, gts, mode, row_base=anchor_offset)
+        else:
+            g_keys, a_keys = _native.iou_pairwise_keys(kind, gts, anchors_local, mode, col_base=anchor_offset)
     return gather_assignment(a_keys, g_keys, n_anchors, group)
