@@ -121,6 +121,16 @@ int sphk_max_iou_assign(int kind, const float* gts, const int32_t* gt_offsets_ho
 int sphk_loss_fwd_bwd(const float* pred, const float* target, int64_t n, int D, float* iou, const float* grad_iou,
                       float* grad_pred, float* grad_target, void* stream);
 
+/* Reduced Sph2Pob IoU loss in one launch: Sph2PobIoULoss(mode='iou') with reduction 'mean' / 'sum'
+ * (sphdet/losses/sph2pob_iou_loss.py:25-58,138-140 + mmdet/models/losses/utils.py weight_reduce_loss):
+ *   partial [sphk_loss_reduce_partials(n)]  per-block sums of weight[i] * (1 - iou[i]); the loss is
+ *                                           scale * sum(partial)  (scale = loss_weight / n | / (avg_factor+eps) | 1)
+ *   weight  [n] or NULL (= 1)
+ *   grad_pred / grad_target [n, D] or NULL: d(loss)/d(box) = -weight[i] * scale * d(iou[i])/d(box) */
+int64_t sphk_loss_reduce_partials(int64_t n);
+int sphk_loss_reduce(const float* pred, const float* target, const float* weight, int64_t n, int D, float scale,
+                     float* partial, float* grad_pred, float* grad_target, void* stream);
+
 /* The same two stages exposed separately so that the GIoU/DIoU/CIoU epilogues
  * (sphdet/losses/sph2pob_iou_loss.py:142-194) can stay as autograd code on the OBBs:
  *   sphk_obb_fwd : (pred,target)[n,D] -> obb1, obb2 [n,5] = (x, y, w, h, angle rad) after

@@ -45,6 +45,9 @@ SIGNATURES = {
                                    _c_float_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "sphk_loss_fwd_bwd": (_int, [_c_float_p, _c_float_p, _i64, _int, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
                                  ctypes.c_void_p]),
+    "sphk_loss_reduce_partials": (_i64, [_i64]),
+    "sphk_loss_reduce": (_int, [_c_float_p, _c_float_p, _c_float_p, _i64, _int, ctypes.c_float, _c_float_p, _c_float_p, _c_float_p,
+                                ctypes.c_void_p]),
     "sphk_obb_fwd": (_int, [_int, _c_float_p, _c_float_p, _i64, _int, _int, _c_float_p, _c_float_p, ctypes.c_void_p]),
     "sphk_obb_bwd": (_int, [_int, _c_float_p, _c_float_p, _i64, _int, _int, _c_float_p, _c_float_p, _c_float_p,
                             _c_float_p, ctypes.c_void_p]),
@@ -277,6 +280,28 @@ def loss_fwd_bwd(pred, target, grad_iou=None, want_grad_pred=False, want_grad_ta
                                      _ptr(gt), _stream(pred)))
     launches += 1
     return iou, gp, gt
+
+
+def loss_reduce(pred, target, weight, scale, want_grad_pred=False, want_grad_target=False):
+    """partial sums of weight * (1 - iou) (loss = scale * partial.sum()) and the gradients of that loss."""
+    global launches
+    pred, target = _boxes(pred, "pred"), _boxes(target, "target")
+    if pred.shape != target.shape:
+        raise SphkError("pred/target shapes differ: %s vs %s" % (tuple(pred.shape), tuple(target.shape)))
+    n, dev = pred.size(0), pred.device
+    if weight is not None:
+        weight = weight.to(device=dev, dtype=torch.float32).contiguous()
+        assert weight.numel() == n
+    partial = torch.empty(max(1, (n + 255) // 256), dtype=torch.float32, device=dev)
+    if n == 0:
+        partial.zero_()
+    gp = torch.empty_like(pred) if want_grad_pred else None
+    gt = torch.empty_like(target) if want_grad_target else None
+    with _on_device(dev):
+        _check(lib.sphk_loss_reduce(_ptr(pred), _ptr(target), _ptr(weight), n, pred.size(1), float(scale), _ptr(partial), _ptr(gp),
+                                    _ptr(gt), _stream(pred)))
+    launches += 1
+    return partial, gp, gt
 
 
 def obb_fwd(kind: str, b1, b2, edge="arc"):

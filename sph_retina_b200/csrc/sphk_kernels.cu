@@ -590,6 +590,44 @@ k_loss_fwd_bwd(const float* __restrict__ pred, const float* __restrict__ target,
     if (grad_target) store_grad<D>(grad_target, i, g2, vec_ok);
 }
 
+// Reduced loss: sum_i w_i (1 - iou_i) as per-block partial sums (deterministic: fixed tree inside a block, the
+// caller adds the few hundred partials) and the gradients already scaled by -w_i * scale, in ONE launch.
+// Replaces the elementwise loss, weight multiply, reduction and the autograd tape of
+// sph2pob_iou_loss.py:104-140 + mmdet/models/losses/utils.py (weight_reduce_loss) for mode 'iou'.
+template <int D>
+__global__ void __launch_bounds__(kThreads)
+k_loss_reduce(const float* __restrict__ pred, const float* __restrict__ target, const float* __restrict__ weight, int64_t n,
+              float scale, float* __restrict__ partial, float* __restrict__ grad_pred, float* __restrict__ grad_target,
+              bool vec_ok) {
+    __shared__ float s_sum[kThreads / 32];
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    float li = 0.0f;
+    if (i < n) {
+        const RawBox x = load_box<D>(pred, i, vec_ok), y = load_box<D>(target, i, vec_ok);
+        const float w = weight ? __ldg(weight + i) : 1.0f;
+        float v;
+        if (grad_pred || grad_target) {
+            float g1[5], g2[5];
+            v = sph2pob_iou_pair_grad(x, y, D, KIND_SPH2POB_STANDARD, EDGE_ARC, -w * scale, g1, g2);
+            if (grad_pred) store_grad<D>(grad_pred, i, g1, vec_ok);
+            if (grad_target) store_grad<D>(grad_target, i, g2, vec_ok);
+        } else {
+            v = sph2pob_iou_pair(x, y, D, KIND_SPH2POB_STANDARD, MODE_IOU, EDGE_ARC);
+        }
+        li = w * (1.0f - v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) li += __shfl_xor_sync(0xFFFFFFFFu, li, o);
+    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = li;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.0f;
+#pragma unroll
+        for (int k = 0; k < kThreads / 32; ++k) t += s_sum[k];
+        partial[blockIdx.x] = t;
+    }
+}
+
 __device__ __forceinline__ void store_obb(float* __restrict__ o, int64_t i, float x, float y, float w, float h, float a) {
     float* q = o + i * 5;
     q[0] = x; q[1] = y; q[2] = w; q[3] = h; q[4] = a;
@@ -1036,6 +1074,22 @@ int sphk_loss_fwd_bwd(const float* pred, const float* target, int64_t n, int D, 
     if (D == 4) k_loss_fwd_bwd<4><<<blocks_for(n), kThreads, 0, s>>>(pred, target, n, iou, grad_iou, grad_pred, grad_target, v);
     else k_loss_fwd_bwd<5><<<blocks_for(n), kThreads, 0, s>>>(pred, target, n, iou, grad_iou, grad_pred, grad_target, v);
     SPHK_LAUNCH_CHECK("k_loss_fwd_bwd");
+    return SPHK_OK;
+}
+
+int64_t sphk_loss_reduce_partials(int64_t n) { return n <= 0 ? 0 : (n + kThreads - 1) / kThreads; }
+
+int sphk_loss_reduce(const float* pred, const float* target, const float* weight, int64_t n, int D, float scale,
+                     float* partial, float* grad_pred, float* grad_target, void* stream) {
+    if (n < 0 || (D != 4 && D != 5)) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_loss_reduce: n < 0 or D not in {4,5}");
+    if (n == 0) return SPHK_OK;
+    if (!pred || !target || !partial) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_loss_reduce: null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool v = aligned16(pred) && aligned16(target) && (!grad_pred || aligned16(grad_pred)) &&
+                   (!grad_target || aligned16(grad_target));
+    if (D == 4) k_loss_reduce<4><<<blocks_for(n), kThreads, 0, s>>>(pred, target, weight, n, scale, partial, grad_pred, grad_target, v);
+    else k_loss_reduce<5><<<blocks_for(n), kThreads, 0, s>>>(pred, target, weight, n, scale, partial, grad_pred, grad_target, v);
+    SPHK_LAUNCH_CHECK("k_loss_reduce");
     return SPHK_OK;
 }
 

@@ -50,6 +50,29 @@ class _Sph2PobIoU(torch.autograd.Function):
                 None if gt is None else (gt * g).to(ctx.in_dtypes[1]))
 
 
+class _Sph2PobReducedLoss(torch.autograd.Function):
+    """scale * sum_i w_i (1 - iou_i) and its gradients from ONE kernel launch (mode 'iou', reduction mean / sum)."""
+
+    @staticmethod
+    def forward(ctx, pred, target, weight, scale):
+        need_p, need_t = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        partial, gp, gt = _native.loss_reduce(pred.detach(), target.detach(), None if weight is None else weight.detach(),
+                                              scale, need_p, need_t)
+        ctx.save_for_backward(*[g for g in (gp, gt) if g is not None])
+        ctx.have = (need_p, need_t)
+        ctx.in_dtypes = (pred.dtype, target.dtype)
+        return (partial.sum() * scale).to(pred.dtype)
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        saved = list(ctx.saved_tensors)
+        gp = saved.pop(0) if ctx.have[0] else None
+        gt = saved.pop(0) if ctx.have[1] else None
+        g = grad_loss.float()
+        return (None if gp is None else (gp * g).to(ctx.in_dtypes[0]),
+                None if gt is None else (gt * g).to(ctx.in_dtypes[1]), None, None)
+
+
 class _Sph2PobObbs(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pred, target, kind):
@@ -192,6 +215,17 @@ class _SphLossBase(nn.Module):
         if weight is not None and weight.dim() > 1:
             assert weight.shape == (pred.size(0), 5)    # :46 weight.shape == obb pred.shape
             weight = weight.mean(-1)
+        if (self.mode == 'iou' and self._transform == 'sph2pob_standard' and reduction in ('mean', 'sum') and pred.is_cuda
+                and not isinstance(avg_factor, torch.Tensor)):     # a tensor avg_factor would need a host sync for the scale
+            # fused: elementwise loss, weights, reduction and both gradients in one kernel launch
+            if avg_factor is None:
+                scale = self.loss_weight / max(pred.size(0), 1) if reduction == 'mean' else self.loss_weight
+            elif reduction == 'mean':
+                scale = self.loss_weight / (avg_factor + torch.finfo(torch.float32).eps)
+            else:
+                raise ValueError('avg_factor can not be used with reduction="sum"')
+            if pred.size(0) > 0:
+                return _Sph2PobReducedLoss.apply(pred, target, weight, float(scale))
         loss = _elementwise_loss(pred, target, self.mode, self.eps, self._transform)
         return self.loss_weight * _weight_reduce_loss(loss, weight, reduction, avg_factor)
 

@@ -135,6 +135,26 @@ def test_aligned_odd_sizes_views_and_streams(api):
     assert api.iou.sph2pob_efficient_iou(b1.double(), b2.double(), is_aligned=True).dtype == torch.float64
 
 
+def test_non_finite_and_out_of_range_inputs_do_not_poison_neighbours(api):
+    """NaN / inf / absurd coordinates in one box must neither hang nor disturb other pairs (they take the
+    reference-order path; the result for the bad pair itself is whatever fp32 gives, 0 for NaN areas)."""
+    b1 = O.generate_boxes(2000, alpha_range=(5, 100), beta_range=(5, 100), box="rbfov", seed=21).to(DEV)
+    b2 = O.generate_boxes(2000, alpha_range=(5, 100), beta_range=(5, 100), box="rbfov", seed=22).to(DEV)
+    good = api.iou.sph2pob_efficient_iou(b1, b2, is_aligned=True)
+    bad1 = b1.clone()
+    bad1[7] = float("nan"); bad1[8, 0] = float("inf"); bad1[9] = torch.tensor([1e9, -1e9, 1e9, 1e9, 1e9], device=DEV)
+    bad1[10, 2:4] = 0.0; bad1[11, 4] = 720.0; bad1[12, 2] = -5.0
+    got = api.iou.sph2pob_efficient_iou(bad1, b2, is_aligned=True)
+    keep = torch.ones(2000, dtype=torch.bool, device=DEV); keep[7:13] = False
+    assert torch.equal(got[keep], good[keep])
+    mat = api.iou.sph2pob_efficient_iou(bad1[:64], b2[:600])
+    ref = api.iou.sph2pob_efficient_iou(b1[:64], b2[:600])
+    rows_ok = torch.ones(64, dtype=torch.bool, device=DEV); rows_ok[7:13] = False
+    assert torch.equal(mat[rows_ok], ref[rows_ok])
+    fin = torch.isfinite(mat[~rows_ok])
+    assert bool(((mat[~rows_ok][fin] >= 0) & (mat[~rows_ok][fin] <= 1)).all())
+
+
 # ---- pairwise ----------------------------------------------------------------------------------
 def test_pairwise_golden_both_orientations(api):
     g = load_golden("pairwise")
