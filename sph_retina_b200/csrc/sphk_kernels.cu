@@ -121,12 +121,14 @@ __global__ void __launch_bounds__(kThreads) k_iou_aligned(const float* __restric
 // per-warp ring of PairS1 records in shared memory; stage 2 (arc, internal angles, gamma, jitter_2 checks)
 // and the clipper then run 32 survivors at a time with full warps.  Pairs on which a reference quirk may be
 // active are queued for the out-of-line reference-order path.
-constexpr int kJobRing = 64, kS1Floats = 15;
+// ring capacities: survivors <= 31 pending + 32 pushed per iteration; slow pairs <= 31 pending + 32 from stage 1
+// + 32 from the stage-2 batch of the same iteration
+constexpr int kJobRing = 64, kSlowRing = 128, kS1Floats = 15;
 
 struct AlignedTile {
     float s1[kThreads / 32][kS1Floats][kJobRing];
     unsigned short jidx[kThreads / 32][kJobRing];
-    unsigned short sidx[kThreads / 32][kJobRing];
+    unsigned short sidx[kThreads / 32][kSlowRing];
 };
 
 template <int D>
@@ -165,7 +167,7 @@ k_iou_aligned2(const float* __restrict__ b1, const float* __restrict__ b2, int64
         }
         tj += __popc(mj);
         unsigned ms = __ballot_sync(0xFFFFFFFFu, st == JOB_SLOW);
-        if (st == JOB_SLOW) T.sidx[warp][(ts + __popc(ms & lt)) & (kJobRing - 1)] = (unsigned short)off;
+        if (st == JOB_SLOW) T.sidx[warp][(ts + __popc(ms & lt)) & (kSlowRing - 1)] = (unsigned short)off;
         ts += __popc(ms);
         if (tj - hj >= need) {
             const int cnt = min(tj - hj, 32);
@@ -186,14 +188,14 @@ k_iou_aligned2(const float* __restrict__ b1, const float* __restrict__ b2, int64
                 if (!slow) out[base + o2] = clip_job_iou(job, mode);
             }
             ms = __ballot_sync(0xFFFFFFFFu, slow);
-            if (slow) T.sidx[warp][(ts + __popc(ms & lt)) & (kJobRing - 1)] = (unsigned short)o2;
+            if (slow) T.sidx[warp][(ts + __popc(ms & lt)) & (kSlowRing - 1)] = (unsigned short)o2;
             ts += __popc(ms);
             hj += cnt;
         }
         while (ts - hs >= need) {
             const int cnt = min(ts - hs, 32);
             __syncwarp();
-            const int o2 = T.sidx[warp][(hs + lane) & (kJobRing - 1)];
+            const int o2 = T.sidx[warp][(hs + lane) & (kSlowRing - 1)];
             __syncwarp();
             if (lane < cnt) out[base + o2] = slow_pair_iou(b1, base + o2, b2, base + o2, D, kind, mode, edge, dense);
             hs += cnt;

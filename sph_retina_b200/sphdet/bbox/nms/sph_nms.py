@@ -11,11 +11,20 @@ import torch
 from .... import _native
 
 
+def _desc_score_key(scores):
+    """int64 in [0, 2**32): ascending key order == descending float32 score (IEEE bit trick, no sort yet)."""
+    b = scores.float().contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    mono = torch.where(b >= 0x80000000, 0xFFFFFFFF - b, b + 0x80000000)     # ascending with the float value
+    return 0xFFFFFFFF - mono
+
+
 def _segments(scores, seg_ids):
-    """order (score-descending inside a segment, segments by ascending id), offsets, longest segment."""
-    order = torch.argsort(scores, descending=True, stable=True)
-    order = order[torch.argsort(seg_ids[order], stable=True)]
-    _, counts = torch.unique_consecutive(seg_ids[order], return_counts=True)
+    """One sort on the composite key (segment ascending, score descending): order, offsets, longest segment.
+    (The reference sorts per class with torch.argsort(descending=True), sph_nms.py:65; equal scores are in
+    unspecified order there as well.)"""
+    key = (seg_ids.long() << 32) | _desc_score_key(scores)
+    key, order = torch.sort(key)
+    _, counts = torch.unique_consecutive(key >> 32, return_counts=True)
     offsets = torch.zeros(counts.numel() + 1, dtype=torch.int32, device=scores.device)
     offsets[1:] = counts.cumsum(0)
     return order, offsets, int(counts.max().item())
@@ -25,8 +34,6 @@ def _keep_indices(boxes, scores, seg_ids, iou_threshold):
     """Indices (into boxes) that survive the per-segment greedy NMS, unordered."""
     order, offsets, longest = _segments(scores, seg_ids)
     flags = _native.nms_batched(boxes, order, offsets, longest, iou_threshold)
-    if bool((flags == 0xFF).any()):
-        raise _native.SphkError("sphk_nms_batched refused a segment (max_seg_len too small)")
     return order[flags.bool()]
 
 
@@ -53,13 +60,12 @@ def sph_batched_nms(boxes, scores, idxs, nms_cfg, iou_calculator='sph2pob_effici
 
 
 def sph_batched_nms_images(boxes, scores, labels, image_ids, iou_threshold=0.5):
-    """Test-time batch: one launch over every (image, class) segment of a whole batch.
-    Returns the kept indices (into boxes), grouped by image and score-descending inside an image."""
-    num_labels = int(labels.max().item()) + 1 if labels.numel() else 1
-    seg = image_ids.long() * num_labels + labels.long()
+    """Test-time batch: one launch over every (image, class) segment of a whole batch (labels < 2**20,
+    image ids < 2**11).  Returns the kept indices (into boxes), grouped by image and score-descending inside an image."""
+    # segment id = (image, label); 20 bits for the label, 11 for the image keep it below 2**31 (no host sync)
+    seg = (image_ids.long() << 20) | labels.long()
     keep = _keep_indices(boxes, scores, seg, iou_threshold)
-    keep = keep[torch.argsort(scores[keep], descending=True, stable=True)]
-    return keep[torch.argsort(image_ids[keep], stable=True)]
+    return keep[torch.argsort((image_ids[keep].long() << 32) | _desc_score_key(scores[keep]))]
 
 
 class SphNMS:

@@ -135,6 +135,20 @@ def test_aligned_odd_sizes_views_and_streams(api):
     assert api.iou.sph2pob_efficient_iou(b1.double(), b2.double(), is_aligned=True).dtype == torch.float64
 
 
+def test_aligned_all_pairs_on_the_reference_order_path(api, c_oracle):
+    """Loss-style input: every pair is (near-)coincident, so every pair leaves the fast path -- the slow-pair ring
+    of the aligned kernel is under maximum pressure (stage-1 and stage-2 rejects in the same iteration)."""
+    t = O.generate_boxes(100_003, alpha_range=(5, 100), beta_range=(5, 100), box="rbfov", seed=31)
+    p = t.clone()
+    p[::2] += torch.randn(50_002, 5) * 1e-3          # arc < 2e-3 rad: rejected by stage 2
+    p[1::4] = t[1::4]                                # identical: similarity mask, rejected by stage 1
+    for kind, fn in ((0, api.iou.sph2pob_efficient_iou), (1, api.iou.sph2pob_standard_iou)):
+        got = fn(p.to(DEV), t.to(DEV), is_aligned=True).cpu().numpy()
+        want = c_oracle_aligned(c_oracle, kind, p.numpy(), t.numpy())
+        err = np.abs(got - want)
+        assert np.median(err) < 1e-6 and err.max() < 1e-5, (np.median(err), err.max(), int(np.argmax(err)))
+
+
 def test_non_finite_and_out_of_range_inputs_do_not_poison_neighbours(api):
     """NaN / inf / absurd coordinates in one box must neither hang nor disturb other pairs (they take the
     reference-order path; the result for the bad pair itself is whatever fp32 gives, 0 for NaN areas)."""
