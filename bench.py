@@ -398,8 +398,10 @@ def run_ours(args):
                 traffic = None
         roofline = {"bound": "hbm", "achieved": hbm_achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": hbm_achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peaks_src,
-                    "kernel": "k_iou_pairwise", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": bytes_per_launch,
-                    "note": "HBM is NOT what bounds this kernel (4 B written per pair): see roofline_fp32"}
+                    "kernel": "k_iou_pairwise2", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": bytes_per_launch,
+                    "note": "kernel_ms = timed step / launches per step (CUDA events; includes the 6 us k_box_pre and launch gaps; "
+                            "ncu: 36 us for the kernel alone, profiles/).  HBM is NOT what bounds this kernel (4 B written per "
+                            "pair): see roofline_fp32"}
         result["roofline"] = roofline
         peak_tf = fp32_peak(torch, native, dev)
         tf = pairs_per_launch * FLOP_PER_PAIR / (kernel_ms * 1e-3) / 1e12
