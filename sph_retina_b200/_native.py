@@ -65,10 +65,16 @@ class SphkError(RuntimeError):
 
 
 def _load():
-    if not os.path.isfile(LIB_PATH):
-        raise ImportError(
-            "sph_retina_b200: %s is missing. Build it with `python -m sph_retina_b200.build` "
-            "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+    # (re)build in-tree when the library is missing or older than its sources; nothing else can serve this path
+    try:
+        from . import build as _build
+        if _build.is_stale():
+            _build.build()
+    except Exception as e:
+        if not os.path.isfile(LIB_PATH):
+            raise ImportError(
+                "sph_retina_b200: %s is missing and could not be built (%s). Build it with "
+                "`python -m sph_retina_b200.build` (nvcc, sm_100a). There is no CPU fallback." % (LIB_PATH, e))
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)

@@ -44,12 +44,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
+    # build next to the target and rename atomically: several ranks may find the library stale at the same time
+    tmp = "%s.tmp.%d" % (LIB_PATH, os.getpid())
     cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else [])
-    cmd += ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd += ["-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
+        if os.path.exists(tmp):
+            os.unlink(tmp)
         raise RuntimeError("nvcc failed building libsphk.so")
+    os.replace(tmp, LIB_PATH)
     if verbose:
         sys.stderr.write(res.stderr)
     return LIB_PATH
