@@ -1,14 +1,20 @@
 // sphk_kernels.cu -- sm_100a kernels and the C ABI (include/sphk.h) of the spherical-box IoU path.
 //
 // Kernels (all fp32 CUDA-core work; no tensor cores -- nothing here is a contraction):
-//   k_iou_aligned      one thread per aligned pair                      (config #1, Sph/FoV siblings)
-//   k_iou_pairwise     lanes <-> columns (coalesced matrix rows), row tile broadcast from shared
-//                      memory, fused row/column max+argmax              (configs #2, #5)
-//   k_loss_fwd_bwd     one thread per pair, recompute-in-backward        (config #3)
-//   k_obb_fwd/bwd, k_riou_fwd_bwd   the two loss stages exposed separately (GIoU/DIoU/CIoU epilogues)
-//   k_nms              one CTA per (image, class) segment, 32-pivot blocks of warp-ballot
-//                      suppression words + in-warp serial scan            (config #4)
-// The per-pair arithmetic lives in sphk_math.cuh / sphk_grad.cuh.
+//   k_iou_aligned2     aligned Sph2Pob IoU: stage 1 per pair, stage 2 + clipper warp-compacted        (config #1)
+//   k_iou_aligned      aligned Sph-IoU / FoV-IoU, one thread per pair                                 (siblings)
+//   k_box_pre          per-box records (BoxRec + BoxCull) of both operands of an N x M call
+//   k_iou_pairwise2    N x M Sph2Pob IoU: lane <-> column tiles, 7-FMA prefilter, ballot compaction into
+//                      per-warp rings, fused row/column max+argmax keys, tie pass, image batches  (configs #2, #5)
+//   k_iou_pairwise     N x M Sph-IoU / FoV-IoU (plain tile kernel)
+//   k_iou_project      rbb_angle = 'project' ablation variant, double precision
+//   k_assign_targets, k_assign_epilogue   MaxIoUAssigner thresholds / low-quality matching on the packed keys
+//   k_loss_fwd_bwd, k_loss_reduce         IoU + both gradients in one launch (elementwise / reduced)   (config #3)
+//   k_obb_fwd/bwd, k_riou_fwd_bwd         the two loss stages exposed separately (GIoU/DIoU/CIoU epilogues)
+//   k_nms              one CTA per (image, class) segment, 32-pivot rounds of warp-ballot suppression
+//                      words + in-warp greedy scan                                                    (config #4)
+// The per-pair arithmetic lives in sphk_math.cuh (reference-order path, clipper), sphk_fast.cuh (records,
+// prefilter, fast path) and sphk_grad.cuh (analytic backward).
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
