@@ -153,10 +153,11 @@ int sphk_riou_fwd_bwd(const float* obb1, const float* obb2, int64_t n, float* io
  *   seg_offsets [S+1]  int32, segment s covers order[seg_offsets[s] .. seg_offsets[s+1])
  *   max_seg_len        an upper bound of the segment lengths (sizes the per-CTA shared memory;
  *                      a longer segment is refused: its keep bytes are set to 0xFF)
+ *   typical_seg_len    0, or the usual segment length when max_seg_len is only a loose bound (sizes the CTA)
  *   keep        [M]    uint8, keep[q] = 1 iff the box order[q] survives (same positions as `order`)
  * A box is suppressed iff IoU(pivot as bboxes1, box as bboxes2) > iou_threshold (:70-73). */
 int sphk_nms_batched(const float* boxes, const int32_t* order, const int32_t* seg_offsets, int32_t S,
-                     int32_t max_seg_len, int D, float iou_threshold, uint8_t* keep, void* stream);
+                     int32_t max_seg_len, int32_t typical_seg_len, int D, float iou_threshold, uint8_t* keep, void* stream);
 
 /* Measurement helpers (bench.py; no counterpart in the reference).
  * sphk_probe_fp32: FMA-chain microbenchmark that yields the FP32 CUDA-core peak the Sph2Pob kernels

@@ -53,7 +53,7 @@ SIGNATURES = {
                             _c_float_p, ctypes.c_void_p]),
     "sphk_riou_fwd_bwd": (_int, [_c_float_p, _c_float_p, _i64, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
                                  ctypes.c_void_p]),
-    "sphk_nms_batched": (_int, [_c_float_p, ctypes.c_void_p, ctypes.c_void_p, _i32, _i32, _int, ctypes.c_float,
+    "sphk_nms_batched": (_int, [_c_float_p, ctypes.c_void_p, ctypes.c_void_p, _i32, _i32, _i32, _int, ctypes.c_float,
                                 ctypes.c_void_p, ctypes.c_void_p]),
     "sphk_probe_fp32": (_int, [_i32, _i32, _c_float_p, ctypes.c_void_p]),
     "sphk_set_dense": (_int, [_int]),
@@ -356,7 +356,7 @@ def riou_fwd_bwd(o1, o2, grad_iou=None, want1=False, want2=False):
     return iou, g1, g2
 
 
-def nms_batched(boxes, order, seg_offsets, max_seg_len: int, iou_threshold: float) -> torch.Tensor:
+def nms_batched(boxes, order, seg_offsets, max_seg_len: int, iou_threshold: float, typical_seg_len: int = 0) -> torch.Tensor:
     """keep flags (uint8, aligned with `order`) of the greedy per-segment spherical NMS."""
     global launches
     boxes = _boxes(boxes, "boxes")
@@ -368,7 +368,7 @@ def nms_batched(boxes, order, seg_offsets, max_seg_len: int, iou_threshold: floa
     if S <= 0 or order.numel() == 0:
         return keep
     with _on_device(dev):
-        _check(lib.sphk_nms_batched(_ptr(boxes), _ptr(order), _ptr(seg_offsets), S, int(max_seg_len), boxes.size(1),
+        _check(lib.sphk_nms_batched(_ptr(boxes), _ptr(order), _ptr(seg_offsets), S, int(max_seg_len), int(typical_seg_len), boxes.size(1),
                                     float(iou_threshold), _ptr(keep), _stream(boxes)))
     launches += 1
     return keep

@@ -1144,7 +1144,7 @@ int sphk_riou_fwd_bwd(const float* obb1, const float* obb2, int64_t n, float* io
 }
 
 int sphk_nms_batched(const float* boxes, const int32_t* order, const int32_t* seg_offsets, int32_t S, int32_t max_seg_len,
-                     int D, float iou_threshold, uint8_t* keep, void* stream) {
+                     int32_t typical_seg_len, int D, float iou_threshold, uint8_t* keep, void* stream) {
     if (S < 0 || max_seg_len < 0 || (D != 4 && D != 5)) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_nms_batched: bad S, max_seg_len or D");
     if (S == 0 || max_seg_len == 0) return SPHK_OK;
     if (!boxes || !order || !seg_offsets || !keep) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_nms_batched: null pointer");
@@ -1153,9 +1153,10 @@ int sphk_nms_batched(const float* boxes, const int32_t* order, const int32_t* se
     if (smem > 200u * 1024u) return fail(SPHK_ERR_UNSUPPORTED, "sphk_nms_batched: segment longer than 49,000 boxes");
     cudaStream_t s = (cudaStream_t)stream;
     const bool v = aligned16(boxes);
-    // one CTA per segment; its width follows the longest segment: a 32-pivot round has up to 32 * k/32 (pivot, word)
-    // units, one warp each
-    const int nt = max_seg_len <= 64 ? 128 : (max_seg_len <= 256 ? 256 : (max_seg_len <= 512 ? 512 : 1024));
+    // one CTA per segment; its width follows the typical segment length (the longest one when no hint is given):
+    // a 32-pivot round has up to 32 * k/32 (pivot, word) units, one warp each
+    const int tl = (typical_seg_len > 0 && typical_seg_len < max_seg_len) ? typical_seg_len : max_seg_len;
+    const int nt = tl <= 64 ? 128 : (tl <= 256 ? 256 : (tl <= 512 ? 512 : 1024));
     cudaError_t e;
     if (D == 4) {
         e = cudaFuncSetAttribute(k_nms<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -59,12 +59,26 @@ def sph_batched_nms(boxes, scores, idxs, nms_cfg, iou_calculator='sph2pob_effici
     return dets, keep
 
 
-def sph_batched_nms_images(boxes, scores, labels, image_ids, iou_threshold=0.5):
+def sph_batched_nms_images(boxes, scores, labels, image_ids, iou_threshold=0.5, num_images=None, num_classes=None,
+                           max_per_segment=None):
     """Test-time batch: one launch over every (image, class) segment of a whole batch (labels < 2**20,
-    image ids < 2**11).  Returns the kept indices (into boxes), grouped by image and score-descending inside an image."""
-    # segment id = (image, label); 20 bits for the label, 11 for the image keep it below 2**31 (no host sync)
-    seg = (image_ids.long() << 20) | labels.long()
-    keep = _keep_indices(boxes, scores, seg, iou_threshold)
+    image ids < 2**11).  Returns the kept indices (into boxes), grouped by image and score-descending inside an image.
+
+    With the three hints (batch size, number of classes, an upper bound of the boxes per (image, class) segment, e.g.
+    nms_pre) the segment table is built densely on the device and the only host synchronisation left is the final
+    compaction of the kept indices."""
+    if num_images is None or num_classes is None or max_per_segment is None:
+        seg = (image_ids.long() << 20) | labels.long()
+        keep = _keep_indices(boxes, scores, seg, iou_threshold)
+    else:
+        seg = image_ids.long() * int(num_classes) + labels.long()
+        key, order = torch.sort((seg << 32) | _desc_score_key(scores))
+        counts = torch.bincount(seg, minlength=int(num_images) * int(num_classes))
+        offsets = torch.zeros(counts.numel() + 1, dtype=torch.int32, device=scores.device)
+        offsets[1:] = counts.cumsum(0)
+        typical = max(1, (2 * boxes.size(0)) // max(1, counts.numel()))     # twice the mean segment length
+        flags = _native.nms_batched(boxes, order, offsets, int(max_per_segment), iou_threshold, typical)
+        keep = order[flags == 1]          # a refused (too long) segment is flagged 0xFF and drops out: size the hint right
     return keep[torch.argsort((image_ids[keep].long() << 32) | _desc_score_key(scores[keep]))]
 
 

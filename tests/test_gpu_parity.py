@@ -473,6 +473,8 @@ def test_nms_batch_of_images_equals_per_image(api):
     labels = torch.randint(0, 7, (B * n,), device=DEV)
     image_ids = torch.arange(B, device=DEV).repeat_interleave(n)
     keep = api.nms.sph_batched_nms_images(boxes, scores, labels, image_ids, 0.5)
+    hinted = api.nms.sph_batched_nms_images(boxes, scores, labels, image_ids, 0.5, num_images=B, num_classes=7, max_per_segment=n)
+    assert torch.equal(keep, hinted)
     for b in range(B):
         sel = (image_ids == b).nonzero().view(-1)
         _, k1 = api.nms.SphNMS()(boxes[sel], scores[sel], labels[sel], dict(iou_threshold=0.5))
