@@ -445,24 +445,26 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
     const float pbias = col_ok ? (dense ? -1e30f : pc1.y) : 1e30f;
     int hf = 0, tf = 0, hs = 0, ts = 0;          // ring head / tail counters (fast, slow)
     const unsigned lt = (1u << lane) - 1u;
-    // one extra iteration (r == nr) drains the rings, so that each batch body exists once in the code
+    // Alternate between a tight scan phase (prefilter rows until 32 live pairs are queued or the rows are used up)
+    // and ONE batch site (so that the expensive code exists once); the rings are flushed when the rows are done.
+    int r = 0;
 #pragma unroll 1
-    for (int r = 0; r <= nr; ++r) {
-        const bool last = r == nr;
-        bool live = false;
-        if (!last) {
+    for (;;) {
+#pragma unroll 1
+        while (r < nr && tf - hf < 32) {
             const float4 g0 = T.rcull[r][0];
             const float2 g1 = *reinterpret_cast<const float2*>(&T.rcull[r][1]);
             // cos(arc) < cos(r_g + r_p) - margin  <=>  the planar boxes cannot touch  (sphk_fast.cuh: pre_disjoint)
             const float dot = fmaf(g0.x, pc0.x, fmaf(g0.y, pc0.y, g0.z * pc0.z));
             const float thr = fmaf(g0.w, pc0.w, fmaf(-g1.x, pc1.x, g1.y + pbias));
-            live = !(dot < thr);
+            const bool live = !(dot < thr);
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, live);
+            if (live) T.ring[warp][0][(tf + __popc(m & lt)) & (kRing - 1)] = (unsigned short)((r << 5) | lane);
+            tf += __popc(m);
+            ++r;
         }
-        const unsigned m = __ballot_sync(0xFFFFFFFFu, live);
-        if (live) T.ring[warp][0][(tf + __popc(m & lt)) & (kRing - 1)] = (unsigned short)((r << 5) | lane);
-        tf += __popc(m);
-        const int need = last ? 1 : 32;           // the last iteration flushes whatever is pending
-        if (tf - hf >= need) {
+        const bool rows_done = r >= nr;
+        if (tf > hf) {                             // here: >= 32 queued, or the rows are done
             const int cnt = min(tf - hf, 32);
             __syncwarp();
             const int e = T.ring[warp][0][(hf + lane) & (kRing - 1)];
@@ -479,6 +481,8 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
             ts += __popc(ms);
             hf += cnt;
         }
+        const bool drained = rows_done && tf == hf;
+        const int need = drained ? 1 : 32;          // no more fast work can come: flush the reference-order ring
         while (ts - hs >= need) {
             const int cnt = min(ts - hs, 32);
             __syncwarp();
@@ -490,6 +494,7 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
             }
             hs += cnt;
         }
+        if (drained) break;
     }
     // ---- merge the tile's max/argmax into the global keys
     if (o.want_row || o.want_col || o.tie) {

@@ -13,16 +13,16 @@ from .... import _native
 
 def _desc_score_key(scores):
     """int64 in [0, 2**32): ascending key order == descending float32 score (IEEE bit trick, no sort yet)."""
-    b = scores.float().contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
-    mono = torch.where(b >= 0x80000000, 0xFFFFFFFF - b, b + 0x80000000)     # ascending with the float value
-    return 0xFFFFFFFF - mono
+    b = scores.float().contiguous().view(torch.int32)
+    m = b ^ ((b >> 31) & 0x7FFFFFFF)            # signed-int order == float order
+    return (~m).to(torch.int64) + 0x80000000    # reversed, shifted into [0, 2**32)
 
 
-def _segments(scores, seg_ids):
+def _segments(scores, seg_ids, desc=None):
     """One sort on the composite key (segment ascending, score descending): order, offsets, longest segment.
     (The reference sorts per class with torch.argsort(descending=True), sph_nms.py:65; equal scores are in
     unspecified order there as well.)"""
-    key = (seg_ids.long() << 32) | _desc_score_key(scores)
+    key = (seg_ids.long() << 32) | (_desc_score_key(scores) if desc is None else desc)
     key, order = torch.sort(key)
     _, counts = torch.unique_consecutive(key >> 32, return_counts=True)
     offsets = torch.zeros(counts.numel() + 1, dtype=torch.int32, device=scores.device)
@@ -30,9 +30,9 @@ def _segments(scores, seg_ids):
     return order, offsets, int(counts.max().item())
 
 
-def _keep_indices(boxes, scores, seg_ids, iou_threshold):
+def _keep_indices(boxes, scores, seg_ids, iou_threshold, desc=None):
     """Indices (into boxes) that survive the per-segment greedy NMS, unordered."""
-    order, offsets, longest = _segments(scores, seg_ids)
+    order, offsets, longest = _segments(scores, seg_ids, desc)
     flags = _native.nms_batched(boxes, order, offsets, longest, iou_threshold)
     return order[flags.bool()]
 
@@ -67,19 +67,20 @@ def sph_batched_nms_images(boxes, scores, labels, image_ids, iou_threshold=0.5, 
     With the three hints (batch size, number of classes, an upper bound of the boxes per (image, class) segment, e.g.
     nms_pre) the segment table is built densely on the device and the only host synchronisation left is the final
     compaction of the kept indices."""
+    desc = _desc_score_key(scores)
     if num_images is None or num_classes is None or max_per_segment is None:
         seg = (image_ids.long() << 20) | labels.long()
-        keep = _keep_indices(boxes, scores, seg, iou_threshold)
+        keep = _keep_indices(boxes, scores, seg, iou_threshold, desc)
     else:
         seg = image_ids.long() * int(num_classes) + labels.long()
-        key, order = torch.sort((seg << 32) | _desc_score_key(scores))
+        key, order = torch.sort((seg << 32) | desc)
         counts = torch.bincount(seg, minlength=int(num_images) * int(num_classes))
         offsets = torch.zeros(counts.numel() + 1, dtype=torch.int32, device=scores.device)
         offsets[1:] = counts.cumsum(0)
         typical = max(1, (2 * boxes.size(0)) // max(1, counts.numel()))     # twice the mean segment length
         flags = _native.nms_batched(boxes, order, offsets, int(max_per_segment), iou_threshold, typical)
         keep = order[flags == 1]          # a refused (too long) segment is flagged 0xFF and drops out: size the hint right
-    return keep[torch.argsort((image_ids[keep].long() << 32) | _desc_score_key(scores[keep]))]
+    return keep[torch.argsort((image_ids[keep].long() << 32) | desc[keep])]
 
 
 class SphNMS:
