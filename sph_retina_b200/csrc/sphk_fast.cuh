@@ -86,9 +86,13 @@ SPHK_HD bool pre_disjoint(const BoxCull& g, const BoxCull& p) {
     return dot < thr;
 }
 
+// 1/sqrt(x) to ~1 ulp (MUFU.RSQ): used to normalise (cos, sin) pairs and for the conservative cull radius, where
+// a 2e-7 relative error is immaterial (rsqrtf() without fast-math adds a dozen instructions of special-case handling)
 SPHK_HD float rsqrt_f(float x) {
 #if defined(__CUDA_ARCH__)
-    return rsqrtf(x);
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 #else
     return 1.0f / sqrtf(x);
 #endif
