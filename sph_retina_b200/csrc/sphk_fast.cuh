@@ -16,6 +16,8 @@
 // clamps, gamma beyond +-179 deg) pair_fast() declines and the caller runs the reference-order code of
 // sphk_math.cuh (sph2pob_iou_pair).  Both paths share riou_core().
 #pragma once
+#include <string.h>
+
 #include "sphk_math.cuh"
 
 namespace sphk {
@@ -217,6 +219,48 @@ SPHK_HD int pair_stage1(const RawBox& x, const RawBox& y, int D, int edge, bool 
         if (4.0f * s->hav * k * k > R * R) return JOB_DEAD;
     }
     return JOB_READY;
+}
+
+// ---- stage 0 of the aligned kernel: "cannot touch" from approximate trigonometry ----------------------
+// The same dead test as pair_stage1() (series lower bound of the arc against r_g + r_p), but on a haversine built
+// from four MUFU sines (sin.approx: absolute error < 1e-6 on [-pi, pi]) and on the RAW sizes, at a fraction of the
+// instructions: it runs for every pair, everything exact runs only for the survivors.  Conservative by construction:
+//   * hav is lowered by kHavSlack = 2e-5 >= 3 x (6 sine errors);
+//   * raw alpha / beta (deg -> rad) can only exceed the clamped, edge-converted planar sizes for 'arc' and 'chord'
+//     (2 sin(a/2) <= a; jitter_1's lower clamp adds <= 4.3e-6 rad, inside the 8e-4 margin); 'tangent' is not culled;
+//   * centres outside [0, 360] x [0, 180] (which jitter_1 would clamp), -0.0 and NaNs are never culled: one unsigned
+//     compare on the bit patterns (non-negative floats order like unsigned integers);
+//   * NaN / inf sizes make the comparison false.
+// true => pair_stage1(cull) would return JOB_DEAD as well, and the reference's IoU is exactly 0.
+constexpr float kHavSlack = 2e-5f;
+SPHK_HD float sin_approx(float x) {
+#if defined(__CUDA_ARCH__)
+    return __sinf(x);
+#else
+    return sinf(x);
+#endif
+}
+SPHK_HD uint32_t f32_bits(float x) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(x);
+#else
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    return u;
+#endif
+}
+SPHK_HD bool pair_far_apart(const RawBox& x, const RawBox& y, int edge) {
+    const uint32_t ta = f32_bits(x.t), tb = f32_bits(y.t), pa = f32_bits(x.p + x.p), pb = f32_bits(y.p + y.p);
+    const uint32_t m1 = ta > tb ? ta : tb, m2 = pa > pb ? pa : pb;
+    if ((m1 > m2 ? m1 : m2) > 0x43B40000u || edge == EDGE_TANGENT) return false;       // 360.0f
+    const float kh = (float)(SPHK_PI_D / 360.0);
+    const float sdt = sin_approx((y.t - x.t) * kh), sdp = sin_approx((y.p - x.p) * kh);
+    const float s1 = sin_approx(x.p * kDeg2Rad), s2 = sin_approx(y.p * kDeg2Rad);
+    const float hav = fmaf(s1 * s2, sdt * sdt, sdp * sdp) - kHavSlack;
+    const float q1 = fmaf(x.a, x.a, x.b * x.b), q2 = fmaf(y.a, y.a, y.b * y.b);
+    const float R = fmaf((q1 * rsqrt_f(q1) + q2 * rsqrt_f(q2)) * (0.5f * kDeg2Rad), 1.0002f, 8e-4f);
+    const float k = fmaf(hav, fmaf(hav, 0.075f, 0.16666667f), 1.0f);
+    return 4.0f * hav * k * k > R * R;
 }
 
 SPHK_HD int pair_stage2(const PairS1& s, int D, int kind, ClipJob* job) {

@@ -31,7 +31,8 @@ namespace {
 
 thread_local char g_err[256] = "";
 int g_dense = 0;   // sphk_set_dense: 1 = no disjoint-pair early-outs (measurement only)
-const int g_force_iters = [] { const char* e = getenv("SPHK_ALIGNED_ITERS"); return e ? atoi(e) : 0; }();
+const int g_force_ctas = [] { const char* e = getenv("SPHK_ALIGNED_CTAS"); return e ? atoi(e) : 0; }();   // tuning hook
+const int g_force_minb = [] { const char* e = getenv("SPHK_ALIGNED_MINB"); return e ? atoi(e) : 0; }();
 const int g_force_tr = [] { const char* e = getenv("SPHK_TR"); return e ? atoi(e) : 0; }();
 
 int fail(int code, const char* what) {
@@ -121,91 +122,156 @@ __global__ void __launch_bounds__(kThreads) k_iou_aligned(const float* __restric
     out[i] = v;
 }
 
-// ---- aligned, Sph2Pob kinds: two stages, the second one warp-compacted ------------------------------
-// Stage 1 (pair_stage1) runs for every pair: jitter_1, three degree-domain sincos, hav, conservative dead
-// test -- about half of random pairs end here with an exact 0.  Survivors are ballot-compacted into a
-// per-warp ring of PairS1 records in shared memory; stage 2 (arc, internal angles, gamma, jitter_2 checks)
-// and the clipper then run 32 survivors at a time with full warps.  Pairs on which a reference quirk may be
-// active are queued for the out-of-line reference-order path.
-// ring capacities: survivors <= 31 pending + 32 pushed per iteration; slow pairs <= 31 pending + 32 from stage 1
-// + 32 from the stage-2 batch of the same iteration
-constexpr int kJobRing = 64, kSlowRing = 128, kS1Floats = 15;
+// ---- aligned, Sph2Pob kinds: cheap conservative cull for all pairs, everything exact warp-compacted ---------
+// Stage 0 (pair_far_apart) runs for every pair: ~40 instructions (four MUFU sines, a lowered haversine against the
+// circumradii) prove about 58 % of random pairs disjoint -- an exact 0.  The raw boxes of the survivors are
+// ballot-compacted into a per-warp ring in shared memory; jitter_1, the degree-domain sincos, the transform
+// (pair_stage1 / pair_stage2) and the clipper then run 32 survivors at a time with full warps.  Pairs on which a
+// reference quirk may be active are queued once more for the out-of-line reference-order path.
+// Ring capacities: survivors <= 31 pending + 32 pushed per round; slow pairs <= 31 pending + 32 from one batch.
+constexpr int kJobRing = 64, kSlowRing = 64, kJobWords = 12;   // 48-byte entries: conflict-free LDS.128 / STS.128
 
 struct AlignedTile {
-    float s1[kThreads / 32][kS1Floats][kJobRing];
-    unsigned short jidx[kThreads / 32][kJobRing];
-    unsigned short sidx[kThreads / 32][kSlowRing];
+    // entry = (t1, p1, a1, b1 | t2, p2, a2, b2 | g1, g2, round << 5 | lane, -)
+    __align__(16) float job[kThreads / 32][kJobRing][kJobWords];
+    int sidx[kThreads / 32][kSlowRing];
+    // boxes of the next round, fetched with cp.async one round ahead: [warp][operand][5 x 32 floats]
+    // (vectorised BFoV: lane-major float4; otherwise component-major, conflict-free either way)
+    __align__(16) float pre[kThreads / 32][2][160];
 };
 
-template <int D>
-__global__ void __launch_bounds__(kThreads)
+__device__ __forceinline__ void cp_async4(float* s, const float* g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(s)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async16(float* s, const float* g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(s)), "l"(g) : "memory");
+}
+// Fetch the 32 boxes of chunk c (box index c * 32 + lane) of one operand into the warp's staging slot.
+// VEC (16-byte aligned base): a whole chunk is 32 * D contiguous floats, copied as 16-byte pieces (D = 4: one per
+// lane; D = 5: 40 pieces, lanes 0-7 take a second one) into a box-major slot; the last, partial chunk of the operand
+// (index `full`, `tail` boxes) uses 4-byte copies into the same layout.  Not VEC: 4-byte copies, component-major.
+template <int D, bool VEC>
+__device__ __forceinline__ void prefetch_chunk(float* slot, const float* __restrict__ b, int c, int full, int tail, int lane) {
+    const float* src = b + (int64_t)c * (32 * D);
+    if (VEC && c < full) {
+        cp_async16(slot + 4 * lane, src + 4 * lane);
+        if (D == 5 && lane < 8) cp_async16(slot + 128 + 4 * lane, src + 128 + 4 * lane);
+    } else if (c < full || lane < tail) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) cp_async4(VEC ? slot + lane * D + k : slot + k * 32 + lane, src + lane * D + k);
+    }
+}
+template <int D, bool VEC>
+__device__ __forceinline__ RawBox fetched_box(const float* slot, int lane) {
+    RawBox r;
+    if (VEC && D == 4) {
+        const float4 v = *reinterpret_cast<const float4*>(slot + lane * 4);
+        r.t = v.x; r.p = v.y; r.a = v.z; r.b = v.w; r.g = 0.0f;
+    } else if (VEC) {       // box-major, stride 5 words: conflict-free
+        const float* q = slot + lane * 5;
+        r.t = q[0]; r.p = q[1]; r.a = q[2]; r.b = q[3]; r.g = q[4];
+    } else {
+        r.t = slot[lane]; r.p = slot[32 + lane]; r.a = slot[64 + lane]; r.b = slot[96 + lane];
+        r.g = (D == 5) ? slot[128 + lane] : 0.0f;
+    }
+    return r;
+}
+
+template <int D, bool VEC, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
 k_iou_aligned2(const float* __restrict__ b1, const float* __restrict__ b2, int64_t P, int kind, int mode, int edge,
-               float* __restrict__ out, int iters, bool vec_ok, bool dense) {
+               float* __restrict__ out, bool dense) {
     __shared__ AlignedTile T;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t base = ((int64_t)blockIdx.x * (kThreads / 32) + warp) * iters * 32;
-    if (base >= P) return;
+    // Persistent warps: the grid is at most one resident wave; warp wg takes the 32-pair chunks wg, wg + nw,
+    // wg + 2 nw, ... so that at any moment the whole GPU streams one contiguous window of the inputs.
+    // A queued pair is remembered as (round << 5 | lane): the host keeps rounds < 2^26 (and chunks < 2^31).
+    const int nw = (int)gridDim.x * (kThreads / 32), wg = (int)blockIdx.x * (kThreads / 32) + warp;
+    const int full = (int)(P >> 5), tail = (int)(P & 31), chunks = full + (tail ? 1 : 0);
     int hj = 0, tj = 0, hs = 0, ts = 0;
     const unsigned lt = (1u << lane) - 1u;
-    // one extra iteration (it == iters) drains the rings, so that each batch body exists once in the code
+    float* const slot1 = T.pre[warp][0];
+    float* const slot2 = T.pre[warp][1];
+    // the boxes of the next round are fetched one round ahead (cp.async into shared memory: no registers are
+    // held across the arithmetic, and the DRAM latency hides behind a round or a whole batch)
+    int c = wg, k = 0;
+    if (c < chunks) {
+        prefetch_chunk<D, VEC>(slot1, b1, c, full, tail, lane);
+        prefetch_chunk<D, VEC>(slot2, b2, c, full, tail, lane);
+    }
 #pragma unroll 1
-    for (int it = 0; it <= iters; ++it) {
-        const bool last = it == iters;
-        const int need = last ? 1 : 32;
-        const int off = it * 32 + lane;
-        const int64_t i = base + off;
-        int st = JOB_DEAD;
-        PairS1 q;
-        if (!last && i < P) {
-            const RawBox x = load_box<D>(b1, i, vec_ok), y = load_box<D>(b2, i, vec_ok);
-            st = pair_stage1(x, y, D, edge, !dense, &q);
-            if (st == JOB_DEAD) out[i] = 0.0f;
+    for (;;) {
+        // ---- scan: stage 0 on whole chunks until 32 survivors are queued or the chunks are used up
+#pragma unroll 1
+        while (c < chunks && tj - hj < 32) {
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            if (VEC) __syncwarp();                      // pieces were fetched by other lanes
+            const int64_t i = (int64_t)c * 32 + lane;
+            const bool ok = c < full || lane < tail;
+            RawBox x, y;
+            x.t = x.p = x.a = x.b = x.g = 0.0f;
+            y = x;
+            if (ok) { x = fetched_box<D, VEC>(slot1, lane); y = fetched_box<D, VEC>(slot2, lane); }
+            if (VEC) __syncwarp();                      // everybody has read the slot before it is refilled
+            c += nw;
+            if (c < chunks) {
+                prefetch_chunk<D, VEC>(slot1, b1, c, full, tail, lane);
+                prefetch_chunk<D, VEC>(slot2, b2, c, full, tail, lane);
+            }
+            bool live = false;
+            if (ok) {
+                live = dense || !pair_far_apart(x, y, edge);
+                if (!live) out[i] = 0.0f;
+            }
+            const unsigned mj = __ballot_sync(0xFFFFFFFFu, live);
+            if (live) {
+                float4* e = reinterpret_cast<float4*>(T.job[warp][(tj + __popc(mj & lt)) & (kJobRing - 1)]);
+                e[0] = make_float4(x.t, x.p, x.a, x.b);
+                e[1] = make_float4(y.t, y.p, y.a, y.b);
+                e[2] = make_float4(x.g, y.g, __int_as_float((k << 5) | lane), 0.0f);
+            }
+            tj += __popc(mj);
+            ++k;
         }
-        const unsigned mj = __ballot_sync(0xFFFFFFFFu, st == JOB_READY);
-        if (st == JOB_READY) {
-            const int slot = (tj + __popc(mj & lt)) & (kJobRing - 1);
-            float (*r)[kJobRing] = T.s1[warp];
-            r[0][slot] = q.hav; r[1][slot] = q.sdt; r[2][slot] = q.cdt; r[3][slot] = q.sdp; r[4][slot] = q.cdp;
-            r[5][slot] = q.s1; r[6][slot] = q.c1; r[7][slot] = q.s2; r[8][slot] = q.c2;
-            r[9][slot] = q.w1; r[10][slot] = q.h1; r[11][slot] = q.w2; r[12][slot] = q.h2;
-            if (D == 5) { r[13][slot] = q.g1; r[14][slot] = q.g2; }
-            T.jidx[warp][slot] = (unsigned short)off;
-        }
-        tj += __popc(mj);
-        unsigned ms = __ballot_sync(0xFFFFFFFFu, st == JOB_SLOW);
-        if (st == JOB_SLOW) T.sidx[warp][(ts + __popc(ms & lt)) & (kSlowRing - 1)] = (unsigned short)off;
-        ts += __popc(ms);
-        if (tj - hj >= need) {
+        // ---- one batch of up to 32 survivors: jitter_1, transform, clipper (the expensive code exists once)
+        if (tj > hj) {
             const int cnt = min(tj - hj, 32);
             __syncwarp();
-            const int slot = (hj + lane) & (kJobRing - 1);
-            const float (*r)[kJobRing] = T.s1[warp];
-            PairS1 c;
-            c.hav = r[0][slot]; c.sdt = r[1][slot]; c.cdt = r[2][slot]; c.sdp = r[3][slot]; c.cdp = r[4][slot];
-            c.s1 = r[5][slot]; c.c1 = r[6][slot]; c.s2 = r[7][slot]; c.c2 = r[8][slot];
-            c.w1 = r[9][slot]; c.h1 = r[10][slot]; c.w2 = r[11][slot]; c.h2 = r[12][slot];
-            c.g1 = (D == 5) ? r[13][slot] : 0.0f; c.g2 = (D == 5) ? r[14][slot] : 0.0f;
-            const int o2 = T.jidx[warp][slot];
+            const float4* e = reinterpret_cast<const float4*>(T.job[warp][(hj + lane) & (kJobRing - 1)]);
+            const float4 e0 = e[0], e1 = e[1], e2 = e[2];
             __syncwarp();
+            const int o2 = __float_as_int(e2.z);
             bool slow = false;
             if (lane < cnt) {
+                RawBox x, y;
+                x.t = e0.x; x.p = e0.y; x.a = e0.z; x.b = e0.w; x.g = e2.x;
+                y.t = e1.x; y.p = e1.y; y.a = e1.z; y.b = e1.w; y.g = e2.y;
+                PairS1 q;
                 ClipJob job;
-                slow = pair_stage2(c, D, kind, &job) != JOB_READY;
-                if (!slow) out[base + o2] = clip_job_iou(job, mode);
+                int st = pair_stage1(x, y, D, edge, !dense, &q);
+                if (st == JOB_READY) st = pair_stage2(q, D, kind, &job);
+                slow = st == JOB_SLOW;
+                if (!slow) out[(((int64_t)(o2 >> 5) * nw + wg) << 5) + (o2 & 31)] = (st == JOB_DEAD) ? 0.0f : clip_job_iou(job, mode);
             }
-            ms = __ballot_sync(0xFFFFFFFFu, slow);
-            if (slow) T.sidx[warp][(ts + __popc(ms & lt)) & (kSlowRing - 1)] = (unsigned short)o2;
+            const unsigned ms = __ballot_sync(0xFFFFFFFFu, slow);
+            if (slow) T.sidx[warp][(ts + __popc(ms & lt)) & (kSlowRing - 1)] = o2;
             ts += __popc(ms);
             hj += cnt;
         }
+        const bool drained = c >= chunks && tj == hj;
+        const int need = drained ? 1 : 32;             // no more fast work can come: flush the reference-order ring
         while (ts - hs >= need) {
             const int cnt = min(ts - hs, 32);
             __syncwarp();
             const int o2 = T.sidx[warp][(hs + lane) & (kSlowRing - 1)];
             __syncwarp();
-            if (lane < cnt) out[base + o2] = slow_pair_iou(b1, base + o2, b2, base + o2, D, kind, mode, edge, dense);
+            if (lane < cnt) {
+                const int64_t p = (((int64_t)(o2 >> 5) * nw + wg) << 5) + (o2 & 31);
+                out[p] = slow_pair_iou(b1, p, b2, p, D, kind, mode, edge, dense);
+            }
             hs += cnt;
         }
+        if (drained) break;
     }
 }
 
@@ -841,17 +907,25 @@ int sphk_iou_aligned(int kind, const float* b1, const float* b2, int64_t P, int 
         if (kind == SPHK_KIND_SPH) k_iou_aligned<KIND_SPH, 4><<<g, kThreads, 0, s>>>(b1, b2, P, mode, edge, out, v, g_dense != 0);
         else k_iou_aligned<KIND_FOV, 4><<<g, kThreads, 0, s>>>(b1, b2, P, mode, edge, out, v, g_dense != 0);
     } else {
-        // pairs per warp = 32 * iters: enough warps for ~2 waves of 4 CTAs per SM, at most 512 pairs per warp
-        const int sms = sm_count();
-        int64_t iters = (P + (int64_t)kThreads * 8 * sms - 1) / ((int64_t)kThreads * 8 * sms);
-        iters = iters < 1 ? 1 : (iters > 16 ? 16 : iters);
-        if (g_force_iters >= 1 && g_force_iters <= 16) iters = g_force_iters;   // tuning hook (SPHK_ALIGNED_ITERS)
-        const int64_t per_cta = (int64_t)kThreads * iters;
-        const int64_t g64 = (P + per_cta - 1) / per_cta;
-        if (g64 > 0x7FFFFFFFll) return fail(SPHK_ERR_UNSUPPORTED, "sphk_iou_aligned: P too large; split the call");
+        // persistent warps: at most one resident wave (MINB CTAs of 8 warps per SM), at least 4 rounds of 32 pairs per
+        // warp (so that the survivor batches fill)
+        const int64_t chunks = (P + 31) / 32, wpc = kThreads / 32;
+        if (chunks > 0x7FFFFFFFll) return fail(SPHK_ERR_UNSUPPORTED, "sphk_iou_aligned: P too large; split the call");
+        const int minb = (g_force_minb == 3 || g_force_minb == 4) ? g_force_minb : 4;
+        int64_t g64 = (chunks + wpc * 4 - 1) / (wpc * 4);
+        const int64_t wave = (g_force_ctas > 0) ? g_force_ctas : (int64_t)minb * sm_count();
+        if (g64 > wave) g64 = wave;
         const unsigned g = (unsigned)g64;
-        if (D == 4) k_iou_aligned2<4><<<g, kThreads, 0, s>>>(b1, b2, P, kind, mode, edge, out, (int)iters, v, g_dense != 0);
-        else k_iou_aligned2<5><<<g, kThreads, 0, s>>>(b1, b2, P, kind, mode, edge, out, (int)iters, false, g_dense != 0);
+        const bool dn = g_dense != 0;
+#define SPHK_AL2(DD, VV, MB) k_iou_aligned2<DD, VV, MB><<<g, kThreads, 0, s>>>(b1, b2, P, kind, mode, edge, out, dn)
+        if (minb == 3) {
+            if (D == 4) { if (v) SPHK_AL2(4, true, 3); else SPHK_AL2(4, false, 3); }
+            else { if (v) SPHK_AL2(5, true, 3); else SPHK_AL2(5, false, 3); }
+        } else {
+            if (D == 4) { if (v) SPHK_AL2(4, true, 4); else SPHK_AL2(4, false, 4); }
+            else { if (v) SPHK_AL2(5, true, 4); else SPHK_AL2(5, false, 4); }
+        }
+#undef SPHK_AL2
     }
     SPHK_LAUNCH_CHECK("k_iou_aligned");
     return SPHK_OK;

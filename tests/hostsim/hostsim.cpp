@@ -45,17 +45,42 @@ void hostsim_iou_aligned_v2(int kind, const float* b1, const float* b2, long P, 
     }
 }
 
-// The aligned formulation (k_iou_aligned2): stage 1 for every pair, stage 2 + clipper for the survivors.
+// The aligned formulation (k_iou_aligned2): stage 0 (approximate cull) for every pair; jitter_1 + transform +
+// clipper for the survivors.  path: 0 = culled by stage 0, 3 = culled by the exact test of stage 1, 1 = fast, 2 = slow.
 void hostsim_iou_aligned_v3(int kind, const float* b1, const float* b2, long P, int D, int mode, int edge, float* out,
                             unsigned char* path) {
     for (long i = 0; i < P; ++i) {
         const RawBox x = load_box(b1, i, D), y = load_box(b2, i, D);
+        if (pair_far_apart(x, y, edge)) { out[i] = 0.0f; if (path) path[i] = 0; continue; }
         PairS1 s1;
         ClipJob job;
         int st = pair_stage1(x, y, D, edge, true, &s1);
         if (st == JOB_READY) st = pair_stage2(s1, D, kind, &job);
-        if (path) path[i] = (st == JOB_DEAD) ? 0 : (st == JOB_READY ? 1 : 2);
+        if (path) path[i] = (st == JOB_DEAD) ? 3 : (st == JOB_READY ? 1 : 2);
         out[i] = (st == JOB_DEAD) ? 0.0f : (st == JOB_READY ? clip_job_iou(job, mode) : sph2pob_iou_pair(x, y, D, kind, mode, edge));
+    }
+}
+
+// Stage 0 against the exact tests: far[i] = pair_far_apart, dead1[i] = pair_stage1(cull) == JOB_DEAD or slow-path
+// pair whose jittered OBBs are disjoint (obb_disjoint), hav[i] = the exact haversine of stage 1 (NaN when slow).
+void hostsim_stage0(const float* b1, const float* b2, long P, int D, int edge, unsigned char* far, unsigned char* dead1,
+                    float* hav) {
+    for (long i = 0; i < P; ++i) {
+        const RawBox x = load_box(b1, i, D), y = load_box(b2, i, D);
+        far[i] = pair_far_apart(x, y, edge) ? 1 : 0;
+        PairS1 s1;
+        const int st = pair_stage1(x, y, D, edge, true, &s1);
+        hav[i] = (st == JOB_SLOW) ? NAN : s1.hav;
+        if (st == JOB_SLOW) {
+            const bool m = jitter1_mask(x, y, D);
+            const JitBox g = jitter1_role1(x, m, D), p = jitter1_role2(y, m, D);
+            XformAux aux;
+            ObbPair o = sph2pob_efficient(g, p, D, edge, &aux);
+            jitter2(o);
+            dead1[i] = obb_disjoint(o) ? 1 : 0;
+        } else {
+            dead1[i] = (st == JOB_DEAD) ? 1 : 0;
+        }
     }
 }
 

@@ -149,6 +149,29 @@ def test_aligned_all_pairs_on_the_reference_order_path(api, c_oracle):
         assert np.median(err) < 1e-6 and err.max() < 1e-5, (np.median(err), err.max(), int(np.argmax(err)))
 
 
+def test_aligned_cull_never_changes_a_result(api):
+    """The stage-0 cull of the aligned kernel works on MUFU sines: with the early-outs disabled (dense mode:
+    every pair goes through jitter_1 + transform + clipper) the output must be bit-identical -- on random pairs and
+    on pairs placed within +-10 % of the touching distance (tiny to oversize boxes, poles, seam)."""
+    from test_hostsim_math import near_touching_pairs
+    sets = [near_touching_pairs(400_000, s) for s in (0, 1, 2)]
+    r1 = O.generate_boxes(1_000_000, alpha_range=(1, 100), beta_range=(1, 100), box="rbfov", seed=40).numpy()
+    r2 = O.generate_boxes(1_000_000, alpha_range=(1, 100), beta_range=(1, 100), box="rbfov", seed=41).numpy()
+    sets.append((r1, r2))
+    for b1, b2 in sets:
+        for D in (4, 5):
+            x, y = cu(b1[:, :D]), cu(b2[:, :D])
+            for edge in ("arc", "chord", "tangent"):
+                fast = api.iou.sph2pob_efficient_iou(x, y, is_aligned=True, rbb_edge=edge)
+                prev = api.native.set_dense(True)
+                try:
+                    dense = api.iou.sph2pob_efficient_iou(x, y, is_aligned=True, rbb_edge=edge)
+                finally:
+                    api.native.set_dense(prev)
+                assert torch.equal(fast, dense), (D, edge, int((fast != dense).sum()))
+        assert 0.02 < float((fast > 0).float().mean()) < 0.98         # both outcomes are exercised
+
+
 def test_non_finite_and_out_of_range_inputs_do_not_poison_neighbours(api):
     """NaN / inf / absurd coordinates in one box must neither hang nor disturb other pairs (they take the
     reference-order path; the result for the bad pair itself is whatever fp32 gives, 0 for NaN areas)."""

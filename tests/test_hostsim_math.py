@@ -149,6 +149,54 @@ def test_fast_formulations_equal_reference_order_path(hostsim, fn):
         assert (path == 1).mean() > 0.3
 
 
+def near_touching_pairs(n, seed):
+    """Pairs whose centre distance sits within a few per cent of the sum of the circumradii (where a cull test
+    decides), for small, medium and oversize boxes, all over the sphere incl. poles and the seam."""
+    rng = np.random.RandomState(seed)
+    size = np.exp(rng.uniform(np.log(0.02), np.log(150.0), (n, 4)))            # alpha, beta of both boxes (deg)
+    size[::9] = rng.uniform(170, 400, (len(size[::9]), 4))
+    t1, p1 = rng.uniform(0, 360, n), np.degrees(np.arccos(rng.uniform(-1, 1, n)))
+    p1[::17] = rng.uniform(0, 0.5, len(p1[::17])); p1[5::17] = 180 - rng.uniform(0, 0.5, len(p1[5::17]))
+    r = 0.5 * (np.hypot(size[:, 0], size[:, 1]) + np.hypot(size[:, 2], size[:, 3]))
+    dist = np.radians(np.minimum(r * rng.uniform(0.9, 1.1, n), 179.9))          # great-circle distance to box 2
+    brg = rng.uniform(0, 2 * np.pi, n)
+    lat1 = np.radians(90 - p1)
+    lat2 = np.arcsin(np.clip(np.sin(lat1) * np.cos(dist) + np.cos(lat1) * np.sin(dist) * np.cos(brg), -1, 1))
+    dlon = np.arctan2(np.sin(brg) * np.sin(dist) * np.cos(lat1), np.cos(dist) - np.sin(lat1) * np.sin(lat2))
+    t2, p2 = (t1 + np.degrees(dlon)) % 360.0, 90 - np.degrees(lat2)
+    g = rng.uniform(-90, 90, (n, 2))
+    b1 = np.stack([t1, p1, size[:, 0], size[:, 1], g[:, 0]], 1).astype(np.float32)
+    b2 = np.stack([t2, p2, size[:, 2], size[:, 3], g[:, 1]], 1).astype(np.float32)
+    return b1, b2
+
+
+def test_stage0_cull_is_conservative(hostsim):
+    """pair_far_apart (the approximate-trigonometry cull every aligned pair goes through) may only fire where the
+    exact dead test of stage 1 fires too, with room for the MUFU sine error (1e-6 per sine, 6 sines: the GPU suite
+    measures the real thing), and must never fire on out-of-range centres."""
+    ub = ctypes.POINTER(ctypes.c_ubyte)
+    for D in (4, 5):
+        for seed in (0, 1):
+            b1, b2 = near_touching_pairs(300_000, seed)
+            b1, b2 = np.ascontiguousarray(b1[:, :D]), np.ascontiguousarray(b2[:, :D])
+            n = len(b1)
+            far, dead1, hav = np.empty(n, np.uint8), np.empty(n, np.uint8), np.empty(n, np.float32)
+            for edge in (0, 1, 2):
+                hostsim.hostsim_stage0(b1.ctypes.data_as(fp), b2.ctypes.data_as(fp), ctypes.c_long(n), D, edge,
+                                       far.ctypes.data_as(ub), dead1.ctypes.data_as(ub), hav.ctypes.data_as(fp))
+                assert not (far.astype(bool) & ~dead1.astype(bool)).any()
+                if edge == 2:
+                    assert not far.any()
+                else:
+                    assert far.sum() > 0.5 * dead1.sum()        # it decides (tiny boxes fall inside the haversine slack)
+            # out-of-range / non-finite centres are never culled
+            bad = b1.copy()
+            bad[::4, 0] = 360.5; bad[1::4, 1] = -0.25; bad[2::4, 0] = np.nan; bad[3::4, 1] = 180.25
+            hostsim.hostsim_stage0(bad.ctypes.data_as(fp), b2.ctypes.data_as(fp), ctypes.c_long(n), D, 0,
+                                   far.ctypes.data_as(ub), dead1.ctypes.data_as(ub), hav.ctypes.data_as(fp))
+            assert not far.any()
+
+
 @pytest.mark.parametrize("box", ["bfov", "rbfov"])
 def test_project_angle_variant(hostsim, box):
     """rbb_angle='project' (sph2pob_efficient.py:92-93, sph2pob_standard.py:99-100)."""
