@@ -107,6 +107,69 @@ struct ClipJob {
 };
 enum { JOB_READY = 0, JOB_DEAD = 1, JOB_SLOW = 2 };
 
+// sin / cos of the ends of the reference's clamped-acos range (kAcosLo = acos(1 - 1e-7))
+constexpr float kSinLo = 4.47213587e-4f, kCosLo = 0.9999999f;
+
+// |angle| confined to [kAcosLo, pi - kAcosLo] on its (sin, cos); the sign of the angle is the sign of the sine,
+// zero counting as negative (sph2pob_efficient.py:224-225, sph2pob_standard.py:220-235)
+SPHK_HD void clamp_axis(float& s, float& c) {
+    if (fabsf(s) < kSinLo) {
+        s = (s > 0.0f) ? kSinLo : -kSinLo;
+        c = (c < 0.0f) ? -kCosLo : kCosLo;
+    }
+}
+
+// Common tail of the fast transform.  In: the arc (outside the acos clamp zone), the internal angles
+// a_g = atan2(sag, cag), a_p = atan2(sap, cap) as unit vectors, sin / cos of gamma (0, 1 for BFoV) and gamma itself in
+// degrees, the planar sizes.  Applies the clamped-acos range of the reference (before gamma in 'efficient', after it
+// in 'standard') and jitter_2 (sph_iou_api.py:222-242) in the rotated frame:
+//   * its mask can only fire through the sizes or the angles here (|x1 - x2| = arc >= 2e-3 > eps); then box 1 moves by
+//     (eps, eps), grows by 2 eps and turns by eps; box 2 moves by (2 eps, 2 eps), grows by eps and turns by 5 eps;
+//   * angles matter only when the boxes are nearly parallel (cos r > 0, |sin r| < 2.5e-3 covers eps' + 4 eps): that rare
+//     lane recovers the angles themselves (unwrapped, as the reference holds them) and replays jitter_2 on them.
+// The size and angle clamps of jitter_2 cannot be active: sizes near the minimum and |gamma| > 179 deg never get here.
+SPHK_HD void finish_job(float arc, float sag, float cag, float sap, float cap, float sg1, float cg1, float sg2, float cg2,
+                        float g1_deg, float g2_deg, float w1, float h1, float w2, float h2, int D, int kind, ClipJob* job) {
+    const bool standard = (kind == KIND_SPH2POB_STANDARD);
+    if (!standard) { clamp_axis(sag, cag); clamp_axis(sap, cap); }
+    float c1 = cag, s1 = sag, c2 = cap, s2 = sap;
+    if (D == 5) {       // a - gamma
+        c1 = fmaf(cag, cg1, sag * sg1); s1 = fmaf(sag, cg1, -cag * sg1);
+        c2 = fmaf(cap, cg2, sap * sg2); s2 = fmaf(sap, cg2, -cap * sg2);
+    }
+    if (standard) { clamp_axis(s1, c1); clamp_axis(s2, c2); }
+    float cr = fmaf(c2, c1, s2 * s1), sr = fmaf(s2, c1, -c2 * s1);         // r = a2 - a1
+    bool m = (fabsf(w1 - w2) < kEps) | (fabsf(h1 - h2) < kEps);
+    float dx = arc, dy = 0.0f;
+    if (cr > 0.0f && fabsf(sr) < 2.5e-3f) {
+        // nearly parallel: the angles themselves, as the reference-order path holds them
+        float a1, a2;
+        if (standard) {
+            a1 = atan2f(s1, c1); a2 = atan2f(s2, c2);                       // wrapped after gamma, then clamped
+        } else {
+            a1 = atan2f(sag, cag); a2 = atan2f(sap, cap);
+            if (D == 5) { a1 -= g1_deg * kDeg2Rad; a2 -= g2_deg * kDeg2Rad; }   // unwrapped (sph2pob_efficient.py:55-57)
+        }
+        m = m | (fabsf(a1 - a2) < kEps);
+        if (m) { a1 += kEps; a2 += kEps5; }
+        if (fabsf(a1 - a2) < kEpsA) { a1 += kEpsA; a2 += kEpsA2; }
+        sincos_f(a1, &s1, &c1);
+        sincos_f(a2 - a1, &sr, &cr);
+    } else if (m) {
+        // turn box 1 by eps and the relative angle by 4 eps
+        const float ce = 0.99999999237f, se = 1.2345678e-4f, c4 = 0.9999998781f, s4 = 4.9382710e-4f;
+        const float t1 = fmaf(c1, ce, -s1 * se), u1 = fmaf(s1, ce, c1 * se);
+        const float tr = fmaf(cr, c4, -sr * s4), ur = fmaf(sr, c4, cr * s4);
+        c1 = t1; s1 = u1; cr = tr; sr = ur;
+    }
+    if (m) { w1 += kEps2; h1 += kEps2; w2 += kEps; h2 += kEps; dx = arc + kEps; dy = kEps; }
+    job->sr = (sr == 0.0f) ? 1e-30f : sr;
+    job->cr = (cr == 0.0f) ? 1e-30f : cr;
+    // centre of box 2 in the frame of box 1: R(-a1) (dx, dy)   (same for both transforms)
+    job->px = fmaf(c1, dx, s1 * dy); job->py = fmaf(-s1, dx, c1 * dy);
+    job->w1 = w1; job->h1 = h1; job->w2 = w2; job->h2 = h2;
+}
+
 // Transform stage of the fast path.  JOB_READY: *job is set.  JOB_DEAD (only with cull = true): the planar
 // boxes cannot touch, IoU is exactly 0.  JOB_SLOW: a reference quirk may be active, run sph2pob_iou_pair.
 SPHK_HD int pair_job(const BoxRec& g, const BoxRec& p, int D, int kind, bool cull, ClipJob* job) {
@@ -131,24 +194,7 @@ SPHK_HD int pair_job(const BoxRec& g, const BoxRec& p, int D, int kind, bool cul
     if (!(S2g > 1e-30f && S2p > 1e-30f)) return JOB_SLOW;
     const float ig = rsqrt_f(S2g), ip = rsqrt_f(S2p);
     // a_g = atan2(ng, mg), a_p = atan2(np, mp): only their sine and cosine are ever used
-    const float sag = ng * ig, cag = mg * ig, sap = np * ip, cap = mp * ip;
-    // a1 = a_g - gamma_g, a2 = a_p - gamma_p
-    const float c1 = fmaf(cag, g.cg, sag * g.sg), s1 = fmaf(sag, g.cg, -cag * g.sg);
-    const float c2 = fmaf(cap, p.cg, sap * p.sg), s2 = fmaf(sap, p.cg, -cap * p.sg);
-    // the reference clamps |angle| into [4.47e-4, pi - 4.47e-4] (before gamma in 'efficient', after
-    // it in 'standard') and gives angle == 0 the sign -1: stay clear of both ends
-    const bool near_axis = (kind == KIND_SPH2POB_STANDARD) ? (fabsf(s1) < 1e-3f || fabsf(s2) < 1e-3f)
-                                                           : (fabsf(sag) < 1e-3f || fabsf(sap) < 1e-3f);
-    if (near_axis) return JOB_SLOW;
-    float cr = fmaf(c2, c1, s2 * s1), sr = fmaf(s2, c1, -c2 * s1);         // r = a2 - a1
-    // jitter_2 (sph_iou_api.py:222-242) must be inactive: sizes differ by > eps, angles by > eps'
-    if (fabsf(g.w - p.w) < 2e-4f || fabsf(g.h - p.h) < 2e-4f) return JOB_SLOW;
-    if (cr > 0.0f && fabsf(sr) < 2e-3f) return JOB_SLOW;
-    job->sr = (sr == 0.0f) ? 1e-30f : sr;
-    job->cr = (cr == 0.0f) ? 1e-30f : cr;
-    // centre of box 2 in the frame of box 1: R(-a1) (arc, 0)   (same for both transforms)
-    job->px = c1 * arc; job->py = -s1 * arc;
-    job->w1 = g.w; job->h1 = g.h; job->w2 = p.w; job->h2 = p.h;
+    finish_job(arc, ng * ig, mg * ig, np * ip, mp * ip, g.sg, g.cg, p.sg, p.cg, g.g, p.g, g.w, g.h, p.w, p.h, D, kind, job);
     return JOB_READY;
 }
 
@@ -273,25 +319,12 @@ SPHK_HD int pair_stage2(const PairS1& s, int D, int kind, ClipJob* job) {
     const float S2g = fmaf(ng, ng, mg * mg), S2p = fmaf(np, np, mp * mp);
     if (!(S2g > 1e-30f && S2p > 1e-30f)) return JOB_SLOW;
     const float ig = rsqrt_f(S2g), ip = rsqrt_f(S2p);
-    const float sag = ng * ig, cag = mg * ig, sap = np * ip, cap = mp * ip;
-    float c1 = cag, s1 = sag, c2 = cap, s2 = sap;
+    float sg1 = 0.0f, cg1 = 1.0f, sg2 = 0.0f, cg2 = 1.0f;
     if (D == 5) {
-        float sg1, cg1, sg2, cg2;
         sincos_deg(s.g1, 0.0f, &sg1, &cg1);
         sincos_deg(s.g2, 0.0f, &sg2, &cg2);
-        c1 = fmaf(cag, cg1, sag * sg1); s1 = fmaf(sag, cg1, -cag * sg1);
-        c2 = fmaf(cap, cg2, sap * sg2); s2 = fmaf(sap, cg2, -cap * sg2);
     }
-    const bool near_axis = (kind == KIND_SPH2POB_STANDARD) ? (fabsf(s1) < 1e-3f || fabsf(s2) < 1e-3f)
-                                                           : (fabsf(sag) < 1e-3f || fabsf(sap) < 1e-3f);
-    if (near_axis) return JOB_SLOW;
-    const float cr = fmaf(c2, c1, s2 * s1), sr = fmaf(s2, c1, -c2 * s1);
-    if (fabsf(s.w1 - s.w2) < 2e-4f || fabsf(s.h1 - s.h2) < 2e-4f) return JOB_SLOW;
-    if (cr > 0.0f && fabsf(sr) < 2e-3f) return JOB_SLOW;
-    job->sr = (sr == 0.0f) ? 1e-30f : sr;
-    job->cr = (cr == 0.0f) ? 1e-30f : cr;
-    job->px = c1 * arc; job->py = -s1 * arc;
-    job->w1 = s.w1; job->h1 = s.h1; job->w2 = s.w2; job->h2 = s.h2;
+    finish_job(arc, ng * ig, mg * ig, np * ip, mp * ip, sg1, cg1, sg2, cg2, s.g1, s.g2, s.w1, s.h1, s.w2, s.h2, D, kind, job);
     return JOB_READY;
 }
 

@@ -38,7 +38,7 @@ def hostsim():
     src = os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")
     out_dir = os.path.join(ROOT, "tests", "hostsim", "_build")
     out = os.path.join(out_dir, "libhostsim.so")
-    deps = [src] + [os.path.join(ROOT, "sph_retina_b200", "csrc", f) for f in ("sphk_math.cuh", "sphk_grad.cuh")]
+    deps = [src] + [os.path.join(ROOT, "sph_retina_b200", "csrc", f) for f in ("sphk_math.cuh", "sphk_fast.cuh", "sphk_grad.cuh")]
     if not os.path.isfile(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         os.makedirs(out_dir, exist_ok=True)
         subprocess.check_call([_system_gxx(), "-O2", "-fPIC", "-shared", "-DSPHK_WITH_GRAD", "-ffp-contract=fast",

@@ -172,6 +172,27 @@ def test_aligned_cull_never_changes_a_result(api):
         assert 0.02 < float((fast > 0).float().mean()) < 0.98         # both outcomes are exercised
 
 
+def test_fast_path_inside_the_quirk_zones(api, c_oracle):
+    """jitter_2 triggered through sizes / nearly parallel boxes and internal angles inside the clamped-acos zone are
+    evaluated by the fast path of both kernels (aligned, N x M): against the float64 C oracle, with the allowance for
+    pairs that sit within fp32 rounding of eps / eps' (tests/test_hostsim_math.py)."""
+    from test_hostsim_math import quirk_zone_pairs
+    for D in (4, 5):
+        b1, b2 = quirk_zone_pairs(120_000, D)
+        b1, b2 = np.ascontiguousarray(b1[:, :D]), np.ascontiguousarray(b2[:, :D])
+        x, y = cu(b1), cu(b2)
+        for kind, tr in ((0, "efficient"), (1, "standard")):
+            fn = getattr(api.iou, "sph2pob_%s_iou" % tr)
+            truth = c_oracle_aligned(c_oracle, kind, b1, b2)
+            err = np.abs(fn(x, y, is_aligned=True).cpu().numpy() - truth)
+            assert (err > 1e-5).sum() <= 12 and err.max() < 1e-3 and np.median(err) < 2e-7, (D, tr, (err > 1e-5).sum(), err.max())
+            # the same pairs on the diagonal of N x M blocks
+            for lo in (0, 60_000):
+                blk = fn(x[lo:lo + 1536], y[lo:lo + 1536]).diagonal().cpu().numpy()
+                e2 = np.abs(blk - truth[lo:lo + 1536])
+                assert (e2 > 1e-5).sum() <= 2 and e2.max() < 1e-3 and np.median(e2) < 2e-7, (D, tr, lo, e2.max())
+
+
 def test_non_finite_and_out_of_range_inputs_do_not_poison_neighbours(api):
     """NaN / inf / absurd coordinates in one box must neither hang nor disturb other pairs (they take the
     reference-order path; the result for the bad pair itself is whatever fp32 gives, 0 for NaN areas)."""

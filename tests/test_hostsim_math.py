@@ -149,6 +149,43 @@ def test_fast_formulations_equal_reference_order_path(hostsim, fn):
         assert (path == 1).mean() > 0.3
 
 
+def quirk_zone_pairs(n, seed):
+    """Overlapping pairs that sit inside the zones where a reference quirk is active WITHOUT jitter_1's similarity
+    mask: sizes within jitter_2's eps (rad), boxes nearly parallel (|a1 - a2| < eps, eps'), internal angles inside
+    the clamped-acos zone (centres on one meridian / one latitude circle near the equator), and mixtures."""
+    rng = np.random.RandomState(seed)
+    t1, p1 = rng.uniform(5, 355, n), rng.uniform(20, 160, n)
+    a1, b1 = rng.uniform(5, 90, n), rng.uniform(5, 90, n)
+    a2, b2 = rng.uniform(5, 90, n), rng.uniform(5, 90, n)
+    off = rng.uniform(0.15, 0.6, n) * np.minimum(np.hypot(a1, b1), np.hypot(a2, b2))
+    brg = rng.uniform(0, 2 * np.pi, n)
+    g1, g2 = rng.uniform(-90, 90, n), rng.uniform(-90, 90, n)
+    k = np.arange(n) % 6
+    sgn = rng.choice([-1.0, 1.0], n)
+    small = sgn * np.exp(rng.uniform(np.log(2e-4), np.log(6e-3), n))          # deg: > jitter_1's eps, < jitter_2's eps (rad)
+    a2 = np.where(k == 0, a1 + small, a2)                                     # widths within eps
+    b2 = np.where(k == 1, b1 + small, b2)                                     # heights within eps
+    brg = np.where(k == 2, np.round(brg / np.pi) * np.pi + small * 0.05, brg)      # same meridian: |sin a| tiny
+    p1 = np.where(k == 3, 90 + small, p1)                                     # both on the equator ...
+    brg = np.where(k == 3, np.pi / 2 + small * 0.01, brg)                     # ... east-west: angle at the other clamp end
+    dp, dt = -off * np.cos(brg), off * np.sin(brg) / np.maximum(np.sin(np.radians(p1)), 0.2)
+    t2, p2 = t1 + dt, np.clip(p1 + dp, 1, 179)
+    # nearly parallel planar boxes: gamma_2 chosen so that (a_g - gamma_1) - (a_p - gamma_2) = delta, |delta| up to 3e-3 rad
+    # (the internal angles from the tangent-plane bearings, sphk_math.cuh).  Where gamma_2 has to be wrapped into
+    # (-179, 179) the unwrapped angles of 'efficient' end up 2 pi apart while 'standard' still sees them parallel.
+    tg, pg, tp, pp = (np.radians(v.astype(np.float32).astype(np.float64)) for v in (t1, p1, t2 % 360.0, p2))
+    hth = np.sin(0.5 * (tp - tg)) ** 2
+    ag = np.arctan2(np.sin(pp - pg) - 2 * np.cos(pg) * np.sin(pp) * hth, -np.sin(pp) * np.sin(tp - tg))
+    ap = np.arctan2(np.sin(pp - pg) + 2 * np.cos(pp) * np.sin(pg) * hth, -np.sin(pg) * np.sin(tp - tg))
+    delta = sgn * np.exp(rng.uniform(np.log(1e-5), np.log(3e-3), n))
+    want = g1 - np.degrees(ag - ap) + np.degrees(delta)
+    want = (want + 180.0) % 360.0 - 180.0
+    g2 = np.where((k >= 4) & (np.abs(want) < 178.0), want, g2)
+    B1 = np.stack([t1, p1, a1, b1, g1], 1).astype(np.float32)
+    B2 = np.stack([t2 % 360.0, p2, a2, b2, g2], 1).astype(np.float32)
+    return B1, B2
+
+
 def near_touching_pairs(n, seed):
     """Pairs whose centre distance sits within a few per cent of the sum of the circumradii (where a cull test
     decides), for small, medium and oversize boxes, all over the sphere incl. poles and the seam."""
@@ -195,6 +232,29 @@ def test_stage0_cull_is_conservative(hostsim):
             hostsim.hostsim_stage0(bad.ctypes.data_as(fp), b2.ctypes.data_as(fp), ctypes.c_long(n), D, 0,
                                    far.ctypes.data_as(ub), dead1.ctypes.data_as(ub), hav.ctypes.data_as(fp))
             assert not far.any()
+
+
+@pytest.mark.parametrize("fn", ["hostsim_iou_aligned_v2", "hostsim_iou_aligned_v3"])
+def test_fast_path_inside_the_quirk_zones(hostsim, c_oracle, fn):
+    """jitter_2 (size and angle triggers) and the clamped-acos zone are handled by the fast path itself: it must
+    agree with the reference-order path of the same header and with the float64 C oracle there."""
+    from test_oracle_golden import _c_aligned as c_aligned
+    for D in (4, 5):
+        b1, b2 = quirk_zone_pairs(120_000, D)
+        b1, b2 = np.ascontiguousarray(b1[:, :D]), np.ascontiguousarray(b2[:, :D])
+        for kind in (0, 1):
+            want = hs_aligned(hostsim, kind, b1, b2)
+            got, path = hs_fast(hostsim, fn, kind, b1, b2)
+            truth = c_aligned(c_oracle, kind, b1, b2)
+            assert (path == 1).mean() > 0.9, (path == 1).mean()             # ... and it really is the fast path
+            e_fast, e_slow = np.abs(got - truth), np.abs(want - truth)
+            # A pair whose |a1 - a2| (or size difference) lies within fp32 rounding of eps / eps' takes the other
+            # branch of jitter_2 than the float64 run -- in ANY fp32 evaluation, the reference-order path included
+            # (a few pairs in 1e5 here, a ~1e-4 step): both paths are held to the same allowance.
+            for e in (e_fast, e_slow):
+                assert (e > 1e-5).sum() <= 12 and e.max() < 1e-3, (fn, D, kind, (e > 1e-5).sum(), e.max(), int(np.argmax(e)))
+            assert np.median(e_fast) < 2e-7
+            assert (truth > 0.02).mean() > 0.9
 
 
 @pytest.mark.parametrize("box", ["bfov", "rbfov"])
