@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SPHK_ABI_VERSION 2
+#define SPHK_ABI_VERSION 3
 
 enum sphk_status {
     SPHK_OK = 0,
@@ -144,6 +144,39 @@ int sphk_obb_bwd(int kind, const float* b1, const float* b2, int64_t n, int D, i
                  const float* grad_obb2, float* grad_b1, float* grad_b2, void* stream);
 int sphk_riou_fwd_bwd(const float* obb1, const float* obb2, int64_t n, float* iou, const float* grad_iou,
                       float* grad_obb1, float* grad_obb2, void* stream);
+
+/* The spherical delta box coders: DeltaXYWHSphBBoxCoder (D = 4) and DeltaXYWHASphBBoxCoder (D = 5)
+ * (sphdet/bbox/coder/delta_xywh_sph_bbox_coder.py:45-115,117-262; delta_xywha_rsph_bbox_coder.py:45-115,117-268).
+ * means / stds: HOST arrays of D floats (target_means / target_stds); wh_ratio_clip, clip_border, add_ctr_clamp,
+ * ctr_clamp as in the coder's constructor / decode().
+ *   sphk_coder_decode     : out[n, D] = delta2bbox(rois[n, D], deltas[n, D])
+ *   sphk_coder_decode_bwd : grad_deltas[n, D] = d(total)/d(deltas) from grad_out = d(total)/d(out) (zero where a clamp
+ *                           of the decode is active, as torch.clamp's backward does)
+ *   sphk_coder_encode     : out[n, D] = bbox2delta(proposals[n, D], gt[n, D]) */
+int sphk_coder_decode(const float* rois, const float* deltas, int64_t n, int D, const float* means, const float* stds,
+                      float wh_ratio_clip, int clip_border, int add_ctr_clamp, float ctr_clamp, float* out, void* stream);
+int sphk_coder_decode_bwd(const float* rois, const float* deltas, const float* grad_out, int64_t n, int D, const float* means,
+                          const float* stds, float wh_ratio_clip, int clip_border, int add_ctr_clamp, float ctr_clamp,
+                          float* grad_deltas, void* stream);
+int sphk_coder_encode(const float* proposals, const float* gt, int64_t n, int D, const float* means, const float* stds,
+                      float* out, void* stream);
+
+/* The regression branch of the head's loss with reg_decoded_bbox=True, in one launch
+ * (sphdet/models/heads/sph_retina_head.py:252-265: bbox_coder.decode(anchors, bbox_pred) then
+ * Sph2PobIoULoss(mode='iou')(pred, target, weight, avg_factor)).  It is called on ALL anchors of a
+ * batch with zero weights for the negatives: rows whose weight is 0 are skipped (loss 0 * finite, gradient 0 * finite),
+ * the others are compacted and evaluated 32 at a time: decode, jitter_1, sph2pob_standard, jitter_2, rotated IoU, and
+ * the whole backward down to the deltas.
+ *   anchors, deltas, target [n, D]
+ *   weight   NULL (= 1), [n] (weight_cols = 1) or [n, weight_cols] (row mean, sph2pob_iou_loss.py:43-48;
+ *            weight_cols = D as the head passes bbox_weights)
+ *   partial  [sphk_decode_loss_partials(n)] per-CTA sums of weight[i] * (1 - iou[i]); loss = scale * sum(partial)
+ *   grad_deltas [n, D] or NULL: d(loss)/d(deltas) (every row is written) */
+int64_t sphk_decode_loss_partials(int64_t n);
+int sphk_decode_loss_reduce(const float* anchors, const float* deltas, const float* target, const float* weight,
+                            int weight_cols, int64_t n, int D, const float* means, const float* stds, float wh_ratio_clip,
+                            int clip_border, int add_ctr_clamp, float ctr_clamp, float scale, float* partial,
+                            float* grad_deltas, void* stream);
 
 /* Batched greedy spherical NMS (SphNMS / sph_batched_nms / sph_nms_op,
  * sphdet/bbox/nms/sph_nms.py:22-74) with Sph2Pob-efficient IoU.

@@ -238,6 +238,59 @@ def golden_nms(R):
     print("nms", {k: v.shape for k, v in out.items() if "keep" in k})
 
 
+def golden_coder(R):
+    """Box coders and the decode -> Sph2PobIoULoss step of the head (reg_decoded_bbox=True): anchors from the real
+    anchor grid, deltas that trigger every clamp, ~10 % positive rows (2-D weights as the head passes them)."""
+    out = {}
+    A = anchors_512x1024()[::37].contiguous()
+    n = A.size(0)
+    for box, D, cls in (("bfov", 4, R.DeltaXYWHSphBBoxCoder), ("rbfov", 5, R.DeltaXYWHASphBBoxCoder)):
+        torch.manual_seed(51 + D)
+        anchors = A[:, :D].clone()
+        if D == 5:
+            anchors[:, 4] = (torch.rand(n) - 0.5) * 60
+        means = (0.01, -0.02, 0.03, 0.0, 0.02)[:D]
+        stds = (0.1, 0.1, 0.2, 0.2, 0.1)[:D]
+        deltas = torch.randn(n, D) * 1.5
+        deltas[::13] *= 12                                 # size / border / gamma clamps fire
+        target = R.generate_boxes(n, alpha_range=(5, 100), beta_range=(5, 100), dtype="float", box=box)
+        pos = torch.rand(n) < 0.1
+        # positives: targets near the anchors (what the assigner produces), deltas near the encoding of the target
+        target[pos] = (anchors[pos] + torch.randn(int(pos.sum()), D) * torch.tensor([4, 4, 6, 6, 10.0])[:D]).clamp(min=1)
+        target[~pos] = 0
+        weight = pos.float()[:, None].expand(n, D).contiguous()
+        out.update({box + "_anchors": _np(anchors), box + "_deltas": _np(deltas), box + "_target": _np(target),
+                    box + "_weight": _np(weight), box + "_means": np.array(means), box + "_stds": np.array(stds)})
+        for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+            for cname, kw in (("plain", {}), ("norm", dict(target_means=means, target_stds=stds)),
+                              ("ctr", dict(target_means=means, target_stds=stds, add_ctr_clamp=True, ctr_clamp=8)),
+                              ("noclip", dict(target_stds=stds, clip_border=False))):
+                coder = cls(**kw)
+                dec = coder.decode(anchors.to(dt), deltas.to(dt))
+                out["%s_%s_decode_%s" % (box, cname, tag)] = _np(dec)
+                out["%s_%s_encode_%s" % (box, cname, tag)] = _np(coder.encode(anchors.to(dt), dec))
+            # the head's regression loss: decode -> Sph2PobIoULoss(pred, target, weight, avg_factor = #positives)
+            coder = cls(target_means=means, target_stds=stds)
+            # deltas of the positives: the encoding of the target plus noise (a realistic mid-training prediction)
+            d2 = deltas.clone()
+            d2[pos] = coder.encode(anchors[pos], target[pos]) + torch.randn(int(pos.sum()), D) * 0.5
+            out[box + "_loss_deltas"] = _np(d2)
+            for mode in ("iou", "ciou"):
+                L = R.Sph2PobIoULoss(mode=mode, loss_weight=1.5)
+                dd = d2.to(dt).clone().requires_grad_(True)
+                if dt == torch.float64:
+                    with rh.float64_mode():
+                        loss = L(coder.decode(anchors.to(dt), dd), target.to(dt), weight.to(dt), avg_factor=float(pos.sum()))
+                        loss.backward()
+                else:
+                    loss = L(coder.decode(anchors.to(dt), dd), target.to(dt), weight.to(dt), avg_factor=float(pos.sum()))
+                    loss.backward()
+                out["%s_%s_loss_%s" % (box, mode, tag)] = _np(loss)
+                out["%s_%s_gdeltas_%s" % (box, mode, tag)] = _np(dd.grad)
+        print("coder", box, n, int(pos.sum()), float(out[box + "_iou_loss_f64"]))
+    np.savez_compressed(os.path.join(OUT, "coder.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     R = rh.load_reference()
@@ -246,3 +299,4 @@ if __name__ == "__main__":
     golden_pairwise(R)
     golden_loss(R)
     golden_nms(R)
+    golden_coder(R)

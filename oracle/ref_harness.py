@@ -191,6 +191,25 @@ def load_reference():
     iou_loss = importlib.import_module("sphdet.losses.sph2pob_iou_loss")
     transform = importlib.import_module("sphdet.losses.sph2pob_transform")
 
+    # bbox coders (sphdet/bbox/coder/delta_xywh*_sph_bbox_coder.py): need only the mmdet base class and registry
+    for name in ("mmdet.core.bbox.coder",):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__path__ = []
+            sys.modules[name] = m
+    base_coder = types.ModuleType("mmdet.core.bbox.coder.base_bbox_coder")
+
+    class BaseBBoxCoder:                                  # mmdet/core/bbox/coder/base_bbox_coder.py: an ABC with no state
+        def __init__(self, **kwargs):
+            pass
+    base_coder.BaseBBoxCoder = BaseBBoxCoder
+    sys.modules["mmdet.core.bbox.coder.base_bbox_coder"] = base_coder
+    bbox_builder = types.ModuleType("mmdet.core.bbox.builder")
+    bbox_builder.BBOX_CODERS = _PassThroughRegistry("bbox_coder")
+    sys.modules["mmdet.core.bbox.builder"] = bbox_builder
+    coder4 = _load_file("_ref_coder_bfov", "sphdet/bbox/coder/delta_xywh_sph_bbox_coder.py")
+    coder5 = _load_file("_ref_coder_rbfov", "sphdet/bbox/coder/delta_xywha_rsph_bbox_coder.py")
+
     gen = _load_file("_ref_generate_data", "tests/utils/generate_data.py")
 
     ns = types.SimpleNamespace(
@@ -204,6 +223,8 @@ def load_reference():
         Sph2PobIoULoss=iou_loss.Sph2PobIoULoss,
         jiter_spherical_bboxes=api.jiter_spherical_bboxes,
         jiter_rotated_bboxes=api.jiter_rotated_bboxes,
+        DeltaXYWHSphBBoxCoder=coder4.DeltaXYWHSphBBoxCoder, DeltaXYWHASphBBoxCoder=coder5.DeltaXYWHASphBBoxCoder,
+        coder4=coder4, coder5=coder5,
     )
     _LOADED = ns
     return ns

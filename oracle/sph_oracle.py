@@ -436,6 +436,65 @@ def sph2pob_iou_loss(pred, target, weight=None, avg_factor=None, mode="iou", eps
     return loss_weight * loss
 
 
+# ---- bbox coders (sphdet/bbox/coder/delta_xywh_sph_bbox_coder.py:117-262, delta_xywha_rsph_bbox_coder.py:117-268)
+def bbox2delta(proposals, gt, means=None, stds=None):
+    """(d_theta, d_phi, d_alpha, d_beta[, d_gamma]) of gt w.r.t. proposals: centre offsets in units of the proposal
+    size, log size ratios, gamma difference in radians; then (x - mean) / std.  Sizes clipped at 1e-7.
+    The reference casts both inputs to float32 (:139-140), whatever comes in."""
+    D = proposals.size(-1)
+    eps = 1e-7
+    proposals, gt = proposals.float(), gt.float()
+    px, py = proposals[..., 0], proposals[..., 1]
+    pw, ph = proposals[..., 2].clamp(min=eps), proposals[..., 3].clamp(min=eps)
+    gx, gy = gt[..., 0], gt[..., 1]
+    gw, gh = gt[..., 2].clamp(min=eps), gt[..., 3].clamp(min=eps)
+    cols = [(gx - px) / pw, (gy - py) / ph, torch.log(gw / pw), torch.log(gh / ph)]
+    if D == 5:
+        cols.append(torch.deg2rad(gt[..., 4] - proposals[..., 4]))
+    deltas = torch.stack(cols, dim=-1)
+    means = deltas.new_tensor(means if means is not None else [0.0] * D)
+    stds = deltas.new_tensor(stds if stds is not None else [1.0] * D)
+    return (deltas - means) / stds
+
+
+def delta2bbox(rois, deltas, means=None, stds=None, wh_ratio_clip=16 / 1000, clip_border=True, add_ctr_clamp=False,
+               ctr_clamp=32):
+    """Inverse of bbox2delta with the reference's clamps: |d_size| <= |log(wh_ratio_clip)| (only from above with
+    add_ctr_clamp, which also clamps the centre shift to +-ctr_clamp), then -- clip_border -- theta into
+    [1e-7, 360 - 1e-7], phi / alpha / beta into [1e-7, 180 - 1e-7], gamma into [-90 + 1e-7, 90 - 1e-7]."""
+    D = rois.size(-1)
+    eps = 1e-7
+    means = deltas.new_tensor(means if means is not None else [0.0] * D)
+    stds = deltas.new_tensor(stds if stds is not None else [1.0] * D)
+    d = deltas * stds + means
+    dxy_wh = rois[:, 2:4] * d[:, :2]
+    max_ratio = abs(math.log(wh_ratio_clip))
+    if add_ctr_clamp:
+        dxy_wh = dxy_wh.clamp(min=-ctr_clamp, max=ctr_clamp)
+        dwh = d[:, 2:4].clamp(max=max_ratio)
+    else:
+        dwh = d[:, 2:4].clamp(min=-max_ratio, max=max_ratio)
+    gxy = rois[:, :2] + dxy_wh
+    gwh = rois[:, 2:4] * dwh.exp()
+    cols = [gxy, gwh]
+    if D == 5:
+        cols.append((rois[:, 4] + torch.rad2deg(d[:, 4]))[:, None])
+    b = torch.cat(cols, dim=-1)
+    if clip_border:
+        lo = [eps, eps, eps, eps, -90 + eps][:D]
+        hi = [360 - eps, 180 - eps, 180 - eps, 180 - eps, 90 - eps][:D]
+        b = torch.stack([b[:, k].clamp(min=lo[k], max=hi[k]) for k in range(D)], dim=-1)
+    return b
+
+
+def decode_iou_loss(anchors, deltas, target, weight=None, avg_factor=None, mode="iou", reduction="mean", loss_weight=1.0,
+                    **coder):
+    """What the head does with reg_decoded_bbox=True (sphdet/models/heads/sph_retina_head.py:252-265):
+    bbox_coder.decode(anchors, bbox_pred) -> Sph2PobIoULoss(pred, target, weight, avg_factor)."""
+    return sph2pob_iou_loss(delta2bbox(anchors, deltas, **coder), target, weight=weight, avg_factor=avg_factor, mode=mode,
+                            reduction=reduction, loss_weight=loss_weight)
+
+
 # --------------------------------------------------------------------------- #
 # spherical NMS (sphdet/bbox/nms/sph_nms.py:22-74)
 # --------------------------------------------------------------------------- #

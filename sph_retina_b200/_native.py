@@ -18,7 +18,7 @@ EDGE = {"arc": 0, "chord": 1, "tangent": 2}
 ANGLE = {"equator": 0, "project": 1}
 
 SPHK_OK = 0
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _c_float_p = ctypes.c_void_p  # raw device addresses
 _i64 = ctypes.c_int64
@@ -53,6 +53,17 @@ SIGNATURES = {
                             _c_float_p, ctypes.c_void_p]),
     "sphk_riou_fwd_bwd": (_int, [_c_float_p, _c_float_p, _i64, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
                                  ctypes.c_void_p]),
+    "sphk_coder_decode": (_int, [_c_float_p, _c_float_p, _i64, _int, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float),
+                                 ctypes.c_float, _int, _int, ctypes.c_float, _c_float_p, ctypes.c_void_p]),
+    "sphk_coder_decode_bwd": (_int, [_c_float_p, _c_float_p, _c_float_p, _i64, _int, ctypes.POINTER(ctypes.c_float),
+                                     ctypes.POINTER(ctypes.c_float), ctypes.c_float, _int, _int, ctypes.c_float, _c_float_p,
+                                     ctypes.c_void_p]),
+    "sphk_coder_encode": (_int, [_c_float_p, _c_float_p, _i64, _int, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float),
+                                 _c_float_p, ctypes.c_void_p]),
+    "sphk_decode_loss_partials": (_i64, [_i64]),
+    "sphk_decode_loss_reduce": (_int, [_c_float_p, _c_float_p, _c_float_p, _c_float_p, _int, _i64, _int,
+                                       ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), ctypes.c_float, _int, _int,
+                                       ctypes.c_float, ctypes.c_float, _c_float_p, _c_float_p, ctypes.c_void_p]),
     "sphk_nms_batched": (_int, [_c_float_p, ctypes.c_void_p, ctypes.c_void_p, _i32, _i32, _i32, _int, ctypes.c_float,
                                 ctypes.c_void_p, ctypes.c_void_p]),
     "sphk_probe_fp32": (_int, [_i32, _i32, _c_float_p, ctypes.c_void_p]),
@@ -308,6 +319,81 @@ def loss_reduce(pred, target, weight, scale, want_grad_pred=False, want_grad_tar
                                     _ptr(gt), _stream(pred)))
     launches += 1
     return partial, gp, gt
+
+
+def _host5(values, D, default):
+    v = list(values) if values is not None else [default] * D
+    if len(v) < D:
+        raise SphkError("coder: %d means/stds given for %d-column boxes" % (len(v), D))
+    return (ctypes.c_float * 5)(*([float(x) for x in v[:D]] + [default] * (5 - D)))
+
+
+def coder_decode(rois, deltas, means=None, stds=None, wh_ratio_clip=16 / 1000, clip_border=True, add_ctr_clamp=False,
+                 ctr_clamp=32, grad_out=None):
+    """delta2bbox(rois, deltas) [n, D]; with grad_out = d(total)/d(decoded) it returns d(total)/d(deltas) instead."""
+    global launches
+    rois, deltas = _boxes(rois, "rois"), _boxes(deltas, "deltas")
+    if rois.shape != deltas.shape:
+        raise SphkError("coder: rois %s and deltas %s differ in shape" % (tuple(rois.shape), tuple(deltas.shape)))
+    n, D, dev = rois.size(0), rois.size(1), rois.device
+    out = torch.empty_like(rois)
+    m, sd = _host5(means, D, 0.0), _host5(stds, D, 1.0)
+    with _on_device(dev):
+        if grad_out is None:
+            _check(lib.sphk_coder_decode(_ptr(rois), _ptr(deltas), n, D, m, sd, float(wh_ratio_clip), int(bool(clip_border)),
+                                         int(bool(add_ctr_clamp)), float(ctr_clamp), _ptr(out), _stream(rois)))
+        else:
+            grad_out = grad_out.to(device=dev, dtype=torch.float32).contiguous()
+            assert grad_out.shape == rois.shape
+            _check(lib.sphk_coder_decode_bwd(_ptr(rois), _ptr(deltas), _ptr(grad_out), n, D, m, sd, float(wh_ratio_clip),
+                                             int(bool(clip_border)), int(bool(add_ctr_clamp)), float(ctr_clamp), _ptr(out),
+                                             _stream(rois)))
+    launches += 1
+    return out
+
+
+def coder_encode(proposals, gt, means=None, stds=None):
+    """bbox2delta(proposals, gt) [n, D]."""
+    global launches
+    proposals, gt = _boxes(proposals, "proposals"), _boxes(gt, "gt")
+    if proposals.shape != gt.shape:
+        raise SphkError("coder: proposals %s and gt %s differ in shape" % (tuple(proposals.shape), tuple(gt.shape)))
+    n, D, dev = proposals.size(0), proposals.size(1), proposals.device
+    out = torch.empty_like(proposals)
+    with _on_device(dev):
+        _check(lib.sphk_coder_encode(_ptr(proposals), _ptr(gt), n, D, _host5(means, D, 0.0), _host5(stds, D, 1.0), _ptr(out),
+                                     _stream(proposals)))
+    launches += 1
+    return out
+
+
+def decode_loss_reduce(anchors, deltas, target, weight, scale, want_grad=True, means=None, stds=None, wh_ratio_clip=16 / 1000,
+                       clip_border=True, add_ctr_clamp=False, ctr_clamp=32):
+    """One launch for the head's regression loss with decoded boxes: per-CTA partial sums of weight * (1 - iou)
+    (loss = scale * partial.sum()) and d(loss)/d(deltas).  weight: None, [n] or [n, k] (row mean)."""
+    global launches
+    anchors, deltas, target = _boxes(anchors, "anchors"), _boxes(deltas, "deltas"), _boxes(target, "target")
+    if not (anchors.shape == deltas.shape == target.shape):
+        raise SphkError("decode+loss: anchors %s, deltas %s, target %s differ in shape" %
+                        (tuple(anchors.shape), tuple(deltas.shape), tuple(target.shape)))
+    n, D, dev = anchors.size(0), anchors.size(1), anchors.device
+    wcols = 0
+    if weight is not None:
+        weight = weight.to(device=dev, dtype=torch.float32).contiguous()
+        wcols = 1 if weight.dim() == 1 else weight.size(1)
+        if weight.size(0) != n or weight.dim() > 2:
+            raise SphkError("decode+loss: weight %s does not match %d rows" % (tuple(weight.shape), n))
+    partial = torch.empty(max(1, lib.sphk_decode_loss_partials(n)), dtype=torch.float32, device=dev)
+    if n == 0:
+        partial.zero_()
+    grad = torch.empty_like(deltas) if want_grad else None
+    with _on_device(dev):
+        _check(lib.sphk_decode_loss_reduce(_ptr(anchors), _ptr(deltas), _ptr(target), _ptr(weight), wcols, n, D,
+                                           _host5(means, D, 0.0), _host5(stds, D, 1.0), float(wh_ratio_clip),
+                                           int(bool(clip_border)), int(bool(add_ctr_clamp)), float(ctr_clamp), float(scale),
+                                           _ptr(partial), _ptr(grad), _stream(anchors)))
+    launches += 1
+    return partial, grad
 
 
 def obb_fwd(kind: str, b1, b2, edge="arc"):

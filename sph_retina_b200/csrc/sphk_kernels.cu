@@ -21,6 +21,7 @@
 #include <string.h>
 
 #include "../../include/sphk.h"
+#include "sphk_coder.cuh"
 #include "sphk_fast.cuh"
 #include "sphk_grad.cuh"
 #include "sphk_math.cuh"
@@ -782,6 +783,128 @@ k_riou_fwd_bwd(const float* __restrict__ obb1, const float* __restrict__ obb2, i
     if (grad_obb2) store_grad<5>(grad_obb2, i, g2, false);
 }
 
+// ---- box coders + the decode -> loss step of the head ---------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(kThreads)
+k_coder_decode(const float* __restrict__ rois, const float* __restrict__ deltas, const float* __restrict__ grad_out, int64_t n,
+               CoderParams cp, float* __restrict__ out, bool vec_ok) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    const RawBox roi = load_box<D>(rois, i, vec_ok), dl = load_box<D>(deltas, i, vec_ok);
+    const float d[5] = {dl.t, dl.p, dl.a, dl.b, dl.g};
+    uint32_t pass;
+    float jac[5], v[5];
+    const RawBox b = coder_decode(roi, d, D, cp, &pass, jac);
+    if (grad_out) {       // backward: out = d(total)/d(deltas)
+        const RawBox go = load_box<D>(grad_out, i, vec_ok);
+        const float g[5] = {go.t, go.p, go.a, go.b, go.g};
+        coder_decode_grad(g, pass, jac, D, v);
+    } else {
+        v[0] = b.t; v[1] = b.p; v[2] = b.a; v[3] = b.b; v[4] = b.g;
+    }
+    store_grad<D>(out, i, v, vec_ok);
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreads)
+k_coder_encode(const float* __restrict__ proposals, const float* __restrict__ gt, int64_t n, CoderParams cp,
+               float* __restrict__ out, bool vec_ok) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    float v[5];
+    coder_encode(load_box<D>(proposals, i, vec_ok), load_box<D>(gt, i, vec_ok), D, cp, v);
+    store_grad<D>(out, i, v, vec_ok);
+}
+
+// Persistent warps scan the rows 32 at a time: read the weight(s), zero the row's gradient, ballot-compact the rows
+// with a non-zero weight into a per-warp ring; 32 queued rows at a time go through decode + loss + backward.
+// The loss is accumulated per lane in a fixed order and reduced per CTA: deterministic for a given n.
+constexpr int kLossRing = 64;
+
+template <int D>
+__global__ void __launch_bounds__(kThreads)
+k_decode_loss(const float* __restrict__ anchors, const float* __restrict__ deltas, const float* __restrict__ target,
+              const float* __restrict__ weight, int wcols, int64_t n, CoderParams cp, float scale,
+              float* __restrict__ partial, float* __restrict__ grad) {
+    __shared__ int s_ring[kThreads / 32][kLossRing];
+    __shared__ float s_w[kThreads / 32][kLossRing];
+    __shared__ float s_sum[kThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nw = (int)gridDim.x * (kThreads / 32), wg = (int)blockIdx.x * (kThreads / 32) + warp;
+    const int chunks = (int)((n + 31) >> 5);
+    const unsigned lt = (1u << lane) - 1u;
+    int head = 0, tail = 0;
+    float acc = 0.0f;
+    int c = wg;
+#pragma unroll 1
+    for (;;) {
+#pragma unroll 1
+        while (c < chunks && tail - head < 32) {
+            const int64_t i = (int64_t)c * 32 + lane;
+            float w = 0.0f;
+            if (i < n) {
+                if (wcols == 0) {
+                    w = 1.0f;
+                } else {
+                    const float* q = weight + i * wcols;
+                    float sum = 0.0f;
+                    for (int k = 0; k < wcols; ++k) sum += __ldg(q + k);
+                    w = (wcols == 1) ? sum : sum / (float)wcols;
+                }
+            }
+            if (grad) {       // the chunk's 32 * D gradient floats, coalesced
+                const int64_t f0 = (int64_t)c * (32 * D), fend = n * D;
+#pragma unroll
+                for (int k = 0; k < D; ++k)
+                    if (f0 + k * 32 + lane < fend) grad[f0 + k * 32 + lane] = 0.0f;
+            }
+            const bool live = (i < n) && (w != 0.0f);
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, live);
+            if (live) {
+                const int slot = (tail + __popc(m & lt)) & (kLossRing - 1);
+                s_ring[warp][slot] = (int)i;
+                s_w[warp][slot] = w;
+            }
+            tail += __popc(m);
+            c += nw;
+        }
+        if (tail == head) break;                 // chunks used up and nothing queued
+        const int cnt = min(tail - head, 32);
+        __syncwarp();
+        const int row = s_ring[warp][(head + lane) & (kLossRing - 1)];
+        const float w = s_w[warp][(head + lane) & (kLossRing - 1)];
+        __syncwarp();
+        if (lane < cnt) {
+            const RawBox roi = load_box<D>(anchors, row, false), dl = load_box<D>(deltas, row, false);
+            const RawBox tg = load_box<D>(target, row, false);
+            const float d[5] = {dl.t, dl.p, dl.a, dl.b, dl.g};
+            uint32_t pass;
+            float jac[5], g1[5], g2[5], gd[5];
+            const RawBox pred = coder_decode(roi, d, D, cp, &pass, jac);
+            float iou;
+            if (grad) {
+                iou = sph2pob_iou_pair_grad(pred, tg, D, KIND_SPH2POB_STANDARD, EDGE_ARC, -w * scale, g1, g2);
+                coder_decode_grad(g1, pass, jac, D, gd);
+                store_grad<D>(grad, row, gd, false);
+            } else {
+                iou = sph2pob_iou_pair(pred, tg, D, KIND_SPH2POB_STANDARD, MODE_IOU, EDGE_ARC);
+            }
+            acc += w * (1.0f - iou);
+        }
+        head += cnt;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+    if (lane == 0) s_sum[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.0f;
+#pragma unroll
+        for (int k = 0; k < kThreads / 32; ++k) t += s_sum[k];
+        partial[blockIdx.x] = t;
+    }
+}
+
 // ---- NMS ---------------------------------------------------------------------------------------
 // One CTA per segment (the boxes of one (image, class) group, score-descending through `order`).
 // Pivots are taken 32 at a time.  For a block of 32 pivots every warp builds suppression words
@@ -1219,6 +1342,100 @@ int sphk_riou_fwd_bwd(const float* obb1, const float* obb2, int64_t n, float* io
     if (!obb1 || !obb2) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_riou_fwd_bwd: null OBB pointer");
     k_riou_fwd_bwd<<<blocks_for(n), kThreads, 0, (cudaStream_t)stream>>>(obb1, obb2, n, iou, grad_iou, grad_obb1, grad_obb2);
     SPHK_LAUNCH_CHECK("k_riou_fwd_bwd");
+    return SPHK_OK;
+}
+
+static int coder_params(const char* who, int D, const float* means, const float* stds, float wh_ratio_clip, int clip_border,
+                        int add_ctr_clamp, float ctr_clamp, CoderParams* cp) {
+    if (D != 4 && D != 5) return fail(SPHK_ERR_INVALID_ARGUMENT, "coder: D not in {4,5}");
+    if (!(wh_ratio_clip > 0.0f)) return fail(SPHK_ERR_INVALID_ARGUMENT, "coder: wh_ratio_clip must be positive");
+    for (int k = 0; k < 5; ++k) {
+        cp->mean[k] = (means && k < D) ? means[k] : 0.0f;
+        cp->stdv[k] = (stds && k < D) ? stds[k] : 1.0f;
+    }
+    cp->max_ratio = fabsf(logf(wh_ratio_clip));
+    cp->ctr_clamp = ctr_clamp;
+    cp->clip_border = clip_border ? 1 : 0;
+    cp->add_ctr_clamp = add_ctr_clamp ? 1 : 0;
+    (void)who;
+    return SPHK_OK;
+}
+
+static int coder_decode_impl(const float* rois, const float* deltas, const float* grad_out, int64_t n, int D, const float* means,
+                             const float* stds, float wh_ratio_clip, int clip_border, int add_ctr_clamp, float ctr_clamp,
+                             float* out, void* stream) {
+    CoderParams cp;
+    const int rc = coder_params("decode", D, means, stds, wh_ratio_clip, clip_border, add_ctr_clamp, ctr_clamp, &cp);
+    if (rc != SPHK_OK) return rc;
+    if (n < 0) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_coder_decode: n < 0");
+    if (n == 0) return SPHK_OK;
+    if (!rois || !deltas || !out) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_coder_decode: null pointer");
+    const bool v = aligned16(rois) && aligned16(deltas) && aligned16(out) && (!grad_out || aligned16(grad_out));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (D == 4) k_coder_decode<4><<<blocks_for(n), kThreads, 0, s>>>(rois, deltas, grad_out, n, cp, out, v);
+    else k_coder_decode<5><<<blocks_for(n), kThreads, 0, s>>>(rois, deltas, grad_out, n, cp, out, v);
+    SPHK_LAUNCH_CHECK("k_coder_decode");
+    return SPHK_OK;
+}
+
+int sphk_coder_decode(const float* rois, const float* deltas, int64_t n, int D, const float* means, const float* stds,
+                      float wh_ratio_clip, int clip_border, int add_ctr_clamp, float ctr_clamp, float* out, void* stream) {
+    return coder_decode_impl(rois, deltas, nullptr, n, D, means, stds, wh_ratio_clip, clip_border, add_ctr_clamp, ctr_clamp, out, stream);
+}
+
+int sphk_coder_decode_bwd(const float* rois, const float* deltas, const float* grad_out, int64_t n, int D, const float* means,
+                          const float* stds, float wh_ratio_clip, int clip_border, int add_ctr_clamp, float ctr_clamp,
+                          float* grad_deltas, void* stream) {
+    if (n > 0 && !grad_out) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_coder_decode_bwd: null grad_out");
+    return coder_decode_impl(rois, deltas, grad_out, n, D, means, stds, wh_ratio_clip, clip_border, add_ctr_clamp, ctr_clamp,
+                             grad_deltas, stream);
+}
+
+int sphk_coder_encode(const float* proposals, const float* gt, int64_t n, int D, const float* means, const float* stds,
+                      float* out, void* stream) {
+    CoderParams cp;
+    const int rc = coder_params("encode", D, means, stds, 1.0f, 0, 0, 0.0f, &cp);
+    if (rc != SPHK_OK) return rc;
+    if (n < 0) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_coder_encode: n < 0");
+    if (n == 0) return SPHK_OK;
+    if (!proposals || !gt || !out) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_coder_encode: null pointer");
+    const bool v = aligned16(proposals) && aligned16(gt) && aligned16(out);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (D == 4) k_coder_encode<4><<<blocks_for(n), kThreads, 0, s>>>(proposals, gt, n, cp, out, v);
+    else k_coder_encode<5><<<blocks_for(n), kThreads, 0, s>>>(proposals, gt, n, cp, out, v);
+    SPHK_LAUNCH_CHECK("k_coder_encode");
+    return SPHK_OK;
+}
+
+// grid of the fused decode + loss kernel: persistent warps, at most 2 CTAs per SM (~105 registers per thread),
+// at least 8 chunks of 32 rows per warp
+static int64_t decode_loss_grid(int64_t n) {
+    if (n <= 0) return 0;
+    const int64_t chunks = (n + 31) / 32, wpc = kThreads / 32;
+    int64_t g = (chunks + wpc * 8 - 1) / (wpc * 8);
+    const int64_t wave = 2ll * sm_count();
+    return g > wave ? wave : g;
+}
+
+int64_t sphk_decode_loss_partials(int64_t n) { return decode_loss_grid(n); }
+
+int sphk_decode_loss_reduce(const float* anchors, const float* deltas, const float* target, const float* weight,
+                            int weight_cols, int64_t n, int D, const float* means, const float* stds, float wh_ratio_clip,
+                            int clip_border, int add_ctr_clamp, float ctr_clamp, float scale, float* partial,
+                            float* grad_deltas, void* stream) {
+    CoderParams cp;
+    const int rc = coder_params("decode_loss", D, means, stds, wh_ratio_clip, clip_border, add_ctr_clamp, ctr_clamp, &cp);
+    if (rc != SPHK_OK) return rc;
+    if (n < 0 || n > 0x7FFFFFFFll) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_decode_loss_reduce: n < 0 or n >= 2^31");
+    if (n == 0) return SPHK_OK;
+    if (!anchors || !deltas || !target || !partial) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_decode_loss_reduce: null pointer");
+    if (weight_cols < 0 || weight_cols > 8 || (weight_cols > 0 && !weight) || (weight_cols == 0 && weight))
+        return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_decode_loss_reduce: weight / weight_cols mismatch (0 with NULL, else 1..8)");
+    const unsigned g = (unsigned)decode_loss_grid(n);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (D == 4) k_decode_loss<4><<<g, kThreads, 0, s>>>(anchors, deltas, target, weight, weight_cols, n, cp, scale, partial, grad_deltas);
+    else k_decode_loss<5><<<g, kThreads, 0, s>>>(anchors, deltas, target, weight, weight_cols, n, cp, scale, partial, grad_deltas);
+    SPHK_LAUNCH_CHECK("k_decode_loss");
     return SPHK_OK;
 }
 

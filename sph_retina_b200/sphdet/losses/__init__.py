@@ -1,3 +1,4 @@
-from .sph2pob_iou_loss import OBBIoULoss, Sph2PobIoULoss, SphIoULoss, sph2pob_iou, sph2pob_obbs, rotated_iou
+from .sph2pob_iou_loss import (OBBIoULoss, Sph2PobDecodedIoULoss, Sph2PobIoULoss, SphIoULoss, rotated_iou, sph2pob_iou,
+                               sph2pob_obbs)
 
-__all__ = ['Sph2PobIoULoss', 'SphIoULoss', 'OBBIoULoss', 'sph2pob_iou', 'sph2pob_obbs', 'rotated_iou']
+__all__ = ['Sph2PobIoULoss', 'Sph2PobDecodedIoULoss', 'SphIoULoss', 'OBBIoULoss', 'sph2pob_iou', 'sph2pob_obbs', 'rotated_iou']

@@ -230,6 +230,25 @@ class _SphLossBase(nn.Module):
         return self.loss_weight * _weight_reduce_loss(loss, weight, reduction, avg_factor)
 
 
+class _DecodedReducedLoss(torch.autograd.Function):
+    """scale * sum_i w_i (1 - iou(decode(anchor_i, delta_i), target_i)) and d/d(deltas) from ONE kernel launch."""
+
+    @staticmethod
+    def forward(ctx, anchors, deltas, target, weight, scale, coder_kw):
+        need = ctx.needs_input_grad[1]
+        partial, grad = _native.decode_loss_reduce(anchors.detach(), deltas.detach(), target.detach(),
+                                                   None if weight is None else weight.detach(), scale, want_grad=need, **coder_kw)
+        if need:
+            ctx.save_for_backward(grad)
+        ctx.in_dtype = deltas.dtype
+        return (partial.sum() * scale).to(deltas.dtype)
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        (grad,) = ctx.saved_tensors if ctx.needs_input_grad[1] else (None,)
+        return None, (None if grad is None else (grad * grad_loss.float()).to(ctx.in_dtype)), None, None, None, None
+
+
 class OBBIoULoss(_SphLossBase):
     """Name kept for parity with sph2pob_iou_loss.py:16; here it already includes the Sph2Pob transform
     (the reference applies it through the ``Sph2PobTransfrom`` class decorator)."""
@@ -255,3 +274,38 @@ class SphIoULoss(_SphLossBase):
         if mode != 'iou':
             raise NotImplementedError("SphIoULoss: the reference returns None for mode != 'iou'")
         super().__init__(mode, eps, reduction, loss_weight)
+
+
+@LOSSES.register_module()
+class Sph2PobDecodedIoULoss(Sph2PobIoULoss):
+    """``bbox_coder.decode`` + ``Sph2PobIoULoss`` of the head's regression branch in one step (SURVEY.md 8f row 2;
+    sphdet/models/heads/sph_retina_head.py:252-265 with reg_decoded_bbox=True):
+
+        loss_bbox = self.loss_bbox.forward_decoded(self.bbox_coder, anchors, bbox_pred, bbox_targets, bbox_weights,
+                                                   avg_factor=num_total_samples)
+
+    equals ``self.loss_bbox(self.bbox_coder.decode(anchors, bbox_pred), bbox_targets, bbox_weights, avg_factor=...)``.
+    The head calls it on ALL anchors of the batch with zero weights for the negatives; for mode 'iou' one kernel reads
+    the weights, skips the zero rows and runs decode, transform, IoU and the whole backward for the others.  The plain
+    ``forward(pred, target, ...)`` of ``Sph2PobIoULoss`` is inherited unchanged."""
+
+    def forward_decoded(self, bbox_coder, anchors, bbox_pred, target, weight=None, avg_factor=None, reduction_override=None,
+                        wh_ratio_clip=16 / 1000):
+        assert reduction_override in (None, 'none', 'mean', 'sum')
+        reduction = reduction_override if reduction_override else self.reduction
+        D = target.size(-1)
+        fused = (self.mode == 'iou' and reduction in ('mean', 'sum') and bbox_pred.is_cuda and bbox_pred.dim() == 2
+                 and bbox_pred.size(1) == D and bbox_pred.size(0) > 0 and not isinstance(avg_factor, torch.Tensor)
+                 and (weight is None or weight.dim() == 1 or weight.size(1) == D))
+        if not fused:
+            return self.forward(bbox_coder.decode(anchors, bbox_pred, wh_ratio_clip=wh_ratio_clip), target, weight,
+                                avg_factor=avg_factor, reduction_override=reduction_override)
+        if avg_factor is None:
+            scale = self.loss_weight / bbox_pred.size(0) if reduction == 'mean' else self.loss_weight
+        elif reduction == 'mean':
+            scale = self.loss_weight / (avg_factor + torch.finfo(torch.float32).eps)
+        else:
+            raise ValueError('avg_factor can not be used with reduction="sum"')
+        # (no "any positive weight" test: that is a host sync; with all-zero weights the kernel returns exactly the
+        # zero loss and zero gradient the reference's early-out produces, sph2pob_iou_loss.py:36-39)
+        return _DecodedReducedLoss.apply(anchors, bbox_pred, target, weight, float(scale), bbox_coder.kernel_kwargs(wh_ratio_clip))

@@ -52,6 +52,7 @@ def _resolve(path, attr, fallback_name):
 IOU_CALCULATORS, IOU_CALCULATORS_IS_MMDET = _resolve("mmdet.core.bbox.iou_calculators.builder", "IOU_CALCULATORS",
                                                       "IoU calculator")
 LOSSES, LOSSES_IS_MMDET = _resolve("mmdet.models.builder", "LOSSES", "loss")
+BBOX_CODERS, BBOX_CODERS_IS_MMDET = _resolve("mmdet.core.bbox.builder", "BBOX_CODERS", "bbox_coder")
 
 
 def build_iou_calculator(cfg, default_args=None):
@@ -67,3 +68,11 @@ def build_loss(cfg):
         from mmdet.models.builder import build_loss as _b
         return _b(cfg)
     return LOSSES.build(cfg)
+
+
+def build_bbox_coder(cfg, default_args=None):
+    """mmdet/core/bbox/builder.py: build_bbox_coder."""
+    if BBOX_CODERS_IS_MMDET:
+        from mmcv.utils import build_from_cfg
+        return build_from_cfg(cfg, BBOX_CODERS, default_args)
+    return BBOX_CODERS.build(cfg, default_args)

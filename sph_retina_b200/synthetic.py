@@ -72,3 +72,31 @@ def nms_batch(images=64, per_image=1000, classes=80, box="bfov", seed=0):
     labels = torch.randint(0, classes, (images * per_image,))
     image_ids = torch.arange(images).repeat_interleave(per_image)
     return boxes.reshape(-1, D).contiguous(), scores, labels, image_ids
+
+
+def head_loss_batch(images=16, pos_fraction=0.0125, stds=(0.1, 0.1, 0.2, 0.2, 0.1), seed=7):
+    """The regression branch of the head's loss on a whole batch: every anchor of every image
+    [images * 98,208, 5] with its delta prediction, target and 2-D weight (sph_retina_head.py:252-265).  ~1.25 % of the
+    anchors are positives (config #2 measured 1,229 of 98,208): their target is a box near the anchor, their deltas the
+    encoding of that target plus noise (a mid-training prediction, IoU ~ 0.6); negatives carry zero targets / weights."""
+    torch.manual_seed(seed)
+    anchors = retina_anchors().repeat(images, 1)
+    n = anchors.size(0)
+    pos = torch.rand(n) < pos_fraction
+    a = anchors[pos]
+    a = torch.cat([a[:, :2], a[:, 2:4].clamp(max=170.0), a[:, 4:]], dim=1)
+    k = int(pos.sum())
+    target = torch.zeros(n, 5)
+    tgt = a + torch.randn(k, 5) * torch.tensor([0.15, 0.15, 0.2, 0.2, 0.0]) * torch.cat([a[:, 2:4], a[:, 2:4], a[:, :1]], 1)
+    tgt[:, 4] = (torch.rand(k) - 0.5) * 90
+    tgt[:, 0] = tgt[:, 0].clamp(1, 359)
+    tgt[:, 1] = tgt[:, 1].clamp(1, 179)
+    tgt[:, 2:4] = tgt[:, 2:4].clamp(1, 175)
+    target[pos] = tgt
+    std = torch.tensor(stds)
+    enc = torch.stack([(tgt[:, 0] - a[:, 0]) / a[:, 2], (tgt[:, 1] - a[:, 1]) / a[:, 3], torch.log(tgt[:, 2] / a[:, 2]),
+                       torch.log(tgt[:, 3] / a[:, 3]), torch.deg2rad(tgt[:, 4] - a[:, 4])], dim=1) / std
+    deltas = torch.randn(n, 5) * 0.1
+    deltas[pos] = enc + torch.randn(k, 5) * 0.8
+    weight = pos.float()[:, None].expand(n, 5).contiguous()
+    return anchors.contiguous(), deltas.contiguous(), target.contiguous(), weight

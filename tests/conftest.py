@@ -38,7 +38,7 @@ def hostsim():
     src = os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")
     out_dir = os.path.join(ROOT, "tests", "hostsim", "_build")
     out = os.path.join(out_dir, "libhostsim.so")
-    deps = [src] + [os.path.join(ROOT, "sph_retina_b200", "csrc", f) for f in ("sphk_math.cuh", "sphk_fast.cuh", "sphk_grad.cuh")]
+    deps = [src] + [os.path.join(ROOT, "sph_retina_b200", "csrc", f) for f in ("sphk_math.cuh", "sphk_fast.cuh", "sphk_grad.cuh", "sphk_coder.cuh")]
     if not os.path.isfile(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         os.makedirs(out_dir, exist_ok=True)
         subprocess.check_call([_system_gxx(), "-O2", "-fPIC", "-shared", "-DSPHK_WITH_GRAD", "-ffp-contract=fast",
@@ -72,3 +72,14 @@ def degenerate_pairs(b1, b2, min_fov_deg=0.06):
     IoF of such a pair is ill-conditioned in ANY fp32 evaluation; these rows are checked at 1e-3."""
     b1, b2 = np.asarray(b1), np.asarray(b2)
     return (np.minimum(b1[:, 2:4].min(axis=1), b2[:, 2:4].min(axis=1)) < min_fov_deg)
+
+
+def grad_rows_ok(got, truth, ref32, live_rows, tol=1e-4):
+    """Row-wise gradient parity: relative L2 error <= tol against the reference's fp64 autograd, or no
+    worse than the reference's own fp32 autograd on that row.  Returns (ok[rows], rel[rows], rel32[rows])."""
+    got, truth, ref32 = (np.asarray(a, np.float64) for a in (got, truth, ref32))
+    den = np.sqrt((truth ** 2).sum(axis=1))
+    rel = np.sqrt(((got - truth) ** 2).sum(axis=1)) / np.maximum(den, 1e-30)
+    rel32 = np.sqrt(((ref32 - truth) ** 2).sum(axis=1)) / np.maximum(den, 1e-30)
+    live = np.asarray(live_rows, bool) & (den > 1e-12)
+    return ((rel <= tol) | (rel <= rel32))[live], rel[live], rel32[live]

@@ -4,6 +4,7 @@
 // C-ABI library and fails loudly without a GPU.
 #include "../../sph_retina_b200/csrc/sphk_math.cuh"
 #include "../../sph_retina_b200/csrc/sphk_fast.cuh"
+#include "../../sph_retina_b200/csrc/sphk_coder.cuh"
 #ifdef SPHK_WITH_GRAD
 #include "../../sph_retina_b200/csrc/sphk_grad.cuh"
 #endif
@@ -105,6 +106,35 @@ void hostsim_obbs(int kind, const float* b1, const float* b2, long P, int D, int
     }
 }
 
+static CoderParams make_coder(int D, const float* means, const float* stds, float wh_ratio_clip, int clip_border,
+                              int add_ctr_clamp, float ctr_clamp) {
+    CoderParams cp;
+    for (int k = 0; k < 5; ++k) { cp.mean[k] = (means && k < D) ? means[k] : 0.0f; cp.stdv[k] = (stds && k < D) ? stds[k] : 1.0f; }
+    cp.max_ratio = fabsf(logf(wh_ratio_clip));
+    cp.ctr_clamp = ctr_clamp; cp.clip_border = clip_border; cp.add_ctr_clamp = add_ctr_clamp;
+    return cp;
+}
+
+// box coders (csrc/sphk_coder.cuh): out = delta2bbox(rois, deltas) / bbox2delta(rois, gt)
+void hostsim_coder_decode(const float* rois, const float* deltas, long n, int D, const float* means, const float* stds,
+                          float wh_ratio_clip, int clip_border, int add_ctr_clamp, float ctr_clamp, float* out) {
+    const CoderParams cp = make_coder(D, means, stds, wh_ratio_clip, clip_border, add_ctr_clamp, ctr_clamp);
+    for (long i = 0; i < n; ++i) {
+        uint32_t pass; float jac[5];
+        const RawBox b = coder_decode(load_box(rois, i, D), deltas + i * D, D, cp, &pass, jac);
+        const float v[5] = {b.t, b.p, b.a, b.b, b.g};
+        for (int k = 0; k < D; ++k) out[i * D + k] = v[k];
+    }
+}
+void hostsim_coder_encode(const float* rois, const float* gt, long n, int D, const float* means, const float* stds, float* out) {
+    const CoderParams cp = make_coder(D, means, stds, 1.0f, 0, 0, 0.0f);
+    for (long i = 0; i < n; ++i) {
+        float v[5];
+        coder_encode(load_box(rois, i, D), load_box(gt, i, D), D, cp, v);
+        for (int k = 0; k < D; ++k) out[i * D + k] = v[k];
+    }
+}
+
 #ifdef SPHK_WITH_GRAD
 // fused loss forward/backward (standard transform): iou[P], g1[P,D], g2[P,D] for upstream grad_iou[P]
 void hostsim_loss_fwd_bwd(const float* b1, const float* b2, const float* grad_iou, long P, int D, float* iou,
@@ -115,6 +145,26 @@ void hostsim_loss_fwd_bwd(const float* b1, const float* b2, const float* grad_io
         iou[i] = sph2pob_iou_pair_grad(x, y, D, KIND_SPH2POB_STANDARD, EDGE_ARC, grad_iou[i], ga, gb);
         for (int k = 0; k < D; ++k) { g1[i * D + k] = ga[k]; g2[i * D + k] = gb[k]; }
     }
+}
+
+// the head's decode -> Sph2PobIoULoss step (k_decode_loss): returns sum_i w_i (1 - iou_i), gd = d(scale * that)/d(deltas)
+double hostsim_decode_loss(const float* anchors, const float* deltas, const float* target, const float* weight, long n, int D,
+                           const float* means, const float* stds, float wh_ratio_clip, int clip_border, int add_ctr_clamp,
+                           float ctr_clamp, float scale, float* gd) {
+    const CoderParams cp = make_coder(D, means, stds, wh_ratio_clip, clip_border, add_ctr_clamp, ctr_clamp);
+    double total = 0.0;
+    for (long i = 0; i < n; ++i) {
+        const float w = weight ? weight[i] : 1.0f;
+        for (int k = 0; k < D; ++k) gd[i * D + k] = 0.0f;
+        if (w == 0.0f) continue;
+        uint32_t pass; float jac[5], g1[5], g2[5], g[5];
+        const RawBox pred = coder_decode(load_box(anchors, i, D), deltas + i * D, D, cp, &pass, jac);
+        const float iou = sph2pob_iou_pair_grad(pred, load_box(target, i, D), D, KIND_SPH2POB_STANDARD, EDGE_ARC, -w * scale, g1, g2);
+        coder_decode_grad(g1, pass, jac, D, g);
+        for (int k = 0; k < D; ++k) gd[i * D + k] = g[k];
+        total += (double)w * (1.0 - (double)iou);
+    }
+    return total;
 }
 
 #endif

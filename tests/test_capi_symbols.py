@@ -24,7 +24,8 @@ def built_lib():
 def test_header_declares_the_expected_entry_points():
     names = declared_symbols()
     for must in ("sphk_iou_aligned", "sphk_iou_pairwise", "sphk_loss_fwd_bwd", "sphk_nms_batched", "sphk_obb_fwd",
-                 "sphk_obb_bwd", "sphk_riou_fwd_bwd", "sphk_last_error_string", "sphk_abi_version"):
+                 "sphk_obb_bwd", "sphk_riou_fwd_bwd", "sphk_coder_decode", "sphk_coder_encode", "sphk_decode_loss_reduce",
+                 "sphk_last_error_string", "sphk_abi_version"):
         assert must in names
 
 
@@ -33,7 +34,7 @@ def test_library_exports_every_declared_symbol(built_lib):
     for name in declared_symbols():
         assert hasattr(lib, name), "libsphk.so does not export %s" % name
     lib.sphk_abi_version.restype = ctypes.c_int
-    assert lib.sphk_abi_version() == 2
+    assert lib.sphk_abi_version() == 3
 
 
 def test_binding_covers_the_header(built_lib):

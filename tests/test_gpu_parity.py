@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import ROOT, degenerate_pairs, load_golden, within
+from conftest import ROOT, degenerate_pairs, grad_rows_ok, load_golden, within
 
 pytestmark = pytest.mark.gpu
 
@@ -533,6 +533,115 @@ def test_multiclass_nms_wrapper(api):
                                                 return_inds=True, box_version=4)
     assert dets.shape[1] == 5 and dets.shape[0] <= 100 and labels.shape[0] == dets.shape[0]
     assert bool((dets[:-1, -1] >= dets[1:, -1]).all()) and float(dets[:, -1].min()) > 0.3
+
+
+# ---- box coders and the fused decode -> loss step ---------------------------------
+@pytest.mark.parametrize("box", ["bfov", "rbfov"])
+def test_coder_golden(api, box):
+    from sph_retina_b200.sphdet.bbox.coder import DeltaXYWHASphBBoxCoder, DeltaXYWHSphBBoxCoder
+    from test_oracle_golden import coder_kwargs
+    g = load_golden("coder")
+    cls = DeltaXYWHSphBBoxCoder if box == "bfov" else DeltaXYWHASphBBoxCoder
+    anchors, deltas = cu(g[box + "_anchors"]), cu(g[box + "_deltas"])
+    keep_a, keep_d = anchors.clone(), deltas.clone()
+    for name in ("plain", "norm", "ctr", "noclip"):
+        kw = coder_kwargs(g, box, name)
+        ckw = {("target_" + k if k in ("means", "stds") else k): v for k, v in kw.items()}
+        coder = cls(**ckw)
+        dec = coder.decode(anchors, deltas)
+        np.testing.assert_allclose(dec.cpu().numpy(), g["%s_%s_decode_f64" % (box, name)], rtol=3e-6, atol=2e-5)
+        enc = coder.encode(anchors, cu(g["%s_%s_decode_f32" % (box, name)]))
+        np.testing.assert_allclose(enc.cpu().numpy(), g["%s_%s_encode_f32" % (box, name)], rtol=2e-5, atol=2e-5)
+        # backward of decode == autograd through the torch restatement (clamp semantics included)
+        d1 = deltas.clone().requires_grad_(True)
+        up = torch.randn_like(deltas)
+        (coder.decode(anchors, d1) * up).sum().backward()
+        d2 = deltas.double().clone().requires_grad_(True)
+        (O.delta2bbox(anchors.double(), d2, **kw) * up.double()).sum().backward()
+        np.testing.assert_allclose(d1.grad.cpu().numpy(), d2.grad.cpu().numpy(), rtol=1e-5, atol=1e-5)
+    assert torch.equal(anchors, keep_a) and torch.equal(deltas, keep_d)
+    # per-class deltas [N, C * D] share the roi (delta_xywh_sph_bbox_coder.py:238)
+    coder = cls()
+    D = anchors.size(1)
+    multi = torch.cat([deltas, deltas * 0.5, deltas * 0.0], dim=1)
+    out = coder.decode(anchors, multi)
+    assert out.shape == (anchors.size(0), 3 * D)
+    assert torch.equal(out[:, :D], coder.decode(anchors, deltas)) and torch.equal(out[:, 2 * D:], coder.decode(anchors, deltas * 0.0))
+    assert coder.decode(anchors[:0], deltas[:0]).shape[0] == 0
+
+
+@pytest.mark.parametrize("box", ["bfov", "rbfov"])
+def test_decoded_loss_fused(api, box):
+    """Sph2PobDecodedIoULoss.forward_decoded == Sph2PobIoULoss(coder.decode(...)) of the reference (golden: its own coder
+    + loss + autograd, fp64), for the fused one-launch path (mode iou) and the composed path (ciou)."""
+    from sph_retina_b200.sphdet.bbox.coder import DeltaXYWHASphBBoxCoder, DeltaXYWHSphBBoxCoder
+    from sph_retina_b200.sphdet.losses import Sph2PobDecodedIoULoss, Sph2PobIoULoss
+    g = load_golden("coder")
+    cls = DeltaXYWHSphBBoxCoder if box == "bfov" else DeltaXYWHASphBBoxCoder
+    coder = cls(target_means=tuple(g[box + "_means"].tolist()), target_stds=tuple(g[box + "_stds"].tolist()))
+    anchors, target, weight = cu(g[box + "_anchors"]), cu(g[box + "_target"]), cu(g[box + "_weight"])
+    npos = float((weight[:, 0] > 0).sum())
+    pos = (weight[:, 0] > 0).cpu().numpy()
+    for mode in ("iou", "ciou"):
+        L = Sph2PobDecodedIoULoss(mode=mode, loss_weight=1.5)
+        d = cu(g[box + "_loss_deltas"]).requires_grad_(True)
+        before = api.native.launches
+        loss = L.forward_decoded(coder, anchors, d, target, weight, avg_factor=npos)
+        if mode == "iou":
+            assert api.native.launches - before == 1            # one kernel for the whole step
+        loss.backward()
+        assert abs(float(loss.detach()) - float(g["%s_%s_loss_f64" % (box, mode)])) < 3e-5
+        ok, rel, rel32 = grad_rows_ok(d.grad.cpu().numpy(), g["%s_%s_gdeltas_f64" % (box, mode)],
+                                      g["%s_%s_gdeltas_f32" % (box, mode)], pos)
+        assert ok.mean() > 0.99 and np.median(rel) < 5e-6, (mode, ok.mean(), np.median(rel))
+        assert not bool(d.grad[~torch.from_numpy(pos).to(DEV)].any())
+        # == the two-step composition through the same kernels
+        d2 = cu(g[box + "_loss_deltas"]).requires_grad_(True)
+        two = Sph2PobIoULoss(mode=mode, loss_weight=1.5)(coder.decode(anchors, d2), target, weight, avg_factor=npos)
+        two.backward()
+        assert abs(float(two) - float(loss)) < 2e-6
+        np.testing.assert_allclose(d.grad.cpu().numpy(), d2.grad.cpu().numpy(), rtol=2e-4, atol=1e-8)
+    L = Sph2PobDecodedIoULoss(loss_weight=2.0)
+    # 1-D weights, no weights, sum reduction, all-zero weights (the reference's early-out), no grad
+    d = cu(g[box + "_loss_deltas"])
+    w1 = weight[:, 0].contiguous()
+    a = L.forward_decoded(coder, anchors, d, target, w1, avg_factor=npos)
+    b = L.forward_decoded(coder, anchors, d, target, weight, avg_factor=npos)
+    assert abs(float(a) - float(b)) < 1e-6
+    s1 = L.forward_decoded(coder, anchors, d, target, w1, reduction_override="sum")
+    assert abs(float(s1) - float(a) * npos) < 1e-3 * float(s1)
+    dense = L.forward_decoded(coder, anchors[pos.nonzero()[0]], d[pos.nonzero()[0]], target[pos.nonzero()[0]])
+    assert abs(float(dense) - float(a)) < 1e-5 * max(1.0, float(a))
+    dz = d.clone().requires_grad_(True)
+    z = L.forward_decoded(coder, anchors, dz, target, torch.zeros_like(weight), avg_factor=npos)
+    z.backward()
+    assert float(z) == 0.0 and not bool(dz.grad.any())
+
+
+def test_decoded_loss_full_batch_shape(api):
+    """The real call shape: 16 images x 98 208 anchors (RBFoV), ~1 % positives.  The fused step must equal the loss
+    restricted to the positive rows (zero-weight rows contribute nothing) and write a zero gradient everywhere else."""
+    from sph_retina_b200 import synthetic as S
+    from sph_retina_b200.sphdet.bbox.coder import DeltaXYWHASphBBoxCoder
+    from sph_retina_b200.sphdet.losses import Sph2PobDecodedIoULoss
+    anchors, deltas, target, weight = (t.to(DEV) for t in S.head_loss_batch(16))
+    n = anchors.size(0)
+    assert n == 16 * 98208
+    coder = DeltaXYWHASphBBoxCoder(target_stds=(0.1, 0.1, 0.2, 0.2, 0.1))
+    L = Sph2PobDecodedIoULoss(loss_weight=1.0)
+    pos = weight[:, 0] > 0
+    npos = float(pos.sum())
+    assert 0.002 * n < npos < 0.03 * n
+    d = deltas.clone().requires_grad_(True)
+    loss = L.forward_decoded(coder, anchors, d, target, weight, avg_factor=npos)
+    loss.backward()
+    dp = deltas[pos].clone().requires_grad_(True)
+    ref = L.forward_decoded(coder, anchors[pos], dp, target[pos], None, avg_factor=npos)
+    ref.backward()
+    assert abs(float(loss) - float(ref)) < 1e-5 * max(1.0, float(ref))
+    assert torch.allclose(d.grad[pos], dp.grad, rtol=1e-5, atol=1e-9)
+    assert not bool(d.grad[~pos].any())
+    assert 0.05 < float(loss) < 0.95
 
 
 # ---- full-size property checks (BASELINE.json configs) --------------------------------------------

@@ -9,7 +9,7 @@ import ctypes
 import numpy as np
 import pytest
 
-from conftest import degenerate_pairs, load_golden, within
+from conftest import degenerate_pairs, grad_rows_ok, load_golden, within
 
 fp = ctypes.POINTER(ctypes.c_float)
 
@@ -255,6 +255,49 @@ def test_fast_path_inside_the_quirk_zones(hostsim, c_oracle, fn):
                 assert (e > 1e-5).sum() <= 12 and e.max() < 1e-3, (fn, D, kind, (e > 1e-5).sum(), e.max(), int(np.argmax(e)))
             assert np.median(e_fast) < 2e-7
             assert (truth > 0.02).mean() > 0.9
+
+
+def _f5(v):
+    return (ctypes.c_float * 5)(*(list(v) + [0.0] * (5 - len(v)))) if v is not None else None
+
+
+@pytest.mark.parametrize("box", ["bfov", "rbfov"])
+def test_coder_and_decode_loss(hostsim, box):
+    """csrc/sphk_coder.cuh on the host: decode / encode of every coder variant against the reference's coder classes,
+    and the fused decode -> loss step (value and d/d(deltas)) against the reference's autograd."""
+    from test_oracle_golden import coder_kwargs
+    g = load_golden("coder")
+    anchors, deltas = np.ascontiguousarray(g[box + "_anchors"]), np.ascontiguousarray(g[box + "_deltas"])
+    n, D = anchors.shape
+    for name in ("plain", "norm", "ctr", "noclip"):
+        kw = coder_kwargs(g, box, name)
+        out = np.empty((n, D), np.float32)
+        hostsim.hostsim_coder_decode(anchors.ctypes.data_as(fp), deltas.ctypes.data_as(fp), ctypes.c_long(n), D,
+                                     _f5(kw.get("means")), _f5(kw.get("stds")), ctypes.c_float(16 / 1000),
+                                     int(kw.get("clip_border", True)), int(kw.get("add_ctr_clamp", False)),
+                                     ctypes.c_float(kw.get("ctr_clamp", 32)), out.ctypes.data_as(fp))
+        want = g["%s_%s_decode_f64" % (box, name)]
+        np.testing.assert_allclose(out, want, rtol=3e-6, atol=2e-5)
+        dec = np.ascontiguousarray(g["%s_%s_decode_f32" % (box, name)])
+        enc = np.empty((n, D), np.float32)
+        hostsim.hostsim_coder_encode(anchors.ctypes.data_as(fp), dec.ctypes.data_as(fp), ctypes.c_long(n), D,
+                                     _f5(kw.get("means")), _f5(kw.get("stds")), enc.ctypes.data_as(fp))
+        np.testing.assert_allclose(enc, g["%s_%s_encode_f32" % (box, name)], rtol=2e-5, atol=2e-5)
+    kw = coder_kwargs(g, box, "norm")
+    d2, target = np.ascontiguousarray(g[box + "_loss_deltas"]), np.ascontiguousarray(g[box + "_target"])
+    w = np.ascontiguousarray(g[box + "_weight"].mean(axis=1).astype(np.float32))
+    scale = 1.5 / (float((w > 0).sum()) + float(np.finfo(np.float32).eps))
+    gd = np.empty((n, D), np.float32)
+    hostsim.hostsim_decode_loss.restype = ctypes.c_double
+    total = hostsim.hostsim_decode_loss(anchors.ctypes.data_as(fp), d2.ctypes.data_as(fp), target.ctypes.data_as(fp),
+                                        w.ctypes.data_as(fp), ctypes.c_long(n), D, _f5(kw["means"]), _f5(kw["stds"]),
+                                        ctypes.c_float(16 / 1000), 1, 0, ctypes.c_float(32), ctypes.c_float(scale),
+                                        gd.ctypes.data_as(fp))
+    assert abs(total * scale - float(g[box + "_iou_loss_f64"])) < 2e-5
+    ok, rel, rel32 = grad_rows_ok(gd, g[box + "_iou_gdeltas_f64"], g[box + "_iou_gdeltas_f32"], w > 0)
+    assert ok.mean() > 0.99 and np.median(rel) < 3e-6, (ok.mean(), np.median(rel))
+    assert (rel > 1e-4).sum() <= 0.5 * (rel32 > 1e-4).sum() + 2
+    assert not gd[w == 0].any()
 
 
 @pytest.mark.parametrize("box", ["bfov", "rbfov"])

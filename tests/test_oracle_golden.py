@@ -119,6 +119,40 @@ def test_restatement_nms(box):
     assert keep.tolist() == g[box + "_keep_agnostic"].tolist()
 
 
+CODER_VARIANTS = (("plain", {}), ("norm", "norm"), ("ctr", "ctr"), ("noclip", "noclip"))
+
+
+def coder_kwargs(g, box, name):
+    means, stds = tuple(g[box + "_means"].tolist()), tuple(g[box + "_stds"].tolist())
+    return {"plain": {}, "norm": dict(means=means, stds=stds),
+            "ctr": dict(means=means, stds=stds, add_ctr_clamp=True, ctr_clamp=8),
+            "noclip": dict(stds=stds, clip_border=False)}[name]
+
+
+@pytest.mark.parametrize("box", ["bfov", "rbfov"])
+def test_restatement_coder(box):
+    """delta2bbox / bbox2delta and the head's decode -> Sph2PobIoULoss step against the reference's own coder classes."""
+    g = load_golden("coder")
+    anchors, deltas = torch.from_numpy(g[box + "_anchors"]).double(), torch.from_numpy(g[box + "_deltas"]).double()
+    for name, _ in CODER_VARIANTS:
+        kw = coder_kwargs(g, box, name)
+        dec = O.delta2bbox(anchors, deltas, **kw)
+        assert np.abs(dec.numpy() - g["%s_%s_decode_f64" % (box, name)]).max() < 1e-9, (box, name)
+        enc = O.bbox2delta(anchors, dec, means=kw.get("means"), stds=kw.get("stds"))
+        np.testing.assert_allclose(enc.numpy(), g["%s_%s_encode_f64" % (box, name)], rtol=1e-5, atol=1e-5)   # fp32 inside
+        dec32 = O.delta2bbox(anchors.float(), deltas.float(), **kw).numpy()
+        np.testing.assert_allclose(dec32, g["%s_%s_decode_f32" % (box, name)], rtol=2e-6, atol=1e-6)
+    target, weight = torch.from_numpy(g[box + "_target"]).double(), torch.from_numpy(g[box + "_weight"]).double()
+    kw = coder_kwargs(g, box, "norm")
+    for mode in ("iou", "ciou"):
+        d = torch.from_numpy(g[box + "_loss_deltas"]).double().requires_grad_(True)
+        loss = O.decode_iou_loss(anchors, d, target, weight, avg_factor=float((weight[:, 0] > 0).sum()), mode=mode,
+                                 loss_weight=1.5, **kw)
+        loss.backward()
+        assert abs(float(loss.detach()) - float(g["%s_%s_loss_f64" % (box, mode)])) < 1e-9
+        assert np.abs(d.grad.numpy() - g["%s_%s_gdeltas_f64" % (box, mode)]).max() < 1e-9
+
+
 # ---- the float64 C restatement (exact polygon clipping) ----------------------------------------
 def _c_aligned(lib, kind, b1, b2, mode=0, edge=0):
     b1, b2 = np.ascontiguousarray(b1, np.float32), np.ascontiguousarray(b2, np.float32)
