@@ -307,6 +307,44 @@ def other_configs(torch, native, dev, flush):
     G = S.generate_boxes(1024, alpha_range=(1, 100), beta_range=(1, 100), box="rbfov", seed=1).to(dev)
     ms = quick(torch, lambda: sph_max_overlaps(A, G), iters=3, warmup=1, flush=flush)
     out["sweep_1Mx1024_fused_max"] = {"ms": ms, "pairs_per_s": (1 << 30) / ms * 1e3}
+    del A, G
+    # configs[0] as a stream of calls: 8 input sets (288 MB > L2, nothing re-used between calls), the 8 calls captured in
+    # one CUDA graph -- no host launch gaps, no dirty L2 lines from a flush write
+    sets = [(S.generate_boxes(n, alpha_range=(1, 100), beta_range=(1, 100), box="bfov", seed=10 + 2 * i).to(dev),
+             S.generate_boxes(n, alpha_range=(1, 100), beta_range=(1, 100), box="bfov", seed=11 + 2 * i).to(dev)) for i in range(8)]
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for a, b in sets:
+            sph2pob_efficient_iou(a, b, is_aligned=True)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        keep = [sph2pob_efficient_iou(a, b, is_aligned=True) for a, b in sets]
+    ms = quick(torch, graph.replay) / len(sets)
+    out["aligned_1M_bfov_stream_of_calls"] = {"ms_per_call": ms, "pairs_per_s": n / ms * 1e3,
+                                              "how": "8 input sets (288 MB, larger than L2), 8 calls in one CUDA graph, no flush"}
+    del graph, keep, sets
+    # SURVEY.md 8f row 2 -- the regression branch of the head's loss on a whole batch: bbox_coder.decode on all
+    # 16 x 98,208 anchors + Sph2PobIoULoss(weight = 0 for the negatives) + backward to the deltas
+    from sph_retina_b200.sphdet.bbox.coder import DeltaXYWHASphBBoxCoder
+    from sph_retina_b200.sphdet.losses import Sph2PobDecodedIoULoss
+    anchors_b, deltas, target_b, weight = (t.to(dev) for t in S.head_loss_batch(IMAGES))
+    coder = DeltaXYWHASphBBoxCoder(target_stds=(0.1, 0.1, 0.2, 0.2, 0.1))
+    LD = Sph2PobDecodedIoULoss(mode="iou", loss_weight=1.0)
+    npos = float((weight[:, 0] > 0).sum())
+
+    def fused():
+        d = deltas.detach().requires_grad_(True)
+        LD.forward_decoded(coder, anchors_b, d, target_b, weight, avg_factor=npos).backward()
+
+    def two_step():
+        d = deltas.detach().requires_grad_(True)
+        L_ = Sph2PobIoULoss(mode="iou", loss_weight=1.0)
+        L_(coder.decode(anchors_b, d), target_b, weight, avg_factor=npos).backward()
+    ms_fused, ms_two = quick(torch, fused, iters=5, flush=flush), quick(torch, two_step, iters=5, flush=flush)
+    out["head_loss_16img"] = {"rows": anchors_b.size(0), "positives": int(npos), "fused_fwd_bwd_ms": ms_fused,
+                              "decode_then_loss_fwd_bwd_ms": ms_two, "rows_per_s_fused": anchors_b.size(0) / ms_fused * 1e3}
     return out
 
 
