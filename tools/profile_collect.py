@@ -1,0 +1,51 @@
+#!/usr/bin/env python
+"""Turns the scratch evidence of tools/profile_round.sh (gpurun_out/*_<tag>.*) into the tracked summaries under
+profiles/: bench lines, the ncu launch list, per-kernel counter summaries + detail CSVs, stall and hot-spot tables and
+traffic.json (dram bytes per launch of the dominant kernels, read by bench.py's roofline object).
+    python tools/profile_collect.py r01_v10"""
+import csv
+import io
+import json
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1]
+src, dst = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+for a, b in (("bench_%s.json" % tag, "bench_%s.json" % tag), ("bench_ref_%s.json" % tag, "bench_%s_reference_arm.json" % tag),
+             ("launches_%s.csv" % tag, "ncu_launches_%s.csv" % tag)):
+    if os.path.isfile(os.path.join(src, a)):
+        shutil.copy(os.path.join(src, a), os.path.join(dst, b))
+traffic = {}
+kernels = ["aligned", "aligned5", "assign", "sweep", "loss", "nms", "nms_agnostic", "assigner", "headloss"]
+for k in kernels:
+    rep = os.path.join(src, "prof_%s_%s.ncu-rep" % (k, tag))
+    if not os.path.isfile(rep):
+        continue
+    summ = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), rep], capture_output=True, text=True).stdout
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    tmp = os.path.join(src, "_raw_%s.csv" % k)
+    open(tmp, "w").write(raw)
+    stalls = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_stalls.py"), tmp], capture_output=True, text=True).stdout
+    open(os.path.join(dst, "ncu_%s_%s_summary.txt" % (k, tag)), "w").write(summ + "\nwarp stalls (cycles per issued instruction)\n" + stalls)
+    det = subprocess.run(["ncu", "-i", rep, "--page", "details", "--csv"], capture_output=True, text=True).stdout
+    open(os.path.join(dst, "ncu_%s_%s_details.csv" % (k, tag)), "w").write(det)
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr = rows[0]
+    r = rows[2]
+    rd, wr = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    units = rows[1]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    traffic[k] = float(r[rd].replace(",", "")) * scale.get(units[rd], 1.0) + float(r[wr].replace(",", "")) * scale.get(units[wr], 1.0)
+    kern = {"aligned": "k_iou_aligned2", "aligned5": "k_iou_aligned2", "assign": "k_iou_pairwise2", "sweep": "k_iou_pairwise2",
+            "loss": "k_loss", "nms": "k_nms", "nms_agnostic": "k_nms", "assigner": "k_iou_pairwise2", "headloss": "k_decode_loss"}[k]
+    if k in ("aligned", "assign", "sweep", "headloss"):
+        hot = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_hotspots.py"), rep,
+                              os.path.join(ROOT, "sph_retina_b200", "_lib", "libsphk.so"), kern, "--top", "45"], capture_output=True, text=True).stdout
+        open(os.path.join(dst, "ncu_%s_%s_hotspots.txt" % (k, tag)), "w").write(hot)
+traffic["source"] = ("ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, one launch "
+                     "(profiles/ncu_*_%s_details.csv)" % tag)
+json.dump(traffic, open(os.path.join(dst, "traffic.json"), "w"), indent=1)
+print(json.dumps(traffic, indent=1))

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Launches one hot-path kernel a few times on BASELINE-shaped synthetic input (for ncu captures).
-    python tools/run_kernel.py aligned|aligned5|loss|nms|nms_agnostic|sweep|assign [--iters 5]"""
+    python tools/run_kernel.py aligned|aligned5|loss|nms|nms_agnostic|sweep|assign|assigner|headloss [--iters 5]"""
 import argparse
 import os
 import sys
@@ -39,6 +39,17 @@ elif a.which == "sweep":
     A = S.generate_boxes(1 << 20, alpha_range=(1, 100), beta_range=(1, 100), box="rbfov", seed=0).to(dev)
     G = S.generate_boxes(1024, alpha_range=(1, 100), beta_range=(1, 100), box="rbfov", seed=1).to(dev)
     fn = lambda: sph_max_overlaps(A, G)
+elif a.which == "headloss":
+    from sph_retina_b200.sphdet.bbox.coder import DeltaXYWHASphBBoxCoder
+    from sph_retina_b200.sphdet.losses import Sph2PobDecodedIoULoss
+    anchors, deltas, target, weight = (t.to(dev) for t in S.head_loss_batch(16))
+    coder = DeltaXYWHASphBBoxCoder(target_stds=(0.1, 0.1, 0.2, 0.2, 0.1))
+    LD = Sph2PobDecodedIoULoss()
+    npos = float((weight[:, 0] > 0).sum())
+
+    def fn():
+        d = deltas.detach().requires_grad_(True)
+        LD.forward_decoded(coder, anchors, d, target, weight, avg_factor=npos).backward()
 elif a.which == "assigner":
     from sph_retina_b200.sphdet.assigners import SphMaxIoUAssigner
     gts, anchors = S.assignment_batch()
