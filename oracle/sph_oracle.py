@@ -495,6 +495,30 @@ def decode_iou_loss(anchors, deltas, target, weight=None, avg_factor=None, mode=
                             reduction=reduction, loss_weight=loss_weight)
 
 
+def get_bboxes_single(cls_score_list, bbox_pred_list, mlvl_priors, cfg, box_version=4, **coder):
+    """SphRetinaHead._get_bboxes_single + _bbox_post_process for one image (sph_retina_head.py:35-212) with sigmoid
+    classification, mmdet's filter_scores_and_topk (mmdet/core/utils/misc.py:143-152), the coder restatement above
+    and the greedy NMS below.  Returns (det_bboxes [K, D + 1], det_labels [K])."""
+    bbs, scs, lbs = [], [], []
+    for cls_score, bbox_pred, priors in zip(cls_score_list, bbox_pred_list, mlvl_priors):
+        bbox_pred = bbox_pred.permute(1, 2, 0).reshape(-1, box_version)
+        num_cls = cls_score.size(0) * cls_score.size(1) * cls_score.size(2) // bbox_pred.size(0)
+        scores = cls_score.permute(1, 2, 0).reshape(-1, num_cls).sigmoid()
+        valid = scores > cfg["score_thr"]
+        vs, vi = scores[valid], torch.nonzero(valid)
+        k = min(cfg["nms_pre"], vi.size(0))
+        vs, order = vs.sort(descending=True)
+        keep_idxs, labels = vi[order[:k]].unbind(dim=1)
+        bbs.append(delta2bbox(priors[keep_idxs], bbox_pred[keep_idxs], **coder))
+        scs.append(vs[:k])
+        lbs.append(labels)
+    bboxes, scores, labels = torch.cat(bbs), torch.cat(scs), torch.cat(lbs)
+    if bboxes.numel() == 0:
+        return torch.cat([bboxes, scores[:, None]], -1), labels
+    dets, keep = nms_batched(bboxes, scores, labels, cfg["nms"]["iou_threshold"])
+    return dets[:cfg["max_per_img"]], labels[keep][:cfg["max_per_img"]]
+
+
 # --------------------------------------------------------------------------- #
 # spherical NMS (sphdet/bbox/nms/sph_nms.py:22-74)
 # --------------------------------------------------------------------------- #

@@ -60,21 +60,27 @@ def sph_batched_nms(boxes, scores, idxs, nms_cfg, iou_calculator='sph2pob_effici
 
 
 def sph_batched_nms_images(boxes, scores, labels, image_ids, iou_threshold=0.5, num_images=None, num_classes=None,
-                           max_per_segment=None):
+                           max_per_segment=None, valid=None):
     """Test-time batch: one launch over every (image, class) segment of a whole batch (labels < 2**20,
     image ids < 2**11).  Returns the kept indices (into boxes), grouped by image and score-descending inside an image.
 
     With the three hints (batch size, number of classes, an upper bound of the boxes per (image, class) segment, e.g.
     nms_pre) the segment table is built densely on the device and the only host synchronisation left is the final
-    compaction of the kept indices."""
+    compaction of the kept indices.  ``valid`` (bool [M], needs the hints): boxes to leave out -- padded candidate lists
+    go in as they are; the invalid ones are parked behind the last segment and never looked at."""
     desc = _desc_score_key(scores)
     if num_images is None or num_classes is None or max_per_segment is None:
+        if valid is not None:
+            raise ValueError("valid= needs num_images, num_classes and max_per_segment")
         seg = (image_ids.long() << 20) | labels.long()
         keep = _keep_indices(boxes, scores, seg, iou_threshold, desc)
     else:
+        nseg = int(num_images) * int(num_classes)
         seg = image_ids.long() * int(num_classes) + labels.long()
+        if valid is not None:
+            seg = torch.where(valid, seg, seg.new_full((), nseg))
         key, order = torch.sort((seg << 32) | desc)
-        counts = torch.bincount(seg, minlength=int(num_images) * int(num_classes))
+        counts = torch.bincount(seg, minlength=nseg + 1)[:nseg]
         offsets = torch.zeros(counts.numel() + 1, dtype=torch.int32, device=scores.device)
         offsets[1:] = counts.cumsum(0)
         typical = max(1, (2 * boxes.size(0)) // max(1, counts.numel()))     # twice the mean segment length

@@ -599,7 +599,7 @@ def test_decoded_loss_fused(api, box):
         d2 = cu(g[box + "_loss_deltas"]).requires_grad_(True)
         two = Sph2PobIoULoss(mode=mode, loss_weight=1.5)(coder.decode(anchors, d2), target, weight, avg_factor=npos)
         two.backward()
-        assert abs(float(two) - float(loss)) < 2e-6
+        assert abs(float(two.detach()) - float(loss.detach())) < 2e-6
         np.testing.assert_allclose(d.grad.cpu().numpy(), d2.grad.cpu().numpy(), rtol=2e-4, atol=1e-8)
     L = Sph2PobDecodedIoULoss(loss_weight=2.0)
     # 1-D weights, no weights, sum reduction, all-zero weights (the reference's early-out), no grad
@@ -615,7 +615,7 @@ def test_decoded_loss_fused(api, box):
     dz = d.clone().requires_grad_(True)
     z = L.forward_decoded(coder, anchors, dz, target, torch.zeros_like(weight), avg_factor=npos)
     z.backward()
-    assert float(z) == 0.0 and not bool(dz.grad.any())
+    assert float(z.detach()) == 0.0 and not bool(dz.grad.any())
 
 
 def test_decoded_loss_full_batch_shape(api):
@@ -642,6 +642,54 @@ def test_decoded_loss_full_batch_shape(api):
     assert torch.allclose(d.grad[pos], dp.grad, rtol=1e-5, atol=1e-9)
     assert not bool(d.grad[~pos].any())
     assert 0.05 < float(loss) < 0.95
+
+
+# ---- test-time post-processing of the head ----------------------------------------
+def _head_outputs(B, C, D, seed):
+    from sph_retina_b200 import synthetic as S
+    strides, H, W, A = (32, 64, 128), 512, 1024, 9
+    priors_all = S.retina_anchors(H, W, strides, box="rbfov" if D == 5 else "bfov")
+    g = torch.Generator().manual_seed(seed)
+    cls, reg, priors, off = [], [], [], 0
+    for s in strides:
+        h, w = H // s, W // s
+        n = h * w * A
+        priors.append(priors_all[off:off + n].contiguous())
+        off += n
+        cls.append(torch.randn(B, A * C, h, w, generator=g) * 2.0 - 3.0)
+        reg.append(torch.randn(B, A * D, h, w, generator=g) * 0.3)
+    return cls, reg, priors
+
+
+@pytest.mark.parametrize("D", [4, 5])
+def test_head_post_processing_batch_and_single(api, D):
+    """get_bboxes_batch (one topk per level, one decode launch, one NMS launch for the batch) and get_bboxes_single
+    (the reference's per-image contract) against the CPU restatement of sph_retina_head.py:35-212 (float64 NMS)."""
+    from sph_retina_b200.sphdet.bbox.coder import DeltaXYWHASphBBoxCoder, DeltaXYWHSphBBoxCoder
+    from sph_retina_b200.sphdet.models.heads import get_bboxes_batch, get_bboxes_single
+    B, C = 3, 6
+    cls, reg, priors = _head_outputs(B, C, D, seed=3 + D)
+    cfg = dict(nms_pre=150, score_thr=0.05, nms=dict(type="nms", iou_threshold=0.5), max_per_img=60)
+    stds = (0.1, 0.1, 0.2, 0.2, 0.1)[:D]
+    coder = (DeltaXYWHSphBBoxCoder if D == 4 else DeltaXYWHASphBBoxCoder)(target_stds=stds)
+    cls_d, reg_d, pri_d = [t.to(DEV) for t in cls], [t.to(DEV) for t in reg], [t.to(DEV) for t in priors]
+    batch = get_bboxes_batch(cls_d, reg_d, pri_d, coder, cfg, box_version=D)
+    assert len(batch) == B
+    for b in range(B):
+        want_det, want_lab = O.get_bboxes_single([t[b].double() for t in cls], [t[b].double() for t in reg],
+                                                 [p.double() for p in priors], cfg, box_version=D, stds=stds)
+        single = get_bboxes_single([t[b] for t in cls_d], [t[b] for t in reg_d], pri_d, coder, cfg, box_version=D)
+        for name, (det, lab) in (("batch", batch[b]), ("single", single)):
+            assert det.shape == want_det.shape and 10 < det.size(0) <= cfg["max_per_img"], (name, b, det.shape, want_det.shape)
+            np.testing.assert_allclose(det.cpu().numpy(), want_det.numpy(), rtol=1e-4, atol=2e-4, err_msg="%s %d" % (name, b))
+            assert torch.equal(lab.cpu(), want_lab)
+            assert bool((det[:-1, -1] >= det[1:, -1]).all())
+    # nothing above the threshold in one image: that image comes back empty, the others are unaffected
+    for t in cls_d:
+        t[1] = -20.0
+    again = get_bboxes_batch(cls_d, reg_d, pri_d, coder, cfg, box_version=D)
+    assert again[1][0].shape == (0, D + 1) and again[1][1].numel() == 0
+    assert torch.equal(again[0][0], batch[0][0]) and torch.equal(again[2][1], batch[2][1])
 
 
 # ---- full-size property checks (BASELINE.json configs) --------------------------------------------
