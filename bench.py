@@ -283,8 +283,16 @@ def other_configs(torch, native, dev, flush):
                                                        max_per_segment=1000), iters=5, flush=flush)
     out["nms_64img_1000box_80cls"] = {"ms": ms, "images_per_s": 64 / ms * 1e3, "ms_with_shape_hints": ms_h,
                                       "images_per_s_with_shape_hints": 64 / ms_h * 1e3}
+    from sph_retina_b200.sphdet.bbox.nms import sph_nms_image_blocks
+    ms_d = quick(torch, lambda: sph_nms_image_blocks(boxes, scores, labels, 64, 80, 0.5, 100), iters=5, flush=flush)
+    out["nms_64img_1000box_80cls"].update({"ms_device_pipeline": ms_d, "images_per_s_device_pipeline": 64 / ms_d * 1e3,
+                                           "device_pipeline": "sphk_nms_images: per-image sort, per-segment NMS and per-image "
+                                                              "ordering in three launches, top-100 per image, no host sync"})
     ms = quick(torch, lambda: sph_batched_nms_images(boxes, scores, torch.zeros_like(labels), image_ids, 0.5), iters=5, flush=flush)
-    out["nms_64img_1000box_class_agnostic"] = {"ms": ms, "images_per_s": 64 / ms * 1e3}
+    zl = torch.zeros_like(labels)
+    ms_d = quick(torch, lambda: sph_nms_image_blocks(boxes, scores, zl, 64, 1, 0.5, 100), iters=5, flush=flush)
+    out["nms_64img_1000box_class_agnostic"] = {"ms": ms, "images_per_s": 64 / ms * 1e3, "ms_device_pipeline": ms_d,
+                                               "images_per_s_device_pipeline": 64 / ms_d * 1e3}
     # configs[1] again, but all 16 images' GT in ONE call (legal whenever the anchors are shared by the images, as in
     # RetinaNet: SURVEY.md 3.1 "same anchors for every image"): [16*32, 98208] in two launches instead of 32
     gts, anchors = S.assignment_batch(IMAGES, GTS)

@@ -192,6 +192,22 @@ int sphk_decode_loss_reduce(const float* anchors, const float* deltas, const flo
 int sphk_nms_batched(const float* boxes, const int32_t* order, const int32_t* seg_offsets, int32_t S,
                      int32_t max_seg_len, int32_t typical_seg_len, int D, float iou_threshold, uint8_t* keep, void* stream);
 
+/* The same NMS for a test-time batch laid out as `num_images` equal blocks of `per_image` candidates (what the head's
+ * post-processing produces: nms_pre candidates per level and image, sph_retina_head.py:169-212 then :35-101), with no
+ * host-side sort and no synchronisation: per image one CTA sorts (label, score descending) in shared memory and emits the
+ * (image, class) segments, `k_nms` runs on them, and a second per-image CTA orders the survivors of all classes by
+ * descending score.
+ *   boxes [M, D], scores [M], labels [M] int64 in [0, num_classes), M = num_images * per_image (<= 16384 per image)
+ *   valid [M] uint8 or NULL: 0 leaves a candidate out (padding, scores under score_thr)
+ *   out_idx   [num_images, max_out] int32: indices into boxes of the kept candidates of each image, score-descending
+ *             (equal scores: lower index first), -1 beyond the count -- max_out plays nms_cfg.max_num / max_per_img
+ *   out_count [num_images] int32
+ *   workspace sphk_nms_images_workspace_bytes(num_images, per_image, num_classes) bytes, 16-byte aligned */
+int64_t sphk_nms_images_workspace_bytes(int32_t num_images, int32_t per_image, int32_t num_classes);
+int sphk_nms_images(const float* boxes, const float* scores, const int64_t* labels, const uint8_t* valid, int32_t num_images,
+                    int32_t per_image, int32_t num_classes, int D, float iou_threshold, int32_t max_out, int32_t* out_idx,
+                    int32_t* out_count, void* workspace, void* stream);
+
 /* Measurement helpers (bench.py; no counterpart in the reference).
  * sphk_probe_fp32: FMA-chain microbenchmark that yields the FP32 CUDA-core peak the Sph2Pob kernels
  *   are bounded by (SURVEY.md 8d asks for a measured denominator): launches `blocks` x 256 threads,

@@ -66,6 +66,9 @@ SIGNATURES = {
                                        ctypes.c_float, ctypes.c_float, _c_float_p, _c_float_p, ctypes.c_void_p]),
     "sphk_nms_batched": (_int, [_c_float_p, ctypes.c_void_p, ctypes.c_void_p, _i32, _i32, _i32, _int, ctypes.c_float,
                                 ctypes.c_void_p, ctypes.c_void_p]),
+    "sphk_nms_images_workspace_bytes": (_i64, [_i32, _i32, _i32]),
+    "sphk_nms_images": (_int, [_c_float_p, _c_float_p, ctypes.c_void_p, ctypes.c_void_p, _i32, _i32, _i32, _int, ctypes.c_float,
+                               _i32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "sphk_probe_fp32": (_int, [_i32, _i32, _c_float_p, ctypes.c_void_p]),
     "sphk_set_dense": (_int, [_int]),
 }
@@ -458,6 +461,35 @@ def nms_batched(boxes, order, seg_offsets, max_seg_len: int, iou_threshold: floa
                                     float(iou_threshold), _ptr(keep), _stream(boxes)))
     launches += 1
     return keep
+
+
+def nms_images(boxes, scores, labels, num_images: int, num_classes: int, iou_threshold: float, max_out: int, valid=None):
+    """Greedy per-(image, class) NMS of a batch laid out as `num_images` equal blocks of candidates, entirely on the
+    device (three launches, no sort on the host side, no synchronisation).  Returns (idx [num_images, max_out] int32
+    into boxes, score-descending per image, -1 padded; count [num_images] int32)."""
+    global launches
+    boxes = _boxes(boxes, "boxes")
+    dev = boxes.device
+    M = boxes.size(0)
+    if num_images <= 0 or M % num_images != 0:
+        raise SphkError("nms_images: %d boxes are not %d equal blocks" % (M, num_images))
+    per_image = M // num_images
+    scores = scores.to(device=dev, dtype=torch.float32).contiguous()
+    labels = labels.to(device=dev, dtype=torch.int64).contiguous()
+    if scores.numel() != M or labels.numel() != M:
+        raise SphkError("nms_images: scores / labels do not match the boxes")
+    if valid is not None:
+        valid = valid.to(device=dev, dtype=torch.uint8).contiguous()
+        assert valid.numel() == M
+    out_idx = torch.empty((num_images, max_out), dtype=torch.int32, device=dev)
+    out_count = torch.empty(num_images, dtype=torch.int32, device=dev)
+    ws = _workspace(dev, lib.sphk_nms_images_workspace_bytes(num_images, per_image, num_classes))
+    with _on_device(dev):
+        _check(lib.sphk_nms_images(_ptr(boxes), _ptr(scores), _ptr(labels), _ptr(valid), num_images, per_image, num_classes,
+                                   boxes.size(1), float(iou_threshold), int(max_out), _ptr(out_idx), _ptr(out_count), _ptr(ws),
+                                   _stream(boxes)))
+    launches += 3
+    return out_idx, out_count
 
 
 def probe_fp32(blocks: int, iters: int, device) -> float:

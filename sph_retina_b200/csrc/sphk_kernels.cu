@@ -915,11 +915,11 @@ k_decode_loss(const float* __restrict__ anchors, const float* __restrict__ delta
 template <int D>
 __global__ void __launch_bounds__(1024)
 k_nms(const float* __restrict__ boxes, const int32_t* __restrict__ order, const int32_t* __restrict__ seg_offsets,
-      float thr, uint8_t* __restrict__ keep, int max_words, bool vec_ok) {
+      const int32_t* __restrict__ seg_len, float thr, uint8_t* __restrict__ keep, int max_words, bool vec_ok) {
     extern __shared__ uint32_t s_mem[];
     const int seg = blockIdx.x;
     const int start = seg_offsets[seg];
-    const int k = seg_offsets[seg + 1] - start;
+    const int k = seg_len ? seg_len[seg] : seg_offsets[seg + 1] - start;     // seg_len: segments need not be adjacent
     if (k <= 0) return;
     const int W = (k + 31) >> 5;
     if (W > max_words) {   // caller under-sized max_seg_len: refuse rather than overrun shared memory
@@ -961,6 +961,102 @@ k_nms(const float* __restrict__ boxes, const int32_t* __restrict__ order, const 
         __syncthreads();
     }
     for (int q = threadIdx.x; q < k; q += blockDim.x) keep[start + q] = ((removed[q >> 5] >> (q & 31)) & 1u) ? 0 : 1;
+}
+
+// ---- NMS of a batch laid out as equal blocks of K candidates per image: everything on the device ----------
+// k_img_sort    one CTA per image: 64-bit keys (label, score descending, position) sorted in shared memory (bitonic);
+//               writes `order` (indices into the boxes) and the (start, length) of every (image, class) segment
+// k_nms         unchanged, one CTA per (image, class) segment
+// k_img_collect one CTA per image: the survivors of all its classes, score-descending, the first max_out of them
+__device__ __forceinline__ uint32_t desc_score_bits(float sc) {
+    // ascending order of the result == descending order of the float (NaN ends up first, like torch.sort(descending=True))
+    const uint32_t b = __float_as_uint(sc);
+    const uint32_t asc = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    return ~asc;
+}
+
+__device__ __forceinline__ void bitonic_sort_u64(unsigned long long* s, int n) {     // n: a power of two
+    for (int k = 2; k <= n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const unsigned long long a = s[i], b = s[l];
+                    if ((a > b) == ((i & k) == 0)) { s[i] = b; s[l] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+k_img_sort(const float* __restrict__ scores, const int64_t* __restrict__ labels, const uint8_t* __restrict__ valid, int K, int Kp,
+           int C, int32_t* __restrict__ order, int32_t* __restrict__ seg_start, int32_t* __restrict__ seg_len) {
+    extern __shared__ unsigned long long s_keys[];           // [Kp] keys, then [C + 1] ints
+    int* s_cnt = reinterpret_cast<int*>(s_keys + Kp);
+    const int b = blockIdx.x;
+    const int64_t base = (int64_t)b * K;
+    for (int c = threadIdx.x; c <= C; c += blockDim.x) s_cnt[c] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < Kp; i += blockDim.x) {
+        unsigned long long key = ~0ull;
+        if (i < K) {
+            const int64_t lab = labels[base + i];
+            const bool ok = (!valid || valid[base + i]) && lab >= 0 && lab < C;
+            const unsigned long long l16 = ok ? (unsigned long long)lab : 0xFFFEull;     // left-out boxes: behind every class
+            key = (l16 << 48) | ((unsigned long long)desc_score_bits(scores[base + i]) << 16) | (unsigned long long)i;
+            if (ok) atomicAdd(&s_cnt[lab], 1);
+        }
+        s_keys[i] = key;
+    }
+    __syncthreads();
+    bitonic_sort_u64(s_keys, Kp);
+    for (int i = threadIdx.x; i < K; i += blockDim.x) order[base + i] = (int32_t)(base + (int64_t)(s_keys[i] & 0xFFFFull));
+    if (threadIdx.x < 32) {      // exclusive scan of the class counts by one warp
+        int run = 0;
+        for (int c0 = 0; c0 < C; c0 += 32) {
+            const int c = c0 + threadIdx.x;
+            const int v = (c < C) ? s_cnt[c] : 0;
+            int inc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                if ((int)threadIdx.x >= o) inc += t;
+            }
+            if (c < C) {
+                seg_start[(int64_t)b * C + c] = (int32_t)(base + run + inc - v);
+                seg_len[(int64_t)b * C + c] = v;
+            }
+            run += __shfl_sync(0xFFFFFFFFu, inc, 31);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+k_img_collect(const float* __restrict__ scores, const int32_t* __restrict__ order, const uint8_t* __restrict__ keep, int K, int Kp,
+              int max_out, int32_t* __restrict__ out_idx, int32_t* __restrict__ out_count) {
+    extern __shared__ unsigned long long s_keys[];
+    __shared__ int s_n;
+    const int b = blockIdx.x;
+    const int64_t base = (int64_t)b * K;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < Kp; i += blockDim.x) {
+        unsigned long long key = ~0ull;
+        if (i < K && keep[base + i] == 1) {
+            const int32_t idx = order[base + i];
+            key = ((unsigned long long)desc_score_bits(scores[idx]) << 32) | (unsigned long long)(uint32_t)idx;
+            atomicAdd(&s_n, 1);
+        }
+        s_keys[i] = key;
+    }
+    __syncthreads();
+    bitonic_sort_u64(s_keys, Kp);
+    const int n = min(s_n, max_out);
+    for (int i = threadIdx.x; i < max_out; i += blockDim.x)
+        out_idx[(int64_t)b * max_out + i] = (i < n) ? (int32_t)(s_keys[i] & 0xFFFFFFFFull) : -1;
+    if (threadIdx.x == 0) out_count[b] = n;
 }
 
 __global__ void __launch_bounds__(kThreads) k_probe_fp32(int iters, float* __restrict__ sink) {
@@ -1457,13 +1553,75 @@ int sphk_nms_batched(const float* boxes, const int32_t* order, const int32_t* se
     if (D == 4) {
         e = cudaFuncSetAttribute(k_nms<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_nms)");
-        k_nms<4><<<S, nt, smem, s>>>(boxes, order, seg_offsets, iou_threshold, keep, max_words, v);
+        k_nms<4><<<S, nt, smem, s>>>(boxes, order, seg_offsets, nullptr, iou_threshold, keep, max_words, v);
     } else {
         e = cudaFuncSetAttribute(k_nms<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_nms)");
-        k_nms<5><<<S, nt, smem, s>>>(boxes, order, seg_offsets, iou_threshold, keep, max_words, v);
+        k_nms<5><<<S, nt, smem, s>>>(boxes, order, seg_offsets, nullptr, iou_threshold, keep, max_words, v);
     }
     SPHK_LAUNCH_CHECK("k_nms");
+    return SPHK_OK;
+}
+
+int64_t sphk_nms_images_workspace_bytes(int32_t num_images, int32_t per_image, int32_t num_classes) {
+    if (num_images < 0 || per_image < 0 || num_classes < 0) return 0;
+    const int64_t M = (int64_t)num_images * per_image, S = (int64_t)num_images * num_classes;
+    return align16(M * 4) + align16(S * 4) + align16(S * 4) + align16(M);      // order, segment starts, lengths, keep flags
+}
+
+int sphk_nms_images(const float* boxes, const float* scores, const int64_t* labels, const uint8_t* valid, int32_t num_images,
+                    int32_t per_image, int32_t num_classes, int D, float iou_threshold, int32_t max_out, int32_t* out_idx,
+                    int32_t* out_count, void* workspace, void* stream) {
+    if (num_images < 0 || per_image < 0 || num_classes <= 0 || max_out < 0 || (D != 4 && D != 5))
+        return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_nms_images: bad sizes or D");
+    if (num_images == 0) return SPHK_OK;
+    if (!out_idx || !out_count) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_nms_images: null output pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (per_image == 0) {
+        cudaError_t e = cudaMemsetAsync(out_count, 0, (size_t)num_images * sizeof(int32_t), s);
+        if (e == cudaSuccess && max_out > 0) e = cudaMemsetAsync(out_idx, 0xFF, (size_t)num_images * max_out * sizeof(int32_t), s);
+        return e == cudaSuccess ? SPHK_OK : cuda_fail(e, "cudaMemsetAsync(nms outputs)");
+    }
+    if (!boxes || !scores || !labels || !workspace) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_nms_images: null pointer");
+    if (!aligned16(workspace)) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_nms_images: workspace must be 16-byte aligned");
+    if (per_image > 16384 || num_classes > 0xFFF0)
+        return fail(SPHK_ERR_UNSUPPORTED, "sphk_nms_images: more than 16384 candidates per image or 65520 classes; use sphk_nms_batched");
+    int Kp = 32;
+    while (Kp < per_image) Kp <<= 1;
+    const int64_t M = (int64_t)num_images * per_image, S = (int64_t)num_images * num_classes;
+    if (M > 0x7FFFFFFFll || S > 0x7FFFFFFFll) return fail(SPHK_ERR_UNSUPPORTED, "sphk_nms_images: batch too large");
+    char* w = (char*)workspace;
+    int32_t* order = (int32_t*)w;      w += align16(M * 4);
+    int32_t* seg_start = (int32_t*)w;  w += align16(S * 4);
+    int32_t* seg_len = (int32_t*)w;    w += align16(S * 4);
+    uint8_t* keep = (uint8_t*)w;
+    cudaError_t e = cudaMemsetAsync(keep, 0, (size_t)M, s);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(keep)");
+    const int nt_sort = Kp >= 1024 ? 1024 : Kp;
+    const size_t smem_sort = (size_t)Kp * 8 + ((size_t)num_classes + 1) * 4, smem_col = (size_t)Kp * 8;
+    if (smem_sort > 200u * 1024u) return fail(SPHK_ERR_UNSUPPORTED, "sphk_nms_images: per-image block does not fit shared memory");
+    e = cudaFuncSetAttribute(k_img_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sort);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_img_collect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_col);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_img_sort)");
+    k_img_sort<<<num_images, nt_sort, smem_sort, s>>>(scores, labels, valid, per_image, Kp, num_classes, order, seg_start, seg_len);
+    SPHK_LAUNCH_CHECK("k_img_sort");
+    const int max_words = (per_image + 31) / 32;
+    const size_t smem = (size_t)max_words * 33u * sizeof(uint32_t);
+    const int tl = (int)((2 * (int64_t)per_image) / num_classes) + 1;        // twice the mean segment length
+    const int nt = tl <= 64 ? 128 : (tl <= 256 ? 256 : (tl <= 512 ? 512 : 1024));
+    const bool v = aligned16(boxes);
+    if (D == 4) {
+        e = cudaFuncSetAttribute(k_nms<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_nms)");
+        k_nms<4><<<(unsigned)S, nt, smem, s>>>(boxes, order, seg_start, seg_len, iou_threshold, keep, max_words, v);
+    } else {
+        e = cudaFuncSetAttribute(k_nms<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_nms)");
+        k_nms<5><<<(unsigned)S, nt, smem, s>>>(boxes, order, seg_start, seg_len, iou_threshold, keep, max_words, v);
+    }
+    SPHK_LAUNCH_CHECK("k_nms");
+    k_img_collect<<<num_images, nt_sort, smem_col, s>>>(scores, order, keep, per_image, Kp, max_out, out_idx, out_count);
+    SPHK_LAUNCH_CHECK("k_img_collect");
     return SPHK_OK;
 }
 

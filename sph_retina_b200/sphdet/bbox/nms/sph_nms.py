@@ -89,6 +89,17 @@ def sph_batched_nms_images(boxes, scores, labels, image_ids, iou_threshold=0.5, 
     return keep[torch.argsort((image_ids[keep].long() << 32) | desc[keep])]
 
 
+def sph_nms_image_blocks(boxes, scores, labels, num_images, num_classes, iou_threshold=0.5, max_per_img=None, valid=None):
+    """Test-time NMS of a whole batch whose candidates come as `num_images` equal, contiguous blocks (what the head's
+    post-processing emits): sort, per-(image, class) suppression and the per-image score ordering all run on the device
+    (``sphk_nms_images``: three launches, no host synchronisation).  Returns ``(idx [num_images, max_per_img] int32,
+    count [num_images] int32)``: ``idx[b, :count[b]]`` are the kept boxes of image b, score-descending -- the same
+    boxes ``SphNMS`` keeps for that image (equal scores are ordered by index here, unspecified in the reference)."""
+    per_image = boxes.size(0) // max(1, num_images)
+    max_out = per_image if max_per_img is None else min(int(max_per_img), per_image)
+    return _native.nms_images(boxes, scores, labels, int(num_images), int(num_classes), iou_threshold, max(max_out, 1), valid)
+
+
 class SphNMS:
     """sph_nms.py:7-19.  ``iou_calculator`` other than 'sph2pob_efficient' select CPU/planar routines
     of the reference that are outside this path: refused loudly."""

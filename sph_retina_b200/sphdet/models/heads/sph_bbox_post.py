@@ -5,14 +5,15 @@ level sigmoid -> ``filter_scores_and_topk`` (mmdet/core/utils/misc.py:104-165) -
 
 The reference does this image by image, level by level: ~60 eager kernels, two host syncs per level (``nonzero``), and
 the Python NMS loop per image.  ``get_bboxes_batch`` takes the head outputs of the whole batch: per level ONE ``topk``
-over every image, one decode launch and one NMS launch for all images x levels x classes; the only host
-synchronisation is the final compaction of the kept detections.  ``get_bboxes_single`` keeps the reference's
+over every image, one decode launch and the device-side NMS pipeline (``sphk_nms_images``: sort, suppression, per-image
+ordering in three launches) for all images x levels x classes; the only host synchronisation is reading the per-image
+counts of the kept detections.  ``get_bboxes_single`` keeps the reference's
 per-image contract on top of the same kernels."""
 from __future__ import annotations
 
 import torch
 
-from ...bbox.nms.sph_nms import SphNMS, sph_batched_nms_images
+from ...bbox.nms.sph_nms import SphNMS, sph_batched_nms_images, sph_nms_image_blocks
 
 
 def filter_scores_and_topk(scores, score_thr, topk, results=None):
@@ -102,14 +103,19 @@ def get_bboxes_batch(cls_scores, bbox_preds, mlvl_priors, bbox_coder, cfg, box_v
     K = scores.size(1)
     boxes = bbox_coder.decode(torch.cat(pr, 1).reshape(-1, D), torch.cat(dl, 1).reshape(-1, D))     # one launch
     scores, labels = scores.reshape(-1), labels.reshape(-1)
-    image_ids = torch.arange(B, device=scores.device).repeat_interleave(K)
-    keep = sph_batched_nms_images(boxes, scores, labels, image_ids, iou_thr, num_images=B, num_classes=num_cls,
-                                  max_per_segment=K, valid=scores > score_thr)
-    counts = torch.bincount(image_ids[keep], minlength=B).tolist()          # the one host synchronisation
-    max_per_img = _cfg_get(cfg, 'max_per_img', K)
-    out, start = [], 0
-    for b in range(B):
-        sel = keep[start:start + min(counts[b], max_per_img)]
-        out.append((torch.cat([boxes[sel], scores[sel, None]], -1), labels[sel]))
-        start += counts[b]
-    return out
+    max_per_img = min(int(_cfg_get(cfg, 'max_per_img', K)), K)
+    if K <= 16384:
+        # sort, suppression and per-image ordering on the device; the one host synchronisation is reading the counts
+        idx, count = sph_nms_image_blocks(boxes, scores, labels, B, num_cls, iou_thr, max_per_img, valid=scores > score_thr)
+        counts = count.tolist()
+        sels = [idx[b, :counts[b]].long() for b in range(B)]
+    else:
+        image_ids = torch.arange(B, device=scores.device).repeat_interleave(K)
+        keep = sph_batched_nms_images(boxes, scores, labels, image_ids, iou_thr, num_images=B, num_classes=num_cls,
+                                      max_per_segment=K, valid=scores > score_thr)
+        counts = torch.bincount(image_ids[keep], minlength=B).tolist()
+        sels, start = [], 0
+        for b in range(B):
+            sels.append(keep[start:start + min(counts[b], max_per_img)])
+            start += counts[b]
+    return [(torch.cat([boxes[sel], scores[sel, None]], -1), labels[sel]) for sel in sels]
