@@ -201,7 +201,8 @@ int sphk_nms_batched(const float* boxes, const int32_t* order, const int32_t* se
  *   valid [M] uint8 or NULL: 0 leaves a candidate out (padding, scores under score_thr)
  *   out_idx   [num_images, max_out] int32: indices into boxes of the kept candidates of each image, score-descending
  *             (equal scores: lower index first), -1 beyond the count -- max_out plays nms_cfg.max_num / max_per_img
- *   out_count [num_images] int32
+ *   out_count [num_images] int32; -1 for an image that holds a wanted candidate whose label is outside
+ *             [0, num_classes): its result must not be used (the caller re-runs it through sphk_nms_batched)
  *   workspace sphk_nms_images_workspace_bytes(num_images, per_image, num_classes) bytes, 16-byte aligned */
 int64_t sphk_nms_images_workspace_bytes(int32_t num_images, int32_t per_image, int32_t num_classes);
 int sphk_nms_images(const float* boxes, const float* scores, const int64_t* labels, const uint8_t* valid, int32_t num_images,

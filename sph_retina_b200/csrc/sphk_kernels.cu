@@ -912,62 +912,6 @@ k_decode_loss(const float* __restrict__ anchors, const float* __restrict__ delta
 // columns j > i that are still alive; warp 0 then replays the greedy order inside the block with
 // plain register/shared-memory bit operations (no IoU, no block barrier per pivot).  Pivots and
 // columns already removed by earlier blocks are never evaluated.
-template <int D>
-__global__ void __launch_bounds__(1024)
-k_nms(const float* __restrict__ boxes, const int32_t* __restrict__ order, const int32_t* __restrict__ seg_offsets,
-      const int32_t* __restrict__ seg_len, float thr, uint8_t* __restrict__ keep, int max_words, bool vec_ok) {
-    extern __shared__ uint32_t s_mem[];
-    const int seg = blockIdx.x;
-    const int start = seg_offsets[seg];
-    const int k = seg_len ? seg_len[seg] : seg_offsets[seg + 1] - start;     // seg_len: segments need not be adjacent
-    if (k <= 0) return;
-    const int W = (k + 31) >> 5;
-    if (W > max_words) {   // caller under-sized max_seg_len: refuse rather than overrun shared memory
-        for (int q = threadIdx.x; q < k; q += blockDim.x) keep[start + q] = 0xFF;
-        return;
-    }
-    uint32_t* removed = s_mem;             // [W]
-    uint32_t* mask = s_mem + max_words;    // [32][W]
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    for (int w = threadIdx.x; w < W; w += blockDim.x) removed[w] = 0u;
-    __syncthreads();
-    for (int i0 = 0; i0 < k; i0 += 32) {
-        const int nb = min(32, k - i0);
-        const int w0 = i0 >> 5;
-        const int nw = W - w0;
-        const uint32_t dead_pivots = removed[w0];
-        for (int unit = warp; unit < nb * nw; unit += nwarps) {
-            const int pi = unit / nw, jw = w0 + unit % nw;
-            const int i = i0 + pi, j = (jw << 5) + lane;
-            bool sup = false;
-            if (!((dead_pivots >> pi) & 1u) && j < k && j > i && !((removed[jw] >> lane) & 1u)) {
-                const int bi = order[start + i], bj = order[start + j];
-                const RawBox x = load_box<D>(boxes, bi, vec_ok), y = load_box<D>(boxes, bj, vec_ok);
-                sup = pair_iou_any(boxes, bi, boxes, bj, x, y, D, KIND_SPH2POB_EFFICIENT, MODE_IOU, EDGE_ARC) > thr;
-            }
-            const uint32_t word = __ballot_sync(0xFFFFFFFFu, sup);
-            if (lane == 0) mask[pi * W + jw] = word;
-        }
-        __syncthreads();
-        if (warp == 0) {
-            for (int pi = 0; pi < nb; ++pi) {
-                const bool alive = !((removed[w0] >> pi) & 1u);
-                __syncwarp();
-                if (alive)
-                    for (int w = w0 + lane; w < W; w += 32) removed[w] |= mask[pi * W + w];
-                __syncwarp();
-            }
-        }
-        __syncthreads();
-    }
-    for (int q = threadIdx.x; q < k; q += blockDim.x) keep[start + q] = ((removed[q >> 5] >> (q & 31)) & 1u) ? 0 : 1;
-}
-
-// ---- NMS of a batch laid out as equal blocks of K candidates per image: everything on the device ----------
-// k_img_sort    one CTA per image: 64-bit keys (label, score descending, position) sorted in shared memory (bitonic);
-//               writes `order` (indices into the boxes) and the (start, length) of every (image, class) segment
-// k_nms         unchanged, one CTA per (image, class) segment
-// k_img_collect one CTA per image: the survivors of all its classes, score-descending, the first max_out of them
 __device__ __forceinline__ uint32_t desc_score_bits(float sc) {
     // ascending order of the result == descending order of the float (NaN ends up first, like torch.sort(descending=True))
     const uint32_t b = __float_as_uint(sc);
@@ -990,30 +934,159 @@ __device__ __forceinline__ void bitonic_sort_u64(unsigned long long* s, int n) {
     }
 }
 
+// `scores` != NULL: the segment arrives unordered (k_img_scatter) and is first put into (score descending, index
+// ascending) order by its own CTA, in shared memory (`sort_cap` keys; the box indices then stay there).
+template <int D>
 __global__ void __launch_bounds__(1024)
-k_img_sort(const float* __restrict__ scores, const int64_t* __restrict__ labels, const uint8_t* __restrict__ valid, int K, int Kp,
-           int C, int32_t* __restrict__ order, int32_t* __restrict__ seg_start, int32_t* __restrict__ seg_len) {
-    extern __shared__ unsigned long long s_keys[];           // [Kp] keys, then [C + 1] ints
-    int* s_cnt = reinterpret_cast<int*>(s_keys + Kp);
+k_nms(const float* __restrict__ boxes, int32_t* order, const int32_t* __restrict__ seg_offsets,
+      const int32_t* __restrict__ seg_len, const float* __restrict__ scores, int sort_cap, int32_t* __restrict__ bad_image,
+      int segs_per_image, float thr, uint8_t* __restrict__ keep, int max_words, bool vec_ok) {
+    extern __shared__ uint32_t s_mem[];
+    const int seg = blockIdx.x;
+    const int start = seg_offsets[seg];
+    const int k = seg_len ? seg_len[seg] : seg_offsets[seg + 1] - start;     // seg_len: segments need not be adjacent
+    if (k <= 0) return;
+    const int W = (k + 31) >> 5;
+    if (W > max_words) {   // caller under-sized max_seg_len: refuse rather than overrun shared memory
+        for (int q = threadIdx.x; q < k; q += blockDim.x) keep[start + q] = 0xFF;
+        return;
+    }
+    uint32_t* removed = s_mem;             // [W]
+    uint32_t* mask = s_mem + max_words;    // [32][W]
+    unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(s_mem + ((33 * max_words + 1) & ~1));   // [sort_cap]
+    bool idx_in_smem = false;
+    if (scores) {
+        int kp = 32;
+        while (kp < k) kp <<= 1;
+        if (kp == 32) {
+            // up to 32 candidates: one warp sorts them in registers (shuffle network), no block barrier per stage
+            if (threadIdx.x < 32) {
+                unsigned long long key = ~0ull;
+                if ((int)threadIdx.x < k) {
+                    const int32_t idx = order[start + threadIdx.x];
+                    key = ((unsigned long long)desc_score_bits(scores[idx]) << 32) | (unsigned long long)(uint32_t)idx;
+                }
+#pragma unroll
+                for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+                    for (int j = kk >> 1; j > 0; j >>= 1) {
+                        const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, key, j);
+                        const bool lower = (threadIdx.x & j) == 0, up = (threadIdx.x & kk) == 0;
+                        key = ((key > other) == (lower == up)) ? other : key;
+                    }
+                }
+                s_keys[threadIdx.x] = key;
+                if ((int)threadIdx.x < k) order[start + threadIdx.x] = (int32_t)(key & 0xFFFFFFFFull);
+            }
+            __syncthreads();
+            idx_in_smem = true;
+        } else if (kp <= sort_cap) {
+            for (int q = threadIdx.x; q < kp; q += blockDim.x) {
+                unsigned long long key = ~0ull;
+                if (q < k) {
+                    const int32_t idx = order[start + q];
+                    key = ((unsigned long long)desc_score_bits(scores[idx]) << 32) | (unsigned long long)(uint32_t)idx;
+                }
+                s_keys[q] = key;
+            }
+            __syncthreads();
+            bitonic_sort_u64(s_keys, kp);
+            for (int q = threadIdx.x; q < k; q += blockDim.x) order[start + q] = (int32_t)(s_keys[q] & 0xFFFFFFFFull);
+            idx_in_smem = true;
+        } else {
+            // longer than the sorting buffer (> 4096 candidates of one class in one image): not handled here; the image is
+            // reported as unusable (out_count = -1) and the caller takes the general path (sphk_nms_batched)
+            if (threadIdx.x == 0) bad_image[seg / segs_per_image] = 1;
+            return;
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int w = threadIdx.x; w < W; w += blockDim.x) removed[w] = 0u;
+    __syncthreads();
+    for (int i0 = 0; i0 < k; i0 += 32) {
+        const int nb = min(32, k - i0);
+        const int w0 = i0 >> 5;
+        const int nw = W - w0;
+        const uint32_t dead_pivots = removed[w0];
+        // Work units of this round, one warp each.  The diagonal word (the block's own 32 columns) only has the pairs
+        // pi < pj: they are enumerated as a flattened triangle, 32 pairs per unit, so that short segments -- where
+        // the diagonal word is all there is -- still run full warps.  Every other word is one (pivot, word) unit
+        // with lane = column.
+        const int tri = nb * (nb - 1) / 2, tri_units = (tri + 31) >> 5, units = tri_units + nb * (nw - 1);
+        for (int q = threadIdx.x; q < nb; q += blockDim.x) mask[q * W + w0] = 0u;
+        __syncthreads();
+        for (int unit = warp; unit < units; unit += nwarps) {
+            if (unit < tri_units) {
+                const int p = (unit << 5) + lane;
+                bool sup = false;
+                int pi = 0, pj = 0;
+                if (p < tri) {
+                    // row pi holds the pairs (pi, pi+1 .. nb-1); rows before it hold pi * (2 nb - pi - 1) / 2 pairs
+                    pi = (int)(((float)(2 * nb - 1) - sqrtf((float)((2 * nb - 1) * (2 * nb - 1) - 8 * p))) * 0.5f);
+                    while (pi > 0 && pi * (2 * nb - pi - 1) / 2 > p) --pi;
+                    while ((pi + 1) * (2 * nb - pi - 2) / 2 <= p) ++pi;
+                    pj = pi + 1 + (p - pi * (2 * nb - pi - 1) / 2);
+                    if (!((dead_pivots >> pi) & 1u) && !((dead_pivots >> pj) & 1u)) {
+                        const int bi = idx_in_smem ? (int)(uint32_t)s_keys[i0 + pi] : order[start + i0 + pi];
+                        const int bj = idx_in_smem ? (int)(uint32_t)s_keys[i0 + pj] : order[start + i0 + pj];
+                        const RawBox x = load_box<D>(boxes, bi, vec_ok), y = load_box<D>(boxes, bj, vec_ok);
+                        sup = pair_iou_any(boxes, bi, boxes, bj, x, y, D, KIND_SPH2POB_EFFICIENT, MODE_IOU, EDGE_ARC) > thr;
+                    }
+                }
+                if (sup) atomicOr(&mask[pi * W + w0], 1u << pj);
+            } else {
+                const int u = unit - tri_units;
+                const int pi = u / (nw - 1), jw = w0 + 1 + u % (nw - 1);
+                const int i = i0 + pi, j = (jw << 5) + lane;
+                bool sup = false;
+                if (!((dead_pivots >> pi) & 1u) && j < k && !((removed[jw] >> lane) & 1u)) {
+                    const int bi = idx_in_smem ? (int)(uint32_t)s_keys[i] : order[start + i];
+                    const int bj = idx_in_smem ? (int)(uint32_t)s_keys[j] : order[start + j];
+                    const RawBox x = load_box<D>(boxes, bi, vec_ok), y = load_box<D>(boxes, bj, vec_ok);
+                    sup = pair_iou_any(boxes, bi, boxes, bj, x, y, D, KIND_SPH2POB_EFFICIENT, MODE_IOU, EDGE_ARC) > thr;
+                }
+                const uint32_t word = __ballot_sync(0xFFFFFFFFu, sup);
+                if (lane == 0) mask[pi * W + jw] = word;
+            }
+        }
+        __syncthreads();
+        if (warp == 0) {
+            for (int pi = 0; pi < nb; ++pi) {
+                const bool alive = !((removed[w0] >> pi) & 1u);
+                __syncwarp();
+                if (alive)
+                    for (int w = w0 + lane; w < W; w += 32) removed[w] |= mask[pi * W + w];
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+    }
+    for (int q = threadIdx.x; q < k; q += blockDim.x) keep[start + q] = ((removed[q >> 5] >> (q & 31)) & 1u) ? 0 : 1;
+}
+
+// ---- NMS of a batch laid out as equal blocks of K candidates per image: everything on the device ----------
+// k_img_scatter one CTA per image: counts the candidates of every class (shared-memory atomics), scans the counts and
+//               scatters the candidates into their (image, class) segment of `order` -- a counting sort by label;
+//               the order inside a segment is left to the segment's own CTA
+// k_nms         one CTA per (image, class) segment: sorts its candidates by descending score, then suppresses
+// k_img_collect one CTA per image: the survivors of all its classes, compacted and sorted by descending score
+//               (bitonic in shared memory), the first max_out of them
+__global__ void __launch_bounds__(1024)
+k_img_scatter(const int64_t* __restrict__ labels, const uint8_t* __restrict__ valid, int K, int C, int32_t* __restrict__ order,
+              int32_t* __restrict__ seg_start, int32_t* __restrict__ seg_len, int32_t* __restrict__ bad_label) {
+    extern __shared__ int s_cnt[];           // [C] counts, then cursors
     const int b = blockIdx.x;
     const int64_t base = (int64_t)b * K;
-    for (int c = threadIdx.x; c <= C; c += blockDim.x) s_cnt[c] = 0;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) s_cnt[c] = 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < Kp; i += blockDim.x) {
-        unsigned long long key = ~0ull;
-        if (i < K) {
-            const int64_t lab = labels[base + i];
-            const bool ok = (!valid || valid[base + i]) && lab >= 0 && lab < C;
-            const unsigned long long l16 = ok ? (unsigned long long)lab : 0xFFFEull;     // left-out boxes: behind every class
-            key = (l16 << 48) | ((unsigned long long)desc_score_bits(scores[base + i]) << 16) | (unsigned long long)i;
-            if (ok) atomicAdd(&s_cnt[lab], 1);
-        }
-        s_keys[i] = key;
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+        const int64_t lab = labels[base + i];
+        const bool wanted = !valid || valid[base + i];
+        if (wanted && lab >= 0 && lab < C) atomicAdd(&s_cnt[lab], 1);
+        else if (wanted) bad_label[b] = 1;      // reported through out_count = -1: the caller must not trust this image
     }
     __syncthreads();
-    bitonic_sort_u64(s_keys, Kp);
-    for (int i = threadIdx.x; i < K; i += blockDim.x) order[base + i] = (int32_t)(base + (int64_t)(s_keys[i] & 0xFFFFull));
-    if (threadIdx.x < 32) {      // exclusive scan of the class counts by one warp
+    if (threadIdx.x < 32) {      // exclusive scan of the class counts by one warp; the counts become cursors
         int run = 0;
         for (int c0 = 0; c0 < C; c0 += 32) {
             const int c = c0 + threadIdx.x;
@@ -1027,36 +1100,106 @@ k_img_sort(const float* __restrict__ scores, const int64_t* __restrict__ labels,
             if (c < C) {
                 seg_start[(int64_t)b * C + c] = (int32_t)(base + run + inc - v);
                 seg_len[(int64_t)b * C + c] = v;
+                s_cnt[c] = run + inc - v;
             }
             run += __shfl_sync(0xFFFFFFFFu, inc, 31);
         }
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+        const int64_t lab = labels[base + i];
+        if ((!valid || valid[base + i]) && lab >= 0 && lab < C) order[base + atomicAdd(&s_cnt[lab], 1)] = (int32_t)(base + i);
+    }
 }
+
+constexpr int kSelBins = 2048;
 
 __global__ void __launch_bounds__(1024)
 k_img_collect(const float* __restrict__ scores, const int32_t* __restrict__ order, const uint8_t* __restrict__ keep, int K, int Kp,
-              int max_out, int32_t* __restrict__ out_idx, int32_t* __restrict__ out_count) {
+              int max_out, const int32_t* __restrict__ bad_label, int32_t* __restrict__ out_idx, int32_t* __restrict__ out_count) {
     extern __shared__ unsigned long long s_keys[];
-    __shared__ int s_n;
+    __shared__ int s_hist[kSelBins];
+    __shared__ int s_n, s_total, s_bin;
+    __shared__ unsigned s_kmin, s_kmax;
     const int b = blockIdx.x;
     const int64_t base = (int64_t)b * K;
-    if (threadIdx.x == 0) s_n = 0;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { s_n = 0; s_total = 0; s_bin = kSelBins; s_kmin = 0xFFFFFFFFu; s_kmax = 0u; }
+    for (int q = threadIdx.x; q < kSelBins; q += blockDim.x) s_hist[q] = 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < Kp; i += blockDim.x) {
-        unsigned long long key = ~0ull;
-        if (i < K && keep[base + i] == 1) {
-            const int32_t idx = order[base + i];
-            key = ((unsigned long long)desc_score_bits(scores[idx]) << 32) | (unsigned long long)(uint32_t)idx;
-            atomicAdd(&s_n, 1);
-        }
-        s_keys[i] = key;
+    // ---- pass A: how many survivors, and the range of their (descending-score) keys
+    for (int i0 = 0; i0 < K; i0 += blockDim.x) {
+        const int i = i0 + threadIdx.x;
+        const bool kept = i < K && keep[base + i] == 1;           // (positions no segment covers keep their initial 0)
+        const unsigned key = kept ? desc_score_bits(scores[order[base + i]]) : 0u;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, kept);
+        const unsigned lo = __reduce_min_sync(0xFFFFFFFFu, kept ? key : 0xFFFFFFFFu), hi = __reduce_max_sync(0xFFFFFFFFu, key);
+        if (lane == 0 && m) { atomicAdd(&s_total, __popc(m)); atomicMin(&s_kmin, lo); atomicMax(&s_kmax, hi); }
     }
     __syncthreads();
-    bitonic_sort_u64(s_keys, Kp);
-    const int n = min(s_n, max_out);
+    const int total = s_total;
+    const unsigned kmin = s_kmin, span = s_kmax - s_kmin;
+    // ---- selection (only when it pays): a histogram over the key range finds the bin that holds the max_out-th best
+    // score; only the survivors up to that bin are sorted
+    const bool select = total > max_out && total > 512 && span > 0u;
+    if (select) {
+        for (int i0 = 0; i0 < K; i0 += blockDim.x) {
+            const int i = i0 + threadIdx.x;
+            if (i < K && keep[base + i] == 1) {
+                const unsigned key = desc_score_bits(scores[order[base + i]]);
+                atomicAdd(&s_hist[(int)(((unsigned long long)(key - kmin) * (kSelBins - 1)) / span)], 1);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {          // first bin at which the running count reaches max_out
+            constexpr int per = kSelBins / 32;
+            int sum = 0;
+            for (int q = 0; q < per; ++q) sum += s_hist[lane * per + q];
+            int inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            int run = inc - sum;
+            if (run < max_out && inc >= max_out) {
+                for (int q = 0; q < per; ++q) {
+                    run += s_hist[lane * per + q];
+                    if (run >= max_out) { s_bin = lane * per + q; break; }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    const int bin_hi = s_bin;
+    // ---- compaction (one shared-memory atomic per warp) of the survivors [up to the boundary bin]
+    for (int i0 = 0; i0 < K; i0 += blockDim.x) {
+        const int i = i0 + threadIdx.x;
+        bool take = i < K && keep[base + i] == 1;
+        int32_t idx = 0;
+        unsigned key = 0u;
+        if (take) {
+            idx = order[base + i];
+            key = desc_score_bits(scores[idx]);
+            if (select) take = (int)(((unsigned long long)(key - kmin) * (kSelBins - 1)) / span) <= bin_hi;
+        }
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, take);
+        int slot = 0;
+        if (lane == 0 && m) slot = atomicAdd(&s_n, __popc(m));
+        slot = __shfl_sync(0xFFFFFFFFu, slot, 0) + __popc(m & ((1u << lane) - 1u));
+        if (take) s_keys[slot] = ((unsigned long long)key << 32) | (unsigned long long)(uint32_t)idx;
+    }
+    __syncthreads();
+    const int cnt = s_n;
+    int kp = 32;
+    while (kp < cnt) kp <<= 1;
+    for (int i = cnt + threadIdx.x; i < kp; i += blockDim.x) s_keys[i] = ~0ull;
+    __syncthreads();
+    bitonic_sort_u64(s_keys, kp);
+    const int n = min(total, max_out);
     for (int i = threadIdx.x; i < max_out; i += blockDim.x)
         out_idx[(int64_t)b * max_out + i] = (i < n) ? (int32_t)(s_keys[i] & 0xFFFFFFFFull) : -1;
-    if (threadIdx.x == 0) out_count[b] = n;
+    if (threadIdx.x == 0) out_count[b] = bad_label[b] ? -1 : n;
 }
 
 __global__ void __launch_bounds__(kThreads) k_probe_fp32(int iters, float* __restrict__ sink) {
@@ -1553,11 +1696,11 @@ int sphk_nms_batched(const float* boxes, const int32_t* order, const int32_t* se
     if (D == 4) {
         e = cudaFuncSetAttribute(k_nms<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_nms)");
-        k_nms<4><<<S, nt, smem, s>>>(boxes, order, seg_offsets, nullptr, iou_threshold, keep, max_words, v);
+        k_nms<4><<<S, nt, smem, s>>>(boxes, const_cast<int32_t*>(order), seg_offsets, nullptr, nullptr, 0, nullptr, 1, iou_threshold, keep, max_words, v);
     } else {
         e = cudaFuncSetAttribute(k_nms<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_nms)");
-        k_nms<5><<<S, nt, smem, s>>>(boxes, order, seg_offsets, nullptr, iou_threshold, keep, max_words, v);
+        k_nms<5><<<S, nt, smem, s>>>(boxes, const_cast<int32_t*>(order), seg_offsets, nullptr, nullptr, 0, nullptr, 1, iou_threshold, keep, max_words, v);
     }
     SPHK_LAUNCH_CHECK("k_nms");
     return SPHK_OK;
@@ -1566,7 +1709,8 @@ int sphk_nms_batched(const float* boxes, const int32_t* order, const int32_t* se
 int64_t sphk_nms_images_workspace_bytes(int32_t num_images, int32_t per_image, int32_t num_classes) {
     if (num_images < 0 || per_image < 0 || num_classes < 0) return 0;
     const int64_t M = (int64_t)num_images * per_image, S = (int64_t)num_images * num_classes;
-    return align16(M * 4) + align16(S * 4) + align16(S * 4) + align16(M);      // order, segment starts, lengths, keep flags
+    // order, segment starts, lengths, keep flags, per-image "label out of range" flags
+    return align16(M * 4) + align16(S * 4) + align16(S * 4) + align16(M) + align16((int64_t)num_images * 4);
 }
 
 int sphk_nms_images(const float* boxes, const float* scores, const int64_t* labels, const uint8_t* valid, int32_t num_images,
@@ -1594,33 +1738,38 @@ int sphk_nms_images(const float* boxes, const float* scores, const int64_t* labe
     int32_t* order = (int32_t*)w;      w += align16(M * 4);
     int32_t* seg_start = (int32_t*)w;  w += align16(S * 4);
     int32_t* seg_len = (int32_t*)w;    w += align16(S * 4);
-    uint8_t* keep = (uint8_t*)w;
-    cudaError_t e = cudaMemsetAsync(keep, 0, (size_t)M, s);
+    uint8_t* keep = (uint8_t*)w;       w += align16(M);
+    int32_t* bad = (int32_t*)w;
+    cudaError_t e = cudaMemsetAsync(keep, 0, (size_t)(align16(M) + align16((int64_t)num_images * 4)), s);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(keep)");
-    const int nt_sort = Kp >= 1024 ? 1024 : Kp;
-    const size_t smem_sort = (size_t)Kp * 8 + ((size_t)num_classes + 1) * 4, smem_col = (size_t)Kp * 8;
-    if (smem_sort > 200u * 1024u) return fail(SPHK_ERR_UNSUPPORTED, "sphk_nms_images: per-image block does not fit shared memory");
-    e = cudaFuncSetAttribute(k_img_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sort);
+    const int nt_img = Kp >= 1024 ? 1024 : Kp;
+    const size_t smem_sc = (size_t)num_classes * 4, smem_col = (size_t)Kp * 8;
+    e = cudaFuncSetAttribute(k_img_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sc);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_img_collect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_col);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_img_sort)");
-    k_img_sort<<<num_images, nt_sort, smem_sort, s>>>(scores, labels, valid, per_image, Kp, num_classes, order, seg_start, seg_len);
-    SPHK_LAUNCH_CHECK("k_img_sort");
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_img_scatter)");
+    k_img_scatter<<<num_images, nt_img, smem_sc, s>>>(labels, valid, per_image, num_classes, order, seg_start, seg_len, bad);
+    SPHK_LAUNCH_CHECK("k_img_scatter");
+    // k_nms: suppression words sized for the longest possible segment (a whole image); segments of up to sort_cap
+    // candidates are sorted in shared memory, longer ones in place in global memory
     const int max_words = (per_image + 31) / 32;
-    const size_t smem = (size_t)max_words * 33u * sizeof(uint32_t);
-    const int tl = (int)((2 * (int64_t)per_image) / num_classes) + 1;        // twice the mean segment length
-    const int nt = tl <= 64 ? 128 : (tl <= 256 ? 256 : (tl <= 512 ? 512 : 1024));
+    int sort_cap = 32;
+    while (sort_cap < per_image && sort_cap < 4096) sort_cap <<= 1;
+    const size_t smem = (size_t)((33 * max_words + 1) & ~1) * sizeof(uint32_t) + (size_t)sort_cap * 8;
+    // a 32-pivot round has 32 * k/32 (pivot, word) units, one warp each: CTA width for twice the mean segment length
+    const int tl = (int)((2 * (int64_t)per_image) / num_classes) + 1;
+    const int nt = num_classes >= 512 ? 512 : (tl <= 16 ? 128 : (tl <= 64 ? 256 : (tl <= 256 ? 512 : 1024)));   // >= 512: a cap, not a count
     const bool v = aligned16(boxes);
     if (D == 4) {
         e = cudaFuncSetAttribute(k_nms<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_nms)");
-        k_nms<4><<<(unsigned)S, nt, smem, s>>>(boxes, order, seg_start, seg_len, iou_threshold, keep, max_words, v);
+        k_nms<4><<<(unsigned)S, nt, smem, s>>>(boxes, order, seg_start, seg_len, scores, sort_cap, bad, num_classes, iou_threshold, keep, max_words, v);
     } else {
         e = cudaFuncSetAttribute(k_nms<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_nms)");
-        k_nms<5><<<(unsigned)S, nt, smem, s>>>(boxes, order, seg_start, seg_len, iou_threshold, keep, max_words, v);
+        k_nms<5><<<(unsigned)S, nt, smem, s>>>(boxes, order, seg_start, seg_len, scores, sort_cap, bad, num_classes, iou_threshold, keep, max_words, v);
     }
     SPHK_LAUNCH_CHECK("k_nms");
-    k_img_collect<<<num_images, nt_sort, smem_col, s>>>(scores, order, keep, per_image, Kp, max_out, out_idx, out_count);
+    k_img_collect<<<num_images, nt_img, smem_col, s>>>(scores, order, keep, per_image, Kp, max_out, bad, out_idx, out_count);
     SPHK_LAUNCH_CHECK("k_img_collect");
     return SPHK_OK;
 }

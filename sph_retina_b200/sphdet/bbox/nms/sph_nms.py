@@ -11,6 +11,9 @@ import torch
 from .... import _native
 
 
+_LABEL_CAP = 1024     # class ids the single-image fast path of sph_batched_nms covers (LVIS has 1203: general path)
+
+
 def _desc_score_key(scores):
     """int64 in [0, 2**32): ascending key order == descending float32 score (IEEE bit trick, no sort yet)."""
     b = scores.float().contiguous().view(torch.int32)
@@ -51,6 +54,14 @@ def sph_batched_nms(boxes, scores, idxs, nms_cfg, iou_calculator='sph2pob_effici
     assert boxes.size(1) in [4, 5]
     if boxes.size(0) == 0:
         return torch.cat([boxes, scores[:, None]], -1), boxes.new_zeros((0,), dtype=torch.long)
+    if boxes.size(0) <= 16384 and boxes.is_cuda:
+        # one image = one block of the device-side pipeline (sort, suppression, ordering: three launches); labels are
+        # taken to lie in [0, 1024) -- an image that breaks this reports count -1 and goes through the general path
+        idx, count = _native.nms_images(boxes, scores, idxs, 1, _LABEL_CAP, iou_threshold, max(int(max_num), 1))
+        n = int(count)                                       # the host synchronisation the caller needs anyway
+        if n >= 0:
+            keep = idx[0, :min(n, max_num)].long()
+            return torch.cat([boxes[keep], scores[keep, None].to(boxes.dtype)], -1), keep
     keep = _keep_indices(boxes, scores, idxs, iou_threshold)
     keep = keep.sort()[0]                                   # :49 nonzero() order
     kept_scores, inds = scores[keep].sort(descending=True)  # :51
@@ -94,7 +105,9 @@ def sph_nms_image_blocks(boxes, scores, labels, num_images, num_classes, iou_thr
     post-processing emits): sort, per-(image, class) suppression and the per-image score ordering all run on the device
     (``sphk_nms_images``: three launches, no host synchronisation).  Returns ``(idx [num_images, max_per_img] int32,
     count [num_images] int32)``: ``idx[b, :count[b]]`` are the kept boxes of image b, score-descending -- the same
-    boxes ``SphNMS`` keeps for that image (equal scores are ordered by index here, unspecified in the reference)."""
+    boxes ``SphNMS`` keeps for that image (equal scores are ordered by index here, unspecified in the reference).
+    ``count[b] == -1`` flags an image the pipeline does not cover (a label outside [0, num_classes), or more than 4096
+    candidates of one class): run that batch through :func:`sph_batched_nms_images` instead."""
     per_image = boxes.size(0) // max(1, num_images)
     max_out = per_image if max_per_img is None else min(int(max_per_img), per_image)
     return _native.nms_images(boxes, scores, labels, int(num_images), int(num_classes), iou_threshold, max(max_out, 1), valid)

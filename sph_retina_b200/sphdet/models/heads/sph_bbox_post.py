@@ -104,12 +104,16 @@ def get_bboxes_batch(cls_scores, bbox_preds, mlvl_priors, bbox_coder, cfg, box_v
     boxes = bbox_coder.decode(torch.cat(pr, 1).reshape(-1, D), torch.cat(dl, 1).reshape(-1, D))     # one launch
     scores, labels = scores.reshape(-1), labels.reshape(-1)
     max_per_img = min(int(_cfg_get(cfg, 'max_per_img', K)), K)
+    counts = None
     if K <= 16384:
         # sort, suppression and per-image ordering on the device; the one host synchronisation is reading the counts
         idx, count = sph_nms_image_blocks(boxes, scores, labels, B, num_cls, iou_thr, max_per_img, valid=scores > score_thr)
         counts = count.tolist()
-        sels = [idx[b, :counts[b]].long() for b in range(B)]
-    else:
+        if min(counts) >= 0:
+            sels = [idx[b, :counts[b]].long() for b in range(B)]
+        else:
+            counts = None          # an (image, class) segment beyond the device pipeline's sorting buffer: general path
+    if counts is None:
         image_ids = torch.arange(B, device=scores.device).repeat_interleave(K)
         keep = sph_batched_nms_images(boxes, scores, labels, image_ids, iou_thr, num_images=B, num_classes=num_cls,
                                       max_per_segment=K, valid=scores > score_thr)

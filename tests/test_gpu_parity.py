@@ -525,6 +525,22 @@ def test_nms_batch_of_images_equals_per_image(api):
         assert sorted(sel[k1].cpu().tolist()) == sorted(keep[image_ids[keep] == b].cpu().tolist())
 
 
+def test_nms_fast_path_hands_over_what_it_does_not_cover(api):
+    """One class with 4500 candidates (beyond the 4096-key sorting buffer of the device pipeline) and labels >= 1024:
+    SphNMS must silently take the general path and give the same answer."""
+    from sph_retina_b200 import synthetic as S
+    boxes, scores, labels, _ = (t.to(DEV) for t in S.nms_batch(1, 4500, 3, seed=9))
+    nms = api.nms.SphNMS()
+    one = torch.zeros_like(labels)
+    idx, count = api.native.nms_images(boxes, scores, one, 1, 1024, 0.5, 100)
+    assert int(count) == -1
+    idx, count = api.native.nms_images(boxes, scores, labels + 2000, 1, 1024, 0.5, 100)
+    assert int(count) == -1
+    d1, k1 = nms(boxes, scores, one, dict(iou_threshold=0.5))
+    d2, k2 = nms(boxes, scores, one + 7000, dict(iou_threshold=0.5))
+    assert torch.equal(k1, k2) and torch.equal(d1, d2) and 50 < k1.numel() < 4000
+
+
 @pytest.mark.parametrize("box", ["bfov", "rbfov"])
 def test_nms_image_blocks_equals_per_image_nms(api, box):
     """sphk_nms_images (device-side sort + per-segment NMS + per-image ordering) against SphNMS image by image, with
@@ -549,8 +565,12 @@ def test_nms_image_blocks_equals_per_image_nms(api, box):
                 assert int(count[b]) == 0
                 continue
             local = torch.nonzero(m).squeeze(1) + b * K
-            dets, keep = nms(boxes[local], scores[local], labels[local], dict(iou_threshold=0.5))
+            # labels >= 1024 take SphNMS off its own device-pipeline fast path: this is the general (sorted-key) path
+            dets, keep = nms(boxes[local], scores[local], labels[local] + 5000, dict(iou_threshold=0.5))
             want = local[keep]
+            dets2, keep2 = nms(boxes[local], scores[local], labels[local], dict(iou_threshold=0.5))     # fast path
+            assert torch.equal(scores[local][keep2], scores[local][keep]) and torch.equal(dets2[:, -1], dets[:, -1])
+            assert torch.equal(torch.sort(keep2)[0], torch.sort(keep)[0])
             if max_per_img is not None:
                 want = want[:max_per_img]
             assert got.numel() == want.numel(), (b, got.numel(), want.numel())
