@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Launches one hot-path kernel a few times on BASELINE-shaped synthetic input (for ncu captures).
-    python tools/run_kernel.py aligned|aligned5|loss|nms|nms_agnostic|sweep|assign|assigner|headloss [--iters 5]"""
+    python tools/run_kernel.py aligned|aligned5|loss|nms|nms_agnostic|nms_pipeline|sweep|assign|assigner|headloss [--iters 5]"""
 import argparse
 import os
 import sys
@@ -35,6 +35,10 @@ elif a.which in ("nms", "nms_agnostic"):
     if a.which == "nms_agnostic":
         labels = torch.zeros_like(labels)
     fn = lambda: sph_batched_nms_images(boxes, scores, labels, image_ids, 0.5)
+elif a.which == "nms_pipeline":
+    from sph_retina_b200.sphdet.bbox.nms import sph_nms_image_blocks
+    boxes, scores, labels, image_ids = (x.to(dev) for x in S.nms_batch(64, 1000, 80))
+    fn = lambda: sph_nms_image_blocks(boxes, scores, labels, 64, 80, 0.5, 100)
 elif a.which == "sweep":
     A = S.generate_boxes(1 << 20, alpha_range=(1, 100), beta_range=(1, 100), box="rbfov", seed=0).to(dev)
     G = S.generate_boxes(1024, alpha_range=(1, 100), beta_range=(1, 100), box="rbfov", seed=1).to(dev)
