@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SPHK_ABI_VERSION 3
+#define SPHK_ABI_VERSION 4
 
 enum sphk_status {
     SPHK_OK = 0,
@@ -144,6 +144,32 @@ int sphk_obb_bwd(int kind, const float* b1, const float* b2, int64_t n, int D, i
                  const float* grad_obb2, float* grad_b1, float* grad_b2, void* stream);
 int sphk_riou_fwd_bwd(const float* obb1, const float* obb2, int64_t n, float* iou, const float* grad_iou,
                       float* grad_obb1, float* grad_obb2, void* stream);
+
+/* The other regression losses on the Sph2Pob OBBs, forward and backward in ONE launch:
+ *   Sph2PobGDLoss (sphdet/losses/sph2pob_gd_loss.py:7-26; mmrotate 0.3.2 GDLoss: gwd, kld, jd, kld_symmax, kld_symmin),
+ *   Sph2PobKFLoss (sphdet/losses/sph2pob_kf_loss.py:8-26; mmrotate 0.3.2 KFLoss, decoded boxes swapped as at :26),
+ *   Sph2PobL1Loss (sphdet/losses/sph2pob_l1_loss.py:9-94; mmdet L1Loss on bbox2delta of the OBBs),
+ * each behind the Sph2PobTransfrom decorator (sphdet/losses/sph2pob_transform.py:11-37): jitter_1 -> transform ->
+ * jitter_2 per row.  L = 5 columns per row for SPHK_LOSS_L1, else 1.
+ *   fun      GD: 0 none, 1 log1p, 2 sqrt;  KF: 0 none, 1 ln, 2 exp
+ *   flags    GD: bit0 = normalize (gwd) / sqrt (kld family);  L1: bit0 encode, bit1 swap, bit2 angle_modifier='modulus'
+ *   tau, alpha  GDLoss;  beta, eps  KFLoss (mmrotate defaults 1/9, 1e-6)
+ *   transform   SPHK_KIND_SPH2POB_STANDARD (the decorator's default) or _EFFICIENT
+ *   upstream [n] (up_cols = 1), [n, L] (up_cols = L) or NULL (= 1): loss weights or d(total)/d(loss); times `scale`
+ *   loss     [n, L] unweighted elementwise loss, or NULL
+ *   partial  [sphk_loss_reduce_partials(n)] per-block sums of upstream * loss (without scale), or NULL
+ *   grad_pred / grad_target [n, D]: scale * sum_j upstream[i, j] * d(loss[i, j])/d(box), or NULL
+ * Rows whose upstream is entirely zero get a zero gradient and add nothing to `partial`. */
+#define SPHK_LOSS_GWD 0
+#define SPHK_LOSS_KLD 1
+#define SPHK_LOSS_JD 2
+#define SPHK_LOSS_KLD_SYMMAX 3
+#define SPHK_LOSS_KLD_SYMMIN 4
+#define SPHK_LOSS_KFIOU 5
+#define SPHK_LOSS_L1 6
+int sphk_obb_loss(int loss_kind, int fun, int flags, float tau, float alpha, float beta, float eps, int transform,
+                  const float* pred, const float* target, int64_t n, int D, const float* upstream, int up_cols, float scale,
+                  float* loss, float* partial, float* grad_pred, float* grad_target, void* stream);
 
 /* The spherical delta box coders: DeltaXYWHSphBBoxCoder (D = 4) and DeltaXYWHASphBBoxCoder (D = 5)
  * (sphdet/bbox/coder/delta_xywh_sph_bbox_coder.py:45-115,117-262; delta_xywha_rsph_bbox_coder.py:45-115,117-268).

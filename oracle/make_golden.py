@@ -11,6 +11,7 @@ to the GPU box; the reference does not.
 """
 from __future__ import annotations
 
+import json
 import os
 import sys
 import warnings
@@ -215,6 +216,69 @@ def golden_loss(R):
         print("loss", box, float(out["iou_loss_f64"].mean()))
 
 
+OTHER_LOSS_VARIANTS = {
+    # name: (class name, constructor kwargs)            -- SURVEY.md 8f row 3
+    "gwd": ("Sph2PobGDLoss", dict(loss_type="gwd")),
+    "kld": ("Sph2PobGDLoss", dict(loss_type="kld")),
+    "jd": ("Sph2PobGDLoss", dict(loss_type="jd")),
+    "kld_symmax": ("Sph2PobGDLoss", dict(loss_type="kld_symmax")),
+    "kld_symmin": ("Sph2PobGDLoss", dict(loss_type="kld_symmin")),
+    "gwd_sqrt_tau1_raw": ("Sph2PobGDLoss", dict(loss_type="gwd", fun="sqrt", tau=1.0, normalize=False)),
+    "gwd_alpha2_tau2": ("Sph2PobGDLoss", dict(loss_type="gwd", alpha=2.0, tau=2.0)),
+    "kld_none_tau1_nosqrt": ("Sph2PobGDLoss", dict(loss_type="kld", fun="none", tau=1.0, sqrt=False)),
+    "jd_nosqrt": ("Sph2PobGDLoss", dict(loss_type="jd", sqrt=False, alpha=0.5)),
+    "kf": ("Sph2PobKFLoss", dict()),
+    "kf_ln": ("Sph2PobKFLoss", dict(fun="ln")),
+    "kf_exp": ("Sph2PobKFLoss", dict(fun="exp")),
+    "l1": ("Sph2PobL1Loss", dict()),
+    "l1_swap": ("Sph2PobL1Loss", dict(swap=True)),
+    "l1_modulus": ("Sph2PobL1Loss", dict(angle_modifier="modulus")),
+    "l1_plain": ("Sph2PobL1Loss", dict(encode=False)),
+}
+
+
+def golden_other_losses(R):
+    """Sph2PobGDLoss / Sph2PobKFLoss / Sph2PobL1Loss through the reference's own subclasses and Sph2PobTransfrom decorator
+    (GDLoss / KFLoss underneath = oracle/mmrotate_losses.py, the absent mmrotate 0.3.2)."""
+    for box in ("bfov", "rbfov"):
+        D = 4 if box == "bfov" else 5
+        n = 1024
+        torch.manual_seed(53)
+        t = R.generate_boxes(n, alpha_range=(5, 100), beta_range=(5, 100), dtype="float", box=box)
+        p = (t + torch.randn(n, D) * torch.tensor([6, 6, 6, 6, 10.0])[:D]).clamp(min=1)
+        p[:16] = t[:16]                                  # identical rows
+        t[16:32] = 0                                     # the head's negatives carry all-zero targets
+        p[32:64] = (t[32:64] + torch.randn(32, D) * 0.05).clamp(min=1)
+        w1 = (torch.rand(n) > 0.3).float()
+        w2 = torch.rand(n, D) * (torch.rand(n, 1) > 0.3).float()
+        out = dict(pred=_np(p), target=_np(t), w1=_np(w1), w2=_np(w2), variants_json=np.array(json.dumps(OTHER_LOSS_VARIANTS)))
+        for name, (cls, kw) in OTHER_LOSS_VARIANTS.items():
+            for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+                L = getattr(R, cls)(reduction="sum", **kw)
+                pp = p.to(dt).clone().requires_grad_(True)
+                tt = t.to(dt).clone().requires_grad_(True)
+                if dt == torch.float64:
+                    with rh.float64_mode():
+                        el = L(pp, tt, reduction_override="none")
+                        el.sum().backward()
+                else:
+                    el = L(pp, tt, reduction_override="none")
+                    el.sum().backward()
+                out["%s_loss_%s" % (name, tag)] = _np(el)
+                out["%s_gpred_%s" % (name, tag)] = _np(pp.grad)
+                out["%s_gtarget_%s" % (name, tag)] = _np(tt.grad)
+            with rh.float64_mode():
+                L = getattr(R, cls)(loss_weight=2.0, **kw)
+                pd, td = p.double(), t.double()
+                out[name + "_red_mean"] = _np(L(pd, td))
+                out[name + "_red_w2_avg"] = _np(L(pd, td, w2.double(), avg_factor=77.0))
+                out[name + "_red_w2_sum"] = _np(L(pd, td, w2.double(), reduction_override="sum"))
+                if cls != "Sph2PobL1Loss":                # a 1-D weight cannot broadcast against the [n, 5] L1 loss
+                    out[name + "_red_w1_avg"] = _np(L(pd, td, w1.double(), avg_factor=123.0))
+        np.savez_compressed(os.path.join(OUT, "other_losses_%s.npz" % box), **out)
+        print("other losses", box, {k: float(out[k + "_loss_f64"].mean()) for k in OTHER_LOSS_VARIANTS})
+
+
 def golden_nms(R):
     out = {}
     for box in ("bfov", "rbfov"):
@@ -300,3 +364,4 @@ if __name__ == "__main__":
     golden_loss(R)
     golden_nms(R)
     golden_coder(R)
+    golden_other_losses(R)

@@ -162,11 +162,16 @@ def load_reference():
     mm_builder = types.ModuleType("mmdet.models.builder")
     mm_builder.LOSSES = _PassThroughRegistry("loss")
     mm_losses = types.ModuleType("mmdet.models.losses")
+    mm_losses.__path__ = []
     mm_losses.weighted_loss = losses_utils.weighted_loss
-    mm_losses.L1Loss = torch.nn.L1Loss
     sys.modules["mmdet.models"] = mm_models
     sys.modules["mmdet.models.builder"] = mm_builder
     sys.modules["mmdet.models.losses"] = mm_losses
+    sys.modules["mmdet.models.losses.utils"] = losses_utils
+    # the reference's vendored mmdet L1Loss (mmdet/models/losses/smooth_l1_loss.py:107-146), loaded under its package
+    # name so that its relative imports (..builder, .utils) resolve to the modules above
+    smooth_l1 = _load_file("mmdet.models.losses.smooth_l1_loss", "mmdet/models/losses/smooth_l1_loss.py")
+    mm_losses.L1Loss = smooth_l1.L1Loss
     mmrot = types.ModuleType("mmrotate")
     mmrot.__path__ = []
     mmrot_models = types.ModuleType("mmrotate.models")
@@ -180,8 +185,12 @@ def load_reference():
         def forward(self, *a, **k):
             raise NotImplementedError
     mmrot_losses.RotatedIoULoss = _Dummy
-    mmrot_losses.GDLoss = _Dummy
-    mmrot_losses.KFLoss = _Dummy
+    # mmrotate 0.3.2 is absent: GDLoss / KFLoss are the restatement in oracle/mmrotate_losses.py (parity UNPINNED at that
+    # boundary); the reference's own subclasses and its Sph2PobTransfrom decorator run on top of them unchanged
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import mmrotate_losses as _mmr
+    mmrot_losses.GDLoss = _mmr.GDLoss
+    mmrot_losses.KFLoss = _mmr.KFLoss
     sys.modules["mmrotate"] = mmrot
     sys.modules["mmrotate.models"] = mmrot_models
     sys.modules["mmrotate.models.losses"] = mmrot_losses
@@ -190,6 +199,11 @@ def load_reference():
     sys.modules["sphdet.losses"] = losses_pkg
     iou_loss = importlib.import_module("sphdet.losses.sph2pob_iou_loss")
     transform = importlib.import_module("sphdet.losses.sph2pob_transform")
+    gd_loss = importlib.import_module("sphdet.losses.sph2pob_gd_loss")
+    kf_loss = importlib.import_module("sphdet.losses.sph2pob_kf_loss")
+    l1_loss = importlib.import_module("sphdet.losses.sph2pob_l1_loss")
+    # sph2pob_l1_loss.py:25 leaves a pdb.set_trace() in the constructor: make it a no-op for this module only
+    l1_loss.pdb = types.SimpleNamespace(set_trace=lambda *a, **k: None)
 
     # bbox coders (sphdet/bbox/coder/delta_xywh*_sph_bbox_coder.py): need only the mmdet base class and registry
     for name in ("mmdet.core.bbox.coder",):
@@ -221,6 +235,7 @@ def load_reference():
         sph_iou=api.sph_iou, fov_iou=api.fov_iou,
         SphOverlaps2D=calc.SphOverlaps2D, SphNMS=sph_nms.SphNMS,
         Sph2PobIoULoss=iou_loss.Sph2PobIoULoss,
+        Sph2PobGDLoss=gd_loss.Sph2PobGDLoss, Sph2PobKFLoss=kf_loss.Sph2PobKFLoss, Sph2PobL1Loss=l1_loss.Sph2PobL1Loss,
         jiter_spherical_bboxes=api.jiter_spherical_bboxes,
         jiter_rotated_bboxes=api.jiter_rotated_bboxes,
         DeltaXYWHSphBBoxCoder=coder4.DeltaXYWHSphBBoxCoder, DeltaXYWHASphBBoxCoder=coder5.DeltaXYWHASphBBoxCoder,

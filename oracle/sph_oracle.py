@@ -436,6 +436,67 @@ def sph2pob_iou_loss(pred, target, weight=None, avg_factor=None, mode="iou", eps
     return loss_weight * loss
 
 
+# ---- the other Sph2Pob losses --------------------------------------------------------------------
+def _decorated(pred, target, weight):
+    """Sph2PobTransfrom.new_forward (sph2pob_transform.py:24-35): OBBs of the pair + the widened BFoV weight."""
+    if weight is not None and weight.dim() > 1 and target.size(-1) == 4:
+        weight = torch.cat([weight, weight.mean(-1, keepdim=True)], dim=-1)
+    o1, o2 = loss_obbs(pred, target)
+    return o1, o2, weight
+
+
+def sph2pob_gd_loss(pred, target, weight=None, avg_factor=None, reduction_override=None, loss_type="gwd", fun="log1p",
+                    tau=0.0, alpha=1.0, reduction="mean", loss_weight=1.0, **kwargs):
+    """Sph2PobGDLoss (sph2pob_gd_loss.py:7-26) = decorator + mmrotate 0.3.2 GDLoss (oracle/mmrotate_losses.py)."""
+    from mmrotate_losses import GDLoss
+    o1, o2, weight = _decorated(pred, target, weight)
+    return GDLoss(loss_type, fun=fun, tau=tau, alpha=alpha, reduction=reduction, loss_weight=loss_weight, **kwargs)(
+        o1, o2, weight, avg_factor=avg_factor, reduction_override=reduction_override)
+
+
+def sph2pob_kf_loss(pred, target, weight=None, avg_factor=None, reduction_override=None, fun="none", reduction="mean",
+                    loss_weight=1.0):
+    """Sph2PobKFLoss (sph2pob_kf_loss.py:8-26): mmrotate KFLoss with pred_decode=target OBB, targets_decode=pred OBB."""
+    from mmrotate_losses import KFLoss
+    o1, o2, weight = _decorated(pred, target, weight)
+    return KFLoss(fun=fun, reduction=reduction, loss_weight=loss_weight)(
+        o1, o2, weight, avg_factor=avg_factor, pred_decode=o2, targets_decode=o1, reduction_override=reduction_override)
+
+
+def _obb_bbox2delta(proposals, gt, angle_modifier="original", eps=1e-7):
+    """sph2pob_l1_loss.py:40-87 (means 0, stds 1; forced to float32 at :68-69)."""
+    proposals, gt = proposals.float(), gt.float()
+    px, py, pw, ph, pa = proposals.unbind(dim=-1)
+    gx, gy, gw, gh, ga = gt.unbind(dim=-1)
+    pw, ph = pw.clip(min=eps), ph.clip(min=eps)
+    gw, gh = gw.clip(min=eps), gh.clip(min=eps)
+    wrap = (lambda a: a) if angle_modifier == "original" else (lambda a: (a + torch.pi) % torch.pi)
+    return torch.stack([(gx - px) / pw, (gy - py) / ph, torch.log(gw / pw), torch.log(gh / ph),
+                        (wrap(ga) - wrap(pa)) / torch.pi], dim=-1)
+
+
+def sph2pob_l1_loss(pred, target, weight=None, avg_factor=None, reduction_override=None, encode=True, swap=False,
+                    angle_modifier="original", reduction="mean", loss_weight=1.0):
+    """Sph2PobL1Loss (sph2pob_l1_loss.py:9-38) on mmdet's L1Loss (mmdet/models/losses/smooth_l1_loss.py:36-52,107-146)."""
+    o1, o2, weight = _decorated(pred, target, weight)
+    if encode:
+        o1 = _obb_bbox2delta(o2, o1, angle_modifier) if swap else _obb_bbox2delta(o1, o2, angle_modifier)
+        o2 = torch.zeros_like(o2)
+    red = reduction_override if reduction_override else reduction
+    if o2.numel() == 0:
+        return loss_weight * (o1.sum() * 0)
+    loss = torch.abs(o1 - o2)
+    if weight is not None:
+        loss = loss * weight
+    if avg_factor is None:
+        loss = loss.mean() if red == "mean" else loss.sum() if red == "sum" else loss
+    elif red == "mean":
+        loss = loss.sum() / (avg_factor + torch.finfo(torch.float32).eps)
+    elif red != "none":
+        raise ValueError('avg_factor can not be used with reduction="sum"')
+    return loss_weight * loss
+
+
 # ---- bbox coders (sphdet/bbox/coder/delta_xywh_sph_bbox_coder.py:117-262, delta_xywha_rsph_bbox_coder.py:117-268)
 def bbox2delta(proposals, gt, means=None, stds=None):
     """(d_theta, d_phi, d_alpha, d_beta[, d_gamma]) of gt w.r.t. proposals: centre offsets in units of the proposal

@@ -18,7 +18,7 @@ EDGE = {"arc": 0, "chord": 1, "tangent": 2}
 ANGLE = {"equator": 0, "project": 1}
 
 SPHK_OK = 0
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _c_float_p = ctypes.c_void_p  # raw device addresses
 _i64 = ctypes.c_int64
@@ -53,6 +53,9 @@ SIGNATURES = {
                             _c_float_p, ctypes.c_void_p]),
     "sphk_riou_fwd_bwd": (_int, [_c_float_p, _c_float_p, _i64, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
                                  ctypes.c_void_p]),
+    "sphk_obb_loss": (_int, [_int, _int, _int, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, _int, _c_float_p,
+                             _c_float_p, _i64, _int, _c_float_p, _int, ctypes.c_float, _c_float_p, _c_float_p, _c_float_p,
+                             _c_float_p, ctypes.c_void_p]),
     "sphk_coder_decode": (_int, [_c_float_p, _c_float_p, _i64, _int, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float),
                                  ctypes.c_float, _int, _int, ctypes.c_float, _c_float_p, ctypes.c_void_p]),
     "sphk_coder_decode_bwd": (_int, [_c_float_p, _c_float_p, _c_float_p, _i64, _int, ctypes.POINTER(ctypes.c_float),
@@ -322,6 +325,45 @@ def loss_reduce(pred, target, weight, scale, want_grad_pred=False, want_grad_tar
                                     _ptr(gt), _stream(pred)))
     launches += 1
     return partial, gp, gt
+
+
+LOSS_KIND = {"gwd": 0, "kld": 1, "jd": 2, "kld_symmax": 3, "kld_symmin": 4, "kfiou": 5, "l1": 6}
+
+
+def obb_loss(loss_kind, pred, target, upstream=None, scale=1.0, fun=0, flags=0, tau=0.0, alpha=1.0, beta=1.0 / 9.0, eps=1e-6,
+             transform="sph2pob_standard", want_loss=True, want_partial=False, want_grad_pred=False, want_grad_target=False):
+    """GD / KF / L1 loss rows on the Sph2Pob OBBs of aligned (pred, target), forward + backward in one launch
+    (sphk_obb_loss).  Returns (loss [n] or [n, 5] | None, partial | None, grad_pred | None, grad_target | None)."""
+    global launches
+    pred, target = _boxes(pred, "pred"), _boxes(target, "target")
+    if pred.shape != target.shape:
+        raise SphkError("pred/target shapes differ: %s vs %s" % (tuple(pred.shape), tuple(target.shape)))
+    n, dev = pred.size(0), pred.device
+    kind = LOSS_KIND[loss_kind]
+    L = 5 if kind == 6 else 1
+    up_cols = 0
+    if upstream is not None:
+        upstream = upstream.to(device=dev, dtype=torch.float32).contiguous()
+        if upstream.numel() == n * L and L > 1:
+            up_cols = L
+        elif upstream.numel() == n:
+            up_cols = 1
+        else:
+            raise SphkError("upstream has %d elements for %d rows of %d loss columns" % (upstream.numel(), n, L))
+    loss = torch.empty((n, L) if L > 1 else (n,), dtype=torch.float32, device=dev) if want_loss else None
+    partial = None
+    if want_partial:
+        partial = torch.empty(max(1, (n + 255) // 256), dtype=torch.float32, device=dev)
+        if n == 0:
+            partial.zero_()
+    gp = torch.empty_like(pred) if want_grad_pred else None
+    gt = torch.empty_like(target) if want_grad_target else None
+    with _on_device(dev):
+        _check(lib.sphk_obb_loss(kind, int(fun), int(flags), float(tau), float(alpha), float(beta), float(eps), KIND[transform],
+                                 _ptr(pred), _ptr(target), n, pred.size(1), _ptr(upstream), up_cols, float(scale), _ptr(loss),
+                                 _ptr(partial), _ptr(gp), _ptr(gt), _stream(pred)))
+    launches += 1
+    return loss, partial, gp, gt
 
 
 def _host5(values, D, default):

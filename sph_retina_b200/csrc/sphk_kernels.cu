@@ -25,6 +25,7 @@
 #include "sphk_fast.cuh"
 #include "sphk_grad.cuh"
 #include "sphk_math.cuh"
+#include "sphk_obbloss.cuh"
 
 using namespace sphk;
 
@@ -51,6 +52,9 @@ int cuda_fail(cudaError_t e, const char* where) {
     } while (0)
 
 constexpr int kThreads = 256;
+#ifndef SPHK_LOSS_SCALAR
+#define SPHK_LOSS_SCALAR double    // arithmetic type of the GD / KF row losses (dual numbers): their cancellations need it
+#endif
 
 // ---- box loads --------------------------------------------------------------------------------
 template <int D>
@@ -781,6 +785,80 @@ k_riou_fwd_bwd(const float* __restrict__ obb1, const float* __restrict__ obb2, i
     if (iou) iou[i] = v;
     if (grad_obb1) store_grad<5>(grad_obb1, i, g1, false);
     if (grad_obb2) store_grad<5>(grad_obb2, i, g2, false);
+}
+
+// ---- the other Sph2Pob losses (GD / KF / L1 on the transformed OBBs), forward + backward in one launch ----------
+// One thread per row: jitter_1 -> transform(kind) -> jitter_2 -> row loss on dual numbers (sphk_obbloss.cuh) ->
+// jitter_2 / transform backward (sphk_grad.cuh).  `up` = upstream weight / gradient per row ([n]), per element
+// ([n, L]) or NULL (= 1), always multiplied by `scale`.  Rows whose upstream is entirely zero are skipped when no
+// elementwise loss is requested: their gradient is exactly zero and they add nothing to the reduced loss.
+//   loss    [n, L]  unweighted elementwise loss (NULL to skip)
+//   partial [grid]  per-block sums of sum_j up[i, j] * loss[i, j] (without `scale`; NULL to skip)
+//   grad_b1 / grad_b2 [n, D]  scale * sum_j up[i, j] * d(loss[i, j]) / d(box)
+template <int D, typename T>
+__global__ void __launch_bounds__(kThreads)
+k_obb_loss(LossParams lp, int xkind, const float* __restrict__ b1, const float* __restrict__ b2, int64_t n,
+           const float* __restrict__ up, int up_cols, float scale, float* __restrict__ loss, float* __restrict__ partial,
+           float* __restrict__ grad_b1, float* __restrict__ grad_b2, bool vec_ok) {
+    __shared__ float s_sum[kThreads / 32];
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int L = loss_columns(lp.kind);
+    float li = 0.0f;
+    if (i < n) {
+        float u[5] = {1.0f, 1.0f, 1.0f, 1.0f, 1.0f};
+        if (up) {
+#pragma unroll
+            for (int k = 0; k < 5; ++k) u[k] = (k < L) ? __ldg(up + i * up_cols + (up_cols > 1 ? k : 0)) : 0.0f;
+        }
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) any = any || (k < L && u[k] != 0.0f);
+        float gb1[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f}, gb2[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+        if (any || loss) {
+            const RawBox x = load_box<D>(b1, i, vec_ok), y = load_box<D>(b2, i, vec_ok);
+            const bool m = jitter1_mask(x, y, D);
+            const JitBox g = jitter1_role1(x, m, D), p = jitter1_role2(y, m, D);
+            XformAux aux;
+            ObbPair o = (xkind == KIND_SPH2POB_STANDARD) ? sph2pob_standard(g, p, D, EDGE_ARC, &aux)
+                                                         : sph2pob_efficient(g, p, D, EDGE_ARC, &aux);
+            const uint32_t pass2 = jitter2(o);
+            float go1[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f}, go2[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+            float us[5];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) us[k] = u[k] * scale;
+            if (lp.kind == LOSS_L1) {
+                float ell[5];
+                obb_l1_loss_row(o, lp, us, ell, go1, go2);
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    if (loss) loss[i * 5 + k] = ell[k];
+                    li += u[k] * ell[k];
+                }
+            } else {
+                const float v = obb_scalar_loss_row<T>(o, lp, us[0], go1, go2);
+                if (loss) loss[i] = v;
+                li = u[0] * v;
+            }
+            if ((grad_b1 || grad_b2) && any) {
+                jitter2_grad(pass2, go1, go2);
+                xform_grad(xkind, g, p, D, EDGE_ARC, aux, go1, go2, gb1, gb2);
+            }
+            if (!any) li = 0.0f;
+        }
+        if (grad_b1) store_grad<D>(grad_b1, i, gb1, vec_ok);
+        if (grad_b2) store_grad<D>(grad_b2, i, gb2, vec_ok);
+    }
+    if (partial == nullptr) return;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) li += __shfl_xor_sync(0xFFFFFFFFu, li, o);
+    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = li;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.0f;
+#pragma unroll
+        for (int k = 0; k < kThreads / 32; ++k) t += s_sum[k];
+        partial[blockIdx.x] = t;
+    }
 }
 
 // ---- box coders + the decode -> loss step of the head ---------------------------------------------
@@ -1581,6 +1659,32 @@ int sphk_riou_fwd_bwd(const float* obb1, const float* obb2, int64_t n, float* io
     if (!obb1 || !obb2) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_riou_fwd_bwd: null OBB pointer");
     k_riou_fwd_bwd<<<blocks_for(n), kThreads, 0, (cudaStream_t)stream>>>(obb1, obb2, n, iou, grad_iou, grad_obb1, grad_obb2);
     SPHK_LAUNCH_CHECK("k_riou_fwd_bwd");
+    return SPHK_OK;
+}
+
+int sphk_obb_loss(int loss_kind, int fun, int flags, float tau, float alpha, float beta, float eps, int transform,
+                  const float* pred, const float* target, int64_t n, int D, const float* upstream, int up_cols, float scale,
+                  float* loss, float* partial, float* grad_pred, float* grad_target, void* stream) {
+    if (n < 0 || (D != 4 && D != 5)) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_obb_loss: n < 0 or D not in {4,5}");
+    if (loss_kind < SPHK_LOSS_GWD || loss_kind > SPHK_LOSS_L1) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_obb_loss: unknown loss kind");
+    if (fun < 0 || fun > 2) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_obb_loss: unknown fun");
+    if (transform != SPHK_KIND_SPH2POB_EFFICIENT && transform != SPHK_KIND_SPH2POB_STANDARD)
+        return fail(SPHK_ERR_UNSUPPORTED, "sphk_obb_loss: transform must be a Sph2Pob transform");
+    const int L = loss_kind == SPHK_LOSS_L1 ? 5 : 1;
+    if (upstream && up_cols != 1 && up_cols != L) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_obb_loss: up_cols must be 1 or the loss's column count");
+    if (loss_kind != SPHK_LOSS_L1 && loss_kind != SPHK_LOSS_KFIOU && !(alpha != 0.0f))
+        return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_obb_loss: alpha must be non-zero");
+    if (loss_kind == SPHK_LOSS_KFIOU && !(beta > 0.0f)) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_obb_loss: beta must be positive");
+    if (n == 0) return SPHK_OK;
+    if (!pred || !target) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_obb_loss: null box pointer");
+    LossParams lp;
+    lp.kind = loss_kind; lp.fun = fun; lp.flags = flags; lp.tau = tau; lp.alpha = alpha; lp.beta = beta; lp.eps = eps;
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool v = aligned16(pred) && aligned16(target) && (!grad_pred || aligned16(grad_pred)) &&
+                   (!grad_target || aligned16(grad_target));
+    if (D == 4) k_obb_loss<4, SPHK_LOSS_SCALAR><<<blocks_for(n), kThreads, 0, s>>>(lp, transform, pred, target, n, upstream, up_cols, scale, loss, partial, grad_pred, grad_target, v);
+    else k_obb_loss<5, SPHK_LOSS_SCALAR><<<blocks_for(n), kThreads, 0, s>>>(lp, transform, pred, target, n, upstream, up_cols, scale, loss, partial, grad_pred, grad_target, v);
+    SPHK_LAUNCH_CHECK("k_obb_loss");
     return SPHK_OK;
 }
 

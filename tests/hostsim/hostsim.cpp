@@ -7,6 +7,7 @@
 #include "../../sph_retina_b200/csrc/sphk_coder.cuh"
 #ifdef SPHK_WITH_GRAD
 #include "../../sph_retina_b200/csrc/sphk_grad.cuh"
+#include "../../sph_retina_b200/csrc/sphk_obbloss.cuh"
 #endif
 
 using namespace sphk;
@@ -165,6 +166,37 @@ double hostsim_decode_loss(const float* anchors, const float* deltas, const floa
         total += (double)w * (1.0 - (double)iou);
     }
     return total;
+}
+
+// GD / KF / L1 losses on the Sph2Pob OBBs (k_obb_loss): loss[n, L], g1/g2[n, D] = sum_j up[i, j] * d(loss_ij)/d(box);
+// use_double selects the arithmetic type of the dual numbers (the kernel is built with float)
+void hostsim_obb_loss(int kind, int fun, int flags, float tau, float alpha, float beta, float eps, int xkind, const float* b1,
+                      const float* b2, const float* up, int up_cols, long n, int D, int use_double, float* loss, float* g1,
+                      float* g2) {
+    LossParams lp;
+    lp.kind = kind; lp.fun = fun; lp.flags = flags; lp.tau = tau; lp.alpha = alpha; lp.beta = beta; lp.eps = eps;
+    const int L = loss_columns(kind);
+    for (long i = 0; i < n; ++i) {
+        const RawBox x = load_box(b1, i, D), y = load_box(b2, i, D);
+        const bool m = jitter1_mask(x, y, D);
+        const JitBox g = jitter1_role1(x, m, D), p = jitter1_role2(y, m, D);
+        XformAux aux;
+        ObbPair o = (xkind == KIND_SPH2POB_STANDARD) ? sph2pob_standard(g, p, D, EDGE_ARC, &aux)
+                                                     : sph2pob_efficient(g, p, D, EDGE_ARC, &aux);
+        const uint32_t pass2 = jitter2(o);
+        float u[5], go1[5] = {0, 0, 0, 0, 0}, go2[5] = {0, 0, 0, 0, 0}, gb1[5], gb2[5];
+        for (int k = 0; k < 5; ++k) u[k] = up ? up[i * up_cols + (up_cols > 1 ? k : 0)] : 1.0f;
+        if (kind == LOSS_L1) {
+            obb_l1_loss_row(o, lp, u, loss + i * 5, go1, go2);
+        } else {
+            loss[i] = use_double ? obb_scalar_loss_row<double>(o, lp, u[0], go1, go2)
+                                 : obb_scalar_loss_row<float>(o, lp, u[0], go1, go2);
+        }
+        (void)L;
+        jitter2_grad(pass2, go1, go2);
+        xform_grad(xkind, g, p, D, EDGE_ARC, aux, go1, go2, gb1, gb2);
+        for (int k = 0; k < D; ++k) { g1[i * D + k] = gb1[k]; g2[i * D + k] = gb2[k]; }
+    }
 }
 
 #endif

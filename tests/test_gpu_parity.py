@@ -13,7 +13,8 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import ROOT, degenerate_pairs, grad_rows_ok, load_golden, within
+from conftest import (ROOT, check_other_loss, degenerate_pairs, grad_rows_ok, load_golden, other_loss_variants,
+                      within)
 
 pytestmark = pytest.mark.gpu
 
@@ -458,6 +459,94 @@ def test_loss_gradcheck_against_finite_differences(api):
         num[:, k] = (api.losses.sph2pob_iou(p + d, t) - api.losses.sph2pob_iou(p - d, t)) / (2 * h)
     err = (pr.grad - num).norm(dim=1) / num.norm(dim=1).clamp(min=1e-3)
     assert float(err.median()) < 5e-3 and float((err < 5e-2).float().mean()) > 0.97
+
+
+# ---- the other losses on the Sph2Pob OBBs ---------------------------------------------------
+def _other_loss(api, cls, kw, **extra):
+    return getattr(api.losses, cls)(**kw, **extra)
+
+
+@pytest.mark.parametrize("box", ["bfov", "rbfov"])
+def test_other_losses_forward_backward_golden(api, box):
+    """Sph2PobGDLoss (gwd / kld / jd / kld_symmax / kld_symmin + fun / tau / alpha / normalize / sqrt options),
+    Sph2PobKFLoss (none / ln / exp) and Sph2PobL1Loss (encode / swap / modulus / plain): elementwise loss and both
+    gradients against the reference's float64 run (tolerances in conftest.check_other_loss)."""
+    g = load_golden("other_losses_" + box)
+    for name, (cls, kw) in other_loss_variants(g).items():
+        p = cu(g["pred"]).requires_grad_(True)
+        t = cu(g["target"]).requires_grad_(True)
+        L = _other_loss(api, cls, kw, reduction="sum")
+        el = L(p, t, reduction_override="none")
+        assert el.shape == ((p.size(0), 5) if cls == "Sph2PobL1Loss" else (p.size(0),))
+        el.sum().backward()
+        check_other_loss(name, g, el.detach().cpu().numpy(), p.grad.cpu().numpy(), t.grad.cpu().numpy())
+
+
+@pytest.mark.parametrize("box", ["bfov", "rbfov"])
+def test_other_losses_reductions_weights_avg_factor(api, box):
+    g = load_golden("other_losses_" + box)
+    p, t, w1, w2 = cu(g["pred"]), cu(g["target"]), cu(g["w1"]), cu(g["w2"])
+    for name, (cls, kw) in other_loss_variants(g).items():
+        L = _other_loss(api, cls, kw, loss_weight=2.0)
+        rt = 2e-3 if name == "l1_swap" else 5e-5     # l1_swap sums terms of 1e4 with fp32 OBBs
+        np.testing.assert_allclose(L(p, t).item(), g[name + "_red_mean"], rtol=rt, err_msg=name)
+        np.testing.assert_allclose(L(p, t, w2, avg_factor=77.0).item(), g[name + "_red_w2_avg"], rtol=rt, err_msg=name)
+        np.testing.assert_allclose(L(p, t, w2, reduction_override="sum").item(), g[name + "_red_w2_sum"], rtol=rt, err_msg=name)
+        if cls != "Sph2PobL1Loss":
+            np.testing.assert_allclose(L(p, t, w1, avg_factor=123.0).item(), g[name + "_red_w1_avg"], rtol=rt, err_msg=name)
+        with pytest.raises(ValueError):
+            L(p, t, w2, avg_factor=3.0, reduction_override="sum")
+    # the fused reduced path and the elementwise path agree, gradients included; zero-weight rows get exactly zero
+    for cls, kw in (("Sph2PobGDLoss", dict(loss_type="kld")), ("Sph2PobKFLoss", {}), ("Sph2PobL1Loss", {})):
+        L = _other_loss(api, cls, kw, loss_weight=3.0)
+        w = w2 if cls == "Sph2PobL1Loss" else w1
+        if cls == "Sph2PobL1Loss" and w.size(1) == 4:
+            w_full = torch.cat([w, w.mean(-1, keepdim=True)], -1)
+        else:
+            w_full = w
+        pa, ta = p.clone().requires_grad_(True), t.clone().requires_grad_(True)
+        fused = L(pa, ta, w, avg_factor=50.0)
+        fused.backward()
+        pb, tb = p.clone().requires_grad_(True), t.clone().requires_grad_(True)
+        el = L(pb, tb, reduction_override="none")
+        ref = (el * w_full).sum() / (50.0 + torch.finfo(torch.float32).eps)
+        ref.backward()
+        np.testing.assert_allclose(fused.item(), ref.item(), rtol=1e-5)
+        rel = (pa.grad - pb.grad).norm(dim=1) / pb.grad.norm(dim=1).clamp(min=1e-12)
+        assert float(rel[64:].median()) < 1e-6 and float((rel[64:] < 1e-4).float().mean()) > 0.99
+        dead = (w_full == 0) if w_full.dim() == 1 else (w_full == 0).all(dim=1)
+        assert int(dead.sum()) > 0 and float(pa.grad[dead].abs().max()) == 0.0 and float(ta.grad[dead].abs().max()) == 0.0
+        assert torch.isfinite(pa.grad).all() and torch.isfinite(ta.grad).all()
+        z = L(pa, ta, torch.zeros_like(w))
+        assert z.item() == 0.0
+        with torch.no_grad():
+            assert torch.isfinite(L(p, t, w))
+        assert L(p[:0], t[:0]).shape == () and L(p[:0], t[:0], reduction_override="none").numel() == 0
+
+
+def test_other_losses_match_the_oracle_on_seeded_boxes(api):
+    """Seeded PANDORA-style pairs (configs[2] shape, 20k rows): reduced loss of every loss type against the oracle in
+    float64, and the gradient of the reduced loss against the oracle's autograd."""
+    n = 20000
+    t = O.generate_boxes(n, alpha_range=(5, 100), beta_range=(5, 100), box="rbfov", seed=0)
+    torch.manual_seed(1)
+    p = (t + torch.randn(n, 5) * torch.tensor([6, 6, 6, 6, 10.0])).clamp(min=1)
+    w = (torch.rand(n) > 0.5).float()
+    cases = [("Sph2PobGDLoss", O.sph2pob_gd_loss, dict(loss_type=k)) for k in ("gwd", "kld", "jd", "kld_symmax", "kld_symmin")]
+    cases += [("Sph2PobKFLoss", O.sph2pob_kf_loss, {}), ("Sph2PobL1Loss", O.sph2pob_l1_loss, {})]
+    for cls, ofn, kw in cases:
+        ww = w if cls != "Sph2PobL1Loss" else w[:, None].expand(n, 5).contiguous()
+        pd = p.double().requires_grad_(True)
+        want = ofn(pd, t.double(), ww.double(), avg_factor=float(w.sum()), **kw)
+        want.backward()
+        pg = p.to(DEV).requires_grad_(True)
+        got = getattr(api.losses, cls)(**kw)(pg, t.to(DEV), ww.to(DEV), avg_factor=float(w.sum()))
+        got.backward()
+        np.testing.assert_allclose(got.item(), want.item(), rtol=2e-5, err_msg=cls + str(kw))
+        rel = (pg.grad.cpu().double() - pd.grad).norm(dim=1) / pd.grad.norm(dim=1).clamp(min=1e-30)
+        live = w > 0
+        assert float(rel[live].median()) < 3e-6 and float((rel[live] < 1e-4).float().mean()) > 0.995, (cls, kw)
+        assert float(pg.grad[~live].abs().max()) == 0.0
 
 
 # ---- NMS ---------------------------------------------------------------------------------------

@@ -155,3 +155,31 @@ def test_vectorised_assign_wrt_overlaps_equals_the_reference_loop():
                     g, m, l = O.assign_wrt_overlaps(ov, lab, 0.5, neg, a.min_pos_iou, all_, mlq)
                     assert r.num_gts == K and torch.equal(r.gt_inds, g) and torch.equal(r.max_overlaps, m)
                     assert torch.equal(r.labels, l)
+
+
+def test_other_sph2pob_losses_host_contract():
+    """Sph2PobGDLoss / Sph2PobKFLoss / Sph2PobL1Loss (sphdet/losses/__init__.py:3-8): registry names, constructor
+    checks of the mmrotate / reference classes, and the loud failure on CPU tensors."""
+    from sph_retina_b200 import _native
+    from sph_retina_b200.sphdet import registry
+    from sph_retina_b200.sphdet.losses import Sph2PobGDLoss, Sph2PobKFLoss, Sph2PobL1Loss
+    gd = registry.build_loss(dict(type='Sph2PobGDLoss', loss_type='kld', fun='log1p', tau=1.0, loss_weight=5.0, sqrt=False))
+    assert isinstance(gd, Sph2PobGDLoss) and gd.tau == 1.0 and gd.kwargs == dict(sqrt=False) and gd.reduction == 'mean'
+    assert isinstance(registry.build_loss(dict(type='Sph2PobKFLoss', fun='ln')), Sph2PobKFLoss)
+    l1 = registry.build_loss(dict(type='Sph2PobL1Loss', angle_modifier='modulus', swap=True))
+    assert isinstance(l1, Sph2PobL1Loss) and l1.encode and l1.swap
+    for bad in (dict(loss_type='bogus'), dict(loss_type='gwd', fun='exp'), dict(loss_type='gwd', reduction='avg')):
+        with pytest.raises(AssertionError):
+            Sph2PobGDLoss(**bad)
+    with pytest.raises(AssertionError):
+        Sph2PobKFLoss(fun='log1p')
+    with pytest.raises(AssertionError):
+        Sph2PobL1Loss(angle_modifier='wrap')
+    with pytest.raises(TypeError):                      # gwd_loss() takes `normalize`, not `sqrt`
+        Sph2PobGDLoss('gwd', sqrt=True)(torch.zeros(0, 4), torch.zeros(0, 4))
+    b = torch.rand(4, 5) * 50 + 10
+    for loss in (Sph2PobGDLoss('gwd'), Sph2PobKFLoss(), Sph2PobL1Loss()):
+        with pytest.raises(_native.SphkError):
+            loss(b, b.clone())
+        with pytest.raises(AssertionError):
+            loss(b, b.clone(), reduction_override='avg')

@@ -9,7 +9,8 @@ import ctypes
 import numpy as np
 import pytest
 
-from conftest import degenerate_pairs, grad_rows_ok, load_golden, within
+from conftest import (check_other_loss, degenerate_pairs, grad_rows_ok, load_golden, other_loss_kernel_args,
+                      other_loss_variants, within)
 
 fp = ctypes.POINTER(ctypes.c_float)
 
@@ -313,3 +314,53 @@ def test_project_angle_variant(hostsim, box):
         ok, err = within(out, g[tr + "_project_f64"], g[tr + "_project_f32"])
         assert ok.all(), (box, tr, np.where(~ok)[0], err[~ok])
         assert (err > 1e-5).sum() <= 2
+
+
+def hs_obb_loss(lib, cls, kw, pred, target, up=None, use_double=1):
+    kind, fun, flags, tau, alpha = other_loss_kernel_args(cls, kw)
+    p, t = np.ascontiguousarray(pred, np.float32), np.ascontiguousarray(target, np.float32)
+    n, D = p.shape
+    L = 5 if kind == 6 else 1
+    loss, g1, g2 = np.empty((n, L), np.float32), np.empty((n, D), np.float32), np.empty((n, D), np.float32)
+    up_cols = 0
+    if up is not None:
+        up = np.ascontiguousarray(up, np.float32)
+        up_cols = 1 if up.ndim == 1 else up.shape[1]
+    cf = ctypes.c_float
+    lib.hostsim_obb_loss(kind, fun, flags, cf(tau), cf(alpha), cf(1.0 / 9.0), cf(1e-6), 1, p.ctypes.data_as(fp), t.ctypes.data_as(fp),
+                         up.ctypes.data_as(fp) if up is not None else None, up_cols, ctypes.c_long(n), D, use_double,
+                         loss.ctypes.data_as(fp), g1.ctypes.data_as(fp), g2.ctypes.data_as(fp))
+    return (loss if L > 1 else loss[:, 0]), g1, g2
+
+
+@pytest.mark.parametrize("box", ["bfov", "rbfov"])
+def test_other_losses_golden(hostsim, box):
+    """Sph2PobGDLoss / KFLoss / L1Loss rows (csrc/sphk_obbloss.cuh: dual-number row losses in double, as the kernel is
+    built, chained through the fp32 transform backward) against the reference's float64 run."""
+    g = load_golden("other_losses_" + box)
+    for name, (cls, kw) in other_loss_variants(g).items():
+        loss, g1, g2 = hs_obb_loss(hostsim, cls, kw, g["pred"], g["target"])
+        check_other_loss(name, g, loss, g1, g2)
+
+
+def test_other_losses_upstream_is_linear(hostsim):
+    """The per-row / per-element upstream (weights or incoming gradient) scales the gradients and nothing else."""
+    g = load_golden("other_losses_rbfov")
+    rng = np.random.default_rng(0)
+    n = len(g["pred"])
+    for cls, kw, cols in (("Sph2PobGDLoss", dict(loss_type="kld"), 1), ("Sph2PobKFLoss", {}, 1), ("Sph2PobL1Loss", {}, 5)):
+        base = hs_obb_loss(hostsim, cls, kw, g["pred"], g["target"])
+        w = rng.uniform(0.5, 2.0, size=n).astype(np.float32)
+        got = hs_obb_loss(hostsim, cls, kw, g["pred"], g["target"], up=w)
+        np.testing.assert_array_equal(got[0], base[0])
+        for a, b in ((got[1], base[1] * w[:, None]), (got[2], base[2] * w[:, None])):
+            rel, _ = grad_row_error(a[64:], b[64:])          # (rows 0-63: near-identical boxes, cancelling 1e5-sized terms)
+            assert np.median(rel) < 1e-6 and (rel < 1e-4).mean() > 0.99
+        if cols == 5:       # one column at a time adds up to all columns
+            acc = np.zeros_like(base[1], dtype=np.float64)
+            for k in range(5):
+                u = np.zeros((n, 5), np.float32)
+                u[:, k] = 1.0
+                acc += hs_obb_loss(hostsim, cls, kw, g["pred"], g["target"], up=u)[1]
+            rel, _ = grad_row_error(acc[64:], base[1][64:].astype(np.float64))
+            assert np.median(rel) < 1e-6 and (rel < 1e-4).mean() > 0.99

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import ROOT, load_golden
+from conftest import ROOT, load_golden, other_loss_variants
 
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import sph_oracle as O  # noqa: E402
@@ -104,6 +104,32 @@ def test_restatement_loss_and_grads(box):
     np.testing.assert_allclose(O.sph2pob_iou_loss(p, t, w2, loss_weight=2.0).item(), g["red_w2"], rtol=1e-10)
     np.testing.assert_allclose(O.sph2pob_iou_loss(p, t, w1, reduction="sum", loss_weight=2.0).item(), g["red_w1_sum"], rtol=1e-10)
     np.testing.assert_allclose(O.sph2pob_iou_loss(p, t, torch.zeros(n).double(), loss_weight=2.0).item(), g["red_zero_w"], atol=1e-12)
+
+
+@pytest.mark.parametrize("box", ["bfov", "rbfov"])
+def test_restatement_other_losses(box):
+    """Sph2PobGDLoss / Sph2PobKFLoss / Sph2PobL1Loss: the restatement against the reference's
+    own subclasses + decorator run in float64 (the mmrotate base classes are restated, see oracle/mmrotate_losses.py)."""
+    g = load_golden("other_losses_" + box)
+    fns = {"Sph2PobGDLoss": O.sph2pob_gd_loss, "Sph2PobKFLoss": O.sph2pob_kf_loss, "Sph2PobL1Loss": O.sph2pob_l1_loss}
+    w1, w2 = torch.from_numpy(g["w1"]).double(), torch.from_numpy(g["w2"]).double()
+    for name, (cls, kw) in other_loss_variants(g).items():
+        fn = fns[cls]
+        p = torch.from_numpy(g["pred"]).double().requires_grad_(True)
+        t = torch.from_numpy(g["target"]).double().requires_grad_(True)
+        el = fn(p, t, reduction="none", **kw)
+        el.sum().backward()
+        want = g[name + "_loss_f64"]
+        assert np.abs(el.detach().numpy() - want).max() <= 1e-9 * max(1.0, np.abs(want).max()), name
+        for got, key in ((p.grad, "gpred"), (t.grad, "gtarget")):
+            want = g["%s_%s_f64" % (name, key)]
+            assert np.abs(got.numpy() - want).max() <= 1e-7 * max(1.0, np.abs(want).max()), (name, key)
+        p, t = p.detach(), t.detach()
+        np.testing.assert_allclose(fn(p, t, loss_weight=2.0, **kw).item(), g[name + "_red_mean"], rtol=1e-9)
+        np.testing.assert_allclose(fn(p, t, w2, avg_factor=77.0, loss_weight=2.0, **kw).item(), g[name + "_red_w2_avg"], rtol=1e-9)
+        np.testing.assert_allclose(fn(p, t, w2, reduction_override="sum", loss_weight=2.0, **kw).item(), g[name + "_red_w2_sum"], rtol=1e-9)
+        if cls != "Sph2PobL1Loss":
+            np.testing.assert_allclose(fn(p, t, w1, avg_factor=123.0, loss_weight=2.0, **kw).item(), g[name + "_red_w1_avg"], rtol=1e-9)
 
 
 @pytest.mark.parametrize("box", ["bfov", "rbfov"])
