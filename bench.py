@@ -277,6 +277,17 @@ def other_configs(torch, native, dev, flush):
         ms_f = quick(torch, lambda: L(pred, target), flush=flush)
     ms_fb = quick(torch, fwd_bwd, flush=flush)
     out["loss_200k_rbfov"] = {"fwd_ms": ms_f, "fwd_bwd_ms": ms_fb, "pairs_per_s_fwd_bwd": 200_000 / ms_fb * 1e3}
+    # the other losses on the same OBBs: one launch each for loss + both gradients
+    from sph_retina_b200.sphdet.losses import Sph2PobGDLoss, Sph2PobKFLoss, Sph2PobL1Loss
+    other = {}
+    for name, Lo in (("gwd", Sph2PobGDLoss("gwd", reduction="sum")), ("kld", Sph2PobGDLoss("kld", reduction="sum")),
+                     ("kfiou", Sph2PobKFLoss(reduction="sum")), ("l1", Sph2PobL1Loss(reduction="sum"))):
+        def fb(Lo=Lo):
+            p = pred.detach().requires_grad_(True)
+            Lo(p, target).backward()
+        ms = quick(torch, fb, flush=flush)
+        other[name] = {"fwd_bwd_ms": ms, "pairs_per_s_fwd_bwd": 200_000 / ms * 1e3}
+    out["other_losses_200k_rbfov"] = other
     boxes, scores, labels, image_ids = (t.to(dev) for t in S.nms_batch(64, 1000, 80))
     ms = quick(torch, lambda: sph_batched_nms_images(boxes, scores, labels, image_ids, 0.5), iters=5, flush=flush)
     ms_h = quick(torch, lambda: sph_batched_nms_images(boxes, scores, labels, image_ids, 0.5, num_images=64, num_classes=80,

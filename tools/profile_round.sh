@@ -7,7 +7,7 @@ set -u
 tag=${1:-r01}
 mode=${2:-bench}
 shift; shift
-kernels=${*:-aligned aligned5 assign sweep loss nms nms_pipeline assigner headloss}
+kernels=${*:-aligned aligned5 assign sweep loss gdloss nms nms_pipeline assigner headloss}
 out=gpurun_out
 mkdir -p $out
 if [ "$mode" = bench ]; then
@@ -19,7 +19,7 @@ fi
 for k in $kernels; do
     python tools/run_kernel.py $k > $out/plain_$k.log 2>&1 || { echo "plain $k failed"; continue; }
     ncu --set full --import-source on --clock-control none \
-        -k regex:"k_iou_aligned2|k_iou_pairwise2|k_loss|k_nms|k_decode_loss" -s 3 -c 1 -o $out/prof_${k}_$tag -f \
+        -k regex:"k_iou_aligned2|k_iou_pairwise2|k_loss|k_nms|k_decode_loss|k_obb_loss" -s 3 -c 1 -o $out/prof_${k}_$tag -f \
         python tools/run_kernel.py $k > $out/ncu_$k.log 2>&1 || echo "ncu $k failed"
 done
 ls -la $out | grep $tag

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Launches one hot-path kernel a few times on BASELINE-shaped synthetic input (for ncu captures).
-    python tools/run_kernel.py aligned|aligned5|loss|nms|nms_agnostic|nms_pipeline|sweep|assign|assigner|headloss [--iters 5]"""
+    python tools/run_kernel.py aligned|aligned5|loss|gdloss|nms|nms_agnostic|nms_pipeline|sweep|assign|assigner|headloss [--iters 5]"""
 import argparse
 import os
 import sys
@@ -54,6 +54,14 @@ elif a.which == "headloss":
     def fn():
         d = deltas.detach().requires_grad_(True)
         LD.forward_decoded(coder, anchors, d, target, weight, avg_factor=npos).backward()
+elif a.which == "gdloss":
+    from sph_retina_b200.sphdet.losses import Sph2PobGDLoss
+    pred, target = (t.to(dev) for t in S.loss_pairs(200_000))
+    LG = Sph2PobGDLoss("kld", reduction="sum")
+
+    def fn():
+        p = pred.detach().requires_grad_(True)
+        LG(p, target).backward()
 elif a.which == "assigner":
     from sph_retina_b200.sphdet.assigners import SphMaxIoUAssigner
     gts, anchors = S.assignment_batch()
