@@ -11,6 +11,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "libsphk.so")
+_PROBE_LIB = os.environ.get("SPHK_PROBE_LIB")      # tools/ only: an instrumented build of the same sources
 
 KIND = {"sph2pob_efficient": 0, "sph2pob_standard": 1, "sph": 2, "fov": 3}
 MODE = {"iou": 0, "iof": 1}
@@ -92,7 +93,7 @@ def _load():
             raise ImportError(
                 "sph_retina_b200: %s is missing and could not be built (%s). Build it with "
                 "`python -m sph_retina_b200.build` (nvcc, sm_100a). There is no CPU fallback." % (LIB_PATH, e))
-    lib = ctypes.CDLL(LIB_PATH)
+    lib = ctypes.CDLL(_PROBE_LIB or LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = res
@@ -216,7 +217,13 @@ def iou_pairwise(kind: str, rows, cols, mode="iou", edge="arc", want_matrix=True
         _check(lib.sphk_iou_pairwise(KIND[kind], _ptr(rows), R, _ptr(cols), C, rows.size(1), MODE[mode], EDGE[edge],
                                      ANGLE[angle], _ptr(mat), ld, _ptr(rmax), _ptr(rarg), _ptr(cmax), _ptr(carg), row_base, col_base,
                                      _ptr(ws), _stream(rows)))
-    launches += 1 + int(kind in ("sph2pob_efficient", "sph2pob_standard")) + 2 * int(want_row_max) + 2 * int(want_col_max)
+    if kind in ("sph2pob_efficient", "sph2pob_standard"):
+        if mat is not None and R <= 32 and not (want_row_max or want_col_max):
+            launches += 1                                        # k_iou_rows32: records computed inside the CTAs
+        else:
+            launches += 2 + int(want_row_max or want_col_max)   # k_box_pre (zeroes the keys), k_iou_pairwise2[, k_unpack_keys2]
+    else:
+        launches += 1 + 2 * int(want_row_max) + 2 * int(want_col_max) - int(want_row_max and want_col_max)
     return mat, ((rmax, rarg) if want_row_max else None), ((cmax, carg) if want_col_max else None)
 
 
@@ -233,7 +240,7 @@ def iou_pairwise_keys(kind: str, rows, cols, mode="iou", edge="arc", row_base=0,
     with _on_device(dev):
         _check(lib.sphk_iou_pairwise_keys(KIND[kind], _ptr(rows), R, _ptr(cols), C, rows.size(1), MODE[mode], EDGE[edge],
                                           _ptr(rk), _ptr(ck), row_base, col_base, _ptr(ws), _stream(rows)))
-    launches += 4
+    launches += 2
     return rk, ck
 
 

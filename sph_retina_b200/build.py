@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsphk.so")
 SOURCES = ["sphk_kernels.cu"]
-HEADERS = ["sphk_math.cuh", "sphk_fast.cuh", "sphk_grad.cuh", "sphk_coder.cuh", os.path.join("..", "..", "include", "sphk.h")]
+HEADERS = ["sphk_math.cuh", "sphk_fast.cuh", "sphk_grad.cuh", "sphk_coder.cuh", "sphk_obbloss.cuh", os.path.join("..", "..", "include", "sphk.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",

@@ -36,6 +36,10 @@ int g_dense = 0;   // sphk_set_dense: 1 = no disjoint-pair early-outs (measureme
 const int g_force_ctas = [] { const char* e = getenv("SPHK_ALIGNED_CTAS"); return e ? atoi(e) : 0; }();   // tuning hook
 const int g_force_minb = [] { const char* e = getenv("SPHK_ALIGNED_MINB"); return e ? atoi(e) : 0; }();
 const int g_force_tr = [] { const char* e = getenv("SPHK_TR"); return e ? atoi(e) : 0; }();
+// timing probes (tools/assign_probe.py), never set in production: bit 0 = do not launch k_box_pre (stale records),
+// bit 1 = launch k_iou_pairwise2 without programmatic stream serialization
+const int g_no_rows32 = [] { const char* e = getenv("SPHK_NO_ROWS32"); return e ? atoi(e) : 0; }();   // A/B hook
+const int g_probe = [] { const char* e = getenv("SPHK_PROBE"); return e ? atoi(e) : 0; }();
 
 int fail(int code, const char* what) {
     snprintf(g_err, sizeof(g_err), "%s", what);
@@ -383,11 +387,15 @@ struct PairTile {
 template <int D>
 __global__ void __launch_bounds__(kThreads)
 k_box_pre(const float* __restrict__ rows, int64_t R, const float* __restrict__ cols, int64_t C, int edge,
-          float4* __restrict__ rec, float4* __restrict__ cull, bool rows_vec, bool cols_vec) {
+          float4* __restrict__ rec, float4* __restrict__ cull, bool rows_vec, bool cols_vec,
+          unsigned long long* __restrict__ zero_rkey, unsigned long long* __restrict__ zero_ckey) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // k_iou_pairwise2 may start its prologue
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (i >= R + C) return;
     const bool is_row = i < R;
+    // the packed max / argmax keys of the same call start from "nothing seen" (one key per box: no launch of its own)
+    if (is_row) { if (zero_rkey) zero_rkey[i] = 0ull; }
+    else if (zero_ckey) zero_ckey[i - R] = 0ull;
     const RawBox x = is_row ? load_box<D>(rows, i, rows_vec) : load_box<D>(cols, i - R, cols_vec);
     BoxRec b;
     BoxCull c;
@@ -442,6 +450,12 @@ __device__ __forceinline__ void emit_pair(PairTile<TR>& T, const PairOut& o, int
     }
 }
 
+#ifdef SPHK_TIMELINE
+// instrumented build (tools/timeline_probe.py): start / end globaltimer and SM id of every CTA of k_iou_pairwise2
+__device__ unsigned long long g_tl[16384 * 2];
+__device__ unsigned g_tl_sm[16384];
+#endif
+
 template <int D, int TR>
 __global__ void __launch_bounds__(kThreads)
 k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restrict__ cols, int64_t C,
@@ -452,6 +466,10 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
                 const int32_t* __restrict__ row_offsets, int64_t col_stride) {
     __shared__ __align__(16) PairTile<TR> T;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef SPHK_TIMELINE
+    unsigned long long tl0 = 0;
+    if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl0));
+#endif
     // grid = (row tiles, column tiles).  Column tiles are taken heaviest-first: RetinaNet-style anchor lists
     // end with the coarse pyramid levels, whose huge anchors overlap every GT, so the tail of the launch is
     // made of the light tiles.
@@ -567,6 +585,16 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
         }
         if (drained) break;
     }
+#ifdef SPHK_TIMELINE
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long tl1; unsigned smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl1));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        const unsigned b = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        if (b < 16384) { g_tl[2 * b] = tl0; g_tl[2 * b + 1] = tl1; g_tl_sm[b] = smid; }
+    }
+#endif
     // ---- merge the tile's max/argmax into the global keys
     if (o.want_row || o.want_col || o.tie) {
         __syncthreads();
@@ -579,6 +607,134 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
             const unsigned long long key = T.ckey[tid];
             if (key != 0ull && key > col_key[o.c0 + tid]) atomicMax(&col_key[o.c0 + tid], key);
         }
+    }
+}
+
+// ---- few rows x many columns in ONE launch ----------------------------------------------------------------------
+// SphOverlaps2D(gt[R <= 32], anchors[C]) -> [R, C] is the call MaxIoUAssigner makes once per image
+// (mmdet/core/bbox/assigners/max_iou_assigner.py:113).  At this size the general path spends a tenth of the call in
+// k_box_pre and the hand-over to k_iou_pairwise2; here a CTA owns ALL rows and 64 columns, so it can compute the
+// per-box records itself (every column once, the <= 32 rows once per CTA: +0.2 % of the instructions), straight into
+// shared memory -- no workspace, no second kernel.  Warp w works on column group w & 1 (32 columns, lane <-> column,
+// coalesced row segments) and row group w >> 1 (a quarter of the rows); scan, compaction rings, fast path and the
+// out-of-line reference-order path are those of k_iou_pairwise2.
+constexpr int kFC = 64;
+struct RowsTile {
+    float crec[kFC * kRecStride];
+    float rrec[32 * kRecStride];
+    float4 ccull[kFC][2];
+    float4 rcull[32][2];
+    unsigned short ring[kThreads / 32][2][kRing];
+};
+
+__device__ __forceinline__ void put_rec(float* base, int i, const BoxRec& b) {
+    float4* d = reinterpret_cast<float4*>(base + i * kRecStride);
+    d[0] = make_float4(b.t, b.p, b.tj, b.pj);
+    d[1] = make_float4(b.sp, b.cp, b.w, b.h);
+    d[2] = make_float4(b.sg, b.cg, b.a, b.b);
+    d[3] = make_float4(b.g, b.flag, 0.0f, 0.0f);
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreads)
+k_iou_rows32(const float* __restrict__ rows, int R, const float* __restrict__ cols, int64_t C, int kind, int mode, int edge,
+             float* __restrict__ out, int64_t ld, bool dense, bool rows_vec, bool cols_vec) {
+    __shared__ __align__(16) RowsTile T;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // column tiles heaviest-first (anchor lists end with the coarse pyramid levels), as in k_iou_pairwise2
+    const int64_t c0 = (int64_t)(gridDim.x - 1u - blockIdx.x) * kFC;
+    const int cg = warp & 1, rpw = (R + 3) >> 2;
+    const int r_lo = min(R, (warp >> 1) * rpw), r_hi = min(R, r_lo + rpw);
+    const int cl = cg * 32 + lane;
+    const bool col_ok = c0 + cl < C;
+    {
+        // zero-fill this warp's [rows x 32] part of the matrix; live pairs overwrite their entry later (same warp:
+        // ordered by the __syncthreads() below and the __syncwarp() in front of every batch)
+        float* base = out + c0 + cg * 32;
+        const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0) && (c0 + cg * 32 + 32 <= C);
+        if (vec) {
+            for (int rr = r_lo + (lane >> 3); rr < r_hi; rr += 4)
+                *reinterpret_cast<float4*>(base + rr * ld + (lane & 7) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else if (col_ok) {
+            for (int rr = r_lo; rr < r_hi; ++rr) base[rr * ld + lane] = 0.0f;
+        }
+    }
+    // ---- phase 0: per-box records (sphk_fast.cuh: box_pre) by threads 0..63 (columns) and 64..95 (rows)
+    if (tid < kFC + 32) {
+        const bool is_col = tid < kFC;
+        const int i = is_col ? tid : tid - kFC;
+        const bool ok = is_col ? (c0 + i < C) : (i < R);
+        float* recs = is_col ? T.crec : T.rrec;
+        float4* cu = is_col ? T.ccull[i] : T.rcull[i];
+        if (ok) {
+            const RawBox x = is_col ? load_box<D>(cols, c0 + i, cols_vec) : load_box<D>(rows, i, rows_vec);
+            BoxRec b;
+            BoxCull c;
+            box_pre(x, is_col ? 2 : 1, D, edge, &b, &c);
+            put_rec(recs, i, b);
+            cu[0] = make_float4(c.ux, c.uy, c.uz, c.rc);
+            cu[1] = make_float4(c.rs, c.bias, 0.0f, 0.0f);
+        } else {      // never evaluated: a flagged record and operands that fail every test
+            float4* d = reinterpret_cast<float4*>(recs + i * kRecStride);
+            d[0] = make_float4(0.f, 90.f, 0.f, 90.f); d[1] = make_float4(1.f, 0.f, 1e-2f, 1e-2f);
+            d[2] = make_float4(0.f, 1.f, 1.f, 1.f);   d[3] = make_float4(0.f, 1.f, 0.f, 0.f);
+            cu[0] = make_float4(0.f, 0.f, 1.f, 0.f);
+            cu[1] = make_float4(0.f, -10.f, 0.f, 0.f);
+        }
+    }
+    __syncthreads();
+    const float4 pc0 = T.ccull[cl][0], pc1 = T.ccull[cl][1];
+    // ---- phase 1: prefilter + compaction + batches, exactly as k_iou_pairwise2 (this thread's column is cl)
+    const float pbias = col_ok ? (dense ? -1e30f : pc1.y) : 1e30f;
+    int hf = 0, tf = 0, hs = 0, ts = 0;
+    const unsigned lt = (1u << lane) - 1u;
+    int r = r_lo;
+#pragma unroll 1
+    for (;;) {
+#pragma unroll 1
+        while (r < r_hi && tf - hf < 32) {
+            const float4 g0 = T.rcull[r][0];
+            const float2 g1 = *reinterpret_cast<const float2*>(&T.rcull[r][1]);
+            const float dot = fmaf(g0.x, pc0.x, fmaf(g0.y, pc0.y, g0.z * pc0.z));
+            const float thr = fmaf(g0.w, pc0.w, fmaf(-g1.x, pc1.x, g1.y + pbias));
+            const bool live = !(dot < thr);
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, live);
+            if (live) T.ring[warp][0][(tf + __popc(m & lt)) & (kRing - 1)] = (unsigned short)((r << 5) | lane);
+            tf += __popc(m);
+            ++r;
+        }
+        const bool rows_done = r >= r_hi;
+        if (tf > hf) {
+            const int cnt = min(tf - hf, 32);
+            __syncwarp();
+            const int e = T.ring[warp][0][(hf + lane) & (kRing - 1)];
+            __syncwarp();
+            bool slow = false;
+            if (lane < cnt) {
+                const int rr = e >> 5, c = cg * 32 + (e & 31);
+                float v;
+                slow = !pair_fast(load_rec(T.rrec, rr), load_rec(T.crec, c), D, kind, mode, &v);
+                if (!slow) out[rr * ld + c0 + c] = v;
+            }
+            const unsigned ms = __ballot_sync(0xFFFFFFFFu, slow);
+            if (slow) T.ring[warp][1][(ts + __popc(ms & lt)) & (kRing - 1)] = (unsigned short)e;
+            ts += __popc(ms);
+            hf += cnt;
+        }
+        const bool drained = rows_done && tf == hf;
+        const int need = drained ? 1 : 32;
+        while (ts - hs >= need) {
+            const int cnt = min(ts - hs, 32);
+            __syncwarp();
+            const int e = T.ring[warp][1][(hs + lane) & (kRing - 1)];
+            __syncwarp();
+            if (lane < cnt) {
+                const int rr = e >> 5, c = cg * 32 + (e & 31);
+                out[rr * ld + c0 + c] = slow_pair_iou(rows, rr, cols, c0 + c, D, kind, mode, edge, dense);
+            }
+            hs += cnt;
+        }
+        if (drained) break;
     }
 }
 
@@ -643,12 +799,19 @@ __global__ void k_fill_keys(unsigned long long* keys, int64_t n) {
     if (i < n) keys[i] = 0ull;
 }
 
-// unpack (max, argmax); a key that was never raised (no column/row at all) reports (0, base)
-__global__ void k_unpack_keys(const unsigned long long* __restrict__ keys, int64_t n, float* __restrict__ vmax,
-                              int32_t* __restrict__ arg, uint32_t base) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const unsigned long long k = keys[i];
+// unpack (max, argmax); a key that was never raised (no column/row at all) reports (0, base).
+// rows [0, nr) from keys_a, then columns [0, nc) from keys_b, in one launch
+__global__ void k_unpack_keys2(const unsigned long long* __restrict__ keys_a, int64_t na, float* __restrict__ vmax_a,
+                               int32_t* __restrict__ arg_a, uint32_t base_a, const unsigned long long* __restrict__ keys_b,
+                               int64_t nb, float* __restrict__ vmax_b, int32_t* __restrict__ arg_b, uint32_t base_b) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= na + nb) return;
+    const bool second = i >= na;
+    if (second) i -= na;
+    const unsigned long long k = second ? keys_b[i] : keys_a[i];
+    float* vmax = second ? vmax_b : vmax_a;
+    int32_t* arg = second ? arg_b : arg_a;
+    const uint32_t base = second ? base_b : base_a;
     if (vmax) vmax[i] = (k == 0ull) ? 0.0f : __uint_as_float((uint32_t)(k >> 32));
     if (arg) arg[i] = (k == 0ull) ? (int32_t)base : (int32_t)(0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull));
 }
@@ -1385,10 +1548,14 @@ static int launch_pairwise2(int kind, const float* rows, int64_t R, const float*
                             float4* rec, float4* cull, float* out, int64_t ld, unsigned long long* rkey,
                             unsigned long long* ckey, int32_t row_base, int32_t col_base, const float* row_target,
                             int* col_tie, const int32_t* row_offsets, int64_t col_stride, int batch, int64_t max_rows,
-                            cudaStream_t s) {
+                            cudaStream_t s, bool zero_keys = false) {
     const int64_t col_tiles = (C + kThreads - 1) / kThreads;
-    if (D == 4) k_box_pre<4><<<blocks_for(R + C), kThreads, 0, s>>>(rows, R, cols, C, edge, rec, cull, aligned16(rows), aligned16(cols));
-    else k_box_pre<5><<<blocks_for(R + C), kThreads, 0, s>>>(rows, R, cols, C, edge, rec, cull, false, false);
+    // single-image calls: the key arrays have one entry per box and are zeroed by k_box_pre (zero_keys)
+    unsigned long long* zr = (zero_keys && batch == 1) ? rkey : nullptr;
+    unsigned long long* zc = (zero_keys && batch == 1) ? ckey : nullptr;
+    if (g_probe & 1) {
+    } else if (D == 4) k_box_pre<4><<<blocks_for(R + C), kThreads, 0, s>>>(rows, R, cols, C, edge, rec, cull, aligned16(rows), aligned16(cols), zr, zc);
+    else k_box_pre<5><<<blocks_for(R + C), kThreads, 0, s>>>(rows, R, cols, C, edge, rec, cull, false, false, zr, zc);
     // row-tile height: 32 when that already yields many CTAs per SM, else 8 so that the heavy
     // (mostly-live) tiles are spread over more warps and the tail of the launch stays short
     const int64_t tiles32 = col_tiles * ((max_rows + 31) / 32) * batch;
@@ -1408,7 +1575,7 @@ static int launch_pairwise2(int kind, const float* rows, int64_t R, const float*
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = (g_probe & 2) ? 0 : 1;
     const float4* crec = rec;
     const float4* ccull = cull;
     const bool dn = g_dense != 0;
@@ -1460,8 +1627,9 @@ static int pairwise_impl(int kind, const float* rows, int64_t R, const float* co
     cudaStream_t s = (cudaStream_t)stream;
     unsigned long long* rkey = ext_rkey ? ext_rkey : (want_row ? (unsigned long long*)workspace : nullptr);
     unsigned long long* ckey = ext_ckey ? ext_ckey : (want_col ? (unsigned long long*)workspace + R : nullptr);
-    if (want_row && R > 0) k_fill_keys<<<blocks_for(R), kThreads, 0, s>>>(rkey, R);
-    if (want_col && C > 0) k_fill_keys<<<blocks_for(C), kThreads, 0, s>>>(ckey, C);
+    const bool pre_zeroes_keys = !approx && R > 0 && C > 0;      // k_box_pre of the same call does it
+    if (want_row && R > 0 && !pre_zeroes_keys) k_fill_keys<<<blocks_for(R), kThreads, 0, s>>>(rkey, R);
+    if (want_col && C > 0 && !pre_zeroes_keys) k_fill_keys<<<blocks_for(C), kThreads, 0, s>>>(ckey, C);
     if (R > 0 && C > 0) {
         if (!rows || !cols) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: null box pointer");
         const int64_t col_tiles = (C + kThreads - 1) / kThreads;
@@ -1477,16 +1645,29 @@ static int pairwise_impl(int kind, const float* rows, int64_t R, const float* co
                 k_iou_pairwise<KIND_FOV, 4><<<g, kThreads, 0, s>>>(rows, R, cols, C, mode, edge, out, ld, rkey, ckey, (uint32_t)row_base,
                                                                     (uint32_t)col_base, col_tiles, v, g_dense != 0);
         } else {
+            if (out && !want_row && !want_col && !row_target && !col_tie && R <= 32 && !g_no_rows32 &&
+                (C + kFC - 1) / kFC <= 0x7FFFFFFFll) {
+                // the per-image call of MaxIoUAssigner: one launch, records computed inside the CTAs
+                const unsigned g = (unsigned)((C + kFC - 1) / kFC);
+                if (D == 4) k_iou_rows32<4><<<g, kThreads, 0, s>>>(rows, (int)R, cols, C, kind, mode, edge, out, ld, g_dense != 0, aligned16(rows), aligned16(cols));
+                else k_iou_rows32<5><<<g, kThreads, 0, s>>>(rows, (int)R, cols, C, kind, mode, edge, out, ld, g_dense != 0, false, false);
+                SPHK_LAUNCH_CHECK("k_iou_rows32");
+                return SPHK_OK;
+            }
             float4* rec = (float4*)((char*)workspace + keys_bytes(R, C));       // [R + C][4] rows first
             float4* cull = rec + (R + C) * 4;                                    // [R + C][2]
             const int rc = launch_pairwise2(kind, rows, R, cols, C, D, mode, edge, rec, cull, out, ld, rkey, ckey, row_base,
-                                            col_base, row_target, col_tie, nullptr, 0, 1, R, s);
+                                            col_base, row_target, col_tie, nullptr, 0, 1, R, s, true);
             if (rc != SPHK_OK) return rc;
         }
         SPHK_LAUNCH_CHECK("k_iou_pairwise");
     }
-    if ((row_max || row_arg) && R > 0) k_unpack_keys<<<blocks_for(R), kThreads, 0, s>>>(rkey, R, row_max, row_arg, (uint32_t)col_base);
-    if ((col_max || col_arg) && C > 0) k_unpack_keys<<<blocks_for(C), kThreads, 0, s>>>(ckey, C, col_max, col_arg, (uint32_t)row_base);
+    {   // one launch unpacks the row keys and the column keys
+        const int64_t nr_ = (row_max || row_arg) ? R : 0, nc_ = (col_max || col_arg) ? C : 0;
+        if (nr_ + nc_ > 0)
+            k_unpack_keys2<<<blocks_for(nr_ + nc_), kThreads, 0, s>>>(rkey, nr_, row_max, row_arg, (uint32_t)col_base, ckey, nc_, col_max,
+                                                                    col_arg, (uint32_t)row_base);
+    }
     SPHK_LAUNCH_CHECK("k_unpack_keys");
     return SPHK_OK;
 }
@@ -1884,6 +2065,15 @@ int sphk_probe_fp32(int32_t blocks, int32_t iters, float* sink, void* stream) {
     SPHK_LAUNCH_CHECK("k_probe_fp32");
     return SPHK_OK;
 }
+
+#ifdef SPHK_TIMELINE
+int sphk_debug_timeline(unsigned long long* t, unsigned* sm, int n) {
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(t, g_tl, sizeof(unsigned long long) * 2 * n) != cudaSuccess) return -2;
+    if (cudaMemcpyFromSymbol(sm, g_tl_sm, sizeof(unsigned) * n) != cudaSuccess) return -3;
+    return 0;
+}
+#endif
 
 int sphk_set_dense(int on) {
     const int prev = g_dense;

@@ -253,6 +253,30 @@ def test_pairwise_equals_aligned_on_the_expansion(api, kind, R, C):
         assert torch.equal(mat.reshape(-1) == 0, flat == 0)
 
 
+@pytest.mark.parametrize("box", ["bfov", "rbfov"])
+@pytest.mark.parametrize("R,C", [(1, 1), (2, 63), (5, 64), (8, 65), (17, 1000), (31, 4097), (32, 98208)])
+def test_few_rows_single_launch_kernel(api, box, R, C):
+    """k_iou_rows32 (R <= 32: the per-image call of MaxIoUAssigner, records computed inside the CTAs) against the general
+    two-kernel path: the same rows inside a call with more than 32 rows go through k_box_pre + k_iou_pairwise2.  Same
+    per-box records, same fast / reference-order code: bit-identical results, for both transforms and IoF, on views
+    of a wider output and for unaligned inputs."""
+    rows = O.generate_boxes(R, alpha_range=(5, 120), beta_range=(5, 120), box=box, seed=R).to(DEV)
+    cols = O.generate_boxes(C, alpha_range=(1, 150), beta_range=(1, 150), box=box, seed=C + 7).to(DEV)
+    if C > 40:
+        cols[33] = rows[0]                                    # similarity-mask pair -> reference-order path
+        cols[C - 1, 2:4] = 400.0                               # oversize anchor (clamped by jitter_1)
+    pad = O.generate_boxes(40, alpha_range=(5, 120), beta_range=(5, 120), box=box, seed=99).to(DEV)
+    for fn, kw in ((api.iou.sph2pob_efficient_iou, {}), (api.iou.sph2pob_standard_iou, {}),
+                   (api.iou.sph2pob_efficient_iou, dict(mode="iof")), (api.iou.sph2pob_efficient_iou, dict(rbb_edge="chord"))):
+        got = fn(rows, cols, **kw)
+        want = fn(torch.cat([rows, pad]), cols, **kw)[:R]
+        assert got.shape == (R, C) and torch.equal(got, want), (fn.__name__, kw, float((got - want).abs().max()))
+    # unaligned input pointers (D = 4 takes the scalar loads then)
+    buf = torch.zeros(R * rows.size(1) + 1, device=DEV)
+    buf[1:] = rows.reshape(-1)
+    assert torch.equal(api.iou.sph2pob_efficient_iou(buf[1:].view(R, -1), cols), api.iou.sph2pob_efficient_iou(rows, cols))
+
+
 def test_fused_max_argmax(api):
     rows = O.generate_boxes(70, alpha_range=(5, 120), beta_range=(5, 120), box="rbfov", seed=1).to(DEV)
     cols = O.generate_boxes(3000, alpha_range=(5, 120), beta_range=(5, 120), box="rbfov", seed=2).to(DEV)
