@@ -458,10 +458,11 @@ def run_ours(args):
                 traffic = None
         roofline = {"bound": "hbm", "achieved": hbm_achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": hbm_achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peaks_src,
-                    "kernel": "k_iou_pairwise2", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": bytes_per_launch,
-                    "note": "kernel_ms = timed step / launches per step (CUDA events; includes the 6 us k_box_pre and launch gaps; "
-                            "ncu: 36 us for the kernel alone, profiles/).  HBM is NOT what bounds this kernel (4 B written per "
-                            "pair): see roofline_fp32"}
+                    "kernel": "k_iou_rows32" if args.workload == "assign" else "k_iou_pairwise2", "kernel_ms": kernel_ms,
+                    "algorithmic_bytes_per_launch": bytes_per_launch,
+                    "note": "kernel_ms = timed step / kernel launches per step (CUDA events on the launching stream, launch gaps "
+                            "included; the ncu launch list under profiles/ has the kernel alone).  HBM is NOT what bounds this "
+                            "kernel (4 B written per pair): see roofline_fp32"}
         result["roofline"] = roofline
         peak_tf = fp32_peak(torch, native, dev)
         tf = pairs_per_launch * FLOP_PER_PAIR / (kernel_ms * 1e-3) / 1e12
@@ -479,21 +480,32 @@ def run_ours(args):
         out_pin = torch.empty((IMAGES, GTS, anchors_h.size(0)), dtype=torch.float32).pin_memory()
         gts_d, anchors_d = torch.empty_like(gts_pin, device=dev), torch.empty_like(anchors_pin, device=dev)
 
+        side = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+
         def e2e_step():
-            # H2D of this step's inputs, 16 calculator calls, D2H of every matrix, all on the launching stream.
-            # (A side stream for the copies was tried: the per-call output allocation then has to be held across
-            # streams, which costs more than the overlap gains.  The step is bound by the 201 MB D2H over PCIe.)
+            # H2D of this step's inputs on the launching stream, then the 16 calculator calls alternate between two
+            # side streams, each call followed by the D2H of its matrix on its own stream: the kernel of image i + 1 runs
+            # while the copy engine drains image i (every call allocates, computes and copies on ONE stream, so the
+            # caching allocator needs no cross-stream bookkeeping).  The side streams fork from / join the launching
+            # stream, where the timing events are.  The step is bound by the 201 MB D2H over PCIe.
             gts_d.copy_(gts_pin, non_blocking=True)
             anchors_d.copy_(anchors_pin, non_blocking=True)
+            cur = torch.cuda.current_stream(dev)
+            for st in side:
+                st.wait_stream(cur)
             for i in range(IMAGES):
-                out_pin[i].copy_(calc(gts_d[i], anchors_d), non_blocking=True)
+                with torch.cuda.stream(side[i & 1]):
+                    out_pin[i].copy_(calc(gts_d[i], anchors_d), non_blocking=True)
+            for st in side:
+                cur.wait_stream(st)
         e2e_ms = time_steps(torch, e2e_step, max(3, args.steps // 2), 2, flush, barrier)
         t = torch.tensor([statistics.mean(e2e_ms)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": total_pairs_per_step / (float(t.item()) * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": gts_pin.numel() * 4 + anchors_pin.numel() * 4, "d2h_bytes_per_step": out_pin.numel() * 4,
-               "ms_per_step": float(t.item()), "api": "SphOverlaps2D('sph2pob_efficient_iou', 5)(gt, anchors) x 16, pinned host in/out"}
+               "ms_per_step": float(t.item()), "api": "SphOverlaps2D('sph2pob_efficient_iou', 5)(gt, anchors) x 16, pinned host in/out",
+               "streams": "calls alternate between 2 CUDA streams (compute of one image overlaps the D2H of the previous one)"}
         # the consumer only needs max/argmax (MaxIoUAssigner): fused variant, result = 12 B per anchor + 12 B per GT
         amax_pin = torch.empty((IMAGES, anchors_h.size(0)), dtype=torch.float32).pin_memory()
         aarg_pin = torch.empty((IMAGES, anchors_h.size(0)), dtype=torch.int64).pin_memory()

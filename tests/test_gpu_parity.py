@@ -298,6 +298,30 @@ def test_fused_max_argmax(api):
         assert torch.equal(rarg3, rarg + 5000) and torch.equal(carg3, carg + 1000)
 
 
+@pytest.mark.parametrize("R,C", [(1, 70), (7, 64), (20, 3000), (32, 98208)])
+def test_fused_max_argmax_few_rows(api, R, C):
+    """Fused max / argmax for the per-image shape (R <= 32 GT rows; the matrix itself comes from k_iou_rows32, the fused
+    maxima from k_iou_pairwise2): equal to max / first argmax of the matrix, ties to the lowest index, empty rows / columns
+    report (0, base), shard offsets are added."""
+    rows = O.generate_boxes(R, alpha_range=(5, 120), beta_range=(5, 120), box="rbfov", seed=R).to(DEV)
+    cols = O.generate_boxes(C, alpha_range=(5, 120), beta_range=(5, 120), box="rbfov", seed=C).to(DEV)
+    cols[10] = cols[C - 3] = rows[0]                                  # tie across CTAs: lowest column index must win
+    if R > 4:
+        rows[4] = rows[2]                                             # tie inside a column: lowest row index must win
+        rows[R - 1] = torch.tensor([0.0, 0.0, 1.0, 1.0, 0.0], device=DEV)   # a row that overlaps (almost) nothing
+    mat = api.iou.sph2pob_efficient_iou(rows, cols)
+    rmax, rarg, cmax, carg, mat2 = api.iou.sph_max_overlaps(rows, cols, return_matrix=True)
+    assert torch.equal(mat, mat2)
+    assert torch.equal(rmax, mat.max(dim=1)[0]) and torch.equal(cmax, mat.max(dim=0)[0])
+    m = mat.cpu().numpy()
+    assert rarg.cpu().tolist() == [int(np.flatnonzero(m[i] == m[i].max())[0]) for i in range(R)]
+    assert np.array_equal(carg.cpu().numpy(), (m == m.max(axis=0, keepdims=True)).argmax(axis=0))
+    rmax2, rarg2, cmax2, carg2 = api.iou.sph_max_overlaps(rows, cols)
+    assert torch.equal(rmax, rmax2) and torch.equal(rarg, rarg2) and torch.equal(cmax, cmax2) and torch.equal(carg, carg2)
+    _, rarg3, _, carg3 = api.iou.sph_max_overlaps(rows, cols, row_base=1000, col_base=5000)
+    assert torch.equal(rarg3, rarg + 5000) and torch.equal(carg3, carg + 1000)
+
+
 def test_sharding_emulated_on_one_gpu(api):
     """Two 'ranks' processed one after the other on one GPU; merging their packed keys with max() is what
     all_reduce(MAX)/all_gather do (the collective itself is covered by tests/test_sharded_gloo.py)."""

@@ -39,7 +39,7 @@ for k in kernels:
     units = rows[1]
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     traffic[k] = float(r[rd].replace(",", "")) * scale.get(units[rd], 1.0) + float(r[wr].replace(",", "")) * scale.get(units[wr], 1.0)
-    kern = {"aligned": "k_iou_aligned2", "aligned5": "k_iou_aligned2", "assign": "k_iou_pairwise2", "sweep": "k_iou_pairwise2",
+    kern = {"aligned": "k_iou_aligned2", "aligned5": "k_iou_aligned2", "assign": "k_iou_rows32", "sweep": "k_iou_pairwise2",
             "loss": "k_loss", "nms": "k_nms", "nms_pipeline": "k_nms", "assigner": "k_iou_pairwise2", "headloss": "k_decode_loss", "gdloss": "k_obb_loss"}[k]
     if k in ("aligned", "assign", "sweep", "headloss"):
         hot = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_hotspots.py"), rep,
