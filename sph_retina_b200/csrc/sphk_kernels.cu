@@ -39,6 +39,7 @@ const int g_force_tr = [] { const char* e = getenv("SPHK_TR"); return e ? atoi(e
 // timing probes (tools/assign_probe.py), never set in production: bit 0 = do not launch k_box_pre (stale records),
 // bit 1 = launch k_iou_pairwise2 without programmatic stream serialization
 const int g_no_rows32 = [] { const char* e = getenv("SPHK_NO_ROWS32"); return e ? atoi(e) : 0; }();   // A/B hook
+const int g_no_approx4 = [] { const char* e = getenv("SPHK_NO_APPROX4"); return e ? atoi(e) : 0; }();    // A/B hook
 const int g_probe = [] { const char* e = getenv("SPHK_PROBE"); return e ? atoi(e) : 0; }();
 
 int fail(int code, const char* what) {
@@ -129,6 +130,32 @@ __global__ void __launch_bounds__(kThreads) k_iou_aligned(const float* __restric
     if (KIND == KIND_SPH || KIND == KIND_FOV) v = approx_iou_pair(x, y, KIND);
     else v = sph2pob_iou_pair(x, y, D, KIND, mode, edge, dense);
     out[i] = v;
+}
+
+// Sph-IoU / FoV-IoU, aligned: ~100 instructions on 36 bytes per pair, i.e. bound by how many bytes are in flight.
+// Four pairs per thread, all eight 16-byte loads issued before the first use (a CTA covers 1024 consecutive pairs, the
+// four passes are each coalesced): 16 M pairs run at 5.4 TB/s (83 % of the measured copy bandwidth) against 4.7 TB/s
+// with one pair per thread; the one-pair kernel is kept for small launches, where thread count matters more.
+template <int KIND>
+__global__ void __launch_bounds__(kThreads) k_approx_aligned4(const float4* __restrict__ b1, const float4* __restrict__ b2,
+                                                               int64_t P, float* __restrict__ out) {
+    const int64_t i0 = (int64_t)blockIdx.x * (kThreads * 4) + threadIdx.x;
+    float4 x[4], y[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int64_t i = i0 + k * kThreads;
+        if (i < P) { x[k] = __ldg(b1 + i); y[k] = __ldg(b2 + i); }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int64_t i = i0 + k * kThreads;
+        if (i < P) {
+            RawBox a, b;
+            a.t = x[k].x; a.p = x[k].y; a.a = x[k].z; a.b = x[k].w; a.g = 0.0f;
+            b.t = y[k].x; b.p = y[k].y; b.a = y[k].z; b.b = y[k].w; b.g = 0.0f;
+            out[i] = approx_iou_pair(a, b, KIND);
+        }
+    }
 }
 
 // ---- aligned, Sph2Pob kinds: cheap conservative cull for all pairs, everything exact warp-compacted ---------
@@ -1507,7 +1534,11 @@ int sphk_iou_aligned(int kind, const float* b1, const float* b2, int64_t P, int 
         else k_iou_project<5><<<blocks_for(P), kThreads, 0, s>>>(b1, P, b2, P, true, kind, mode, edge, out, 0);
     } else if (kind == SPHK_KIND_SPH || kind == SPHK_KIND_FOV) {
         const unsigned g = blocks_for(P);
-        if (kind == SPHK_KIND_SPH) k_iou_aligned<KIND_SPH, 4><<<g, kThreads, 0, s>>>(b1, b2, P, mode, edge, out, v, g_dense != 0);
+        if (v && !g_no_approx4 && P >= (int64_t)3 << 20) {      // below ~3 M pairs one pair per thread keeps more loads in flight
+            const unsigned g4 = (unsigned)((P + kThreads * 4 - 1) / (kThreads * 4));
+            if (kind == SPHK_KIND_SPH) k_approx_aligned4<KIND_SPH><<<g4, kThreads, 0, s>>>((const float4*)b1, (const float4*)b2, P, out);
+            else k_approx_aligned4<KIND_FOV><<<g4, kThreads, 0, s>>>((const float4*)b1, (const float4*)b2, P, out);
+        } else if (kind == SPHK_KIND_SPH) k_iou_aligned<KIND_SPH, 4><<<g, kThreads, 0, s>>>(b1, b2, P, mode, edge, out, v, g_dense != 0);
         else k_iou_aligned<KIND_FOV, 4><<<g, kThreads, 0, s>>>(b1, b2, P, mode, edge, out, v, g_dense != 0);
     } else {
         // persistent warps: at most one resident wave (MINB CTAs of 8 warps per SM), at least 4 rounds of 32 pairs per
