@@ -245,7 +245,7 @@ def fp32_peak(torch, native, dev):
     return best
 
 
-def other_configs(torch, native, dev, flush):
+def other_configs(torch, native, dev, flush, hbm_peak_gbs=6544.3):
     """The remaining BASELINE.json configurations, timed briefly on one GPU (kernel time, inputs resident)."""
     from sph_retina_b200 import synthetic as S
     from sph_retina_b200.sphdet.bbox.nms import sph_batched_nms_images
@@ -266,6 +266,16 @@ def other_configs(torch, native, dev, flush):
     ms = quick(torch, lambda: sph2pob_efficient_iou(b1, b2, is_aligned=True), flush=flush)
     native.set_dense(False)
     out["aligned_1M_rbfov_dense"] = {"ms": ms, "pairs_per_s": n / ms * 1e3}
+    # the same calls at 16 M pairs (inputs 512 MB, larger than L2): the throughput once the ~10 us of launch + ramp are amortised
+    n16 = 16_000_000
+    c1 = S.generate_boxes(n16, alpha_range=(1, 100), beta_range=(1, 100), box="bfov", seed=0).to(dev)
+    c2 = S.generate_boxes(n16, alpha_range=(1, 100), beta_range=(1, 100), box="bfov", seed=1).to(dev)
+    ms = quick(torch, lambda: sph2pob_efficient_iou(c1, c2, is_aligned=True), iters=5, flush=flush)
+    out["aligned_16M_bfov"] = {"ms": ms, "pairs_per_s": n16 / ms * 1e3}
+    ms = quick(torch, lambda: sph_iou(c1, c2, is_aligned=True), iters=5, flush=flush)
+    out["aligned_16M_sph_iou"] = {"ms": ms, "pairs_per_s": n16 / ms * 1e3, "hbm_gbs": n16 * 36 / ms / 1e6,
+                                  "hbm_frac_of_measured_peak": n16 * 36 / ms / 1e6 / hbm_peak_gbs}
+    del c1, c2
     pred, target = S.loss_pairs(200_000)
     pred, target = pred.to(dev), target.to(dev)
     L = Sph2PobIoULoss(mode="iou", reduction="sum")
@@ -555,7 +565,7 @@ def run_ours(args):
         if world == 1 and not args.no_extras:
             if True:
                 try:
-                    line["other_configs"] = other_configs(torch, native, dev, flush)
+                    line["other_configs"] = other_configs(torch, native, dev, flush, peaks["hbm_gbs"])
                 except Exception as e:   # the headline line must still be printed
                     line["other_configs"] = {"error": repr(e)}
         emit(line)

@@ -668,6 +668,10 @@ k_iou_rows32(const float* __restrict__ rows, int R, const float* __restrict__ co
              float* __restrict__ out, int64_t ld, bool dense, bool rows_vec, bool cols_vec) {
     __shared__ __align__(16) RowsTile T;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef SPHK_TIMELINE
+    unsigned long long tl0 = 0;
+    if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl0));
+#endif
     // column tiles heaviest-first (anchor lists end with the coarse pyramid levels), as in k_iou_pairwise2
     const int64_t c0 = (int64_t)(gridDim.x - 1u - blockIdx.x) * kFC;
     const int cg = warp & 1, rpw = (R + 3) >> 2;
@@ -763,6 +767,15 @@ k_iou_rows32(const float* __restrict__ rows, int R, const float* __restrict__ co
         }
         if (drained) break;
     }
+#ifdef SPHK_TIMELINE
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long tl1; unsigned smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl1));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        if (blockIdx.x < 16384) { g_tl[2 * blockIdx.x] = tl0; g_tl[2 * blockIdx.x + 1] = tl1; g_tl_sm[blockIdx.x] = smid; }
+    }
+#endif
 }
 
 // ---- MaxIoUAssigner without the matrix (mmdet/core/bbox/assigners/max_iou_assigner.py:135-220) ------------

@@ -271,6 +271,11 @@ def test_few_rows_single_launch_kernel(api, box, R, C):
         got = fn(rows, cols, **kw)
         want = fn(torch.cat([rows, pad]), cols, **kw)[:R]
         assert got.shape == (R, C) and torch.equal(got, want), (fn.__name__, kw, float((got - want).abs().max()))
+    # a view of a wider output (ld > C, rows not 16-byte aligned): only the view is written
+    wide = torch.full((R, C + 7), -1.0, device=DEV)
+    api.native.iou_pairwise("sph2pob_efficient", rows, cols, out=wide[:, 3:3 + C])
+    assert torch.equal(wide[:, 3:3 + C], api.iou.sph2pob_efficient_iou(rows, cols))
+    assert bool((wide[:, :3] == -1).all()) and bool((wide[:, 3 + C:] == -1).all())
     # unaligned input pointers (D = 4 takes the scalar loads then)
     buf = torch.zeros(R * rows.size(1) + 1, device=DEV)
     buf[1:] = rows.reshape(-1)
