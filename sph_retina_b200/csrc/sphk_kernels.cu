@@ -490,7 +490,7 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
                 float* __restrict__ out, int64_t ld, unsigned long long* __restrict__ row_key,
                 unsigned long long* __restrict__ col_key, uint32_t row_base, uint32_t col_base, bool dense,
                 const float* __restrict__ row_target, int* __restrict__ col_tie,
-                const int32_t* __restrict__ row_offsets, int64_t col_stride) {
+                const int32_t* __restrict__ row_offsets, int64_t col_stride, float* __restrict__ tile_rmax) {
     __shared__ __align__(16) PairTile<TR> T;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #ifdef SPHK_TIMELINE
@@ -534,6 +534,13 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
     // Programmatic dependent launch: everything above overlaps the tail of k_box_pre; its records are
     // needed from here on.
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (o.tie && tile_rmax) {
+        // Tie pass of the assigner: an entry can equal its row's maximum only inside a tile whose own maximum of that
+        // row IS the maximum.  The max / argmax pass left every tile's row maxima in tile_rmax[column tile][row]: all
+        // but a handful of tiles leave here (a disabled row has target -1, a tile maximum is >= 0).
+        const bool mine = tid < nr && tile_rmax[(int64_t)ct * R + o.r0 + tid] == __ldg(row_target + o.r0 + tid);
+        if (!__syncthreads_or(mine ? 1 : 0)) return;
+    }
     // ---- phase 0: stage the tile's records (columns: records -> shared memory, cull operands -> registers)
     stage_rec(T.crec, tid, rec + R * 4, o.c0 + tid, col_ok);
     T.ckey[tid] = 0ull;
@@ -629,6 +636,7 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
         if (o.want_row && tid < nr) {
             const unsigned long long key = T.rkey[tid];
             if (key != 0ull && key > row_key[o.r0 + tid]) atomicMax(&row_key[o.r0 + tid], key);
+            if (tile_rmax) tile_rmax[(int64_t)ct * R + o.r0 + tid] = __uint_as_float((uint32_t)(key >> 32));
         }
         if (o.want_col && col_ok) {
             const unsigned long long key = T.ckey[tid];
@@ -1592,12 +1600,12 @@ static int launch_pairwise2(int kind, const float* rows, int64_t R, const float*
                             float4* rec, float4* cull, float* out, int64_t ld, unsigned long long* rkey,
                             unsigned long long* ckey, int32_t row_base, int32_t col_base, const float* row_target,
                             int* col_tie, const int32_t* row_offsets, int64_t col_stride, int batch, int64_t max_rows,
-                            cudaStream_t s, bool zero_keys = false) {
+                            cudaStream_t s, bool zero_keys = false, float* tile_rmax = nullptr, bool records_ready = false) {
     const int64_t col_tiles = (C + kThreads - 1) / kThreads;
     // single-image calls: the key arrays have one entry per box and are zeroed by k_box_pre (zero_keys)
     unsigned long long* zr = (zero_keys && batch == 1) ? rkey : nullptr;
     unsigned long long* zc = (zero_keys && batch == 1) ? ckey : nullptr;
-    if (g_probe & 1) {
+    if ((g_probe & 1) || records_ready) {      // (records_ready: a second pass over the operands of the previous launch)
     } else if (D == 4) k_box_pre<4><<<blocks_for(R + C), kThreads, 0, s>>>(rows, R, cols, C, edge, rec, cull, aligned16(rows), aligned16(cols), zr, zc);
     else k_box_pre<5><<<blocks_for(R + C), kThreads, 0, s>>>(rows, R, cols, C, edge, rec, cull, false, false, zr, zc);
     // row-tile height: 32 when that already yields many CTAs per SM, else 8 so that the heavy
@@ -1626,7 +1634,7 @@ static int launch_pairwise2(int kind, const float* rows, int64_t R, const float*
     cudaError_t le;
 #define SPHK_PW2(DD, TR)                                                                                               \
     le = cudaLaunchKernelEx(&cfg, k_iou_pairwise2<DD, TR>, rows, R, cols, C, crec, ccull, kind, mode, edge, out, ld, rkey, \
-                            ckey, (uint32_t)row_base, (uint32_t)col_base, dn, row_target, col_tie, row_offsets, col_stride)
+                            ckey, (uint32_t)row_base, (uint32_t)col_base, dn, row_target, col_tie, row_offsets, col_stride, tile_rmax)
     if (D == 4 && tr == 32) SPHK_PW2(4, 32);
     else if (D == 4 && tr == 16) SPHK_PW2(4, 16);
     else if (D == 4) SPHK_PW2(4, 8);
@@ -1752,9 +1760,11 @@ static inline int64_t align16(int64_t x) { return (x + 15) & ~15ll; }
 
 int64_t sphk_max_iou_assign_workspace_bytes(int64_t sumK, int64_t N, int32_t batch) {
     if (sumK < 0 || N < 0 || batch < 0) return 0;
-    // row keys, column keys per image, records, tie targets, per-image zero rows, per (image, anchor) claims, offsets
+    // row keys, column keys per image, records, tie targets, per-image zero rows, per (image, anchor) claims, offsets,
+    // per (column tile, GT) maxima for the tie pass
     return align16(sumK * 8) + align16((int64_t)batch * N * 8) + (sumK + N) * (int64_t)((kBoxRecFloats + kBoxCullFloats) * sizeof(float)) +
-           align16(sumK * 4) + align16((int64_t)batch * 4) + align16((int64_t)batch * N * 4) + align16(((int64_t)batch + 1) * 4);
+           align16(sumK * 4) + align16((int64_t)batch * 4) + align16((int64_t)batch * N * 4) + align16(((int64_t)batch + 1) * 4) +
+           align16(sumK * ((N + kThreads - 1) / kThreads) * 4);
 }
 
 int sphk_max_iou_assign(int kind, const float* gts, const int32_t* gt_offsets_host, int32_t batch, const float* boxes,
@@ -1785,7 +1795,8 @@ int sphk_max_iou_assign(int kind, const float* gts, const int32_t* gt_offsets_ho
     float* target = (float*)w;                                     w += align16(sumK * 4);
     int* zero_row = (int*)w;                                       w += align16((int64_t)batch * 4);
     int* last = (int*)w;                                           w += align16((int64_t)batch * N * 4);
-    int32_t* offsets = (int32_t*)w;
+    int32_t* offsets = (int32_t*)w;                                w += align16(((int64_t)batch + 1) * 4);
+    float* tile_rmax = (float*)w;      // [column tiles][sumK], written by every tile of pass 1 before pass 2 reads it
     cudaError_t e = cudaMemcpyAsync(offsets, gt_offsets_host, ((size_t)batch + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, s);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(gt_offsets)");
     // one memset covers row keys + column keys; another one the zero rows + claims
@@ -1795,7 +1806,7 @@ int sphk_max_iou_assign(int kind, const float* gts, const int32_t* gt_offsets_ho
     if (sumK > 0) {
         // pass 1: per-GT and per-(image, anchor) max / argmax
         int rc = launch_pairwise2(kind, gts, sumK, boxes, N, D, SPHK_MODE_IOU, SPHK_EDGE_ARC, rec, cull, nullptr, N, rkey, ckey, 0, 0,
-                                  nullptr, nullptr, offsets, N, batch, max_rows, s);
+                                  nullptr, nullptr, offsets, N, batch, max_rows, s, false, tile_rmax);
         if (rc != SPHK_OK) return rc;
         if (match_low_quality) {
             k_assign_targets<<<blocks_for(sumK), kThreads, 0, s>>>(rkey, sumK, offsets, batch, N, min_pos_iou, gt_max_assign_all != 0,
@@ -1803,7 +1814,7 @@ int sphk_max_iou_assign(int kind, const float* gts, const int32_t* gt_offsets_ho
             if (gt_max_assign_all) {
                 // pass 2: which anchors tie the row maxima (same kernel, same operands: bit-identical overlaps)
                 rc = launch_pairwise2(kind, gts, sumK, boxes, N, D, SPHK_MODE_IOU, SPHK_EDGE_ARC, rec, cull, nullptr, N, nullptr, nullptr,
-                                      0, 0, target, last, offsets, N, batch, max_rows, s);
+                                      0, 0, target, last, offsets, N, batch, max_rows, s, false, tile_rmax, true);
                 if (rc != SPHK_OK) return rc;
             }
         }
