@@ -298,6 +298,18 @@ def other_configs(torch, native, dev, flush, hbm_peak_gbs=6544.3):
         ms = quick(torch, fb, flush=flush)
         other[name] = {"fwd_bwd_ms": ms, "pairs_per_s_fwd_bwd": 200_000 / ms * 1e3}
     out["other_losses_200k_rbfov"] = other
+    # training targets of the head for the 16 images (assign -> PseudoSampler -> labels / weights / box targets): two C-ABI calls
+    from sph_retina_b200.sphdet.assigners import SphMaxIoUAssigner
+    from sph_retina_b200.sphdet.models.heads import get_targets_batch
+    gts16, anc = S.assignment_batch(images=16)
+    gts16, anc = gts16.to(dev), anc.to(dev)
+    glist = list(gts16)
+    llist = [torch.randint(0, 80, (g.size(0),), device=dev) for g in glist]
+    asg = SphMaxIoUAssigner(0.5, 0.4, min_pos_iou=0, iou_calculator=dict(type='SphOverlaps2D', backend='sph2pob_efficient_iou', box_version=5))
+    ms = quick(torch, lambda: get_targets_batch(anc, glist, llist, asg, 80, sync_counts=False), flush=flush)
+    out["train_targets_16img"] = {"ms": ms, "anchors_per_s": 16 * anc.size(0) / ms * 1e3,
+                                  "what": "SphMaxIoUAssigner + PseudoSampler + anchor_head._get_targets_single for 16 images x 98208 "
+                                          "anchors x 32 GT: sphk_max_iou_assign + sphk_anchor_targets, no host sync"}
     boxes, scores, labels, image_ids = (t.to(dev) for t in S.nms_batch(64, 1000, 80))
     ms = quick(torch, lambda: sph_batched_nms_images(boxes, scores, labels, image_ids, 0.5), iters=5, flush=flush)
     ms_h = quick(torch, lambda: sph_batched_nms_images(boxes, scores, labels, image_ids, 0.5, num_images=64, num_classes=80,

@@ -109,6 +109,22 @@ int sphk_max_iou_assign(int kind, const float* gts, const int32_t* gt_offsets_ho
                         int gt_max_assign_all, int match_low_quality, const int64_t* gt_labels, int64_t* gt_inds,
                         float* max_overlaps, int64_t* labels, void* workspace, void* stream);
 
+/* Training targets of the anchor head for a batch of images that share the anchors, PseudoSampler case
+ * (mmdet/models/dense_heads/anchor_head.py:254-285 _get_targets_single; mmdet/core/bbox/samplers/pseudo_sampler.py),
+ * computed from the assignment of sphk_max_iou_assign without leaving the device:
+ *   gt_inds      [batch, N]     0 = negative, -1 = ignored, k + 1 = positive for GT k of its image
+ *   anchors [N, D], gts [sumK, D] (all images), gt_labels [sumK] or NULL (then positives get label 0),
+ *   gt_offsets   [batch + 1]    DEVICE array: image b owns gts[gt_offsets[b] : gt_offsets[b + 1]]
+ *   num_classes  background label; pos_weight: train_cfg.pos_weight (<= 0: positives weigh 1)
+ *   reg_decoded_bbox != 0: bbox_targets = the assigned GT box; else bbox_coder.encode(anchor, GT) with the HOST arrays
+ *                means / stds (D floats each, NULL = 0 / 1)
+ *   labels [batch, N] int64, label_weights [batch, N], bbox_targets / bbox_weights [batch, N, D]
+ *   counts [batch, 2] int32: positives, negatives per image (zeroed here) */
+int sphk_anchor_targets(const int64_t* gt_inds, int32_t batch, int64_t N, int D, const float* anchors, const float* gts,
+                        const int64_t* gt_labels, const int32_t* gt_offsets, int64_t num_classes, float pos_weight,
+                        int reg_decoded_bbox, const float* means, const float* stds, int64_t* labels, float* label_weights,
+                        float* bbox_targets, float* bbox_weights, int32_t* counts, void* stream);
+
 /* Sph2Pob loss, fused forward + backward (Sph2PobIoULoss, mode='iou'):
  * replaces Sph2PobTransfrom.new_forward (sphdet/losses/sph2pob_transform.py:24-35: jitter_1,
  * sph2pob_standard, jitter_2) followed by diff_iou_rotated_2d(...).clamp(0,1)

@@ -650,6 +650,30 @@ def assign_wrt_overlaps(overlaps, gt_labels=None, pos_iou_thr=0.5, neg_iou_thr=0
     return assigned, max_overlaps, labels
 
 
+def get_targets_single(anchors, gt_bboxes, gt_labels, gt_inds, num_classes, reg_decoded_bbox=True, pos_weight=-1,
+                       means=None, stds=None):
+    """mmdet/models/dense_heads/anchor_head.py:254-285 (_get_targets_single after the assigner, every anchor valid) with the
+    PseudoSampler (mmdet/core/bbox/samplers/pseudo_sampler.py:33-39: pos = nonzero(gt_inds > 0), neg = nonzero(gt_inds == 0)).
+    Returns (labels, label_weights, bbox_targets, bbox_weights, num_pos, num_neg)."""
+    n = anchors.size(0)
+    bbox_targets = torch.zeros_like(anchors, dtype=torch.float)
+    bbox_weights = torch.zeros_like(anchors)
+    labels = anchors.new_full((n,), num_classes, dtype=torch.long)
+    label_weights = anchors.new_zeros(n, dtype=torch.float)
+    pos_inds = torch.nonzero(gt_inds > 0, as_tuple=False).squeeze(-1).unique()
+    neg_inds = torch.nonzero(gt_inds == 0, as_tuple=False).squeeze(-1).unique()
+    if len(pos_inds) > 0:
+        pos_gt = gt_bboxes[gt_inds[pos_inds] - 1]
+        pos_bbox_targets = pos_gt if reg_decoded_bbox else bbox2delta(anchors[pos_inds], pos_gt, means, stds)
+        bbox_targets[pos_inds, :] = pos_bbox_targets.float()
+        bbox_weights[pos_inds, :] = 1.0
+        labels[pos_inds] = 0 if gt_labels is None else gt_labels[gt_inds[pos_inds] - 1]
+        label_weights[pos_inds] = 1.0 if pos_weight <= 0 else pos_weight
+    if len(neg_inds) > 0:
+        label_weights[neg_inds] = 1.0
+    return labels, label_weights, bbox_targets, bbox_weights, len(pos_inds), len(neg_inds)
+
+
 # --------------------------------------------------------------------------- #
 # synthetic inputs (tests/utils/generate_data.py:10-42, dtype='float' branch)
 # --------------------------------------------------------------------------- #

@@ -44,6 +44,9 @@ SIGNATURES = {
     "sphk_max_iou_assign": (_int, [_int, _c_float_p, ctypes.POINTER(_i32), _i32, _c_float_p, _i64, _int, ctypes.c_float,
                                    ctypes.c_float, ctypes.c_float, ctypes.c_float, _int, _int, ctypes.c_void_p, ctypes.c_void_p,
                                    _c_float_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "sphk_anchor_targets": (_int, [ctypes.c_void_p, _i32, _i64, _int, _c_float_p, _c_float_p, ctypes.c_void_p, ctypes.c_void_p, _i64,
+                                   ctypes.c_float, _int, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), ctypes.c_void_p,
+                                   _c_float_p, _c_float_p, _c_float_p, ctypes.c_void_p, ctypes.c_void_p]),
     "sphk_loss_fwd_bwd": (_int, [_c_float_p, _c_float_p, _i64, _int, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
                                  ctypes.c_void_p]),
     "sphk_loss_reduce_partials": (_i64, [_i64]),
@@ -289,6 +292,40 @@ def max_iou_assign(kind: str, gts, gt_offsets, boxes, pos_iou_thr, neg_lo, neg_h
                                        _ptr(max_overlaps), _ptr(labels), _ptr(ws), _stream(boxes)))
     launches += 6
     return gt_inds, max_overlaps, labels
+
+
+def anchor_targets(gt_inds, anchors, gts, gt_labels, gt_offsets, num_classes, pos_weight=-1.0, reg_decoded_bbox=True, means=None,
+                   stds=None):
+    """labels, label_weights, bbox_targets, bbox_weights, counts[B, 2] of the anchor head from an assignment
+    (sphk_anchor_targets).  gt_inds [B, N] int64 as returned by max_iou_assign; gt_offsets: python list of B + 1 ints."""
+    global launches
+    anchors = _boxes(anchors, "anchors")
+    dev, N, D = anchors.device, anchors.size(0), anchors.size(1)
+    B = len(gt_offsets) - 1
+    sumK = int(gt_offsets[-1])
+    assert gt_inds.shape == (B, N) and gt_inds.dtype == torch.int64 and gt_inds.is_cuda and gt_inds.is_contiguous()
+    if sumK > 0:
+        gts = _boxes(gts, "gt_bboxes")
+        assert gts.shape == (sumK, D)
+        if gt_labels is not None:
+            gt_labels = gt_labels.to(device=dev, dtype=torch.int64).contiguous()
+            assert gt_labels.numel() == sumK
+    else:
+        gts, gt_labels = None, None
+    offs = torch.tensor([int(v) for v in gt_offsets], dtype=torch.int32).to(dev, non_blocking=True)
+    labels = torch.empty((B, N), dtype=torch.int64, device=dev)
+    label_weights = torch.empty((B, N), dtype=torch.float32, device=dev)
+    bbox_targets = torch.empty((B, N, D), dtype=torch.float32, device=dev)
+    bbox_weights = torch.empty((B, N, D), dtype=torch.float32, device=dev)
+    counts = torch.empty((B, 2), dtype=torch.int32, device=dev)
+    if B > 0:
+        with _on_device(dev):
+            _check(lib.sphk_anchor_targets(_ptr(gt_inds), B, N, D, _ptr(anchors), _ptr(gts), _ptr(gt_labels), _ptr(offs), int(num_classes),
+                                           float(pos_weight), int(bool(reg_decoded_bbox)), _host5(means, D, 0.0), _host5(stds, D, 1.0),
+                                           _ptr(labels), _ptr(label_weights), _ptr(bbox_targets), _ptr(bbox_weights), _ptr(counts),
+                                           _stream(anchors)))
+        launches += 1
+    return labels, label_weights, bbox_targets, bbox_weights, counts
 
 
 def loss_fwd_bwd(pred, target, grad_iou=None, want_grad_pred=False, want_grad_target=False):

@@ -1105,6 +1105,50 @@ k_coder_encode(const float* __restrict__ proposals, const float* __restrict__ gt
     store_grad<D>(out, i, v, vec_ok);
 }
 
+// ---- training targets of the anchor head (mmdet/models/dense_heads/anchor_head.py:254-285, PseudoSampler) -------
+// From the assignment (gt_inds: 0 negative, -1 ignored, k + 1 = GT k of the image) straight to what loss_single
+// consumes: labels, label_weights, bbox_targets (the GT box itself with reg_decoded_bbox, else bbox_coder.encode(anchor,
+// GT)), bbox_weights and the per-image positive / negative counts.  One thread per (image, anchor); grid.y = image.
+template <int D>
+__global__ void __launch_bounds__(kThreads)
+k_anchor_targets(const int64_t* __restrict__ gt_inds, int64_t N, const float* __restrict__ anchors, const float* __restrict__ gts,
+                 const int64_t* __restrict__ gt_labels, const int32_t* __restrict__ offsets, int64_t num_classes, float pos_w,
+                 bool decoded, CoderParams cp, int64_t* __restrict__ labels, float* __restrict__ label_weights,
+                 float* __restrict__ bbox_targets, float* __restrict__ bbox_weights, int32_t* __restrict__ counts) {
+    __shared__ int s_cnt[2];
+    if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int b = blockIdx.y;
+    const int64_t a = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    bool pos = false, neg = false;
+    if (a < N) {
+        const int64_t i = (int64_t)b * N + a;
+        const int64_t gi = gt_inds[i];
+        pos = gi > 0; neg = gi == 0;
+        float t[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        int64_t lab = num_classes;
+        if (pos) {
+            const int64_t g = (int64_t)offsets[b] + gi - 1;
+            const RawBox gt = load_box<D>(gts, g, false);
+            if (decoded) { t[0] = gt.t; t[1] = gt.p; t[2] = gt.a; t[3] = gt.b; t[4] = gt.g; }
+            else coder_encode(load_box<D>(anchors, a, false), gt, D, cp, t);
+            lab = gt_labels ? gt_labels[g] : 0;            // only an RPN passes gt_labels = None: foreground = class 0
+        }
+        labels[i] = lab;
+        label_weights[i] = pos ? (pos_w <= 0.0f ? 1.0f : pos_w) : (neg ? 1.0f : 0.0f);
+        const float w = pos ? 1.0f : 0.0f;
+#pragma unroll
+        for (int k = 0; k < D; ++k) { bbox_targets[i * D + k] = t[k]; bbox_weights[i * D + k] = w; }
+    }
+    const unsigned mp = __ballot_sync(0xFFFFFFFFu, pos), mn = __ballot_sync(0xFFFFFFFFu, neg);
+    if ((threadIdx.x & 31) == 0) {
+        if (mp) atomicAdd(&s_cnt[0], __popc(mp));
+        if (mn) atomicAdd(&s_cnt[1], __popc(mn));
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 && s_cnt[threadIdx.x]) atomicAdd(&counts[b * 2 + threadIdx.x], s_cnt[threadIdx.x]);
+}
+
 // Persistent warps scan the rows 32 at a time: read the weight(s), zero the row's gradient, ballot-compact the rows
 // with a non-zero weight into a per-warp ring; 32 queued rows at a time go through decode + loss + backward.
 // The loss is accumulated per lane in a fixed order and reduced per CTA: deterministic for a given n.
@@ -1937,6 +1981,30 @@ static int coder_params(const char* who, int D, const float* means, const float*
     cp->clip_border = clip_border ? 1 : 0;
     cp->add_ctr_clamp = add_ctr_clamp ? 1 : 0;
     (void)who;
+    return SPHK_OK;
+}
+
+int sphk_anchor_targets(const int64_t* gt_inds, int32_t batch, int64_t N, int D, const float* anchors, const float* gts,
+                        const int64_t* gt_labels, const int32_t* gt_offsets, int64_t num_classes, float pos_weight,
+                        int reg_decoded_bbox, const float* means, const float* stds, int64_t* labels, float* label_weights,
+                        float* bbox_targets, float* bbox_weights, int32_t* counts, void* stream) {
+    if (batch < 0 || N < 0 || (D != 4 && D != 5)) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_anchor_targets: bad batch, N or D");
+    if (batch > 65535) return fail(SPHK_ERR_UNSUPPORTED, "sphk_anchor_targets: more than 65535 images");
+    if (batch == 0) return SPHK_OK;
+    if (!counts) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_anchor_targets: null counts");
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)batch * 2 * sizeof(int32_t), s);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(counts)");
+    if (N == 0) return SPHK_OK;
+    if (!gt_inds || !anchors || !gt_offsets || !labels || !label_weights || !bbox_targets || !bbox_weights)
+        return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_anchor_targets: null pointer");
+    CoderParams cp;
+    const int rc = coder_params("sphk_anchor_targets", D, means, stds, 1.0f, 0, 0, 0.0f, &cp);
+    if (rc != SPHK_OK) return rc;
+    const dim3 grid(blocks_for(N), (unsigned)batch);
+    if (D == 4) k_anchor_targets<4><<<grid, kThreads, 0, s>>>(gt_inds, N, anchors, gts, gt_labels, gt_offsets, num_classes, pos_weight, reg_decoded_bbox != 0, cp, labels, label_weights, bbox_targets, bbox_weights, counts);
+    else k_anchor_targets<5><<<grid, kThreads, 0, s>>>(gt_inds, N, anchors, gts, gt_labels, gt_offsets, num_classes, pos_weight, reg_decoded_bbox != 0, cp, labels, label_weights, bbox_targets, bbox_weights, counts);
+    SPHK_LAUNCH_CHECK("k_anchor_targets");
     return SPHK_OK;
 }
 

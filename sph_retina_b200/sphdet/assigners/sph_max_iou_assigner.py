@@ -108,6 +108,14 @@ class SphMaxIoUAssigner:
     def _assign_fused(self, bboxes, gt_bboxes, gt_labels):
         return self.assign_batch(bboxes, [gt_bboxes], None if gt_labels is None else [gt_labels])[0]
 
+    def _assign_batch_raw(self, boxes, gts, offsets, labels=None):
+        """(gt_inds [B, N], max_overlaps [B, N], labels [B, N] | None) for the concatenated GT lists `gts` with image
+        offsets `offsets` (python list of B + 1 ints): the tensors of sphk_max_iou_assign before they are cut per image."""
+        lo, hi = self._neg_range()
+        with torch.no_grad():
+            return _native.max_iou_assign(_KINDS[self.iou_calculator.backend], gts, offsets, boxes, self.pos_iou_thr, lo, hi,
+                                          self.min_pos_iou, self.gt_max_assign_all, self.match_low_quality, labels)
+
     def assign_batch(self, bboxes, gt_bboxes_list, gt_labels_list=None):
         """All images of a step in one go when they share the anchor list (RetinaNet: SURVEY.md 3.1, the reference
         loops over the images in Python, mmdet/models/dense_heads/anchor_head.py:368-377).  One C-ABI call
@@ -127,11 +135,7 @@ class SphMaxIoUAssigner:
         if gt_labels_list is not None and offsets[-1] > 0:
             ll = [l for l, c in zip(gt_labels_list, counts) if c > 0]
             labels = torch.cat(ll) if len(ll) > 1 else ll[0]
-        lo, hi = self._neg_range()
-        with torch.no_grad():
-            gt_inds, max_overlaps, out_labels = _native.max_iou_assign(
-                _KINDS[calc.backend], gts, offsets, boxes, self.pos_iou_thr, lo, hi, self.min_pos_iou,
-                self.gt_max_assign_all, self.match_low_quality, labels)
+        gt_inds, max_overlaps, out_labels = self._assign_batch_raw(boxes, gts, offsets, labels)
         res = []
         for b, k in enumerate(counts):
             lab = None

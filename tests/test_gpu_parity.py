@@ -514,6 +514,44 @@ def test_loss_gradcheck_against_finite_differences(api):
     assert float(err.median()) < 5e-3 and float((err < 5e-2).float().mean()) > 0.97
 
 
+@pytest.mark.parametrize("decoded", [True, False])
+def test_anchor_targets_batch(api, decoded):
+    """get_targets_batch (sphk_max_iou_assign + sphk_anchor_targets) against the literal per-image reference chain run on
+    the kernel's own overlaps: assign_wrt_overlaps -> PseudoSampler -> anchor_head._get_targets_single.  Labels, weights and
+    counts are exact; decoded targets are the GT boxes bit for bit, encoded ones match bbox2delta to fp32 rounding."""
+    from sph_retina_b200 import synthetic as S
+    from sph_retina_b200.sphdet.assigners import SphMaxIoUAssigner
+    from sph_retina_b200.sphdet.bbox.coder import DeltaXYWHASphBBoxCoder
+    from sph_retina_b200.sphdet.models.heads import get_targets_batch
+    gts, anchors = S.assignment_batch(images=4)
+    anchors = anchors[::3].contiguous().to(DEV)
+    gt_list = [gts[0].to(DEV), gts[1][:5].to(DEV), gts[2][:0].to(DEV), gts[3].to(DEV)]          # one image without GT
+    gen = torch.Generator().manual_seed(0)
+    lab_list = [torch.randint(0, 80, (g.size(0),), generator=gen).to(DEV) for g in gt_list]
+    A = SphMaxIoUAssigner(0.5, 0.4, min_pos_iou=0, iou_calculator=dict(type='SphOverlaps2D', backend='sph2pob_efficient_iou', box_version=5))
+    coder = DeltaXYWHASphBBoxCoder(target_stds=(0.1, 0.1, 0.2, 0.2, 0.1))
+    labels, lw, bt, bw, npos, nneg = get_targets_batch(anchors, gt_list, lab_list, A, 80, bbox_coder=coder,
+                                                       reg_decoded_bbox=decoded, pos_weight=-1)
+    assert labels.shape == (4, anchors.size(0)) and bt.shape == (4, anchors.size(0), 5)
+    tot_pos = tot_neg = 0
+    for b, (g, l) in enumerate(zip(gt_list, lab_list)):
+        ov = api.iou.SphOverlaps2D('sph2pob_efficient_iou', 5)(g, anchors).cpu()
+        gi, _, _ = O.assign_wrt_overlaps(ov, None, 0.5, 0.4, 0.0, True, True)
+        want = O.get_targets_single(anchors.cpu(), g.cpu(), l.cpu(), gi, 80, reg_decoded_bbox=decoded, pos_weight=-1,
+                                    means=None, stds=[0.1, 0.1, 0.2, 0.2, 0.1])
+        assert torch.equal(labels[b].cpu(), want[0]) and torch.equal(lw[b].cpu(), want[1]) and torch.equal(bw[b].cpu(), want[3])
+        if decoded:
+            assert torch.equal(bt[b].cpu(), want[2])
+        else:
+            assert float((bt[b].cpu() - want[2]).abs().max()) < 2e-5
+        tot_pos += max(want[4], 1)
+        tot_neg += max(want[5], 1)
+    assert (npos, nneg) == (tot_pos, tot_neg) and npos > 100
+    # pos_weight > 0, RPN-style call without labels, and the no-sync variant
+    _, lw2, _, _, cnt, _ = get_targets_batch(anchors, gt_list, None, A, 1, reg_decoded_bbox=True, pos_weight=2.5, sync_counts=False)
+    assert torch.equal(lw2 == 2.5, bw[..., 0] == 1) and cnt.shape == (4, 2) and int(cnt[2, 0]) == 0 and int(cnt[2, 1]) == anchors.size(0)
+
+
 # ---- the other losses on the Sph2Pob OBBs (SURVEY.md 8f row 3) ---------------------------------------------------
 def _other_loss(api, cls, kw, **extra):
     return getattr(api.losses, cls)(**kw, **extra)

@@ -201,3 +201,17 @@ def test_c_oracle_aligned(c_oracle, box):
             err = np.abs(got - g["%s_%s_f64" % (tr, key)])
             assert np.median(err) < 1e-9
             assert (err > 1e-6).mean() < 5e-3, (box, tr, key, (err > 1e-6).sum())
+
+
+def test_restatement_get_targets_single_hand_case():
+    """anchor_head.py:254-285 on a case small enough to check by hand."""
+    anchors = torch.tensor([[10., 20, 30, 40], [50, 60, 10, 10], [90, 90, 20, 20], [0, 0, 5, 5]])
+    gts = torch.tensor([[12., 22, 28, 36], [88, 92, 22, 18]])
+    gt_inds = torch.tensor([1, 0, 2, -1])
+    labels, lw, bt, bw, npos, nneg = O.get_targets_single(anchors, gts, torch.tensor([7, 3]), gt_inds, 80)
+    assert labels.tolist() == [7, 80, 3, 80] and lw.tolist() == [1, 1, 1, 0] and (npos, nneg) == (2, 1)
+    assert torch.equal(bt[0], gts[0]) and torch.equal(bt[2], gts[1]) and not bt[1].any() and not bt[3].any()
+    assert bw.tolist() == [[1] * 4, [0] * 4, [1] * 4, [0] * 4]
+    enc = O.get_targets_single(anchors, gts, None, gt_inds, 1, reg_decoded_bbox=False, pos_weight=2.0, stds=[0.1, 0.1, 0.2, 0.2])
+    assert enc[0].tolist() == [0, 1, 0, 1] and enc[1].tolist() == [2, 1, 2, 0]
+    np.testing.assert_allclose(enc[2][0].numpy(), [(12 - 10) / 30 / 0.1, (22 - 20) / 40 / 0.1, np.log(28 / 30) / 0.2, np.log(36 / 40) / 0.2], rtol=1e-5)
