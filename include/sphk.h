@@ -39,7 +39,9 @@ enum sphk_kind {
     SPHK_KIND_SPH2POB_EFFICIENT = 0, /* 'sph2pob_efficient_iou'  sphdet/iou/sph_iou_api.py:97-98   */
     SPHK_KIND_SPH2POB_STANDARD = 1,  /* 'sph2pob_standard_iou'   sphdet/iou/sph_iou_api.py:94-95   */
     SPHK_KIND_SPH = 2,               /* 'sph_iou'                sphdet/iou/sph_iou_api.py:130-151 */
-    SPHK_KIND_FOV = 3                /* 'fov_iou'                sphdet/iou/sph_iou_api.py:156-177 */
+    SPHK_KIND_FOV = 3,               /* 'fov_iou'                sphdet/iou/sph_iou_api.py:156-177 */
+    SPHK_KIND_NAIVE = 4              /* 'naive_iou'              sphdet/iou/sph_iou_api.py:181-198 (planar IoU of the
+                                        sph2pix boxes; BFoV or RBFoV, mode 'iou' only)                            */
 };
 enum sphk_mode { SPHK_MODE_IOU = 0, SPHK_MODE_IOF = 1 };                     /* sph_iou_api.py:49     */
 enum sphk_edge { SPHK_EDGE_ARC = 0, SPHK_EDGE_CHORD = 1, SPHK_EDGE_TANGENT = 2 }; /* sph2pob_efficient.py:100-108 */
@@ -221,7 +223,8 @@ int sphk_decode_loss_reduce(const float* anchors, const float* deltas, const flo
                             float* grad_deltas, void* stream);
 
 /* Batched greedy spherical NMS (SphNMS / sph_batched_nms / sph_nms_op,
- * sphdet/bbox/nms/sph_nms.py:22-74) with Sph2Pob-efficient IoU.
+ * sphdet/bbox/nms/sph_nms.py:22-74).  kind: the IoU SphNMS was built with (sph_nms.py:8-16) -- SPHK_KIND_SPH2POB_EFFICIENT
+ * (its default) or SPHK_KIND_NAIVE (the reference's indoor360 configs: test_cfg.iou_calculator = 'naive_iou').
  *   boxes       [M, D]
  *   order       [M]    int32 indices into boxes, grouped by segment (one segment = one
  *                      (image, class) group), score-descending inside a segment (:65)
@@ -232,7 +235,8 @@ int sphk_decode_loss_reduce(const float* anchors, const float* deltas, const flo
  *   keep        [M]    uint8, keep[q] = 1 iff the box order[q] survives (same positions as `order`)
  * A box is suppressed iff IoU(pivot as bboxes1, box as bboxes2) > iou_threshold (:70-73). */
 int sphk_nms_batched(const float* boxes, const int32_t* order, const int32_t* seg_offsets, int32_t S,
-                     int32_t max_seg_len, int32_t typical_seg_len, int D, float iou_threshold, uint8_t* keep, void* stream);
+                     int32_t max_seg_len, int32_t typical_seg_len, int D, int kind, float iou_threshold, uint8_t* keep,
+                     void* stream);
 
 /* The same NMS for a test-time batch laid out as `num_images` equal blocks of `per_image` candidates (what the head's
  * post-processing produces: nms_pre candidates per level and image, sph_retina_head.py:169-212 then :35-101), with no
@@ -248,8 +252,8 @@ int sphk_nms_batched(const float* boxes, const int32_t* order, const int32_t* se
  *   workspace sphk_nms_images_workspace_bytes(num_images, per_image, num_classes) bytes, 16-byte aligned */
 int64_t sphk_nms_images_workspace_bytes(int32_t num_images, int32_t per_image, int32_t num_classes);
 int sphk_nms_images(const float* boxes, const float* scores, const int64_t* labels, const uint8_t* valid, int32_t num_images,
-                    int32_t per_image, int32_t num_classes, int D, float iou_threshold, int32_t max_out, int32_t* out_idx,
-                    int32_t* out_count, void* workspace, void* stream);
+                    int32_t per_image, int32_t num_classes, int D, int kind, float iou_threshold, int32_t max_out,
+                    int32_t* out_idx, int32_t* out_count, void* workspace, void* stream);
 
 /* Measurement helpers (bench.py; no counterpart in the reference).
  * sphk_probe_fp32: FMA-chain microbenchmark that yields the FP32 CUDA-core peak the Sph2Pob kernels

@@ -279,6 +279,37 @@ def golden_other_losses(R):
         print("other losses", box, {k: float(out[k + "_loss_f64"].mean()) for k in OTHER_LOSS_VARIANTS})
 
 
+def golden_naive(R):
+    """naive_iou (sph_iou_api.py:181-198) through the reference's own function and box formator (mmcv's two planar ops
+    underneath are stand-ins: oracle/ref_harness.py), aligned + N x M, and SphNMS('naive_iou') keep sets."""
+    out = {}
+    for box in ("bfov", "rbfov"):
+        torch.manual_seed(61)
+        n = 2048
+        b1 = R.generate_boxes(n, alpha_range=(1, 120), beta_range=(1, 120), dtype="float", box=box)
+        b2 = (b1 + torch.randn_like(b1) * torch.tensor([8, 8, 8, 8, 15.0])[:b1.size(1)]).clamp(min=0.5)
+        b2[:64] = R.generate_boxes(64, alpha_range=(1, 120), beta_range=(1, 120), dtype="float", box=box)   # unrelated pairs
+        b2[64:96] = b1[64:96]                                                                                # identical pairs
+        out[box + "_b1"], out[box + "_b2"] = _np(b1), _np(b2)
+        out[box + "_aligned_f32"] = _np(R.naive_iou(b1, b2, is_aligned=True))
+        out[box + "_aligned_f64"] = _np(_ref64(R.naive_iou, b1, b2, is_aligned=True))
+        rows, cols = b1[:37], b2[:301]
+        out[box + "_rc_f32"] = _np(R.naive_iou(rows, cols))
+        out[box + "_rc_f64"] = _np(_ref64(R.naive_iou, rows, cols))
+        torch.manual_seed(62)
+        seeds = R.generate_boxes(80, alpha_range=(5, 60), beta_range=(5, 60), dtype="float", box=box)
+        boxes = (seeds.repeat(5, 1) + torch.randn(400, seeds.size(1)) * 2).clamp(min=1)
+        boxes[350:400] = boxes[300:350]
+        scores, idxs = torch.rand(400), torch.randint(0, 6, (400,))
+        for thr in (0.3, 0.5):
+            dets, keep = R.SphNMS("naive_iou")(boxes, scores, idxs, dict(type="nms", iou_threshold=thr, max_num=150))
+            out["%s_keep_thr%d" % (box, int(thr * 10))] = _np(keep)
+        out["%s_pair_iou_f64" % box] = _np(_ref64(R.naive_iou, boxes, boxes)).astype(np.float32)
+        out["%s_boxes" % box], out["%s_scores" % box], out["%s_idxs" % box] = _np(boxes), _np(scores), _np(idxs)
+    np.savez_compressed(os.path.join(OUT, "naive.npz"), **out)
+    print("naive", {k: (v.shape, float(np.nanmean(v))) for k, v in out.items() if "aligned_f64" in k or "keep" in k})
+
+
 def golden_nms(R):
     out = {}
     for box in ("bfov", "rbfov"):
@@ -365,3 +396,4 @@ if __name__ == "__main__":
     golden_nms(R)
     golden_coder(R)
     golden_other_losses(R)
+    golden_naive(R)

@@ -77,9 +77,12 @@ def load_reference():
     diff_mod = _load_file("_ref_diff_iou_rotated", "sphdet/iou/diff_iou_rotated.py")
 
     def box_iou_rotated(b1, b2, mode="iou", aligned=False, clockwise=True):
-        # stand-in for mmcv.ops.box_iou_rotated (call site sph_iou_api.py:79 always
-        # passes aligned=True, clockwise=True)
-        assert aligned and clockwise
+        # stand-in for mmcv.ops.box_iou_rotated (call site sph_iou_api.py:79 passes aligned=True, clockwise=True;
+        # naive_iou, :194, passes (b1, b2, mode, is_aligned))
+        assert clockwise
+        if not aligned:
+            R, C = b1.size(0), b2.size(0)
+            return box_iou_rotated(b1.repeat_interleave(C, 0), b2.repeat(R, 1), mode, True).view(R, C)
         corners1 = diff_mod.box2corners(b1.unsqueeze(0))
         corners2 = diff_mod.box2corners(b2.unsqueeze(0))
         inter, _ = diff_mod.oriented_box_intersection_2d(corners1, corners2)
@@ -98,7 +101,10 @@ def load_reference():
     mmcv_ops = types.ModuleType("mmcv.ops")
     mmcv_ops.box_iou_rotated = box_iou_rotated
     mmcv_ops.diff_iou_rotated_2d = diff_mod.diff_iou_rotated_2d
-    mmcv_ops.bbox_overlaps = _unavailable
+    # mmcv.ops.bbox_overlaps (planar, used by naive_iou for BFoV): the restatement of the published mmcv 1.6.0 kernel
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import sph_oracle as _so
+    mmcv_ops.bbox_overlaps = _so.mmcv_bbox_overlaps
     mmcv_ops.batched_nms = _unavailable
     mmcv.ops = mmcv_ops
     mmcv.jit = lambda *a, **k: (lambda f: f)
@@ -232,7 +238,7 @@ def load_reference():
         generate_boxes=gen.generate_boxes,
         sph2pob_efficient_iou=api.sph2pob_efficient_iou,
         sph2pob_standard_iou=api.sph2pob_standard_iou,
-        sph_iou=api.sph_iou, fov_iou=api.fov_iou,
+        sph_iou=api.sph_iou, fov_iou=api.fov_iou, naive_iou=api.naive_iou,
         SphOverlaps2D=calc.SphOverlaps2D, SphNMS=sph_nms.SphNMS,
         Sph2PobIoULoss=iou_loss.Sph2PobIoULoss,
         Sph2PobGDLoss=gd_loss.Sph2PobGDLoss, Sph2PobKFLoss=kf_loss.Sph2PobKFLoss, Sph2PobL1Loss=l1_loss.Sph2PobL1Loss,

@@ -436,6 +436,49 @@ def sph2pob_iou_loss(pred, target, weight=None, avg_factor=None, mode="iou", eps
     return loss_weight * loss
 
 
+# --------------------------------------------------------------------------- #
+# naive_iou (sph_iou_api.py:181-198)
+# --------------------------------------------------------------------------- #
+def mmcv_bbox_overlaps(b1, b2, mode="iou", aligned=False, offset=0):
+    """mmcv-full 1.6.0 ``bbox_overlaps`` (mmcv/ops/csrc/common/cuda/bbox_overlaps_cuda_kernel.cuh; the package is not
+    in the reference tree -- parity UNPINNED at that boundary, published kernel restated): xyxy boxes,
+    inter / max(area1 + area2 - inter, offset) ('iou') or inter / max(area1, offset) ('iof')."""
+    if not aligned:
+        R, C = b1.size(0), b2.size(0)
+        return mmcv_bbox_overlaps(b1.repeat_interleave(C, 0), b2.repeat(R, 1), mode, True, offset).view(R, C)
+    a1 = (b1[:, 2] - b1[:, 0] + offset) * (b1[:, 3] - b1[:, 1] + offset)
+    a2 = (b2[:, 2] - b2[:, 0] + offset) * (b2[:, 3] - b2[:, 1] + offset)
+    w = (torch.min(b1[:, 2], b2[:, 2]) - torch.max(b1[:, 0], b2[:, 0]) + offset).clamp(min=0)
+    h = (torch.min(b1[:, 3], b2[:, 3]) - torch.max(b1[:, 1], b2[:, 1]) + offset).clamp(min=0)
+    inter = w * h
+    base = (a1 + a2 - inter) if mode == "iou" else a1
+    return inter / base.clamp(min=offset)
+
+
+def sph2pix(boxes, img_size=(512, 1024)):
+    """Sph2PlanarBoxTransform('sph2pix') (box_formator.py:79-87,176-193): xyxy for BFoV, (x, y, w, h, -gamma rad) for RBFoV."""
+    img_h, img_w = img_size
+    x, y = (boxes[:, 0] / 360) * img_w, (boxes[:, 1] / 180) * img_h
+    w, h = (boxes[:, 2] / 360) * img_w, (boxes[:, 3] / 180) * img_h
+    if boxes.size(1) == 4:
+        return torch.stack([x - w / 2, y - h / 2, x + w / 2, y + h / 2], dim=1)
+    return torch.stack([x, y, w, h, -torch.deg2rad(boxes[:, 4])], dim=1)
+
+
+def naive_iou(b1, b2, mode="iou", is_aligned=False):
+    """sph_iou_api.py:181-198: planar IoU of the sph2pix boxes (mmcv bbox_overlaps / box_iou_rotated), no jitter, no clamp."""
+    assert mode == "iou"
+    rows, cols = b1.size(0), b2.size(0)
+    if rows * cols == 0:
+        return b1.new_zeros((rows, 1)) if is_aligned else b1.new_zeros((rows, cols))
+    p1, p2 = sph2pix(b1), sph2pix(b2)
+    if b1.size(1) == 4:
+        return mmcv_bbox_overlaps(p1, p2, mode, is_aligned)
+    if not is_aligned:
+        return rotated_iou(p1.repeat_interleave(cols, 0), p2.repeat(rows, 1), mode).view(rows, cols)
+    return rotated_iou(p1, p2, mode)
+
+
 # ---- the other Sph2Pob losses (SURVEY.md 8f row 3) --------------------------------------------------------------------
 def _decorated(pred, target, weight):
     """Sph2PobTransfrom.new_forward (sph2pob_transform.py:24-35): OBBs of the pair + the widened BFoV weight."""

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "libsphk.so")
 _PROBE_LIB = os.environ.get("SPHK_PROBE_LIB")      # tools/ only: an instrumented build of the same sources
 
-KIND = {"sph2pob_efficient": 0, "sph2pob_standard": 1, "sph": 2, "fov": 3}
+KIND = {"sph2pob_efficient": 0, "sph2pob_standard": 1, "sph": 2, "fov": 3, "naive": 4}
 MODE = {"iou": 0, "iof": 1}
 EDGE = {"arc": 0, "chord": 1, "tangent": 2}
 ANGLE = {"equator": 0, "project": 1}
@@ -71,10 +71,10 @@ SIGNATURES = {
     "sphk_decode_loss_reduce": (_int, [_c_float_p, _c_float_p, _c_float_p, _c_float_p, _int, _i64, _int,
                                        ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), ctypes.c_float, _int, _int,
                                        ctypes.c_float, ctypes.c_float, _c_float_p, _c_float_p, ctypes.c_void_p]),
-    "sphk_nms_batched": (_int, [_c_float_p, ctypes.c_void_p, ctypes.c_void_p, _i32, _i32, _i32, _int, ctypes.c_float,
+    "sphk_nms_batched": (_int, [_c_float_p, ctypes.c_void_p, ctypes.c_void_p, _i32, _i32, _i32, _int, _int, ctypes.c_float,
                                 ctypes.c_void_p, ctypes.c_void_p]),
     "sphk_nms_images_workspace_bytes": (_i64, [_i32, _i32, _i32]),
-    "sphk_nms_images": (_int, [_c_float_p, _c_float_p, ctypes.c_void_p, ctypes.c_void_p, _i32, _i32, _i32, _int, ctypes.c_float,
+    "sphk_nms_images": (_int, [_c_float_p, _c_float_p, ctypes.c_void_p, ctypes.c_void_p, _i32, _i32, _i32, _int, _int, ctypes.c_float,
                                _i32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "sphk_probe_fp32": (_int, [_i32, _i32, _c_float_p, ctypes.c_void_p]),
     "sphk_set_dense": (_int, [_int]),
@@ -531,7 +531,11 @@ def riou_fwd_bwd(o1, o2, grad_iou=None, want1=False, want2=False):
     return iou, g1, g2
 
 
-def nms_batched(boxes, order, seg_offsets, max_seg_len: int, iou_threshold: float, typical_seg_len: int = 0) -> torch.Tensor:
+NMS_KIND = {"sph2pob_efficient": 0, "naive_iou": 4}      # SphNMS's iou_calculator names (sph_nms.py:8-16)
+
+
+def nms_batched(boxes, order, seg_offsets, max_seg_len: int, iou_threshold: float, typical_seg_len: int = 0,
+                iou_calculator: str = "sph2pob_efficient") -> torch.Tensor:
     """keep flags (uint8, aligned with `order`) of the greedy per-segment spherical NMS."""
     global launches
     boxes = _boxes(boxes, "boxes")
@@ -544,12 +548,13 @@ def nms_batched(boxes, order, seg_offsets, max_seg_len: int, iou_threshold: floa
         return keep
     with _on_device(dev):
         _check(lib.sphk_nms_batched(_ptr(boxes), _ptr(order), _ptr(seg_offsets), S, int(max_seg_len), int(typical_seg_len), boxes.size(1),
-                                    float(iou_threshold), _ptr(keep), _stream(boxes)))
+                                    NMS_KIND[iou_calculator], float(iou_threshold), _ptr(keep), _stream(boxes)))
     launches += 1
     return keep
 
 
-def nms_images(boxes, scores, labels, num_images: int, num_classes: int, iou_threshold: float, max_out: int, valid=None):
+def nms_images(boxes, scores, labels, num_images: int, num_classes: int, iou_threshold: float, max_out: int, valid=None,
+               iou_calculator: str = "sph2pob_efficient"):
     """Greedy per-(image, class) NMS of a batch laid out as `num_images` equal blocks of candidates, entirely on the
     device (three launches, no sort on the host side, no synchronisation).  Returns (idx [num_images, max_out] int32
     into boxes, score-descending per image, -1 padded; count [num_images] int32)."""
@@ -572,8 +577,8 @@ def nms_images(boxes, scores, labels, num_images: int, num_classes: int, iou_thr
     ws = _workspace(dev, lib.sphk_nms_images_workspace_bytes(num_images, per_image, num_classes))
     with _on_device(dev):
         _check(lib.sphk_nms_images(_ptr(boxes), _ptr(scores), _ptr(labels), _ptr(valid), num_images, per_image, num_classes,
-                                   boxes.size(1), float(iou_threshold), int(max_out), _ptr(out_idx), _ptr(out_count), _ptr(ws),
-                                   _stream(boxes)))
+                                   boxes.size(1), NMS_KIND[iou_calculator], float(iou_threshold), int(max_out), _ptr(out_idx),
+                                   _ptr(out_count), _ptr(ws), _stream(boxes)))
     launches += 3
     return out_idx, out_count
 

@@ -128,6 +128,7 @@ __global__ void __launch_bounds__(kThreads) k_iou_aligned(const float* __restric
     const RawBox x = load_box<D>(b1, i, vec_ok), y = load_box<D>(b2, i, vec_ok);
     float v;
     if (KIND == KIND_SPH || KIND == KIND_FOV) v = approx_iou_pair(x, y, KIND);
+    else if (KIND == KIND_NAIVE) v = naive_iou_pair(x, y, D, mode);
     else v = sph2pob_iou_pair(x, y, D, KIND, mode, edge, dense);
     out[i] = v;
 }
@@ -362,6 +363,7 @@ k_iou_pairwise(const float* __restrict__ rows, int64_t R, const float* __restric
         float v = 0.0f;
         if (col_ok) {
             if (KIND == KIND_SPH || KIND == KIND_FOV) v = approx_iou_pair(x, y, KIND);
+            else if (KIND == KIND_NAIVE) v = naive_iou_pair(x, y, D, mode);
             else v = sph2pob_iou_pair(x, y, D, KIND, mode, edge, dense);
             if (out) out[(r0 + r) * ld + col] = v;
             if (v > best_v) { best_v = v; best_r = (uint32_t)r; }
@@ -1267,13 +1269,22 @@ __device__ __forceinline__ void bitonic_sort_u64(unsigned long long* s, int n) {
     }
 }
 
+// The pivot test of sph_nms_op (sph_nms.py:70-73): the candidate survives iff IoU(pivot, candidate) <= thr (so a NaN IoU,
+// which only the unclamped planar `naive_iou` can produce, suppresses).  kind: Sph2Pob-efficient (SphNMS's default) or naive.
+__device__ __noinline__ float naive_pair_outofline(const RawBox& x, const RawBox& y, int D) { return naive_iou_pair(x, y, D, MODE_IOU); }
+__device__ __forceinline__ bool nms_suppresses(const float* __restrict__ boxes, int bi, int bj, const RawBox& x, const RawBox& y,
+                                               int D, int kind, float thr) {
+    if (kind == KIND_NAIVE) return !(naive_pair_outofline(x, y, D) <= thr);
+    return pair_iou_any(boxes, bi, boxes, bj, x, y, D, KIND_SPH2POB_EFFICIENT, MODE_IOU, EDGE_ARC) > thr;
+}
+
 // `scores` != NULL: the segment arrives unordered (k_img_scatter) and is first put into (score descending, index
 // ascending) order by its own CTA, in shared memory (`sort_cap` keys; the box indices then stay there).
 template <int D>
 __global__ void __launch_bounds__(1024)
 k_nms(const float* __restrict__ boxes, int32_t* order, const int32_t* __restrict__ seg_offsets,
       const int32_t* __restrict__ seg_len, const float* __restrict__ scores, int sort_cap, int32_t* __restrict__ bad_image,
-      int segs_per_image, float thr, uint8_t* __restrict__ keep, int max_words, bool vec_ok) {
+      int segs_per_image, float thr, uint8_t* __restrict__ keep, int max_words, bool vec_ok, int kind) {
     extern __shared__ uint32_t s_mem[];
     const int seg = blockIdx.x;
     const int start = seg_offsets[seg];
@@ -1363,7 +1374,7 @@ k_nms(const float* __restrict__ boxes, int32_t* order, const int32_t* __restrict
                         const int bi = idx_in_smem ? (int)(uint32_t)s_keys[i0 + pi] : order[start + i0 + pi];
                         const int bj = idx_in_smem ? (int)(uint32_t)s_keys[i0 + pj] : order[start + i0 + pj];
                         const RawBox x = load_box<D>(boxes, bi, vec_ok), y = load_box<D>(boxes, bj, vec_ok);
-                        sup = pair_iou_any(boxes, bi, boxes, bj, x, y, D, KIND_SPH2POB_EFFICIENT, MODE_IOU, EDGE_ARC) > thr;
+                        sup = nms_suppresses(boxes, bi, bj, x, y, D, kind, thr);
                     }
                 }
                 if (sup) atomicOr(&mask[pi * W + w0], 1u << pj);
@@ -1376,7 +1387,7 @@ k_nms(const float* __restrict__ boxes, int32_t* order, const int32_t* __restrict
                     const int bi = idx_in_smem ? (int)(uint32_t)s_keys[i] : order[start + i];
                     const int bj = idx_in_smem ? (int)(uint32_t)s_keys[j] : order[start + j];
                     const RawBox x = load_box<D>(boxes, bi, vec_ok), y = load_box<D>(boxes, bj, vec_ok);
-                    sup = pair_iou_any(boxes, bi, boxes, bj, x, y, D, KIND_SPH2POB_EFFICIENT, MODE_IOU, EDGE_ARC) > thr;
+                    sup = nms_suppresses(boxes, bi, bj, x, y, D, kind, thr);
                 }
                 const uint32_t word = __ballot_sync(0xFFFFFFFFu, sup);
                 if (lane == 0) mask[pi * W + jw] = word;
@@ -1584,7 +1595,8 @@ int sphk_device_info(int* sm_count, int* cc_major, int* cc_minor) {
 int sphk_iou_aligned(int kind, const float* b1, const float* b2, int64_t P, int D, int mode, int edge, int angle,
                      float* out, void* stream) {
     if (P < 0 || (D != 4 && D != 5)) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_aligned: P < 0 or D not in {4,5}");
-    if (kind < 0 || kind > 3) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_aligned: unknown kind");
+    if (kind < 0 || kind > SPHK_KIND_NAIVE) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_aligned: unknown kind");
+    if (kind == SPHK_KIND_NAIVE && mode != SPHK_MODE_IOU) return fail(SPHK_ERR_UNSUPPORTED, "naive_iou supports mode 'iou' only (sph_iou_api.py:182)");
     if (mode != SPHK_MODE_IOU && mode != SPHK_MODE_IOF) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_aligned: unknown mode");
     if (edge < 0 || edge > 2) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_aligned: unknown edge");
     if (angle != SPHK_ANGLE_EQUATOR && angle != SPHK_ANGLE_PROJECT) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_aligned: unknown angle");
@@ -1597,6 +1609,9 @@ int sphk_iou_aligned(int kind, const float* b1, const float* b2, int64_t P, int 
     if (angle == SPHK_ANGLE_PROJECT && kind <= SPHK_KIND_SPH2POB_STANDARD) {
         if (D == 4) k_iou_project<4><<<blocks_for(P), kThreads, 0, s>>>(b1, P, b2, P, true, kind, mode, edge, out, 0);
         else k_iou_project<5><<<blocks_for(P), kThreads, 0, s>>>(b1, P, b2, P, true, kind, mode, edge, out, 0);
+    } else if (kind == SPHK_KIND_NAIVE) {
+        if (D == 4) k_iou_aligned<KIND_NAIVE, 4><<<blocks_for(P), kThreads, 0, s>>>(b1, b2, P, mode, edge, out, v, false);
+        else k_iou_aligned<KIND_NAIVE, 5><<<blocks_for(P), kThreads, 0, s>>>(b1, b2, P, mode, edge, out, false, false);
     } else if (kind == SPHK_KIND_SPH || kind == SPHK_KIND_FOV) {
         const unsigned g = blocks_for(P);
         if (v && !g_no_approx4 && P >= (int64_t)3 << 20) {      // below ~3 M pairs one pair per thread keeps more loads in flight
@@ -1696,12 +1711,14 @@ static int pairwise_impl(int kind, const float* rows, int64_t R, const float* co
                          const float* row_target, int* col_tie, unsigned long long* ext_rkey = nullptr,
                          unsigned long long* ext_ckey = nullptr) {
     if (R < 0 || C < 0 || (D != 4 && D != 5)) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: bad R, C or D");
-    if (kind < 0 || kind > 3) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: unknown kind");
+    if (kind < 0 || kind > SPHK_KIND_NAIVE) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: unknown kind");
+    if (kind == SPHK_KIND_NAIVE && mode != SPHK_MODE_IOU) return fail(SPHK_ERR_UNSUPPORTED, "naive_iou supports mode 'iou' only (sph_iou_api.py:182)");
     if (mode != SPHK_MODE_IOU && mode != SPHK_MODE_IOF) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: unknown mode");
     if (edge < 0 || edge > 2) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: unknown edge");
     if (angle != SPHK_ANGLE_EQUATOR && angle != SPHK_ANGLE_PROJECT) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: unknown angle");
-    const bool approx = (kind == SPHK_KIND_SPH || kind == SPHK_KIND_FOV);
-    if (approx && (D != 4 || mode != SPHK_MODE_IOU))
+    // "approx": the kinds evaluated one pair per thread by the generic tile kernel (no per-box records, no prefilter)
+    const bool approx = (kind == SPHK_KIND_SPH || kind == SPHK_KIND_FOV || kind == SPHK_KIND_NAIVE);
+    if (approx && kind != SPHK_KIND_NAIVE && (D != 4 || mode != SPHK_MODE_IOU))
         return fail(SPHK_ERR_UNSUPPORTED, "sph_iou / fov_iou take BFoV boxes (D = 4) and mode 'iou' only");
     if (out && ld < C) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: ld < C");
     if (R + (int64_t)(uint32_t)row_base > 0xFFFFFFFFll || C + (int64_t)(uint32_t)col_base > 0xFFFFFFFFll)
@@ -1734,7 +1751,13 @@ static int pairwise_impl(int kind, const float* rows, int64_t R, const float* co
             const int64_t row_tiles = (R + kTileRows - 1) / kTileRows;
             if (col_tiles * row_tiles > 0x7FFFFFFFll) return fail(SPHK_ERR_UNSUPPORTED, "sphk_iou_pairwise: grid too large; shard the call");
             const unsigned g = (unsigned)(col_tiles * row_tiles);
-            if (kind == SPHK_KIND_SPH)
+            if (kind == SPHK_KIND_NAIVE && D == 4)
+                k_iou_pairwise<KIND_NAIVE, 4><<<g, kThreads, 0, s>>>(rows, R, cols, C, mode, edge, out, ld, rkey, ckey, (uint32_t)row_base,
+                                                                      (uint32_t)col_base, col_tiles, v, false);
+            else if (kind == SPHK_KIND_NAIVE)
+                k_iou_pairwise<KIND_NAIVE, 5><<<g, kThreads, 0, s>>>(rows, R, cols, C, mode, edge, out, ld, rkey, ckey, (uint32_t)row_base,
+                                                                      (uint32_t)col_base, col_tiles, false, false);
+            else if (kind == SPHK_KIND_SPH)
                 k_iou_pairwise<KIND_SPH, 4><<<g, kThreads, 0, s>>>(rows, R, cols, C, mode, edge, out, ld, rkey, ckey, (uint32_t)row_base,
                                                                     (uint32_t)col_base, col_tiles, v, g_dense != 0);
             else
@@ -2087,8 +2110,10 @@ int sphk_decode_loss_reduce(const float* anchors, const float* deltas, const flo
 }
 
 int sphk_nms_batched(const float* boxes, const int32_t* order, const int32_t* seg_offsets, int32_t S, int32_t max_seg_len,
-                     int32_t typical_seg_len, int D, float iou_threshold, uint8_t* keep, void* stream) {
+                     int32_t typical_seg_len, int D, int kind, float iou_threshold, uint8_t* keep, void* stream) {
     if (S < 0 || max_seg_len < 0 || (D != 4 && D != 5)) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_nms_batched: bad S, max_seg_len or D");
+    if (kind != SPHK_KIND_SPH2POB_EFFICIENT && kind != SPHK_KIND_NAIVE)
+        return fail(SPHK_ERR_UNSUPPORTED, "sphk_nms_batched: kind must be sph2pob_efficient or naive (SphNMS, sph_nms.py:8-16)");
     if (S == 0 || max_seg_len == 0) return SPHK_OK;
     if (!boxes || !order || !seg_offsets || !keep) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_nms_batched: null pointer");
     const int max_words = (max_seg_len + 31) / 32;
@@ -2104,11 +2129,11 @@ int sphk_nms_batched(const float* boxes, const int32_t* order, const int32_t* se
     if (D == 4) {
         e = cudaFuncSetAttribute(k_nms<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_nms)");
-        k_nms<4><<<S, nt, smem, s>>>(boxes, const_cast<int32_t*>(order), seg_offsets, nullptr, nullptr, 0, nullptr, 1, iou_threshold, keep, max_words, v);
+        k_nms<4><<<S, nt, smem, s>>>(boxes, const_cast<int32_t*>(order), seg_offsets, nullptr, nullptr, 0, nullptr, 1, iou_threshold, keep, max_words, v, kind);
     } else {
         e = cudaFuncSetAttribute(k_nms<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_nms)");
-        k_nms<5><<<S, nt, smem, s>>>(boxes, const_cast<int32_t*>(order), seg_offsets, nullptr, nullptr, 0, nullptr, 1, iou_threshold, keep, max_words, v);
+        k_nms<5><<<S, nt, smem, s>>>(boxes, const_cast<int32_t*>(order), seg_offsets, nullptr, nullptr, 0, nullptr, 1, iou_threshold, keep, max_words, v, kind);
     }
     SPHK_LAUNCH_CHECK("k_nms");
     return SPHK_OK;
@@ -2122,10 +2147,12 @@ int64_t sphk_nms_images_workspace_bytes(int32_t num_images, int32_t per_image, i
 }
 
 int sphk_nms_images(const float* boxes, const float* scores, const int64_t* labels, const uint8_t* valid, int32_t num_images,
-                    int32_t per_image, int32_t num_classes, int D, float iou_threshold, int32_t max_out, int32_t* out_idx,
+                    int32_t per_image, int32_t num_classes, int D, int kind, float iou_threshold, int32_t max_out, int32_t* out_idx,
                     int32_t* out_count, void* workspace, void* stream) {
     if (num_images < 0 || per_image < 0 || num_classes <= 0 || max_out < 0 || (D != 4 && D != 5))
         return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_nms_images: bad sizes or D");
+    if (kind != SPHK_KIND_SPH2POB_EFFICIENT && kind != SPHK_KIND_NAIVE)
+        return fail(SPHK_ERR_UNSUPPORTED, "sphk_nms_images: kind must be sph2pob_efficient or naive (SphNMS, sph_nms.py:8-16)");
     if (num_images == 0) return SPHK_OK;
     if (!out_idx || !out_count) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_nms_images: null output pointer");
     cudaStream_t s = (cudaStream_t)stream;
@@ -2170,11 +2197,11 @@ int sphk_nms_images(const float* boxes, const float* scores, const int64_t* labe
     if (D == 4) {
         e = cudaFuncSetAttribute(k_nms<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_nms)");
-        k_nms<4><<<(unsigned)S, nt, smem, s>>>(boxes, order, seg_start, seg_len, scores, sort_cap, bad, num_classes, iou_threshold, keep, max_words, v);
+        k_nms<4><<<(unsigned)S, nt, smem, s>>>(boxes, order, seg_start, seg_len, scores, sort_cap, bad, num_classes, iou_threshold, keep, max_words, v, kind);
     } else {
         e = cudaFuncSetAttribute(k_nms<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_nms)");
-        k_nms<5><<<(unsigned)S, nt, smem, s>>>(boxes, order, seg_start, seg_len, scores, sort_cap, bad, num_classes, iou_threshold, keep, max_words, v);
+        k_nms<5><<<(unsigned)S, nt, smem, s>>>(boxes, order, seg_start, seg_len, scores, sort_cap, bad, num_classes, iou_threshold, keep, max_words, v, kind);
     }
     SPHK_LAUNCH_CHECK("k_nms");
     k_img_collect<<<num_images, nt_img, smem_col, s>>>(scores, order, keep, per_image, Kp, max_out, bad, out_idx, out_count);

@@ -33,7 +33,7 @@
 namespace sphk {
 
 // ---- enums shared with the C ABI (include/sphk.h) -------------------------------------
-enum Kind { KIND_SPH2POB_EFFICIENT = 0, KIND_SPH2POB_STANDARD = 1, KIND_SPH = 2, KIND_FOV = 3 };
+enum Kind { KIND_SPH2POB_EFFICIENT = 0, KIND_SPH2POB_STANDARD = 1, KIND_SPH = 2, KIND_FOV = 3, KIND_NAIVE = 4 };
 enum Mode { MODE_IOU = 0, MODE_IOF = 1 };
 enum Edge { EDGE_ARC = 0, EDGE_CHORD = 1, EDGE_TANGENT = 2 };
 
@@ -617,6 +617,34 @@ SPHK_HD float approx_iou_pair(const RawBox& b1, const RawBox& b2, int kind) {
     const float inter = fmaxf(hi - lo, 0.0f) * fmaxf(phi - plo, 0.0f);
     const float iou = inter / (ag * bg + ap * bp - inter + 1e-8f);
     return clampf(iou, 0.0f, 1.0f);
+}
+
+// ---- naive_iou (sph_iou_api.py:181-198) -------------------------------------------------------------------------
+// The spherical box read as a planar box of the 512 x 1024 equirectangular image (Sph2PlanarBoxTransform 'sph2pix',
+// box_formator.py:79-87,176-193: x = theta / 360 * W, y = phi / 180 * H, w = alpha / 360 * W, h = beta / 180 * H) and mmcv's
+// planar IoU on it: bbox_overlaps on (x1, y1, x2, y2) for BFoV, box_iou_rotated on (x, y, w, h, -gamma rad) for RBFoV.
+// No jitter and no clamp (what the reference's indoor360 configs use for the test-time NMS).  mmcv-full 1.6.0 is not in
+// the reference tree; its published kernels are restated: bbox_overlaps_cuda_kernel.cuh (offset 0: inter / max(union, 0))
+// and box_iou_rotated_utils.hpp (0 if an area is below 1e-14, else inter / (a1 + a2 - inter)).
+SPHK_HD float naive_iou_pair(const RawBox& b1, const RawBox& b2, int D, int mode) {
+    const float W = 1024.0f, H = 512.0f;
+    const float x1 = (b1.t / 360.0f) * W, y1 = (b1.p / 180.0f) * H, w1 = (b1.a / 360.0f) * W, h1 = (b1.b / 180.0f) * H;
+    const float x2 = (b2.t / 360.0f) * W, y2 = (b2.p / 180.0f) * H, w2 = (b2.a / 360.0f) * W, h2 = (b2.b / 180.0f) * H;
+    if (D == 4) {
+        const float l1 = x1 - w1 / 2, t1 = y1 - h1 / 2, r1 = x1 + w1 / 2, q1 = y1 + h1 / 2;
+        const float l2 = x2 - w2 / 2, t2 = y2 - h2 / 2, r2 = x2 + w2 / 2, q2 = y2 + h2 / 2;
+        const float a1 = (r1 - l1) * (q1 - t1), a2 = (r2 - l2) * (q2 - t2);
+        const float iw = fmaxf(fminf(r1, r2) - fmaxf(l1, l2), 0.0f), ih = fmaxf(fminf(q1, q2) - fmaxf(t1, t2), 0.0f);
+        const float inter = iw * ih;
+        const float base = (mode == MODE_IOF) ? fmaxf(a1, 0.0f) : fmaxf(a1 + a2 - inter, 0.0f);
+        return inter / base;
+    }
+    ObbPair o;
+    o.x1 = x1; o.y1 = y1; o.w1 = w1; o.h1 = h1; o.a1 = -b1.g * kDeg2Rad;
+    o.x2 = x2; o.y2 = y2; o.w2 = w2; o.h2 = h2; o.a2 = -b2.g * kDeg2Rad;
+    if (w1 * h1 < 1e-14f || w2 * h2 < 1e-14f) return 0.0f;
+    if (obb_disjoint(o)) return 0.0f;
+    return riou_value(o, mode);
 }
 
 }  // namespace sphk

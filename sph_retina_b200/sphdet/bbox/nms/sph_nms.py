@@ -33,10 +33,10 @@ def _segments(scores, seg_ids, desc=None):
     return order, offsets, int(counts.max().item())
 
 
-def _keep_indices(boxes, scores, seg_ids, iou_threshold, desc=None):
+def _keep_indices(boxes, scores, seg_ids, iou_threshold, desc=None, iou_calculator='sph2pob_efficient'):
     """Indices (into boxes) that survive the per-segment greedy NMS, unordered."""
     order, offsets, longest = _segments(scores, seg_ids, desc)
-    flags = _native.nms_batched(boxes, order, offsets, longest, iou_threshold)
+    flags = _native.nms_batched(boxes, order, offsets, longest, iou_threshold, iou_calculator=iou_calculator)
     return order[flags.bool()]
 
 
@@ -57,12 +57,13 @@ def sph_batched_nms(boxes, scores, idxs, nms_cfg, iou_calculator='sph2pob_effici
     if boxes.size(0) <= 16384 and boxes.is_cuda:
         # one image = one block of the device-side pipeline (sort, suppression, ordering: three launches); labels are
         # taken to lie in [0, 1024) -- an image that breaks this reports count -1 and goes through the general path
-        idx, count = _native.nms_images(boxes, scores, idxs, 1, _LABEL_CAP, iou_threshold, max(int(max_num), 1))
+        idx, count = _native.nms_images(boxes, scores, idxs, 1, _LABEL_CAP, iou_threshold, max(int(max_num), 1),
+                                        iou_calculator=iou_calculator)
         n = int(count)                                       # the host synchronisation the caller needs anyway
         if n >= 0:
             keep = idx[0, :min(n, max_num)].long()
             return torch.cat([boxes[keep], scores[keep, None].to(boxes.dtype)], -1), keep
-    keep = _keep_indices(boxes, scores, idxs, iou_threshold)
+    keep = _keep_indices(boxes, scores, idxs, iou_threshold, iou_calculator=iou_calculator)
     keep = keep.sort()[0]                                   # :49 nonzero() order
     kept_scores, inds = scores[keep].sort(descending=True)  # :51
     keep = keep[inds][:max_num]
@@ -71,7 +72,7 @@ def sph_batched_nms(boxes, scores, idxs, nms_cfg, iou_calculator='sph2pob_effici
 
 
 def sph_batched_nms_images(boxes, scores, labels, image_ids, iou_threshold=0.5, num_images=None, num_classes=None,
-                           max_per_segment=None, valid=None):
+                           max_per_segment=None, valid=None, iou_calculator='sph2pob_efficient'):
     """Test-time batch: one launch over every (image, class) segment of a whole batch (labels < 2**20,
     image ids < 2**11).  Returns the kept indices (into boxes), grouped by image and score-descending inside an image.
 
@@ -84,7 +85,7 @@ def sph_batched_nms_images(boxes, scores, labels, image_ids, iou_threshold=0.5, 
         if valid is not None:
             raise ValueError("valid= needs num_images, num_classes and max_per_segment")
         seg = (image_ids.long() << 20) | labels.long()
-        keep = _keep_indices(boxes, scores, seg, iou_threshold, desc)
+        keep = _keep_indices(boxes, scores, seg, iou_threshold, desc, iou_calculator)
     else:
         nseg = int(num_images) * int(num_classes)
         seg = image_ids.long() * int(num_classes) + labels.long()
@@ -95,12 +96,13 @@ def sph_batched_nms_images(boxes, scores, labels, image_ids, iou_threshold=0.5, 
         offsets = torch.zeros(counts.numel() + 1, dtype=torch.int32, device=scores.device)
         offsets[1:] = counts.cumsum(0)
         typical = max(1, (2 * boxes.size(0)) // max(1, counts.numel()))     # twice the mean segment length
-        flags = _native.nms_batched(boxes, order, offsets, int(max_per_segment), iou_threshold, typical)
+        flags = _native.nms_batched(boxes, order, offsets, int(max_per_segment), iou_threshold, typical, iou_calculator)
         keep = order[flags == 1]          # a refused (too long) segment is flagged 0xFF and drops out: size the hint right
     return keep[torch.argsort((image_ids[keep].long() << 32) | desc[keep])]
 
 
-def sph_nms_image_blocks(boxes, scores, labels, num_images, num_classes, iou_threshold=0.5, max_per_img=None, valid=None):
+def sph_nms_image_blocks(boxes, scores, labels, num_images, num_classes, iou_threshold=0.5, max_per_img=None, valid=None,
+                         iou_calculator='sph2pob_efficient'):
     """Test-time NMS of a whole batch whose candidates come as `num_images` equal, contiguous blocks (what the head's
     post-processing emits): sort, per-(image, class) suppression and the per-image score ordering all run on the device
     (``sphk_nms_images``: three launches, no host synchronisation).  Returns ``(idx [num_images, max_per_img] int32,
@@ -110,17 +112,19 @@ def sph_nms_image_blocks(boxes, scores, labels, num_images, num_classes, iou_thr
     candidates of one class): run that batch through :func:`sph_batched_nms_images` instead."""
     per_image = boxes.size(0) // max(1, num_images)
     max_out = per_image if max_per_img is None else min(int(max_per_img), per_image)
-    return _native.nms_images(boxes, scores, labels, int(num_images), int(num_classes), iou_threshold, max(max_out, 1), valid)
+    return _native.nms_images(boxes, scores, labels, int(num_images), int(num_classes), iou_threshold, max(max_out, 1), valid,
+                              iou_calculator=iou_calculator)
 
 
 class SphNMS:
-    """sph_nms.py:7-19.  ``iou_calculator`` other than 'sph2pob_efficient' select CPU/planar routines
-    of the reference that are outside this path: refused loudly."""
+    """sph_nms.py:7-19.  'sph2pob_efficient' (the default) and 'naive_iou' (what the reference's indoor360 configs set:
+    planar IoU of the sph2pix boxes) run in the same NMS kernel; 'unbiased_iou' is the reference's CPU numpy routine,
+    outside this path: refused loudly."""
 
     def __init__(self, iou_calculator='sph2pob_efficient'):
-        if iou_calculator == 'sph2pob_efficient':
+        if iou_calculator in ('sph2pob_efficient', 'naive_iou'):
             self.iou_calculator = iou_calculator
-        elif iou_calculator in ('unbiased_iou', 'naive_iou'):
+        elif iou_calculator == 'unbiased_iou':
             raise NotImplementedError("SphNMS(%r): no CUDA kernel on this path (and no fallback)" % iou_calculator)
         else:
             raise NotImplementedError('Not supported iou_calculator.')

@@ -10,7 +10,7 @@ import torch
 
 from ... import _native
 
-__all__ = ["sph2pob_standard_iou", "sph2pob_efficient_iou", "fov_iou", "sph_iou"]
+__all__ = ["sph2pob_standard_iou", "sph2pob_efficient_iou", "fov_iou", "sph_iou", "naive_iou"]
 
 
 def _empty(bboxes1, rows, cols, is_aligned):
@@ -62,3 +62,13 @@ def fov_iou(bboxes1, bboxes2, mode='iou', is_aligned=False, calculator='diff'):
     """sphdet/iou/sph_iou_api.py:156-177 (+ approximate_ious.py:28-55).  BFoV only."""
     assert mode in ['iou']
     return _run("fov", bboxes1, bboxes2, mode, is_aligned, "arc")
+
+
+def naive_iou(bboxes1, bboxes2, mode='iou', is_aligned=False, box_formator='sph2pix'):
+    """sphdet/iou/sph_iou_api.py:181-198: the boxes read as planar boxes of the 512 x 1024 equirectangular image
+    (``Sph2PlanarBoxTransform('sph2pix')``) and mmcv's planar IoU (``bbox_overlaps`` for BFoV, ``box_iou_rotated`` for
+    RBFoV), no jitter, no clamp -- the calculator the reference's indoor360 configs give to the test-time NMS."""
+    assert mode in ['iou']
+    if box_formator != 'sph2pix':
+        raise NotImplementedError("naive_iou: only box_formator='sph2pix' (the reference's default) has a kernel")
+    return _run("naive", bboxes1, bboxes2, mode, is_aligned, "arc")

@@ -5,7 +5,7 @@ from __future__ import annotations
 import torch
 
 from ..registry import IOU_CALCULATORS
-from .sph_iou_api import fov_iou, sph2pob_efficient_iou, sph2pob_standard_iou, sph_iou
+from .sph_iou_api import fov_iou, naive_iou, sph2pob_efficient_iou, sph2pob_standard_iou, sph_iou
 
 # backends of the reference that have a CUDA kernel here; the others are out of this path's scope
 _BACKENDS = {
@@ -13,6 +13,7 @@ _BACKENDS = {
     'sph2pob_efficient_iou': sph2pob_efficient_iou,
     'fov_iou': fov_iou,
     'sph_iou': sph_iou,
+    'naive_iou': naive_iou,
 }
 _REFERENCE_BACKENDS = ['unbiased_iou', 'sph2pob_standard_iou', 'sph2pob_legacy_iou', 'sph2pob_efficient_iou',
                        'naive_iou', 'fov_iou', 'sph_iou', 'kent_iou']

@@ -83,6 +83,8 @@ def get_bboxes_batch(cls_scores, bbox_preds, mlvl_priors, bbox_coder, cfg, box_v
     score_thr = float(_cfg_get(cfg, 'score_thr', 0.0))
     nms_cfg = _cfg_get(cfg, 'nms') or {}
     iou_thr = float(nms_cfg.get('iou_threshold', 0.5))
+    iou_calc = _cfg_get(cfg, 'iou_calculator', 'sph2pob_efficient')      # test_cfg.iou_calculator (sph_retina_head.py:89-90)
+    SphNMS(iou_calc)                                                      # same refusals as the per-image path
     B, D = cls_scores[0].size(0), box_version
     sc, lb, dl, pr = [], [], [], []
     num_cls = None
@@ -107,7 +109,8 @@ def get_bboxes_batch(cls_scores, bbox_preds, mlvl_priors, bbox_coder, cfg, box_v
     counts = None
     if K <= 16384:
         # sort, suppression and per-image ordering on the device; the one host synchronisation is reading the counts
-        idx, count = sph_nms_image_blocks(boxes, scores, labels, B, num_cls, iou_thr, max_per_img, valid=scores > score_thr)
+        idx, count = sph_nms_image_blocks(boxes, scores, labels, B, num_cls, iou_thr, max_per_img, valid=scores > score_thr,
+                                          iou_calculator=iou_calc)
         counts = count.tolist()
         if min(counts) >= 0:
             sels = [idx[b, :counts[b]].long() for b in range(B)]
@@ -116,7 +119,7 @@ def get_bboxes_batch(cls_scores, bbox_preds, mlvl_priors, bbox_coder, cfg, box_v
     if counts is None:
         image_ids = torch.arange(B, device=scores.device).repeat_interleave(K)
         keep = sph_batched_nms_images(boxes, scores, labels, image_ids, iou_thr, num_images=B, num_classes=num_cls,
-                                      max_per_segment=K, valid=scores > score_thr)
+                                      max_per_segment=K, valid=scores > score_thr, iou_calculator=iou_calc)
         counts = torch.bincount(image_ids[keep], minlength=B).tolist()
         sels, start = [], 0
         for b in range(B):

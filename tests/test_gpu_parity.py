@@ -552,6 +552,46 @@ def test_anchor_targets_batch(api, decoded):
     assert torch.equal(lw2 == 2.5, bw[..., 0] == 1) and cnt.shape == (4, 2) and int(cnt[2, 0]) == 0 and int(cnt[2, 1]) == anchors.size(0)
 
 
+# ---- naive_iou (planar IoU of the sph2pix boxes) and SphNMS('naive_iou') ------------------------------------------
+@pytest.mark.parametrize("box", ["bfov", "rbfov"])
+def test_naive_iou_golden(api, box):
+    g = load_golden("naive")
+    b1, b2 = cu(g[box + "_b1"]), cu(g[box + "_b2"])
+    got = api.iou.naive_iou(b1, b2, is_aligned=True)
+    ok, err = within(got.cpu().numpy(), g[box + "_aligned_f64"], g[box + "_aligned_f32"])
+    assert got.shape == (b1.size(0),) and ok.all(), (np.where(~ok)[0][:10], err[~ok][:10])
+    mat = api.iou.SphOverlaps2D('naive_iou', box_version=b1.size(1))(b1[:37], b2[:301])
+    ok, err = within(mat.cpu().numpy(), g[box + "_rc_f64"], g[box + "_rc_f32"])
+    assert mat.shape == (37, 301) and ok.all(), err[~ok][:10]
+    # N x M equals the aligned call on the expansion (same per-pair function; the two kernels contract its FMAs differently)
+    flat = api.iou.naive_iou(b1[:37].repeat_interleave(301, 0), b2[:301].repeat(37, 1), is_aligned=True)
+    assert float((mat.reshape(-1) - flat).abs().max()) < 2e-6 and torch.equal(mat.reshape(-1) == 0, flat == 0)
+    rmax, rarg, cmax, carg = api.iou.sph_max_overlaps(b1[:37], b2[:301], backend='naive_iou')
+    assert torch.equal(rmax, mat.max(dim=1)[0]) and torch.equal(cmax, mat.max(dim=0)[0])
+
+
+@pytest.mark.parametrize("box", ["bfov", "rbfov"])
+def test_naive_nms_golden_keep_sets(api, box):
+    """SphNMS('naive_iou') -- what the reference's indoor360 configs run at test time -- keep lists equal to the reference's
+    wherever no pair IoU is within 1e-5 of the threshold (BASELINE.json north_star); both the single-image pipeline and the
+    batched per-segment path."""
+    g = load_golden("naive")
+    boxes, scores, idxs = cu(g[box + "_boxes"]), cu(g[box + "_scores"]), cu(g[box + "_idxs"])
+    iou = g[box + "_pair_iou_f64"]
+    same = g[box + "_idxs"][:, None] == g[box + "_idxs"][None, :]
+    for thr in (0.3, 0.5):
+        assert not (np.abs(iou[same] - thr) < 1e-5).any(), "fixture has a pair on the threshold"
+        want = g["%s_keep_thr%d" % (box, int(thr * 10))].tolist()
+        dets, keep = api.nms.SphNMS('naive_iou')(boxes, scores, idxs, dict(type="nms", iou_threshold=thr, max_num=150))
+        assert keep.cpu().tolist() == want and dets.shape == (len(want), boxes.size(1) + 1)
+        from sph_retina_b200.sphdet.bbox.nms import sph_batched_nms_images
+        kept = sph_batched_nms_images(boxes, scores, idxs, torch.zeros_like(idxs), thr, iou_calculator='naive_iou')
+        assert kept.cpu().tolist()[:150] == want
+    if box == "bfov":   # and it is a different calculator: the Sph2Pob NMS keeps another set on this fixture
+        _, keep_sph = api.nms.SphNMS()(boxes, scores, idxs, dict(iou_threshold=0.5, max_num=150))
+        assert keep_sph.cpu().tolist() != g[box + "_keep_thr5"].tolist()
+
+
 # ---- the other losses on the Sph2Pob OBBs (SURVEY.md 8f row 3) ---------------------------------------------------
 def _other_loss(api, cls, kw, **extra):
     return getattr(api.losses, cls)(**kw, **extra)

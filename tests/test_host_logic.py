@@ -157,6 +157,25 @@ def test_vectorised_assign_wrt_overlaps_equals_the_reference_loop():
                     assert torch.equal(r.labels, l)
 
 
+def test_naive_iou_and_nms_calculators_host_contract():
+    """sph_iou_api.py:181-198 / sph_nms.py:8-16: names, defaults and refusals."""
+    from sph_retina_b200.sphdet.bbox.nms import SphNMS
+    from sph_retina_b200.sphdet.iou import SphOverlaps2D, naive_iou
+    E = inspect.Parameter.empty
+    assert [(p.name, p.default) for p in inspect.signature(naive_iou).parameters.values()] == [
+        ('bboxes1', E), ('bboxes2', E), ('mode', 'iou'), ('is_aligned', False), ('box_formator', 'sph2pix')]
+    b = torch.rand(3, 4) * 50 + 10
+    with pytest.raises(AssertionError):
+        naive_iou(b, b, mode='iof')
+    with pytest.raises(NotImplementedError):
+        naive_iou(b, b, box_formator='sph2tan')
+    assert naive_iou(b[:0], b).shape == (0, 3) and SphOverlaps2D('naive_iou')(b, b[:0]).shape == (3, 0)
+    assert SphNMS('naive_iou').iou_calculator == 'naive_iou' and SphNMS().iou_calculator == 'sph2pob_efficient'
+    for bad in ('unbiased_iou', 'planar'):
+        with pytest.raises(NotImplementedError):
+            SphNMS(bad)
+
+
 def test_other_sph2pob_losses_host_contract():
     """Sph2PobGDLoss / Sph2PobKFLoss / Sph2PobL1Loss (sphdet/losses/__init__.py:3-8): registry names, constructor
     checks of the mmrotate / reference classes, and the loud failure on CPU tensors."""

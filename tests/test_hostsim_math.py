@@ -364,3 +364,13 @@ def test_other_losses_upstream_is_linear(hostsim):
                 acc += hs_obb_loss(hostsim, cls, kw, g["pred"], g["target"], up=u)[1]
             rel, _ = grad_row_error(acc[64:], base[1][64:].astype(np.float64))
             assert np.median(rel) < 1e-6 and (rel < 1e-4).mean() > 0.99
+
+
+@pytest.mark.parametrize("box", ["bfov", "rbfov"])
+def test_naive_iou_golden(hostsim, box):
+    """naive_iou_pair (planar IoU of the sph2pix boxes; the clipper for RBFoV) against the reference's float64 run."""
+    g = load_golden("naive")
+    got = hs_aligned(hostsim, 4, g[box + "_b1"], g[box + "_b2"])
+    ok, err = within(got, g[box + "_aligned_f64"], g[box + "_aligned_f32"])
+    assert ok.all(), (np.where(~ok)[0][:10], err[~ok][:10])
+    assert np.nanmax(err) < 5e-6

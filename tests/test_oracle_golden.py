@@ -215,3 +215,19 @@ def test_restatement_get_targets_single_hand_case():
     enc = O.get_targets_single(anchors, gts, None, gt_inds, 1, reg_decoded_bbox=False, pos_weight=2.0, stds=[0.1, 0.1, 0.2, 0.2])
     assert enc[0].tolist() == [0, 1, 0, 1] and enc[1].tolist() == [2, 1, 2, 0]
     np.testing.assert_allclose(enc[2][0].numpy(), [(12 - 10) / 30 / 0.1, (22 - 20) / 40 / 0.1, np.log(28 / 30) / 0.2, np.log(36 / 40) / 0.2], rtol=1e-5)
+
+
+@pytest.mark.parametrize("box", ["bfov", "rbfov"])
+def test_restatement_naive_iou_and_its_nms(box):
+    """naive_iou (sph_iou_api.py:181-198) and SphNMS('naive_iou') against the reference's own functions."""
+    g = load_golden("naive")
+    b1, b2 = torch.from_numpy(g[box + "_b1"]), torch.from_numpy(g[box + "_b2"])
+    got = O.naive_iou(b1.double(), b2.double(), is_aligned=True).numpy()
+    np.testing.assert_allclose(got, g[box + "_aligned_f64"], atol=1e-9, equal_nan=True)
+    got = O.naive_iou(b1[:37].double(), b2[:301].double()).numpy()
+    np.testing.assert_allclose(got, g[box + "_rc_f64"], atol=1e-9, equal_nan=True)
+    np.testing.assert_allclose(O.naive_iou(b1, b2, is_aligned=True).numpy(), g[box + "_aligned_f32"], atol=1e-6, equal_nan=True)
+    boxes, scores, idxs = (torch.from_numpy(g["%s_%s" % (box, k)]) for k in ("boxes", "scores", "idxs"))
+    for thr in (0.3, 0.5):
+        _, keep = O.nms_batched(boxes, scores, idxs, thr, max_num=150, iou_fn=lambda a, b: O.naive_iou(a, b))
+        assert keep.tolist() == g["%s_keep_thr%d" % (box, int(thr * 10))].tolist()
