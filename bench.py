@@ -68,34 +68,77 @@ class ClockSampler:
     background thread every ~2 ms (the timed region lasts tens of ms: too short for `nvidia-smi -lms`)."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, gpu_index):
-        self.gpu_index, self.thread, self.stop_flag = gpu_index, None, False
+    _CHILD = r"""
+import json, signal, sys, time
+import pynvml as nv
+nv.nvmlInit()
+hs = [nv.nvmlDeviceGetHandleByIndex(int(a)) for a in sys.argv[1:]]
+sm, power, mask, stop = [], [], 0, [False]
+signal.signal(signal.SIGTERM, lambda *a: stop.__setitem__(0, True))
+print("ready", flush=True)
+while not stop[0]:
+    for h in hs:
+        try:
+            sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+            power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+        except Exception:
+            pass
+    time.sleep(0.002)
+print(json.dumps({"sm": sm, "mask": mask, "power": power,
+                  "max": float(nv.nvmlDeviceGetMaxClockInfo(hs[0], nv.NVML_CLOCK_SM)) if hs else None}), flush=True)
+"""
+
+    def __init__(self, gpu_indices, external=False):
+        """gpu_indices: the local GPUs to watch.  In a multi-rank run ONE rank watches all of them, from a child PROCESS
+        (external=True): a sampler thread in every rank competes with that rank's launch thread for the interpreter lock
+        and with the other ranks for the host cores, which the 32 us-per-call assign workload can feel."""
+        self.external, self.child, self.gpu_indices = external and len(gpu_indices) > 0, None, list(gpu_indices)
+        self.thread, self.stop_flag = None, False
         self.sm, self.reasons, self.max_mhz, self.power = [], set(), None, []
+        self.hs = []
         try:
             import pynvml
             pynvml.nvmlInit()
             vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-            phys = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].isdigit() else gpu_index
-            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
-            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            for g in gpu_indices:
+                phys = int(vis.split(",")[g]) if vis and vis.split(",")[g].isdigit() else g
+                self.hs.append(pynvml.nvmlDeviceGetHandleByIndex(phys))
+            self.nv = pynvml if self.hs else None
+            if self.hs:
+                self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.hs[0], pynvml.NVML_CLOCK_SM))
         except Exception:
             self.nv = None
 
     def _loop(self):
-        nv, h = self.nv, self.h
+        nv = self.nv
         while not self.stop_flag:
-            try:
-                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
-                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
-                for bit, name in self.REASONS.items():
-                    if mask & bit:
-                        self.reasons.add(name)
-                self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
-            except Exception:
-                pass
+            for h in self.hs:
+                try:
+                    self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    for bit, name in self.REASONS.items():
+                        if mask & bit:
+                            self.reasons.add(name)
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                except Exception:
+                    pass
             time.sleep(0.002)
 
+    def _physical(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        return [str(int(vis.split(",")[g]) if vis and vis.split(",")[g].isdigit() else g) for g in self.gpu_indices]
+
     def start(self):
+        if self.external:
+            import subprocess
+            try:
+                self.child = subprocess.Popen([sys.executable, "-c", self._CHILD] + self._physical(), stdout=subprocess.PIPE, text=True)
+                if self.child.stdout.readline().strip() != "ready":
+                    self.child = None
+            except Exception:
+                self.child = None
+            return
         if self.nv is None:
             return
         import threading
@@ -103,6 +146,17 @@ class ClockSampler:
         self.thread.start()
 
     def stop(self):
+        if self.external:
+            if self.child is None:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+            self.child.terminate()
+            try:
+                d = json.loads(self.child.communicate(timeout=10)[0].strip().splitlines()[-1])
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml sampler failed"]}
+            return {"sm_mhz": statistics.median(d["sm"]) if d["sm"] else None, "sm_max_mhz": d["max"],
+                    "reasons": sorted(n for b, n in self.REASONS.items() if d["mask"] & b), "samples": len(d["sm"]),
+                    "power_w_max": max(d["power"]) if d["power"] else None, "gpus_watched": len(self.gpu_indices)}
         if self.thread is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
         self.stop_flag = True
@@ -399,6 +453,15 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # one slice of the host cores per rank: the launch thread of a rank is then never queued behind another rank's
+        # threads (torchrun does not pin; the per-image calls of the assign workload are ~30 us apart)
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = len(cores) // int(os.environ.get("LOCAL_WORLD_SIZE", world))
+            if per >= 1:
+                os.sched_setaffinity(0, cores[local_rank * per:(local_rank + 1) * per])
+        except (AttributeError, OSError, ValueError):
+            pass
         dist.init_process_group("nccl", device_id=dev)
     from sph_retina_b200 import _native as native
     from sph_retina_b200 import synthetic as S
@@ -445,7 +508,8 @@ def run_ours(args):
                     "per-anchor and per-GT max/argmax, NCCL all_gather + all_reduce(MAX) of packed keys in the timed region")
 
     # ---- timed region (device time, per-step events, L2 flushed between steps) --------------------
-    sampler = ClockSampler(local_rank)
+    # rank 0 watches every local GPU of the run; the other ranks do not run a sampler thread
+    sampler = ClockSampler(list(range(int(os.environ.get("LOCAL_WORLD_SIZE", world)))) if rank == 0 else [], external=world > 1)
     l0 = native.launches
     for _ in range(args.warmup):
         step()
