@@ -40,8 +40,11 @@ enum sphk_kind {
     SPHK_KIND_SPH2POB_STANDARD = 1,  /* 'sph2pob_standard_iou'   sphdet/iou/sph_iou_api.py:94-95   */
     SPHK_KIND_SPH = 2,               /* 'sph_iou'                sphdet/iou/sph_iou_api.py:130-151 */
     SPHK_KIND_FOV = 3,               /* 'fov_iou'                sphdet/iou/sph_iou_api.py:156-177 */
-    SPHK_KIND_NAIVE = 4              /* 'naive_iou'              sphdet/iou/sph_iou_api.py:181-198 (planar IoU of the
+    SPHK_KIND_NAIVE = 4,             /* 'naive_iou'              sphdet/iou/sph_iou_api.py:181-198 (planar IoU of the
                                         sph2pix boxes; BFoV or RBFoV, mode 'iou' only)                            */
+    SPHK_KIND_UNBIASED = 5           /* 'unbiased_iou'           sphdet/iou/sph_iou_api.py:103-125 (exact spherical IoU,
+                                        unbiased_iou_bfov.py / unbiased_iou_rbfov.py; the default backend of
+                                        SphOverlaps2D; evaluated in double; mode 'iou' only)                      */
 };
 enum sphk_mode { SPHK_MODE_IOU = 0, SPHK_MODE_IOF = 1 };                     /* sph_iou_api.py:49     */
 enum sphk_edge { SPHK_EDGE_ARC = 0, SPHK_EDGE_CHORD = 1, SPHK_EDGE_TANGENT = 2 }; /* sph2pob_efficient.py:100-108 */
@@ -224,7 +227,8 @@ int sphk_decode_loss_reduce(const float* anchors, const float* deltas, const flo
 
 /* Batched greedy spherical NMS (SphNMS / sph_batched_nms / sph_nms_op,
  * sphdet/bbox/nms/sph_nms.py:22-74).  kind: the IoU SphNMS was built with (sph_nms.py:8-16) -- SPHK_KIND_SPH2POB_EFFICIENT
- * (its default) or SPHK_KIND_NAIVE (the reference's indoor360 configs: test_cfg.iou_calculator = 'naive_iou').
+ * (its default), SPHK_KIND_NAIVE (the reference's indoor360 configs: test_cfg.iou_calculator = 'naive_iou') or
+ * SPHK_KIND_UNBIASED (its pandora configs: 'unbiased_iou').
  *   boxes       [M, D]
  *   order       [M]    int32 indices into boxes, grouped by segment (one segment = one
  *                      (image, class) group), score-descending inside a segment (:65)

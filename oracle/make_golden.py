@@ -310,6 +310,41 @@ def golden_naive(R):
     print("naive", {k: (v.shape, float(np.nanmean(v))) for k, v in out.items() if "aligned_f64" in k or "keep" in k})
 
 
+def golden_unbiased(R):
+    """unbiased_iou (sph_iou_api.py:103-125; numpy classes unbiased_iou_bfov.Sph / unbiased_iou_rbfov.Sph) run on float64
+    copies of the float32 boxes ("truth": the method needs double, unbiased_iou_bfov.py:187) and as shipped on float32,
+    aligned + N x M, and SphNMS('unbiased_iou') keep sets from the float64 run."""
+    out = {}
+    for box in ("bfov", "rbfov"):
+        torch.manual_seed(71)
+        n = 1536
+        b1 = R.generate_boxes(n, alpha_range=(1, 120), beta_range=(1, 120), dtype="float", box=box)
+        b2 = (b1 + torch.randn_like(b1) * torch.tensor([8, 8, 8, 8, 15.0])[:b1.size(1)]).clamp(min=0.5)
+        b2[:, 0].clamp_(0, 360); b2[:, 1].clamp_(0, 180); b2[:, 2:4].clamp_(max=179)
+        b2[:64] = R.generate_boxes(64, alpha_range=(1, 120), beta_range=(1, 120), dtype="float", box=box)   # unrelated pairs
+        b2[64:96] = b1[64:96]                                                                                # identical pairs
+        b2[96:128, 2:4] = b1[96:128, 2:4] * 0.4                                                              # nested boxes
+        b2[96:128, :2] = b1[96:128, :2] + 0.5
+        out[box + "_b1"], out[box + "_b2"] = _np(b1), _np(b2)
+        out[box + "_aligned_f32"] = _np(R.unbiased_iou(b1, b2, is_aligned=True))
+        out[box + "_aligned_f64"] = _np(R.unbiased_iou(b1.double(), b2.double(), is_aligned=True)).astype(np.float64)
+        rows, cols = b1[:23], b2[:201]
+        out[box + "_rc_f32"] = _np(R.unbiased_iou(rows, cols))
+        out[box + "_rc_f64"] = _np(R.unbiased_iou(rows.double(), cols.double())).astype(np.float64)
+        torch.manual_seed(72)
+        seeds = R.generate_boxes(60, alpha_range=(5, 60), beta_range=(5, 60), dtype="float", box=box)
+        boxes = (seeds.repeat(5, 1) + torch.randn(300, seeds.size(1)) * 2).clamp(min=1)
+        boxes[:, 1].clamp_(1, 179)
+        scores, idxs = torch.rand(300), torch.randint(0, 5, (300,))
+        for thr in (0.3, 0.5):
+            _, keep = R.SphNMS("unbiased_iou")(boxes.double(), scores.double(), idxs, dict(type="nms", iou_threshold=thr, max_num=120))
+            out["%s_keep_thr%d" % (box, int(thr * 10))] = _np(keep)
+        out["%s_pair_iou_f64" % box] = _np(R.unbiased_iou(boxes.double(), boxes.double())).astype(np.float32)
+        out["%s_boxes" % box], out["%s_scores" % box], out["%s_idxs" % box] = _np(boxes), _np(scores), _np(idxs)
+    np.savez_compressed(os.path.join(OUT, "unbiased.npz"), **out)
+    print("unbiased", {k: (v.shape, float(np.nanmean(v))) for k, v in out.items() if "aligned_f" in k or "keep" in k})
+
+
 def golden_nms(R):
     out = {}
     for box in ("bfov", "rbfov"):
@@ -397,3 +432,4 @@ if __name__ == "__main__":
     golden_coder(R)
     golden_other_losses(R)
     golden_naive(R)
+    golden_unbiased(R)

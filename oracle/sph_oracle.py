@@ -479,6 +479,70 @@ def naive_iou(b1, b2, mode="iou", is_aligned=False):
     return rotated_iou(p1, p2, mode)
 
 
+# --------------------------------------------------------------------------- #
+# unbiased_iou (sph_iou_api.py:103-125; unbiased_iou_bfov.py:10-204, unbiased_iou_rbfov.py:4-181)
+# --------------------------------------------------------------------------- #
+def _unbiased_normals(box, rotated):
+    """getNormal: inward unit normals (left, right, up, down) of the four boundary circles, [4, n, 3]; RBFoV: rotated
+    about the view axis by gamma (roll_T)."""
+    theta, phi, fx, fy = box[:, 0:1], box[:, 1:2], box[:, 2:3] / 2, box[:, 3:4] / 2
+    look = torch.cat([torch.sin(phi) * torch.cos(theta), torch.sin(phi) * torch.sin(theta), torch.cos(phi)], dim=1)
+    right = torch.cat([-torch.sin(theta), torch.cos(theta), torch.zeros_like(theta)], dim=1)
+    up = torch.cat([-torch.cos(phi) * torch.cos(theta), -torch.cos(phi) * torch.sin(theta), torch.sin(phi)], dim=1)
+    N = [-torch.cos(fx) * right + torch.sin(fx) * look, torch.cos(fx) * right + torch.sin(fx) * look,
+         -torch.cos(fy) * up + torch.sin(fy) * look, torch.cos(fy) * up + torch.sin(fy) * look]
+    if rotated:
+        g = box[:, 4]
+        c, s_, k = torch.cos(g), torch.sin(g), 1 - torch.cos(g)
+        nx, ny, nz = look[:, 0], look[:, 1], look[:, 2]
+        M = torch.stack([torch.stack([nx * nx * k + c, nx * ny * k - nz * s_, nx * nz * k + ny * s_], -1),
+                         torch.stack([nx * ny * k + nz * s_, ny * ny * k + c, ny * nz * k - nx * s_], -1),
+                         torch.stack([nx * nz * k - ny * s_, ny * nz * k + nx * s_, nz * nz * k + c], -1)], -2)
+        N = [torch.einsum("nij,nj->ni", M, v) for v in N]
+    return torch.stack(N)
+
+
+def unbiased_iou(b1, b2, is_aligned=False):
+    """Restatement of the reference's Unbiased-IoU pipeline (vectorised; float64 inside, float32 out, like the numpy
+    classes fed with double boxes): jitter, 40 candidate vertices, round(V . N, 8) >= 0 for the eight normals, area from
+    the interior angles of the counted vertices (duplicates are not merged: the DFS clean-up is disabled in the reference),
+    the two different closing formulas of the BFoV / RBFoV files, clamp."""
+    rows, cols = b1.size(0), b2.size(0)
+    if rows * cols == 0:
+        return b1.new_zeros((rows, 1)) if is_aligned else b1.new_zeros((rows, cols))
+    D = b1.size(1)
+    if not is_aligned:
+        b1, b2 = b1.repeat_interleave(cols, 0), b2.repeat(rows, 1)
+    j1, j2 = jitter_spherical(b1.double().clone(), b2.double().clone())
+    j1, j2 = torch.deg2rad(j1), torch.deg2rad(j2)
+    N1, N2 = _unbiased_normals(j1, D == 5), _unbiased_normals(j2, D == 5)
+    N = torch.cat([N1, N2])                                       # [8, n, 3]
+    cand, e0, e1 = [], [], []
+    for Nb in (N1, N2):
+        for a, b in ((0, 2), (3, 0), (2, 1), (1, 3)):             # left x up, down x left, up x right, right x down
+            c = torch.cross(Nb[a], Nb[b], dim=-1)
+            cand.append(c / c.norm(dim=1, keepdim=True)); e0.append(Nb[a]); e1.append(Nb[b])
+    for i in range(4):
+        for j in range(4):
+            c = torch.cross(N1[i], N2[j], dim=-1)
+            v = c / (c.norm(dim=1, keepdim=True) + 1e-10)
+            cand += [v, -v]; e0 += [N1[i], N2[j]]; e1 += [N2[j], N1[i]]
+    V, E0, E1 = torch.stack(cand), torch.stack(e0), torch.stack(e1)          # [40, n, 3]
+    dots = torch.einsum("vni,kni->vnk", V, N)
+    valid = (torch.round(dots * 1e8) >= 0).all(dim=2)                        # [40, n]
+    ang = torch.arccos((-(E0 * E1).sum(-1)).clamp(-1, 1))
+    count = valid.sum(0)
+    inter = (ang * valid).sum(0) - (count - 2).double() * math.pi       # (int tensor * float would round pi to float32)
+    inter = torch.where(count == 0, torch.zeros_like(inter), inter)
+
+    def area(fx, fy):
+        return 4 * torch.arccos(-torch.sin(fx / 2) * torch.sin(fy / 2)) - 2 * math.pi
+    a1, a2 = area(j1[:, 2], j1[:, 3]), area(j2[:, 2], j2[:, 3])
+    iou = (inter + 1e-8) / (a1 + a2 - (inter + 1e-8)) if D == 4 else inter / (a1 + a2 - inter + 1e-8)
+    iou = iou.float().clamp(0, 1)
+    return iou if is_aligned else iou.view(rows, cols)
+
+
 # ---- the other Sph2Pob losses (SURVEY.md 8f row 3) --------------------------------------------------------------------
 def _decorated(pred, target, weight):
     """Sph2PobTransfrom.new_forward (sph2pob_transform.py:24-35): OBBs of the pair + the widened BFoV weight."""

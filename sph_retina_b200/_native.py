@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "libsphk.so")
 _PROBE_LIB = os.environ.get("SPHK_PROBE_LIB")      # tools/ only: an instrumented build of the same sources
 
-KIND = {"sph2pob_efficient": 0, "sph2pob_standard": 1, "sph": 2, "fov": 3, "naive": 4}
+KIND = {"sph2pob_efficient": 0, "sph2pob_standard": 1, "sph": 2, "fov": 3, "naive": 4, "unbiased": 5}
 MODE = {"iou": 0, "iof": 1}
 EDGE = {"arc": 0, "chord": 1, "tangent": 2}
 ANGLE = {"equator": 0, "project": 1}
@@ -531,7 +531,7 @@ def riou_fwd_bwd(o1, o2, grad_iou=None, want1=False, want2=False):
     return iou, g1, g2
 
 
-NMS_KIND = {"sph2pob_efficient": 0, "naive_iou": 4}      # SphNMS's iou_calculator names (sph_nms.py:8-16)
+NMS_KIND = {"sph2pob_efficient": 0, "naive_iou": 4, "unbiased_iou": 5}      # SphNMS's iou_calculator names (sph_nms.py:8-16)
 
 
 def nms_batched(boxes, order, seg_offsets, max_seg_len: int, iou_threshold: float, typical_seg_len: int = 0,

@@ -129,6 +129,7 @@ __global__ void __launch_bounds__(kThreads) k_iou_aligned(const float* __restric
     float v;
     if (KIND == KIND_SPH || KIND == KIND_FOV) v = approx_iou_pair(x, y, KIND);
     else if (KIND == KIND_NAIVE) v = naive_iou_pair(x, y, D, mode);
+    else if (KIND == KIND_UNBIASED) v = unbiased_iou_pair(x, y, D);
     else v = sph2pob_iou_pair(x, y, D, KIND, mode, edge, dense);
     out[i] = v;
 }
@@ -364,6 +365,7 @@ k_iou_pairwise(const float* __restrict__ rows, int64_t R, const float* __restric
         if (col_ok) {
             if (KIND == KIND_SPH || KIND == KIND_FOV) v = approx_iou_pair(x, y, KIND);
             else if (KIND == KIND_NAIVE) v = naive_iou_pair(x, y, D, mode);
+            else if (KIND == KIND_UNBIASED) v = unbiased_iou_pair(x, y, D);
             else v = sph2pob_iou_pair(x, y, D, KIND, mode, edge, dense);
             if (out) out[(r0 + r) * ld + col] = v;
             if (v > best_v) { best_v = v; best_r = (uint32_t)r; }
@@ -1272,9 +1274,11 @@ __device__ __forceinline__ void bitonic_sort_u64(unsigned long long* s, int n) {
 // The pivot test of sph_nms_op (sph_nms.py:70-73): the candidate survives iff IoU(pivot, candidate) <= thr (so a NaN IoU,
 // which only the unclamped planar `naive_iou` can produce, suppresses).  kind: Sph2Pob-efficient (SphNMS's default) or naive.
 __device__ __noinline__ float naive_pair_outofline(const RawBox& x, const RawBox& y, int D) { return naive_iou_pair(x, y, D, MODE_IOU); }
+__device__ __noinline__ float unbiased_pair_outofline(const RawBox& x, const RawBox& y, int D) { return unbiased_iou_pair(x, y, D); }
 __device__ __forceinline__ bool nms_suppresses(const float* __restrict__ boxes, int bi, int bj, const RawBox& x, const RawBox& y,
                                                int D, int kind, float thr) {
     if (kind == KIND_NAIVE) return !(naive_pair_outofline(x, y, D) <= thr);
+    if (kind == KIND_UNBIASED) return !(unbiased_pair_outofline(x, y, D) <= thr);
     return pair_iou_any(boxes, bi, boxes, bj, x, y, D, KIND_SPH2POB_EFFICIENT, MODE_IOU, EDGE_ARC) > thr;
 }
 
@@ -1595,8 +1599,9 @@ int sphk_device_info(int* sm_count, int* cc_major, int* cc_minor) {
 int sphk_iou_aligned(int kind, const float* b1, const float* b2, int64_t P, int D, int mode, int edge, int angle,
                      float* out, void* stream) {
     if (P < 0 || (D != 4 && D != 5)) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_aligned: P < 0 or D not in {4,5}");
-    if (kind < 0 || kind > SPHK_KIND_NAIVE) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_aligned: unknown kind");
-    if (kind == SPHK_KIND_NAIVE && mode != SPHK_MODE_IOU) return fail(SPHK_ERR_UNSUPPORTED, "naive_iou supports mode 'iou' only (sph_iou_api.py:182)");
+    if (kind < 0 || kind > SPHK_KIND_UNBIASED) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_aligned: unknown kind");
+    if ((kind == SPHK_KIND_NAIVE || kind == SPHK_KIND_UNBIASED) && mode != SPHK_MODE_IOU)
+        return fail(SPHK_ERR_UNSUPPORTED, "naive_iou / unbiased_iou support mode 'iou' only (sph_iou_api.py:104,182)");
     if (mode != SPHK_MODE_IOU && mode != SPHK_MODE_IOF) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_aligned: unknown mode");
     if (edge < 0 || edge > 2) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_aligned: unknown edge");
     if (angle != SPHK_ANGLE_EQUATOR && angle != SPHK_ANGLE_PROJECT) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_aligned: unknown angle");
@@ -1612,6 +1617,9 @@ int sphk_iou_aligned(int kind, const float* b1, const float* b2, int64_t P, int 
     } else if (kind == SPHK_KIND_NAIVE) {
         if (D == 4) k_iou_aligned<KIND_NAIVE, 4><<<blocks_for(P), kThreads, 0, s>>>(b1, b2, P, mode, edge, out, v, false);
         else k_iou_aligned<KIND_NAIVE, 5><<<blocks_for(P), kThreads, 0, s>>>(b1, b2, P, mode, edge, out, false, false);
+    } else if (kind == SPHK_KIND_UNBIASED) {
+        if (D == 4) k_iou_aligned<KIND_UNBIASED, 4><<<blocks_for(P), kThreads, 0, s>>>(b1, b2, P, mode, edge, out, v, false);
+        else k_iou_aligned<KIND_UNBIASED, 5><<<blocks_for(P), kThreads, 0, s>>>(b1, b2, P, mode, edge, out, false, false);
     } else if (kind == SPHK_KIND_SPH || kind == SPHK_KIND_FOV) {
         const unsigned g = blocks_for(P);
         if (v && !g_no_approx4 && P >= (int64_t)3 << 20) {      // below ~3 M pairs one pair per thread keeps more loads in flight
@@ -1711,14 +1719,15 @@ static int pairwise_impl(int kind, const float* rows, int64_t R, const float* co
                          const float* row_target, int* col_tie, unsigned long long* ext_rkey = nullptr,
                          unsigned long long* ext_ckey = nullptr) {
     if (R < 0 || C < 0 || (D != 4 && D != 5)) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: bad R, C or D");
-    if (kind < 0 || kind > SPHK_KIND_NAIVE) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: unknown kind");
-    if (kind == SPHK_KIND_NAIVE && mode != SPHK_MODE_IOU) return fail(SPHK_ERR_UNSUPPORTED, "naive_iou supports mode 'iou' only (sph_iou_api.py:182)");
+    if (kind < 0 || kind > SPHK_KIND_UNBIASED) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: unknown kind");
+    if ((kind == SPHK_KIND_NAIVE || kind == SPHK_KIND_UNBIASED) && mode != SPHK_MODE_IOU)
+        return fail(SPHK_ERR_UNSUPPORTED, "naive_iou / unbiased_iou support mode 'iou' only (sph_iou_api.py:104,182)");
     if (mode != SPHK_MODE_IOU && mode != SPHK_MODE_IOF) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: unknown mode");
     if (edge < 0 || edge > 2) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: unknown edge");
     if (angle != SPHK_ANGLE_EQUATOR && angle != SPHK_ANGLE_PROJECT) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: unknown angle");
     // "approx": the kinds evaluated one pair per thread by the generic tile kernel (no per-box records, no prefilter)
-    const bool approx = (kind == SPHK_KIND_SPH || kind == SPHK_KIND_FOV || kind == SPHK_KIND_NAIVE);
-    if (approx && kind != SPHK_KIND_NAIVE && (D != 4 || mode != SPHK_MODE_IOU))
+    const bool approx = (kind == SPHK_KIND_SPH || kind == SPHK_KIND_FOV || kind == SPHK_KIND_NAIVE || kind == SPHK_KIND_UNBIASED);
+    if ((kind == SPHK_KIND_SPH || kind == SPHK_KIND_FOV) && (D != 4 || mode != SPHK_MODE_IOU))
         return fail(SPHK_ERR_UNSUPPORTED, "sph_iou / fov_iou take BFoV boxes (D = 4) and mode 'iou' only");
     if (out && ld < C) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: ld < C");
     if (R + (int64_t)(uint32_t)row_base > 0xFFFFFFFFll || C + (int64_t)(uint32_t)col_base > 0xFFFFFFFFll)
@@ -1751,7 +1760,13 @@ static int pairwise_impl(int kind, const float* rows, int64_t R, const float* co
             const int64_t row_tiles = (R + kTileRows - 1) / kTileRows;
             if (col_tiles * row_tiles > 0x7FFFFFFFll) return fail(SPHK_ERR_UNSUPPORTED, "sphk_iou_pairwise: grid too large; shard the call");
             const unsigned g = (unsigned)(col_tiles * row_tiles);
-            if (kind == SPHK_KIND_NAIVE && D == 4)
+            if (kind == SPHK_KIND_UNBIASED && D == 4)
+                k_iou_pairwise<KIND_UNBIASED, 4><<<g, kThreads, 0, s>>>(rows, R, cols, C, mode, edge, out, ld, rkey, ckey, (uint32_t)row_base,
+                                                                         (uint32_t)col_base, col_tiles, v, false);
+            else if (kind == SPHK_KIND_UNBIASED)
+                k_iou_pairwise<KIND_UNBIASED, 5><<<g, kThreads, 0, s>>>(rows, R, cols, C, mode, edge, out, ld, rkey, ckey, (uint32_t)row_base,
+                                                                         (uint32_t)col_base, col_tiles, false, false);
+            else if (kind == SPHK_KIND_NAIVE && D == 4)
                 k_iou_pairwise<KIND_NAIVE, 4><<<g, kThreads, 0, s>>>(rows, R, cols, C, mode, edge, out, ld, rkey, ckey, (uint32_t)row_base,
                                                                       (uint32_t)col_base, col_tiles, v, false);
             else if (kind == SPHK_KIND_NAIVE)
@@ -2112,8 +2127,8 @@ int sphk_decode_loss_reduce(const float* anchors, const float* deltas, const flo
 int sphk_nms_batched(const float* boxes, const int32_t* order, const int32_t* seg_offsets, int32_t S, int32_t max_seg_len,
                      int32_t typical_seg_len, int D, int kind, float iou_threshold, uint8_t* keep, void* stream) {
     if (S < 0 || max_seg_len < 0 || (D != 4 && D != 5)) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_nms_batched: bad S, max_seg_len or D");
-    if (kind != SPHK_KIND_SPH2POB_EFFICIENT && kind != SPHK_KIND_NAIVE)
-        return fail(SPHK_ERR_UNSUPPORTED, "sphk_nms_batched: kind must be sph2pob_efficient or naive (SphNMS, sph_nms.py:8-16)");
+    if (kind != SPHK_KIND_SPH2POB_EFFICIENT && kind != SPHK_KIND_NAIVE && kind != SPHK_KIND_UNBIASED)
+        return fail(SPHK_ERR_UNSUPPORTED, "sphk_nms_batched: kind must be sph2pob_efficient, naive or unbiased (SphNMS, sph_nms.py:8-16)");
     if (S == 0 || max_seg_len == 0) return SPHK_OK;
     if (!boxes || !order || !seg_offsets || !keep) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_nms_batched: null pointer");
     const int max_words = (max_seg_len + 31) / 32;
@@ -2151,8 +2166,8 @@ int sphk_nms_images(const float* boxes, const float* scores, const int64_t* labe
                     int32_t* out_count, void* workspace, void* stream) {
     if (num_images < 0 || per_image < 0 || num_classes <= 0 || max_out < 0 || (D != 4 && D != 5))
         return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_nms_images: bad sizes or D");
-    if (kind != SPHK_KIND_SPH2POB_EFFICIENT && kind != SPHK_KIND_NAIVE)
-        return fail(SPHK_ERR_UNSUPPORTED, "sphk_nms_images: kind must be sph2pob_efficient or naive (SphNMS, sph_nms.py:8-16)");
+    if (kind != SPHK_KIND_SPH2POB_EFFICIENT && kind != SPHK_KIND_NAIVE && kind != SPHK_KIND_UNBIASED)
+        return fail(SPHK_ERR_UNSUPPORTED, "sphk_nms_images: kind must be sph2pob_efficient, naive or unbiased (SphNMS, sph_nms.py:8-16)");
     if (num_images == 0) return SPHK_OK;
     if (!out_idx || !out_count) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_nms_images: null output pointer");
     cudaStream_t s = (cudaStream_t)stream;

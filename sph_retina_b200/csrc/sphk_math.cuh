@@ -33,7 +33,7 @@
 namespace sphk {
 
 // ---- enums shared with the C ABI (include/sphk.h) -------------------------------------
-enum Kind { KIND_SPH2POB_EFFICIENT = 0, KIND_SPH2POB_STANDARD = 1, KIND_SPH = 2, KIND_FOV = 3, KIND_NAIVE = 4 };
+enum Kind { KIND_SPH2POB_EFFICIENT = 0, KIND_SPH2POB_STANDARD = 1, KIND_SPH = 2, KIND_FOV = 3, KIND_NAIVE = 4, KIND_UNBIASED = 5 };
 enum Mode { MODE_IOU = 0, MODE_IOF = 1 };
 enum Edge { EDGE_ARC = 0, EDGE_CHORD = 1, EDGE_TANGENT = 2 };
 
@@ -645,6 +645,106 @@ SPHK_HD float naive_iou_pair(const RawBox& b1, const RawBox& b2, int D, int mode
     if (w1 * h1 < 1e-14f || w2 * h2 < 1e-14f) return 0.0f;
     if (obb_disjoint(o)) return 0.0f;
     return riou_value(o, mode);
+}
+
+// ---- unbiased_iou (sph_iou_api.py:103-125): the exact spherical IoU ------------------------------------------------
+// sphdet/iou/unbiased_iou_bfov.py:10-204 (BFoV) and unbiased_iou_rbfov.py:4-181 (RBFoV), as the reference runs them: each
+// box is the intersection of four hemispheres (inward normals N_left/right/up/down, rotated about the view axis by gamma
+// for RBFoV); the candidate vertices of the intersection polygon are the 4 + 4 box corners and +-(N_i x N'_j) for the 16
+// pairs of boundary circles of the two boxes; a candidate counts if round(V . N, 8) >= 0 for all eight normals; the
+// area is sum over the counted vertices of acos(-E0 . E1) (the interior angle between the two circles meeting there)
+// minus (count - 2) pi -- no ordering of the vertices is needed, and duplicates are NOT merged (the DFS clean-up is
+// switched off in the reference: unbiased_iou_bfov.py:176).  All of it in double: the method subtracts O(1) angles to
+// get areas of 1e-4 sr and its own validity test works at 5e-9.
+struct D3 { double x, y, z; };
+SPHK_HD D3 d3(double x, double y, double z) { D3 r; r.x = x; r.y = y; r.z = z; return r; }
+SPHK_HD D3 d3_cross(const D3& a, const D3& b) { return d3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+SPHK_HD double d3_dot(const D3& a, const D3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+SPHK_HD D3 d3_lin(double a, const D3& u, double b, const D3& v) { return d3(a * u.x + b * v.x, a * u.y + b * v.y, a * u.z + b * v.z); }
+
+// normals in the reference's order: left, right, up, down.  theta, phi, fx, fy, gamma in radians.
+SPHK_HD void unbiased_normals(double theta, double phi, double fx, double fy, double gamma, bool rotated, D3* N) {
+    const double st = sin(theta), ct = cos(theta), sp = sin(phi), cp = cos(phi);
+    const D3 look = d3(sp * ct, sp * st, cp), right = d3(-st, ct, 0.0), up = d3(-cp * ct, -cp * st, sp);
+    const double sx = sin(0.5 * fx), cx = cos(0.5 * fx), sy = sin(0.5 * fy), cy = cos(0.5 * fy);
+    N[0] = d3_lin(-cx, right, sx, look);
+    N[1] = d3_lin(cx, right, sx, look);
+    N[2] = d3_lin(-cy, up, sy, look);
+    N[3] = d3_lin(cy, up, sy, look);
+    if (rotated) {      // roll_T (unbiased_iou_rbfov.py:10-33): Rodrigues rotation about the view axis by gamma
+        const double cg = cos(gamma), sg = sin(gamma), k = 1.0 - cg;
+        const double nx = look.x, ny = look.y, nz = look.z;
+        const double m11 = nx * nx * k + cg, m12 = nx * ny * k - nz * sg, m13 = nx * nz * k + ny * sg;
+        const double m21 = nx * ny * k + nz * sg, m22 = ny * ny * k + cg, m23 = ny * nz * k - nx * sg;
+        const double m31 = nx * nz * k - ny * sg, m32 = ny * nz * k + nx * sg, m33 = nz * nz * k + cg;
+        for (int i = 0; i < 4; ++i) {
+            const D3 v = N[i];
+            N[i] = d3(m11 * v.x + m12 * v.y + m13 * v.z, m21 * v.x + m22 * v.y + m23 * v.z, m31 * v.x + m32 * v.y + m33 * v.z);
+        }
+    }
+}
+
+// one candidate vertex V (unit, or the reference's nearly-unit V / (|V| + 1e-10)) on circles with normals E0, E1
+SPHK_HD void unbiased_vertex(const D3& V, const D3& E0, const D3& E1, const D3* N, double* sum, int* count) {
+    bool ok = true;
+    for (int k = 0; k < 8; ++k) ok = ok && (rint(d3_dot(V, N[k]) * 1e8) >= 0.0);     // np.round(., 8) >= 0
+    if (ok) {
+        double c = -d3_dot(E0, E1);
+        c = c < -1.0 ? -1.0 : (c > 1.0 ? 1.0 : c);
+        *sum += acos(c);
+        *count += 1;
+    }
+}
+
+SPHK_HD double unbiased_area(double fx, double fy) { return 4.0 * acos(-sin(0.5 * fx) * sin(0.5 * fy)) - 2.0 * SPHK_PI_D; }
+
+SPHK_HD float unbiased_iou_pair(const RawBox& b1, const RawBox& b2, int D) {
+    // jiter_spherical_bboxes (sph_iou_api.py:244-260) in double, on the float32 box values: with nearly coincident
+    // boundary circles the 5e-9 validity test decides which vertices count, so the jittered values must be those of the
+    // reference's float64 run to the last bit, not the fp32-rounded ones of JitBox
+    const double eps = SPHK_EPS_D;
+    const double u[5] = {b1.t, b1.p, b1.a, b1.b, b1.g}, v[5] = {b2.t, b2.p, b2.a, b2.b, b2.g};
+    bool m = false;
+    for (int k = 0; k < D; ++k) m = m || (fabs(u[k] - v[k]) < eps);
+    double x[5], y[5];
+    for (int k = 0; k < 5; ++k) { x[k] = (k < D) ? (m ? u[k] - 2.0 * eps : u[k]) : 0.0; y[k] = (k < D) ? (m ? v[k] + eps : v[k]) : 0.0; }
+    x[0] = fmin(fmax(x[0], 2.0 * eps), 360.0 - eps);
+    y[0] = fmin(fmax(y[0], eps), 360.0 - 2.0 * eps);
+    for (int k = 1; k < 4; ++k) { x[k] = fmin(fmax(x[k], 2.0 * eps), 180.0 - eps); y[k] = fmin(fmax(y[k], eps), 180.0 - 2.0 * eps); }
+    if (D == 5) y[4] = fmin(fmax(y[4], -360.0 + 2.0 * eps), 360.0 - 2.0 * eps);       // both clamps of :257-258 hit bboxes2
+    const double d2r = SPHK_PI_D / 180.0;
+    const double fx1 = x[2] * d2r, fy1 = x[3] * d2r, fx2 = y[2] * d2r, fy2 = y[3] * d2r;
+    D3 N[8];
+    unbiased_normals(x[0] * d2r, x[1] * d2r, fx1, fy1, x[4] * d2r, D == 5, N);
+    unbiased_normals(y[0] * d2r, y[1] * d2r, fx2, fy2, y[4] * d2r, D == 5, N + 4);
+    double sum = 0.0;
+    int count = 0;
+    // corners (getNormal: left x up, down x left, up x right, right x down), normalised
+    const int ca[4] = {0, 3, 2, 1}, cb[4] = {2, 0, 1, 3};
+    for (int b = 0; b < 2; ++b) {
+        for (int k = 0; k < 4; ++k) {
+            const D3& E0 = N[4 * b + ca[k]];
+            const D3& E1 = N[4 * b + cb[k]];
+            const D3 c = d3_cross(E0, E1);
+            const double inv = 1.0 / sqrt(d3_dot(c, c));
+            unbiased_vertex(d3(c.x * inv, c.y * inv, c.z * inv), E0, E1, N, &sum, &count);
+        }
+    }
+    // crossings of a boundary circle of box 1 with one of box 2: +-(N_i x N'_j) / (|.| + 1e-10)
+    for (int i = 0; i < 4; ++i) {
+        for (int j = 0; j < 4; ++j) {
+            const D3 c = d3_cross(N[i], N[4 + j]);
+            const double inv = 1.0 / (sqrt(d3_dot(c, c)) + 1e-10);
+            const D3 v = d3(c.x * inv, c.y * inv, c.z * inv);
+            unbiased_vertex(v, N[i], N[4 + j], N, &sum, &count);
+            unbiased_vertex(d3(-v.x, -v.y, -v.z), N[4 + j], N[i], N, &sum, &count);
+        }
+    }
+    const double inter = (count == 0) ? 0.0 : sum - (double)(count - 2) * SPHK_PI_D;
+    const double a1 = unbiased_area(fx1, fy1), a2 = unbiased_area(fx2, fy2);
+    // the two files end differently (unbiased_iou_bfov.py:199 / unbiased_iou_rbfov.py:175)
+    const double iou = (D == 4) ? (inter + 1e-8) / (a1 + a2 - (inter + 1e-8)) : inter / (a1 + a2 - inter + 1e-8);
+    return clampf((float)iou, 0.0f, 1.0f);        // .float() then clamp(0, 1) (sph_iou_api.py:125)
 }
 
 }  // namespace sphk

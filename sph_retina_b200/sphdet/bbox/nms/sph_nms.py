@@ -117,15 +117,13 @@ def sph_nms_image_blocks(boxes, scores, labels, num_images, num_classes, iou_thr
 
 
 class SphNMS:
-    """sph_nms.py:7-19.  'sph2pob_efficient' (the default) and 'naive_iou' (what the reference's indoor360 configs set:
-    planar IoU of the sph2pix boxes) run in the same NMS kernel; 'unbiased_iou' is the reference's CPU numpy routine,
-    outside this path: refused loudly."""
+    """sph_nms.py:7-19.  All three calculators of the reference run in the same NMS kernel: 'sph2pob_efficient' (the
+    default), 'naive_iou' (the indoor360 configs: planar IoU of the sph2pix boxes) and 'unbiased_iou' (the pandora configs:
+    the exact spherical IoU, CPU numpy in the reference, a double-precision device function here)."""
 
     def __init__(self, iou_calculator='sph2pob_efficient'):
-        if iou_calculator in ('sph2pob_efficient', 'naive_iou'):
+        if iou_calculator in ('sph2pob_efficient', 'naive_iou', 'unbiased_iou'):
             self.iou_calculator = iou_calculator
-        elif iou_calculator == 'unbiased_iou':
-            raise NotImplementedError("SphNMS(%r): no CUDA kernel on this path (and no fallback)" % iou_calculator)
         else:
             raise NotImplementedError('Not supported iou_calculator.')
 

@@ -8,7 +8,7 @@ import torch
 from ... import _native
 
 _KINDS = {'sph2pob_standard_iou': 'sph2pob_standard', 'sph2pob_efficient_iou': 'sph2pob_efficient',
-          'fov_iou': 'fov', 'sph_iou': 'sph', 'naive_iou': 'naive'}
+          'fov_iou': 'fov', 'sph_iou': 'sph', 'naive_iou': 'naive', 'unbiased_iou': 'unbiased'}
 
 
 def sph_max_overlaps(bboxes1, bboxes2, backend='sph2pob_efficient_iou', mode='iou', box_version=None,

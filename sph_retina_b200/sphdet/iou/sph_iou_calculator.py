@@ -5,7 +5,7 @@ from __future__ import annotations
 import torch
 
 from ..registry import IOU_CALCULATORS
-from .sph_iou_api import fov_iou, naive_iou, sph2pob_efficient_iou, sph2pob_standard_iou, sph_iou
+from .sph_iou_api import fov_iou, naive_iou, sph2pob_efficient_iou, sph2pob_standard_iou, sph_iou, unbiased_iou
 
 # backends of the reference that have a CUDA kernel here; the others are out of this path's scope
 _BACKENDS = {
@@ -14,6 +14,7 @@ _BACKENDS = {
     'fov_iou': fov_iou,
     'sph_iou': sph_iou,
     'naive_iou': naive_iou,
+    'unbiased_iou': unbiased_iou,
 }
 _REFERENCE_BACKENDS = ['unbiased_iou', 'sph2pob_standard_iou', 'sph2pob_legacy_iou', 'sph2pob_efficient_iou',
                        'naive_iou', 'fov_iou', 'sph_iou', 'kent_iou']
@@ -23,9 +24,9 @@ _REFERENCE_BACKENDS = ['unbiased_iou', 'sph2pob_standard_iou', 'sph2pob_legacy_i
 class SphOverlaps2D(object):
     """2D Overlaps Calculator for spherical boxes (sph_iou_calculator.py:8-51).
 
-    Signature and defaults are the reference's.  Its default backend 'unbiased_iou' is a CPU numpy
-    routine outside this path: calling with it raises NotImplementedError; the spherical configs
-    pass backend='sph2pob_efficient_iou' (configs/_base_/models/sph_rotated_retinanet_r50_fpn.py:18-19)."""
+    Signature and defaults are the reference's, default backend 'unbiased_iou' included (a CPU numpy routine there, a
+    double-precision kernel here); the spherical configs pass backend='sph2pob_efficient_iou'
+    (configs/_base_/models/sph_rotated_retinanet_r50_fpn.py:18-19).  'sph2pob_legacy_iou' and 'kent_iou' have no kernel."""
 
     def __init__(self, backend='unbiased_iou', box_version=4):
         self.backend = backend

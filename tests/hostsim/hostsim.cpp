@@ -26,6 +26,7 @@ void hostsim_iou_aligned(int kind, const float* b1, const float* b2, long P, int
         const RawBox x = load_box(b1, i, D), y = load_box(b2, i, D);
         out[i] = (kind == KIND_SPH || kind == KIND_FOV) ? approx_iou_pair(x, y, kind)
                  : (kind == KIND_NAIVE)                 ? naive_iou_pair(x, y, D, mode)
+                 : (kind == KIND_UNBIASED)              ? unbiased_iou_pair(x, y, D)
                                                         : sph2pob_iou_pair(x, y, D, kind, mode, edge);
     }
 }

@@ -592,6 +592,41 @@ def test_naive_nms_golden_keep_sets(api, box):
         assert keep_sph.cpu().tolist() != g[box + "_keep_thr5"].tolist()
 
 
+# ---- unbiased_iou (the exact spherical IoU; SphOverlaps2D's default backend) and SphNMS('unbiased_iou') ---------------
+@pytest.mark.parametrize("box", ["bfov", "rbfov"])
+def test_unbiased_iou_golden(api, box):
+    g = load_golden("unbiased")
+    b1, b2 = cu(g[box + "_b1"]), cu(g[box + "_b2"])
+    got = api.iou.unbiased_iou(b1, b2, is_aligned=True)
+    err = np.abs(got.cpu().numpy() - g[box + "_aligned_f64"])
+    # 1e-5 everywhere except, at most, a degenerate pair whose vertex test (5e-9) falls the other way with CUDA's libm
+    assert got.shape == (b1.size(0),) and (err > 1e-5).sum() <= 2, (np.where(err > 1e-5)[0], err.max())
+    mat = api.iou.SphOverlaps2D(box_version=b1.size(1))(b1[:23], b2[:201])            # the reference's default backend
+    assert mat.shape == (23, 201) and (np.abs(mat.cpu().numpy() - g[box + "_rc_f64"]) > 1e-5).sum() <= 2
+    flat = api.iou.unbiased_iou(b1[:23].repeat_interleave(201, 0), b2[:201].repeat(23, 1), is_aligned=True)
+    assert torch.equal(mat.reshape(-1), flat)
+    # against the oracle on fresh seeded boxes
+    x = O.generate_boxes(4000, alpha_range=(2, 150), beta_range=(2, 150), box=box, seed=5)
+    y = (x + torch.randn_like(x) * 10).clamp(min=1)
+    y[:, 0].clamp_(0, 360); y[:, 1].clamp_(0, 180); y[:, 2:4].clamp_(max=179)
+    err = (api.iou.unbiased_iou(x.to(DEV), y.to(DEV), is_aligned=True).cpu() - O.unbiased_iou(x, y, is_aligned=True)).abs()
+    assert int((err > 1e-5).sum()) <= 4, err.max()
+
+
+@pytest.mark.parametrize("box", ["bfov", "rbfov"])
+def test_unbiased_nms_golden_keep_sets(api, box):
+    """SphNMS('unbiased_iou') (the reference's pandora configs) against the keep lists of the reference's float64 run."""
+    g = load_golden("unbiased")
+    boxes, scores, idxs = cu(g[box + "_boxes"]), cu(g[box + "_scores"]), cu(g[box + "_idxs"])
+    iou = g[box + "_pair_iou_f64"]
+    same = g[box + "_idxs"][:, None] == g[box + "_idxs"][None, :]
+    for thr in (0.3, 0.5):
+        assert not (np.abs(iou[same] - thr) < 1e-5).any(), "fixture has a pair on the threshold"
+        want = g["%s_keep_thr%d" % (box, int(thr * 10))].tolist()
+        _, keep = api.nms.SphNMS('unbiased_iou')(boxes, scores, idxs, dict(type="nms", iou_threshold=thr, max_num=120))
+        assert keep.cpu().tolist() == want
+
+
 # ---- the other losses on the Sph2Pob OBBs (SURVEY.md 8f row 3) ---------------------------------------------------
 def _other_loss(api, cls, kw, **extra):
     return getattr(api.losses, cls)(**kw, **extra)

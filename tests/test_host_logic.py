@@ -60,7 +60,9 @@ def test_empty_inputs_and_errors_follow_the_reference():
     with pytest.raises(AssertionError):
         sph2pob_efficient_iou(b, b, rbb_edge='diagonal')                   # sph_iou_api.py:51
     with pytest.raises(NotImplementedError):
-        sph_overlaps(b, b, backend='unbiased_iou')                         # outside the path: refused, not faked
+        sph_overlaps(b, b, backend='kent_iou')                             # outside the path: refused, not faked
+    with pytest.raises(NotImplementedError):
+        sph_overlaps(b, b, backend='sph2pob_legacy_iou')
 
 
 def test_no_cpu_fallback():
@@ -171,9 +173,9 @@ def test_naive_iou_and_nms_calculators_host_contract():
         naive_iou(b, b, box_formator='sph2tan')
     assert naive_iou(b[:0], b).shape == (0, 3) and SphOverlaps2D('naive_iou')(b, b[:0]).shape == (3, 0)
     assert SphNMS('naive_iou').iou_calculator == 'naive_iou' and SphNMS().iou_calculator == 'sph2pob_efficient'
-    for bad in ('unbiased_iou', 'planar'):
-        with pytest.raises(NotImplementedError):
-            SphNMS(bad)
+    assert SphNMS('unbiased_iou').iou_calculator == 'unbiased_iou'
+    with pytest.raises(NotImplementedError):
+        SphNMS('planar')
 
 
 def test_other_sph2pob_losses_host_contract():

@@ -374,3 +374,16 @@ def test_naive_iou_golden(hostsim, box):
     ok, err = within(got, g[box + "_aligned_f64"], g[box + "_aligned_f32"])
     assert ok.all(), (np.where(~ok)[0][:10], err[~ok][:10])
     assert np.nanmax(err) < 5e-6
+
+
+@pytest.mark.parametrize("box", ["bfov", "rbfov"])
+def test_unbiased_iou_golden(hostsim, box):
+    """unbiased_iou_pair (the exact spherical IoU, double precision) against the reference's numpy classes run on float64
+    copies of the boxes: identical, nested, unrelated and overlapping pairs.  The reference's own float32 run is off by up
+    to 1.0 on 2-3 % of these pairs (its validity test works at 5e-9)."""
+    g = load_golden("unbiased")
+    got = hs_aligned(hostsim, 5, g[box + "_b1"], g[box + "_b2"])
+    err = np.abs(got - g[box + "_aligned_f64"])
+    err32 = np.abs(g[box + "_aligned_f32"] - g[box + "_aligned_f64"])
+    assert err.max() < 1e-6, (np.where(err >= 1e-6)[0][:10], err.max())
+    assert (err32 > 1e-5).sum() > 10

@@ -231,3 +231,19 @@ def test_restatement_naive_iou_and_its_nms(box):
     for thr in (0.3, 0.5):
         _, keep = O.nms_batched(boxes, scores, idxs, thr, max_num=150, iou_fn=lambda a, b: O.naive_iou(a, b))
         assert keep.tolist() == g["%s_keep_thr%d" % (box, int(thr * 10))].tolist()
+
+
+@pytest.mark.parametrize("box", ["bfov", "rbfov"])
+def test_restatement_unbiased_iou_and_its_nms(box):
+    """unbiased_iou (sph_iou_api.py:103-125) against the reference's numpy classes fed with float64 copies of the boxes."""
+    g = load_golden("unbiased")
+    b1, b2 = torch.from_numpy(g[box + "_b1"]), torch.from_numpy(g[box + "_b2"])
+    got = O.unbiased_iou(b1, b2, is_aligned=True).numpy()
+    err = np.abs(got - g[box + "_aligned_f64"])
+    assert (err > 1e-6).sum() <= 1, np.where(err > 1e-6)[0]          # (a degenerate pair may land on the other side of the 5e-9 test)
+    err = np.abs(O.unbiased_iou(b1[:23], b2[:201]).numpy() - g[box + "_rc_f64"])
+    assert (err > 1e-6).sum() <= 1
+    boxes, scores, idxs = (torch.from_numpy(g["%s_%s" % (box, k)]) for k in ("boxes", "scores", "idxs"))
+    for thr in (0.3, 0.5):
+        _, keep = O.nms_batched(boxes, scores, idxs, thr, max_num=120, iou_fn=lambda a, b: O.unbiased_iou(a, b))
+        assert keep.tolist() == g["%s_keep_thr%d" % (box, int(thr * 10))].tolist()
