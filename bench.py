@@ -316,6 +316,16 @@ def other_configs(torch, native, dev, flush, hbm_peak_gbs=6544.3):
             for name, fn in (("sph_iou", sph_iou), ("fov_iou", fov_iou)):
                 ms = quick(torch, lambda: fn(b1, b2, is_aligned=True), flush=flush)
                 out["aligned_1M_%s" % name] = {"ms": ms, "pairs_per_s": n / ms * 1e3, "hbm_gbs": n * 36 / ms / 1e6}
+    # the other two calculators of the reference on configs[0]'s boxes: naive_iou (planar IoU of the sph2pix boxes) and
+    # unbiased_iou (exact spherical IoU, double precision per pair; CPU numpy in the reference, ~40 s per million pairs)
+    from sph_retina_b200.sphdet.iou import naive_iou, unbiased_iou
+    for box in ("bfov", "rbfov"):
+        u1 = S.generate_boxes(n, alpha_range=(1, 100), beta_range=(1, 100), box=box, seed=0).to(dev)
+        u2 = S.generate_boxes(n, alpha_range=(1, 100), beta_range=(1, 100), box=box, seed=1).to(dev)
+        for name, fn in (("naive_iou", naive_iou), ("unbiased_iou", unbiased_iou)):
+            ms = quick(torch, lambda: fn(u1, u2, is_aligned=True), iters=5, flush=flush)
+            out["aligned_1M_%s_%s" % (name, box)] = {"ms": ms, "pairs_per_s": n / ms * 1e3}
+    del u1, u2
     native.set_dense(True)
     ms = quick(torch, lambda: sph2pob_efficient_iou(b1, b2, is_aligned=True), flush=flush)
     native.set_dense(False)
@@ -375,6 +385,9 @@ def other_configs(torch, native, dev, flush, hbm_peak_gbs=6544.3):
     out["nms_64img_1000box_80cls"].update({"ms_device_pipeline": ms_d, "images_per_s_device_pipeline": 64 / ms_d * 1e3,
                                            "device_pipeline": "sphk_nms_images: per-image sort, per-segment NMS and per-image "
                                                               "ordering in three launches, top-100 per image, no host sync"})
+    for calc_name in ("naive_iou", "unbiased_iou"):        # the calculators the reference's indoor360 / pandora configs give SphNMS
+        ms_k = quick(torch, lambda: sph_nms_image_blocks(boxes, scores, labels, 64, 80, 0.5, 100, iou_calculator=calc_name), iters=5, flush=flush)
+        out["nms_64img_1000box_80cls"]["ms_device_pipeline_" + calc_name] = ms_k
     ms = quick(torch, lambda: sph_batched_nms_images(boxes, scores, torch.zeros_like(labels), image_ids, 0.5), iters=5, flush=flush)
     zl = torch.zeros_like(labels)
     ms_d = quick(torch, lambda: sph_nms_image_blocks(boxes, scores, zl, 64, 1, 0.5, 100), iters=5, flush=flush)
