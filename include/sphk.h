@@ -42,9 +42,11 @@ enum sphk_kind {
     SPHK_KIND_FOV = 3,               /* 'fov_iou'                sphdet/iou/sph_iou_api.py:156-177 */
     SPHK_KIND_NAIVE = 4,             /* 'naive_iou'              sphdet/iou/sph_iou_api.py:181-198 (planar IoU of the
                                         sph2pix boxes; BFoV or RBFoV, mode 'iou' only)                            */
-    SPHK_KIND_UNBIASED = 5           /* 'unbiased_iou'           sphdet/iou/sph_iou_api.py:103-125 (exact spherical IoU,
+    SPHK_KIND_UNBIASED = 5,          /* 'unbiased_iou'           sphdet/iou/sph_iou_api.py:103-125 (exact spherical IoU,
                                         unbiased_iou_bfov.py / unbiased_iou_rbfov.py; the default backend of
                                         SphOverlaps2D; evaluated in double; mode 'iou' only)                      */
+    SPHK_KIND_SPH2POB_LEGACY = 6     /* 'sph2pob_legacy_iou'     sphdet/iou/sph_iou_api.py:91-92 (sph2pob_legacy.py:8-31,
+                                        the hand-crafted first transform; BFoV only; rbb_angle ignored)           */
 };
 enum sphk_mode { SPHK_MODE_IOU = 0, SPHK_MODE_IOF = 1 };                     /* sph_iou_api.py:49     */
 enum sphk_edge { SPHK_EDGE_ARC = 0, SPHK_EDGE_CHORD = 1, SPHK_EDGE_TANGENT = 2 }; /* sph2pob_efficient.py:100-108 */

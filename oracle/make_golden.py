@@ -345,6 +345,30 @@ def golden_unbiased(R):
     print("unbiased", {k: (v.shape, float(np.nanmean(v))) for k, v in out.items() if "aligned_f" in k or "keep" in k})
 
 
+def golden_legacy(R):
+    """sph2pob_legacy_iou (sph_iou_api.py:91-92; BFoV only): the pair set of golden_aligned, every mode / edge option, an
+    R x C call, and the 7 hand-picked pairs of tests/test_all_ious.py:243-261."""
+    b1, b2 = make_pairs(R, 4096, "bfov", seed=13)
+    fn = R.sph2pob_legacy_iou
+    out = dict(b1=_np(b1), b2=_np(b2))
+    for mode in ("iou", "iof"):
+        out["%s_f32" % mode] = _np(fn(b1, b2, mode=mode, is_aligned=True))
+        out["%s_f64" % mode] = _np(_ref64(fn, b1, b2, mode=mode, is_aligned=True))
+    for edge in ("chord", "tangent"):
+        out["%s_f32" % edge] = _np(fn(b1, b2, is_aligned=True, rbb_edge=edge))
+        out["%s_f64" % edge] = _np(_ref64(fn, b1, b2, is_aligned=True, rbb_edge=edge))
+    out["rc_f32"] = _np(fn(b1[:29], b2[:333]))
+    out["rc_f64"] = _np(_ref64(fn, b1[:29], b2[:333]))
+    g1 = torch.tensor([[40, 50, 35, 55], [30, 60, 60, 60], [50, -78, 25, 46], [30, 75, 30, 60],
+                       [40, 70, 25, 30], [30, 75, 30, 30], [30, 60, 60, 60]]).float()
+    g2 = torch.tensor([[35, 20, 37, 50], [55, 40, 60, 60], [30, -75, 26, 45], [60, 40, 60, 60],
+                       [60, 85, 30, 30], [60, 55, 40, 50], [60, 60, 60, 60]]).float()
+    k1, k2 = R.box_formator.geo2sph(g1), R.box_formator.geo2sph(g2)
+    out.update(kat_b1=_np(k1), kat_b2=_np(k2), kat_iou=_np(fn(k1, k2, is_aligned=True)))
+    np.savez_compressed(os.path.join(OUT, "legacy.npz"), **out)
+    print("legacy", out["kat_iou"], float(np.nanmean(out["iou_f64"])), int(np.isnan(out["iou_f64"]).sum()), int(np.isnan(out["iou_f32"]).sum()))
+
+
 def golden_nms(R):
     out = {}
     for box in ("bfov", "rbfov"):
@@ -433,3 +457,4 @@ if __name__ == "__main__":
     golden_other_losses(R)
     golden_naive(R)
     golden_unbiased(R)
+    golden_legacy(R)

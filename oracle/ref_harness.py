@@ -238,6 +238,7 @@ def load_reference():
         generate_boxes=gen.generate_boxes,
         sph2pob_efficient_iou=api.sph2pob_efficient_iou,
         sph2pob_standard_iou=api.sph2pob_standard_iou,
+        sph2pob_legacy_iou=api.sph2pob_legacy_iou,
         sph_iou=api.sph_iou, fov_iou=api.fov_iou, naive_iou=api.naive_iou, unbiased_iou=api.unbiased_iou,
         SphOverlaps2D=calc.SphOverlaps2D, SphNMS=sph_nms.SphNMS,
         Sph2PobIoULoss=iou_loss.Sph2PobIoULoss,

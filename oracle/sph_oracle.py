@@ -145,6 +145,49 @@ def sph2pob_efficient(b1, b2, rbb_edge="arc", rbb_angle="equator"):
 
 
 # --------------------------------------------------------------------------- #
+# Sph2Pob-legacy (sph2pob_legacy.py:8-31), BFoV only, output angles in radians
+# --------------------------------------------------------------------------- #
+def sph2pob_legacy(b1, b2, rbb_edge="arc", rbb_angle=None):
+    """The hand-crafted first version of the transform ('the calculated internal angle is not accurate',
+    sph2pob_legacy.py:10-11): both centres moved to the equator keeping their great-circle distance and their latitude
+    difference (:38-82), the box angle measured between the meridian tangent at the box and the one at the pair's
+    mid-longitude (:99-129).  ``torch.chunk(box, 4)`` (:52-53) makes it BFoV-only."""
+    assert rbb_edge in ("arc", "chord", "tangent")
+    assert b1.size(1) == 4 and b2.size(1) == 4, "sph2pob_legacy takes BFoV boxes (torch.chunk(., 4) at sph2pob_legacy.py:52)"
+    pi = math.pi
+    far = (b1[:, 0] - b2[:, 0]).abs() > 180                                    # standardize_spherical_box :224-244
+    tg = torch.where(far, torch.remainder(b1[:, 0] + 180, 360), b1[:, 0])
+    tp = torch.where(far, torch.remainder(b2[:, 0] + 180, 360), b2[:, 0])
+    r1 = torch.deg2rad(torch.stack([tg, b1[:, 1], b1[:, 2], b1[:, 3]], dim=1))
+    r2 = torch.deg2rad(torch.stack([tp, b2[:, 1], b2[:, 2], b2[:, 3]], dim=1))
+    # transform_position :38-82 ('convention' radians :203-221: theta - pi, pi/2 - phi)
+    theta_g, phi_g, theta_p, phi_p = r1[:, 0] - pi, pi / 2 - r1[:, 1], r2[:, 0] - pi, pi / 2 - r2[:, 1]
+    phi_i = (phi_g + phi_p) / 2
+    phi_g_, phi_p_ = phi_g - phi_i, phi_p - phi_i
+    d_phi, d_theta = (phi_g - phi_p).abs(), (theta_g - theta_p).abs()
+    L = 2 * torch.arcsin(torch.sqrt(torch.sin(d_phi / 2) ** 2 + torch.cos(phi_g) * torch.cos(phi_p) * torch.sin(d_theta / 2) ** 2))
+    d_theta_ = (2 * torch.arcsin(torch.sqrt((torch.sin(L / 2) ** 2 - torch.sin(d_phi / 2) ** 2)
+                                            / (torch.cos(phi_g_) * torch.cos(phi_p_))))).abs()
+    one = torch.ones((), dtype=b1.dtype)
+    theta_p_ = d_theta_ * torch.where(theta_p > theta_g, one, -one)
+
+    # transfrom_anlge :99-129 ('math' radians = plain deg2rad)
+    def internal(theta, phi, theta_ref):
+        d_box = torch.stack([torch.cos(phi) * torch.cos(theta), torch.cos(phi) * torch.sin(theta), -torch.sin(phi)], dim=1)
+        d_ref = torch.stack([torch.cos(phi) * torch.cos(theta_ref), torch.cos(phi) * torch.sin(theta_ref), -torch.sin(phi)], dim=1)
+        ang = torch.acos((_unit(d_box) * _unit(d_ref)).sum(dim=1).clamp(COS_LO, COS_HI)) / pi * 180          # degrees, :197-200
+        ang = ang.abs()
+        keep = ((theta >= theta_ref) & (phi < pi / 2)) | ((theta <= theta_ref) & (phi > pi / 2))
+        return torch.deg2rad(torch.where(keep, ang, -ang))                                                    # :275-277
+    theta_mid = (r1[:, 0] + r2[:, 0]) / 2
+    ag, ap = internal(r1[:, 0], r1[:, 1], theta_mid), internal(r2[:, 0], r2[:, 1], theta_mid)
+    zero = torch.zeros_like(ag)
+    o1 = torch.stack([zero, phi_g_, _edge(r1[:, 2], rbb_edge), _edge(r1[:, 3], rbb_edge), ag], dim=1)
+    o2 = torch.stack([theta_p_, phi_p_, _edge(r2[:, 2], rbb_edge), _edge(r2[:, 3], rbb_edge), ap], dim=1)
+    return o1, o2
+
+
+# --------------------------------------------------------------------------- #
 # Sph2Pob-standard (sph2pob_standard.py:8-80), output angles in radians
 # --------------------------------------------------------------------------- #
 def _frame_from_angles(theta, phi):
@@ -313,7 +356,7 @@ def sph2pob_iou(b1, b2, transform="efficient", mode="iou", is_aligned=False,
     R, C = b1.size(0), b2.size(0)
     if R * C == 0:
         return b1.new_zeros((R, 1)) if is_aligned else b1.new_zeros((R, C))
-    fn = sph2pob_efficient if transform == "efficient" else sph2pob_standard
+    fn = {"efficient": sph2pob_efficient, "standard": sph2pob_standard, "legacy": sph2pob_legacy}[transform]
     e1, e2 = _expand(b1, b2, is_aligned)
     outs = []
     for s in range(0, e1.size(0), chunk):

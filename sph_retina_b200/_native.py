@@ -13,7 +13,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "libsphk.so")
 _PROBE_LIB = os.environ.get("SPHK_PROBE_LIB")      # tools/ only: an instrumented build of the same sources
 
-KIND = {"sph2pob_efficient": 0, "sph2pob_standard": 1, "sph": 2, "fov": 3, "naive": 4, "unbiased": 5}
+KIND = {"sph2pob_efficient": 0, "sph2pob_standard": 1, "sph": 2, "fov": 3, "naive": 4, "unbiased": 5,
+        "sph2pob_legacy": 6}
 MODE = {"iou": 0, "iof": 1}
 EDGE = {"arc": 0, "chord": 1, "tangent": 2}
 ANGLE = {"equator": 0, "project": 1}

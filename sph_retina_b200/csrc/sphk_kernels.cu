@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(kThreads) k_iou_aligned(const float* __restric
     if (KIND == KIND_SPH || KIND == KIND_FOV) v = approx_iou_pair(x, y, KIND);
     else if (KIND == KIND_NAIVE) v = naive_iou_pair(x, y, D, mode);
     else if (KIND == KIND_UNBIASED) v = unbiased_iou_pair(x, y, D);
+    else if (KIND == KIND_SPH2POB_LEGACY) v = sph2pob_legacy_iou_pair(x, y, mode, edge);
     else v = sph2pob_iou_pair(x, y, D, KIND, mode, edge, dense);
     out[i] = v;
 }
@@ -366,6 +367,7 @@ k_iou_pairwise(const float* __restrict__ rows, int64_t R, const float* __restric
             if (KIND == KIND_SPH || KIND == KIND_FOV) v = approx_iou_pair(x, y, KIND);
             else if (KIND == KIND_NAIVE) v = naive_iou_pair(x, y, D, mode);
             else if (KIND == KIND_UNBIASED) v = unbiased_iou_pair(x, y, D);
+            else if (KIND == KIND_SPH2POB_LEGACY) v = sph2pob_legacy_iou_pair(x, y, mode, edge);
             else v = sph2pob_iou_pair(x, y, D, KIND, mode, edge, dense);
             if (out) out[(r0 + r) * ld + col] = v;
             if (v > best_v) { best_v = v; best_r = (uint32_t)r; }
@@ -1599,7 +1601,9 @@ int sphk_device_info(int* sm_count, int* cc_major, int* cc_minor) {
 int sphk_iou_aligned(int kind, const float* b1, const float* b2, int64_t P, int D, int mode, int edge, int angle,
                      float* out, void* stream) {
     if (P < 0 || (D != 4 && D != 5)) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_aligned: P < 0 or D not in {4,5}");
-    if (kind < 0 || kind > SPHK_KIND_UNBIASED) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_aligned: unknown kind");
+    if (kind < 0 || kind > SPHK_KIND_SPH2POB_LEGACY) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_aligned: unknown kind");
+    if (kind == SPHK_KIND_SPH2POB_LEGACY && D != 4)
+        return fail(SPHK_ERR_UNSUPPORTED, "sph2pob_legacy_iou takes BFoV boxes (D = 4) only (torch.chunk(., 4), sph2pob_legacy.py:52)");
     if ((kind == SPHK_KIND_NAIVE || kind == SPHK_KIND_UNBIASED) && mode != SPHK_MODE_IOU)
         return fail(SPHK_ERR_UNSUPPORTED, "naive_iou / unbiased_iou support mode 'iou' only (sph_iou_api.py:104,182)");
     if (mode != SPHK_MODE_IOU && mode != SPHK_MODE_IOF) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_aligned: unknown mode");
@@ -1620,6 +1624,8 @@ int sphk_iou_aligned(int kind, const float* b1, const float* b2, int64_t P, int 
     } else if (kind == SPHK_KIND_UNBIASED) {
         if (D == 4) k_iou_aligned<KIND_UNBIASED, 4><<<blocks_for(P), kThreads, 0, s>>>(b1, b2, P, mode, edge, out, v, false);
         else k_iou_aligned<KIND_UNBIASED, 5><<<blocks_for(P), kThreads, 0, s>>>(b1, b2, P, mode, edge, out, false, false);
+    } else if (kind == SPHK_KIND_SPH2POB_LEGACY) {
+        k_iou_aligned<KIND_SPH2POB_LEGACY, 4><<<blocks_for(P), kThreads, 0, s>>>(b1, b2, P, mode, edge, out, v, false);
     } else if (kind == SPHK_KIND_SPH || kind == SPHK_KIND_FOV) {
         const unsigned g = blocks_for(P);
         if (v && !g_no_approx4 && P >= (int64_t)3 << 20) {      // below ~3 M pairs one pair per thread keeps more loads in flight
@@ -1719,14 +1725,17 @@ static int pairwise_impl(int kind, const float* rows, int64_t R, const float* co
                          const float* row_target, int* col_tie, unsigned long long* ext_rkey = nullptr,
                          unsigned long long* ext_ckey = nullptr) {
     if (R < 0 || C < 0 || (D != 4 && D != 5)) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: bad R, C or D");
-    if (kind < 0 || kind > SPHK_KIND_UNBIASED) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: unknown kind");
+    if (kind < 0 || kind > SPHK_KIND_SPH2POB_LEGACY) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: unknown kind");
+    if (kind == SPHK_KIND_SPH2POB_LEGACY && D != 4)
+        return fail(SPHK_ERR_UNSUPPORTED, "sph2pob_legacy_iou takes BFoV boxes (D = 4) only (torch.chunk(., 4), sph2pob_legacy.py:52)");
     if ((kind == SPHK_KIND_NAIVE || kind == SPHK_KIND_UNBIASED) && mode != SPHK_MODE_IOU)
         return fail(SPHK_ERR_UNSUPPORTED, "naive_iou / unbiased_iou support mode 'iou' only (sph_iou_api.py:104,182)");
     if (mode != SPHK_MODE_IOU && mode != SPHK_MODE_IOF) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: unknown mode");
     if (edge < 0 || edge > 2) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: unknown edge");
     if (angle != SPHK_ANGLE_EQUATOR && angle != SPHK_ANGLE_PROJECT) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: unknown angle");
     // "approx": the kinds evaluated one pair per thread by the generic tile kernel (no per-box records, no prefilter)
-    const bool approx = (kind == SPHK_KIND_SPH || kind == SPHK_KIND_FOV || kind == SPHK_KIND_NAIVE || kind == SPHK_KIND_UNBIASED);
+    const bool approx = (kind == SPHK_KIND_SPH || kind == SPHK_KIND_FOV || kind == SPHK_KIND_NAIVE || kind == SPHK_KIND_UNBIASED ||
+                         kind == SPHK_KIND_SPH2POB_LEGACY);
     if ((kind == SPHK_KIND_SPH || kind == SPHK_KIND_FOV) && (D != 4 || mode != SPHK_MODE_IOU))
         return fail(SPHK_ERR_UNSUPPORTED, "sph_iou / fov_iou take BFoV boxes (D = 4) and mode 'iou' only");
     if (out && ld < C) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: ld < C");
@@ -1760,7 +1769,10 @@ static int pairwise_impl(int kind, const float* rows, int64_t R, const float* co
             const int64_t row_tiles = (R + kTileRows - 1) / kTileRows;
             if (col_tiles * row_tiles > 0x7FFFFFFFll) return fail(SPHK_ERR_UNSUPPORTED, "sphk_iou_pairwise: grid too large; shard the call");
             const unsigned g = (unsigned)(col_tiles * row_tiles);
-            if (kind == SPHK_KIND_UNBIASED && D == 4)
+            if (kind == SPHK_KIND_SPH2POB_LEGACY)
+                k_iou_pairwise<KIND_SPH2POB_LEGACY, 4><<<g, kThreads, 0, s>>>(rows, R, cols, C, mode, edge, out, ld, rkey, ckey, (uint32_t)row_base,
+                                                                               (uint32_t)col_base, col_tiles, v, false);
+            else if (kind == SPHK_KIND_UNBIASED && D == 4)
                 k_iou_pairwise<KIND_UNBIASED, 4><<<g, kThreads, 0, s>>>(rows, R, cols, C, mode, edge, out, ld, rkey, ckey, (uint32_t)row_base,
                                                                          (uint32_t)col_base, col_tiles, v, false);
             else if (kind == SPHK_KIND_UNBIASED)

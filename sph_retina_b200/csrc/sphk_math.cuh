@@ -33,7 +33,8 @@
 namespace sphk {
 
 // ---- enums shared with the C ABI (include/sphk.h) -------------------------------------
-enum Kind { KIND_SPH2POB_EFFICIENT = 0, KIND_SPH2POB_STANDARD = 1, KIND_SPH = 2, KIND_FOV = 3, KIND_NAIVE = 4, KIND_UNBIASED = 5 };
+enum Kind { KIND_SPH2POB_EFFICIENT = 0, KIND_SPH2POB_STANDARD = 1, KIND_SPH = 2, KIND_FOV = 3, KIND_NAIVE = 4, KIND_UNBIASED = 5,
+            KIND_SPH2POB_LEGACY = 6 };
 enum Mode { MODE_IOU = 0, MODE_IOF = 1 };
 enum Edge { EDGE_ARC = 0, EDGE_CHORD = 1, EDGE_TANGENT = 2 };
 
@@ -588,6 +589,55 @@ SPHK_HD float sph2pob_iou_pair_project(const RawBox& b1, const RawBox& b2, int D
     return riou_value(o, mode);
 }
 
+// ---- Sph2Pob-legacy (sph2pob_legacy.py:8-31 behind sph2pob_legacy_iou, sph_iou_api.py:91-92) ------------------------
+// The reference's first, hand-crafted transform (BFoV only: torch.chunk(box, 4) at :52-53).  Position (:38-82): both
+// centres go to the equator keeping their latitudes relative to the mid-latitude and their great-circle distance L
+// (haversine), which fixes the longitude difference there.  Angle (:99-129): between the meridian tangent at the box
+// centre and the one at (mid-longitude of the pair, same latitude), clamped acos, sign from a quadrant rule.  Like the
+// 'project' variant it is a rarely used option: explicit formulas in double precision, then the common jitter_2 + clipper.
+SPHK_HD double legacy_internal_angle(double th, double ph, double th_mid) {
+    const double cp = cos(ph), sp = sin(ph);
+    double c = cp * cp * cos(th - th_mid) + sp * sp;              // d(th, ph) . d(th_mid, ph), both unit
+    c = c < -1.0 + 1e-7 ? -1.0 + 1e-7 : (c > 1.0 - 1e-7 ? 1.0 - 1e-7 : c);
+    const double ang = fabs(acos(c));
+    const double half_pi = 0.5 * SPHK_PI_D;
+    const bool keep = ((th >= th_mid) && (ph < half_pi)) || ((th <= th_mid) && (ph > half_pi));      // :127-128
+    return keep ? ang : -ang;
+}
+
+SPHK_HD ObbPair sph2pob_legacy(const JitBox& g, const JitBox& p, int edge) {
+    const double k = SPHK_PI_D / 180.0;
+    double tg = (double)g.t_hi + (double)g.t_lo, tp = (double)p.t_hi + (double)p.t_lo;          // degrees
+    if (fabs(tg - tp) > 180.0) { tg = fmod(tg + 180.0, 360.0); tp = fmod(tp + 180.0, 360.0); }    // :224-244
+    const double th_g = tg * k, th_p = tp * k;
+    const double ph_g = ((double)g.p_hi + (double)g.p_lo) * k, ph_p = ((double)p.p_hi + (double)p.p_lo) * k;
+    // 'convention' radians (:203-221): longitude theta - pi (only differences are used), latitude pi/2 - phi
+    const double lat_g = 0.5 * SPHK_PI_D - ph_g, lat_p = 0.5 * SPHK_PI_D - ph_p, lat_i = 0.5 * (lat_g + lat_p);
+    const double yg = lat_g - lat_i, yp = lat_p - lat_i;
+    const double sh = sin(0.5 * fabs(lat_g - lat_p)), st = sin(0.5 * fabs(th_g - th_p));
+    const double L = 2.0 * asin(sqrt(sh * sh + cos(lat_g) * cos(lat_p) * st * st));
+    const double sL = sin(0.5 * L);
+    const double dth = fabs(2.0 * asin(sqrt((sL * sL - sh * sh) / (cos(yg) * cos(yp)))));
+    const double th_mid = 0.5 * (th_g + th_p);
+    ObbPair o;
+    o.x1 = 0.0f; o.y1 = (float)yg;
+    o.x2 = (float)((th_p > th_g) ? dth : -dth); o.y2 = (float)yp;
+    o.a1 = (float)legacy_internal_angle(th_g, ph_g, th_mid);
+    o.a2 = (float)legacy_internal_angle(th_p, ph_p, th_mid);
+    o.w1 = edge_len_deg(g.a, edge); o.h1 = edge_len_deg(g.b, edge);
+    o.w2 = edge_len_deg(p.a, edge); o.h2 = edge_len_deg(p.b, edge);
+    return o;
+}
+
+SPHK_HD float sph2pob_legacy_iou_pair(const RawBox& b1, const RawBox& b2, int mode, int edge) {
+    const bool m = jitter1_mask(b1, b2, 4);
+    const JitBox g = jitter1_role1(b1, m, 4), p = jitter1_role2(b2, m, 4);
+    ObbPair o = sph2pob_legacy(g, p, edge);
+    jitter2(o);
+    if (obb_disjoint(o)) return 0.0f;
+    return riou_value(o, mode);
+}
+
 // ---- Sph-IoU / FoV-IoU (approximate_ious.py:3-55 behind sph_iou_api.py:130-177) -------
 SPHK_HD float approx_iou_pair(const RawBox& b1, const RawBox& b2, int kind) {
     const bool m = jitter1_mask(b1, b2, 4);
@@ -684,19 +734,41 @@ SPHK_HD void unbiased_normals(double theta, double phi, double fx, double fy, do
     }
 }
 
-// one candidate vertex V (unit, or the reference's nearly-unit V / (|V| + 1e-10)) on circles with normals E0, E1
-SPHK_HD void unbiased_vertex(const D3& V, const D3& E0, const D3& E1, const D3* N, double* sum, int* count) {
-    bool ok = true;
-    for (int k = 0; k < 8; ++k) ok = ok && (rint(d3_dot(V, N[k]) * 1e8) >= 0.0);     // np.round(., 8) >= 0
-    if (ok) {
-        double c = -d3_dot(E0, E1);
-        c = c < -1.0 ? -1.0 : (c > 1.0 ? 1.0 : c);
-        *sum += acos(c);
-        *count += 1;
+// A candidate V = c / (|c| + delta) (c = E0 x E1; delta = 0 for a box corner, 1e-10 for a crossing) and its antipode -V.
+// The reference counts V iff round(V . N_k, 8) >= 0 for the eight normals, i.e. rint(1e8 V . N_k) >= 0; since rint is odd
+// and c -> -c negates every product exactly, -V counts iff rint(1e8 V . N_k) <= 0 for all k.  Nearly all candidates fail
+// by a wide margin, which t_k = c . N_k shows without the square root and the division: 1e8 V . N_k < -0.5 is certain once
+// t_k < 0 and t_k^2 > 1e-16 |c|^2 + 2e-36 (that is -t_k > 0.7e-8 |c| + 1e-18, against the 0.5e-8 (|c| + 1e-10) of the
+// test and rounding errors of 1e-15 |c|).  Only candidates not rejected that way go through the reference's arithmetic.
+// A[4], B[4]: the normals of the two boxes (any order: the test is an AND over all eight).
+// Returns bit 0: V counts, bit 1: -V counts.
+SPHK_HD int unbiased_candidate(const D3& c, double delta, const D3* A, const D3* B, bool want_neg) {
+    const double n2 = d3_dot(c, c), thr = 1e-16 * n2 + 2e-36;
+    bool pos = true, neg = want_neg;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double ta = d3_dot(c, A[k]), tb = d3_dot(c, B[k]);
+        const double sa = ta * fabs(ta), sb = tb * fabs(tb);          // signed squares: one compare each side
+        pos = pos && !(sa < -thr) && !(sb < -thr);
+        neg = neg && !(sa > thr) && !(sb > thr);
     }
+    if (!(pos || neg)) return 0;
+    const double inv = 1.0 / (sqrt(n2) + delta);
+    const D3 V = d3(c.x * inv, c.y * inv, c.z * inv);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double ra = rint(d3_dot(V, A[k]) * 1e8), rb = rint(d3_dot(V, B[k]) * 1e8);     // np.round(., 8): sign of rint(1e8 x)
+        pos = pos && (ra >= 0.0) && (rb >= 0.0);
+        neg = neg && (ra <= 0.0) && (rb <= 0.0);
+    }
+    return (pos ? 1 : 0) | (neg ? 2 : 0);
 }
 
-SPHK_HD double unbiased_area(double fx, double fy) { return 4.0 * acos(-sin(0.5 * fx) * sin(0.5 * fy)) - 2.0 * SPHK_PI_D; }
+SPHK_HD void d3_rotate4(D3* Q) { const D3 t = Q[0]; Q[0] = Q[1]; Q[1] = Q[2]; Q[2] = Q[3]; Q[3] = t; }
+
+SPHK_HD double unbiased_angle(double minus_cos) {      // interArea: arccos(clip(-E0 . E1, -1, 1))
+    return acos(minus_cos < -1.0 ? -1.0 : (minus_cos > 1.0 ? 1.0 : minus_cos));
+}
 
 SPHK_HD float unbiased_iou_pair(const RawBox& b1, const RawBox& b2, int D) {
     // jiter_spherical_bboxes (sph_iou_api.py:244-260) in double, on the float32 box values: with nearly coincident
@@ -705,43 +777,59 @@ SPHK_HD float unbiased_iou_pair(const RawBox& b1, const RawBox& b2, int D) {
     const double eps = SPHK_EPS_D;
     const double u[5] = {b1.t, b1.p, b1.a, b1.b, b1.g}, v[5] = {b2.t, b2.p, b2.a, b2.b, b2.g};
     bool m = false;
-    for (int k = 0; k < D; ++k) m = m || (fabs(u[k] - v[k]) < eps);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) m = m || (k < D && fabs(u[k] - v[k]) < eps);
     double x[5], y[5];
+#pragma unroll
     for (int k = 0; k < 5; ++k) { x[k] = (k < D) ? (m ? u[k] - 2.0 * eps : u[k]) : 0.0; y[k] = (k < D) ? (m ? v[k] + eps : v[k]) : 0.0; }
     x[0] = fmin(fmax(x[0], 2.0 * eps), 360.0 - eps);
     y[0] = fmin(fmax(y[0], eps), 360.0 - 2.0 * eps);
+#pragma unroll
     for (int k = 1; k < 4; ++k) { x[k] = fmin(fmax(x[k], 2.0 * eps), 180.0 - eps); y[k] = fmin(fmax(y[k], eps), 180.0 - 2.0 * eps); }
     if (D == 5) y[4] = fmin(fmax(y[4], -360.0 + 2.0 * eps), 360.0 - 2.0 * eps);       // both clamps of :257-258 hit bboxes2
     const double d2r = SPHK_PI_D / 180.0;
     const double fx1 = x[2] * d2r, fy1 = x[3] * d2r, fx2 = y[2] * d2r, fy2 = y[3] * d2r;
-    D3 N[8];
-    unbiased_normals(x[0] * d2r, x[1] * d2r, fx1, fy1, x[4] * d2r, D == 5, N);
-    unbiased_normals(y[0] * d2r, y[1] * d2r, fx2, fy2, y[4] * d2r, D == 5, N + 4);
+    // The interior angle at a box's own corner is the same at all four: -(N_a . N_b) = -sin(fx/2) sin(fy/2) for the four
+    // pairs of getNormal (roll_T is a rotation), and the box area is 4 of them minus 2 pi (Sph.area).
+    const double corner1 = unbiased_angle(-sin(0.5 * fx1) * sin(0.5 * fy1)), corner2 = unbiased_angle(-sin(0.5 * fx2) * sin(0.5 * fy2));
+    const double a1 = 4.0 * corner1 - 2.0 * SPHK_PI_D, a2 = 4.0 * corner2 - 2.0 * SPHK_PI_D;
+    // normals kept in cyclic order (left, up, right, down) so that corner k is Q[k] x Q[k+1]: the reference's four
+    // (left x up, down x left, up x right, right x down).  The candidate loops are NOT unrolled -- each iteration works on
+    // element 0 (and 1) and then rotates the array, so the arrays stay in registers with one copy of the test in the
+    // instruction stream (the unrolled form was 24 copies and stalled on instruction fetch).
+    D3 A[4], B[4];
+    {
+        D3 N[4];
+        unbiased_normals(x[0] * d2r, x[1] * d2r, fx1, fy1, x[4] * d2r, D == 5, N);
+        A[0] = N[0]; A[1] = N[2]; A[2] = N[1]; A[3] = N[3];
+        unbiased_normals(y[0] * d2r, y[1] * d2r, fx2, fy2, y[4] * d2r, D == 5, N);
+        B[0] = N[0]; B[1] = N[2]; B[2] = N[1]; B[3] = N[3];
+    }
     double sum = 0.0;
     int count = 0;
-    // corners (getNormal: left x up, down x left, up x right, right x down), normalised
-    const int ca[4] = {0, 3, 2, 1}, cb[4] = {2, 0, 1, 3};
-    for (int b = 0; b < 2; ++b) {
-        for (int k = 0; k < 4; ++k) {
-            const D3& E0 = N[4 * b + ca[k]];
-            const D3& E1 = N[4 * b + cb[k]];
-            const D3 c = d3_cross(E0, E1);
-            const double inv = 1.0 / sqrt(d3_dot(c, c));
-            unbiased_vertex(d3(c.x * inv, c.y * inv, c.z * inv), E0, E1, N, &sum, &count);
-        }
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {                       // corners of box 1
+        if (unbiased_candidate(d3_cross(A[0], A[1]), 0.0, A, B, false)) { sum += corner1; count += 1; }
+        d3_rotate4(A);
+    }
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {                       // corners of box 2
+        if (unbiased_candidate(d3_cross(B[0], B[1]), 0.0, A, B, false)) { sum += corner2; count += 1; }
+        d3_rotate4(B);
     }
     // crossings of a boundary circle of box 1 with one of box 2: +-(N_i x N'_j) / (|.| + 1e-10)
-    for (int i = 0; i < 4; ++i) {
-        for (int j = 0; j < 4; ++j) {
-            const D3 c = d3_cross(N[i], N[4 + j]);
-            const double inv = 1.0 / (sqrt(d3_dot(c, c)) + 1e-10);
-            const D3 v = d3(c.x * inv, c.y * inv, c.z * inv);
-            unbiased_vertex(v, N[i], N[4 + j], N, &sum, &count);
-            unbiased_vertex(d3(-v.x, -v.y, -v.z), N[4 + j], N[i], N, &sum, &count);
+#pragma unroll 1
+    for (int ij = 0; ij < 16; ++ij) {
+        const int hit = unbiased_candidate(d3_cross(A[0], B[0]), 1e-10, A, B, true);
+        if (hit) {
+            const double ang = unbiased_angle(-d3_dot(A[0], B[0]));
+            sum += (hit == 3) ? 2.0 * ang : ang;
+            count += (hit == 3) ? 2 : 1;
         }
+        d3_rotate4(B);
+        if ((ij & 3) == 3) d3_rotate4(A);
     }
     const double inter = (count == 0) ? 0.0 : sum - (double)(count - 2) * SPHK_PI_D;
-    const double a1 = unbiased_area(fx1, fy1), a2 = unbiased_area(fx2, fy2);
     // the two files end differently (unbiased_iou_bfov.py:199 / unbiased_iou_rbfov.py:175)
     const double iou = (D == 4) ? (inter + 1e-8) / (a1 + a2 - (inter + 1e-8)) : inter / (a1 + a2 - inter + 1e-8);
     return clampf((float)iou, 0.0f, 1.0f);        // .float() then clamp(0, 1) (sph_iou_api.py:125)

@@ -8,7 +8,8 @@ import torch
 from ... import _native
 
 _KINDS = {'sph2pob_standard_iou': 'sph2pob_standard', 'sph2pob_efficient_iou': 'sph2pob_efficient',
-          'fov_iou': 'fov', 'sph_iou': 'sph', 'naive_iou': 'naive', 'unbiased_iou': 'unbiased'}
+          'fov_iou': 'fov', 'sph_iou': 'sph', 'naive_iou': 'naive', 'unbiased_iou': 'unbiased',
+          'sph2pob_legacy_iou': 'sph2pob_legacy'}
 
 
 def sph_max_overlaps(bboxes1, bboxes2, backend='sph2pob_efficient_iou', mode='iou', box_version=None,

@@ -10,7 +10,7 @@ import torch
 
 from ... import _native
 
-__all__ = ["sph2pob_standard_iou", "sph2pob_efficient_iou", "fov_iou", "sph_iou", "naive_iou", "unbiased_iou"]
+__all__ = ["sph2pob_standard_iou", "sph2pob_efficient_iou", "sph2pob_legacy_iou", "fov_iou", "sph_iou", "naive_iou", "unbiased_iou"]
 
 
 def _empty(bboxes1, rows, cols, is_aligned):
@@ -50,6 +50,14 @@ def sph2pob_efficient_iou(bboxes1, bboxes2, mode='iou', is_aligned=False, calcul
                           rbb_angle='equator'):
     """sphdet/iou/sph_iou_api.py:97-98."""
     return _sph2pob_iou("sph2pob_efficient", bboxes1, bboxes2, mode, is_aligned, calculator, rbb_edge, rbb_angle)
+
+
+def sph2pob_legacy_iou(bboxes1, bboxes2, mode='iou', is_aligned=False, calculator='common', rbb_edge='arc'):
+    """sphdet/iou/sph_iou_api.py:91-92: the hand-crafted first version of the transform (sph2pob_legacy.py:8-31).  BFoV
+    only, as in the reference (``torch.chunk(box, 4)`` at sph2pob_legacy.py:52-53 fails on five columns)."""
+    if bboxes1.size(0) * bboxes2.size(0) != 0 and (bboxes1.size(-1) != 4 or bboxes2.size(-1) != 4):
+        raise ValueError("sph2pob_legacy_iou takes BFoV boxes [n, 4] (sph2pob_legacy.py:52-53)")
+    return _sph2pob_iou("sph2pob_legacy", bboxes1, bboxes2, mode, is_aligned, calculator, rbb_edge, 'equator')
 
 
 def sph_iou(bboxes1, bboxes2, mode='iou', is_aligned=False, calculator='diff'):

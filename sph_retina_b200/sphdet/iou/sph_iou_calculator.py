@@ -5,7 +5,8 @@ from __future__ import annotations
 import torch
 
 from ..registry import IOU_CALCULATORS
-from .sph_iou_api import fov_iou, naive_iou, sph2pob_efficient_iou, sph2pob_standard_iou, sph_iou, unbiased_iou
+from .sph_iou_api import (fov_iou, naive_iou, sph2pob_efficient_iou, sph2pob_legacy_iou, sph2pob_standard_iou, sph_iou,
+                          unbiased_iou)
 
 # backends of the reference that have a CUDA kernel here; the others are out of this path's scope
 _BACKENDS = {
@@ -15,6 +16,7 @@ _BACKENDS = {
     'sph_iou': sph_iou,
     'naive_iou': naive_iou,
     'unbiased_iou': unbiased_iou,
+    'sph2pob_legacy_iou': sph2pob_legacy_iou,
 }
 _REFERENCE_BACKENDS = ['unbiased_iou', 'sph2pob_standard_iou', 'sph2pob_legacy_iou', 'sph2pob_efficient_iou',
                        'naive_iou', 'fov_iou', 'sph_iou', 'kent_iou']
@@ -26,7 +28,8 @@ class SphOverlaps2D(object):
 
     Signature and defaults are the reference's, default backend 'unbiased_iou' included (a CPU numpy routine there, a
     double-precision kernel here); the spherical configs pass backend='sph2pob_efficient_iou'
-    (configs/_base_/models/sph_rotated_retinanet_r50_fpn.py:18-19).  'sph2pob_legacy_iou' and 'kent_iou' have no kernel."""
+    (configs/_base_/models/sph_rotated_retinanet_r50_fpn.py:18-19).  Of the reference's eight backend names only 'kent_iou'
+    (the Kent-distribution code, out of scope) has no kernel."""
 
     def __init__(self, backend='unbiased_iou', box_version=4):
         self.backend = backend

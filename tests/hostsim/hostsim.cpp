@@ -27,6 +27,7 @@ void hostsim_iou_aligned(int kind, const float* b1, const float* b2, long P, int
         out[i] = (kind == KIND_SPH || kind == KIND_FOV) ? approx_iou_pair(x, y, kind)
                  : (kind == KIND_NAIVE)                 ? naive_iou_pair(x, y, D, mode)
                  : (kind == KIND_UNBIASED)              ? unbiased_iou_pair(x, y, D)
+                 : (kind == KIND_SPH2POB_LEGACY)        ? sph2pob_legacy_iou_pair(x, y, mode, edge)
                                                         : sph2pob_iou_pair(x, y, D, kind, mode, edge);
     }
 }

@@ -56,6 +56,8 @@ def test_argument_validation_needs_no_gpu(built_lib):
     assert lib.sphk_nms_batched(None, None, None, 3, 9, 0, 4, 1, 0.5, None, None) == -3    # NMS calculator: efficient, naive or unbiased
     assert lib.sphk_iou_aligned(4, None, None, 10, 5, 1, 0, 0, None, None) == -3          # naive_iou: mode 'iou' only
     assert lib.sphk_iou_aligned(5, None, None, 10, 4, 1, 0, 0, None, None) == -3          # unbiased_iou: mode 'iou' only
+    assert lib.sphk_iou_aligned(6, None, None, 10, 5, 0, 0, 0, None, None) == -3          # sph2pob_legacy_iou: BFoV only
+    assert lib.sphk_iou_aligned(7, None, None, 10, 4, 0, 0, 0, None, None) == -1          # unknown kind
     assert lib.sphk_loss_fwd_bwd(None, None, 5, 4, None, None, None, None, None) == -1  # null boxes
 
 

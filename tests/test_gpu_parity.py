@@ -627,6 +627,29 @@ def test_unbiased_nms_golden_keep_sets(api, box):
         assert keep.cpu().tolist() == want
 
 
+# ---- sph2pob_legacy_iou (the reference's first transform; BFoV only) ----------------------------------------------------
+def test_sph2pob_legacy_golden(api):
+    g = load_golden("legacy")
+    b1, b2 = cu(g["b1"]), cu(g["b2"])
+    small = np.minimum(g["b1"][:, 2:4].min(axis=1), g["b2"][:, 2:4].min(axis=1))
+    speck = degenerate_pairs(g["b1"], g["b2"])
+    for key, kw in (("iou", {}), ("iof", dict(mode="iof")), ("chord", dict(rbb_edge="chord")), ("tangent", dict(rbb_edge="tangent"))):
+        got = api.iou.sph2pob_legacy_iou(b1, b2, is_aligned=True, **kw).cpu().numpy()
+        ok, err = within(got, g[key + "_f64"], g[key + "_f32"])
+        ok |= (small < 1.5) & (err < 1e-4)           # the stand-in's num / (den + 1e-8): see tests/test_hostsim_math.py
+        assert ok[~speck].all(), (key, np.where(~ok & ~speck)[0][:10], err[~ok & ~speck][:10])
+        assert got.min() >= 0.0 and got.max() <= 1.0
+    np.testing.assert_allclose(api.iou.sph2pob_legacy_iou(cu(g["kat_b1"]), cu(g["kat_b2"]), is_aligned=True).cpu().numpy(),
+                               g["kat_iou"], atol=5e-6)
+    mat = api.iou.SphOverlaps2D('sph2pob_legacy_iou', 4)(b1[:29], b2[:333])
+    ok, err = within(mat.cpu().numpy(), g["rc_f64"], g["rc_f32"])
+    assert mat.shape == (29, 333) and (~ok).sum() <= 2, err[~ok]
+    flat = api.iou.sph2pob_legacy_iou(b1[:29].repeat_interleave(333, 0), b2[:333].repeat(29, 1), is_aligned=True)
+    assert torch.equal(mat.reshape(-1), flat)
+    with pytest.raises(ValueError):
+        api.iou.sph2pob_legacy_iou(torch.rand(3, 5, device=DEV), torch.rand(3, 5, device=DEV))
+
+
 # ---- the other losses on the Sph2Pob OBBs ---------------------------------------------------
 def _other_loss(api, cls, kw, **extra):
     return getattr(api.losses, cls)(**kw, **extra)

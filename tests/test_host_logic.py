@@ -61,8 +61,8 @@ def test_empty_inputs_and_errors_follow_the_reference():
         sph2pob_efficient_iou(b, b, rbb_edge='diagonal')                   # sph_iou_api.py:51
     with pytest.raises(NotImplementedError):
         sph_overlaps(b, b, backend='kent_iou')                             # outside the path: refused, not faked
-    with pytest.raises(NotImplementedError):
-        sph_overlaps(b, b, backend='sph2pob_legacy_iou')
+    with pytest.raises(ValueError):
+        sph_overlaps(torch.zeros(2, 5), torch.zeros(2, 5), backend='sph2pob_legacy_iou')   # BFoV only (sph2pob_legacy.py:52-53)
 
 
 def test_no_cpu_fallback():

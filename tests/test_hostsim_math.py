@@ -387,3 +387,56 @@ def test_unbiased_iou_golden(hostsim, box):
     err32 = np.abs(g[box + "_aligned_f32"] - g[box + "_aligned_f64"])
     assert err.max() < 1e-6, (np.where(err >= 1e-6)[0][:10], err.max())
     assert (err32 > 1e-5).sum() > 10
+
+
+@pytest.mark.parametrize("box", ["bfov", "rbfov"])
+def test_unbiased_iou_clear_rejection_is_exact(hostsim, box):
+    """unbiased_iou_pair rejects most of the 40 candidate vertices on c . N_k alone (no square root, no division); that
+    shortcut must never change a result: random unrelated pairs (mostly disjoint), wide boxes up to the 180-degree clamp,
+    boxes at the poles, across the 0/360 seam and touching side by side, against the restatement (which evaluates
+    round(V . N, 8) >= 0 for all 40 candidates of every pair)."""
+    import os
+    import sys
+    import torch
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import sph_oracle as O
+    n = 6000
+    b1 = O.generate_boxes(n, alpha_range=(1, 179.9), beta_range=(1, 179.9), box=box, seed=31)
+    b2 = O.generate_boxes(n, alpha_range=(1, 179.9), beta_range=(1, 179.9), box=box, seed=32)
+    b1[:1500, 2:4] *= 0.1; b2[:1500, 2:4] *= 0.1                        # small boxes: nearly all disjoint
+    b1[1500:1700, 1] = torch.tensor([0.0, 180.0]).repeat(100)          # poles
+    b2[1700:1900, 0] = (b1[1700:1900, 0] + 359.0) % 360                  # neighbours across the seam
+    b2[1700:1900, 1] = b1[1700:1900, 1]
+    b2[1900:2100] = b1[1900:2100]; b2[1900:2100, 0] = (b1[1900:2100, 0] + b1[1900:2100, 2]) % 360   # touching side by side
+    want = O.unbiased_iou(b1, b2, is_aligned=True).numpy()
+    got = hs_aligned(hostsim, 5, b1.numpy(), b2.numpy())
+    err = np.abs(got - want)
+    assert err.max() < 1e-6, (np.where(err >= 1e-6)[0][:10], err.max())
+    assert (want < 1e-6).mean() > 0.2 and (want > 0.01).mean() > 0.2      # both regimes are exercised
+
+
+def test_sph2pob_legacy_golden(hostsim):
+    """sph2pob_legacy_iou_pair (kind 6, BFoV) against the reference's own sph2pob_legacy_iou: modes, edges, the 7 known
+    answers of tests/test_all_ious.py.  Criterion of SURVEY.md 8(c): within 1e-5 of the reference's fp64 run, or no
+    further from it than the reference's fp32 run (whose clamped acos near 1 is good to ~2e-4 rad only)."""
+    g = load_golden("legacy")
+    for key, mode, edge in (("iou", 0, 0), ("iof", 1, 0), ("chord", 0, 1), ("tangent", 0, 2)):
+        got = hs_aligned(hostsim, 6, g["b1"], g["b2"], mode, edge)
+        ok, err = within(got, g[key + "_f64"], g[key + "_f32"])
+        # The golden values go through the reference's vendored diff_iou_rotated_2d (the stand-in for mmcv's box_iou_rotated,
+        # SURVEY.md 8c), whose crossing parameter is num / (den + 1e-8) with den ~ w * h: boxes of ~1 degree are 3e-5 off
+        # the exact intersection there, and the <0.06 degree specks jitter_2 inflates to 2.5e-4 rad (den ~ 1e-8, which the
+        # legacy transform -- unlike efficient / standard -- leaves overlapping) are off by a factor.  The kernel clips exactly.
+        small = np.minimum(g["b1"][:, 2:4].min(axis=1), g["b2"][:, 2:4].min(axis=1))
+        ok |= (small < 1.5) & (err < 1e-4)
+        speck = degenerate_pairs(g["b1"], g["b2"])
+        assert ok[~speck].all(), (key, np.where(~ok & ~speck)[0][:10], err[~ok & ~speck][:10])
+        assert (err[~speck] > 1e-5).sum() <= 4 and np.median(err) < 1e-7
+        assert np.nanmin(got) >= 0.0 and np.nanmax(got) <= 1.0
+    # the zero-size pair (both boxes become eps-sized, then 2.5e-4 / 1.25e-4 rad squares whose corners overlap by 6.5e-5 x
+    # 6.3e-5 after jitter_2's shifts): exact IoU = 4.08e-9 / 7.48e-8
+    i = int(np.where((g["b1"] == 0).all(axis=1) & (g["b2"] == 0).all(axis=1))[0][0])
+    assert abs(hs_aligned(hostsim, 6, g["b1"][i:i + 1], g["b2"][i:i + 1])[0] - 0.0545) < 2e-3
+    np.testing.assert_allclose(hs_aligned(hostsim, 6, g["kat_b1"], g["kat_b2"]), g["kat_iou"], atol=5e-6)
+    np.testing.assert_allclose(g["kat_iou"], [0.232635, 0.333749, 0.617413, 0.138463, 0.286415, 0.203624, 0.554315], atol=2e-6)

@@ -247,3 +247,18 @@ def test_restatement_unbiased_iou_and_its_nms(box):
     for thr in (0.3, 0.5):
         _, keep = O.nms_batched(boxes, scores, idxs, thr, max_num=120, iou_fn=lambda a, b: O.unbiased_iou(a, b))
         assert keep.tolist() == g["%s_keep_thr%d" % (box, int(thr * 10))].tolist()
+
+
+def test_restatement_sph2pob_legacy():
+    """oracle.sph2pob_legacy (sph2pob_legacy.py:8-31) behind the common pipeline against the reference's sph2pob_legacy_iou."""
+    g = load_golden("legacy")
+    b1, b2 = torch.from_numpy(g["b1"]), torch.from_numpy(g["b2"])
+    for key, kw in (("iou", {}), ("iof", dict(mode="iof")), ("chord", dict(rbb_edge="chord")), ("tangent", dict(rbb_edge="tangent"))):
+        got = O.sph2pob_iou(b1.double(), b2.double(), transform="legacy", is_aligned=True, **kw).numpy()
+        np.testing.assert_allclose(got, g[key + "_f64"], atol=1e-8)
+        got = O.sph2pob_iou(b1, b2, transform="legacy", is_aligned=True, **kw).numpy()
+        np.testing.assert_allclose(got, g[key + "_f32"], atol=1e-6)
+    got = O.sph2pob_iou(b1[:29].double(), b2[:333].double(), transform="legacy").numpy()
+    np.testing.assert_allclose(got, g["rc_f64"], atol=1e-8)
+    with pytest.raises(AssertionError):
+        O.sph2pob_legacy(torch.zeros(2, 5), torch.zeros(2, 5))

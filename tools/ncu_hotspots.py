@@ -28,7 +28,8 @@ def main():
             cur["hdr"] = row
         elif cur is not None and cur["hdr"] and len(row) == len(cur["hdr"]):
             cur["rows"].append(row)
-    blk = [b for b in blocks if pat in b["name"]][0]
+    base_name = pat.split("<")[0]
+    blk = [b for b in blocks if base_name in b["name"]][0]          # (ncu prints template arguments as "(int)5, (int)4")
     hdr = blk["hdr"]
     ia, ii, isamp = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("# Samples")
     base = int(blk["rows"][0][ia], 16)
@@ -45,7 +46,9 @@ def main():
     for l in dis.splitlines():
         m = re.match(r"\s*\.section\s+\.text\.(\S+?),", l)
         if m:
-            inside = key in m.group(1) and all(t in m.group(1) for t in re.findall(r"\d+", pat.split("<")[1])) if "<" in pat else key in m.group(1)
+            # integer template arguments are mangled as I Li<n>E ... E right after the name
+            frag = key + ("I" + "".join("Li%sE" % t for t in re.findall(r"\d+", pat.split("<")[1])) if "<" in pat else "")
+            inside = frag in m.group(1)
             continue
         if not inside:
             continue
