@@ -369,6 +369,40 @@ def golden_legacy(R):
     print("legacy", out["kat_iou"], float(np.nanmean(out["iou_f64"])), int(np.isnan(out["iou_f64"]).sum()), int(np.isnan(out["iou_f32"]).sum()))
 
 
+def golden_legacy_loss(R):
+    """SphIoULossLegacy = Sph2PobTransfrom()(mmrotate RotatedIoULoss) (sph2pob_iou_loss.py:199-216) on the rows of golden_loss:
+    per-row losses and both gradients for the three modes, fp32 and fp64 runs, plus the reductions."""
+    out = {}
+    for box in ("bfov", "rbfov"):
+        g = np.load(os.path.join(OUT, "loss_%s.npz" % box))
+        p, t, w1, w2 = (torch.from_numpy(g[k]) for k in ("pred", "target", "w1", "w2"))
+        for mode in ("log", "linear", "square"):
+            for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+                L = R.SphIoULossLegacy(mode=mode, reduction="sum")
+                pp, tt = p.to(dt).clone().requires_grad_(True), t.to(dt).clone().requires_grad_(True)
+                if dt == torch.float64:
+                    with rh.float64_mode():
+                        el = L(pp, tt, reduction_override="none")
+                        el.sum().backward()
+                else:
+                    el = L(pp, tt, reduction_override="none")
+                    el.sum().backward()
+                out["%s_%s_loss_%s" % (box, mode, tag)] = _np(el)
+                out["%s_%s_gpred_%s" % (box, mode, tag)] = _np(pp.grad)
+                out["%s_%s_gtarget_%s" % (box, mode, tag)] = _np(tt.grad)
+        with rh.float64_mode():
+            L = R.SphIoULossLegacy(loss_weight=2.0)
+            pd, td = p.double(), t.double()
+            out[box + "_red_mean"] = _np(L(pd, td))
+            out[box + "_red_w1_avg"] = _np(L(pd, td, w1.double(), avg_factor=123.0))
+            out[box + "_red_w2"] = _np(L(pd, td, w2.double()))
+            out[box + "_red_w1_sum"] = _np(L(pd, td, w1.double(), reduction_override="sum"))
+            out[box + "_red_zero_w"] = _np(L(pd, td, torch.zeros_like(pd)))      # (a 1-D zero weight fails to broadcast in mmrotate)
+            out[box + "_red_linear"] = _np(R.SphIoULossLegacy(linear=True)(pd, td, w1.double()))
+        print("legacy loss", box, float(out[box + "_log_loss_f64"].mean()), float(out[box + "_red_mean"]))
+    np.savez_compressed(os.path.join(OUT, "legacy_loss.npz"), **out)
+
+
 def golden_nms(R):
     out = {}
     for box in ("bfov", "rbfov"):
@@ -458,3 +492,4 @@ if __name__ == "__main__":
     golden_naive(R)
     golden_unbiased(R)
     golden_legacy(R)
+    golden_legacy_loss(R)

@@ -3,6 +3,7 @@ subclasses for its "other" Sph2Pob losses:
 
     sphdet/losses/sph2pob_gd_loss.py:2,9    class Sph2PobGDLoss(GDLoss)      from mmrotate.models.losses import GDLoss
     sphdet/losses/sph2pob_kf_loss.py:2,10   class Sph2PobKFLoss(KFLoss)      from mmrotate.models.losses import KFLoss
+    sphdet/losses/sph2pob_iou_loss.py:8,201 class SphIoULossLegacy(RotatedIoULoss)  from mmrotate.models.losses import RotatedIoULoss
 
 PARITY UNPINNED at the mmrotate boundary: mmrotate (pinned to 0.3.2 by the reference's README.md:95,102) is a
 third-party package that is neither vendored in the reference tree nor installable offline.  What follows restates the
@@ -239,3 +240,46 @@ class KFLoss(nn.Module):
             weight = weight.mean(-1)
         return kfiou_loss(pred, target, fun=self.fun, weight=weight, avg_factor=avg_factor, pred_decode=pred_decode,
                           targets_decode=targets_decode, reduction=reduction, **kwargs) * self.loss_weight
+
+
+# ---- rotated_iou_loss.py (mmrotate 0.3.2) ---------------------------------------------------------------------------
+# The base class of the reference's SphIoULossLegacy (sphdet/losses/sph2pob_iou_loss.py:199-216:
+# ``Sph2PobTransfrom()(RotatedIoULoss)``).  ``iou_fn``: mmcv.ops.diff_iou_rotated_2d at run time (the harness installs the
+# reference's vendored copy under that name).
+@weighted_loss
+def rotated_iou_loss(pred, target, linear=False, mode="log", eps=1e-6):
+    assert mode in ["linear", "square", "log"]
+    if linear:
+        mode = "linear"
+    from mmcv.ops import diff_iou_rotated_2d
+    ious = diff_iou_rotated_2d(pred.unsqueeze(0), target.unsqueeze(0))
+    ious = ious.squeeze(0).clamp(min=eps)
+    if mode == "linear":
+        return 1 - ious
+    if mode == "square":
+        return 1 - ious ** 2
+    return -ious.log()
+
+
+class RotatedIoULoss(nn.Module):
+    def __init__(self, linear=False, eps=1e-6, reduction="mean", loss_weight=1.0, mode="log"):
+        super().__init__()
+        assert mode in ("linear", "square", "log")
+        if linear:
+            mode = "linear"
+        self.mode = mode
+        self.linear = linear
+        self.eps = eps
+        self.reduction = reduction
+        self.loss_weight = loss_weight
+
+    def forward(self, pred, target, weight=None, avg_factor=None, reduction_override=None, **kwargs):
+        assert reduction_override in (None, "none", "mean", "sum")
+        reduction = reduction_override if reduction_override else self.reduction
+        if (weight is not None) and (not torch.any(weight > 0)) and (reduction != "none"):
+            return (pred * weight).sum()
+        if weight is not None and weight.dim() > 1:
+            assert weight.shape == pred.shape
+            weight = weight.mean(-1)
+        return self.loss_weight * rotated_iou_loss(pred, target, weight, mode=self.mode, eps=self.eps, reduction=reduction,
+                                                   avg_factor=avg_factor, **kwargs)

@@ -196,6 +196,7 @@ def load_reference():
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     import mmrotate_losses as _mmr
     mmrot_losses.GDLoss = _mmr.GDLoss
+    mmrot_losses.RotatedIoULoss = _mmr.RotatedIoULoss
     mmrot_losses.KFLoss = _mmr.KFLoss
     sys.modules["mmrotate"] = mmrot
     sys.modules["mmrotate.models"] = mmrot_models
@@ -241,7 +242,7 @@ def load_reference():
         sph2pob_legacy_iou=api.sph2pob_legacy_iou,
         sph_iou=api.sph_iou, fov_iou=api.fov_iou, naive_iou=api.naive_iou, unbiased_iou=api.unbiased_iou,
         SphOverlaps2D=calc.SphOverlaps2D, SphNMS=sph_nms.SphNMS,
-        Sph2PobIoULoss=iou_loss.Sph2PobIoULoss,
+        Sph2PobIoULoss=iou_loss.Sph2PobIoULoss, SphIoULossLegacy=iou_loss.SphIoULossLegacy,
         Sph2PobGDLoss=gd_loss.Sph2PobGDLoss, Sph2PobKFLoss=kf_loss.Sph2PobKFLoss, Sph2PobL1Loss=l1_loss.Sph2PobL1Loss,
         jiter_spherical_bboxes=api.jiter_spherical_bboxes,
         jiter_rotated_bboxes=api.jiter_rotated_bboxes,

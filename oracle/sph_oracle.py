@@ -455,6 +455,13 @@ def sph2pob_iou_loss_elementwise(pred, target, mode="iou", eps=1e-6):
     raise NotImplementedError(mode)
 
 
+def sph_iou_loss_legacy_elementwise(pred, target, mode="log", eps=1e-6):
+    """SphIoULossLegacy (sph2pob_iou_loss.py:199-216): mmrotate 0.3.2 rotated_iou_loss on the Sph2Pob OBBs; per-row loss."""
+    o1, o2 = loss_obbs(pred, target)
+    ious = rotated_iou(o1, o2).clamp(min=eps)
+    return {"linear": 1 - ious, "square": 1 - ious ** 2, "log": -ious.log()}[mode]
+
+
 def sph2pob_iou_loss(pred, target, weight=None, avg_factor=None, mode="iou", eps=1e-6,
                      reduction="mean", loss_weight=1.0):
     """Sph2PobIoULoss.forward: sph2pob_transform.py:24-35, sph2pob_iou_loss.py:25-58,

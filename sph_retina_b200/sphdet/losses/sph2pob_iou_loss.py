@@ -262,6 +262,45 @@ class Sph2PobIoULoss(_SphLossBase):
 
 
 @LOSSES.register_module()
+class SphIoULossLegacy(nn.Module):
+    """sphdet/losses/sph2pob_iou_loss.py:199-216 -- ``Sph2PobTransfrom()(RotatedIoULoss)``: mmrotate 0.3.2's rotated IoU
+    loss (``-log(iou)``, ``1 - iou`` or ``1 - iou^2`` of ``diff_iou_rotated_2d(...).clamp(min=eps)``) on the Sph2Pob OBBs of
+    the pair.  The IoU and its two gradients come from the same single launch as ``Sph2PobIoULoss`` (``sphk_loss_fwd_bwd``);
+    the scalar map and the reduction are torch ops on the [n] vector.
+
+    pred / target: spherical boxes [n, 4|5] in degrees; weight: None, [n] or [n, box_version]."""
+
+    def __init__(self, linear=False, eps=1e-6, reduction='mean', loss_weight=1.0, mode='log'):
+        super().__init__()
+        assert mode in ('linear', 'square', 'log')
+        self.mode = 'linear' if linear else mode
+        self.linear = linear
+        self.eps = eps
+        self.reduction = reduction
+        self.loss_weight = loss_weight
+
+    def forward(self, pred, target, weight=None, avg_factor=None, reduction_override=None, **kwargs):
+        box_version = target.size(-1)
+        if weight is not None and weight.dim() > 1 and box_version == 4:       # sph2pob_transform.py:32-34
+            weight = torch.cat([weight, weight.mean(-1, keepdim=True)], dim=-1)
+        assert reduction_override in (None, 'none', 'mean', 'sum')
+        reduction = reduction_override if reduction_override else self.reduction
+        if weight is not None and not torch.any(weight > 0) and reduction != 'none':
+            return pred.sum() * 0                                              # rotated_iou_loss.py: (pred * weight).sum()
+        if weight is not None and weight.dim() > 1:
+            assert weight.shape == (pred.size(0), 5)
+            weight = weight.mean(-1)
+        ious = _Sph2PobIoU.apply(pred, target).clamp(min=self.eps)
+        if self.mode == 'linear':
+            loss = 1 - ious
+        elif self.mode == 'square':
+            loss = 1 - ious ** 2
+        else:
+            loss = -ious.log()
+        return self.loss_weight * _weight_reduce_loss(loss, weight, reduction, avg_factor)
+
+
+@LOSSES.register_module()
 class SphIoULoss(_SphLossBase):
     """sphdet/losses/sph2pob_iou_loss.py:239-296.  The reference class is non-functional as shipped
     (its calculator='diff' branch is dead code); this one computes what it was written to compute for

@@ -497,6 +497,49 @@ def test_loss_reductions_weights_avg_factor(api, box):
         assert torch.isfinite(L(p, t))
 
 
+@pytest.mark.parametrize("box", ["bfov", "rbfov"])
+@pytest.mark.parametrize("mode", ["log", "linear", "square"])
+def test_legacy_iou_loss_golden(api, box, mode):
+    """SphIoULossLegacy (sph2pob_iou_loss.py:199-216; mmrotate's RotatedIoULoss on the Sph2Pob OBBs) against the reference's
+    own class: per-row loss (compared as the IoU it encodes for 'log': -log amplifies a 1e-5 IoU error of a 1e-3 IoU to
+    1e-2) and both gradients, fp64 truth with the reference's fp32 run as the yardstick."""
+    g, base = load_golden("legacy_loss"), load_golden("loss_" + box)
+    p, t = cu(base["pred"]).requires_grad_(True), cu(base["target"]).requires_grad_(True)
+    el = api.losses.SphIoULossLegacy(mode=mode, reduction="sum")(p, t, reduction_override="none")
+    assert el.shape == (p.size(0),)
+    el.sum().backward()
+    key = "%s_%s_" % (box, mode)
+    as_iou = (lambda x: np.exp(-np.asarray(x, np.float64))) if mode == "log" else (lambda x: np.asarray(x, np.float64))
+    ok, err = within(as_iou(el.detach().cpu().numpy()), as_iou(g[key + "loss_f64"]), as_iou(g[key + "loss_f32"]), tol=2e-5)
+    assert ok.all(), (np.where(~ok)[0], err[~ok])
+    for got, name in ((p.grad, "gpred"), (t.grad, "gtarget")):
+        truth, ref32 = g[key + name + "_f64"], g[key + name + "_f32"]
+        rel, den = grad_row_error(got.cpu().numpy(), truth)
+        rel32, _ = grad_row_error(ref32, truth)
+        live = den > 1e-9
+        assert np.abs(got.cpu().numpy()[~live]).max(initial=0.0) < 1e-6
+        good = (rel <= 1e-4) | (rel <= rel32)
+        assert good[live].mean() > 0.995, (name, (~good & live).sum())
+        assert np.median(rel[live]) < 3e-6
+
+
+@pytest.mark.parametrize("box", ["bfov", "rbfov"])
+def test_legacy_iou_loss_reductions(api, box):
+    g, base = load_golden("legacy_loss"), load_golden("loss_" + box)
+    p, t, w1, w2 = cu(base["pred"]), cu(base["target"]), cu(base["w1"]), cu(base["w2"])
+    L = api.losses.SphIoULossLegacy(loss_weight=2.0)
+    np.testing.assert_allclose(L(p, t).item(), g[box + "_red_mean"], rtol=1e-4)
+    np.testing.assert_allclose(L(p, t, w1, avg_factor=123.0).item(), g[box + "_red_w1_avg"], rtol=1e-4)
+    np.testing.assert_allclose(L(p, t, w2).item(), g[box + "_red_w2"], rtol=1e-4)
+    np.testing.assert_allclose(L(p, t, w1, reduction_override="sum").item(), g[box + "_red_w1_sum"], rtol=1e-4)
+    np.testing.assert_allclose(api.losses.SphIoULossLegacy(linear=True)(p, t, w1).item(), g[box + "_red_linear"], rtol=2e-5)
+    pz = p.clone().requires_grad_(True)
+    z = L(pz, t, torch.zeros_like(p))
+    assert z.item() == 0.0 == float(g[box + "_red_zero_w"])
+    z.backward()
+    assert float(pz.grad.abs().max()) == 0.0
+
+
 def test_loss_gradcheck_against_finite_differences(api):
     """Independent of the reference: central differences of the kernel's own forward (fp32, so loose)."""
     t = O.generate_boxes(512, alpha_range=(20, 80), beta_range=(20, 80), box="rbfov", seed=2)

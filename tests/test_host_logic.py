@@ -204,3 +204,17 @@ def test_other_sph2pob_losses_host_contract():
             loss(b, b.clone())
         with pytest.raises(AssertionError):
             loss(b, b.clone(), reduction_override='avg')
+
+
+def test_legacy_iou_loss_host_contract():
+    """SphIoULossLegacy: constructor of mmrotate's RotatedIoULoss (linear overrides mode), registered in LOSSES."""
+    from sph_retina_b200.sphdet.losses import SphIoULossLegacy
+    from sph_retina_b200.sphdet.registry import LOSSES
+    L = SphIoULossLegacy()
+    assert (L.mode, L.eps, L.reduction, L.loss_weight) == ('log', 1e-6, 'mean', 1.0)
+    assert SphIoULossLegacy(linear=True, mode='square').mode == 'linear'
+    with pytest.raises(AssertionError):
+        SphIoULossLegacy(mode='iou')
+    assert LOSSES.get('SphIoULossLegacy') is SphIoULossLegacy
+    with pytest.raises(AssertionError):
+        L(torch.zeros(2, 4), torch.zeros(2, 4), reduction_override='max')

@@ -262,3 +262,18 @@ def test_restatement_sph2pob_legacy():
     np.testing.assert_allclose(got, g["rc_f64"], atol=1e-8)
     with pytest.raises(AssertionError):
         O.sph2pob_legacy(torch.zeros(2, 5), torch.zeros(2, 5))
+
+
+@pytest.mark.parametrize("box", ["bfov", "rbfov"])
+def test_restatement_legacy_iou_loss(box):
+    """oracle.sph_iou_loss_legacy_elementwise against the reference's SphIoULossLegacy (float64 run): losses and gradients."""
+    g, base = load_golden("legacy_loss"), load_golden("loss_" + box)
+    for mode in ("log", "linear", "square"):
+        p = torch.from_numpy(base["pred"]).double().requires_grad_(True)
+        t = torch.from_numpy(base["target"]).double().requires_grad_(True)
+        el = O.sph_iou_loss_legacy_elementwise(p, t, mode)
+        el.sum().backward()
+        key = "%s_%s_" % (box, mode)
+        np.testing.assert_allclose(el.detach().numpy(), g[key + "loss_f64"], atol=1e-8)
+        np.testing.assert_allclose(p.grad.numpy(), g[key + "gpred_f64"], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(t.grad.numpy(), g[key + "gtarget_f64"], rtol=1e-6, atol=1e-7)
