@@ -735,31 +735,35 @@ SPHK_HD void unbiased_normals(double theta, double phi, double fx, double fy, do
 }
 
 // A candidate V = c / (|c| + delta) (c = E0 x E1; delta = 0 for a box corner, 1e-10 for a crossing) and its antipode -V.
-// The reference counts V iff round(V . N_k, 8) >= 0 for the eight normals, i.e. rint(1e8 V . N_k) >= 0; since rint is odd
-// and c -> -c negates every product exactly, -V counts iff rint(1e8 V . N_k) <= 0 for all k.  Nearly all candidates fail
-// by a wide margin, which t_k = c . N_k shows without the square root and the division: 1e8 V . N_k < -0.5 is certain once
-// t_k < 0 and t_k^2 > 1e-16 |c|^2 + 2e-36 (that is -t_k > 0.7e-8 |c| + 1e-18, against the 0.5e-8 (|c| + 1e-10) of the
-// test and rounding errors of 1e-15 |c|).  Only candidates not rejected that way go through the reference's arithmetic.
+// The reference counts V iff round(V . N_k, 8) >= 0 for the eight normals, i.e. rint(1e8 V . N_k) >= 0, i.e.
+// 1e8 V . N_k >= -0.5 (half-to-even: -0.5 rounds to -0, which passes), i.e. with t_k = c . N_k
+//     t_k >= -0.5e-8 (|c| + delta)        for all k;
+// c -> -c negates every product exactly, so -V counts iff t_k <= +0.5e-8 (|c| + delta) for all k.  The same t_k serve
+// both, and neither the division nor the normalised vector is needed.  (t_k / (|c| + delta) and the reference's
+// fl(V) . N_k differ by rounding at 1e-16 relative, which matters only if a product sits within 1e-15 of the threshold;
+// where boundary circles are parallel to 1e-7 rad the decision is noise in the reference too -- its sin / cos differ from
+// CUDA's in the last place.)  Nearly all candidates fail by a wide margin, which the squares show without the square
+// root: t_k < 0 and t_k^2 > 1e-16 |c|^2 + 2e-36 implies -t_k > 0.7e-8 |c| + 1e-18 > 0.5e-8 (|c| + 1e-10).
 // A[4], B[4]: the normals of the two boxes (any order: the test is an AND over all eight).
 // Returns bit 0: V counts, bit 1: -V counts.
 SPHK_HD int unbiased_candidate(const D3& c, double delta, const D3* A, const D3* B, bool want_neg) {
     const double n2 = d3_dot(c, c), thr = 1e-16 * n2 + 2e-36;
+    double t[8];
     bool pos = true, neg = want_neg;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const double ta = d3_dot(c, A[k]), tb = d3_dot(c, B[k]);
-        const double sa = ta * fabs(ta), sb = tb * fabs(tb);          // signed squares: one compare each side
+        t[k] = d3_dot(c, A[k]);
+        t[4 + k] = d3_dot(c, B[k]);
+        const double sa = t[k] * fabs(t[k]), sb = t[4 + k] * fabs(t[4 + k]);          // signed squares: one compare each side
         pos = pos && !(sa < -thr) && !(sb < -thr);
         neg = neg && !(sa > thr) && !(sb > thr);
     }
     if (!(pos || neg)) return 0;
-    const double inv = 1.0 / (sqrt(n2) + delta);
-    const D3 V = d3(c.x * inv, c.y * inv, c.z * inv);
+    const double bound = 0.5e-8 * (sqrt(n2) + delta);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const double ra = rint(d3_dot(V, A[k]) * 1e8), rb = rint(d3_dot(V, B[k]) * 1e8);     // np.round(., 8): sign of rint(1e8 x)
-        pos = pos && (ra >= 0.0) && (rb >= 0.0);
-        neg = neg && (ra <= 0.0) && (rb <= 0.0);
+    for (int k = 0; k < 8; ++k) {
+        pos = pos && (t[k] >= -bound);
+        neg = neg && (t[k] <= bound);
     }
     return (pos ? 1 : 0) | (neg ? 2 : 0);
 }

@@ -440,3 +440,26 @@ def test_sph2pob_legacy_golden(hostsim):
     assert abs(hs_aligned(hostsim, 6, g["b1"][i:i + 1], g["b2"][i:i + 1])[0] - 0.0545) < 2e-3
     np.testing.assert_allclose(hs_aligned(hostsim, 6, g["kat_b1"], g["kat_b2"]), g["kat_iou"], atol=5e-6)
     np.testing.assert_allclose(g["kat_iou"], [0.232635, 0.333749, 0.617413, 0.138463, 0.286415, 0.203624, 0.554315], atol=2e-6)
+
+
+@pytest.mark.parametrize("box", ["bfov", "rbfov"])
+def test_unbiased_iou_near_coincident_pairs(hostsim, box):
+    """The vertex test of unbiased_iou_pair works on t_k = c . N_k against 0.5e-8 (|c| + delta) instead of the reference's
+    round(V . N_k, 8) >= 0 on the normalised vector: the two can only differ where the reference itself is decided by
+    rounding noise.  Identical, integer-valued and slightly perturbed pairs (where boundary circles nearly coincide) against
+    the restatement, which follows the reference's arithmetic."""
+    import os
+    import sys
+    import torch
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import sph_oracle as O
+    n = 3000
+    for scale in (0.0, 1e-4, 1e-2, 1.0):
+        b1 = O.generate_boxes(n, alpha_range=(0.5, 120), beta_range=(0.5, 120), box=box, seed=7)
+        b2 = (b1 + torch.randn_like(b1) * scale).clamp(min=0.2)
+        b2[:, 0].clamp_(0, 360); b2[:, 1].clamp_(0, 180); b2[:, 2:4].clamp_(max=179.5)
+        b1[:500], b2[:500] = b1[:500].round(), b2[:500].round()          # integer annotations: jitter_1's mask fires
+        want = O.unbiased_iou(b1, b2, is_aligned=True).numpy()
+        err = np.abs(hs_aligned(hostsim, 5, b1.numpy(), b2.numpy()) - want)
+        assert (err > 1e-6).sum() <= 1, (scale, np.where(err > 1e-6)[0][:10], err.max())
