@@ -23,6 +23,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define SPHK_HD __host__ __device__ __forceinline__
@@ -746,25 +747,43 @@ SPHK_HD void unbiased_normals(double theta, double phi, double fx, double fy, do
 // root: t_k < 0 and t_k^2 > 1e-16 |c|^2 + 2e-36 implies -t_k > 0.7e-8 |c| + 1e-18 > 0.5e-8 (|c| + 1e-10).
 // A[4], B[4]: the normals of the two boxes (any order: the test is an AND over all eight).
 // Returns bit 0: V counts, bit 1: -V counts.
+// (The comparisons are written as sign bits of a sum, OR-ed together as integers: a chain of `x < y` on doubles against
+// one threshold is turned by the compiler into a running fmin / fmax, which costs ~9 instructions per element on sm_100a.)
+SPHK_HD int d_hi(double x) {
+#if defined(__CUDA_ARCH__)
+    return __double2hiint(x);
+#else
+    long long b;
+    memcpy(&b, &x, sizeof b);
+    return (int)(b >> 32);
+#endif
+}
+
 SPHK_HD int unbiased_candidate(const D3& c, double delta, const D3* A, const D3* B, bool want_neg) {
     const double n2 = d3_dot(c, c), thr = 1e-16 * n2 + 2e-36;
     double t[8];
-    bool pos = true, neg = want_neg;
+    int below = 0, above = 0;               // sign bit set: some t_k |t_k| < -thr  /  some t_k |t_k| > thr
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         t[k] = d3_dot(c, A[k]);
         t[4 + k] = d3_dot(c, B[k]);
-        const double sa = t[k] * fabs(t[k]), sb = t[4 + k] * fabs(t[4 + k]);          // signed squares: one compare each side
-        pos = pos && !(sa < -thr) && !(sb < -thr);
-        neg = neg && !(sa > thr) && !(sb > thr);
     }
-    if (!(pos || neg)) return 0;
-    const double bound = 0.5e-8 * (sqrt(n2) + delta);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        pos = pos && (t[k] >= -bound);
-        neg = neg && (t[k] <= bound);
+        below |= d_hi(fma(t[k], fabs(t[k]), thr));
+        above |= d_hi(fma(-t[k], fabs(t[k]), thr));
     }
+    bool pos = below >= 0, neg = want_neg && above >= 0;
+    if (!(pos || neg)) return 0;
+    const double bound = 0.5e-8 * (sqrt(n2) + delta);
+    below = 0; above = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        below |= d_hi(t[k] + bound);        // t_k < -bound
+        above |= d_hi(bound - t[k]);        // t_k >  bound
+    }
+    pos = pos && below >= 0;
+    neg = neg && above >= 0;
     return (pos ? 1 : 0) | (neg ? 2 : 0);
 }
 
