@@ -400,6 +400,23 @@ def other_configs(torch, native, dev, flush, hbm_peak_gbs=6544.3):
     calc = SphOverlaps2D('sph2pob_efficient_iou', 5)
     ms = quick(torch, lambda: calc(gts.view(-1, 5), anchors).view(IMAGES, GTS, -1), flush=flush)
     out["assign_16img_one_call"] = {"ms": ms, "pairs_per_s": IMAGES * GTS * anchors.size(0) / ms * 1e3}
+    # the headline step (one call per image) with the 16 calls alternating between two CUDA streams: the drain of one
+    # launch (its last CTAs, ~a quarter of a 31 us kernel) is covered by the start of the next
+    s2 = [torch.cuda.Stream(), torch.cuda.Stream()]
+
+    def two_streams():
+        cur = torch.cuda.current_stream()
+        for st in s2:
+            st.wait_stream(cur)
+        keep = []
+        for i in range(IMAGES):
+            with torch.cuda.stream(s2[i & 1]):
+                keep.append(calc(gts[i], anchors))
+        for st in s2:
+            cur.wait_stream(st)
+        return keep
+    ms = quick(torch, two_streams, flush=flush)
+    out["assign_16img_per_image_calls_two_streams"] = {"ms": ms, "pairs_per_s": IMAGES * GTS * anchors.size(0) / ms * 1e3}
     # the consumer of configs[1]: MaxIoUAssigner(pos 0.5, neg 0.3, min_pos 0) per image.  (a) the drop-in way:
     # matrix from the calculator + assign_wrt_overlaps on it; (b) SphMaxIoUAssigner: no matrix, two fused passes
     from sph_retina_b200.sphdet.assigners import SphMaxIoUAssigner
