@@ -403,6 +403,23 @@ def golden_legacy_loss(R):
     np.savez_compressed(os.path.join(OUT, "legacy_loss.npz"), **out)
 
 
+def golden_planar_nms(R):
+    """PlanarNMS (planar_nms.py:7-18; test_cfg.iou_calculator = 'planar') on the BFoV boxes of golden_naive: the reference's
+    class on top of the restated mmcv batched_nms; class-agnostic (its default) and per class, two thresholds."""
+    g = np.load(os.path.join(OUT, "naive.npz"))
+    boxes, scores, idxs = (torch.from_numpy(g["bfov_" + k]) for k in ("boxes", "scores", "idxs"))
+    out = {}
+    for thr in (0.3, 0.5):
+        for tag, kw in (("agnostic", {}), ("per_class", dict(class_agnostic=False))):
+            dets, keep = R.PlanarNMS()(boxes.clone(), scores.clone(), idxs, dict(type="nms", iou_threshold=thr), **kw)
+            out["keep_%s_thr%d" % (tag, int(thr * 10))] = _np(keep)
+            out["dets_%s_thr%d" % (tag, int(thr * 10))] = _np(dets)
+    dets, keep = R.PlanarNMS()(boxes.clone(), scores.clone(), idxs, dict(type="nms", iou_threshold=0.5, max_num=40, score_threshold=0.2))
+    out["keep_max40_score02"] = _np(keep)
+    np.savez_compressed(os.path.join(OUT, "planar_nms.npz"), **out)
+    print("planar nms", {k: len(v) for k, v in out.items() if k.startswith("keep")})
+
+
 def golden_nms(R):
     out = {}
     for box in ("bfov", "rbfov"):
@@ -493,3 +510,4 @@ if __name__ == "__main__":
     golden_unbiased(R)
     golden_legacy(R)
     golden_legacy_loss(R)
+    golden_planar_nms(R)

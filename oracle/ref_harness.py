@@ -105,7 +105,7 @@ def load_reference():
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     import sph_oracle as _so
     mmcv_ops.bbox_overlaps = _so.mmcv_bbox_overlaps
-    mmcv_ops.batched_nms = _unavailable
+    mmcv_ops.batched_nms = _so.mmcv_batched_nms      # published mmcv 1.6.0 algorithm restated (unpinned at that boundary)
     mmcv.ops = mmcv_ops
     mmcv.jit = lambda *a, **k: (lambda f: f)
     sys.modules.setdefault("mmcv", mmcv)
@@ -160,6 +160,10 @@ def load_reference():
     nms_pkg.__path__ = [os.path.join(REFERENCE_ROOT, "sphdet", "bbox", "nms")]
     sys.modules["sphdet.bbox.nms"] = nms_pkg
     sph_nms = importlib.import_module("sphdet.bbox.nms.sph_nms")
+    try:
+        planar_nms = importlib.import_module("sphdet.bbox.nms.planar_nms")
+    except Exception:
+        planar_nms = None
 
     # losses: exec obb_iou_loss / OBBIoULoss with the in-tree weighted_loss (mmdet/models/losses/utils.py)
     losses_utils = _load_mmdet_loss_utils()
@@ -241,7 +245,7 @@ def load_reference():
         sph2pob_standard_iou=api.sph2pob_standard_iou,
         sph2pob_legacy_iou=api.sph2pob_legacy_iou,
         sph_iou=api.sph_iou, fov_iou=api.fov_iou, naive_iou=api.naive_iou, unbiased_iou=api.unbiased_iou,
-        SphOverlaps2D=calc.SphOverlaps2D, SphNMS=sph_nms.SphNMS,
+        SphOverlaps2D=calc.SphOverlaps2D, SphNMS=sph_nms.SphNMS, PlanarNMS=getattr(planar_nms, 'PlanarNMS', None),
         Sph2PobIoULoss=iou_loss.Sph2PobIoULoss, SphIoULossLegacy=iou_loss.SphIoULossLegacy,
         Sph2PobGDLoss=gd_loss.Sph2PobGDLoss, Sph2PobKFLoss=kf_loss.Sph2PobKFLoss, Sph2PobL1Loss=l1_loss.Sph2PobL1Loss,
         jiter_spherical_bboxes=api.jiter_spherical_bboxes,

@@ -505,6 +505,58 @@ def mmcv_bbox_overlaps(b1, b2, mode="iou", aligned=False, offset=0):
     return inter / base.clamp(min=offset)
 
 
+def mmcv_nms(boxes, scores, iou_threshold, offset=0, score_threshold=0, max_num=-1):
+    """mmcv-full 1.6.0 ``nms`` (mmcv/ops/nms.py: NMSop.forward + nms; kernel nms_cuda_kernel.cuh -- parity UNPINNED at that
+    boundary, published algorithm restated): drop scores <= score_threshold, visit by descending score, suppress a box iff
+    inter / (a1 + a2 - inter) > iou_threshold against a kept one.  Returns (dets [k, 5] score-descending, keep [k])."""
+    index = None
+    if score_threshold > 0:
+        index = (scores > score_threshold).nonzero(as_tuple=False).view(-1)
+        boxes, scores = boxes[index], scores[index]
+    order = torch.argsort(scores, descending=True, stable=True)
+    b = boxes[order]
+    area = (b[:, 2] - b[:, 0] + offset) * (b[:, 3] - b[:, 1] + offset)
+    alive = torch.ones(b.size(0), dtype=torch.bool)
+    kept = []
+    for i in range(b.size(0)):
+        if not alive[i]:
+            continue
+        kept.append(i)
+        w = (torch.min(b[i, 2], b[i + 1:, 2]) - torch.max(b[i, 0], b[i + 1:, 0]) + offset).clamp(min=0)
+        h = (torch.min(b[i, 3], b[i + 1:, 3]) - torch.max(b[i, 1], b[i + 1:, 1]) + offset).clamp(min=0)
+        inter = w * h
+        alive[i + 1:] &= ~(inter / (area[i] + area[i + 1:] - inter) > iou_threshold)
+    keep = order[torch.tensor(kept, dtype=torch.long)]
+    if max_num > 0:
+        keep = keep[:max_num]
+    dets = torch.cat([boxes[keep], scores[keep, None]], dim=1)
+    return dets, (keep if index is None else index[keep])
+
+
+def mmcv_batched_nms(boxes, scores, idxs, nms_cfg, class_agnostic=False):
+    """mmcv-full 1.6.0 ``batched_nms`` (mmcv/ops/nms.py) for nms_cfg type 'nms' below split_thr: classes are separated by
+    shifting every box by label * (max coordinate + 1)."""
+    if nms_cfg is None:
+        scores, inds = scores.sort(descending=True)
+        return torch.cat([boxes[inds], scores[:, None]], -1), inds
+    cfg = dict(nms_cfg)
+    class_agnostic = cfg.pop("class_agnostic", class_agnostic)
+    if class_agnostic:
+        boxes_for_nms = boxes
+    else:
+        boxes_for_nms = boxes + (idxs.to(boxes) * (boxes.max() + 1))[:, None]
+    assert cfg.pop("type", "nms") == "nms"
+    assert boxes.size(0) < cfg.pop("split_thr", 10000), "the per-class loop of mmcv above split_thr is not restated"
+    dets, keep = mmcv_nms(boxes_for_nms, scores, **cfg)
+    return torch.cat([boxes[keep], dets[:, -1:]], -1), keep
+
+
+def planar_nms(boxes, scores, idxs, nms_cfg, class_agnostic=True):
+    """PlanarNMS('sph2pix') (sphdet/bbox/nms/planar_nms.py:7-18)."""
+    dets_, keep = mmcv_batched_nms(sph2pix(boxes), scores, idxs, nms_cfg, class_agnostic)
+    return torch.cat([boxes[keep], dets_[:, -1:]], dim=-1), keep
+
+
 def sph2pix(boxes, img_size=(512, 1024)):
     """Sph2PlanarBoxTransform('sph2pix') (box_formator.py:79-87,176-193): xyxy for BFoV, (x, y, w, h, -gamma rad) for RBFoV."""
     img_h, img_w = img_size

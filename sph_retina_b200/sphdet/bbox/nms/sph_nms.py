@@ -131,6 +131,45 @@ class SphNMS:
         return sph_batched_nms(boxes, scores, idxs, nms_cfg, self.iou_calculator, class_agnostic)
 
 
+class PlanarNMS:
+    """sphdet/bbox/nms/planar_nms.py:7-18 -- what the head uses when ``test_cfg.iou_calculator == 'planar'``
+    (sph_retina_head.py:89-90): the boxes read as planar (x1, y1, x2, y2) boxes of the 512 x 1024 image
+    (``Sph2PlanarBoxTransform('sph2pix')``) and mmcv's ``batched_nms`` of type 'nms' on them.  That is the suppression rule
+    of ``SphNMS('naive_iou')`` for BFoV boxes (IoU = inter / (a1 + a2 - inter), suppress iff IoU > thr), class-agnostic by
+    default (planar_nms.py:11) -- so it runs in the same NMS kernel with one segment per image, or one per label when
+    ``class_agnostic`` is False (mmcv's coordinate-offset trick separates the classes exactly)."""
+
+    def __init__(self, box_formator='sph2pix'):
+        if box_formator != 'sph2pix':
+            raise NotImplementedError("PlanarNMS: only box_formator='sph2pix' (the reference's default) has a kernel")
+        self.box_formator = box_formator
+
+    def __call__(self, boxes, scores, idxs, nms_cfg, class_agnostic=True):
+        if nms_cfg is None:                                   # mmcv batched_nms: no NMS, sorted by score
+            scores, inds = scores.sort(descending=True)
+            return torch.cat([boxes[inds], scores[:, None]], -1), inds
+        cfg = nms_cfg.copy()
+        class_agnostic = cfg.pop('class_agnostic', class_agnostic)
+        if cfg.pop('type', 'nms') != 'nms':
+            raise NotImplementedError("PlanarNMS: only mmcv's hard 'nms' has a kernel here")
+        if boxes.size(-1) != 4:
+            raise NotImplementedError("PlanarNMS: mmcv's nms takes (x1, y1, x2, y2): BFoV boxes only")
+        cfg.pop('split_thr', None)                            # (a batching detail of mmcv: same result either way)
+        thr = cfg.pop('iou_threshold', 0.5)
+        max_num = cfg.pop('max_num', -1)
+        score_thr = cfg.pop('score_threshold', 0)
+        index = None
+        if score_thr > 0:                                     # mmcv nms: boxes at or below the score threshold drop out first
+            index = (scores > score_thr).nonzero(as_tuple=False).view(-1)
+            boxes, scores, idxs = boxes[index], scores[index], idxs[index]
+        labels = torch.zeros_like(idxs) if class_agnostic else idxs
+        inner = dict(iou_threshold=thr)
+        if max_num > 0:
+            inner['max_num'] = max_num
+        dets, keep = sph_batched_nms(boxes, scores, labels, inner, 'naive_iou')
+        return dets, (keep if index is None else index[keep])
+
+
 def multiclass_nms(multi_bboxes, multi_scores, score_thr, nms_cfg, max_num=-1, score_factors=None,
                    return_inds=False, nms_op=None, box_version=4):
     """sphdet/bbox/nms/utils.py:6-95 (R-CNN heads) with ``nms_op`` defaulting to :class:`SphNMS`."""

@@ -13,7 +13,7 @@ from __future__ import annotations
 
 import torch
 
-from ...bbox.nms.sph_nms import SphNMS, sph_batched_nms_images, sph_nms_image_blocks
+from ...bbox.nms.sph_nms import PlanarNMS, SphNMS, sph_batched_nms_images, sph_nms_image_blocks
 
 
 def filter_scores_and_topk(scores, score_thr, topk, results=None):
@@ -68,7 +68,10 @@ def get_bboxes_single(cls_score_list, bbox_pred_list, mlvl_priors, bbox_coder, c
         return bboxes, scores, labels
     if bboxes.numel() == 0:
         return torch.cat([bboxes, scores[:, None]], -1), labels
-    nms = SphNMS(iou_calculator=_cfg_get(cfg, 'iou_calculator', 'sph2pob_efficient'))
+    if _cfg_get(cfg, 'iou_calculator', 'sph2pob_efficient') == 'planar':          # sph_retina_head.py:89-90
+        nms = PlanarNMS(box_formator=_cfg_get(cfg, 'box_formator', 'sph2pix'))
+    else:
+        nms = SphNMS(iou_calculator=_cfg_get(cfg, 'iou_calculator', 'sph2pob_efficient'))
     det_bboxes, keep = nms(bboxes, scores, labels, _cfg_get(cfg, 'nms'))
     max_per_img = _cfg_get(cfg, 'max_per_img', det_bboxes.size(0))
     return det_bboxes[:max_per_img], labels[keep][:max_per_img]
@@ -84,6 +87,9 @@ def get_bboxes_batch(cls_scores, bbox_preds, mlvl_priors, bbox_coder, cfg, box_v
     nms_cfg = _cfg_get(cfg, 'nms') or {}
     iou_thr = float(nms_cfg.get('iou_threshold', 0.5))
     iou_calc = _cfg_get(cfg, 'iou_calculator', 'sph2pob_efficient')      # test_cfg.iou_calculator (sph_retina_head.py:89-90)
+    if iou_calc == 'planar':                   # class-agnostic planar NMS per image: the per-image contract covers it
+        return [get_bboxes_single([c[b] for c in cls_scores], [p[b] for p in bbox_preds], mlvl_priors, bbox_coder, cfg,
+                                  box_version=box_version) for b in range(cls_scores[0].size(0))]
     SphNMS(iou_calc)                                                      # same refusals as the per-image path
     B, D = cls_scores[0].size(0), box_version
     sc, lb, dl, pr = [], [], [], []

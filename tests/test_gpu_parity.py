@@ -635,6 +635,26 @@ def test_naive_nms_golden_keep_sets(api, box):
         assert keep_sph.cpu().tolist() != g[box + "_keep_thr5"].tolist()
 
 
+def test_planar_nms_golden_keep_sets(api):
+    """PlanarNMS (test_cfg.iou_calculator = 'planar', planar_nms.py:7-18) against the keep lists of the reference's class:
+    class-agnostic (its default) and per class, max_num and score_threshold of mmcv's nms."""
+    g, base = load_golden("planar_nms"), load_golden("naive")
+    boxes, scores, idxs = cu(base["bfov_boxes"]), cu(base["bfov_scores"]), cu(base["bfov_idxs"])
+    iou = base["bfov_pair_iou_f64"]
+    from sph_retina_b200.sphdet.bbox.nms import PlanarNMS
+    for thr in (0.3, 0.5):
+        assert not (np.abs(iou - thr) < 1e-5).any(), "fixture has a pair on the threshold"
+        for tag, kw in (("agnostic", {}), ("per_class", dict(class_agnostic=False))):
+            dets, keep = PlanarNMS()(boxes, scores, idxs, dict(type="nms", iou_threshold=thr), **kw)
+            want = g["keep_%s_thr%d" % (tag, int(thr * 10))]
+            assert keep.cpu().tolist() == want.tolist()
+            np.testing.assert_allclose(dets.cpu().numpy(), g["dets_%s_thr%d" % (tag, int(thr * 10))], rtol=0, atol=0)
+    _, keep = PlanarNMS()(boxes, scores, idxs, dict(type="nms", iou_threshold=0.5, max_num=40, score_threshold=0.2))
+    assert keep.cpu().tolist() == g["keep_max40_score02"].tolist()
+    _, keep = PlanarNMS()(boxes, scores, idxs, None)
+    assert torch.equal(scores[keep], scores.sort(descending=True)[0])
+
+
 # ---- unbiased_iou (the exact spherical IoU; SphOverlaps2D's default backend) and SphNMS('unbiased_iou') ---------------
 @pytest.mark.parametrize("box", ["bfov", "rbfov"])
 def test_unbiased_iou_golden(api, box):

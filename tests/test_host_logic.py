@@ -218,3 +218,17 @@ def test_legacy_iou_loss_host_contract():
     assert LOSSES.get('SphIoULossLegacy') is SphIoULossLegacy
     with pytest.raises(AssertionError):
         L(torch.zeros(2, 4), torch.zeros(2, 4), reduction_override='max')
+
+
+def test_planar_nms_host_contract():
+    from sph_retina_b200.sphdet.bbox.nms import PlanarNMS
+    assert PlanarNMS().box_formator == 'sph2pix'
+    with pytest.raises(NotImplementedError):
+        PlanarNMS('sph2tan')
+    b = torch.rand(4, 5)
+    with pytest.raises(NotImplementedError):
+        PlanarNMS()(b, torch.rand(4), torch.zeros(4, dtype=torch.long), dict(type='nms', iou_threshold=0.5))      # RBFoV
+    with pytest.raises(NotImplementedError):
+        PlanarNMS()(b[:, :4], torch.rand(4), torch.zeros(4, dtype=torch.long), dict(type='soft_nms'))
+    dets, keep = PlanarNMS()(b[:, :4], torch.tensor([0.1, 0.9, 0.5, 0.3]), torch.zeros(4, dtype=torch.long), None)
+    assert keep.tolist() == [1, 2, 3, 0] and dets.shape == (4, 5)

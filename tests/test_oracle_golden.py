@@ -277,3 +277,19 @@ def test_restatement_legacy_iou_loss(box):
         np.testing.assert_allclose(el.detach().numpy(), g[key + "loss_f64"], atol=1e-8)
         np.testing.assert_allclose(p.grad.numpy(), g[key + "gpred_f64"], rtol=1e-6, atol=1e-7)
         np.testing.assert_allclose(t.grad.numpy(), g[key + "gtarget_f64"], rtol=1e-6, atol=1e-7)
+
+
+def test_restatement_planar_nms():
+    """oracle.planar_nms (PlanarNMS over the restated mmcv batched_nms) against the reference's class, and against the
+    independent route: per class it is the greedy NMS of SphNMS('naive_iou') on the same boxes."""
+    g, base = load_golden("planar_nms"), load_golden("naive")
+    boxes, scores, idxs = (torch.from_numpy(base["bfov_" + k]) for k in ("boxes", "scores", "idxs"))
+    for thr in (0.3, 0.5):
+        for tag, kw in (("agnostic", {}), ("per_class", dict(class_agnostic=False))):
+            dets, keep = O.planar_nms(boxes, scores, idxs, dict(type="nms", iou_threshold=thr), **kw)
+            assert keep.tolist() == g["keep_%s_thr%d" % (tag, int(thr * 10))].tolist()
+            np.testing.assert_array_equal(dets.numpy(), g["dets_%s_thr%d" % (tag, int(thr * 10))])
+        _, keep = O.nms_batched(boxes, scores, idxs, thr, iou_fn=lambda a, b: O.naive_iou(a, b))
+        assert keep.tolist() == g["keep_per_class_thr%d" % int(thr * 10)].tolist()
+    _, keep = O.planar_nms(boxes, scores, idxs, dict(type="nms", iou_threshold=0.5, max_num=40, score_threshold=0.2))
+    assert keep.tolist() == g["keep_max40_score02"].tolist()
