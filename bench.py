@@ -326,6 +326,17 @@ def other_configs(torch, native, dev, flush, hbm_peak_gbs=6544.3):
             ms = quick(torch, lambda: fn(u1, u2, is_aligned=True), iters=5, flush=flush)
             out["aligned_1M_%s_%s" % (name, box)] = {"ms": ms, "pairs_per_s": n / ms * 1e3}
     del u1, u2
+    # the format conversions either side of the path (sphdet/bbox/box_formator.py), one launch each, 16 M boxes (HBM-bound)
+    from sph_retina_b200.sphdet.bbox.box_formator import Planar2SphBoxTransform, Sph2PlanarBoxTransform
+    nb = 16_000_000
+    f4 = S.generate_boxes(nb, alpha_range=(1, 100), beta_range=(1, 100), box="bfov", seed=3).to(dev)
+    to_planar, to_sph = Sph2PlanarBoxTransform('sph2pix', 4), Planar2SphBoxTransform('pix2sph', 4)
+    ms = quick(torch, lambda: to_planar(f4), iters=5, flush=flush)
+    pl = to_planar(f4)
+    ms2 = quick(torch, lambda: to_sph(pl), iters=5, flush=flush)
+    out["box_format_16M_bfov"] = {"sph2planar_ms": ms, "planar2sph_ms": ms2, "hbm_gbs_sph2planar": nb * 32 / ms / 1e6,
+                                  "hbm_frac_of_measured_peak": nb * 32 / ms / 1e6 / hbm_peak_gbs}
+    del f4, pl
     native.set_dense(True)
     ms = quick(torch, lambda: sph2pob_efficient_iou(b1, b2, is_aligned=True), flush=flush)
     native.set_dense(False)

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SPHK_ABI_VERSION 4
+#define SPHK_ABI_VERSION 5
 
 enum sphk_status {
     SPHK_OK = 0,
@@ -226,6 +226,16 @@ int sphk_decode_loss_reduce(const float* anchors, const float* deltas, const flo
                             int weight_cols, int64_t n, int D, const float* means, const float* stds, float wh_ratio_clip,
                             int clip_border, int add_ctr_clamp, float ctr_clamp, float scale, float* partial,
                             float* grad_deltas, void* stream);
+
+/* Box format conversions either side of the IoU path (sphdet/bbox/box_formator.py), one launch, row-wise:
+ *   fmt  0 xyxy2xywh (:17-23)      1 xywh2xyxy (:25-31)       2 obb2hbb_wywh (:33-50, [n,5] -> [n,4])   3 obb2hbb_xyxy (:52-55)
+ *        4 bfov2rbfov (:57-61)     5 geo2sph (:64-68)         6 sph2geo (:70-74)                        7 sph2pix (:77-84)
+ *        8 pix2sph (:86-93)        9 sph2tan (:99-107)       10 tan2sph (:109-117)
+ *       11 / 12 Sph2PlanarBoxTransform('sph2pix' / 'sph2tan') (:166-182): [n,4] -> xyxy, [n,5] -> (x, y, w, h, -gamma rad)
+ *       13 / 14 Planar2SphBoxTransform(pix / tan) (:185-200): xyxy -> bfov [n,4] or rbfov [n,5] (gamma = 0)
+ *   in [n, d_in], out [n, d_out]; img_h, img_w: the equirectangular image size of the pix / tan formats ((512, 1024) in the
+ *   reference).  The pure-arithmetic formats are bit-identical to the reference's fp32 torch expressions. */
+int sphk_box_format(int fmt, const float* in, int64_t n, int d_in, int d_out, float img_h, float img_w, float* out, void* stream);
 
 /* Batched greedy spherical NMS (SphNMS / sph_batched_nms / sph_nms_op,
  * sphdet/bbox/nms/sph_nms.py:22-74).  kind: the IoU SphNMS was built with (sph_nms.py:8-16) -- SPHK_KIND_SPH2POB_EFFICIENT

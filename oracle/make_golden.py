@@ -420,6 +420,33 @@ def golden_planar_nms(R):
     print("planar nms", {k: len(v) for k, v in out.items() if k.startswith("keep")})
 
 
+def golden_box_format(R):
+    """sphdet/bbox/box_formator.py through the reference's own functions and classes (fp32, as the pipeline runs them)."""
+    bf = R.box_formator
+    torch.manual_seed(81)
+    sph4 = R.generate_boxes(1500, alpha_range=(0.5, 179), beta_range=(0.5, 179), dtype="float", box="bfov")
+    sph5 = R.generate_boxes(1500, alpha_range=(0.5, 179), beta_range=(0.5, 179), dtype="float", box="rbfov")
+    xywh = torch.rand(1500, 4) * torch.tensor([1024., 512., 300., 200.])
+    xyxy = bf.xywh2xyxy(xywh)
+    obb = torch.cat([torch.randn(1500, 2), torch.rand(1500, 2) * 3, (torch.rand(1500, 1) - 0.5) * 7], dim=1)
+    geo = torch.cat([torch.rand(1500, 1) * 360 - 180, torch.rand(1500, 1) * 180 - 90, torch.rand(1500, 3) * 90], dim=1)
+    out = dict(sph4=_np(sph4), sph5=_np(sph5), xywh=_np(xywh), xyxy=_np(xyxy), obb=_np(obb), geo=_np(geo))
+    out["xyxy2xywh"] = _np(bf.xyxy2xywh(xyxy)); out["xywh2xyxy"] = _np(xyxy)
+    out["obb2hbb_wywh"] = _np(bf.obb2hbb_wywh(obb)); out["obb2hbb_xyxy"] = _np(bf.obb2hbb_xyxy(obb))
+    out["bfov2rbfov"] = _np(bf.bfov2rbfov(sph4))
+    out["geo2sph_5"] = _np(bf.geo2sph(geo)); out["geo2sph_4"] = _np(bf.geo2sph(geo[:, :4].contiguous()))
+    out["sph2geo_5"] = _np(bf.sph2geo(sph5)); out["sph2geo_4"] = _np(bf.sph2geo(sph4))
+    for mode in ("sph2pix", "sph2tan"):
+        for size in ((512, 1024), (960, 1920)):
+            tag = "%s_%d" % (mode, size[0])
+            out["planar4_" + tag] = _np(bf.Sph2PlanarBoxTransform(mode, 4)(sph4, size))
+            out["planar5_" + tag] = _np(bf.Sph2PlanarBoxTransform(mode, 5)(sph5, size))
+            out["back4_" + tag] = _np(bf.Planar2SphBoxTransform(mode, 4)(xyxy, size))
+            out["back5_" + tag] = _np(bf.Planar2SphBoxTransform(mode, 5)(xyxy, size))
+    np.savez_compressed(os.path.join(OUT, "box_format.npz"), **out)
+    print("box_format", len(out))
+
+
 def golden_nms(R):
     out = {}
     for box in ("bfov", "rbfov"):
@@ -511,3 +538,4 @@ if __name__ == "__main__":
     golden_legacy(R)
     golden_legacy_loss(R)
     golden_planar_nms(R)
+    golden_box_format(R)

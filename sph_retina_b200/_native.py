@@ -20,7 +20,7 @@ EDGE = {"arc": 0, "chord": 1, "tangent": 2}
 ANGLE = {"equator": 0, "project": 1}
 
 SPHK_OK = 0
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 _c_float_p = ctypes.c_void_p  # raw device addresses
 _i64 = ctypes.c_int64
@@ -68,6 +68,7 @@ SIGNATURES = {
                                      ctypes.c_void_p]),
     "sphk_coder_encode": (_int, [_c_float_p, _c_float_p, _i64, _int, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float),
                                  _c_float_p, ctypes.c_void_p]),
+    "sphk_box_format": (_int, [_int, _c_float_p, _i64, _int, _int, ctypes.c_float, ctypes.c_float, _c_float_p, ctypes.c_void_p]),
     "sphk_decode_loss_partials": (_i64, [_i64]),
     "sphk_decode_loss_reduce": (_int, [_c_float_p, _c_float_p, _c_float_p, _c_float_p, _int, _i64, _int,
                                        ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), ctypes.c_float, _int, _int,
@@ -455,6 +456,29 @@ def coder_encode(proposals, gt, means=None, stds=None):
                                      _stream(proposals)))
     launches += 1
     return out
+
+
+BOX_FORMAT = {"xyxy2xywh": 0, "xywh2xyxy": 1, "obb2hbb_xywh": 2, "obb2hbb_xyxy": 3, "bfov2rbfov": 4, "geo2sph": 5, "sph2geo": 6,
+              "sph2pix": 7, "pix2sph": 8, "sph2tan": 9, "tan2sph": 10, "sph2planar_pix": 11, "sph2planar_tan": 12,
+              "planar2sph_pix": 13, "planar2sph_tan": 14}
+
+
+def box_format(fmt, boxes, d_out, img_size=(512, 1024)):
+    """One launch of k_box_format: boxes [n, d_in] float32 -> [n, d_out] (sphdet/bbox/box_formator.py conversions)."""
+    global launches
+    if not boxes.is_cuda:
+        raise SphkError("box_format: boxes must be a CUDA tensor (no CPU path)")
+    if boxes.dim() != 2 or boxes.size(1) not in (4, 5):
+        raise SphkError("box_format: boxes must be [n, 4] or [n, 5], got %s" % (tuple(boxes.shape),))
+    b = boxes.detach()
+    if b.dtype != torch.float32 or not b.is_contiguous():
+        b = b.float().contiguous()
+    out = torch.empty((b.size(0), d_out), dtype=torch.float32, device=b.device)
+    with _on_device(b.device):
+        _check(lib.sphk_box_format(BOX_FORMAT[fmt], _ptr(b), b.size(0), b.size(1), int(d_out), float(img_size[0]), float(img_size[1]),
+                                   _ptr(out), _stream(b)))
+    launches += 1
+    return out if out.dtype == boxes.dtype else out.to(boxes.dtype)
 
 
 def decode_loss_reduce(anchors, deltas, target, weight, scale, want_grad=True, means=None, stds=None, wh_ratio_clip=16 / 1000,

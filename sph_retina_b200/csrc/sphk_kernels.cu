@@ -22,6 +22,7 @@
 
 #include "../../include/sphk.h"
 #include "sphk_coder.cuh"
+#include "sphk_format.cuh"
 #include "sphk_fast.cuh"
 #include "sphk_grad.cuh"
 #include "sphk_math.cuh"
@@ -1100,6 +1101,38 @@ k_coder_decode(const float* __restrict__ rois, const float* __restrict__ deltas,
     store_grad<D>(out, i, v, vec_ok);
 }
 
+// ---- box format conversions (sphdet/bbox/box_formator.py): one thread per row ---------------------------------------
+__global__ void __launch_bounds__(kThreads) k_box_format(const float* __restrict__ in, int64_t n, int fmt, int d_in, int d_out,
+                                                          float img_h, float img_w, float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    float a[5], b[5];
+    for (int k = 0; k < d_in; ++k) a[k] = in[i * d_in + k];
+    box_format_row(fmt, a, d_in, b, d_out, img_h, img_w);
+    for (int k = 0; k < d_out; ++k) out[i * d_out + k] = b[k];
+}
+
+// four-column rows in and out (every format between planar and spherical BFoV boxes): 16-byte loads and stores, four rows
+// per thread with the four loads issued before the first use (HBM-bound: what keeps enough bytes in flight per SM)
+__global__ void __launch_bounds__(kThreads) k_box_format4(const float4* __restrict__ in, int64_t n, int fmt, float img_h, float img_w,
+                                                           float4* __restrict__ out) {
+    const int64_t base = (int64_t)blockIdx.x * (kThreads * 4) + threadIdx.x;
+    float4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int64_t i = base + (int64_t)k * kThreads;
+        v[k] = (i < n) ? __ldg(in + i) : make_float4(0.0f, 0.0f, 1.0f, 1.0f);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int64_t i = base + (int64_t)k * kThreads;
+        const float a[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+        float b[4];
+        box_format_row(fmt, a, 4, b, 4, img_h, img_w);
+        if (i < n) out[i] = make_float4(b[0], b[1], b[2], b[3]);
+    }
+}
+
 template <int D>
 __global__ void __launch_bounds__(kThreads)
 k_coder_encode(const float* __restrict__ proposals, const float* __restrict__ gt, int64_t n, CoderParams cp,
@@ -2086,6 +2119,25 @@ int sphk_coder_decode_bwd(const float* rois, const float* deltas, const float* g
     if (n > 0 && !grad_out) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_coder_decode_bwd: null grad_out");
     return coder_decode_impl(rois, deltas, grad_out, n, D, means, stds, wh_ratio_clip, clip_border, add_ctr_clamp, ctr_clamp,
                              grad_deltas, stream);
+}
+
+int sphk_box_format(int fmt, const float* in, int64_t n, int d_in, int d_out, float img_h, float img_w, float* out, void* stream) {
+    if (fmt < 0 || fmt >= FMT_COUNT) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_box_format: unknown format");
+    if (n < 0) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_box_format: n < 0");
+    const bool planar2sph = (fmt == FMT_PLANAR2SPH_PIX || fmt == FMT_PLANAR2SPH_TAN);
+    const bool keeps = (fmt == FMT_GEO2SPH || fmt == FMT_SPH2GEO || fmt == FMT_SPH2PLANAR_PIX || fmt == FMT_SPH2PLANAR_TAN);
+    if ((d_in != 4 && d_in != 5) || (d_out != 4 && d_out != 5)) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_box_format: columns must be 4 or 5");
+    if (keeps ? (d_out != d_in) : (d_in != box_format_cols_in(fmt, d_out) || (!planar2sph && d_out != box_format_cols_out(fmt, d_in))))
+        return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_box_format: column counts do not fit the format");
+    if (!(img_h > 0.0f) || !(img_w > 0.0f)) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_box_format: image size must be positive");
+    if (n == 0) return SPHK_OK;
+    if (!in || !out) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_box_format: null pointer");
+    if (d_in == 4 && d_out == 4 && aligned16(in) && aligned16(out))
+        k_box_format4<<<blocks_for((n + 3) / 4), kThreads, 0, (cudaStream_t)stream>>>((const float4*)in, n, fmt, img_h, img_w, (float4*)out);
+    else
+        k_box_format<<<blocks_for(n), kThreads, 0, (cudaStream_t)stream>>>(in, n, fmt, d_in, d_out, img_h, img_w, out);
+    SPHK_LAUNCH_CHECK("k_box_format");
+    return SPHK_OK;
 }
 
 int sphk_coder_encode(const float* proposals, const float* gt, int64_t n, int D, const float* means, const float* stds,

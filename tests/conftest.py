@@ -128,3 +128,16 @@ def check_other_loss(name, g, loss, gpred, gtarget, identical_rows=16):
         assert good.mean() > 0.99, (name, key, (~good).sum())
         assert np.median(rel) < 3e-6, (name, key, np.median(rel))
         assert (rel > 1e-4).sum() < 0.5 * (rel32 > 1e-4).sum(), (name, key)
+
+
+BOX_FORMAT_CASES = [   # (format id, input key, d_out, golden key, image size, exact)
+    (0, "xyxy", 4, "xyxy2xywh", (512, 1024), True), (1, "xywh", 4, "xywh2xyxy", (512, 1024), True),
+    (2, "obb", 4, "obb2hbb_wywh", (512, 1024), False), (3, "obb", 4, "obb2hbb_xyxy", (512, 1024), False),
+    (4, "sph4", 5, "bfov2rbfov", (512, 1024), True),
+    (5, "geo", 5, "geo2sph_5", (512, 1024), True), (6, "sph5", 5, "sph2geo_5", (512, 1024), True), (6, "sph4", 4, "sph2geo_4", (512, 1024), True),
+    (11, "sph4", 4, "planar4_sph2pix_512", (512, 1024), True), (11, "sph5", 5, "planar5_sph2pix_512", (512, 1024), True),
+    (11, "sph4", 4, "planar4_sph2pix_960", (960, 1920), True), (11, "sph5", 5, "planar5_sph2pix_960", (960, 1920), True),
+    (12, "sph4", 4, "planar4_sph2tan_512", (512, 1024), False), (12, "sph5", 5, "planar5_sph2tan_960", (960, 1920), False),
+    (13, "xyxy", 4, "back4_sph2pix_512", (512, 1024), True), (13, "xyxy", 5, "back5_sph2pix_960", (960, 1920), True),
+    (14, "xyxy", 4, "back4_sph2tan_512", (512, 1024), False), (14, "xyxy", 5, "back5_sph2tan_960", (960, 1920), False),
+]

@@ -5,6 +5,7 @@
 #include "../../sph_retina_b200/csrc/sphk_math.cuh"
 #include "../../sph_retina_b200/csrc/sphk_fast.cuh"
 #include "../../sph_retina_b200/csrc/sphk_coder.cuh"
+#include "../../sph_retina_b200/csrc/sphk_format.cuh"
 #ifdef SPHK_WITH_GRAD
 #include "../../sph_retina_b200/csrc/sphk_grad.cuh"
 #include "../../sph_retina_b200/csrc/sphk_obbloss.cuh"
@@ -203,4 +204,13 @@ void hostsim_obb_loss(int kind, int fun, int flags, float tau, float alpha, floa
 }
 
 #endif
+void hostsim_box_format(int fmt, const float* in, long n, int d_in, int d_out, float img_h, float img_w, float* out) {
+    for (long i = 0; i < n; ++i) {
+        float a[5], b[5];
+        for (int k = 0; k < d_in; ++k) a[k] = in[i * d_in + k];
+        box_format_row(fmt, a, d_in, b, d_out, img_h, img_w);
+        for (int k = 0; k < d_out; ++k) out[i * d_out + k] = b[k];
+    }
+}
+
 }  // extern "C"

@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol(built_lib):
     for name in declared_symbols():
         assert hasattr(lib, name), "libsphk.so does not export %s" % name
     lib.sphk_abi_version.restype = ctypes.c_int
-    assert lib.sphk_abi_version() == 4
+    assert lib.sphk_abi_version() == 5
 
 
 def test_binding_covers_the_header(built_lib):
@@ -59,6 +59,10 @@ def test_argument_validation_needs_no_gpu(built_lib):
     assert lib.sphk_iou_aligned(6, None, None, 10, 5, 0, 0, 0, None, None) == -3          # sph2pob_legacy_iou: BFoV only
     assert lib.sphk_iou_aligned(7, None, None, 10, 4, 0, 0, 0, None, None) == -1          # unknown kind
     assert lib.sphk_loss_fwd_bwd(None, None, 5, 4, None, None, None, None, None) == -1  # null boxes
+    assert lib.sphk_box_format(15, None, 0, 4, 4, 512.0, 1024.0, None, None) == -1        # unknown format
+    assert lib.sphk_box_format(2, None, 0, 4, 4, 512.0, 1024.0, None, None) == -1         # obb2hbb takes 5 columns
+    assert lib.sphk_box_format(11, None, 0, 5, 5, 512.0, 1024.0, None, None) == 0         # empty is fine
+    assert lib.sphk_box_format(13, None, 3, 4, 5, 512.0, 1024.0, None, None) == -1        # null pointers
 
 
 def test_sass_is_sm100a(built_lib):

@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import (ROOT, check_other_loss, degenerate_pairs, grad_rows_ok, load_golden, other_loss_variants,
+from conftest import (BOX_FORMAT_CASES, ROOT, check_other_loss, degenerate_pairs, grad_rows_ok, load_golden, other_loss_variants,
                       within)
 
 pytestmark = pytest.mark.gpu
@@ -688,6 +688,32 @@ def test_unbiased_nms_golden_keep_sets(api, box):
         want = g["%s_keep_thr%d" % (box, int(thr * 10))].tolist()
         _, keep = api.nms.SphNMS('unbiased_iou')(boxes, scores, idxs, dict(type="nms", iou_threshold=thr, max_num=120))
         assert keep.cpu().tolist() == want
+
+
+# ---- box format conversions either side of the path (sphdet/bbox/box_formator.py) ----------------------------------------
+def test_box_format_golden(api):
+    from sph_retina_b200.sphdet.bbox import box_formator as bf
+    g = load_golden("box_format")
+    for fmt, key, d_out, want_key, size, exact in BOX_FORMAT_CASES:
+        names = {v: k for k, v in api.native.BOX_FORMAT.items()}
+        got = api.native.box_format(names[fmt], cu(g[key]), d_out, size).cpu().numpy()
+        if exact:
+            assert np.array_equal(got, g[want_key]), (want_key, np.abs(got - g[want_key]).max())
+        else:
+            np.testing.assert_allclose(got, g[want_key], rtol=1e-4, atol=1e-4, err_msg=want_key)   # tan(alpha / 2) near 180 degrees
+    # the reference's names and classes
+    sph4, sph5, xyxy = cu(g["sph4"]), cu(g["sph5"]), cu(g["xyxy"])
+    assert np.array_equal(bf.Sph2PlanarBoxTransform('sph2pix')(sph4).cpu().numpy(), g["planar4_sph2pix_512"])
+    assert np.array_equal(bf.Sph2PlanarBoxTransform('sph2pix', 5)(sph5, (960, 1920)).cpu().numpy(), g["planar5_sph2pix_960"])
+    assert np.array_equal(bf.Planar2SphBoxTransform('pix2sph', 5)(xyxy, (960, 1920)).cpu().numpy(), g["back5_sph2pix_960"])
+    assert np.array_equal(bf.xyxy2xywh(xyxy).cpu().numpy(), g["xyxy2xywh"]) and np.array_equal(bf.bfov2rbfov(sph4).cpu().numpy(), g["bfov2rbfov"])
+    assert np.array_equal(bf.geo2sph(cu(g["geo"])).cpu().numpy(), g["geo2sph_5"]) and np.array_equal(bf.sph2geo(sph4).cpu().numpy(), g["sph2geo_4"])
+    np.testing.assert_allclose(bf.obb2hbb_xyxy(cu(g["obb"])).cpu().numpy(), g["obb2hbb_xyxy"], rtol=2e-6, atol=2e-5)
+    assert bf.is_valid_boxes(sph4) and not bf.is_valid_boxes(sph4 + 400) and bf.xywh2xyxy(xyxy[:0]).shape == (0, 4)
+    # round trip and no mutation of the input
+    before = sph4.clone()
+    back = bf.Planar2SphBoxTransform()(bf.Sph2PlanarBoxTransform()(sph4))
+    assert torch.equal(sph4, before) and float((back - sph4).abs().max()) < 2e-4
 
 
 # ---- sph2pob_legacy_iou (the reference's first transform; BFoV only) ----------------------------------------------------

@@ -9,7 +9,7 @@ import ctypes
 import numpy as np
 import pytest
 
-from conftest import (check_other_loss, degenerate_pairs, grad_rows_ok, load_golden, other_loss_kernel_args,
+from conftest import (BOX_FORMAT_CASES, check_other_loss, degenerate_pairs, grad_rows_ok, load_golden, other_loss_kernel_args,
                       other_loss_variants, within)
 
 fp = ctypes.POINTER(ctypes.c_float)
@@ -463,3 +463,21 @@ def test_unbiased_iou_near_coincident_pairs(hostsim, box):
         want = O.unbiased_iou(b1, b2, is_aligned=True).numpy()
         err = np.abs(hs_aligned(hostsim, 5, b1.numpy(), b2.numpy()) - want)
         assert (err > 1e-6).sum() <= 1, (scale, np.where(err > 1e-6)[0][:10], err.max())
+
+
+def test_box_format_golden(hostsim):
+    """box_format_row (csrc/sphk_format.cuh) against the reference's box_formator functions / classes: the pure-arithmetic
+    formats bit for bit, the ones through tan / atan / sin / cos to 1e-4 (libm against torch's vectorised kernels)."""
+    g = load_golden("box_format")
+    for fmt, key, d_out, want_key, size, exact in BOX_FORMAT_CASES:
+        x = np.ascontiguousarray(g[key], np.float32)
+        if fmt == 5 and d_out == 4:
+            x = np.ascontiguousarray(x[:, :4])
+        out = np.empty((len(x), d_out), np.float32)
+        hostsim.hostsim_box_format(fmt, x.ctypes.data_as(fp), ctypes.c_long(len(x)), x.shape[1], d_out, ctypes.c_float(size[0]),
+                                   ctypes.c_float(size[1]), out.ctypes.data_as(fp))
+        want = g[want_key]
+        if exact:
+            assert np.array_equal(out, want), (want_key, np.abs(out - want).max())
+        else:
+            np.testing.assert_allclose(out, want, rtol=1e-4, atol=1e-4, err_msg=want_key)   # tan(alpha / 2) near alpha = 180 amplifies an ulp 200 x
