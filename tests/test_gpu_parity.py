@@ -668,6 +668,9 @@ def test_unbiased_iou_golden(api, box):
     assert mat.shape == (23, 201) and (np.abs(mat.cpu().numpy() - g[box + "_rc_f64"]) > 1e-5).sum() <= 2
     flat = api.iou.unbiased_iou(b1[:23].repeat_interleave(201, 0), b2[:201].repeat(23, 1), is_aligned=True)
     assert torch.equal(mat.reshape(-1), flat)
+    rmax, rarg, cmax, carg = api.iou.sph_max_overlaps(b1[:23], b2[:201], backend='unbiased_iou')     # fused max / argmax, no matrix
+    assert torch.equal(rmax, mat.max(dim=1)[0]) and torch.equal(cmax, mat.max(dim=0)[0])
+    assert torch.equal(mat[torch.arange(23), rarg.long()], rmax) and torch.equal(mat[carg.long(), torch.arange(201)], cmax)
     # against the oracle on fresh seeded boxes
     x = O.generate_boxes(4000, alpha_range=(2, 150), beta_range=(2, 150), box=box, seed=5)
     y = (x + torch.randn_like(x) * 10).clamp(min=1)
@@ -1111,6 +1114,31 @@ def test_head_post_processing_batch_and_single(api, D):
     again = get_bboxes_batch(cls_d, reg_d, pri_d, coder, cfg, box_version=D)
     assert again[1][0].shape == (0, D + 1) and again[1][1].numel() == 0
     assert torch.equal(again[0][0], batch[0][0]) and torch.equal(again[2][1], batch[2][1])
+
+
+@pytest.mark.parametrize("calc", ["naive_iou", "unbiased_iou", "planar"])
+def test_head_post_processing_other_calculators(api, calc):
+    """test_cfg.iou_calculator = 'naive_iou' (indoor360), 'unbiased_iou' (pandora) and 'planar' (PlanarNMS): the whole-batch
+    pipeline equals the per-image contract, and the per-image result equals decode + the calculator's own NMS class."""
+    from sph_retina_b200.sphdet.bbox.coder import DeltaXYWHSphBBoxCoder
+    from sph_retina_b200.sphdet.bbox.nms import PlanarNMS, SphNMS
+    from sph_retina_b200.sphdet.models.heads import get_bboxes_batch, get_bboxes_single
+    B, C, D = 2, 5, 4
+    cls, reg, priors = _head_outputs(B, C, D, seed=11)
+    cfg = dict(nms_pre=120, score_thr=0.05, nms=dict(type="nms", iou_threshold=0.5), max_per_img=50, iou_calculator=calc)
+    coder = DeltaXYWHSphBBoxCoder(target_stds=(0.1, 0.1, 0.2, 0.2))
+    cls_d, reg_d, pri_d = [t.to(DEV) for t in cls], [t.to(DEV) for t in reg], [t.to(DEV) for t in priors]
+    batch = get_bboxes_batch(cls_d, reg_d, pri_d, coder, cfg, box_version=D)
+    for b in range(B):
+        det, lab = get_bboxes_single([t[b] for t in cls_d], [t[b] for t in reg_d], pri_d, coder, cfg, box_version=D)
+        assert 5 < det.size(0) <= 50 and det.shape == batch[b][0].shape
+        np.testing.assert_allclose(batch[b][0].cpu().numpy(), det.cpu().numpy(), rtol=0, atol=1e-6)
+        assert torch.equal(batch[b][1], lab)
+        boxes, scores, labels = get_bboxes_single([t[b] for t in cls_d], [t[b] for t in reg_d], pri_d, coder, cfg, box_version=D,
+                                                  with_nms=False)
+        nms = PlanarNMS() if calc == "planar" else SphNMS(calc)
+        want, keep = nms(boxes, scores, labels, cfg["nms"])
+        assert torch.equal(det, want[:50]) and torch.equal(lab, labels[keep][:50])
 
 
 # ---- full-size property checks (BASELINE.json configs) --------------------------------------------
