@@ -5,12 +5,19 @@ maths regressions; the GPU suite (tests/test_gpu_parity.py) repeats the checks t
 Parity criterion: |kernel - reference fp64| <= 1e-5, or the kernel is at least as
 close to the fp64 run as the reference's own fp32 run on that element."""
 import ctypes
+import os
+import sys
 
 import numpy as np
 import pytest
+import torch
 
+from conftest import ROOT
 from conftest import (BOX_FORMAT_CASES, check_other_loss, degenerate_pairs, grad_rows_ok, load_golden, other_loss_kernel_args,
                       other_loss_variants, within)
+
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import sph_oracle as O  # noqa: E402  (the checker the device maths is compared with where no golden vector exists)
 
 fp = ctypes.POINTER(ctypes.c_float)
 
@@ -395,12 +402,6 @@ def test_unbiased_iou_clear_rejection_is_exact(hostsim, box):
     shortcut must never change a result: random unrelated pairs (mostly disjoint), wide boxes up to the 180-degree clamp,
     boxes at the poles, across the 0/360 seam and touching side by side, against the restatement (which evaluates
     round(V . N, 8) >= 0 for all 40 candidates of every pair)."""
-    import os
-    import sys
-    import torch
-    from conftest import ROOT
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import sph_oracle as O
     n = 6000
     b1 = O.generate_boxes(n, alpha_range=(1, 179.9), beta_range=(1, 179.9), box=box, seed=31)
     b2 = O.generate_boxes(n, alpha_range=(1, 179.9), beta_range=(1, 179.9), box=box, seed=32)
@@ -448,12 +449,6 @@ def test_unbiased_iou_near_coincident_pairs(hostsim, box):
     round(V . N_k, 8) >= 0 on the normalised vector: the two can only differ where the reference itself is decided by
     rounding noise.  Identical, integer-valued and slightly perturbed pairs (where boundary circles nearly coincide) against
     the restatement, which follows the reference's arithmetic."""
-    import os
-    import sys
-    import torch
-    from conftest import ROOT
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import sph_oracle as O
     n = 3000
     for scale in (0.0, 1e-4, 1e-2, 1.0):
         b1 = O.generate_boxes(n, alpha_range=(0.5, 120), beta_range=(0.5, 120), box=box, seed=7)
