@@ -19,7 +19,7 @@ fi
 for k in $kernels; do
     python tools/run_kernel.py $k > $out/plain_$k.log 2>&1 || { echo "plain $k failed"; continue; }
     ncu --set full --import-source on --clock-control none \
-        -k regex:"k_iou_aligned2|k_iou_pairwise2|k_iou_rows32|k_loss|k_nms|k_decode_loss|k_obb_loss|k_box_format" -s 3 -c 1 -o $out/prof_${k}_$tag -f \
+        -k regex:"k_iou_aligned2|k_iou_pairwise2|k_iou_rows32|k_loss|k_nms|k_decode_loss|k_obb_loss|k_box_format|k_approx_aligned4" -s 3 -c 1 -o $out/prof_${k}_$tag -f \
         python tools/run_kernel.py $k > $out/ncu_$k.log 2>&1 || echo "ncu $k failed"
 done
 ls -la $out | grep $tag

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Launches one hot-path kernel a few times on BASELINE-shaped synthetic input (for ncu captures).
-    python tools/run_kernel.py aligned|aligned5|loss|gdloss|nms|nms_agnostic|nms_pipeline|sweep|assign|assigner|headloss|format [--iters 5]"""
+    python tools/run_kernel.py aligned|aligned5|loss|gdloss|nms|nms_agnostic|nms_pipeline|sweep|assign|assigner|headloss|format|approx [--iters 5]"""
 import argparse
 import os
 import sys
@@ -62,6 +62,11 @@ elif a.which == "gdloss":
     def fn():
         p = pred.detach().requires_grad_(True)
         LG(p, target).backward()
+elif a.which == "approx":
+    from sph_retina_b200.sphdet.iou import sph_iou
+    c1 = S.generate_boxes(16_000_000, alpha_range=(1, 100), beta_range=(1, 100), box="bfov", seed=0).to(dev)
+    c2 = S.generate_boxes(16_000_000, alpha_range=(1, 100), beta_range=(1, 100), box="bfov", seed=1).to(dev)
+    fn = lambda: sph_iou(c1, c2, is_aligned=True)
 elif a.which == "format":
     from sph_retina_b200.sphdet.bbox.box_formator import Sph2PlanarBoxTransform
     sph = S.generate_boxes(1 << 24, alpha_range=(1, 100), beta_range=(1, 100), box="bfov", seed=0).to(dev)
