@@ -640,7 +640,42 @@ SPHK_HD float sph2pob_legacy_iou_pair(const RawBox& b1, const RawBox& b2, int mo
 }
 
 // ---- Sph-IoU / FoV-IoU (approximate_ious.py:3-55 behind sph_iou_api.py:130-177) -------
-SPHK_HD float approx_iou_pair(const RawBox& b1, const RawBox& b2, int kind) {
+// Everything after jitter_1: dt = theta_p - theta_g (degrees, already moved by -/+360 where |dtheta| > 180),
+// pgd / ppd = the two phi (degrees), dpd = phi_p - phi_g (degrees), the four extents in degrees.
+// A product that feeds a sum of two products stays a rounded product (mul_keep): which of the two the compiler would
+// contract into an FMA otherwise depends on the code around the inlined copy, and the aligned and N x M kernels must
+// return the same bits for the same pair.
+#if defined(__CUDA_ARCH__)
+SPHK_HD float mul_keep(float a, float b) { return __fmul_rn(a, b); }
+#else
+SPHK_HD float mul_keep(float a, float b) { return a * b; }
+#endif
+
+SPHK_HD float approx_iou_tail(float dt, float pgd, float ppd, float dpd, float gad, float gbd, float pad, float pbd,
+                              int kind) {
+    const float pg = kHalfPi - pgd * kDeg2Rad, pp = kHalfPi - ppd * kDeg2Rad;
+    const float dphi = mul_keep(-dpd, kDeg2Rad);   // pp - pg
+    const float ag = mul_keep(gad, kDeg2Rad), bg = mul_keep(gbd, kDeg2Rad), ap = mul_keep(pad, kDeg2Rad), bp = mul_keep(pbd, kDeg2Rad);
+    const float dtr = mul_keep(dt, kDeg2Rad);
+    // overlaps are translation invariant: measure everything relative to box 1's centre
+    float lo, hi;
+    if (kind == KIND_SPH) {
+        lo = fmaxf(-0.5f * ag, dtr - 0.5f * ap);
+        hi = fminf(0.5f * ag, dtr + 0.5f * ap);
+    } else {
+        const float delta = mul_keep(dtr, cosf(0.5f * (pg + pp)));
+        lo = fmaxf(-0.5f * ag, delta - 0.5f * ap);
+        hi = fminf(0.5f * ag, delta + 0.5f * ap);
+    }
+    const float plo = fmaxf(-0.5f * bg, dphi - 0.5f * bp);
+    const float phi = fminf(0.5f * bg, dphi + 0.5f * bp);
+    const float inter = mul_keep(fmaxf(hi - lo, 0.0f), fmaxf(phi - plo, 0.0f));
+    const float iou = inter / (fmaf(ag, bg, mul_keep(ap, bp)) - inter + 1e-8f);
+    return clampf(iou, 0.0f, 1.0f);
+}
+
+// The pair as jitter_1 leaves it in general: shifted where two columns are within eps, clamped at the range ends.
+SPHK_HD float approx_iou_pair_general(const RawBox& b1, const RawBox& b2, int kind) {
     const bool m = jitter1_mask(b1, b2, 4);
     const JitBox g = jitter1_role1(b1, m, 4), p = jitter1_role2(b2, m, 4);
     const float dlo = p.t_lo - g.t_lo;
@@ -649,25 +684,33 @@ SPHK_HD float approx_iou_pair(const RawBox& b1, const RawBox& b2, int kind) {
     // i.e. the difference moves by -/+360.  (360 - hi) is exact, so the small result is too.
     if (dt > 180.0f) dt = -(g.t_hi + (360.0f - p.t_hi)) + dlo;
     else if (dt < -180.0f) dt = (p.t_hi + (360.0f - g.t_hi)) + dlo;
-    const float pg = kHalfPi - (g.p_hi + g.p_lo) * kDeg2Rad, pp = kHalfPi - (p.p_hi + p.p_lo) * kDeg2Rad;
-    const float dphi = -((p.p_hi - g.p_hi) + (p.p_lo - g.p_lo)) * kDeg2Rad;   // pp - pg
-    const float ag = g.a * kDeg2Rad, bg = g.b * kDeg2Rad, ap = p.a * kDeg2Rad, bp = p.b * kDeg2Rad;
-    const float dtr = dt * kDeg2Rad;
-    // overlaps are translation invariant: measure everything relative to box 1's centre
-    float lo, hi;
-    if (kind == KIND_SPH) {
-        lo = fmaxf(-0.5f * ag, dtr - 0.5f * ap);
-        hi = fminf(0.5f * ag, dtr + 0.5f * ap);
-    } else {
-        const float delta = dtr * cosf(0.5f * (pg + pp));
-        lo = fmaxf(-0.5f * ag, delta - 0.5f * ap);
-        hi = fminf(0.5f * ag, delta + 0.5f * ap);
-    }
-    const float plo = fmaxf(-0.5f * bg, dphi - 0.5f * bp);
-    const float phi = fminf(0.5f * bg, dphi + 0.5f * bp);
-    const float inter = fmaxf(hi - lo, 0.0f) * fmaxf(phi - plo, 0.0f);
-    const float iou = inter / (ag * bg + ap * bp - inter + 1e-8f);
-    return clampf(iou, 0.0f, 1.0f);
+    return approx_iou_tail(dt, g.p_hi + g.p_lo, p.p_hi + p.p_lo, (p.p_hi - g.p_hi) + (p.p_lo - g.p_lo), g.a, g.b, p.a, p.b,
+                           kind);
+}
+
+// True when jitter_1 is the identity on this pair: no two columns within eps (no shift) and no coordinate inside
+// the clamp zone of either role (jit_coord with shift 0: below = raw < lo_off, above = (raw - end) > hi_off; both
+// are monotonic in raw, so the four columns are tested through their min / max).  A NaN column fails every
+// comparison in jit_coord and is skipped by fminf / fmaxf here: it passes through unclamped on both paths.
+SPHK_HD bool jitter1_is_identity4(const RawBox& x, const RawBox& y) {
+    const bool m = jitter1_mask(x, y, 4);
+    const float xlo = fminf(fminf(x.t, x.p), fminf(x.a, x.b)), ylo = fminf(fminf(y.t, y.p), fminf(y.a, y.b));
+    const float xhi = fmaxf(fmaxf(x.p, x.a), x.b), yhi = fmaxf(fmaxf(y.p, y.a), y.b);
+    const bool c1 = (xlo < kEps2) | ((x.t - 360.0f) > -kEps) | ((xhi - 180.0f) > -kEps);     // role of bboxes1
+    const bool c2 = (ylo < kEps) | ((y.t - 360.0f) > -kEps2) | ((yhi - 180.0f) > -kEps2);     // role of bboxes2
+    return !(m | c1 | c2);
+}
+
+// Nearly every pair of a real workload is untouched by jitter_1; the hi + lo bookkeeping of the general form is
+// ~110 of its ~180 instructions.  With every lo = 0 and every hi = raw the general expressions reduce to the ones
+// below up to the sign of a zero, which no later operation observes: the two paths return the same bits
+// (tests/test_hostsim_math.py::test_approx_identity_path_is_bit_identical).
+SPHK_HD float approx_iou_pair(const RawBox& b1, const RawBox& b2, int kind) {
+    if (!jitter1_is_identity4(b1, b2)) return approx_iou_pair_general(b1, b2, kind);
+    float dt = b2.t - b1.t;
+    if (dt > 180.0f) dt = -(b1.t + (360.0f - b2.t));
+    else if (dt < -180.0f) dt = b2.t + (360.0f - b1.t);
+    return approx_iou_tail(dt, b1.p, b2.p, b2.p - b1.p, b1.a, b1.b, b2.a, b2.b, kind);
 }
 
 // ---- naive_iou (sph_iou_api.py:181-198) -------------------------------------------------------------------------

@@ -33,6 +33,16 @@ void hostsim_iou_aligned(int kind, const float* b1, const float* b2, long P, int
     }
 }
 
+// Sph-IoU / FoV-IoU through the general jitter_1 form only (hi + lo bookkeeping for every pair) and, in path[i], whether
+// approx_iou_pair takes its identity shortcut on that pair -- to check that the shortcut returns the same bits.
+void hostsim_approx_general(int kind, const float* b1, const float* b2, long P, float* out, unsigned char* path) {
+    for (long i = 0; i < P; ++i) {
+        const RawBox x = load_box(b1, i, 4), y = load_box(b2, i, 4);
+        out[i] = approx_iou_pair_general(x, y, kind);
+        path[i] = jitter1_is_identity4(x, y) ? 1 : 0;
+    }
+}
+
 // The N x M formulation (csrc/sphk_fast.cuh): per-box precompute, prefilter, fast path with fallback.
 // path[i] (optional): 0 = prefilter said disjoint, 1 = fast path, 2 = reference-order path.
 void hostsim_iou_aligned_v2(int kind, const float* b1, const float* b2, long P, int D, int mode, int edge, float* out,

@@ -73,6 +73,47 @@ def test_sph_fov(hostsim):
         assert np.abs(got - g[k + "_f64"]).max() < 2e-6
 
 
+def test_approx_identity_path_is_bit_identical(hostsim):
+    """approx_iou_pair skips the hi + lo jitter bookkeeping where jitter_1 is the identity; it must return the bits of
+    the general form on every pair: random boxes, boxes across the seam, and boxes on / next to the clamp zones and
+    within eps of each other (where the shortcut must NOT be taken: path 0)."""
+    rng = np.random.default_rng(7)
+    n = 400_000
+    def boxes(n):
+        return np.stack([rng.uniform(0, 360, n), rng.uniform(0, 180, n), rng.uniform(1, 100, n), rng.uniform(1, 100, n)], 1).astype(np.float32)
+    b1, b2 = boxes(n), boxes(n)
+    # wrap cases: thetas on opposite sides of the seam
+    b1[:50_000, 0] = rng.uniform(0, 30, 50_000); b2[:50_000, 0] = rng.uniform(330, 360, 50_000)
+    b1[50_000:100_000, 0] = rng.uniform(330, 360, 50_000); b2[50_000:100_000, 0] = rng.uniform(0, 30, 50_000)
+    # clamp zones and range ends of every column, both roles
+    eps = np.float32(1e-4 * 1.2345678)
+    ends = {0: 360.0, 1: 180.0, 2: 180.0, 3: 180.0}
+    k = 100_000
+    for col, end in ends.items():
+        for b in (b1, b2):
+            idx = rng.integers(k, 2 * k, 3000)
+            b[idx, col] = rng.choice([0.0, 1e-5, eps, 2 * eps, 3 * eps, np.nextafter(eps, np.float32(1)), np.nextafter(2 * eps, np.float32(0)),
+                                      end, end - eps, end - 2 * eps, end - 3 * eps, np.nextafter(np.float32(end), np.float32(0)), -0.0, -1.0, end + 1],
+                                     3000).astype(np.float32)
+    # near-equal columns (the similarity mask): copies, copies moved by less / more than eps, integer-valued boxes
+    j = slice(2 * k, 2 * k + 60_000)
+    b2[j] = b1[j]
+    b2[2 * k + 20_000:2 * k + 40_000] += rng.uniform(-2, 2, (20_000, 4)).astype(np.float32) * eps
+    b1[2 * k + 40_000:2 * k + 60_000] = np.round(b1[2 * k + 40_000:2 * k + 60_000])
+    b2[2 * k + 40_000:2 * k + 60_000] = np.round(b1[2 * k + 40_000:2 * k + 60_000] + rng.integers(-3, 4, (20_000, 4)))
+    # non-finite columns pass through both forms alike
+    b1[-20:, 1] = np.nan; b2[-40:-20, 2] = np.inf
+    u8 = ctypes.POINTER(ctypes.c_ubyte)
+    for kind in (2, 3):
+        got = hs_aligned(hostsim, kind, b1, b2)
+        ref, path = np.empty(n, np.float32), np.empty(n, np.uint8)
+        hostsim.hostsim_approx_general(kind, b1.ctypes.data_as(fp), b2.ctypes.data_as(fp), ctypes.c_long(n), ref.ctypes.data_as(fp),
+                                       path.ctypes.data_as(u8))
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), int((got.view(np.uint32) != ref.view(np.uint32)).sum())
+        assert path[:k].mean() > 0.99 and 0 < path[k:].mean() < 1          # both branches exercised
+        assert path[2 * k:2 * k + 20_000].sum() == 0                        # identical boxes never take the shortcut
+
+
 def test_known_answers(hostsim):
     g = load_golden("kat")
     for kind, name in ((0, "sph2pob_efficient_iou"), (1, "sph2pob_standard_iou"), (2, "sph_iou"), (3, "fov_iou")):
