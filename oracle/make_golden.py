@@ -523,6 +523,42 @@ def golden_coder(R):
     np.savez_compressed(os.path.join(OUT, "coder.npz"), **out)
 
 
+def golden_distance_coder(R):
+    """DistancePointSphBBoxCoder (sphdet/bbox/coder/distance_point_sph_bbox_coder.py): points of the FCOS strides on the
+    512 x 1024 image, distances that leave the image on some rows; decode with and without the border clamp, 4 and 5
+    columns, the gradient of a weighted sum of the decoded boxes w.r.t. the distances, encode of the decoded boxes with
+    and without max_dis, a second image size."""
+    torch.manual_seed(11)
+    out = {}
+    n = 1000
+    for tag, shape in (("512", (512, 1024)), ("960", (960, 1920))):
+        H, W = shape
+        stride = torch.tensor([8., 16., 32., 64., 128.])[torch.randint(0, 5, (n,))]
+        pts = torch.stack([torch.floor(torch.rand(n) * W / stride) * stride + torch.floor(stride / 2),
+                           torch.floor(torch.rand(n) * H / stride) * stride + torch.floor(stride / 2)], 1)
+        dist = torch.rand(n, 4) * stride[:, None] * 6
+        dist[:100] *= 8                                        # far outside the image: the clamp is active
+        dist[100:130] = 0                                      # zero-size boxes
+        gamma = torch.rand(n, 1) * 180 - 90
+        wsum = torch.randn(n, 4)
+        out["points_" + tag], out["dist_" + tag], out["gamma_" + tag], out["w_" + tag] = _np(pts), _np(dist), _np(gamma), _np(wsum)
+        for D in (4, 5):
+            coder = R.DistancePointSphBBoxCoder(box_version=D, img_shape=shape if tag == "960" else None)
+            d = dist if D == 4 else torch.cat([dist, gamma], 1)
+            for clip, ms in (("clip", shape), ("noclip", None)):
+                dd = d.clone().requires_grad_(True)
+                dec = coder.decode(pts, dd, max_shape=ms, img_shape=shape)
+                (dec[:, :4] * wsum).sum().backward()
+                out["decode%d_%s_%s" % (D, clip, tag)] = _np(dec)
+                out["decode%d_%s_%s_grad" % (D, clip, tag)] = _np(dd.grad)
+                for md_tag, md in (("nomax", None), ("max", 64.0)):
+                    out["encode%d_%s_%s_%s" % (D, clip, md_tag, tag)] = _np(coder.encode(pts, dec.detach(), max_dis=md, img_shape=shape))
+        nob = R.DistancePointSphBBoxCoder(clip_border=False)
+        out["decode4_clip_border_false_" + tag] = _np(nob.decode(pts, dist, max_shape=shape, img_shape=shape))
+    np.savez_compressed(os.path.join(OUT, "distance_coder.npz"), **out)
+    print("distance coder", len(out), "arrays")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     R = rh.load_reference()
@@ -539,3 +575,4 @@ if __name__ == "__main__":
     golden_legacy_loss(R)
     golden_planar_nms(R)
     golden_box_format(R)
+    golden_distance_coder(R)

@@ -235,6 +235,13 @@ def load_reference():
     coder4 = _load_file("_ref_coder_bfov", "sphdet/bbox/coder/delta_xywh_sph_bbox_coder.py")
     coder5 = _load_file("_ref_coder_rbfov", "sphdet/bbox/coder/delta_xywha_rsph_bbox_coder.py")
 
+    # the anchor-free heads' coder imports ..box_formator relatively: load it under its package name (the package's
+    # __init__ pulls in the Kent coder and scipy, so the file is loaded by path)
+    dist_coder = None
+    if getattr(box_formator, "__file__", None):
+        dist_coder = _load_file("sphdet.bbox.coder.distance_point_sph_bbox_coder",
+                                "sphdet/bbox/coder/distance_point_sph_bbox_coder.py")
+
     gen = _load_file("_ref_generate_data", "tests/utils/generate_data.py")
 
     ns = types.SimpleNamespace(
@@ -251,7 +258,8 @@ def load_reference():
         jiter_spherical_bboxes=api.jiter_spherical_bboxes,
         jiter_rotated_bboxes=api.jiter_rotated_bboxes,
         DeltaXYWHSphBBoxCoder=coder4.DeltaXYWHSphBBoxCoder, DeltaXYWHASphBBoxCoder=coder5.DeltaXYWHASphBBoxCoder,
-        coder4=coder4, coder5=coder5,
+        coder4=coder4, coder5=coder5, dist_coder=dist_coder,
+        DistancePointSphBBoxCoder=getattr(dist_coder, 'DistancePointSphBBoxCoder', None),
     )
     _LOADED = ns
     return ns

@@ -757,6 +757,34 @@ def delta2bbox(rois, deltas, means=None, stds=None, wh_ratio_clip=16 / 1000, cli
     return b
 
 
+# ---- the anchor-free heads' coder (sphdet/bbox/coder/distance_point_sph_bbox_coder.py:72-162) ----------------------------
+def distance2bbox(points, distance, max_shape=None, img_shape=(512, 1024)):
+    """:72-127 (two-dimensional input): pixel box from the point and the four distances, optional border clamp, then
+    xyxy2xywh (box_formator.py:17-23) and _pix2sph_box_transform (:85-92); a fifth column is handed through."""
+    x1, y1 = points[:, 0] - distance[:, 0], points[:, 1] - distance[:, 1]
+    x2, y2 = points[:, 0] + distance[:, 2], points[:, 1] + distance[:, 3]
+    if max_shape is not None:
+        x1, x2 = x1.clamp(min=0, max=max_shape[1]), x2.clamp(min=0, max=max_shape[1])
+        y1, y2 = y1.clamp(min=0, max=max_shape[0]), y2.clamp(min=0, max=max_shape[0])
+    img_h, img_w = img_shape
+    x, y, w, h = (x1 + x2) / 2, (y1 + y2) / 2, x2 - x1, y2 - y1
+    cols = [(x / img_w) * 360, (y / img_h) * 180, (w / img_w) * 360, (h / img_h) * 180]
+    if distance.size(-1) == 5:
+        cols.append(distance[:, 4])
+    return torch.stack(cols, dim=-1)
+
+
+def bbox2distance(points, bbox, max_dis=None, eps=0.1, img_shape=(512, 1024)):
+    """:130-162: the box's sph2pix corners (sph2pix above) measured from the point, clamped to [0, max_dis - eps]."""
+    xyxy = sph2pix(bbox[:, :4], img_shape)
+    cols = [points[:, 0] - xyxy[:, 0], points[:, 1] - xyxy[:, 1], xyxy[:, 2] - points[:, 0], xyxy[:, 3] - points[:, 1]]
+    if max_dis is not None:
+        cols = [c.clamp(min=0, max=max_dis - eps) for c in cols]
+    if bbox.size(-1) == 5:
+        cols.append(bbox[:, 4])
+    return torch.stack(cols, dim=-1)
+
+
 def decode_iou_loss(anchors, deltas, target, weight=None, avg_factor=None, mode="iou", reduction="mean", loss_weight=1.0,
                     **coder):
     """What the head does with reg_decoded_bbox=True (sphdet/models/heads/sph_retina_head.py:252-265):

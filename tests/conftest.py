@@ -141,3 +141,37 @@ BOX_FORMAT_CASES = [   # (format id, input key, d_out, golden key, image size, e
     (13, "xyxy", 4, "back4_sph2pix_512", (512, 1024), True), (13, "xyxy", 5, "back5_sph2pix_960", (960, 1920), True),
     (14, "xyxy", 4, "back4_sph2tan_512", (512, 1024), False), (14, "xyxy", 5, "back5_sph2tan_960", (960, 1920), False),
 ]
+
+
+def check_distance_coder(coder_mod, dev):
+    """DistancePointSphBBoxCoder against tests/golden/distance_coder.npz (the reference's class through
+    oracle/make_golden.py::golden_distance_coder): decode bit for bit with / without the border clamp, 4 and 5 columns, two
+    image sizes; its gradient w.r.t. the distances; encode with / without max_dis; clip_border=False; empty input."""
+    import torch
+    g = load_golden("distance_coder")
+    T = lambda k: torch.from_numpy(g[k]).to(dev)
+    for tag, shape in (("512", (512, 1024)), ("960", (960, 1920))):
+        pts, dist, gamma, wsum = T("points_" + tag), T("dist_" + tag), T("gamma_" + tag), T("w_" + tag)
+        for D in (4, 5):
+            coder = coder_mod.DistancePointSphBBoxCoder(box_version=D, img_shape=shape if tag == "960" else None)
+            d = dist if D == 4 else torch.cat([dist, gamma], 1)
+            for clip, ms in (("clip", shape), ("noclip", None)):
+                dd = d.clone().requires_grad_(True)
+                dec = coder.decode(pts, dd, max_shape=ms, img_shape=shape)
+                assert dec.shape == (len(pts), D)
+                assert torch.equal(dec.detach(), T("decode%d_%s_%s" % (D, clip, tag))), (D, clip, tag)
+                (dec[:, :4] * wsum).sum().backward()
+                want = T("decode%d_%s_%s_grad" % (D, clip, tag))
+                assert float((dd.grad - want).abs().max()) <= 1e-6 * float(want.abs().max()), (D, clip, tag)
+                assert torch.equal(dd.grad == 0, want == 0)                  # clamped rows: exactly no gradient
+                for md_tag, md in (("nomax", None), ("max", 64.0)):
+                    enc = coder.encode(pts, dec.detach(), max_dis=md, img_shape=shape)
+                    assert torch.equal(enc, T("encode%d_%s_%s_%s" % (D, clip, md_tag, tag))), (D, clip, md_tag, tag)
+        nob = coder_mod.DistancePointSphBBoxCoder(clip_border=False)
+        assert torch.equal(nob.decode(pts, dist, max_shape=shape, img_shape=shape), T("decode4_clip_border_false_" + tag))
+    coder = coder_mod.DistancePointSphBBoxCoder()
+    e2, e4 = torch.zeros(0, 2, device=dev), torch.zeros(0, 4, device=dev)
+    assert coder.decode(e2, e4, max_shape=(512, 1024)).shape == (0, 4) and coder.encode(e2, e4).shape == (0, 4)
+    import pytest
+    with pytest.raises(AssertionError):
+        coder.decode(pts, torch.cat([dist, gamma], 1))                       # box_version 4 coder, five columns

@@ -1169,3 +1169,10 @@ def test_config5_sweep_slice(api, c_oracle):
     want = c_oracle_aligned(c_oracle, 0, np.repeat(rows, 1024, axis=0), np.tile(G.cpu().numpy(), (64, 1))).reshape(64, 1024)
     got = api.iou.sph2pob_efficient_iou(A[12345:12345 + 64], G).cpu().numpy()
     assert np.abs(got - want).max() < 1e-5
+
+
+def test_distance_point_coder_golden(api):
+    """DistancePointSphBBoxCoder (sphdet/bbox/coder/distance_point_sph_bbox_coder.py) through sphk_box_format."""
+    from conftest import check_distance_coder
+    from sph_retina_b200.sphdet.bbox.coder import distance_point_sph_bbox_coder as M
+    check_distance_coder(M, DEV)

@@ -517,3 +517,20 @@ def test_box_format_golden(hostsim):
             assert np.array_equal(out, want), (want_key, np.abs(out - want).max())
         else:
             np.testing.assert_allclose(out, want, rtol=1e-4, atol=1e-4, err_msg=want_key)   # tan(alpha / 2) near alpha = 180 amplifies an ulp 200 x
+
+
+def test_distance_point_coder_golden(hostsim, monkeypatch):
+    """The product's DistancePointSphBBoxCoder host code with the box-format launch replaced by the same row function built
+    for the host (hostsim_box_format = csrc/sphk_format.cuh): what the GPU suite checks through the C ABI, on the CPU."""
+    from conftest import check_distance_coder
+    from sph_retina_b200 import _native
+    from sph_retina_b200.sphdet.bbox.coder import distance_point_sph_bbox_coder as M
+
+    def host_box_format(fmt, boxes, d_out, img_size=(512, 1024)):
+        x = np.ascontiguousarray(boxes.detach().numpy(), np.float32)
+        out = np.empty((len(x), d_out), np.float32)
+        hostsim.hostsim_box_format(_native.BOX_FORMAT[fmt], x.ctypes.data_as(fp), ctypes.c_long(len(x)), x.shape[1], d_out,
+                                   ctypes.c_float(img_size[0]), ctypes.c_float(img_size[1]), out.ctypes.data_as(fp))
+        return torch.from_numpy(out)
+    monkeypatch.setattr(_native, "box_format", host_box_format)
+    check_distance_coder(M, "cpu")

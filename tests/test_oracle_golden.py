@@ -293,3 +293,18 @@ def test_restatement_planar_nms():
         assert keep.tolist() == g["keep_per_class_thr%d" % int(thr * 10)].tolist()
     _, keep = O.planar_nms(boxes, scores, idxs, dict(type="nms", iou_threshold=0.5, max_num=40, score_threshold=0.2))
     assert keep.tolist() == g["keep_max40_score02"].tolist()
+
+
+def test_restatement_distance_point_coder():
+    """distance2bbox / bbox2distance against the reference's DistancePointSphBBoxCoder, bit for bit."""
+    g = load_golden("distance_coder")
+    T = lambda k: torch.from_numpy(g[k])
+    for tag, shape in (("512", (512, 1024)), ("960", (960, 1920))):
+        pts = T("points_" + tag)
+        for D in (4, 5):
+            d = T("dist_" + tag) if D == 4 else torch.cat([T("dist_" + tag), T("gamma_" + tag)], 1)
+            for clip, ms in (("clip", shape), ("noclip", None)):
+                dec = O.distance2bbox(pts, d, ms, shape)
+                assert torch.equal(dec, T("decode%d_%s_%s" % (D, clip, tag)))
+                for md_tag, md in (("nomax", None), ("max", 64.0)):
+                    assert torch.equal(O.bbox2distance(pts, dec, md, 0.1, shape), T("encode%d_%s_%s_%s" % (D, clip, md_tag, tag)))
