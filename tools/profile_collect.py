@@ -18,8 +18,9 @@ for a, b in (("bench_%s.json" % tag, "bench_%s.json" % tag), ("bench_ref_%s.json
              ("launches_%s.csv" % tag, "ncu_launches_%s.csv" % tag)):
     if os.path.isfile(os.path.join(src, a)):
         shutil.copy(os.path.join(src, a), os.path.join(dst, b))
-traffic = {}
-kernels = ["aligned", "aligned5", "assign", "sweep", "loss", "nms", "nms_pipeline", "assigner", "headloss", "gdloss"]
+tpath = os.path.join(dst, "traffic.json")
+traffic = {k: v for k, v in (json.load(open(tpath)) if os.path.isfile(tpath) else {}).items() if k != "source"}
+kernels = ["aligned", "aligned5", "assign", "sweep", "loss", "nms", "nms_pipeline", "assigner", "headloss", "gdloss", "format", "approx"]
 for k in kernels:
     rep = os.path.join(src, "prof_%s_%s.ncu-rep" % (k, tag))
     if not os.path.isfile(rep):
@@ -40,7 +41,7 @@ for k in kernels:
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     traffic[k] = float(r[rd].replace(",", "")) * scale.get(units[rd], 1.0) + float(r[wr].replace(",", "")) * scale.get(units[wr], 1.0)
     kern = {"aligned": "k_iou_aligned2", "aligned5": "k_iou_aligned2", "assign": "k_iou_rows32", "sweep": "k_iou_pairwise2",
-            "loss": "k_loss", "nms": "k_nms", "nms_pipeline": "k_nms", "assigner": "k_iou_pairwise2", "headloss": "k_decode_loss", "gdloss": "k_obb_loss"}[k]
+            "loss": "k_loss", "nms": "k_nms", "nms_pipeline": "k_nms", "assigner": "k_iou_pairwise2", "headloss": "k_decode_loss", "gdloss": "k_obb_loss", "format": "k_box_format4", "approx": "k_approx_aligned4"}[k]
     if k in ("aligned", "assign", "sweep", "headloss"):
         hot = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_hotspots.py"), rep,
                               os.path.join(ROOT, "sph_retina_b200", "_lib", "libsphk.so"), kern, "--top", "45"], capture_output=True, text=True).stdout

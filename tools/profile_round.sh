@@ -7,7 +7,7 @@ set -u
 tag=${1:-r01}
 mode=${2:-bench}
 shift; shift
-kernels=${*:-aligned aligned5 assign sweep loss gdloss nms nms_pipeline assigner headloss}
+kernels=${*:-aligned aligned5 assign sweep loss gdloss nms nms_pipeline assigner headloss format approx}
 out=gpurun_out
 mkdir -p $out
 if [ "$mode" = bench ]; then
