@@ -232,3 +232,17 @@ def test_planar_nms_host_contract():
         PlanarNMS()(b[:, :4], torch.rand(4), torch.zeros(4, dtype=torch.long), dict(type='soft_nms'))
     dets, keep = PlanarNMS()(b[:, :4], torch.tensor([0.1, 0.9, 0.5, 0.3]), torch.zeros(4, dtype=torch.long), None)
     assert keep.tolist() == [1, 2, 3, 0] and dets.shape == (4, 5)
+
+
+def test_sph_l1_loss_alias():
+    """sphdet/losses/__init__.py:1: SphL1Loss = mmdet's L1Loss (|pred - target|, weight, avg_factor, reductions)."""
+    from sph_retina_b200.sphdet.losses import SphL1Loss
+    torch.manual_seed(0)
+    p, t, w = torch.randn(7, 4, requires_grad=True), torch.randn(7, 4), torch.rand(7, 4)
+    assert torch.allclose(SphL1Loss()(p, t), (p - t).abs().mean())
+    assert torch.allclose(SphL1Loss(reduction='sum', loss_weight=2.0)(p, t, w), 2.0 * ((p - t).abs() * w).sum())
+    assert torch.allclose(SphL1Loss()(p, t, w, avg_factor=3.0), ((p - t).abs() * w).sum() / (3.0 + torch.finfo(torch.float32).eps))
+    assert SphL1Loss()(p, t, reduction_override='none').shape == (7, 4)
+    assert SphL1Loss()(p[:0], t[:0]).item() == 0.0
+    SphL1Loss()(p, t, w).backward()
+    assert torch.allclose(p.grad, torch.sign(p.detach() - t) * w / 28)
