@@ -45,25 +45,36 @@ def _cfg_get(cfg, key, default=None):
 
 
 def get_bboxes_single(cls_score_list, bbox_pred_list, mlvl_priors, bbox_coder, cfg, box_version=4, use_sigmoid_cls=True,
-                      with_nms=True):
+                      with_nms=True, score_factor_list=None, img_shape=None):
     """One image, the reference's contract (sph_retina_head.py:103-212 then :35-101): cls_score_list[l] is
     [A * C, H, W], bbox_pred_list[l] is [A * box_version, H, W], mlvl_priors[l] is [H * W * A, box_version].
-    Returns (det_bboxes [K, box_version + 1], det_labels [K]) -- or (bboxes, scores, labels) when with_nms is False."""
+    Returns (det_bboxes [K, box_version + 1], det_labels [K]) -- or (bboxes, scores, labels) when with_nms is False.
+
+    The anchor-free heads share the block (sph_fcos_head.py:196-321): ``score_factor_list[l]`` ([1, H, W] centerness
+    logits) multiplies the kept scores by its sigmoid before the NMS (:225-227), ``mlvl_priors[l]`` are then the [H * W, 2]
+    points of ``DistancePointSphBBoxCoder`` and ``img_shape`` (H, W) is handed to ``decode`` as ``max_shape`` (:312-313)."""
     nms_pre = _cfg_get(cfg, 'nms_pre', -1)
     score_thr = _cfg_get(cfg, 'score_thr', 0.0)
-    mlvl_bboxes, mlvl_scores, mlvl_labels = [], [], []
-    for cls_score, bbox_pred, priors in zip(cls_score_list, bbox_pred_list, mlvl_priors):
+    mlvl_bboxes, mlvl_scores, mlvl_labels, mlvl_factors = [], [], [], []
+    if score_factor_list is None or score_factor_list[0] is None:
+        score_factor_list = [None] * len(cls_score_list)
+    decode_kw = {} if img_shape is None else dict(max_shape=img_shape)
+    for cls_score, bbox_pred, priors, score_factor in zip(cls_score_list, bbox_pred_list, mlvl_priors, score_factor_list):
         assert cls_score.size()[-2:] == bbox_pred.size()[-2:]
         bbox_pred = bbox_pred.permute(1, 2, 0).reshape(-1, box_version)
         num_cls = cls_score.size(0) // (bbox_pred.size(0) // (cls_score.size(-1) * cls_score.size(-2)))
         cls_score = cls_score.permute(1, 2, 0).reshape(-1, num_cls)
         scores = cls_score.sigmoid() if use_sigmoid_cls else cls_score.softmax(-1)[:, :-1]
         topk = nms_pre if nms_pre > 0 else scores.numel()
-        scores, labels, _, filtered = filter_scores_and_topk(scores, score_thr, topk, dict(bbox_pred=bbox_pred, priors=priors))
-        mlvl_bboxes.append(bbox_coder.decode(filtered['priors'], filtered['bbox_pred']))
+        scores, labels, keep_idxs, filtered = filter_scores_and_topk(scores, score_thr, topk, dict(bbox_pred=bbox_pred, priors=priors))
+        mlvl_bboxes.append(bbox_coder.decode(filtered['priors'], filtered['bbox_pred'], **decode_kw))
         mlvl_scores.append(scores)
         mlvl_labels.append(labels)
+        if score_factor is not None:
+            mlvl_factors.append(score_factor.permute(1, 2, 0).reshape(-1).sigmoid()[keep_idxs])
     bboxes, scores, labels = torch.cat(mlvl_bboxes), torch.cat(mlvl_scores), torch.cat(mlvl_labels)
+    if mlvl_factors:
+        scores = scores * torch.cat(mlvl_factors)
     if not with_nms:
         return bboxes, scores, labels
     if bboxes.numel() == 0:

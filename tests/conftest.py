@@ -175,3 +175,57 @@ def check_distance_coder(coder_mod, dev):
     import pytest
     with pytest.raises(AssertionError):
         coder.decode(pts, torch.cat([dist, gamma], 1))                       # box_version 4 coder, five columns
+
+
+def check_anchor_free_post_processing(post_mod, coder_mod, O, dev, with_nms):
+    """get_bboxes_single with score factors and the point coder (sph_fcos_head.py:196-321) against the literal chain on
+    the oracle's restatements: per level sigmoid -> filter_scores_and_topk -> distance2bbox(max_shape=img_shape), then
+    scores x sigmoid(centerness) and, with_nms, the greedy class-wise NMS of the oracle."""
+    import torch
+    torch.manual_seed(5)
+    H, W, C, D = 512, 1024, 5, 4
+    cls, reg, ctr, pts = [], [], [], []
+    for s in (32, 64, 128):
+        h, w = H // s, W // s
+        cls.append(torch.randn(C, h, w) - 1.0)
+        reg.append(torch.rand(D, h, w) * s * 5)
+        ctr.append(torch.randn(1, h, w))
+        ys, xs = torch.meshgrid(torch.arange(h) * s + s // 2, torch.arange(w) * s + s // 2, indexing="ij")
+        pts.append(torch.stack([xs.reshape(-1), ys.reshape(-1)], -1).float())
+    cfg = dict(nms_pre=200, score_thr=0.05, nms=dict(iou_threshold=0.5), max_per_img=50, iou_calculator='sph2pob_efficient')
+    coder = coder_mod.DistancePointSphBBoxCoder()
+    to = lambda xs: [x.to(dev) for x in xs]
+    clip, noclip, raw, fac, lbs = [], [], [], [], []
+    for c, r, f, p in zip(cls, reg, ctr, pts):
+        r = r.permute(1, 2, 0).reshape(-1, D)
+        sc = c.permute(1, 2, 0).reshape(-1, C).sigmoid()
+        valid = sc > cfg["score_thr"]
+        vs, vi = sc[valid], torch.nonzero(valid)
+        vs, order = vs.sort(descending=True)                                # distinct random scores: the order is determined
+        keep, labels = vi[order[:min(cfg["nms_pre"], vi.size(0))]].unbind(dim=1)
+        clip.append(O.distance2bbox(p[keep], r[keep], (H, W), (H, W)))
+        noclip.append(O.distance2bbox(p[keep], r[keep], None, (H, W)))
+        raw.append(vs[:len(keep)])
+        fac.append(f.permute(1, 2, 0).reshape(-1).sigmoid()[keep])
+        lbs.append(labels)
+    clip, noclip, raw, fac, lbs = torch.cat(clip), torch.cat(noclip), torch.cat(raw), torch.cat(fac), torch.cat(lbs)
+    assert len(clip) > 300 and not torch.equal(clip, noclip)               # all three levels contribute, the clamp is active
+    b, sc, lb = post_mod.get_bboxes_single(to(cls), to(reg), to(pts), coder, cfg, box_version=D, with_nms=False,
+                                           score_factor_list=to(ctr), img_shape=(H, W))
+    assert torch.equal(b.cpu(), clip) and torch.equal(lb.cpu(), lbs)
+    assert float((sc.cpu() - raw * fac).abs().max()) < 1e-6
+    b0, sc0, lb0 = b, sc, lb
+    # without the two arguments the call is the anchor-based heads' one: no factor, decode without max_shape
+    b, sc, lb = post_mod.get_bboxes_single(to(cls), to(reg), to(pts), coder, cfg, box_version=D, with_nms=False)
+    assert torch.equal(b.cpu(), noclip) and torch.equal(lb.cpu(), lbs) and float((sc.cpu() - raw).abs().max()) < 1e-6
+    b, sc, lb = post_mod.get_bboxes_single(to(cls), to(reg), to(pts), coder, cfg, box_version=D, with_nms=False,
+                                           score_factor_list=[None] * 3)
+    assert float((sc.cpu() - raw).abs().max()) < 1e-6
+    if with_nms:
+        dets, labels = post_mod.get_bboxes_single(to(cls), to(reg), to(pts), coder, cfg, box_version=D,
+                                                  score_factor_list=to(ctr), img_shape=(H, W))
+        # the NMS itself is pinned to the oracle elsewhere (test_nms_*): here, that the block hands it these candidates
+        wd, wk = post_mod.SphNMS('sph2pob_efficient')(b0.to(dev), sc0.to(dev), lb0.to(dev), cfg["nms"])
+        assert dets.shape[1] == D + 1 and 0 < len(dets) == min(len(wk), cfg["max_per_img"])
+        assert torch.equal(labels, lb0.to(dev)[wk][:cfg["max_per_img"]]) and torch.equal(dets, wd[:cfg["max_per_img"]])
+        assert bool((dets[:-1, -1] >= dets[1:, -1]).all())

@@ -1176,3 +1176,11 @@ def test_distance_point_coder_golden(api):
     from conftest import check_distance_coder
     from sph_retina_b200.sphdet.bbox.coder import distance_point_sph_bbox_coder as M
     check_distance_coder(M, DEV)
+
+
+def test_anchor_free_head_post_processing(api):
+    """get_bboxes_single with centerness score factors and the point coder (sph_fcos_head.py:196-321)."""
+    from conftest import check_anchor_free_post_processing
+    from sph_retina_b200.sphdet.bbox.coder import distance_point_sph_bbox_coder as M
+    from sph_retina_b200.sphdet.models.heads import sph_bbox_post
+    check_anchor_free_post_processing(sph_bbox_post, M, O, DEV, with_nms=True)

@@ -534,3 +534,7 @@ def test_distance_point_coder_golden(hostsim, monkeypatch):
         return torch.from_numpy(out)
     monkeypatch.setattr(_native, "box_format", host_box_format)
     check_distance_coder(M, "cpu")
+    # the anchor-free heads' test-time block up to the NMS (which has no host twin: the GPU suite runs it)
+    from conftest import check_anchor_free_post_processing
+    from sph_retina_b200.sphdet.models.heads import sph_bbox_post
+    check_anchor_free_post_processing(sph_bbox_post, M, O, "cpu", with_nms=False)
