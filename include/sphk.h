@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SPHK_ABI_VERSION 5
+#define SPHK_ABI_VERSION 6
 
 enum sphk_status {
     SPHK_OK = 0,
@@ -90,6 +90,19 @@ int sphk_iou_pairwise(int kind, const float* rows, int64_t R, const float* cols,
 int sphk_iou_pairwise_keys(int kind, const float* rows, int64_t R, const float* cols, int64_t C, int D, int mode, int edge,
                            uint64_t* row_keys, uint64_t* col_keys, int32_t row_base, int32_t col_base, void* workspace,
                            void* stream);
+
+/* Row-sharded N x M across GPUs (BASELINE configs[4]; sph_retina_b200/sharded.py): what follows the all-gather of the
+ * shards' packed keys.  The long operand (anchors) is split contiguously and balanced over `world` shards (the first
+ * n_long % world shards own one row more), the short operand (ground truths) is replicated.  Each shard contributes a
+ * block of cap + n_short keys (cap >= ceil(n_long / world)): the sphk_iou_pairwise_keys of its rows (entries past its own
+ * slice are padding), then its keys of the short operand with GLOBAL row indices.
+ *   gathered [world, cap + n_short]  the all-gathered blocks (for world = 1: the single block)
+ *   long_max / long_arg [n_long]     per long-operand box: max over the short set / its index  (int64, as torch.max)
+ *   short_max / short_arg [n_short]  per short-operand box: max over ALL shards / global index, ties -> lowest index
+ * Contract reproduced: overlaps.max(dim=0) / .max(dim=1) of mmdet/core/bbox/assigners/max_iou_assigner.py:173-176 on
+ * the unsharded matrix.  One launch; a key of 0 ("no positive overlap") reads as (0.0, index 0). */
+int sphk_unpack_gathered_keys(const uint64_t* gathered, int32_t world, int64_t n_long, int64_t n_short, int64_t cap,
+                              float* long_max, int64_t* long_arg, float* short_max, int64_t* short_arg, void* stream);
 
 /* Second pass of MaxIoUAssigner's low-quality matching with gt_max_assign_all=True
  * (mmdet/core/bbox/assigners/max_iou_assigner.py:201-205: for each GT i in ascending order,

@@ -20,7 +20,7 @@ EDGE = {"arc": 0, "chord": 1, "tangent": 2}
 ANGLE = {"equator": 0, "project": 1}
 
 SPHK_OK = 0
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 _c_float_p = ctypes.c_void_p  # raw device addresses
 _i64 = ctypes.c_int64
@@ -41,6 +41,8 @@ SIGNATURES = {
                                       _i32, _i32, ctypes.c_void_p, ctypes.c_void_p]),
     "sphk_iou_pairwise_ties": (_int, [_int, _c_float_p, _i64, _c_float_p, _i64, _int, _int, _int, _c_float_p, ctypes.c_void_p,
                                       _i32, ctypes.c_void_p, ctypes.c_void_p]),
+    "sphk_unpack_gathered_keys": (_int, [ctypes.c_void_p, _i32, _i64, _i64, _i64, _c_float_p, ctypes.c_void_p, _c_float_p,
+                                         ctypes.c_void_p, ctypes.c_void_p]),
     "sphk_max_iou_assign_workspace_bytes": (_i64, [_i64, _i64, _i32]),
     "sphk_max_iou_assign": (_int, [_int, _c_float_p, ctypes.POINTER(_i32), _i32, _c_float_p, _i64, _int, ctypes.c_float,
                                    ctypes.c_float, ctypes.c_float, ctypes.c_float, _int, _int, ctypes.c_void_p, ctypes.c_void_p,
@@ -217,7 +219,7 @@ def iou_pairwise(kind: str, rows, cols, mode="iou", edge="arc", want_matrix=True
         cmax = torch.empty(C, dtype=torch.float32, device=dev)
         carg = torch.empty(C, dtype=torch.int32, device=dev)
     if want_row_max or want_col_max or kind in ("sph2pob_efficient", "sph2pob_standard"):
-        ws = _workspace(dev, 104 * (R + C) + 32)     # >= sphk_iou_pairwise_workspace_bytes(R, C)
+        ws = _workspace(dev, 136 * (R + C) + 32)     # >= sphk_iou_pairwise_workspace_bytes(R, C)
     with _on_device(dev):
         _check(lib.sphk_iou_pairwise(KIND[kind], _ptr(rows), R, _ptr(cols), C, rows.size(1), MODE[mode], EDGE[edge],
                                      ANGLE[angle], _ptr(mat), ld, _ptr(rmax), _ptr(rarg), _ptr(cmax), _ptr(carg), row_base, col_base,
@@ -232,21 +234,45 @@ def iou_pairwise(kind: str, rows, cols, mode="iou", edge="arc", want_matrix=True
     return mat, ((rmax, rarg) if want_row_max else None), ((cmax, carg) if want_col_max else None)
 
 
-def iou_pairwise_keys(kind: str, rows, cols, mode="iou", edge="arc", row_base=0, col_base=0):
+def iou_pairwise_keys(kind: str, rows, cols, mode="iou", edge="arc", row_base=0, col_base=0, row_keys_out=None,
+                      col_keys_out=None):
     """Fused max/argmax of the N x M overlaps as the kernel's packed keys, without unpacking:
     (row_keys[R], col_keys[C]) int64 = float32 bits << 32 | (0xFFFFFFFF - index); 0 = no positive overlap.
-    Integer MAX over shards of such keys = (max value, lowest index): what the multi-GPU sweep reduces."""
+    Integer MAX over shards of such keys = (max value, lowest index): what the multi-GPU sweep reduces.
+    ``row_keys_out`` / ``col_keys_out``: contiguous int64 CUDA tensors to write into (slices of a communication buffer)."""
     global launches
     rows, cols = _boxes(rows, "bboxes1"), _boxes(cols, "bboxes2")
     R, C, dev = rows.size(0), cols.size(0), rows.device
-    rk = torch.empty(R, dtype=torch.int64, device=dev)
-    ck = torch.empty(C, dtype=torch.int64, device=dev)
-    ws = _workspace(dev, 104 * (R + C) + 32)
+    rk = row_keys_out if row_keys_out is not None else torch.empty(R, dtype=torch.int64, device=dev)
+    ck = col_keys_out if col_keys_out is not None else torch.empty(C, dtype=torch.int64, device=dev)
+    for k, n in ((rk, R), (ck, C)):
+        if not (k.is_cuda and k.dtype == torch.int64 and k.is_contiguous() and k.numel() == n and k.device == dev):
+            raise SphkError("key outputs must be contiguous int64 CUDA tensors of %d elements on %s" % (n, dev))
+    ws = _workspace(dev, 136 * (R + C) + 32)
     with _on_device(dev):
         _check(lib.sphk_iou_pairwise_keys(KIND[kind], _ptr(rows), R, _ptr(cols), C, rows.size(1), MODE[mode], EDGE[edge],
                                           _ptr(rk), _ptr(ck), row_base, col_base, _ptr(ws), _stream(rows)))
     launches += 2
     return rk, ck
+
+
+def unpack_gathered_keys(gathered, world: int, n_long: int, n_short: int, cap: int):
+    """Row-sharded N x M: (long_max[n_long], long_arg[n_long] int64, short_max[n_short], short_arg[n_short] int64) from
+    the all-gathered key blocks [world, cap + n_short] (include/sphk.h: sphk_unpack_gathered_keys), one launch."""
+    global launches
+    if not (gathered.is_cuda and gathered.dtype == torch.int64 and gathered.is_contiguous()
+            and gathered.numel() == world * (cap + n_short)):
+        raise SphkError("gathered must be a contiguous int64 CUDA tensor of world * (cap + n_short) keys")
+    dev = gathered.device
+    lmax = torch.empty(n_long, dtype=torch.float32, device=dev)
+    larg = torch.empty(n_long, dtype=torch.int64, device=dev)
+    smax = torch.empty(n_short, dtype=torch.float32, device=dev)
+    sarg = torch.empty(n_short, dtype=torch.int64, device=dev)
+    with _on_device(dev):
+        _check(lib.sphk_unpack_gathered_keys(_ptr(gathered), world, n_long, n_short, cap, _ptr(lmax), _ptr(larg), _ptr(smax),
+                                             _ptr(sarg), _stream(gathered)))
+    launches += 1
+    return lmax, larg, smax, sarg
 
 
 def iou_pairwise_ties(kind: str, rows, cols, row_target, mode="iou", edge="arc", row_base=0):
@@ -257,7 +283,7 @@ def iou_pairwise_ties(kind: str, rows, cols, row_target, mode="iou", edge="arc",
     row_target = row_target.to(device=dev, dtype=torch.float32).contiguous()
     assert row_target.numel() == R
     tie = torch.empty(C, dtype=torch.int32, device=dev)
-    ws = _workspace(dev, 104 * (R + C) + 32)
+    ws = _workspace(dev, 136 * (R + C) + 32)
     with _on_device(dev):
         _check(lib.sphk_iou_pairwise_ties(KIND[kind], _ptr(rows), R, _ptr(cols), C, rows.size(1), MODE[mode], EDGE[edge],
                                           _ptr(row_target), _ptr(tie), row_base, _ptr(ws), _stream(rows)))

@@ -30,12 +30,21 @@ struct BoxRec {
     float sg, cg, a, b;   // sin / cos gamma (0, 1 for BFoV); raw alpha, beta (deg) for the similarity mask
     float g, flag, pad0, pad1;  // raw gamma (deg); flag != 0: reference-order path only
 };
-// Prefilter operands of one box.  32 bytes = 2 x float4.
+// Prefilter operands of one box.  64 bytes = 4 x float4.
+//   circle test (pre_disjoint):      centre unit vector u, cos / sin of r = circumradius of the planar box + jitter margin
+//   box-frame test (pre_outside_box): the box's own planar axes as 3-D tangent vectors e (width axis) and f (height
+//                                     axis) at its centre, its half sizes + margin, and r itself
 struct BoxCull {
-    float ux, uy, uz, rc;  // centre unit vector; cos(r), r = circumradius of the planar box + jitter margin
-    float rs, bias, pad0, pad1;  // sin(r); bias: -1e-6 (rounding margin) or -10 (box too large to ever be culled)
+    float ux, uy, uz, rc;    // centre unit vector; cos(r)
+    float rs, bias, r, pad0; // sin(r); bias: -1e-6 (rounding margin) or -10 (box too large to ever be culled); r (rad)
+    float ex, ey, ez, hwm;   // width axis; half width + kBoxMargin (rad), 10 = this box never culls by its frame
+    float fx, fy, fz, hhm;   // height axis; half height + kBoxMargin
 };
-constexpr int kBoxRecFloats = 16, kBoxCullFloats = 8;
+constexpr int kBoxRecFloats = 16, kBoxCullFloats = 16;
+// What may move between the records and the jittered OBBs the reference clips (sph_iou_api.py:222-260): centres by
+// <= 3.5e-4 rad (jitter_2) + 4.5e-4 (acos clamp of the arc), half sizes by <= 1.3e-4, the frame of box 1 by
+// <= eps + eps' + the acos clamp of its angle = 1.9e-3 rad, i.e. the partner's centre by <= pi * 1.9e-3 = 6e-3.
+constexpr float kBoxMargin = 8e-3f;
 
 // Record of one box in its role (1 = bboxes1 / rows, 2 = bboxes2 / columns); the jittered box is returned too.
 SPHK_HD JitBox box_rec(const RawBox& x, int role, int D, int edge, BoxRec* rec) {
@@ -77,7 +86,18 @@ SPHK_HD void box_pre(const RawBox& x, int role, int D, int edge, BoxRec* rec, Bo
     } else {
         cull->rs = 0.0f; cull->rc = 0.0f; cull->bias = -10.0f;
     }
-    cull->pad0 = 0.0f; cull->pad1 = 0.0f;
+    cull->r = (r == r) ? r : 10.0f;
+    cull->pad0 = 0.0f;
+    // The planar box's axes in 3-D.  With east = (-sin t, cos t, 0) and south = (cos p cos t, cos p sin t, -sin p) at the
+    // centre, the Sph2Pob frame of the box (internal angle minus gamma, sph2pob_efficient.py:53-57) has its width
+    // axis along cos(g) east - sin(g) south and its height axis along sin(g) east + cos(g) south: the partner's
+    // centre sits at arc * (cos, sin)(bearing) in that frame, and u_partner . axis = sin(arc) * (cos, sin)(bearing).
+    const float sx = rec->cp * ct, sy = rec->cp * st, sz = -rec->sp;
+    cull->ex = fmaf(rec->cg, -st, -rec->sg * sx); cull->ey = fmaf(rec->cg, ct, -rec->sg * sy); cull->ez = -rec->sg * sz;
+    cull->fx = fmaf(rec->sg, -st, rec->cg * sx);  cull->fy = fmaf(rec->sg, ct, rec->cg * sy);  cull->fz = rec->cg * sz;
+    const bool frame_ok = rec->flag == 0.0f;       // reference-order-only boxes keep the circle test alone
+    cull->hwm = frame_ok ? fmaf(0.5f, rec->w, kBoxMargin) : 10.0f;
+    cull->hhm = frame_ok ? fmaf(0.5f, rec->h, kBoxMargin) : 10.0f;
 }
 
 // true: the planar boxes are disjoint for every jitter outcome (centre distance > sum of the circumradii
@@ -86,6 +106,24 @@ SPHK_HD bool pre_disjoint(const BoxCull& g, const BoxCull& p) {
     const float dot = fmaf(g.ux, p.ux, fmaf(g.uy, p.uy, g.uz * p.uz));
     const float thr = fmaf(g.rc, p.rc, fmaf(-g.rs, p.rs, g.bias + p.bias));
     return dot < thr;
+}
+
+// true: the centre of box p lies outside box g grown by r_p (+ margin) along one of g's own axes -> the planar boxes
+// cannot touch -> IoU is exactly 0 in the reference.  In g's planar frame p sits at arc * (c, s) with (c, s) the unit
+// bearing; a = u_p . axis_g = sin(arc) * c.  For T = half size + margin + r_p <= pi/2: sin is concave on [0, pi], so
+// sin(arc |c|) >= sin(arc) |c| = |a|, hence arc |c| >= asin|a| >= |a| (1 + a^2 / 6); if that lower bound exceeds T the
+// centre is farther than T along the axis.  For T > pi/2 the bound (<= 7/6) can never exceed it: no special case.
+// 6 FMA + 2 x 4 instructions; half sizes of 10 (flagged boxes) or r = 10 (NaN sizes) switch the test off.
+SPHK_HD bool pre_outside_box(float ex, float ey, float ez, float hwm, float fx, float fy, float fz, float hhm,
+                             float pux, float puy, float puz, float pr) {
+    const float a = fmaf(ex, pux, fmaf(ey, puy, ez * puz));
+    const float b = fmaf(fx, pux, fmaf(fy, puy, fz * puz));
+    const float la = fabsf(a) * fmaf(a * a, 0.16666667f, 1.0f);
+    const float lb = fabsf(b) * fmaf(b * b, 0.16666667f, 1.0f);
+    return (la > hwm + pr) | (lb > hhm + pr);
+}
+SPHK_HD bool pre_outside_box(const BoxCull& g, const BoxCull& p) {
+    return pre_outside_box(g.ex, g.ey, g.ez, g.hwm, g.fx, g.fy, g.fz, g.hhm, p.ux, p.uy, p.uz, p.r);
 }
 
 // 1/sqrt(x) to ~1 ulp (MUFU.RSQ): used to normalise (cos, sin) pairs and for the conservative cull radius, where

@@ -1,35 +1,32 @@
-"""Row-sharded N x M overlaps for large anchor x GT sweeps (BASELINE config #5).
+"""Row-sharded N x M overlaps for large anchor x GT sweeps (BASELINE configs[4]).
 
-One process per GPU.  The long (anchor) axis is split contiguously over the ranks, the short (GT)
-set is replicated; every rank runs the fused max/argmax kernel on its shard with GLOBAL index
-offsets, and NCCL is used only for
-  * one all_gather of the packed per-anchor (max, argmax over GT)   -- 8 B per anchor,
-  * one all_reduce(MAX) of the packed per-GT (max, argmax over anchors) -- 8 B per GT.
-Packing: int64 key = float32 bits << 32 | (0xFFFFFFFF - index).  IoU >= 0, so integer order is
-(value, then LOWEST index); MAX over ranks therefore equals the single-device tie rule.
+One process per GPU.  The long (anchor) axis is split contiguously over the ranks, the short (GT) set is
+replicated.  Every rank runs the fused max/argmax kernel on its shard with GLOBAL index offsets; the kernel
+writes its packed keys straight into the rank's communication block
 
-The reference has no multi-GPU awareness on this path; the single-device contract
-being reproduced is MaxIoUAssigner's overlaps.max(dim=0/1)
-(mmdet/core/bbox/assigners/max_iou_assigner.py:173-176)."""
+    block = [ keys of the rank's anchors (cap = ceil(n / world) slots) | the rank's keys of the G ground truths ]
+
+and the exchange is ONE NCCL ``all_gather_into_tensor`` of the blocks (8 B per anchor + 8 B x G per rank) followed by
+ONE kernel launch (``sphk_unpack_gathered_keys``) that writes the per-anchor (max, argmax) of the whole anchor set in
+global order and reduces the per-GT keys over the ranks.  No padding copy, no concatenation, no eager unpacking.
+Packing: int64 key = float32 bits << 32 | (0xFFFFFFFF - index).  IoU >= 0, so integer order is (value, then LOWEST
+index); the maximum over ranks therefore equals the single-device tie rule.
+
+The reference has no multi-GPU awareness on this path; the single-device contract being reproduced is
+MaxIoUAssigner's overlaps.max(dim=0/1) (mmdet/core/bbox/assigners/max_iou_assigner.py:173-176)."""
 from __future__ import annotations
 
 import torch
 import torch.distributed as dist
 
 _IDX_MASK = 0xFFFFFFFF
+_KINDS = {'sph2pob_standard_iou': 'sph2pob_standard', 'sph2pob_efficient_iou': 'sph2pob_efficient'}
 
 
 def pack_keys(values: torch.Tensor, indices: torch.Tensor) -> torch.Tensor:
-    """(float32 >= 0, index < 2**32) -> sortable int64 keys."""
+    """(float32 >= 0, index < 2**32) -> the kernel's sortable int64 keys."""
     bits = values.detach().to(torch.float32).contiguous().view(torch.int32).to(torch.int64)
     return (bits << 32) | (_IDX_MASK - indices.to(torch.int64))
-
-
-def unpack_keys(keys: torch.Tensor):
-    """keys -> (values, indices); the kernel's 0 key ("no positive overlap") reads as (0.0, index 0)."""
-    vals = (keys >> 32).to(torch.int32).view(torch.float32)
-    idx = torch.where(keys == 0, torch.zeros_like(keys), _IDX_MASK - (keys & _IDX_MASK))
-    return vals, idx
 
 
 def shard_bounds(n: int, world: int, rank: int):
@@ -39,26 +36,48 @@ def shard_bounds(n: int, world: int, rank: int):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def gather_assignment(anchor_keys_local: torch.Tensor, gt_keys_local: torch.Tensor, n_anchors: int, group=None):
-    """Collective step: local packed keys -> global (anchor_max, anchor_arg, gt_max, gt_arg) on every rank."""
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
+def block_capacity(n_anchors: int, world: int) -> int:
+    """Anchor-key slots of one rank's block: the largest shard."""
+    return -(-n_anchors // world)
+
+
+def _world(group=None):
+    return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+
+_blocks = {}
+
+
+def key_block(n_anchors: int, n_gt: int, world: int, device, fresh: bool = False) -> torch.Tensor:
+    """The rank's communication block [cap + n_gt] int64.  The slots past the rank's own shard are padding that no
+    kernel writes: they are zeroed once here.  One block per (device, shape) is kept and re-used: the kernel that fills
+    it, the collective that reads it and the unpack that follows are ordered on the caller's stream."""
+    key = (str(device), n_anchors, n_gt, world)
+    blk = None if fresh else _blocks.get(key)
+    if blk is None:
+        blk = torch.zeros(block_capacity(n_anchors, world) + n_gt, dtype=torch.int64, device=device)
+        if not fresh:
+            _blocks[key] = blk
+    return blk
+
+
+def exchange_blocks(block: torch.Tensor, group=None) -> torch.Tensor:
+    """all-gather of the ranks' blocks -> [world, cap + n_gt]; the only collective of the sharded path."""
+    world = _world(group)
     if world == 1:
-        a_keys, g_keys = anchor_keys_local, gt_keys_local
-    else:
-        rank = dist.get_rank(group)
-        sizes = [shard_bounds(n_anchors, world, r) for r in range(world)]
-        cap = max(hi - lo for lo, hi in sizes)
-        pad = anchor_keys_local.new_zeros(cap)
-        pad[:anchor_keys_local.numel()] = anchor_keys_local
-        gathered = anchor_keys_local.new_empty(world * cap)
-        dist.all_gather_into_tensor(gathered, pad, group=group)
-        a_keys = torch.cat([gathered[r * cap:r * cap + (hi - lo)] for r, (lo, hi) in enumerate(sizes)])
-        g_keys = gt_keys_local.clone()
-        dist.all_reduce(g_keys, op=dist.ReduceOp.MAX, group=group)
-        assert sizes[rank][1] - sizes[rank][0] == anchor_keys_local.numel()
-    a_max, a_arg = unpack_keys(a_keys)
-    g_max, g_arg = unpack_keys(g_keys)
-    return a_max, a_arg, g_max, g_arg
+        return block.view(1, -1)
+    gathered = torch.empty((world, block.numel()), dtype=block.dtype, device=block.device)
+    dist.all_gather_into_tensor(gathered.view(-1), block, group=group)
+    return gathered
+
+
+def gather_assignment(block: torch.Tensor, n_anchors: int, n_gt: int, group=None):
+    """Collective step: the rank's filled block -> global (anchor_max, anchor_arg, gt_max, gt_arg) on every rank
+    (argmax int64 as torch.max returns it).  One all_gather + one kernel launch."""
+    from . import _native
+    world = _world(group)
+    gathered = exchange_blocks(block, group)
+    return _native.unpack_gathered_keys(gathered, world, n_anchors, n_gt, block_capacity(n_anchors, world))
 
 
 def sharded_max_overlaps(anchors_local, gts, n_anchors, anchor_offset, backend='sph2pob_efficient_iou', mode='iou',
@@ -66,16 +85,29 @@ def sharded_max_overlaps(anchors_local, gts, n_anchors, anchor_offset, backend='
     """overlaps.max over both axes of the logical [n_anchors x n_gt] (or transposed) matrix.
 
     anchors_local : this rank's contiguous shard [n_local, D] starting at global row `anchor_offset`
+                    (= shard_bounds(n_anchors, world, rank))
     gts           : the replicated short set [G, D]
     anchors_are   : 'bboxes1' -> IoU(anchor, gt) (config #5 call), 'bboxes2' -> IoU(gt, anchor)
                     (the assigner's orientation); the jitters are role-asymmetric, so this matters.
     Returns (anchor_max[n_anchors], anchor_arg -> gt index, gt_max[G], gt_arg -> global anchor index)."""
     from . import _native
-    kind = {'sph2pob_standard_iou': 'sph2pob_standard', 'sph2pob_efficient_iou': 'sph2pob_efficient'}[backend]
-    # the kernel's packed keys go straight into the collectives: no unpack / repack round trip
+    kind = _KINDS[backend]
+    world = _world(group)
+    n_local, n_gt = anchors_local.size(0), gts.size(0)
+    rank = dist.get_rank(group) if world > 1 else 0
+    lo, hi = shard_bounds(n_anchors, world, rank)
+    if (lo, hi - lo) != (anchor_offset, n_local):
+        raise ValueError("rank %d of %d must hold anchors [%d, %d) of %d, got offset %d and %d rows"
+                         % (rank, world, lo, hi, n_anchors, anchor_offset, n_local))
+    cap = block_capacity(n_anchors, world)
+    block = key_block(n_anchors, n_gt, world, anchors_local.device)
+    a_out, g_out = block[:n_local], block[cap:]
+    # the kernel's packed keys go straight into the communication block: no unpack / repack / copy
     with torch.no_grad():
         if anchors_are == 'bboxes1':
-            a_keys, g_keys = _native.iou_pairwise_keys(kind, anchors_local, gts, mode, row_base=anchor_offset)
+            _native.iou_pairwise_keys(kind, anchors_local, gts, mode, row_base=anchor_offset, row_keys_out=a_out,
+                                      col_keys_out=g_out)
         else:
-            g_keys, a_keys = _native.iou_pairwise_keys(kind, gts, anchors_local, mode, col_base=anchor_offset)
-    return gather_assignment(a_keys, g_keys, n_anchors, group)
+            _native.iou_pairwise_keys(kind, gts, anchors_local, mode, col_base=anchor_offset, row_keys_out=g_out,
+                                      col_keys_out=a_out)
+    return gather_assignment(block, n_anchors, n_gt, group)

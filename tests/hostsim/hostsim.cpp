@@ -44,7 +44,7 @@ void hostsim_approx_general(int kind, const float* b1, const float* b2, long P, 
 }
 
 // The N x M formulation (csrc/sphk_fast.cuh): per-box precompute, prefilter, fast path with fallback.
-// path[i] (optional): 0 = prefilter said disjoint, 1 = fast path, 2 = reference-order path.
+// path[i] (optional): 0 = circle prefilter said disjoint, 4 = box-frame prefilter did, 1 = fast path, 2 = reference-order path.
 void hostsim_iou_aligned_v2(int kind, const float* b1, const float* b2, long P, int D, int mode, int edge, float* out,
                             unsigned char* path) {
     for (long i = 0; i < P; ++i) {
@@ -54,10 +54,26 @@ void hostsim_iou_aligned_v2(int kind, const float* b1, const float* b2, long P, 
         box_pre(x, 1, D, edge, &gr, &gc);
         box_pre(y, 2, D, edge, &pr, &pc);
         if (pre_disjoint(gc, pc)) { out[i] = 0.0f; if (path) path[i] = 0; continue; }
+        if (pre_outside_box(gc, pc)) { out[i] = 0.0f; if (path) path[i] = 4; continue; }   // row-frame box test of the scan loops
         float v;
         if (pair_fast(gr, pr, D, kind, mode, &v)) { out[i] = v; if (path) path[i] = 1; continue; }
         out[i] = sph2pob_iou_pair(x, y, D, kind, mode, edge);
         if (path) path[i] = 2;
+    }
+}
+
+// Prefilter verdicts next to the reference-order IoU computed WITHOUT any early-out (dense = true): cull[i] bit 0 = circle
+// test, bit 1 = box-frame test (row = box 1).  A culled pair must have dense IoU exactly 0.
+void hostsim_prefilter(int kind, const float* b1, const float* b2, long P, int D, int mode, int edge, float* dense_iou,
+                       unsigned char* cull) {
+    for (long i = 0; i < P; ++i) {
+        const RawBox x = load_box(b1, i, D), y = load_box(b2, i, D);
+        BoxRec gr, pr;
+        BoxCull gc, pc;
+        box_pre(x, 1, D, edge, &gr, &gc);
+        box_pre(y, 2, D, edge, &pr, &pc);
+        cull[i] = (pre_disjoint(gc, pc) ? 1 : 0) | (pre_outside_box(gc, pc) ? 2 : 0);
+        dense_iou[i] = sph2pob_iou_pair(x, y, D, kind, mode, edge, true);
     }
 }
 

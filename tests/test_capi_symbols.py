@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol(built_lib):
     for name in declared_symbols():
         assert hasattr(lib, name), "libsphk.so does not export %s" % name
     lib.sphk_abi_version.restype = ctypes.c_int
-    assert lib.sphk_abi_version() == 5
+    assert lib.sphk_abi_version() == 6
 
 
 def test_binding_covers_the_header(built_lib):
@@ -51,8 +51,11 @@ def test_argument_validation_needs_no_gpu(built_lib):
     assert lib.sphk_iou_aligned(2, None, None, 10, 5, 0, 0, 0, None, None) == -3          # sph_iou on RBFoV
     assert lib.sphk_iou_aligned(7, None, None, 10, 4, 0, 0, 0, None, None) == -1          # unknown kind
     assert lib.sphk_iou_aligned(0, None, None, 0, 4, 0, 0, 0, None, None) == 0            # empty is fine
-    assert lib.sphk_iou_pairwise_workspace_bytes(10, 20) == 240 + 30 * 96
+    assert lib.sphk_iou_pairwise_workspace_bytes(10, 20) == 240 + 30 * 128
     assert lib.sphk_nms_batched(None, None, None, 0, 0, 0, 4, 0, 0.5, None, None) == 0
+    assert lib.sphk_unpack_gathered_keys(None, 0, 10, 4, 10, None, None, None, None, None) == -1    # world < 1
+    assert lib.sphk_unpack_gathered_keys(None, 2, 10, 4, 4, None, None, None, None, None) == -1     # cap < ceil(n / world)
+    assert lib.sphk_unpack_gathered_keys(None, 2, 0, 0, 0, None, None, None, None, None) == 0       # nothing to do
     assert lib.sphk_nms_batched(None, None, None, 3, 9, 0, 4, 1, 0.5, None, None) == -3    # NMS calculator: efficient, naive or unbiased
     assert lib.sphk_iou_aligned(4, None, None, 10, 5, 1, 0, 0, None, None) == -3          # naive_iou: mode 'iou' only
     assert lib.sphk_iou_aligned(5, None, None, 10, 4, 1, 0, 0, None, None) == -3          # unbiased_iou: mode 'iou' only

@@ -327,29 +327,45 @@ def test_fused_max_argmax_few_rows(api, R, C):
     assert torch.equal(rarg3, rarg + 5000) and torch.equal(carg3, carg + 1000)
 
 
-def test_sharding_emulated_on_one_gpu(api):
-    """Two 'ranks' processed one after the other on one GPU; merging their packed keys with max() is what
-    all_reduce(MAX)/all_gather do (the collective itself is covered by tests/test_sharded_gloo.py)."""
-    from sph_retina_b200.sharded import pack_keys, shard_bounds, sharded_max_overlaps, unpack_keys
-    A = O.generate_boxes(5001, alpha_range=(1, 100), beta_range=(1, 100), box="rbfov", seed=0).to(DEV)
+@pytest.mark.parametrize("world", [3, 8])
+def test_sharding_emulated_on_one_gpu(api, world):
+    """`world` 'ranks' processed one after the other on one GPU: every rank's kernel writes its packed keys into its own
+    communication block, the blocks are stacked (what all_gather_into_tensor delivers: tests/test_sharded_gloo.py) and
+    sphk_unpack_gathered_keys turns them into the global result -- equal to the unsharded call, to the torch
+    restatement of the unpack, and with the lowest-index tie rule across shards."""
+    from sph_retina_b200 import _native
+    from sph_retina_b200.sharded import block_capacity, key_block, shard_bounds, sharded_max_overlaps
+    from test_sharded_gloo import unpack_gathered_reference
+    n = 5003                                   # uneven split: the last shards are one row short (padding slots)
+    A = O.generate_boxes(n, alpha_range=(1, 100), beta_range=(1, 100), box="rbfov", seed=0).to(DEV)
     G = O.generate_boxes(300, alpha_range=(1, 100), beta_range=(1, 100), box="rbfov", seed=1).to(DEV)
     A[4000] = A[17] = G[5]
+    A[100] = torch.tensor([10.0, 90.0, 0.5, 0.5, 0.0], device=DEV)          # an anchor no ground truth touches
+    cap = block_capacity(n, world)
     for orient in ("bboxes1", "bboxes2"):
-        a_max, a_arg, g_max, g_arg = sharded_max_overlaps(A, G, A.size(0), 0, anchors_are=orient)   # world = 1
-        parts, gkeys = [], []
-        for rank in range(3):
-            lo, hi = shard_bounds(A.size(0), 3, rank)
+        a_max, a_arg, g_max, g_arg = sharded_max_overlaps(A, G, n, 0, anchors_are=orient)   # world = 1
+        if orient == "bboxes1":
+            rm, ra, cm, ca = api.iou.sph_max_overlaps(A, G)
+        else:
+            cm, ca, rm, ra = api.iou.sph_max_overlaps(G, A)
+        assert torch.equal(a_max, rm) and torch.equal(g_max, cm)
+        assert torch.equal(a_arg[rm > 0], ra[rm > 0]) and torch.equal(g_arg[cm > 0], ca[cm > 0])
+        assert a_arg.dtype == torch.int64 and g_arg.dtype == torch.int64
+        blocks = []
+        for rank in range(world):
+            lo, hi = shard_bounds(n, world, rank)
+            blk = key_block(n, G.size(0), world, DEV, fresh=True)
             if orient == "bboxes1":
-                rm, ra, cm, ca = api.iou.sph_max_overlaps(A[lo:hi], G, row_base=lo)
-                parts.append(pack_keys(rm, ra)); gkeys.append(pack_keys(cm, ca))
+                _native.iou_pairwise_keys("sph2pob_efficient", A[lo:hi], G, row_base=lo, row_keys_out=blk[:hi - lo], col_keys_out=blk[cap:])
             else:
-                rm, ra, cm, ca = api.iou.sph_max_overlaps(G, A[lo:hi], col_base=lo)
-                parts.append(pack_keys(cm, ca)); gkeys.append(pack_keys(rm, ra))
-        sa_max, sa_arg = unpack_keys(torch.cat(parts))
-        sg_max, sg_arg = unpack_keys(torch.stack(gkeys).max(dim=0)[0])
-        assert torch.equal(sa_max, a_max) and torch.equal(sa_arg, a_arg)
-        assert torch.equal(sg_max, g_max) and torch.equal(sg_arg, g_arg)
-        assert int(g_arg[5]) == 17
+                _native.iou_pairwise_keys("sph2pob_efficient", G, A[lo:hi], col_base=lo, row_keys_out=blk[cap:], col_keys_out=blk[:hi - lo])
+            blocks.append(blk)
+        gathered = torch.stack(blocks)
+        got = _native.unpack_gathered_keys(gathered, world, n, G.size(0), cap)
+        want = unpack_gathered_reference(gathered, world, n, G.size(0), cap)
+        for g_, w_, s_ in zip(got, want, (a_max, a_arg, g_max, g_arg)):
+            assert torch.equal(g_, w_) and torch.equal(g_, s_)
+        assert int(g_arg[5]) == 17 and float(a_max[100]) == 0.0 and int(a_arg[100]) == 0
 
 
 def test_config2_slice_vs_c_oracle(api, c_oracle):

@@ -96,16 +96,31 @@ def test_product_never_imports_the_oracle():
 
 
 def test_key_packing_orders_by_value_then_lowest_index():
-    from sph_retina_b200.sharded import pack_keys, unpack_keys
+    from sph_retina_b200.sharded import pack_keys
+    from test_sharded_gloo import unpack_gathered_reference
     v = torch.tensor([0.0, 0.5, 0.5, 1.0, 0.25])
     i = torch.tensor([7, 9, 3, 4000000000, 0])
     k = pack_keys(v, i)
     assert k.dtype == torch.int64 and bool((k >= 0).all())
-    vv, ii = unpack_keys(k)
+    vv, ii, _, _ = unpack_gathered_reference(k, 1, 5, 0, 5)
     assert torch.equal(vv, v) and ii.tolist() == i.tolist()
     assert k[2] > k[1] > k[4] > k[0] and k[3] == k.max()      # ties -> lowest index wins
-    vals, idx = unpack_keys(torch.stack([k[1], k[2]]).max(dim=0, keepdim=True)[0])
-    assert idx.item() == 3
+    # two ranks' views of one ground truth (block = [0 anchor slots | 1 GT key]): the maximum is (0.5, index 3)
+    _, _, vals, idx = unpack_gathered_reference(torch.stack([k[1:2], k[2:3]]), 2, 0, 1, 0)
+    assert vals.item() == 0.5 and idx.item() == 3
+
+
+def test_block_layout_of_the_sharded_exchange():
+    """key_block / block_capacity / exchange_blocks without a process group (world = 1) and the layout arithmetic."""
+    from sph_retina_b200.sharded import block_capacity, exchange_blocks, key_block, shard_bounds
+    for n, w in ((0, 1), (1, 3), (7, 2), (1 << 20, 8), (1000003, 8)):
+        cap = block_capacity(n, w)
+        assert cap == max(shard_bounds(n, w, r)[1] - shard_bounds(n, w, r)[0] for r in range(w))
+    blk = key_block(10, 4, 1, "cpu", fresh=True)
+    assert blk.shape == (14,) and blk.dtype == torch.int64 and not blk.any()
+    assert key_block(10, 4, 1, "cpu") is key_block(10, 4, 1, "cpu")          # cached per (device, shape)
+    g = exchange_blocks(blk)
+    assert g.shape == (1, 14) and g.data_ptr() == blk.data_ptr()             # world = 1: no copy, no collective
 
 
 def test_shard_bounds_cover_and_balance():

@@ -1,6 +1,8 @@
 """The N>1 host logic of the row-sharded overlaps (sph_retina_b200/sharded.py) on CPU: world_size 2
-and 3 over gloo.  The per-shard IoU here comes from the oracle (test infrastructure); on the GPU box
-tests/test_gpu_parity.py runs the same sharding with the CUDA kernel producing the keys."""
+and 3 over gloo.  The per-shard IoU here comes from the oracle and the unpacking of the gathered blocks from
+`unpack_gathered_reference` below (test infrastructure: a torch restatement of the one-launch kernel
+sphk_unpack_gathered_keys, which the GPU suite checks against this very function); on the GPU box
+tests/test_gpu_parity.py runs the same sharding with the CUDA kernels producing and unpacking the keys."""
 import os
 import socket
 import sys
@@ -22,6 +24,24 @@ def _free_port():
     return p
 
 
+def unpack_gathered_reference(gathered, world, n_long, n_short, cap):
+    """What sphk_unpack_gathered_keys computes (include/sphk.h), in plain torch on whatever device `gathered` is on."""
+    from sph_retina_b200.sharded import shard_bounds
+    gathered = gathered.view(world, cap + n_short)
+    parts = []
+    for r in range(world):
+        lo, hi = shard_bounds(n_long, world, r)
+        parts.append(gathered[r, :hi - lo])
+    a_keys = torch.cat(parts) if parts else gathered.new_zeros(0)
+    g_keys = gathered[:, cap:].max(dim=0)[0]
+
+    def unpack(keys):
+        vals = (keys >> 32).to(torch.int32).view(torch.float32)
+        idx = torch.where(keys == 0, torch.zeros_like(keys), 0xFFFFFFFF - (keys & 0xFFFFFFFF))
+        return vals, idx
+    return unpack(a_keys) + unpack(g_keys)
+
+
 def _plant_ties(anchors, gts):
     """exact duplicates in different shards: the gathered argmax must be the LOWEST global index"""
     if anchors.size(0) > 8:
@@ -35,7 +55,8 @@ def _worker(rank, world, port, n_anchors, out_dir):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import sph_oracle as O
     from test_sharded_gloo import _plant_ties
-    from sph_retina_b200.sharded import gather_assignment, pack_keys, shard_bounds
+    from test_sharded_gloo import unpack_gathered_reference
+    from sph_retina_b200.sharded import block_capacity, exchange_blocks, key_block, pack_keys, shard_bounds
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -44,15 +65,19 @@ def _worker(rank, world, port, n_anchors, out_dir):
         gts = O.generate_boxes(24, alpha_range=(5, 100), beta_range=(5, 100), box="rbfov", seed=4)
         _plant_ties(anchors, gts)
         lo, hi = shard_bounds(n_anchors, world, rank)
-        iou = O.sph2pob_iou(anchors[lo:hi], gts, "efficient").float()            # [n_local, G]
+        cap, G = block_capacity(n_anchors, world), gts.size(0)
+        block = key_block(n_anchors, G, world, "cpu")
+        assert block.numel() == cap + G and not block.any()
         if hi > lo:
+            iou = O.sph2pob_iou(anchors[lo:hi], gts, "efficient").float()        # [n_local, G]
             a_max, a_arg = iou.max(dim=1)
             g_max, g_arg = iou.max(dim=0)
-            a_keys, g_keys = pack_keys(a_max, a_arg), pack_keys(g_max, g_arg + lo)
-        else:
-            a_keys = torch.zeros(0, dtype=torch.int64)
-            g_keys = pack_keys(torch.zeros(gts.size(0)), torch.full((gts.size(0),), lo))
-        res = gather_assignment(a_keys, g_keys, n_anchors)
+            # what the kernel leaves in the block: key 0 where nothing overlaps, GLOBAL anchor indices for the GT keys
+            block[:hi - lo] = torch.where(a_max > 0, pack_keys(a_max, a_arg), torch.zeros_like(a_arg))
+            block[cap:] = torch.where(g_max > 0, pack_keys(g_max, g_arg + lo), torch.zeros_like(g_arg))
+        gathered = exchange_blocks(block)
+        assert gathered.shape == (world, cap + G)
+        res = unpack_gathered_reference(gathered, world, n_anchors, G, cap)
         torch.save([r.clone() for r in res], os.path.join(out_dir, "rank%d.pt" % rank))
     finally:
         dist.destroy_process_group()
@@ -70,8 +95,8 @@ def test_sharded_assignment_equals_single_process(tmp_path, world, n_anchors):
     a_max, a_arg = iou.max(dim=1)
     g_max = iou.max(dim=0)[0]
     # lowest-index tie rule, computed independently of torch.max's convention
-    g_arg = torch.tensor([int(torch.nonzero(iou[:, j] == g_max[j])[0]) for j in range(gts.size(0))])
-    a_arg_low = torch.tensor([int(torch.nonzero(iou[i] == a_max[i])[0]) for i in range(n_anchors)])
+    g_arg = torch.tensor([int(torch.nonzero(iou[:, j] == g_max[j])[0]) if g_max[j] > 0 else 0 for j in range(gts.size(0))])
+    a_arg_low = torch.tensor([int(torch.nonzero(iou[i] == a_max[i])[0]) if a_max[i] > 0 else 0 for i in range(n_anchors)])
     for rank in range(world):
         ra_max, ra_arg, rg_max, rg_arg = torch.load(os.path.join(str(tmp_path), "rank%d.pt" % rank))
         assert torch.equal(ra_max, a_max) and torch.equal(ra_arg, a_arg_low)
