@@ -1,19 +1,23 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the spherical-box IoU hot path (BASELINE.json metric: Sph2Pob-IoU pairs/s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload assign|sweep] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload sweep|assign] [--impl reference]
 
-Default workload = BASELINE.json configs[1] ("assign"): RetinaNet label assignment, pairwise
-Sph2Pob-efficient IoU of 32 RBFoV GT x 98,208 FPN anchors for each of 16 images through the
-registry calculator ``SphOverlaps2D('sph2pob_efficient_iou', 5)`` (one "step" = the 16 matrices).
-N>1 (torchrun, one rank per GPU): every rank processes its own 16 images -- weak scaling, no data-path
-collective (images are independent).  ``--workload sweep`` is configs[4]: the
-1,048,576 x 1,024 RBFoV sweep, anchors row-sharded over the ranks, fused max/argmax, NCCL gather of
-the packed per-anchor / per-GT results inside the timed region (strong scaling).
+Default workload = BASELINE.json configs[4] ("sweep"), the N x M configuration the metric is quoted on at 1/2/4/8 B200:
+pairwise Sph2Pob-efficient IoU of 1,048,576 x 1,024 random RBFoV boxes (1.07 G pairs) with the fused per-anchor and
+per-GT max/argmax -- the reduction MaxIoUAssigner applies to the matrix (mmdet/core/bbox/assigners/max_iou_assigner.py:
+173-176) -- through ``sph_retina_b200.sharded.sharded_max_overlaps``.  One "step" = the whole sweep.  With N > 1
+(torchrun, one rank per GPU) the anchors are row-sharded over the ranks, the 1,024 GT replicated, and the timed step
+contains the NCCL all_gather of the packed keys and the unpack launch: STRONG scaling, total work fixed.  N = 1 runs the
+very same code path (the collective degenerates to a view).  ``--workload assign`` is configs[1] (16 per-image
+``SphOverlaps2D`` calls of 32 GT x 98,208 anchors, full matrices written; replicas, weak scaling); it is also timed
+briefly under ``other_configs`` of the default run, as are configs[0], [2], [3].
 
-One JSON line on stdout (rank 0).  ``--impl reference`` times the reference's CPU implementation of
-the same call (its PyTorch-eager algorithm as restated in oracle/sph_oracle.py; the reference is
-pure Python that needs mmcv and cannot be installed offline -- DESIGN.md) on the host cores.
+One JSON line on stdout (rank 0).  ``--impl reference`` times the reference's own CPU implementation of the same call --
+its unmodified Python files, copied by ``__graft_entry__.build()`` into the git-ignored ``oracle/_ref/`` and imported
+through ``oracle/ref_harness.py`` (the absent mmcv op bound to the reference's vendored ``diff_iou_rotated.py``); if
+``oracle/_ref`` is missing, the torch restatement ``oracle/sph_oracle.py`` ("port") -- on the host cores, each step a
+bounded row slice of the sweep.
 """
 from __future__ import annotations
 
@@ -32,6 +36,10 @@ sys.path.insert(0, ROOT)
 METRIC = "sph2pob_iou_pairs_per_s"
 UNIT = "pairs/s"
 IMAGES, GTS, FLOP_PER_PAIR = 16, 32, 512.0      # W = 512 flop per Sph2Pob-IoU pair
+SWEEP_ANCHORS, SWEEP_GTS = 1 << 20, 1024        # BASELINE.json configs[4]
+REF_ROWS_PER_STEP = 4096                         # reference arm: anchors per step (x 1024 GT = 4.2 M pairs, ~1 s of CPU)
+SWEEP_WORKLOAD = ("sweep: 1,048,576 x 1,024 RBFoV Sph2Pob-efficient IoU (BASELINE configs[4]), anchors row-sharded over the GPUs, "
+                  "fused per-anchor and per-GT max/argmax, one NCCL all_gather of packed keys + one unpack launch in the timed region")
 HBM_FALLBACK_GBS = 6650.0                       # B200_PROFILING.md fallback if MEASURED_PEAKS.json is absent
 
 
@@ -204,39 +212,63 @@ def quick(torch, fn, iters=10, warmup=3, flush=None):
 
 
 # ---------------------------------------------------------------------------------------------------
-# CPU side: the oracle as the reported baseline / the reference arm
+# CPU side: the reference's own implementation (oracle/_ref) or its restatement as the reported baseline / reference arm
 # ---------------------------------------------------------------------------------------------------
-def cpu_port_assign(torch, gts, anchors, images, repeats=1):
-    """The reference's CPU algorithm (PyTorch eager, fp32, all host threads) on `images` images."""
+def sweep_inputs():
+    """BASELINE configs[4]: A = generate_boxes(1,048,576, alpha/beta (1,100), 'rbfov') seed 0 as bboxes1
+    (rows), G = generate_boxes(1,024, same) seed 1 as bboxes2."""
+    from sph_retina_b200 import synthetic as S
+    A = S.generate_boxes(SWEEP_ANCHORS, alpha_range=(1, 100), beta_range=(1, 100), box="rbfov", seed=0)
+    G = S.generate_boxes(SWEEP_GTS, alpha_range=(1, 100), beta_range=(1, 100), box="rbfov", seed=1)
+    return A, G
+
+
+def load_cpu_reference():
+    """(callable(b1, b2) -> [R, C] IoU matrix on the CPU, kind, description).  kind "reference": the reference's own
+    sph2pob_efficient_iou from the files under oracle/_ref (copied there by __graft_entry__.build() in the build
+    container; /root/reference itself does not exist on the GPU box).  kind "port": oracle/sph_oracle.py."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    ref_root = os.path.join(ROOT, "oracle", "_ref")
+    if os.path.isfile(os.path.join(ref_root, "sphdet", "iou", "sph_iou_api.py")):
+        try:
+            os.environ["SPH_REFERENCE_ROOT"] = ref_root
+            import ref_harness
+            ref_harness.REFERENCE_ROOT = ref_root
+            ns = ref_harness.load_reference()
+            return (lambda b1, b2: ns.sph2pob_efficient_iou(b1, b2, is_aligned=False), "reference",
+                    "the reference's own sphdet/iou/sph_iou_api.py::sph2pob_efficient_iou (files under oracle/_ref, unmodified; "
+                    "mmcv.ops.box_iou_rotated bound to the reference's vendored sphdet/iou/diff_iou_rotated.py), PyTorch eager, "
+                    "fp32, torch threads = cores")
+        except Exception as e:      # fall through to the port, and say why
+            log("bench.py: oracle/_ref present but not importable (%r); using the port" % (e,))
     import sph_oracle as O
-    best = None
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        for i in range(images):
-            O.sph2pob_iou(gts[i], anchors, "efficient")
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return images * gts.size(1) * anchors.size(0) / best, best
+    return (lambda b1, b2: O.sph2pob_iou(b1, b2, "efficient"), "port",
+            "oracle/sph_oracle.py: the reference's PyTorch-eager algorithm restated, fp32, torch threads = cores")
 
 
-def cpu_c_port_assign(gts, anchors):
-    """Second CPU line: float64 C restatement with OpenMP (oracle/sph_oracle.c)."""
+def cpu_sweep_slice(fn, A, G, row0, rows):
+    """One bounded sample of the sweep on the CPU: IoU(A[row0:row0+rows], G) and the two max/argmax reductions."""
+    m = fn(A[row0:row0 + rows], G)
+    return m.max(dim=1), m.max(dim=0)
+
+
+def cpu_c_port_sweep(A, G, rows=16384):
+    """Second CPU line: float64 C restatement with OpenMP (oracle/sph_oracle.c) on a row slice of the sweep."""
     import ctypes
     import numpy as np
     try:
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
         lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_build", "libsph_oracle.so"))
-    except Exception as e:  # pragma: no cover
+    except Exception:  # pragma: no cover
         return None
     fp, dp = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)
-    rows, cols = np.ascontiguousarray(gts[0].numpy()), np.ascontiguousarray(anchors.numpy())
-    out = np.empty((rows.shape[0], cols.shape[0]))
+    r, c = np.ascontiguousarray(A[:rows].numpy()), np.ascontiguousarray(G.numpy())
+    out = np.empty((r.shape[0], c.shape[0]))
     best = None
     for _ in range(3):
         t0 = time.perf_counter()
-        lib.sph_oracle_iou_pairwise(0, rows.ctypes.data_as(fp), ctypes.c_long(rows.shape[0]), cols.ctypes.data_as(fp),
-                                    ctypes.c_long(cols.shape[0]), rows.shape[1], 0, 0, out.ctypes.data_as(dp))
+        lib.sph_oracle_iou_pairwise(0, r.ctypes.data_as(fp), ctypes.c_long(r.shape[0]), c.ctypes.data_as(fp),
+                                    ctypes.c_long(c.shape[0]), r.shape[1], 0, 0, out.ctypes.data_as(dp))
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     return out.size / best
@@ -247,33 +279,30 @@ def run_reference(args):
     if rank != 0:
         return
     import torch
-    from sph_retina_b200 import synthetic as S
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    gts, anchors = S.assignment_batch(IMAGES, GTS)
-    # bounded sample per step: one image's matrix; anchors are strided down if K+W would take too long
-    total_steps = args.steps + args.warmup
-    stride = max(1, (total_steps + 29) // 30)
-    anc = anchors[::stride].contiguous()
-    pairs_per_step = GTS * anc.size(0)
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import sph_oracle as O
-    for i in range(args.warmup):
-        O.sph2pob_iou(gts[i % IMAGES], anc, "efficient")
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        O.sph2pob_iou(gts[i % IMAGES], anc, "efficient")
-    dt = time.perf_counter() - t0
+    A, G = sweep_inputs()
+    fn, kind, what = load_cpu_reference()
+    rows = REF_ROWS_PER_STEP
+    windows = SWEEP_ANCHORS // rows
+    pairs_per_step = rows * SWEEP_GTS
+    with torch.no_grad():
+        for i in range(args.warmup):
+            cpu_sweep_slice(fn, A, G, (i % windows) * rows, rows)
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            cpu_sweep_slice(fn, A, G, ((args.warmup + i) % windows) * rows, rows)
+        dt = time.perf_counter() - t0
     value = pairs_per_step * args.steps / dt
-    sample = "1 image per step: %d GT x %d anchors (anchor stride %d) = %d pairs" % (GTS, anc.size(0), stride, pairs_per_step)
+    sample = ("per step: %d consecutive anchors (a different window each step) x %d GT = %d pairs of the 1,048,576 x 1,024 sweep, "
+              "IoU matrix + max/argmax over both axes" % (rows, SWEEP_GTS, pairs_per_step))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "assign: pairwise Sph2Pob-efficient IoU, 32 RBFoV GT x 98208 anchors (512x1024, 9/loc), batch 16",
-                   "api": "sph2pob_efficient_iou (CPU, PyTorch eager)", "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                         "what": "oracle/sph_oracle.py: the reference's PyTorch-eager algorithm, fp32, torch threads = cores"},
+        "config": {"workload": SWEEP_WORKLOAD, "api": "sph2pob_efficient_iou(A, G, is_aligned=False) (CPU, PyTorch eager)",
+                   "pairs_per_step": SWEEP_ANCHORS * SWEEP_GTS, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "what": what},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -299,19 +328,28 @@ def fp32_peak(torch, native, dev):
     return best
 
 
-def other_configs(torch, native, dev, flush, hbm_peak_gbs=6544.3):
+def other_configs(torch, native, dev, flush, hbm_peak_gbs=6544.3, fp32_peak_tf=67.4):
     """The remaining BASELINE.json configurations, timed briefly on one GPU (kernel time, inputs resident)."""
     from sph_retina_b200 import synthetic as S
     from sph_retina_b200.sphdet.bbox.nms import sph_batched_nms_images
-    from sph_retina_b200.sphdet.iou import SphOverlaps2D, fov_iou, sph2pob_efficient_iou, sph_iou, sph_max_overlaps
+    from sph_retina_b200.sphdet.iou import SphOverlaps2D, fov_iou, sph2pob_efficient_iou, sph_iou
     from sph_retina_b200.sphdet.losses import Sph2PobIoULoss
     out = {}
     n = 1_000_000
     for box in ("bfov", "rbfov"):
         b1 = S.generate_boxes(n, alpha_range=(1, 100), beta_range=(1, 100), box=box, seed=0).to(dev)
         b2 = S.generate_boxes(n, alpha_range=(1, 100), beta_range=(1, 100), box=box, seed=1).to(dev)
-        ms = quick(torch, lambda: sph2pob_efficient_iou(b1, b2, is_aligned=True), flush=flush)
-        out["aligned_1M_%s" % box] = {"ms": ms, "pairs_per_s": n / ms * 1e3}
+        ms = quick(torch, lambda: sph2pob_efficient_iou(b1, b2, is_aligned=True), iters=20, flush=flush)
+        native.set_dense(True)
+        ms_dense = quick(torch, lambda: sph2pob_efficient_iou(b1, b2, is_aligned=True), flush=flush)
+        native.set_dense(False)
+        # configs[0] under the bench's own timing: ONE call, L2 flushed before it, CUDA events around it
+        out["aligned_1M_%s" % box] = {"ms": ms, "pairs_per_s": n / ms * 1e3,
+                                      "fp32_frac": n * FLOP_PER_PAIR / (ms * 1e-3) / 1e12 / fp32_peak_tf,
+                                      "dense_ms": ms_dense, "dense_pairs_per_s": n / ms_dense * 1e3,
+                                      "dense_fp32_frac": n * FLOP_PER_PAIR / (ms_dense * 1e-3) / 1e12 / fp32_peak_tf,
+                                      "hbm_gbs": n * (36 if box == "bfov" else 44) / ms / 1e6,
+                                      "timing": "single call, L2 flushed (256 MB write) before every call, CUDA events, median of 20"}
         if box == "bfov":
             for name, fn in (("sph_iou", sph_iou), ("fov_iou", fov_iou)):
                 ms = quick(torch, lambda: fn(b1, b2, is_aligned=True), flush=flush)
@@ -337,10 +375,6 @@ def other_configs(torch, native, dev, flush, hbm_peak_gbs=6544.3):
     out["box_format_16M_bfov"] = {"sph2planar_ms": ms, "planar2sph_ms": ms2, "hbm_gbs_sph2planar": nb * 32 / ms / 1e6,
                                   "hbm_frac_of_measured_peak": nb * 32 / ms / 1e6 / hbm_peak_gbs}
     del f4, pl
-    native.set_dense(True)
-    ms = quick(torch, lambda: sph2pob_efficient_iou(b1, b2, is_aligned=True), flush=flush)
-    native.set_dense(False)
-    out["aligned_1M_rbfov_dense"] = {"ms": ms, "pairs_per_s": n / ms * 1e3}
     # the same calls at 16 M pairs (inputs 512 MB, larger than L2): the throughput once the ~10 us of launch + ramp are amortised
     n16 = 16_000_000
     c1 = S.generate_boxes(n16, alpha_range=(1, 100), beta_range=(1, 100), box="bfov", seed=0).to(dev)
@@ -362,6 +396,28 @@ def other_configs(torch, native, dev, flush, hbm_peak_gbs=6544.3):
         ms_f = quick(torch, lambda: L(pred, target), flush=flush)
     ms_fb = quick(torch, fwd_bwd, flush=flush)
     out["loss_200k_rbfov"] = {"fwd_ms": ms_f, "fwd_bwd_ms": ms_fb, "pairs_per_s_fwd_bwd": 200_000 / ms_fb * 1e3}
+    # the same forward + backward captured in a CUDA graph (the step a training loop replays): what the device needs for
+    # it once the ~10 eager autograd / allocator steps of the host are out of the way
+    try:
+        p_static = pred.detach().clone().requires_grad_(True)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                p_static.grad = None
+                L(p_static, target).backward()
+        torch.cuda.current_stream().wait_stream(side)
+        p_static.grad = None
+        gl = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gl):
+            loss_static = L(p_static, target)
+            loss_static.backward()
+        ms_g = quick(torch, gl.replay, flush=flush)
+        out["loss_200k_rbfov"].update({"fwd_bwd_graph_ms": ms_g, "pairs_per_s_fwd_bwd_graph": 200_000 / ms_g * 1e3,
+                                       "fp32_frac_graph": 200_000 * 3 * FLOP_PER_PAIR / (ms_g * 1e-3) / 1e12 / fp32_peak_tf})
+        del gl
+    except Exception as e:      # capture is an extra: never lose the line over it
+        out["loss_200k_rbfov"]["fwd_bwd_graph_error"] = repr(e)
     # the other losses on the same OBBs: one launch each for loss + both gradients
     from sph_retina_b200.sphdet.losses import Sph2PobGDLoss, Sph2PobKFLoss, Sph2PobL1Loss
     other = {}
@@ -411,6 +467,25 @@ def other_configs(torch, native, dev, flush, hbm_peak_gbs=6544.3):
     calc = SphOverlaps2D('sph2pob_efficient_iou', 5)
     ms = quick(torch, lambda: calc(gts.view(-1, 5), anchors).view(IMAGES, GTS, -1), flush=flush)
     out["assign_16img_one_call"] = {"ms": ms, "pairs_per_s": IMAGES * GTS * anchors.size(0) / ms * 1e3}
+    # configs[1] the drop-in way: one SphOverlaps2D call per image, as MaxIoUAssigner makes them (round 1's headline)
+    ms = quick(torch, lambda: [calc(gts[i], anchors) for i in range(IMAGES)], iters=20, flush=flush)
+    out["assign_16img_per_image_calls"] = {"ms": ms, "pairs_per_s": IMAGES * GTS * anchors.size(0) / ms * 1e3,
+                                           "fp32_frac": IMAGES * GTS * anchors.size(0) * FLOP_PER_PAIR / (ms * 1e-3) / 1e12 / fp32_peak_tf,
+                                           "what": "16 x k_iou_rows32 (one launch per call, chained by programmatic dependent launch)"}
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            [calc(gts[i], anchors) for i in range(IMAGES)]
+        torch.cuda.current_stream().wait_stream(side)
+        ga = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(ga):
+            keep_a = [calc(gts[i], anchors) for i in range(IMAGES)]
+        ms = quick(torch, ga.replay, iters=20, flush=flush)
+        out["assign_16img_per_image_calls"].update({"graph_ms": ms, "graph_pairs_per_s": IMAGES * GTS * anchors.size(0) / ms * 1e3})
+        del ga, keep_a
+    except Exception as e:
+        out["assign_16img_per_image_calls"]["graph_error"] = repr(e)
     # the headline step (one call per image) with the 16 calls alternating between two CUDA streams: the drain of one
     # launch (its last CTAs, ~a quarter of a 31 us kernel) is covered by the start of the next
     s2 = [torch.cuda.Stream(), torch.cuda.Stream()]
@@ -439,11 +514,6 @@ def other_configs(torch, native, dev, flush, hbm_peak_gbs=6544.3):
     ms_c = quick(torch, lambda: asg.assign_batch(anchors, gl, ll), iters=5, flush=flush)
     out["assigner_16img"] = {"matrix_then_assign_ms": ms_a, "fused_per_image_ms": ms_b, "fused_batch_ms": ms_c,
                              "pairs_per_s_fused_batch": IMAGES * GTS * anchors.size(0) / ms_c * 1e3}
-    A = S.generate_boxes(1 << 20, alpha_range=(1, 100), beta_range=(1, 100), box="rbfov", seed=0).to(dev)
-    G = S.generate_boxes(1024, alpha_range=(1, 100), beta_range=(1, 100), box="rbfov", seed=1).to(dev)
-    ms = quick(torch, lambda: sph_max_overlaps(A, G), iters=3, warmup=1, flush=flush)
-    out["sweep_1Mx1024_fused_max"] = {"ms": ms, "pairs_per_s": (1 << 30) / ms * 1e3}
-    del A, G
     # configs[0] as a stream of calls: 8 input sets (288 MB > L2, nothing re-used between calls), the 8 calls captured in
     # one CUDA graph -- no host launch gaps, no dirty L2 lines from a flush write
     sets = [(S.generate_boxes(n, alpha_range=(1, 100), beta_range=(1, 100), box="bfov", seed=10 + 2 * i).to(dev),
@@ -484,6 +554,16 @@ def other_configs(torch, native, dev, flush, hbm_peak_gbs=6544.3):
     return out
 
 
+def ncu_reference(workload):
+    """Counter figures of the dominant kernel from the committed ncu capture (profiles/roofline_ncu.json, written by
+    tools/profile_collect.py from the `ncu --set full` report of the same command)."""
+    path = os.path.join(ROOT, "profiles", "roofline_ncu.json")
+    try:
+        return json.load(open(path)).get(workload)
+    except Exception:
+        return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -495,7 +575,7 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         # one slice of the host cores per rank: the launch thread of a rank is then never queued behind another rank's
-        # threads (torchrun does not pin; the per-image calls of the assign workload are ~30 us apart)
+        # threads (torchrun does not pin)
         try:
             cores = sorted(os.sched_getaffinity(0))
             per = len(cores) // int(os.environ.get("LOCAL_WORLD_SIZE", world))
@@ -512,46 +592,62 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
 
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     flush = L2Flusher(torch, dev)
     peaks, peaks_src = measured_peaks()
-    gts_h, anchors_h = S.assignment_batch(IMAGES, GTS)
-    if world > 1:       # every rank gets its own images (weak scaling)
-        gts_h = torch.stack([S.generate_boxes(GTS, alpha_range=(5, 120), beta_range=(5, 120), box="rbfov",
-                                              seed=100 + rank * IMAGES + i) for i in range(IMAGES)])
     result = {}
     if args.workload == "assign":
+        gts_h, anchors_h = S.assignment_batch(IMAGES, GTS)
+        if world > 1:       # every rank gets its own images (weak scaling, replicas: SURVEY.md 8e)
+            gts_h = torch.stack([S.generate_boxes(GTS, alpha_range=(5, 120), beta_range=(5, 120), box="rbfov",
+                                                  seed=100 + rank * IMAGES + i) for i in range(IMAGES)])
         gts, anchors = gts_h.to(dev), anchors_h.to(dev)
         calc = SphOverlaps2D('sph2pob_efficient_iou', 5)
         pairs_per_step = IMAGES * GTS * anchors.size(0)
 
         def step():
             return [calc(gts[i], anchors) for i in range(IMAGES)]
-        launches_per_step = IMAGES
+
+        def kernel_call():
+            return calc(gts[0], anchors)
+        kernel_name, kernels_per_step, pairs_per_kernel = "k_iou_rows32<5>", IMAGES, GTS * anchors.size(0)
+        rows_k, cols_k = gts[0], anchors
         scaling = "weak"
         total_pairs_per_step = pairs_per_step * world
+        hbm_bytes_per_kernel = GTS * anchors.size(0) * 4 + (GTS + anchors.size(0)) * 5 * 4
         workload = ("assign: pairwise Sph2Pob-efficient IoU, 32 RBFoV GT x 98208 anchors (512x1024, 9/loc), batch 16 "
-                    "per GPU, full [32 x 98208] fp32 matrix written per image")
+                    "per GPU (replicas), full [32 x 98208] fp32 matrix written per image (BASELINE configs[1])")
     else:
-        from sph_retina_b200.sharded import shard_bounds, sharded_max_overlaps
-        n_a = 1 << 20
-        A = S.generate_boxes(n_a, alpha_range=(1, 100), beta_range=(1, 100), box="rbfov", seed=0)
-        G = S.generate_boxes(1024, alpha_range=(1, 100), beta_range=(1, 100), box="rbfov", seed=1).to(dev)
-        lo, hi = shard_bounds(n_a, world, rank)
-        A_loc = A[lo:hi].contiguous().to(dev)
-        pairs_per_step = (hi - lo) * 1024
-        total_pairs_per_step = n_a * 1024
+        from sph_retina_b200.sharded import block_capacity, key_block, shard_bounds, sharded_max_overlaps
+        A_h, G_h = sweep_inputs()
+        lo, hi = shard_bounds(SWEEP_ANCHORS, world, rank)
+        A_loc_h = A_h[lo:hi].contiguous()
+        A_loc, G = A_loc_h.to(dev), G_h.to(dev)
+        pairs_per_step = (hi - lo) * SWEEP_GTS
+        total_pairs_per_step = SWEEP_ANCHORS * SWEEP_GTS
 
         def step():
-            return sharded_max_overlaps(A_loc, G, n_a, lo, anchors_are='bboxes1')
-        launches_per_step = 5
+            return sharded_max_overlaps(A_loc, G, SWEEP_ANCHORS, lo, anchors_are='bboxes1')
+
+        _blk = key_block(SWEEP_ANCHORS, SWEEP_GTS, world, dev, fresh=True)
+        _cap = block_capacity(SWEEP_ANCHORS, world)
+
+        def kernel_call():      # the step without the exchange: k_box_pre + k_iou_pairwise2 into a communication block
+            return native.iou_pairwise_keys("sph2pob_efficient", A_loc, G, row_base=lo, row_keys_out=_blk[:hi - lo], col_keys_out=_blk[_cap:])
+        kernel_name, kernels_per_step, pairs_per_kernel = "k_iou_pairwise2<5,32>", 1, pairs_per_step
+        rows_k, cols_k = A_loc, G
         scaling = "strong"
-        workload = ("sweep: 1,048,576 x 1,024 RBFoV Sph2Pob-efficient IoU, anchors row-sharded over the GPUs, fused "
-                    "per-anchor and per-GT max/argmax, NCCL all_gather + all_reduce(MAX) of packed keys in the timed region")
+        hbm_bytes_per_kernel = (A_loc.size(0) + SWEEP_GTS) * (5 * 4 + 8)
+        workload = SWEEP_WORKLOAD
 
     # ---- timed region (device time, per-step events, L2 flushed between steps) --------------------
     # rank 0 watches every local GPU of the run; the other ranks do not run a sampler thread
     sampler = ClockSampler(list(range(int(os.environ.get("LOCAL_WORLD_SIZE", world)))) if rank == 0 else [], external=world > 1)
-    l0 = native.launches
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
@@ -560,61 +656,93 @@ def run_ours(args):
     ms = time_steps(torch, step, args.steps, 0, flush, barrier)
     clocks = sampler.stop()
     gpu_launches = native.launches - l0
-    total_ms = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(total_ms.item())
+    total_ms = max_over_ranks(sum(ms))
     ms_per_step = total_ms / args.steps
     value = total_pairs_per_step / (ms_per_step * 1e-3)
 
+    # ---- the dominant kernel against the roofline that bounds it: FP32 / ALU instruction issue -------------------
+    # (W = 512 flop per pair for ALL pairs, early-outs included; the early-out rate and the dense
+    # throughput are printed next to it; the HBM view -- 8 B of keys per anchor, or 4 B per pair for the matrix -- is
+    # in roofline_hbm and says nothing about this kernel)
+    kernel_ms = statistics.median(time_steps(torch, kernel_call, 10, 3, flush, lambda: None))
     if rank == 0:
-        kernel_ms = statistics.mean(ms) / launches_per_step if args.workload == "assign" else statistics.mean(ms)
-        if args.workload == "assign":
-            bytes_per_launch = GTS * anchors.size(0) * 4 + (GTS + anchors.size(0)) * 5 * 4
-            pairs_per_launch = GTS * anchors.size(0)
-        else:
-            bytes_per_launch = (A_loc.size(0) + 1024) * (5 * 4 + 8)
-            pairs_per_launch = A_loc.size(0) * 1024
-        hbm_achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")     # dram bytes/launch from the committed ncu capture
-        if os.path.isfile(tpath):
-            try:
-                traffic = json.load(open(tpath)).get(args.workload)
-            except Exception:
-                traffic = None
-        roofline = {"bound": "hbm", "achieved": hbm_achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": hbm_achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peaks_src,
-                    "kernel": "k_iou_rows32" if args.workload == "assign" else "k_iou_pairwise2", "kernel_ms": kernel_ms,
-                    "algorithmic_bytes_per_launch": bytes_per_launch,
-                    "note": "kernel_ms = timed step / kernel launches per step (CUDA events on the launching stream, launch gaps "
-                            "included; the ncu launch list under profiles/ has the kernel alone).  HBM is NOT what bounds this "
-                            "kernel (4 B written per pair): see roofline_fp32"}
-        result["roofline"] = roofline
         peak_tf = fp32_peak(torch, native, dev)
-        tf = pairs_per_launch * FLOP_PER_PAIR / (kernel_ms * 1e-3) / 1e12
-        result["roofline_fp32"] = {"bound": "fp32", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
-                                   "peak_source": "FMA-chain probe (sphk_probe_fp32) on this GPU, same run",
-                                   "flop_per_pair": FLOP_PER_PAIR,
-                                   "note": "algorithmic 512 flop/pair (SURVEY.md 8d) counted for ALL pairs, early-outs included"}
+        tf = pairs_per_kernel * FLOP_PER_PAIR / (kernel_ms * 1e-3) / 1e12
+        live = native.prefilter_live_pairs(rows_k, cols_k)
+        native.set_dense(True)
+        dense_ms = statistics.median(time_steps(torch, kernel_call, 5, 2, flush, lambda: None))
+        native.set_dense(False)
+        prof = ncu_reference(args.workload) or {}
+        nominal = 148 * 128 * 2 * (peaks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e12
+        result["roofline"] = {
+            "bound": "fp32", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
+            "traffic": prof.get("dram_bytes_per_launch"), "kernel": kernel_name, "kernel_ms": kernel_ms,
+            "kernels_per_step": kernels_per_step, "kernel_share_of_step": kernel_ms * kernels_per_step / statistics.mean(ms),
+            "flop_per_pair": FLOP_PER_PAIR, "pairs_per_launch": pairs_per_kernel,
+            "peak_source": "FMA-chain probe (sphk_probe_fp32) on this GPU in this run; nominal 148 SM x 128 lanes x 2 x %.0f MHz = %.1f"
+                           % (peaks.get("sm_max_mhz") or 1965.0, nominal),
+            "peak_nominal": nominal, "frac_of_nominal": tf / nominal,
+            "early_out_rate": 1.0 - live / float(pairs_per_kernel), "live_pairs": live,
+            "dense_kernel_ms": dense_ms, "dense_pairs_per_s": pairs_per_kernel / (dense_ms * 1e-3),
+            "dense_frac": pairs_per_kernel * FLOP_PER_PAIR / (dense_ms * 1e-3) / 1e12 / peak_tf,
+            "ncu": prof.get("counters"), "ncu_source": prof.get("source"),
+            "note": "achieved = ALL pairs of one launch x 512 flop (SURVEY.md 8d) / kernel_ms; kernel_ms = median of 10 launches of the "
+                    "kernel alone (k_box_pre included), CUDA events on the launching stream, L2 flushed; early_out_rate = pairs the "
+                    "prefilter proves disjoint (exact 0 in the reference); dense_* = the same launch with the early-outs disabled "
+                    "(sphk_set_dense); ncu = issue-slot / pipe utilisation of the committed `ncu --set full` capture"}
+        hbm_achieved = hbm_bytes_per_kernel / (kernel_ms * 1e-3) / 1e9
+        result["roofline_hbm"] = {"bound": "hbm", "achieved": hbm_achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                  "frac": hbm_achieved / peaks["hbm_gbs"], "peak_source": peaks_src,
+                                  "algorithmic_bytes_per_launch": hbm_bytes_per_kernel, "traffic": prof.get("dram_bytes_per_launch"),
+                                  "note": "not the bound of this kernel (boxes in, 8 B of packed keys per box out)"}
 
     # ---- end to end: host buffers in, host result out, through the public API ----------------------
     e2e = None
     if args.no_e2e:
         e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "note": "skipped (--no-e2e)"}
-    elif args.workload == "assign":
+    elif args.workload == "sweep":
+        n_loc = hi - lo
+        A_pin, G_pin = A_loc_h.pin_memory(), G_h.pin_memory()
+        A_d, G_d = torch.empty_like(A_pin, device=dev), torch.empty_like(G_pin, device=dev)
+        amax_pin = torch.empty(n_loc, dtype=torch.float32).pin_memory()
+        aarg_pin = torch.empty(n_loc, dtype=torch.int64).pin_memory()
+        gmax_pin = torch.empty(SWEEP_GTS, dtype=torch.float32).pin_memory()
+        garg_pin = torch.empty(SWEEP_GTS, dtype=torch.int64).pin_memory()
+
+        def e2e_step():
+            # every rank: its shard of the anchors and the GT from pinned host memory -> the sharded call (kernels +
+            # collective + unpack) -> its own slice of the per-anchor result and the per-GT result back to pinned host
+            # memory: across the ranks the host holds the whole result exactly once
+            A_d.copy_(A_pin, non_blocking=True)
+            G_d.copy_(G_pin, non_blocking=True)
+            am, aa, gm, ga = sharded_max_overlaps(A_d, G_d, SWEEP_ANCHORS, lo, anchors_are='bboxes1')
+            amax_pin.copy_(am[lo:hi], non_blocking=True)
+            aarg_pin.copy_(aa[lo:hi], non_blocking=True)
+            gmax_pin.copy_(gm, non_blocking=True)
+            garg_pin.copy_(ga, non_blocking=True)
+        e2e_ms = time_steps(torch, e2e_step, max(5, args.steps // 2), 3, flush, barrier)
+        t = max_over_ranks(statistics.mean(e2e_ms))
+        e2e = {"value": total_pairs_per_step / (t * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": SWEEP_ANCHORS * 20 + world * SWEEP_GTS * 20,
+               "d2h_bytes_per_step": SWEEP_ANCHORS * 12 + world * SWEEP_GTS * 12,
+               "ms_per_step": t, "api": "sph_retina_b200.sharded.sharded_max_overlaps(anchors_shard, gts, n_anchors, offset)",
+               "copies": "per rank and step: H2D of its anchor shard (n/N x 20 B) + the GT (20 kB) from pinned memory; D2H of its "
+                         "slice of the gathered (max fp32, argmax int64) per anchor + the per-GT result into pinned memory; "
+                         "byte counts are whole-job sums over the ranks"}
+        if world == 1 and rank == 0:
+            # the same result without the fused reduction: the full 4.3 GB matrix does not leave the device in the
+            # reference either (MaxIoUAssigner reduces it on the GPU); listed for scale
+            e2e["matrix_bytes_not_moved"] = SWEEP_ANCHORS * SWEEP_GTS * 4
+    else:
         gts_pin, anchors_pin = gts_h.pin_memory(), anchors_h.pin_memory()
         out_pin = torch.empty((IMAGES, GTS, anchors_h.size(0)), dtype=torch.float32).pin_memory()
         gts_d, anchors_d = torch.empty_like(gts_pin, device=dev), torch.empty_like(anchors_pin, device=dev)
-
         side = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
 
         def e2e_step():
             # H2D of this step's inputs on the launching stream, then the 16 calculator calls alternate between two
             # side streams, each call followed by the D2H of its matrix on its own stream: the kernel of image i + 1 runs
-            # while the copy engine drains image i (every call allocates, computes and copies on ONE stream, so the
-            # caching allocator needs no cross-stream bookkeeping).  The side streams fork from / join the launching
-            # stream, where the timing events are.  The step is bound by the 201 MB D2H over PCIe.
+            # while the copy engine drains image i.  The step is bound by the 201 MB D2H over PCIe.
             gts_d.copy_(gts_pin, non_blocking=True)
             anchors_d.copy_(anchors_pin, non_blocking=True)
             cur = torch.cuda.current_stream(dev)
@@ -626,65 +754,52 @@ def run_ours(args):
             for st in side:
                 cur.wait_stream(st)
         e2e_ms = time_steps(torch, e2e_step, max(3, args.steps // 2), 2, flush, barrier)
-        t = torch.tensor([statistics.mean(e2e_ms)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = {"value": total_pairs_per_step / (float(t.item()) * 1e-3), "unit": UNIT,
+        t = max_over_ranks(statistics.mean(e2e_ms))
+        e2e = {"value": total_pairs_per_step / (t * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": gts_pin.numel() * 4 + anchors_pin.numel() * 4, "d2h_bytes_per_step": out_pin.numel() * 4,
-               "ms_per_step": float(t.item()), "api": "SphOverlaps2D('sph2pob_efficient_iou', 5)(gt, anchors) x 16, pinned host in/out",
+               "ms_per_step": t, "api": "SphOverlaps2D('sph2pob_efficient_iou', 5)(gt, anchors) x 16, pinned host in/out",
                "streams": "calls alternate between 2 CUDA streams (compute of one image overlaps the D2H of the previous one)"}
-        # the consumer only needs max/argmax (MaxIoUAssigner): fused variant, result = 12 B per anchor + 12 B per GT
-        amax_pin = torch.empty((IMAGES, anchors_h.size(0)), dtype=torch.float32).pin_memory()
-        aarg_pin = torch.empty((IMAGES, anchors_h.size(0)), dtype=torch.int64).pin_memory()
-        gmax_pin = torch.empty((IMAGES, GTS), dtype=torch.float32).pin_memory()
-        garg_pin = torch.empty((IMAGES, GTS), dtype=torch.int64).pin_memory()
-
-        def e2e_fused_step():
-            gts_d.copy_(gts_pin, non_blocking=True)
-            anchors_d.copy_(anchors_pin, non_blocking=True)
-            for i in range(IMAGES):
-                rmax, rarg, cmax, carg = sph_max_overlaps(gts_d[i], anchors_d)
-                amax_pin[i].copy_(cmax, non_blocking=True); aarg_pin[i].copy_(carg, non_blocking=True)
-                gmax_pin[i].copy_(rmax, non_blocking=True); garg_pin[i].copy_(rarg, non_blocking=True)
-        f_ms = statistics.mean(time_steps(torch, e2e_fused_step, max(3, args.steps // 2), 2, flush, barrier))
-        result["e2e_fused_assign"] = {"value": total_pairs_per_step / (f_ms * 1e-3), "unit": UNIT, "ms_per_step": f_ms,
-                                      "d2h_bytes_per_step": IMAGES * (anchors_h.size(0) + GTS) * 12,
-                                      "api": "sph_max_overlaps(gt, anchors): max/argmax per anchor and per GT, no matrix"}
-    else:
-        e2e = {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-               "note": "sweep inputs are resident by definition of the sharded workload; see the assign workload for e2e"}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": workload, "api": "SphOverlaps2D('sph2pob_efficient_iou', box_version=5)",
+            "config": {"workload": workload,
+                       "api": "sharded_max_overlaps -> sphk_iou_pairwise_keys + sphk_unpack_gathered_keys (Sph2Pob-efficient, box_version 5)"
+                              if args.workload == "sweep" else "SphOverlaps2D('sph2pob_efficient_iou', box_version=5)",
                        "pairs_per_step": total_pairs_per_step,
-                       "l2": "256 MB written between timed steps (L2 flush); each step also writes %d MB of output" %
-                             (pairs_per_step * 4 >> 20) if args.workload == "assign" else "256 MB written between timed steps (L2 flush)",
-                       "timing": "CUDA events per step on the launching stream, sum over K steps, max over ranks"},
+                       "l2": "256 MB written between timed steps (L2 flush)",
+                       "timing": "CUDA events per step on the launching stream, sum over K steps, max over ranks",
+                       "collectives_per_step": (1 if world > 1 else 0) if args.workload == "sweep" else 0},
             "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches,
         }
         line.update(result)
-        if world == 1 and not args.no_cpu:
+        if world == 1 and not args.no_cpu and args.workload == "sweep":
             cores = os.cpu_count() or 1
             torch.set_num_threads(cores)
-            v, secs = cpu_port_assign(torch, gts_h, anchors_h, images=2, repeats=2)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": "2 of the 16 images (2 x 32 x 98208 = 6.3 M pairs), best of 2, %.1f s" % secs,
-                                    "what": "oracle/sph_oracle.py: the reference's PyTorch-eager CPU algorithm, fp32, all host threads"}
-            c = cpu_c_port_assign(gts_h, anchors_h)
+            fn, kind, what = load_cpu_reference()
+            rows, best = 8192, None
+            with torch.no_grad():
+                for k in range(2):
+                    t0 = time.perf_counter()
+                    cpu_sweep_slice(fn, A_h, G_h, k * rows, rows)
+                    dt = time.perf_counter() - t0
+                    best = dt if best is None else min(best, dt)
+            line["cpu_baseline"] = {"value": rows * SWEEP_GTS / best, "unit": UNIT, "cores": cores, "kind": kind,
+                                    "sample": "%d anchors x %d GT = %.1f M pairs of the sweep (IoU matrix + both max/argmax), best of 2 "
+                                              "windows, %.1f s" % (rows, SWEEP_GTS, rows * SWEEP_GTS / 1e6, best),
+                                    "what": what}
+            c = cpu_c_port_sweep(A_h, G_h)
             if c:
                 line["cpu_baseline_c_openmp"] = {"value": c, "unit": UNIT, "cores": cores, "kind": "port",
-                                                 "sample": "1 image (3.1 M pairs), best of 3",
+                                                 "sample": "16384 anchors x 1024 GT (16.8 M pairs), best of 3",
                                                  "what": "oracle/sph_oracle.c: float64 scalar restatement, OpenMP"}
         if world == 1 and not args.no_extras:
-            if True:
-                try:
-                    line["other_configs"] = other_configs(torch, native, dev, flush, peaks["hbm_gbs"])
-                except Exception as e:   # the headline line must still be printed
-                    line["other_configs"] = {"error": repr(e)}
+            try:
+                line["other_configs"] = other_configs(torch, native, dev, flush, peaks["hbm_gbs"], line["roofline"]["peak"])
+            except Exception as e:   # the headline line must still be printed
+                line["other_configs"] = {"error": repr(e)}
         emit(line)
     if world > 1:
         dist.barrier()
@@ -697,7 +812,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="assign", choices=["assign", "sweep"])
+    ap.add_argument("--workload", default="sweep", choices=["sweep", "assign"])
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configs and keep the run short (ncu)")

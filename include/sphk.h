@@ -167,6 +167,15 @@ int64_t sphk_loss_reduce_partials(int64_t n);
 int sphk_loss_reduce(const float* pred, const float* target, const float* weight, int64_t n, int D, float scale,
                      float* partial, float* grad_pred, float* grad_target, void* stream);
 
+/* The same launch, finished on the device: *total = scale * sum_i weight[i] * (1 - iou[i]) (one float), so that the
+ * loss of a training step is ONE kernel and no reduction op follows.  The block that finishes last adds the per-block
+ * sums in index order (deterministic).  `scratch`: sphk_loss_total_scratch_bytes(n) bytes, 16-byte aligned, whose FIRST
+ * 16 bytes (the ticket counter) must be zero when the call starts; the kernel leaves them zero, so a buffer that was
+ * zeroed once can serve every later call of the same stream, whatever its n. */
+int64_t sphk_loss_total_scratch_bytes(int64_t n);
+int sphk_loss_reduce_total(const float* pred, const float* target, const float* weight, int64_t n, int D, float scale,
+                           float* total, void* scratch, float* grad_pred, float* grad_target, void* stream);
+
 /* The same two stages exposed separately so that the GIoU/DIoU/CIoU epilogues
  * (sphdet/losses/sph2pob_iou_loss.py:142-194) can stay as autograd code on the OBBs:
  *   sphk_obb_fwd : (pred,target)[n,D] -> obb1, obb2 [n,5] = (x, y, w, h, angle rad) after
@@ -289,9 +298,14 @@ int sphk_nms_images(const float* boxes, const float* scores, const int64_t* labe
  *   are bounded by (SURVEY.md 8d asks for a measured denominator): launches `blocks` x 256 threads,
  *   each running 8 independent chains of `iters` FMAs, i.e. 2*8*iters*256*blocks flop; sink[blocks*256].
  * sphk_set_dense: 1 disables the parity-safe "disjoint pair" early-outs of the Sph2Pob kernels so the
- *   dense throughput can be reported next to the real one; returns the previous setting. */
+ *   dense throughput can be reported next to the real one; returns the previous setting.
+ * sphk_prefilter_count: *live_count (device) = number of pairs of rows[R] x cols[C] that survive the prefilter of
+ *   the N x M kernels (circumscribed-circle and box-frame tests, csrc/sphk_fast.cuh), i.e. that the expensive
+ *   transform + clipping code is run for; early-out rate = 1 - live / (R * C).  Workspace as sphk_iou_pairwise. */
 int sphk_probe_fp32(int32_t blocks, int32_t iters, float* sink, void* stream);
 int sphk_set_dense(int on);
+int sphk_prefilter_count(const float* rows, int64_t R, const float* cols, int64_t C, int D, int edge, uint64_t* live_count,
+                         void* workspace, void* stream);
 
 #ifdef __cplusplus
 }

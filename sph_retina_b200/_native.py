@@ -55,6 +55,9 @@ SIGNATURES = {
     "sphk_loss_reduce_partials": (_i64, [_i64]),
     "sphk_loss_reduce": (_int, [_c_float_p, _c_float_p, _c_float_p, _i64, _int, ctypes.c_float, _c_float_p, _c_float_p, _c_float_p,
                                 ctypes.c_void_p]),
+    "sphk_loss_total_scratch_bytes": (_i64, [_i64]),
+    "sphk_loss_reduce_total": (_int, [_c_float_p, _c_float_p, _c_float_p, _i64, _int, ctypes.c_float, _c_float_p, ctypes.c_void_p,
+                                      _c_float_p, _c_float_p, ctypes.c_void_p]),
     "sphk_obb_fwd": (_int, [_int, _c_float_p, _c_float_p, _i64, _int, _int, _c_float_p, _c_float_p, ctypes.c_void_p]),
     "sphk_obb_bwd": (_int, [_int, _c_float_p, _c_float_p, _i64, _int, _int, _c_float_p, _c_float_p, _c_float_p,
                             _c_float_p, ctypes.c_void_p]),
@@ -82,6 +85,7 @@ SIGNATURES = {
                                _i32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "sphk_probe_fp32": (_int, [_i32, _i32, _c_float_p, ctypes.c_void_p]),
     "sphk_set_dense": (_int, [_int]),
+    "sphk_prefilter_count": (_int, [_c_float_p, _i64, _c_float_p, _i64, _int, _int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
 }
 
 
@@ -387,7 +391,7 @@ def loss_reduce(pred, target, weight, scale, want_grad_pred=False, want_grad_tar
     if weight is not None:
         weight = weight.to(device=dev, dtype=torch.float32).contiguous()
         assert weight.numel() == n
-    partial = torch.empty(max(1, (n + 255) // 256), dtype=torch.float32, device=dev)
+    partial = torch.empty(max(1, int(lib.sphk_loss_reduce_partials(n))), dtype=torch.float32, device=dev)
     if n == 0:
         partial.zero_()
     gp = torch.empty_like(pred) if want_grad_pred else None
@@ -397,6 +401,39 @@ def loss_reduce(pred, target, weight, scale, want_grad_pred=False, want_grad_tar
                                     _ptr(gt), _stream(pred)))
     launches += 1
     return partial, gp, gt
+
+
+_loss_scratch = {}
+
+
+def loss_reduce_total(pred, target, weight, scale, want_grad_pred=False, want_grad_target=False):
+    """(loss, grad_pred, grad_target): loss = scale * sum_i weight_i (1 - iou_i) as a 0-dim tensor written by the kernel
+    itself (ONE launch, no reduction op afterwards) and the gradients of that loss.  The scratch buffer (per-block sums
+    + ticket counter) is kept per (device, stream): every user of it is ordered on that stream, and the kernel hands the
+    counter back at zero."""
+    global launches
+    pred, target = _boxes(pred, "pred"), _boxes(target, "target")
+    if pred.shape != target.shape:
+        raise SphkError("pred/target shapes differ: %s vs %s" % (tuple(pred.shape), tuple(target.shape)))
+    n, dev = pred.size(0), pred.device
+    if weight is not None:
+        weight = weight.to(device=dev, dtype=torch.float32).contiguous()
+        assert weight.numel() == n
+    need = int(lib.sphk_loss_total_scratch_bytes(n))
+    key = (dev.index, _raw_stream(dev.index))
+    scratch = _loss_scratch.get(key)
+    if scratch is None or scratch.numel() < need:
+        scratch = torch.zeros(max(need * 2, 1 << 12), dtype=torch.uint8, device=dev)
+        _loss_scratch[key] = scratch
+    region = scratch                       # ticket counter in its first 16 bytes, zero between calls
+    total = torch.empty((), dtype=torch.float32, device=dev)
+    gp = torch.empty_like(pred) if want_grad_pred else None
+    gt = torch.empty_like(target) if want_grad_target else None
+    with _on_device(dev):
+        _check(lib.sphk_loss_reduce_total(_ptr(pred), _ptr(target), _ptr(weight), n, pred.size(1), float(scale), _ptr(total),
+                                          _ptr(region), _ptr(gp), _ptr(gt), _stream(pred)))
+    launches += 1
+    return total, gp, gt
 
 
 LOSS_KIND = {"gwd": 0, "kld": 1, "jd": 2, "kld_symmax": 3, "kld_symmin": 4, "kfiou": 5, "l1": 6}
@@ -425,7 +462,7 @@ def obb_loss(loss_kind, pred, target, upstream=None, scale=1.0, fun=0, flags=0, 
     loss = torch.empty((n, L) if L > 1 else (n,), dtype=torch.float32, device=dev) if want_loss else None
     partial = None
     if want_partial:
-        partial = torch.empty(max(1, (n + 255) // 256), dtype=torch.float32, device=dev)
+        partial = torch.empty(max(1, int(lib.sphk_loss_reduce_partials(n))), dtype=torch.float32, device=dev)
         if n == 0:
             partial.zero_()
     gp = torch.empty_like(pred) if want_grad_pred else None
@@ -640,6 +677,17 @@ def probe_fp32(blocks: int, iters: int, device) -> float:
     with _on_device(sink.device):
         _check(lib.sphk_probe_fp32(blocks, iters, _ptr(sink), _stream(sink)))
     return 2.0 * 8 * iters * 256 * blocks
+
+
+def prefilter_live_pairs(rows, cols, edge="arc") -> int:
+    """Measurement helper: how many of the R x C pairs survive the prefilter of the N x M kernels (host int; syncs)."""
+    rows, cols = _boxes(rows, "bboxes1"), _boxes(cols, "bboxes2")
+    R, C, dev = rows.size(0), cols.size(0), rows.device
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    ws = _workspace(dev, 136 * (R + C) + 32)
+    with _on_device(dev):
+        _check(lib.sphk_prefilter_count(_ptr(rows), R, _ptr(cols), C, rows.size(1), EDGE[edge], _ptr(cnt), _ptr(ws), _stream(rows)))
+    return int(cnt.item())
 
 
 def set_dense(on: bool) -> bool:

@@ -13,6 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsphk.so")
+TUNING_LIB_PATH = os.path.join(LIB_DIR, "libsphk_tuning.so")   # -DSPHK_TUNING: the A/B hooks of tools/ (never loaded by default)
 SOURCES = ["sphk_kernels.cu"]
 HEADERS = ["sphk_math.cuh", "sphk_fast.cuh", "sphk_grad.cuh", "sphk_coder.cuh", "sphk_obbloss.cuh", os.path.join("..", "..", "include", "sphk.h")]
 
@@ -32,21 +33,36 @@ def find_nvcc() -> str:
     raise RuntimeError("nvcc not found (set NVCC or put it on PATH)")
 
 
-def is_stale() -> bool:
-    if not os.path.isfile(LIB_PATH):
+def source_hash(tuning: bool = False) -> str:
+    """sha256 over the sources, headers, compiler flags and this file: what the built library is a function of."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]:
+        if os.path.exists(f):
+            h.update(open(f, "rb").read())
+    h.update(" ".join(NVCC_FLAGS + (["-DSPHK_TUNING"] if tuning else [])).encode())
+    return h.hexdigest()
+
+
+def is_stale(target: str = LIB_PATH) -> bool:
+    """True when the library is missing or was built from other sources.  Decided by content (a hash stamped next to
+    the library at build time), not by modification times: a snapshot copied to a GPU box keeps no useful mtimes."""
+    stamp = target + ".srchash"
+    if not os.path.isfile(target) or not os.path.isfile(stamp):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+    return open(stamp).read().strip() != source_hash(tuning=(target == TUNING_LIB_PATH))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
-        return LIB_PATH
+def build(force: bool = False, verbose: bool = False, tuning: bool = False) -> str:
+    """tuning=True builds the instrumented twin (environment-variable A/B hooks compiled in) next to the product
+    library; tools/ scripts load it through SPHK_PROBE_LIB.  The product library reads no environment variable."""
+    target = TUNING_LIB_PATH if tuning else LIB_PATH
+    if not force and not is_stale(target):
+        return target
     os.makedirs(LIB_DIR, exist_ok=True)
     # build next to the target and rename atomically: several ranks may find the library stale at the same time
-    tmp = "%s.tmp.%d" % (LIB_PATH, os.getpid())
-    cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else [])
+    tmp = "%s.tmp.%d" % (target, os.getpid())
+    cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + (["-DSPHK_TUNING"] if tuning else [])
     cmd += ["-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
@@ -54,11 +70,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if os.path.exists(tmp):
             os.unlink(tmp)
         raise RuntimeError("nvcc failed building libsphk.so")
-    os.replace(tmp, LIB_PATH)
+    os.replace(tmp, target)
+    with open(target + ".srchash", "w") as f:
+        f.write(source_hash(tuning))
     if verbose:
         sys.stderr.write(res.stderr)
-    return LIB_PATH
+    return target
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, tuning="--tuning" in sys.argv))

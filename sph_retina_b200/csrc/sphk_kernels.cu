@@ -691,6 +691,27 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
     }
 }
 
+// ---- measurement: how many pairs of an N x M call survive the prefilter of the scan loops (bench.py reports the
+// early-out rate next to the throughput).  Same records, same prefilter_live() as k_iou_pairwise2.
+__global__ void __launch_bounds__(kThreads)
+k_prefilter_count(int64_t R, int64_t C, const float4* __restrict__ cull, unsigned long long* __restrict__ live_count) {
+    __shared__ float4 s_rc[32][4];
+    const int64_t r0 = (int64_t)blockIdx.x * 32, col = (int64_t)blockIdx.y * kThreads + threadIdx.x;
+    const int nr = (int)min((int64_t)32, R - r0);
+    if (threadIdx.x < 32 * 4) {
+        const int rr = threadIdx.x >> 2, q = threadIdx.x & 3;
+        if (rr < nr) s_rc[rr][q] = __ldg(cull + (r0 + rr) * 4 + q);
+    }
+    __syncthreads();
+    unsigned n = 0;
+    if (col < C) {
+        const float4 pc0 = __ldg(cull + (R + col) * 4), pc1 = __ldg(cull + (R + col) * 4 + 1);
+        for (int r = 0; r < nr; ++r) n += prefilter_live(s_rc[r], pc0, pc1.x, pc1.y, pc1.z, true) ? 1u : 0u;
+    }
+    n = __reduce_add_sync(0xFFFFFFFFu, n);
+    if ((threadIdx.x & 31) == 0 && n) atomicAdd(live_count, (unsigned long long)n);
+}
+
 // ---- few rows x many columns in ONE launch ----------------------------------------------------------------------
 // SphOverlaps2D(gt[R <= 32], anchors[C]) -> [R, C] is the call MaxIoUAssigner makes once per image
 // (mmdet/core/bbox/assigners/max_iou_assigner.py:113).  At this size the general path spends a tenth of the call in
@@ -985,8 +1006,9 @@ template <int D>
 __global__ void __launch_bounds__(kThreads)
 k_loss_reduce(const float* __restrict__ pred, const float* __restrict__ target, const float* __restrict__ weight, int64_t n,
               float scale, float* __restrict__ partial, float* __restrict__ grad_pred, float* __restrict__ grad_target,
-              bool vec_ok) {
+              bool vec_ok, float* __restrict__ total, unsigned* __restrict__ ticket) {
     __shared__ float s_sum[kThreads / 32];
+    __shared__ bool s_last;
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     float li = 0.0f;
     if (i < n) {
@@ -1012,6 +1034,31 @@ k_loss_reduce(const float* __restrict__ pred, const float* __restrict__ target, 
 #pragma unroll
         for (int k = 0; k < kThreads / 32; ++k) t += s_sum[k];
         partial[blockIdx.x] = t;
+        s_last = false;
+        if (total) {
+            // the block that draws the last ticket adds the partials up -- always in index order, so the sum does not
+            // depend on which block that is -- and hands the ticket counter back at zero for the next call
+            __threadfence();
+            s_last = atomicAdd(ticket, 1u) == gridDim.x - 1u;
+        }
+    }
+    if (!total) return;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    float acc = 0.0f;
+    for (unsigned k = threadIdx.x; k < gridDim.x; k += kThreads) acc += __ldcg(partial + k);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.0f;
+#pragma unroll
+        for (int k = 0; k < kThreads / 32; ++k) t += s_sum[k];
+        *total = t * scale;
+        *ticket = 0u;
     }
 }
 
@@ -2094,8 +2141,30 @@ int sphk_loss_reduce(const float* pred, const float* target, const float* weight
     cudaStream_t s = (cudaStream_t)stream;
     const bool v = aligned16(pred) && aligned16(target) && (!grad_pred || aligned16(grad_pred)) &&
                    (!grad_target || aligned16(grad_target));
-    if (D == 4) k_loss_reduce<4><<<blocks_for(n), kThreads, 0, s>>>(pred, target, weight, n, scale, partial, grad_pred, grad_target, v);
-    else k_loss_reduce<5><<<blocks_for(n), kThreads, 0, s>>>(pred, target, weight, n, scale, partial, grad_pred, grad_target, v);
+    if (D == 4) k_loss_reduce<4><<<blocks_for(n), kThreads, 0, s>>>(pred, target, weight, n, scale, partial, grad_pred, grad_target, v, nullptr, nullptr);
+    else k_loss_reduce<5><<<blocks_for(n), kThreads, 0, s>>>(pred, target, weight, n, scale, partial, grad_pred, grad_target, v, nullptr, nullptr);
+    SPHK_LAUNCH_CHECK("k_loss_reduce");
+    return SPHK_OK;
+}
+
+int64_t sphk_loss_total_scratch_bytes(int64_t n) { return n <= 0 ? 16 : (((n + kThreads - 1) / kThreads * 4 + 15) & ~15ll) + 16; }
+
+int sphk_loss_reduce_total(const float* pred, const float* target, const float* weight, int64_t n, int D, float scale,
+                           float* total, void* scratch, float* grad_pred, float* grad_target, void* stream) {
+    if (n < 0 || (D != 4 && D != 5)) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_loss_reduce_total: n < 0 or D not in {4,5}");
+    if (!total) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_loss_reduce_total: null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0) {
+        const cudaError_t e = cudaMemsetAsync(total, 0, sizeof(float), s);
+        return e == cudaSuccess ? SPHK_OK : cuda_fail(e, "cudaMemsetAsync(total)");
+    }
+    if (!pred || !target || !scratch || !aligned16(scratch)) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_loss_reduce_total: null or unaligned pointer");
+    unsigned* ticket = (unsigned*)scratch;                   // first 16 bytes: the ticket counter (zero between calls)
+    float* partial = (float*)((char*)scratch + 16);
+    const bool v = aligned16(pred) && aligned16(target) && (!grad_pred || aligned16(grad_pred)) &&
+                   (!grad_target || aligned16(grad_target));
+    if (D == 4) k_loss_reduce<4><<<blocks_for(n), kThreads, 0, s>>>(pred, target, weight, n, scale, partial, grad_pred, grad_target, v, total, ticket);
+    else k_loss_reduce<5><<<blocks_for(n), kThreads, 0, s>>>(pred, target, weight, n, scale, partial, grad_pred, grad_target, v, total, ticket);
     SPHK_LAUNCH_CHECK("k_loss_reduce");
     return SPHK_OK;
 }
@@ -2420,6 +2489,26 @@ int sphk_debug_timeline(unsigned long long* t, unsigned* sm, int n) {
     return 0;
 }
 #endif
+
+int sphk_prefilter_count(const float* rows, int64_t R, const float* cols, int64_t C, int D, int edge, uint64_t* live_count,
+                         void* workspace, void* stream) {
+    if (R < 0 || C < 0 || (D != 4 && D != 5) || edge < 0 || edge > 2) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_prefilter_count: bad R, C, D or edge");
+    if (!live_count) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_prefilter_count: null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(live_count, 0, sizeof(uint64_t), s);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(live_count)");
+    if (R == 0 || C == 0) return SPHK_OK;
+    if (!rows || !cols || !workspace || !aligned16(workspace)) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_prefilter_count: null or unaligned pointer");
+    const int64_t row_tiles = (R + 31) / 32, col_tiles = (C + kThreads - 1) / kThreads;
+    if (row_tiles > 0x7FFFFFFFll || col_tiles > 65535) return fail(SPHK_ERR_UNSUPPORTED, "sphk_prefilter_count: grid too large; shard the call");
+    float4* rec = (float4*)((char*)workspace + keys_bytes(R, C));
+    float4* cull = rec + (R + C) * 4;
+    if (D == 4) k_box_pre<4><<<blocks_for(R + C), kThreads, 0, s>>>(rows, R, cols, C, edge, rec, cull, aligned16(rows), aligned16(cols), nullptr, nullptr);
+    else k_box_pre<5><<<blocks_for(R + C), kThreads, 0, s>>>(rows, R, cols, C, edge, rec, cull, false, false, nullptr, nullptr);
+    k_prefilter_count<<<dim3((unsigned)row_tiles, (unsigned)col_tiles), kThreads, 0, s>>>(R, C, cull, (unsigned long long*)live_count);
+    SPHK_LAUNCH_CHECK("k_prefilter_count");
+    return SPHK_OK;
+}
 
 int sphk_set_dense(int on) {
     const int prev = g_dense;

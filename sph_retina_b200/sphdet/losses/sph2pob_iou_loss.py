@@ -56,19 +56,21 @@ class _Sph2PobReducedLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pred, target, weight, scale):
         need_p, need_t = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        partial, gp, gt = _native.loss_reduce(pred.detach(), target.detach(), None if weight is None else weight.detach(),
-                                              scale, need_p, need_t)
+        # the kernel writes the finished scalar: the forward of a training step is this one launch, no reduction op
+        total, gp, gt = _native.loss_reduce_total(pred.detach(), target.detach(), None if weight is None else weight.detach(),
+                                                  scale, need_p, need_t)
         ctx.save_for_backward(*[g for g in (gp, gt) if g is not None])
         ctx.have = (need_p, need_t)
         ctx.in_dtypes = (pred.dtype, target.dtype)
-        return (partial.sum() * scale).to(pred.dtype)
+        return total if pred.dtype == torch.float32 else total.to(pred.dtype)
 
     @staticmethod
     def backward(ctx, grad_loss):
         saved = list(ctx.saved_tensors)
         gp = saved.pop(0) if ctx.have[0] else None
         gt = saved.pop(0) if ctx.have[1] else None
-        g = grad_loss.float()
+        g = grad_loss if grad_loss.dtype == torch.float32 else grad_loss.float()
+        # the stored gradients are already d(loss)/d(box) for an upstream gradient of 1: one multiply per operand
         return (None if gp is None else (gp * g).to(ctx.in_dtypes[0]),
                 None if gt is None else (gt * g).to(ctx.in_dtypes[1]), None, None)
 

@@ -60,6 +60,7 @@ def _worker(rank, world, port, n_anchors, out_dir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)        # the eager oracle must round identically here and in the parent (same chunking)
     try:
         anchors = O.generate_boxes(n_anchors, alpha_range=(5, 100), beta_range=(5, 100), box="rbfov", seed=3)
         gts = O.generate_boxes(24, alpha_range=(5, 100), beta_range=(5, 100), box="rbfov", seed=4)
@@ -91,7 +92,17 @@ def test_sharded_assignment_equals_single_process(tmp_path, world, n_anchors):
     anchors = O.generate_boxes(n_anchors, alpha_range=(5, 100), beta_range=(5, 100), box="rbfov", seed=3)
     gts = O.generate_boxes(24, alpha_range=(5, 100), beta_range=(5, 100), box="rbfov", seed=4)
     _plant_ties(anchors, gts)
-    iou = O.sph2pob_iou(anchors, gts, "efficient").float()
+    # the oracle evaluated shard by shard, single-threaded, exactly as the workers did (vectorised libm paths may
+    # round a tail element differently from a full vector: what is under test is the exchange, not the oracle)
+    from sph_retina_b200.sharded import shard_bounds
+    nt = torch.get_num_threads()
+    torch.set_num_threads(1)
+    try:
+        parts = [O.sph2pob_iou(anchors[lo:hi], gts, "efficient").float() for lo, hi in
+                 (shard_bounds(n_anchors, world, r) for r in range(world)) if hi > lo]
+    finally:
+        torch.set_num_threads(nt)
+    iou = torch.cat(parts)
     a_max, a_arg = iou.max(dim=1)
     g_max = iou.max(dim=0)[0]
     # lowest-index tie rule, computed independently of torch.max's convention
