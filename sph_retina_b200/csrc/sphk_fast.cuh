@@ -305,6 +305,40 @@ SPHK_HD int pair_stage1(const RawBox& x, const RawBox& y, int D, int edge, bool 
     return JOB_READY;
 }
 
+// Stage 1 for the pairs pair_stage1() declines because jitter_1 is NOT the plain lower clamp there: its similarity mask
+// fires (one column of the two boxes within eps: the boxes are shifted apart by -2 eps / +eps first) or a centre is
+// clamped at the upper end of its range (360 - eps is not a float).  Same outputs, but through the hi + lo coordinates of
+// jitter1_role1 / jitter1_role2 (sphk_math.cuh) -- the arithmetic of the reference-order path -- so that the pair can
+// go on through pair_stage2() and the clipper with everybody else instead of ~1500 instructions of reference-order
+// code on one lane (1e-5 of random pairs: at one million pairs that lane was the tail of the whole launch).
+// Still JOB_SLOW: NaNs, sizes in reach of jitter_2's minimum, |gamma| > 179 deg; pair_stage2() adds the acos clamp zones.
+SPHK_HD int pair_stage1_general(const RawBox& x, const RawBox& y, int D, int edge, bool cull, PairS1* s) {
+    const bool m = jitter1_mask(x, y, D);
+    const JitBox g = jitter1_role1(x, m, D), p = jitter1_role2(y, m, D);
+    bool slow = !(x.t == x.t) | !(x.p == x.p) | !(y.t == y.t) | !(y.p == y.p);
+    s->w1 = edge_len_deg(g.a, edge); s->h1 = edge_len_deg(g.b, edge);
+    s->w2 = edge_len_deg(p.a, edge); s->h2 = edge_len_deg(p.b, edge);
+    slow = slow | !(s->w1 >= 2.0f * kMinWh1) | !(s->h1 >= 2.0f * kMinWh1) | !(s->w2 >= 2.0f * kMinWh1) | !(s->h2 >= 2.0f * kMinWh1);
+    s->g1 = 0.0f; s->g2 = 0.0f;
+    if (D == 5) {
+        s->g1 = g.g; s->g2 = p.g;
+        slow = slow | !(fabsf(x.g) <= 179.0f) | !(fabsf(y.g) <= 179.0f);
+    }
+    if (slow) return JOB_SLOW;
+    sincos_deg(0.5f * (p.t_hi - g.t_hi), 0.5f * (p.t_lo - g.t_lo), &s->sdt, &s->cdt);
+    sincos_deg(0.5f * (p.p_hi - g.p_hi), 0.5f * (p.p_lo - g.p_lo), &s->sdp, &s->cdp);
+    sincos_deg(g.p_hi, g.p_lo, &s->s1, &s->c1);
+    sincos_deg(p.p_hi, p.p_lo, &s->s2, &s->c2);
+    s->hav = fmaf(s->s1 * s->s2, s->sdt * s->sdt, s->sdp * s->sdp);
+    if (cull) {
+        const float q1 = fmaf(s->w1, s->w1, s->h1 * s->h1), q2 = fmaf(s->w2, s->w2, s->h2 * s->h2);
+        const float R = fmaf(0.5f * (q1 * rsqrt_f(q1) + q2 * rsqrt_f(q2)), 1.0002f, 8e-4f);
+        const float k = fmaf(s->hav, fmaf(s->hav, 0.075f, 0.16666667f), 1.0f);
+        if (4.0f * s->hav * k * k > R * R) return JOB_DEAD;
+    }
+    return JOB_READY;
+}
+
 // ---- stage 0 of the aligned kernel: "cannot touch" from approximate trigonometry ----------------------
 // The same dead test as pair_stage1() (series lower bound of the arc against r_g + r_p), but on a haversine built
 // from four MUFU sines (sin.approx: absolute error < 1e-6 on [-pi, pi]) and on the RAW sizes, at a fraction of the

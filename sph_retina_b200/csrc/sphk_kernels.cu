@@ -122,6 +122,7 @@ __device__ __forceinline__ float pair_iou_any(const float* __restrict__ b1, int6
     PairS1 s;
     ClipJob j;
     int st = pair_stage1(x, y, D, edge, true, &s);
+    if (st == JOB_SLOW) st = pair_stage1_general(x, y, D, edge, true, &s);
     if (st == JOB_READY) st = pair_stage2(s, D, kind, &j);
     if (st == JOB_DEAD) return 0.0f;
     if (st == JOB_READY) return clip_job_iou(j, mode);
@@ -299,6 +300,7 @@ k_iou_aligned2(const float* __restrict__ b1, const float* __restrict__ b2, int64
                 PairS1 q;
                 ClipJob job;
                 int st = pair_stage1(x, y, D, edge, !dense, &q);
+                if (st == JOB_SLOW) st = pair_stage1_general(x, y, D, edge, !dense, &q);   // similarity mask / upper clamp: hi + lo form
                 if (st == JOB_READY) st = pair_stage2(q, D, kind, &job);
                 slow = st == JOB_SLOW;
                 if (!slow) out[(((int64_t)(o2 >> 5) * nw + wg) << 5) + (o2 & 31)] = (st == JOB_DEAD) ? 0.0f : clip_job_iou(job, mode);

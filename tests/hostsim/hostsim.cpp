@@ -78,7 +78,8 @@ void hostsim_prefilter(int kind, const float* b1, const float* b2, long P, int D
 }
 
 // The aligned formulation (k_iou_aligned2): stage 0 (approximate cull) for every pair; jitter_1 + transform +
-// clipper for the survivors.  path: 0 = culled by stage 0, 3 = culled by the exact test of stage 1, 1 = fast, 2 = slow.
+// clipper for the survivors.  path: 0 = culled by stage 0, 3 = culled by the exact test of stage 1, 1 = fast,
+// 5 = fast through the hi + lo stage 1 (similarity mask / upper clamp), 2 = reference-order path.
 void hostsim_iou_aligned_v3(int kind, const float* b1, const float* b2, long P, int D, int mode, int edge, float* out,
                             unsigned char* path) {
     for (long i = 0; i < P; ++i) {
@@ -87,8 +88,10 @@ void hostsim_iou_aligned_v3(int kind, const float* b1, const float* b2, long P, 
         PairS1 s1;
         ClipJob job;
         int st = pair_stage1(x, y, D, edge, true, &s1);
+        bool general = false;
+        if (st == JOB_SLOW) { st = pair_stage1_general(x, y, D, edge, true, &s1); general = true; }
         if (st == JOB_READY) st = pair_stage2(s1, D, kind, &job);
-        if (path) path[i] = (st == JOB_DEAD) ? 3 : (st == JOB_READY ? 1 : 2);
+        if (path) path[i] = (st == JOB_DEAD) ? 3 : (st == JOB_READY ? (general ? 5 : 1) : 2);
         out[i] = (st == JOB_DEAD) ? 0.0f : (st == JOB_READY ? clip_job_iou(job, mode) : sph2pob_iou_pair(x, y, D, kind, mode, edge));
     }
 }

@@ -369,6 +369,64 @@ def test_fast_path_inside_the_quirk_zones(hostsim, c_oracle, fn):
             assert (truth > 0.02).mean() > 0.9
 
 
+def masked_or_clamped_pairs(n, seed):
+    """Overlapping pairs on which jitter_1 is more than the lower clamp: one column shared exactly or within eps (the
+    similarity mask: both boxes are shifted, sph_iou_api.py:246-251), integer-valued boxes, centres at or next to the
+    upper end of their range (theta -> 360, phi -> 180: the clamp value 360 - eps is not a float)."""
+    rng = np.random.RandomState(seed)
+    t1, p1 = rng.uniform(5, 355, n), rng.uniform(15, 165, n)
+    a1, b1, a2, b2 = (rng.uniform(5, 90, n) for _ in range(4))
+    off = rng.uniform(0.1, 0.6, n) * np.minimum(np.hypot(a1, b1), np.hypot(a2, b2))
+    brg = rng.uniform(0, 2 * np.pi, n)
+    t2 = t1 + off * np.sin(brg) / np.maximum(np.sin(np.radians(p1)), 0.2)
+    p2 = np.clip(p1 - off * np.cos(brg), 1, 179)
+    g1, g2 = rng.uniform(-90, 90, n), rng.uniform(-90, 90, n)
+    B1 = np.stack([t1, p1, a1, b1, g1], 1).astype(np.float32)
+    B2 = np.stack([t2 % 360.0, p2, a2, b2, g2], 1).astype(np.float32)
+    k = np.arange(n) % 8
+    tiny = (rng.uniform(-1, 1, n) * 1.2e-4).astype(np.float32)
+    for col in range(5):                                  # one column equal / within eps
+        sel = k == col
+        B2[sel, col] = B1[sel, col] + np.where(rng.rand(sel.sum()) < 0.5, 0.0, tiny[sel])
+    sel = k == 5                                          # integer-valued annotations
+    B1[sel] = np.round(B1[sel]); B2[sel] = np.round(B2[sel])
+    sel = k == 6                                          # theta at the upper end (box 1, box 2, both)
+    up = 360.0 - np.float32(10.0) ** rng.uniform(-5.5, -3.0, sel.sum()).astype(np.float32)
+    which = rng.randint(0, 3, sel.sum())
+    B1[sel, 0] = np.where(which != 1, up, B1[sel, 0]); B2[sel, 0] = np.where(which != 0, np.minimum(up + 3e-5, 360.0), B2[sel, 0])
+    B2[sel, 0] = np.where(which == 0, 360.0 - rng.uniform(2, 30, sel.sum()), B2[sel, 0])
+    B1[sel, 0] = np.where(which == 1, 360.0 - rng.uniform(2, 30, sel.sum()), B1[sel, 0])
+    sel = k == 7                                          # phi at the upper end: both boxes next to the south pole
+    B1[sel, 1] = 180.0 - np.float32(10.0) ** rng.uniform(-5.5, -3.0, sel.sum()).astype(np.float32)
+    B2[sel, 1] = 180.0 - rng.uniform(2, 25, sel.sum())
+    return B1, B2
+
+
+def test_general_stage1_for_masked_and_clamped_pairs(hostsim, c_oracle):
+    """The aligned kernel keeps pairs with an active similarity mask or an upper-end clamp on its batch path
+    (pair_stage1_general: the hi + lo arithmetic of the reference-order path feeding the common stage 2 + clipper)
+    instead of sending each to ~1500 instructions of reference-order code on one lane.  Same result as that path and
+    as the float64 C oracle."""
+    from test_oracle_golden import _c_aligned as c_aligned
+    for D in (4, 5):
+        b1, b2 = masked_or_clamped_pairs(160_000, 20 + D)
+        b1, b2 = np.ascontiguousarray(b1[:, :D]), np.ascontiguousarray(b2[:, :D])
+        for kind in (0, 1):
+            want = hs_aligned(hostsim, kind, b1, b2)
+            got, path = hs_fast(hostsim, "hostsim_iou_aligned_v3", kind, b1, b2)
+            truth = c_aligned(c_oracle, kind, b1, b2)
+            assert (path == 5).mean() > 0.5, np.bincount(path, minlength=6) / len(path)     # it is what is being tested
+            gen = path == 5
+            e_fast, e_slow = np.abs(got - truth)[gen], np.abs(want - truth)[gen]
+            assert (truth[gen] > 0.02).mean() > 0.8
+            # both paths are held to the same allowance (pairs whose size / angle difference sits within fp32 rounding of
+            # jitter_2's eps take the other branch than the float64 run in ANY fp32 evaluation)
+            for e in (e_fast, e_slow):
+                assert (e > 1e-5).sum() <= 12 and e.max() < 1e-3, (D, kind, (e > 1e-5).sum(), e.max())
+            assert np.median(e_fast) < 3e-7 and np.abs(got - want)[gen].max() < 1e-3
+            assert (np.abs(got - want)[gen] > 5e-6).sum() <= 12
+
+
 def _f5(v):
     return (ctypes.c_float * 5)(*(list(v) + [0.0] * (5 - len(v)))) if v is not None else None
 
