@@ -855,7 +855,7 @@ def nms_batched(boxes, scores, idxs, iou_threshold=0.5, max_num=None, class_agno
 # MaxIoUAssigner.assign_wrt_overlaps (mmdet/core/bbox/assigners/max_iou_assigner.py:135-220)
 # --------------------------------------------------------------------------- #
 def assign_wrt_overlaps(overlaps, gt_labels=None, pos_iou_thr=0.5, neg_iou_thr=0.4, min_pos_iou=0.0,
-                        gt_max_assign_all=True, match_low_quality=True):
+                        gt_max_assign_all=True, match_low_quality=True, lowest_index_ties=False):
     """Literal restatement, Python loop over the GTs included.  Returns (gt_inds, max_overlaps, labels)."""
     num_gts, num_bboxes = overlaps.size(0), overlaps.size(1)
     assigned = overlaps.new_full((num_bboxes,), -1, dtype=torch.long)
@@ -866,6 +866,11 @@ def assign_wrt_overlaps(overlaps, gt_labels=None, pos_iou_thr=0.5, neg_iou_thr=0
         return assigned, overlaps.new_zeros((num_bboxes,)), labels
     max_overlaps, argmax_overlaps = overlaps.max(dim=0)
     gt_max_overlaps, gt_argmax_overlaps = overlaps.max(dim=1)
+    if lowest_index_ties:
+        # torch.max documents no tie rule; the kernels resolve ties to the LOWEST index: state that rule explicitly so
+        # that the comparison is exact (argmax of the first maximal entry along each axis)
+        argmax_overlaps = (overlaps == max_overlaps[None, :]).to(torch.uint8).argmax(dim=0)
+        gt_argmax_overlaps = (overlaps == gt_max_overlaps[:, None]).to(torch.uint8).argmax(dim=1)
     if isinstance(neg_iou_thr, float):
         assigned[(max_overlaps >= 0) & (max_overlaps < neg_iou_thr)] = 0
     else:

@@ -20,6 +20,81 @@ def load_golden(name):
     return np.load(os.path.join(GOLDEN, name + ".npz"))
 
 
+# ---- parity report -------------------------------------------------------------------------------------------------
+# Every numeric comparison of the suite leaves a record here (per test: sample size, max / median error against the
+# reference's float64 run, how many elements exceed the tolerance against the float64 run AND against the reference's
+# own float32 run, and how many elements pass only through each of the criterion's allowances).  At the end of the
+# session the records are written to gpurun_out/parity_report_{gpu,cpu}.json; the GPU file of the round is committed
+# as profiles/parity_r02.json.  Nothing here changes a verdict: it makes the verdicts readable.
+_PARITY = {"tests": {}}
+_CURRENT = [None]
+
+PARITY_NOTES = {
+    "criterion": "IoU: |kernel - reference run in float64| <= 1e-5, OR no farther from it than the reference's own float32 run is "
+                 "on that element (SURVEY.md 8c: the fp32 reference's noise floor against its fp64 run is 1.2e-5..1.2e-3). "
+                 "Gradients: row-wise relative L2 error <= 1e-4 against fp64 autograd, or no worse than the fp32 autograd row. "
+                 "NMS / assignment: index sets equal.",
+    "allowances": {
+        "fp32_clause": "elements with error > tol that pass because the fp32 reference is at least as far from the fp64 run",
+        "degenerate_pairs": "pairs with a box below 0.06 deg (jitter_2 inflates it to a 2.5e-4 rad speck whose position relative to "
+                            "the other box's edge is decided below fp32 resolution): checked at 1e-3",
+        "quirk_zone": "pairs constructed inside jitter_2's eps windows: a size / angle difference within fp32 rounding of eps takes the "
+                      "other branch than the float64 run in ANY fp32 evaluation (the reference-order path included): <= 12 of "
+                      "120,000 pairs may exceed 1e-5 (none 1e-3)",
+    },
+    "kAcosLo": "csrc/sphk_math.cuh:56-58 confines acos-derived angles to [4.47213602e-4, pi - 4.47213602e-4] = acos(1 - 1e-7) as "
+               "the reference's FLOAT64 run clamps them. The reference as shipped in float32 clamps the cosine at fl32(1 - 1e-7) = "
+               "0.99999988, i.e. at 4.88e-4 rad. Inside that zone (centres or tangent directions closer than 4.9e-4 rad to "
+               "(anti)parallel: near-coincident loss / NMS duplicates) the kernels track the float64 run, not the float32 one: a "
+               "documented deviation of up to 4.1e-5 rad in one planar angle / the centre distance, IoU effect <= 2e-5 on such pairs, "
+               "always on the side of the float64 truth.",
+}
+
+
+@pytest.fixture(autouse=True)
+def _parity_scope(request):
+    _CURRENT[0] = request.node.nodeid
+    yield
+    _CURRENT[0] = None
+
+
+def parity_record(check, **fields):
+    """Append one comparison record to the running test's entry of the parity report."""
+    if _CURRENT[0] is None:
+        return
+    rec = {"check": check}
+    for k, v in fields.items():
+        if isinstance(v, (np.floating, np.integer)):
+            v = v.item()
+        rec[k] = v
+    _PARITY["tests"].setdefault(_CURRENT[0], []).append(rec)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    if not _PARITY["tests"]:
+        return
+    import json
+    try:
+        import torch
+        on_gpu = torch.cuda.is_available()
+    except Exception:
+        on_gpu = False
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out_dir, exist_ok=True)
+    totals = {"comparisons": 0, "elements": 0, "n_gt_tol_vs_fp64": 0, "n_gt_tol_vs_fp32_ref": 0, "fp32_ref_n_gt_tol": 0,
+              "n_passed_only_via_fp32_clause": 0, "n_rescued_degenerate": 0, "n_quirk_zone_gt_1e-5": 0, "n_fail_before_allowances": 0}
+    for recs in _PARITY["tests"].values():
+        for r in recs:
+            totals["comparisons"] += 1
+            totals["elements"] += int(r.get("n", 0))
+            for k in list(totals)[2:]:
+                totals[k] += int(r.get(k, 0))
+    doc = {"device": "cuda" if on_gpu else "cpu (hostsim build of the device headers / oracle)", "exit_status": int(exitstatus),
+           "notes": PARITY_NOTES, "totals": totals, "tests": _PARITY["tests"]}
+    with open(os.path.join(out_dir, "parity_report_%s.json" % ("gpu" if on_gpu else "cpu")), "w") as f:
+        json.dump(doc, f, indent=1, sort_keys=True)
+
+
 @pytest.fixture(scope="session")
 def golden():
     return load_golden
@@ -55,15 +130,34 @@ def c_oracle():
     return lib
 
 
-def within(kernel, truth64, ref32=None, tol=1e-5, slack=1.0):
+def within(kernel, truth64, ref32=None, tol=1e-5, slack=1.0, what=None):
     """The parity criterion of SURVEY.md 8(c): |kernel - fp64 reference| <= tol, OR the kernel is at
     least as close to the fp64 run as the reference's own fp32 run is on that element."""
     err = np.abs(np.asarray(kernel, np.float64) - np.asarray(truth64, np.float64))
     ok = err <= tol
+    rec = {"n": int(err.size), "tol": tol, "max_err_vs_fp64": float(err.max()) if err.size else 0.0,
+           "median_err_vs_fp64": float(np.median(err)) if err.size else 0.0, "n_gt_tol_vs_fp64": int((err > tol).sum())}
     if ref32 is not None:
         ref_err = np.abs(np.asarray(ref32, np.float64) - np.asarray(truth64, np.float64))
+        via32 = (~ok) & (err <= slack * ref_err)
         ok |= err <= slack * ref_err
+        d32 = np.abs(np.asarray(kernel, np.float64) - np.asarray(ref32, np.float64))
+        rec.update({"fp32_ref_n_gt_tol": int((ref_err > tol).sum()), "fp32_ref_max_err_vs_fp64": float(ref_err.max()) if err.size else 0.0,
+                    "n_passed_only_via_fp32_clause": int(via32.sum()), "max_diff_vs_fp32_ref": float(d32.max()) if err.size else 0.0,
+                    "n_gt_tol_vs_fp32_ref": int((d32 > tol).sum())})
+    rec["n_fail_before_allowances"] = int((~ok).sum())
+    parity_record(what or "within", **rec)
     return ok, err
+
+
+def allow_degenerate(ok, err, b1, b2, tol=1e-3):
+    """The zero-size-box allowance (see degenerate_pairs), with the number of elements it rescues on record."""
+    deg = degenerate_pairs(b1, b2)
+    if deg.shape != ok.shape:
+        deg = np.broadcast_to(deg.reshape(-1, *([1] * (ok.ndim - 1))), ok.shape) if deg.size == ok.shape[0] else deg.reshape(ok.shape)
+    rescued = (~ok) & deg & (err < tol)
+    parity_record("degenerate_pairs", n=int(deg.sum()), n_rescued_degenerate=int(rescued.sum()), tol=tol)
+    return ok | (deg & (err < tol))
 
 
 def degenerate_pairs(b1, b2, min_fov_deg=0.06):
@@ -82,7 +176,12 @@ def grad_rows_ok(got, truth, ref32, live_rows, tol=1e-4):
     rel = np.sqrt(((got - truth) ** 2).sum(axis=1)) / np.maximum(den, 1e-30)
     rel32 = np.sqrt(((ref32 - truth) ** 2).sum(axis=1)) / np.maximum(den, 1e-30)
     live = np.asarray(live_rows, bool) & (den > 1e-12)
-    return ((rel <= tol) | (rel <= rel32))[live], rel[live], rel32[live]
+    good = ((rel <= tol) | (rel <= rel32))[live]
+    parity_record("grad_rows", n=int(live.sum()), tol=tol, median_rel_vs_fp64=float(np.median(rel[live])) if live.any() else 0.0,
+                  max_rel_vs_fp64=float(rel[live].max()) if live.any() else 0.0, n_gt_tol_vs_fp64=int((rel[live] > tol).sum()),
+                  fp32_ref_n_gt_tol=int((rel32[live] > tol).sum()), fp32_ref_median_rel=float(np.median(rel32[live])) if live.any() else 0.0,
+                  n_passed_only_via_fp32_clause=int(((rel > tol) & (rel <= rel32))[live].sum()), n_fail_before_allowances=int((~good).sum()))
+    return good, rel[live], rel32[live]
 
 
 def other_loss_variants(g):

@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import (BOX_FORMAT_CASES, ROOT, check_other_loss, degenerate_pairs, grad_rows_ok, load_golden, other_loss_variants,
+from conftest import (BOX_FORMAT_CASES, ROOT, allow_degenerate, parity_record, check_other_loss, degenerate_pairs, grad_rows_ok, load_golden, other_loss_variants,
                       within)
 
 pytestmark = pytest.mark.gpu
@@ -64,7 +64,7 @@ def test_aligned_golden(api, box, tr):
         assert got.shape == (len(g["b1"]),) and got.dtype == torch.float32 and got.device == b1.device
         got = got.cpu().numpy()
         ok, err = within(got, g["%s_%s_f64" % (tr, key)], g["%s_%s_f32" % (tr, key)])
-        ok |= degenerate_pairs(g["b1"], g["b2"]) & (err < 1e-3)
+        ok = allow_degenerate(ok, err, g["b1"], g["b2"])
         assert ok.all(), (box, tr, key, np.where(~ok)[0], err[~ok])
         assert (err > 1e-5).sum() <= 2 and np.median(err) < 2e-7
         assert got.min() >= 0.0 and got.max() <= 1.0
@@ -186,6 +186,8 @@ def test_fast_path_inside_the_quirk_zones(api, c_oracle):
             fn = getattr(api.iou, "sph2pob_%s_iou" % tr)
             truth = c_oracle_aligned(c_oracle, kind, b1, b2)
             err = np.abs(fn(x, y, is_aligned=True).cpu().numpy() - truth)
+            parity_record("quirk_zone", n=int(err.size), tol=1e-5, max_err_vs_fp64=float(err.max()), median_err_vs_fp64=float(np.median(err)),
+                          **{"n_quirk_zone_gt_1e-5": int((err > 1e-5).sum()), "allowance": 12, "transform": tr, "D": D})
             assert (err > 1e-5).sum() <= 12 and err.max() < 1e-3 and np.median(err) < 2e-7, (D, tr, (err > 1e-5).sum(), err.max())
             # the same pairs on the diagonal of N x M blocks
             for lo in (0, 60_000):
@@ -340,7 +342,6 @@ def test_sharding_emulated_on_one_gpu(api, world):
     A = O.generate_boxes(n, alpha_range=(1, 100), beta_range=(1, 100), box="rbfov", seed=0).to(DEV)
     G = O.generate_boxes(300, alpha_range=(1, 100), beta_range=(1, 100), box="rbfov", seed=1).to(DEV)
     A[4000] = A[17] = G[5]
-    A[100] = torch.tensor([10.0, 90.0, 0.5, 0.5, 0.0], device=DEV)          # an anchor no ground truth touches
     cap = block_capacity(n, world)
     for orient in ("bboxes1", "bboxes2"):
         a_max, a_arg, g_max, g_arg = sharded_max_overlaps(A, G, n, 0, anchors_are=orient)   # world = 1
@@ -365,7 +366,13 @@ def test_sharding_emulated_on_one_gpu(api, world):
         want = unpack_gathered_reference(gathered, world, n, G.size(0), cap)
         for g_, w_, s_ in zip(got, want, (a_max, a_arg, g_max, g_arg)):
             assert torch.equal(g_, w_) and torch.equal(g_, s_)
-        assert int(g_arg[5]) == 17 and float(a_max[100]) == 0.0 and int(a_arg[100]) == 0
+        assert int(g_arg[5]) == 17
+    # "no positive overlap" (key 0) reads as (0.0, index 0) on both sides
+    far = torch.tensor([[10.0, 90.0, 0.5, 0.5, 0.0], [190.0, 90.0, 20.0, 20.0, 0.0], [12.0, 40.0, 0.5, 0.5, 0.0]], device=DEV)
+    one = torch.tensor([[190.0, 90.0, 20.0, 20.0, 0.0], [300.0, 150.0, 1.0, 1.0, 0.0]], device=DEV)
+    a_max, a_arg, g_max, g_arg = sharded_max_overlaps(far, one, 3, 0)
+    assert a_max.tolist()[0] == 0.0 and a_max.tolist()[2] == 0.0 and a_max.tolist()[1] > 0.9
+    assert a_arg.tolist() == [0, 0, 0] and g_arg.tolist() == [1, 0] and g_max.tolist()[1] == 0.0
 
 
 def test_config2_slice_vs_c_oracle(api, c_oracle):
@@ -395,16 +402,16 @@ def test_fused_assigner_equals_reference_on_the_matrix(api, assign_all, min_pos_
     a = SphMaxIoUAssigner(0.5, 0.3, min_pos_iou=min_pos_iou, gt_max_assign_all=assign_all, iou_calculator=calc)
     res = a.assign(anchors, gts, gt_labels=labels)
     overlaps = calc(gts, anchors)
-    g, m, l = O.assign_wrt_overlaps(overlaps.cpu(), labels.cpu(), 0.5, 0.3, min_pos_iou, assign_all, True)
+    # argmax ties resolve to the LOWEST index in the kernels; torch.max documents no rule, so the literal loop is run with
+    # that rule stated explicitly (oracle: lowest_index_ties) and the comparison is exact for both settings
+    g, m, l = O.assign_wrt_overlaps(overlaps.cpu(), labels.cpu(), 0.5, 0.3, min_pos_iou, assign_all, True, lowest_index_ties=True)
     assert res.num_gts == 32 and res.gt_inds.dtype == torch.int64
     assert torch.equal(res.max_overlaps.cpu(), m)
-    if assign_all:
-        assert torch.equal(res.gt_inds.cpu(), g) and torch.equal(res.labels.cpu(), l)
-    else:
-        # argmax ties are resolved to the lowest index here; torch.max documents no rule: compare where the row max is unique
-        uniq = (overlaps == overlaps.max(dim=1, keepdim=True)[0]).sum(dim=1).cpu() == 1
-        same = res.gt_inds.cpu() == g
-        assert same.float().mean() > 0.999 and bool(uniq.float().mean() > 0.8)
+    assert torch.equal(res.gt_inds.cpu(), g) and torch.equal(res.labels.cpu(), l)
+    ties = int(((overlaps == overlaps.max(dim=1, keepdim=True)[0]).sum(dim=1) > 1).sum())
+    parity_record("assigner_exact", n=int(g.numel()), n_fail_before_allowances=int((res.gt_inds.cpu() != g).sum()), rows_with_tied_maximum=ties,
+                  gt_max_assign_all=bool(assign_all))
+    assert ties >= 1                                       # the duplicated anchors do produce tied row maxima
     assert int((res.gt_inds > 0).sum()) > 100 and int((res.gt_inds == 0).sum()) > 1000 and int((res.gt_inds == -1).sum()) > 10
 
 
@@ -422,12 +429,9 @@ def test_fused_assigner_batch_equals_per_image(api):
         assert len(batch) == len(counts)
         for b, k in enumerate(counts):
             ov = calc(gts[b], anchors) if k else anchors.new_zeros((0, anchors.size(0)))
-            g, m, l = O.assign_wrt_overlaps(ov.cpu(), labels[b].cpu(), 0.5, (0.05, 0.3), 0.1, assign_all, True)
+            g, m, l = O.assign_wrt_overlaps(ov.cpu(), labels[b].cpu(), 0.5, (0.05, 0.3), 0.1, assign_all, True, lowest_index_ties=True)
             assert batch[b].num_gts == k and torch.equal(batch[b].max_overlaps.cpu(), m)
-            if assign_all or k == 0:
-                assert torch.equal(batch[b].gt_inds.cpu(), g) and torch.equal(batch[b].labels.cpu(), l)
-            else:
-                assert (batch[b].gt_inds.cpu() == g).float().mean() > 0.999
+            assert torch.equal(batch[b].gt_inds.cpu(), g) and torch.equal(batch[b].labels.cpu(), l)
             one = a.assign(anchors, gts[b], gt_labels=labels[b])
             assert torch.equal(one.gt_inds, batch[b].gt_inds) and torch.equal(one.max_overlaps, batch[b].max_overlaps)
 
