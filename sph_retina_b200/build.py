@@ -14,6 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsphk.so")
 TUNING_LIB_PATH = os.path.join(LIB_DIR, "libsphk_tuning.so")   # -DSPHK_TUNING: the A/B hooks of tools/ (never loaded by default)
+TIMELINE_LIB_PATH = os.path.join(LIB_DIR, "libsphk_tl.so")     # -DSPHK_TIMELINE: per-CTA / per-warp timestamps (tools/timeline_*.py)
 SOURCES = ["sphk_kernels.cu"]
 HEADERS = ["sphk_math.cuh", "sphk_fast.cuh", "sphk_grad.cuh", "sphk_coder.cuh", "sphk_obbloss.cuh", os.path.join("..", "..", "include", "sphk.h")]
 
@@ -78,5 +79,16 @@ def build(force: bool = False, verbose: bool = False, tuning: bool = False) -> s
     return target
 
 
+def build_timeline() -> str:
+    """The timestamp-instrumented twin (tools/timeline_probe.py, tools/timeline_aligned.py)."""
+    os.makedirs(LIB_DIR, exist_ok=True)
+    cmd = [find_nvcc()] + NVCC_FLAGS + ["-DSPHK_TIMELINE", "-DSPHK_TUNING", "-o", TIMELINE_LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    subprocess.run(cmd, check=True)
+    return TIMELINE_LIB_PATH
+
+
 if __name__ == "__main__":
+    if "--timeline" in sys.argv:
+        print(build_timeline())
+        sys.exit(0)
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, tuning="--tuning" in sys.argv))

@@ -181,6 +181,13 @@ __global__ void __launch_bounds__(kThreads) k_approx_aligned4(const float4* __re
 // reference quirk may be active are queued once more for the out-of-line reference-order path.
 // Ring capacities: survivors <= 31 pending + 32 pushed per round; slow pairs <= 31 pending + 32 from one batch.
 constexpr int kJobRing = 64, kSlowRing = 64, kJobWords = 12;   // 48-byte entries: conflict-free LDS.128 / STS.128
+#ifdef SPHK_TIMELINE
+// instrumented build (tools/timeline_aligned.py): per warp of k_iou_aligned2 -- start, end of its last scan round, end
+// (globaltimer ns), and how many pairs it sent to the reference-order path
+__device__ unsigned long long g_tlw[8192 * 3];
+__device__ unsigned g_tlw_slow[8192];
+__device__ __forceinline__ unsigned long long tl_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#endif
 
 struct AlignedTile {
     // entry = (t1, p1, a1, b1 | t2, p2, a2, b2 | g1, g2, round << 5 | lane, -)
@@ -241,6 +248,10 @@ k_iou_aligned2(const float* __restrict__ b1, const float* __restrict__ b2, int64
     const int full = (int)(P >> 5), tail = (int)(P & 31), chunks = full + (tail ? 1 : 0);
     int hj = 0, tj = 0, hs = 0, ts = 0;
     const unsigned lt = (1u << lane) - 1u;
+#ifdef SPHK_TIMELINE
+    const unsigned long long tl_start = tl_now();
+    unsigned long long tl_scan = tl_start;
+#endif
     float* const slot1 = T.pre[warp][0];
     float* const slot2 = T.pre[warp][1];
     // the boxes of the next round are fetched one round ahead (cp.async into shared memory: no registers are
@@ -283,6 +294,9 @@ k_iou_aligned2(const float* __restrict__ b1, const float* __restrict__ b2, int64
             }
             tj += __popc(mj);
             ++k;
+#ifdef SPHK_TIMELINE
+            tl_scan = tl_now();
+#endif
         }
         // ---- one batch of up to 32 survivors: jitter_1, transform, clipper (the expensive code exists once)
         if (tj > hj) {
@@ -325,6 +339,12 @@ k_iou_aligned2(const float* __restrict__ b1, const float* __restrict__ b2, int64
         }
         if (drained) break;
     }
+#ifdef SPHK_TIMELINE
+    if (lane == 0 && wg < 8192) {
+        g_tlw[3 * wg] = tl_start; g_tlw[3 * wg + 1] = tl_scan; g_tlw[3 * wg + 2] = tl_now();
+        g_tlw_slow[wg] = (unsigned)ts;
+    }
+#endif
 }
 
 // ---- rbb_angle = 'project': one thread per pair, double-precision transform (sphk_math.cuh) ------------
@@ -2484,6 +2504,12 @@ int sphk_probe_fp32(int32_t blocks, int32_t iters, float* sink, void* stream) {
 }
 
 #ifdef SPHK_TIMELINE
+int sphk_debug_timeline_warps(unsigned long long* t, unsigned* slow, int n) {
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(t, g_tlw, sizeof(unsigned long long) * 3 * n) != cudaSuccess) return -2;
+    if (cudaMemcpyFromSymbol(slow, g_tlw_slow, sizeof(unsigned) * n) != cudaSuccess) return -3;
+    return 0;
+}
 int sphk_debug_timeline(unsigned long long* t, unsigned* sm, int n) {
     if (cudaDeviceSynchronize() != cudaSuccess) return -1;
     if (cudaMemcpyFromSymbol(t, g_tl, sizeof(unsigned long long) * 2 * n) != cudaSuccess) return -2;

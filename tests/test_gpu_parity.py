@@ -739,6 +739,58 @@ def test_box_format_golden(api):
     assert torch.equal(sph4, before) and float((back - sph4).abs().max()) < 2e-4
 
 
+def test_box_format_autograd(api):
+    """The conversions are plain torch expressions in the reference (box_formator.py:17-117,166-200), so gradients flow
+    through them; here each one is a kernel launch with an explicit backward.  Checked against autograd through the
+    reference's expressions written out in torch (float64), and the tangent formats must refuse instead of cutting the graph."""
+    from sph_retina_b200.sphdet.bbox import box_formator as bf
+    g = load_golden("box_format")
+    H, W = 960.0, 1920.0
+
+    def ref_xyxy2xywh(b):
+        return torch.stack([(b[:, 0] + b[:, 2]) / 2, (b[:, 1] + b[:, 3]) / 2, b[:, 2] - b[:, 0], b[:, 3] - b[:, 1]], 1)
+
+    def ref_xywh2xyxy(b):
+        return torch.stack([b[:, 0] - b[:, 2] / 2, b[:, 1] - b[:, 3] / 2, b[:, 0] + b[:, 2] / 2, b[:, 1] + b[:, 3] / 2], 1)
+
+    def ref_sph2pix(b):
+        return torch.stack([b[:, 0] / 360 * W, b[:, 1] / 180 * H, b[:, 2] / 360 * W, b[:, 3] / 180 * H], 1)
+
+    def ref_obb2hbb_xywh(o):
+        c, s = torch.cos(o[:, 4]).abs(), torch.sin(o[:, 4]).abs()
+        return torch.stack([o[:, 0], o[:, 1], c * o[:, 2] + s * o[:, 3], s * o[:, 2] + c * o[:, 3]], 1)
+
+    cases = [
+        ("xyxy2xywh", bf.xyxy2xywh, ref_xyxy2xywh, g["xyxy"]),
+        ("xywh2xyxy", bf.xywh2xyxy, ref_xywh2xyxy, g["xywh"]),
+        ("obb2hbb_wywh", bf.obb2hbb_wywh, ref_obb2hbb_xywh, g["obb"]),
+        ("obb2hbb_xyxy", bf.obb2hbb_xyxy, lambda o: ref_xywh2xyxy(ref_obb2hbb_xywh(o)), g["obb"]),
+        ("geo2sph", bf.geo2sph, lambda b: torch.cat([b[:, :1] + 180, 90 - b[:, 1:2], b[:, 2:]], 1), g["geo"]),
+        ("sph2planar4", lambda b: bf.Sph2PlanarBoxTransform('sph2pix', 4)(b, (H, W)), lambda b: ref_xywh2xyxy(ref_sph2pix(b)), g["sph4"]),
+        ("sph2planar5", lambda b: bf.Sph2PlanarBoxTransform('sph2pix', 5)(b, (H, W)),
+         lambda b: torch.cat([ref_sph2pix(b), -torch.deg2rad(b[:, 4:5])], 1), g["sph5"]),
+        ("planar2sph5", lambda b: bf.Planar2SphBoxTransform('pix2sph', 5)(b, (H, W)),
+         lambda b: torch.cat([torch.stack([(b[:, 0] + b[:, 2]) / 2 / W * 360, (b[:, 1] + b[:, 3]) / 2 / H * 180,
+                                           (b[:, 2] - b[:, 0]) / W * 360, (b[:, 3] - b[:, 1]) / H * 180], 1), b[:, :1] * 0], 1), g["xyxy"]),
+    ]
+    for name, fn, ref, data in cases:
+        x = cu(data[:257]).clone().requires_grad_(True)
+        y = fn(x)
+        assert y.requires_grad, name
+        up = torch.randn(y.shape, device=DEV, generator=torch.Generator(device=DEV).manual_seed(3))
+        (y * up).sum().backward()
+        x64 = torch.as_tensor(data[:257]).double().requires_grad_(True)
+        y64 = ref(x64)
+        (y64 * up.cpu().double()).sum().backward()
+        np.testing.assert_allclose(y.detach().cpu().numpy(), y64.detach().numpy(), rtol=3e-6, atol=3e-4, err_msg=name)
+        np.testing.assert_allclose(x.grad.cpu().numpy(), x64.grad.numpy(), rtol=2e-5, atol=2e-5, err_msg=name)
+        with torch.no_grad():                                   # no graph asked for: the plain launch
+            assert not fn(x).requires_grad
+    with pytest.raises(NotImplementedError):
+        bf.Sph2PlanarBoxTransform('sph2tan', 4)(cu(g["sph4"][:8]).requires_grad_(True))
+    assert not bf.Sph2PlanarBoxTransform('sph2tan', 4)(cu(g["sph4"][:8])).requires_grad
+
+
 # ---- sph2pob_legacy_iou (the reference's first transform; BFoV only) ----------------------------------------------------
 def test_sph2pob_legacy_golden(api):
     g = load_golden("legacy")

@@ -1,24 +1,33 @@
 #!/bin/bash
-# Runs ON THE GPU BOX (gpurun --gpus N): the per-N bench lines of both sharded workloads into gpurun_out/.
-#   tools/scale_round.sh <tag> <n1> [n2 ...]        e.g.  r01_v13 1 2 4 8
+# Runs ON THE GPU BOX (gpurun --gpus N): the per-N bench lines of the default (row-sharded sweep) workload into
+# gpurun_out/, launched exactly as the driver launches them.
+#   tools/scale_round.sh <tag> <n1> [n2 ...]        e.g.  r02_v4 1 2
 set -u
 tag=$1; shift
 out=gpurun_out; mkdir -p $out
 port=29600
-for wl in assign sweep; do
-  for n in "$@"; do
-    port=$((port + 1))
-    extra="--no-extras --no-cpu"; [ $wl = sweep ] && extra="$extra --workload sweep --steps 10 --warmup 3"
-    if [ $n = 1 ]; then python bench.py --gpus 1 $extra > $out/scale_${wl}_n${n}_$tag.json 2> $out/scale_${wl}_n${n}_$tag.err
-    else python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $port bench.py --gpus $n $extra \
-           > $out/scale_${wl}_n${n}_$tag.json 2> $out/scale_${wl}_n${n}_$tag.err; fi
-    python - <<PY
-import json
-try:
-    d = json.loads(open("$out/scale_${wl}_n${n}_$tag.json").read().strip().splitlines()[-1])
-    print("$wl", d["n_gpus"], "%.1f Gpairs/s" % (d["value"] / 1e9), "%.3f ms" % d["ms_per_step"], d["clocks"]["reasons"])
-except Exception as e:
-    print("$wl", $n, "FAILED", e)
-PY
-  done
+for n in "$@"; do
+  port=$((port + 1))
+  extra="--no-extras --no-cpu"
+  if [ $n = 1 ]; then python bench.py --gpus 1 $extra > $out/scale_sweep_n${n}_$tag.json 2> $out/scale_sweep_n${n}_$tag.err
+  else NCCL_DEBUG=${NCCL_DEBUG:-WARN} python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $port bench.py --gpus $n $extra \
+         > $out/scale_sweep_n${n}_$tag.json 2> $out/scale_sweep_n${n}_$tag.err; fi
+  [ -s $out/scale_sweep_n${n}_$tag.json ] || tail -20 $out/scale_sweep_n${n}_$tag.err
 done
+python - "$tag" "$@" <<'PY'
+import json, sys
+tag, ns = sys.argv[1], sys.argv[2:]
+base = None
+for n in ns:
+    try:
+        d = json.loads(open("gpurun_out/scale_sweep_n%s_%s.json" % (n, tag)).read().strip().splitlines()[-1])
+        if base is None:
+            base = (int(n), d["value"], d["e2e"]["value"])
+        eff = d["value"] / (base[1] * int(n) / base[0])
+        eff_e = d["e2e"]["value"] / (base[2] * int(n) / base[0])
+        print("sweep N=%s  %.1f Gpairs/s  %.4f ms/step  eff %.3f | e2e %.1f Gpairs/s  %.4f ms  eff %.3f | kernel_ms %.4f  clocks %s %s" % (
+            n, d["value"] / 1e9, d["ms_per_step"], eff, d["e2e"]["value"] / 1e9, d["e2e"]["ms_per_step"], eff_e,
+            d["roofline"]["kernel_ms"], d["clocks"]["sm_mhz"], d["clocks"]["reasons"]))
+    except Exception as e:
+        print("sweep N=%s FAILED %r" % (n, e))
+PY
