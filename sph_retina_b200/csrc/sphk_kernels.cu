@@ -511,19 +511,25 @@ __device__ __forceinline__ void stage_rec(float* base, int i, const float4* __re
 }
 
 // Prefilter of one (row, column) pair in the scan loops of the N x M kernels: the row's operands come from shared memory
-// (4 x float4, BoxCull layout), the column's live in registers.  Test 1 (sphk_fast.cuh: pre_disjoint): cos(arc) <
-// cos(r_g + r_p) - margin, the circumscribed circles cannot touch.  Test 2 (pre_outside_box, `boxcull`): the column's
-// centre lies outside the row box grown by the column's circumradius, along one of the row box's own axes -- on
-// RetinaNet-style anchors x GT this proves another 7.5 % of all pairs disjoint (69 -> 76 %; 80 % have IoU = 0).
+// (4 x float4, BoxCull layout), the column's live in registers.
+//   Test 1 (sphk_fast.cuh: pre_disjoint): cos(arc) < cos(r_g + r_p) - margin, the circumscribed circles cannot touch.
+//   Test 2 (pre_outside_box, BOX): the column's centre lies outside the row box grown by the column's circumradius, along
+//   one of the row box's own axes; evaluated by the lanes test 1 left alive.  It prunes the part of test 1's acceptance
+//   region (a disc of radius R + r around the row box) that lies outside the grown box: ~1/3 of it for small columns
+//   against large rows (RetinaNet anchors x ground truths: 69 -> 76 % of all pairs proven disjoint, 80 % have IoU = 0;
+//   +9.5 % throughput), a few per cent for operands of similar size, where its ~19 instructions per pair cost more than
+//   they save (1 M x 1,024 random boxes: 5.5 % of test 1's survivors pruned, +2.6 % instructions, -1.2 % throughput).
+//   BOX is therefore a compile-time property of the kernel instance and the HOST picks the instance per call
+//   (box_test_pays): ground truths (few rows) against anchors (many columns) get it, long-row sweeps do not.
 // Out-of-range columns and the dense (measurement) mode are folded into pbias / pr.
-__device__ __forceinline__ bool prefilter_live(const float4* __restrict__ rc, const float4& pc0, float prs, float pbias, float pr,
-                                               bool boxcull) {
+template <bool BOX>
+__device__ __forceinline__ bool prefilter_live(const float4* __restrict__ rc, const float4& pc0, float prs, float pbias, float pr) {
     const float4 g0 = rc[0];
     const float2 g1 = *reinterpret_cast<const float2*>(&rc[1]);
     const float dot = fmaf(g0.x, pc0.x, fmaf(g0.y, pc0.y, g0.z * pc0.z));
     const float thr = fmaf(g0.w, pc0.w, fmaf(-g1.x, prs, g1.y + pbias));
     bool live = !(dot < thr);
-    if (boxcull) {
+    if (BOX) {
         const float4 e = rc[2], f = rc[3];
         live = live && !pre_outside_box(e.x, e.y, e.z, e.w, f.x, f.y, f.z, f.w, pc0.x, pc0.y, pc0.z, pr);
     }
@@ -554,7 +560,7 @@ __device__ unsigned long long g_tl[16384 * 2];
 __device__ unsigned g_tl_sm[16384];
 #endif
 
-template <int D, int TR>
+template <int D, int TR, bool BOX>
 __global__ void __launch_bounds__(kThreads)
 k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restrict__ cols, int64_t C,
                 const float4* __restrict__ rec, const float4* __restrict__ cull, int kind, int mode, int edge,
@@ -564,7 +570,7 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
                 const int32_t* __restrict__ row_offsets, int64_t col_stride, float* __restrict__ tile_rmax) {
     __shared__ __align__(16) PairTile<TR> T;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool dense = (flags & 1) != 0, boxcull = (flags & 2) == 0;   // bit 0: sphk_set_dense; bit 1: tuning build only
+    const bool dense = (flags & 1) != 0;                               // sphk_set_dense (measurement)
 #ifdef SPHK_TIMELINE
     unsigned long long tl0 = 0;
     if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl0));
@@ -639,6 +645,7 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
     // Out-of-range columns and the dense (measurement) mode are folded into the bias term of the test.
     const float pbias = col_ok ? (dense ? -1e30f : pc1.y) : 1e30f;
     const float pr = dense ? 1e30f : pc1.z;      // dense (measurement) mode: the box-frame test never fires either
+    (void)pr;
     int hf = 0, tf = 0, hs = 0, ts = 0;          // ring head / tail counters (fast, slow)
     const unsigned lt = (1u << lane) - 1u;
     // Alternate between a tight scan phase (prefilter rows until 32 live pairs are queued or the rows are used up)
@@ -648,7 +655,7 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
     for (;;) {
 #pragma unroll 1
         while (r < nr && tf - hf < 32) {
-            const bool live = prefilter_live(T.rcull[r], pc0, pc1.x, pbias, pr, boxcull);
+            const bool live = prefilter_live<BOX>(T.rcull[r], pc0, pc1.x, pbias, pr);
             const unsigned m = __ballot_sync(0xFFFFFFFFu, live);
             if (live) T.ring[warp][0][(tf + __popc(m & lt)) & (kRing - 1)] = (unsigned short)((r << 5) | lane);
             tf += __popc(m);
@@ -716,7 +723,7 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
 // ---- measurement: how many pairs of an N x M call survive the prefilter of the scan loops (bench.py reports the
 // early-out rate next to the throughput).  Same records, same prefilter_live() as k_iou_pairwise2.
 __global__ void __launch_bounds__(kThreads)
-k_prefilter_count(int64_t R, int64_t C, const float4* __restrict__ cull, unsigned long long* __restrict__ live_count) {
+k_prefilter_count(int64_t R, int64_t C, const float4* __restrict__ cull, unsigned long long* __restrict__ live_count, bool box) {
     __shared__ float4 s_rc[32][4];
     const int64_t r0 = (int64_t)blockIdx.x * 32, col = (int64_t)blockIdx.y * kThreads + threadIdx.x;
     const int nr = (int)min((int64_t)32, R - r0);
@@ -728,7 +735,8 @@ k_prefilter_count(int64_t R, int64_t C, const float4* __restrict__ cull, unsigne
     unsigned n = 0;
     if (col < C) {
         const float4 pc0 = __ldg(cull + (R + col) * 4), pc1 = __ldg(cull + (R + col) * 4 + 1);
-        for (int r = 0; r < nr; ++r) n += prefilter_live(s_rc[r], pc0, pc1.x, pc1.y, pc1.z, true) ? 1u : 0u;
+        for (int r = 0; r < nr; ++r)
+            n += (box ? prefilter_live<true>(s_rc[r], pc0, pc1.x, pc1.y, pc1.z) : prefilter_live<false>(s_rc[r], pc0, pc1.x, pc1.y, pc1.z)) ? 1u : 0u;
     }
     n = __reduce_add_sync(0xFFFFFFFFu, n);
     if ((threadIdx.x & 31) == 0 && n) atomicAdd(live_count, (unsigned long long)n);
@@ -829,7 +837,7 @@ k_iou_rows32(const float* __restrict__ rows, int R, const float* __restrict__ co
     const float4 pc0 = T.ccull[cl][0], pc1 = T.ccull[cl][1];
     // ---- phase 1: prefilter + compaction + batches, exactly as k_iou_pairwise2 (this thread's column is cl)
     const float pbias = col_ok ? (dense ? -1e30f : pc1.y) : 1e30f;
-    const float pr = dense ? 1e30f : pc1.z;
+    const float pr = (dense || (flags & 2)) ? 1e30f : pc1.z;     // (bit 1: tuning build only -- test 2 never fires)
     int hf = 0, tf = 0, hs = 0, ts = 0;
     const unsigned lt = (1u << lane) - 1u;
     int r = r_lo;
@@ -837,7 +845,7 @@ k_iou_rows32(const float* __restrict__ rows, int R, const float* __restrict__ co
     for (;;) {
 #pragma unroll 1
         while (r < r_hi && tf - hf < 32) {
-            const bool live = prefilter_live(T.rcull[r], pc0, pc1.x, pbias, pr, boxcull);
+            const bool live = prefilter_live<true>(T.rcull[r], pc0, pc1.x, pbias, pr);     // few GT rows x many anchors: test 2 pays
             const unsigned m = __ballot_sync(0xFFFFFFFFu, live);
             if (live) T.ring[warp][0][(tf + __popc(m & lt)) & (kRing - 1)] = (unsigned short)((r << 5) | lane);
             tf += __popc(m);
@@ -1854,6 +1862,12 @@ int64_t sphk_iou_pairwise_workspace_bytes(int64_t R, int64_t C) {
     return keys_bytes(R, C) + (R + C) * (int64_t)((kBoxRecFloats + kBoxCullFloats) * sizeof(float));
 }
 
+// Which calls get the kernel instance with the box-frame prefilter test (prefilter_live<true>)?  The test takes the ROW
+// box's frame and the COLUMN's circumradius, so it pays when the rows are the large boxes and the columns the small
+// ones: MaxIoUAssigner's orientation, ground truths (few) x anchors (many).  The host cannot see the boxes; it goes by
+// the shape of the call: rows at least 4 x fewer than columns.  A misjudged call loses ~1 % (see prefilter_live).
+static inline bool box_test_pays(int64_t rows_per_image, int64_t C) { return rows_per_image * 4 <= C; }
+
 // k_box_pre + k_iou_pairwise2 for rows[R] x cols[C] (rows = concatenation of `batch` GT lists when row_offsets is
 // given; max_rows = the longest list).  rec / cull: [R + C] records in the workspace.
 static int launch_pairwise2(int kind, const float* rows, int64_t R, const float* cols, int64_t C, int D, int mode, int edge,
@@ -1872,7 +1886,7 @@ static int launch_pairwise2(int kind, const float* rows, int64_t R, const float*
     // (mostly-live) tiles are spread over more warps and the tail of the launch stays short
     const int64_t tiles32 = col_tiles * ((max_rows + 31) / 32) * batch;
     int tr = (tiles32 >= 16ll * sm_count()) ? 32 : 8;
-    if (g_force_tr == 8 || g_force_tr == 16 || g_force_tr == 32) tr = g_force_tr;   // tuning hook (SPHK_TR)
+    if (g_force_tr == 8 || g_force_tr == 32) tr = g_force_tr;   // tuning hook (SPHK_TR)
     const int64_t row_tiles = (max_rows + tr - 1) / tr;
     if (row_tiles > 0x7FFFFFFFll || col_tiles > 65535 || batch > 65535)
         return fail(SPHK_ERR_UNSUPPORTED, "pairwise: more than 16.7 M columns, 2^31 row tiles or 65535 images; shard the call");
@@ -1890,17 +1904,24 @@ static int launch_pairwise2(int kind, const float* rows, int64_t R, const float*
     cfg.numAttrs = g_no_pdl ? 0 : 1;
     const float4* crec = rec;
     const float4* ccull = cull;
-    const int dn = (g_dense != 0 ? 1 : 0) | (g_no_boxcull ? 2 : 0);
+    const int dn = (g_dense != 0 ? 1 : 0);
+    // which instance: with the box-frame prefilter test (rows = the short, large-box operand: ground truths x anchors) or without
+    const bool box = !g_no_boxcull && box_test_pays(max_rows, C);
     cudaError_t le;
-#define SPHK_PW2(DD, TR)                                                                                               \
-    le = cudaLaunchKernelEx(&cfg, k_iou_pairwise2<DD, TR>, rows, R, cols, C, crec, ccull, kind, mode, edge, out, ld, rkey, \
+#define SPHK_PW2(DD, TR, BX)                                                                                               \
+    le = cudaLaunchKernelEx(&cfg, k_iou_pairwise2<DD, TR, BX>, rows, R, cols, C, crec, ccull, kind, mode, edge, out, ld, rkey, \
                             ckey, (uint32_t)row_base, (uint32_t)col_base, dn, row_target, col_tie, row_offsets, col_stride, tile_rmax)
-    if (D == 4 && tr == 32) SPHK_PW2(4, 32);
-    else if (D == 4 && tr == 16) SPHK_PW2(4, 16);
-    else if (D == 4) SPHK_PW2(4, 8);
-    else if (tr == 32) SPHK_PW2(5, 32);
-    else if (tr == 16) SPHK_PW2(5, 16);
-    else SPHK_PW2(5, 8);
+    if (box) {
+        if (D == 4 && tr == 32) SPHK_PW2(4, 32, true);
+        else if (D == 4) SPHK_PW2(4, 8, true);
+        else if (tr == 32) SPHK_PW2(5, 32, true);
+        else SPHK_PW2(5, 8, true);
+    } else {
+        if (D == 4 && tr == 32) SPHK_PW2(4, 32, false);
+        else if (D == 4) SPHK_PW2(4, 8, false);
+        else if (tr == 32) SPHK_PW2(5, 32, false);
+        else SPHK_PW2(5, 8, false);
+    }
 #undef SPHK_PW2
     if (le != cudaSuccess) return cuda_fail(le, "cudaLaunchKernelEx(k_iou_pairwise2)");
     return SPHK_OK;
@@ -1920,7 +1941,7 @@ static int launch_rows32(int kind, const float* rows, int R, const float* cols, 
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = g_no_pdl ? 0 : 1;
-    const int fl = (g_dense != 0 ? 1 : 0) | (g_no_boxcull ? 2 : 0);
+    const int fl = (g_dense != 0 ? 1 : 0) | (g_no_boxcull ? 2 : 0);     // (bit 1 exists in the tuning build only)
     const bool rv = D == 4 && aligned16(rows), cv = D == 4 && aligned16(cols);
     cudaError_t le;
     if (D == 4) le = cudaLaunchKernelEx(&cfg, k_iou_rows32<4>, rows, R, cols, C, kind, mode, edge, out, ld, fl, rv, cv);
@@ -2533,7 +2554,7 @@ int sphk_prefilter_count(const float* rows, int64_t R, const float* cols, int64_
     float4* cull = rec + (R + C) * 4;
     if (D == 4) k_box_pre<4><<<blocks_for(R + C), kThreads, 0, s>>>(rows, R, cols, C, edge, rec, cull, aligned16(rows), aligned16(cols), nullptr, nullptr);
     else k_box_pre<5><<<blocks_for(R + C), kThreads, 0, s>>>(rows, R, cols, C, edge, rec, cull, false, false, nullptr, nullptr);
-    k_prefilter_count<<<dim3((unsigned)row_tiles, (unsigned)col_tiles), kThreads, 0, s>>>(R, C, cull, (unsigned long long*)live_count);
+    k_prefilter_count<<<dim3((unsigned)row_tiles, (unsigned)col_tiles), kThreads, 0, s>>>(R, C, cull, (unsigned long long*)live_count, box_test_pays(R, C));
     SPHK_LAUNCH_CHECK("k_prefilter_count");
     return SPHK_OK;
 }
