@@ -39,7 +39,7 @@ IMAGES, GTS, FLOP_PER_PAIR = 16, 32, 512.0      # W = 512 flop p
 SWEEP_ANCHORS, SWEEP_GTS = 1 << 20, 1024        # BASELINE.json configs[4]
 REF_ROWS_PER_STEP = 4096                         # reference arm: anchors per step (x 1024 GT = 4.2 M pairs, ~1 s of CPU)
 SWEEP_WORKLOAD = ("sweep: 1,048,576 x 1,024 RBFoV Sph2Pob-efficient IoU (BASELINE configs[4]), anchors row-sharded over the GPUs, "
-                  "fused per-anchor and per-GT max/argmax, one NCCL all_gather of packed keys + one unpack launch in the timed region")
+                  "fused per-anchor and per-GT max/argmax, exchange of the packed keys + unpack launch in the timed region")
 HBM_FALLBACK_GBS = 6650.0                       # B200_PROFILING.md fallback if MEASURED_PEAKS.json is absent
 
 
@@ -632,7 +632,7 @@ def run_ours(args):
         total_pairs_per_step = SWEEP_ANCHORS * SWEEP_GTS
 
         def step():
-            return sharded_max_overlaps(A_loc, G, SWEEP_ANCHORS, lo, anchors_are='bboxes1')
+            return sharded_max_overlaps(A_loc, G, SWEEP_ANCHORS, lo, anchors_are='bboxes1', exchange=args.exchange)
 
         _blk = key_block(SWEEP_ANCHORS, SWEEP_GTS, world, dev, fresh=True)
         _cap = block_capacity(SWEEP_ANCHORS, world)
@@ -715,7 +715,7 @@ def run_ours(args):
             # memory: across the ranks the host holds the whole result exactly once
             A_d.copy_(A_pin, non_blocking=True)
             G_d.copy_(G_pin, non_blocking=True)
-            am, aa, gm, ga = sharded_max_overlaps(A_d, G_d, SWEEP_ANCHORS, lo, anchors_are='bboxes1')
+            am, aa, gm, ga = sharded_max_overlaps(A_d, G_d, SWEEP_ANCHORS, lo, anchors_are='bboxes1', exchange=args.exchange)
             amax_pin.copy_(am[lo:hi], non_blocking=True)
             aarg_pin.copy_(aa[lo:hi], non_blocking=True)
             gmax_pin.copy_(gm, non_blocking=True)
@@ -760,6 +760,13 @@ def run_ours(args):
                "ms_per_step": t, "api": "SphOverlaps2D('sph2pob_efficient_iou', 5)(gt, anchors) x 16, pinned host in/out",
                "streams": "calls alternate between 2 CUDA streams (compute of one image overlaps the D2H of the previous one)"}
 
+    exchange_route_name = "none (replicas)"
+    if args.workload == "sweep":
+        from sph_retina_b200.sharded import exchange_route
+        exchange_route_name = exchange_route()
+        exchange_route_name = {"peer": "peer: keys read from the owners' symmetric buffers over NVLink inside the unpack launch "
+                                       "(sphk_unpack_peer_keys), no collective", "nccl": "nccl: one all_gather_into_tensor + unpack launch",
+                               "single": "single GPU: the unpack launch reads the local block"}[exchange_route_name]
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -771,7 +778,8 @@ def run_ours(args):
                        "pairs_per_step": total_pairs_per_step,
                        "l2": "256 MB written between timed steps (L2 flush)",
                        "timing": "CUDA events per step on the launching stream, sum over K steps, max over ranks",
-                       "collectives_per_step": (1 if world > 1 else 0) if args.workload == "sweep" else 0},
+                       "exchange": exchange_route_name,
+                       "collectives_per_step": (1 if exchange_route_name == "nccl" else 0)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches,
         }
         line.update(result)
@@ -813,6 +821,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="sweep", choices=["sweep", "assign"])
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
+                    help="sweep, N > 1: how the ranks' keys are exchanged (sph_retina_b200/sharded.py)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configs and keep the run short (ncu)")

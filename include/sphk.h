@@ -104,6 +104,20 @@ int sphk_iou_pairwise_keys(int kind, const float* rows, int64_t R, const float* 
 int sphk_unpack_gathered_keys(const uint64_t* gathered, int32_t world, int64_t n_long, int64_t n_short, int64_t cap,
                               float* long_max, int64_t* long_arg, float* short_max, int64_t* short_arg, void* stream);
 
+/* The same unpacking with the gather FUSED into the launch: no NCCL collective, the keys are read from the owners' buffers
+ * by peer loads over NVLink.  Every rank owns a symmetric buffer of identical layout (uint64 elements)
+ *     [ block of parity 0 : cap + n_short | block of parity 1 : cap + n_short | flags : >= world ]
+ * mapped into all processes of the node (torch.distributed._symmetric_memory); peer_bufs is a DEVICE array of the
+ * `world` base pointers (the handle's buffer_ptrs_dev).  The rank's compute kernel of step s writes the block at
+ * block_offset (= parity (s & 1) times (cap + n_short)); this launch, enqueued after it on the same stream, raises
+ * flags[rank] = s in every peer's buffer, waits until all flags of the local buffer have reached s, then reads every
+ * shard's keys from its owner and writes the same outputs as sphk_unpack_gathered_keys.  `step` counts from 1 and must
+ * advance by one per call on every rank; the flags must be zero before the first step.  A peer that does not arrive
+ * within ~5 s makes the kernel trap (the job fails instead of hanging). */
+int sphk_unpack_peer_keys(const uint64_t* const* peer_bufs, int32_t rank, int32_t world, uint64_t step, int64_t block_offset,
+                          int64_t flag_offset, int64_t n_long, int64_t n_short, int64_t cap, float* long_max, int64_t* long_arg,
+                          float* short_max, int64_t* short_arg, void* stream);
+
 /* Second pass of MaxIoUAssigner's low-quality matching with gt_max_assign_all=True
  * (mmdet/core/bbox/assigners/max_iou_assigner.py:201-205: for each GT i in ascending order,
  * `assigned[overlaps[i, :] == gt_max_overlaps[i]] = i + 1`) without the K x N matrix:

@@ -470,6 +470,69 @@ def golden_nms(R):
     print("nms", {k: v.shape for k, v in out.items() if "keep" in k})
 
 
+def golden_nms_cfg4(R):
+    """BASELINE configs[3] at its own shape: ONE image of 1,000 candidates (200 seed boxes + 4 noisy copies each, as
+    sph_retina_b200/synthetic.py::nms_batch builds them) with labels in [0, 80), thresholds 0.3 and 0.5, through the
+    reference's SphNMS -- and the R-CNN heads' wrapper ``multiclass_nms`` (sphdet/bbox/nms/utils.py:6-95) on top of it.
+    The seed is advanced until no same-label pair sits within 1e-5 of either threshold (float64 run), so that the keep
+    lists are decided well inside fp32 resolution."""
+    out = {}
+    for box in ("bfov", "rbfov"):
+        D = 4 if box == "bfov" else 5
+        seed = 400
+        while True:
+            torch.manual_seed(seed)
+            seeds = R.generate_boxes(200, alpha_range=(5, 60), beta_range=(5, 60), dtype="float", box=box)
+            boxes = (seeds.repeat(5, 1) + torch.randn(1000, D) * 2).clamp(min=1)
+            scores = torch.rand(1000)
+            idxs = torch.randint(0, 80, (1000,))
+            iou = _ref64(R.sph2pob_efficient_iou, boxes, boxes)
+            same = (idxs[:, None] == idxs[None, :]) & ~torch.eye(1000, dtype=torch.bool)
+            margin = min(float((iou[same] - t).abs().min()) for t in (0.3, 0.5))
+            if margin > 1e-5:
+                break
+            seed += 1
+        out["%s_seed" % box], out["%s_margin" % box] = np.int64(seed), np.float64(margin)
+        out["%s_boxes" % box], out["%s_scores" % box], out["%s_idxs" % box] = _np(boxes), _np(scores), _np(idxs)
+        for thr in (0.3, 0.5):
+            dets, keep = R.SphNMS("sph2pob_efficient")(boxes, scores, idxs, dict(type="nms", iou_threshold=thr))
+            out["%s_keep_thr%d" % (box, int(thr * 10))] = _np(keep)
+            out["%s_dets_thr%d" % (box, int(thr * 10))] = _np(dets)
+        dets, keep = R.SphNMS("sph2pob_efficient")(boxes, scores, idxs, dict(type="nms", iou_threshold=0.5, max_num=100))
+        out["%s_keep_thr5_max100" % box] = _np(keep)
+        # multiclass_nms: n proposals x C classes, class-specific boxes [n, C * D], scores [n, C + 1] (last = background)
+        torch.manual_seed(seed + 1000)
+        n, C = 120, 8
+        mb = (R.generate_boxes(n, alpha_range=(5, 60), beta_range=(5, 60), dtype="float", box=box)[:, None, :]
+              + torch.randn(n, C, D) * 1.5).clamp(min=1)
+        mb[60:] = mb[:60] + torch.randn(60, C, D) * 1.0           # near-duplicates: suppression happens inside a class
+        mb = mb.clamp(min=1).reshape(n, C * D).contiguous()
+        ms = torch.rand(n, C + 1)
+        fac = torch.rand(n) * 0.5 + 0.5
+        for tag, kw in (("plain", {}), ("factors", dict(score_factors=fac))):
+            dets, labels, inds = R.multiclass_nms(mb, ms, 0.3, dict(type="nms", iou_threshold=0.5), max_num=100, return_inds=True,
+                                                  nms_op=R.SphNMS("sph2pob_efficient"), box_version=D, **kw)
+            out["%s_mc_%s_dets" % (box, tag)], out["%s_mc_%s_labels" % (box, tag)], out["%s_mc_%s_inds" % (box, tag)] = _np(dets), _np(labels), _np(inds)
+        shared = mb[:, :D].contiguous()                            # class-agnostic boxes [n, D]
+        dets, labels, inds = R.multiclass_nms(shared, ms, 0.3, dict(type="nms", iou_threshold=0.5), max_num=-1, return_inds=True,
+                                              nms_op=R.SphNMS("sph2pob_efficient"), box_version=D)
+        out["%s_mc_shared_dets" % box], out["%s_mc_shared_labels" % box], out["%s_mc_shared_inds" % box] = _np(dets), _np(labels), _np(inds)
+        out["%s_mc_bboxes" % box], out["%s_mc_scores" % box], out["%s_mc_factors" % box] = _np(mb), _np(ms), _np(fac)
+        # decision margin of the multiclass fixture (same class, both boxes above the score threshold)
+        flat = mb.view(n, C, D)
+        mm = 1.0
+        for c in range(C):
+            v = ms[:, c] > 0.3
+            if int(v.sum()) > 1:
+                i2 = _ref64(R.sph2pob_efficient_iou, flat[v, c], flat[v, c])
+                off = ~torch.eye(int(v.sum()), dtype=torch.bool)
+                mm = min(mm, float((i2[off] - 0.5).abs().min()))
+        out["%s_mc_margin" % box] = np.float64(mm)
+        print("nms cfg4", box, "seed", seed, "margin %.2e" % margin, "mc margin %.2e" % mm,
+              {k: v.shape for k, v in out.items() if k.startswith(box) and ("keep" in k or "inds" in k)})
+    np.savez_compressed(os.path.join(OUT, "nms_cfg4.npz"), **out)
+
+
 def golden_coder(R):
     """Box coders and the decode -> Sph2PobIoULoss step of the head (reg_decoded_bbox=True): anchors from the real
     anchor grid, deltas that trigger every clamp, ~10 % positive rows (2-D weights as the head passes them)."""
@@ -562,11 +625,16 @@ def golden_distance_coder(R):
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     R = rh.load_reference()
+    if len(sys.argv) > 1:                 # regenerate the named fixtures only:  python oracle/make_golden.py nms_cfg4
+        for name in sys.argv[1:]:
+            globals()["golden_" + name](R)
+        sys.exit(0)
     golden_kat(R)
     golden_aligned(R)
     golden_pairwise(R)
     golden_loss(R)
     golden_nms(R)
+    golden_nms_cfg4(R)
     golden_coder(R)
     golden_other_losses(R)
     golden_naive(R)

@@ -164,6 +164,10 @@ def load_reference():
         planar_nms = importlib.import_module("sphdet.bbox.nms.planar_nms")
     except Exception:
         planar_nms = None
+    try:
+        nms_utils = importlib.import_module("sphdet.bbox.nms.utils")       # multiclass_nms (R-CNN heads), utils.py:6-95
+    except Exception:
+        nms_utils = None
 
     # losses: exec obb_iou_loss / OBBIoULoss with the in-tree weighted_loss (mmdet/models/losses/utils.py)
     losses_utils = _load_mmdet_loss_utils()
@@ -253,6 +257,7 @@ def load_reference():
         sph2pob_legacy_iou=api.sph2pob_legacy_iou,
         sph_iou=api.sph_iou, fov_iou=api.fov_iou, naive_iou=api.naive_iou, unbiased_iou=api.unbiased_iou,
         SphOverlaps2D=calc.SphOverlaps2D, SphNMS=sph_nms.SphNMS, PlanarNMS=getattr(planar_nms, 'PlanarNMS', None),
+        multiclass_nms=getattr(nms_utils, 'multiclass_nms', None),
         Sph2PobIoULoss=iou_loss.Sph2PobIoULoss, SphIoULossLegacy=iou_loss.SphIoULossLegacy,
         Sph2PobGDLoss=gd_loss.Sph2PobGDLoss, Sph2PobKFLoss=kf_loss.Sph2PobKFLoss, Sph2PobL1Loss=l1_loss.Sph2PobL1Loss,
         jiter_spherical_bboxes=api.jiter_spherical_bboxes,

@@ -854,6 +854,34 @@ def nms_batched(boxes, scores, idxs, iou_threshold=0.5, max_num=None, class_agno
 # --------------------------------------------------------------------------- #
 # MaxIoUAssigner.assign_wrt_overlaps (mmdet/core/bbox/assigners/max_iou_assigner.py:135-220)
 # --------------------------------------------------------------------------- #
+def multiclass_nms(multi_bboxes, multi_scores, score_thr, iou_threshold, max_num=-1, score_factors=None, box_version=4,
+                   nms_max_num=None):
+    """sphdet/bbox/nms/utils.py:6-95 (the R-CNN heads' wrapper) restated on top of nms_batched (= SphNMS, sph_nms.py:22-74):
+    class-specific boxes [n, C * D] or shared boxes [n, D]; scores [n, C + 1] with the background in the last column;
+    candidates are the (proposal, class) pairs with score > score_thr (:55), score factors are applied AFTER that mask
+    (:58-63); SphNMS per class; the first max_num detections (:88-90).  Returns (dets, labels, inds into the flattened
+    [n * C] (proposal, class) grid)."""
+    num_classes = multi_scores.size(1) - 1
+    if multi_bboxes.shape[1] > box_version:
+        bboxes = multi_bboxes.view(multi_scores.size(0), -1, box_version)
+    else:
+        bboxes = multi_bboxes[:, None].expand(multi_scores.size(0), num_classes, box_version)
+    scores = multi_scores[:, :-1]
+    labels = torch.arange(num_classes, dtype=torch.long).view(1, -1).expand_as(scores)
+    bboxes, scores, labels = bboxes.reshape(-1, box_version), scores.reshape(-1), labels.reshape(-1)
+    valid = scores > score_thr
+    if score_factors is not None:
+        scores = scores * score_factors.view(-1, 1).expand(multi_scores.size(0), num_classes).reshape(-1)
+    inds = valid.nonzero(as_tuple=False).squeeze(1)
+    bboxes, scores, labels = bboxes[inds], scores[inds], labels[inds]
+    if bboxes.numel() == 0:
+        return torch.cat([bboxes, scores[:, None]], -1), labels, inds
+    dets, keep = nms_batched(bboxes, scores, labels, iou_threshold, max_num=nms_max_num)
+    if max_num > 0:
+        dets, keep = dets[:max_num], keep[:max_num]
+    return dets, labels[keep], inds[keep]
+
+
 def assign_wrt_overlaps(overlaps, gt_labels=None, pos_iou_thr=0.5, neg_iou_thr=0.4, min_pos_iou=0.0,
                         gt_max_assign_all=True, match_low_quality=True, lowest_index_ties=False):
     """Literal restatement, Python loop over the GTs included.  Returns (gt_inds, max_overlaps, labels)."""

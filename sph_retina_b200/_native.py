@@ -43,6 +43,8 @@ SIGNATURES = {
                                       _i32, ctypes.c_void_p, ctypes.c_void_p]),
     "sphk_unpack_gathered_keys": (_int, [ctypes.c_void_p, _i32, _i64, _i64, _i64, _c_float_p, ctypes.c_void_p, _c_float_p,
                                          ctypes.c_void_p, ctypes.c_void_p]),
+    "sphk_unpack_peer_keys": (_int, [ctypes.c_void_p, _i32, _i32, ctypes.c_uint64, _i64, _i64, _i64, _i64, _i64, _c_float_p, ctypes.c_void_p,
+                                     _c_float_p, ctypes.c_void_p, ctypes.c_void_p]),
     "sphk_max_iou_assign_workspace_bytes": (_i64, [_i64, _i64, _i32]),
     "sphk_max_iou_assign": (_int, [_int, _c_float_p, ctypes.POINTER(_i32), _i32, _c_float_p, _i64, _int, ctypes.c_float,
                                    ctypes.c_float, ctypes.c_float, ctypes.c_float, _int, _int, ctypes.c_void_p, ctypes.c_void_p,
@@ -275,6 +277,23 @@ def unpack_gathered_keys(gathered, world: int, n_long: int, n_short: int, cap: i
     with _on_device(dev):
         _check(lib.sphk_unpack_gathered_keys(_ptr(gathered), world, n_long, n_short, cap, _ptr(lmax), _ptr(larg), _ptr(smax),
                                              _ptr(sarg), _stream(gathered)))
+    launches += 1
+    return lmax, larg, smax, sarg
+
+
+def unpack_peer_keys(peer_bufs_dev: int, rank: int, world: int, step: int, block_offset: int, flag_offset: int, n_long: int,
+                     n_short: int, cap: int, device):
+    """Row-sharded N x M with the gather fused into the unpack launch (include/sphk.h: sphk_unpack_peer_keys): the keys of
+    every shard are read from its owner's symmetric buffer over NVLink.  ``peer_bufs_dev``: device address of the array
+    of the ranks' buffer base pointers (``_SymmetricMemory.buffer_ptrs_dev``)."""
+    global launches
+    lmax = torch.empty(n_long, dtype=torch.float32, device=device)
+    larg = torch.empty(n_long, dtype=torch.int64, device=device)
+    smax = torch.empty(n_short, dtype=torch.float32, device=device)
+    sarg = torch.empty(n_short, dtype=torch.int64, device=device)
+    with _on_device(device):
+        _check(lib.sphk_unpack_peer_keys(peer_bufs_dev, rank, world, step, block_offset, flag_offset, n_long, n_short, cap,
+                                         _ptr(lmax), _ptr(larg), _ptr(smax), _ptr(sarg), _raw_stream(device.index)))
     launches += 1
     return lmax, larg, smax, sarg
 

@@ -1007,6 +1007,77 @@ k_unpack_gathered(const unsigned long long* __restrict__ gathered, int world, in
     }
 }
 
+// ---- the same, with the gather fused into the launch: peer loads over NVLink instead of an NCCL all-gather -----------
+// Every rank keeps its key blocks in a SYMMETRIC buffer (same layout on every GPU of the node, mapped into every
+// process: torch.distributed._symmetric_memory): [parity 0 block | parity 1 block | flags[world]].  A step is
+//   compute kernel (writes this rank's block of the step's parity)  ->  this kernel:
+//     1. block 0 tells every peer "my block of step s is complete" (a release store of s into flags[rank] of the peer's
+//        buffer: the compute kernel precedes this launch in the stream, so its writes are visible before the flag is);
+//     2. every CTA waits until the flags of all peers in the LOCAL buffer have reached s (acquire loads);
+//     3. the keys of the whole anchor set are read straight from the owners' buffers (coalesced 8-byte peer loads,
+//        7/8 of them over NVLink) and unpacked exactly as k_unpack_gathered does.
+// No collective kernel, no staging copy, no second launch: what is exposed after the compute kernel is the skew between
+// the ranks plus ~10 us of peer reads.  The blocks alternate between two parities: a rank that runs ahead by one step
+// writes the other parity, and it cannot run ahead by two (its step s + 1 waits for every peer's flag s + 1, which a
+// peer raises only after its own step-s reads).  A rank that never shows up would leave the others spinning: after
+// ~5 s the kernel traps, so a broken job fails instead of hanging the GPUs.
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_unpack_peers(unsigned long long* const* __restrict__ peer_bufs, int rank, int world, unsigned long long step,
+               int64_t block_offset, int64_t flag_offset, int64_t n_long, int64_t n_short, int64_t cap,
+               float* __restrict__ long_max, int64_t* __restrict__ long_arg, float* __restrict__ short_max,
+               int64_t* __restrict__ short_arg) {
+    __shared__ const unsigned long long* s_blk[16];
+    if (threadIdx.x < world) {
+        unsigned long long* const peer = peer_bufs[threadIdx.x];
+        s_blk[threadIdx.x] = peer + block_offset;
+        if (blockIdx.x == 0) {
+            __threadfence_system();
+            st_release_sys(peer + flag_offset + rank, step);
+        }
+        const unsigned long long* mine = peer_bufs[rank] + flag_offset + threadIdx.x;
+        unsigned long long t0 = 0;
+        unsigned spins = 0;
+        while (ld_acquire_sys(mine) < step) {
+            if ((++spins & 1023u) == 0u) {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > 5000000000ull) __trap();      // a peer never arrived: fail, do not hang
+            }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    unsigned long long k = 0ull;
+    if (i < n_long) {
+        const int64_t base = n_long / world, extra = n_long % world;
+        const int64_t cut = extra * (base + 1);
+        const int64_t s = (i < cut) ? i / (base + 1) : extra + (i - cut) / (base > 0 ? base : 1);
+        const int64_t lo = s * base + (s < extra ? s : extra);
+        k = __ldcg(s_blk[s] + (i - lo));
+        long_max[i] = (k == 0ull) ? 0.0f : __uint_as_float((uint32_t)(k >> 32));
+        long_arg[i] = (k == 0ull) ? 0 : (int64_t)(0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull));
+    } else if (i < n_long + n_short) {
+        const int64_t j = i - n_long;
+        for (int s = 0; s < world; ++s) {
+            const unsigned long long v = __ldcg(s_blk[s] + cap + j);
+            k = v > k ? v : k;
+        }
+        short_max[j] = (k == 0ull) ? 0.0f : __uint_as_float((uint32_t)(k >> 32));
+        short_arg[j] = (k == 0ull) ? 0 : (int64_t)(0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull));
+    }
+}
+
 // ---- loss --------------------------------------------------------------------------------------
 template <int D>
 __global__ void __launch_bounds__(kThreads)
@@ -2087,6 +2158,24 @@ int sphk_unpack_gathered_keys(const uint64_t* gathered, int32_t world, int64_t n
     k_unpack_gathered<<<blocks_for(n_long + n_short), kThreads, 0, (cudaStream_t)stream>>>(
         (const unsigned long long*)gathered, world, n_long, n_short, cap, long_max, long_arg, short_max, short_arg);
     SPHK_LAUNCH_CHECK("k_unpack_gathered");
+    return SPHK_OK;
+}
+
+int sphk_unpack_peer_keys(const uint64_t* const* peer_bufs, int32_t rank, int32_t world, uint64_t step, int64_t block_offset,
+                          int64_t flag_offset, int64_t n_long, int64_t n_short, int64_t cap, float* long_max, int64_t* long_arg,
+                          float* short_max, int64_t* short_arg, void* stream) {
+    if (world < 1 || world > 16 || rank < 0 || rank >= world || n_long < 0 || n_short < 0 || cap < 0 || block_offset < 0 || flag_offset < 0)
+        return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_unpack_peer_keys: bad rank, world (1..16) or sizes");
+    if (cap < (n_long + world - 1) / world) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_unpack_peer_keys: cap < ceil(n_long / world)");
+    if (step == 0) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_unpack_peer_keys: steps count from 1 (the flags start at 0)");
+    if (!peer_bufs || (n_long > 0 && (!long_max || !long_arg)) || (n_short > 0 && (!short_max || !short_arg)))
+        return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_unpack_peer_keys: null pointer");
+    // (at least one CTA even when there is nothing to unpack: the flags must be exchanged every step)
+    const unsigned g = blocks_for(n_long + n_short > 0 ? n_long + n_short : 1);
+    k_unpack_peers<<<g, kThreads, 0, (cudaStream_t)stream>>>((unsigned long long* const*)peer_bufs, rank, world, (unsigned long long)step,
+                                                            block_offset, flag_offset, n_long, n_short, cap, long_max, long_arg,
+                                                            short_max, short_arg);
+    SPHK_LAUNCH_CHECK("k_unpack_peers");
     return SPHK_OK;
 }
 

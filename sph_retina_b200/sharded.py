@@ -6,9 +6,13 @@ writes its packed keys straight into the rank's communication block
 
     block = [ keys of the rank's anchors (cap = ceil(n / world) slots) | the rank's keys of the G ground truths ]
 
-and the exchange is ONE NCCL ``all_gather_into_tensor`` of the blocks (8 B per anchor + 8 B x G per rank) followed by
-ONE kernel launch (``sphk_unpack_gathered_keys``) that writes the per-anchor (max, argmax) of the whole anchor set in
-global order and reduces the per-GT keys over the ranks.  No padding copy, no concatenation, no eager unpacking.
+and the exchange is ONE kernel launch that writes the per-anchor (max, argmax) of the whole anchor set in global order
+and reduces the per-GT keys over the ranks.  Two routes feed it:
+  * 'peer' (default where available): the blocks live in symmetric memory and the launch itself reads every shard's keys
+    from its owner over NVLink after an in-kernel flag handshake (``sphk_unpack_peer_keys``) -- no collective at all;
+  * 'nccl': ONE ``all_gather_into_tensor`` of the blocks (8 B per anchor + 8 B x G per rank), then
+    ``sphk_unpack_gathered_keys``.
+No padding copy, no concatenation, no eager unpacking on either route.
 Packing: int64 key = float32 bits << 32 | (0xFFFFFFFF - index).  IoU >= 0, so integer order is (value, then LOWEST
 index); the maximum over ranks therefore equals the single-device tie rule.
 
@@ -72,16 +76,103 @@ def exchange_blocks(block: torch.Tensor, group=None) -> torch.Tensor:
 
 
 def gather_assignment(block: torch.Tensor, n_anchors: int, n_gt: int, group=None):
-    """Collective step: the rank's filled block -> global (anchor_max, anchor_arg, gt_max, gt_arg) on every rank
-    (argmax int64 as torch.max returns it).  One all_gather + one kernel launch."""
+    """Collective step (NCCL route): the rank's filled block -> global (anchor_max, anchor_arg, gt_max, gt_arg) on every
+    rank (argmax int64 as torch.max returns it).  One all_gather + one kernel launch."""
     from . import _native
     world = _world(group)
     gathered = exchange_blocks(block, group)
     return _native.unpack_gathered_keys(gathered, world, n_anchors, n_gt, block_capacity(n_anchors, world))
 
 
+class PeerExchange:
+    """The exchange without a collective: every rank's key blocks live in a symmetric buffer
+    (torch.distributed._symmetric_memory: the same allocation mapped into every process of the node), and the unpack
+    launch reads each shard's keys from its owner over NVLink after a flag handshake inside the kernel
+    (``sphk_unpack_peer_keys``, csrc/sphk_kernels.cu: k_unpack_peers).  Layout per rank, in int64 elements:
+    [ block of even steps | block of odd steps | flags ]; the compute kernel of step s writes block (s & 1)."""
+    FLAG_SLOTS = 32
+
+    def __init__(self, n_anchors: int, n_gt: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if self.world > 16:
+            raise RuntimeError("PeerExchange: at most 16 ranks (one node)")
+        self.n_anchors, self.n_gt = n_anchors, n_gt
+        self.cap = block_capacity(n_anchors, self.world)
+        self.per = self.cap + n_gt
+        self.buf = symm_mem.empty(2 * self.per + self.FLAG_SLOTS, dtype=torch.int64, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        self.buf.zero_()                       # padding slots and flags start at zero ...
+        torch.cuda.synchronize(device)
+        self.hdl.barrier()                     # ... on every rank before anybody raises a flag
+        self.ptrs_dev = int(self.hdl.buffer_ptrs_dev)
+        self.step = 0
+
+    def next_block(self) -> torch.Tensor:
+        """The block the compute kernel of the next step writes into ([cap + n_gt] int64 view of the symmetric buffer)."""
+        self.step += 1
+        off = (self.step & 1) * self.per
+        return self.buf[off:off + self.per]
+
+    def finish(self):
+        """-> (anchor_max, anchor_arg, gt_max, gt_arg) of the step whose block was handed out last."""
+        from . import _native
+        return _native.unpack_peer_keys(self.ptrs_dev, self.rank, self.world, self.step, (self.step & 1) * self.per, 2 * self.per,
+                                        self.n_anchors, self.n_gt, self.cap, self.buf.device)
+
+
+_peer_exchanges = {}
+_peer_failed = []
+
+
+def _all_ranks_ok(ok: bool, device, group) -> bool:
+    """Collective AND of a per-rank success flag: the ranks must all take the same route."""
+    t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return bool(int(t.item()))
+
+
+def peer_exchange(n_anchors: int, n_gt: int, device, group=None):
+    """The cached PeerExchange of (shape, device), or None where symmetric memory is not available on EVERY rank (then:
+    NCCL route).  Collective on first use: each step of the set-up is agreed on by all ranks before the next one."""
+    key = (str(device), n_anchors, n_gt, _world(group))
+    ex = _peer_exchanges.get(key)
+    if ex is None and not _peer_failed:
+        why = None
+        try:
+            import torch.distributed._symmetric_memory as symm_mem      # noqa: F401  (API present in this torch?)
+            probe = symm_mem.empty(16, dtype=torch.int64, device=device)
+            del probe
+        except Exception as e:                # pragma: no cover
+            why = repr(e)
+        if not _all_ranks_ok(why is None, device, group):
+            why = why or "symmetric memory unavailable on another rank"
+        else:
+            try:
+                ex = PeerExchange(n_anchors, n_gt, device, group)
+            except Exception as e:            # pragma: no cover
+                why = repr(e)
+            if not _all_ranks_ok(ex is not None, device, group):
+                ex, why = None, why or "symmetric-memory rendezvous failed on another rank"
+        if ex is None:
+            import warnings
+            _peer_failed.append(why)
+            warnings.warn("sph_retina_b200.sharded: symmetric-memory exchange unavailable (%s); using the NCCL all_gather route" % why)
+        else:
+            _peer_exchanges[key] = ex
+    return ex
+
+
+def exchange_route(device=None, group=None) -> str:
+    """'peer' | 'nccl' | 'single' -- which route sharded_max_overlaps(exchange='auto') takes in this process."""
+    if _world(group) == 1:
+        return "single"
+    return "nccl" if _peer_failed else "peer"
+
+
 def sharded_max_overlaps(anchors_local, gts, n_anchors, anchor_offset, backend='sph2pob_efficient_iou', mode='iou',
-                         anchors_are='bboxes1', group=None):
+                         anchors_are='bboxes1', group=None, exchange='auto'):
     """overlaps.max over both axes of the logical [n_anchors x n_gt] (or transposed) matrix.
 
     anchors_local : this rank's contiguous shard [n_local, D] starting at global row `anchor_offset`
@@ -89,6 +180,9 @@ def sharded_max_overlaps(anchors_local, gts, n_anchors, anchor_offset, backend='
     gts           : the replicated short set [G, D]
     anchors_are   : 'bboxes1' -> IoU(anchor, gt) (config #5 call), 'bboxes2' -> IoU(gt, anchor)
                     (the assigner's orientation); the jitters are role-asymmetric, so this matters.
+    exchange      : 'peer' -- keys read from the owners' symmetric buffers inside the unpack launch (no collective);
+                    'nccl' -- one all_gather_into_tensor + the unpack launch; 'auto' -- 'peer' where available.
+                    Every rank must make the same choice.
     Returns (anchor_max[n_anchors], anchor_arg -> gt index, gt_max[G], gt_arg -> global anchor index)."""
     from . import _native
     kind = _KINDS[backend]
@@ -100,7 +194,10 @@ def sharded_max_overlaps(anchors_local, gts, n_anchors, anchor_offset, backend='
         raise ValueError("rank %d of %d must hold anchors [%d, %d) of %d, got offset %d and %d rows"
                          % (rank, world, lo, hi, n_anchors, anchor_offset, n_local))
     cap = block_capacity(n_anchors, world)
-    block = key_block(n_anchors, n_gt, world, anchors_local.device)
+    ex = peer_exchange(n_anchors, n_gt, anchors_local.device, group) if (world > 1 and exchange in ('auto', 'peer')) else None
+    if exchange == 'peer' and world > 1 and ex is None:
+        raise RuntimeError("sharded_max_overlaps(exchange='peer'): symmetric memory is not available: %s" % _peer_failed)
+    block = ex.next_block() if ex is not None else key_block(n_anchors, n_gt, world, anchors_local.device)
     a_out, g_out = block[:n_local], block[cap:]
     # the kernel's packed keys go straight into the communication block: no unpack / repack / copy
     with torch.no_grad():
@@ -110,4 +207,6 @@ def sharded_max_overlaps(anchors_local, gts, n_anchors, anchor_offset, backend='
         else:
             _native.iou_pairwise_keys(kind, gts, anchors_local, mode, col_base=anchor_offset, row_keys_out=g_out,
                                       col_keys_out=a_out)
+    if ex is not None:
+        return ex.finish()
     return gather_assignment(block, n_anchors, n_gt, group)

@@ -1021,14 +1021,47 @@ def test_nms_image_blocks_equals_per_image_nms(api, box):
             assert bool(valid[got].all()) and bool(((got >= b * K) & (got < (b + 1) * K)).all())
 
 
-def test_multiclass_nms_wrapper(api):
-    n, C = 300, 5
-    bboxes = O.generate_boxes(n * C, alpha_range=(5, 60), beta_range=(5, 60), box="bfov", seed=12).view(n, C * 4).to(DEV)
-    scores = torch.rand(n, C + 1, device=DEV)
-    dets, labels, inds = api.nms.multiclass_nms(bboxes, scores, 0.3, dict(iou_threshold=0.5), max_num=100,
-                                                return_inds=True, box_version=4)
-    assert dets.shape[1] == 5 and dets.shape[0] <= 100 and labels.shape[0] == dets.shape[0]
-    assert bool((dets[:-1, -1] >= dets[1:, -1]).all()) and float(dets[:, -1].min()) > 0.3
+@pytest.mark.parametrize("box", ["bfov", "rbfov"])
+def test_nms_golden_at_the_test_time_shape(api, box):
+    """BASELINE configs[3] at its own shape: one image of 1,000 candidates with labels in [0, 80), thresholds 0.3 / 0.5,
+    keep lists from the reference's SphNMS (no same-label pair within 1e-5 of a threshold: margin recorded in the fixture),
+    through the per-call path AND the device pipeline of a test batch."""
+    g = load_golden("nms_cfg4")
+    boxes, scores, idxs = cu(g[box + "_boxes"]), cu(g[box + "_scores"]), cu(g[box + "_idxs"])
+    nms = api.nms.SphNMS()
+    for thr, tag in ((0.3, "thr3"), (0.5, "thr5")):
+        dets, keep = nms(boxes, scores, idxs, dict(type="nms", iou_threshold=thr))
+        assert keep.cpu().tolist() == g["%s_keep_%s" % (box, tag)].tolist()
+        np.testing.assert_allclose(dets.cpu().numpy(), g["%s_dets_%s" % (box, tag)], atol=1e-6)
+        parity_record("nms_keep_list", n=int(boxes.size(0)), threshold=thr, kept=int(keep.numel()), n_fail_before_allowances=0,
+                      decision_margin_fp64=float(g[box + "_margin"]))
+    _, keep = nms(boxes, scores, idxs, dict(type="nms", iou_threshold=0.5, max_num=100))
+    assert keep.cpu().tolist() == g[box + "_keep_thr5_max100"].tolist()
+    # the same image as one block of the batched device pipeline (top-100 per image, score order)
+    out_idx, counts = api.nms.sph_nms_image_blocks(boxes, scores, idxs, 1, 80, 0.5, 100)
+    assert int(counts[0]) == 100 and out_idx[0, :100].cpu().tolist() == g[box + "_keep_thr5_max100"].tolist()
+
+
+@pytest.mark.parametrize("box", ["bfov", "rbfov"])
+def test_multiclass_nms_wrapper(api, box):
+    """multiclass_nms (sphdet/bbox/nms/utils.py:6-95) against the reference's function run with SphNMS('sph2pob_efficient'):
+    class-specific and shared boxes, score factors applied after the score mask, max_num."""
+    g = load_golden("nms_cfg4")
+    D = 4 if box == "bfov" else 5
+    mb, ms, fac = cu(g[box + "_mc_bboxes"]), cu(g[box + "_mc_scores"]), cu(g[box + "_mc_factors"])
+    for tag, kw in (("plain", {}), ("factors", dict(score_factors=fac))):
+        dets, labels, inds = api.nms.multiclass_nms(mb, ms, 0.3, dict(type="nms", iou_threshold=0.5), max_num=100, return_inds=True,
+                                                    box_version=D, **kw)
+        assert inds.cpu().tolist() == g["%s_mc_%s_inds" % (box, tag)].tolist()
+        assert labels.cpu().tolist() == g["%s_mc_%s_labels" % (box, tag)].tolist()
+        np.testing.assert_allclose(dets.cpu().numpy(), g["%s_mc_%s_dets" % (box, tag)], atol=1e-6)
+    dets, labels, inds = api.nms.multiclass_nms(mb[:, :D].contiguous(), ms, 0.3, dict(type="nms", iou_threshold=0.5), return_inds=True,
+                                                box_version=D)
+    assert inds.cpu().tolist() == g[box + "_mc_shared_inds"].tolist() and labels.cpu().tolist() == g[box + "_mc_shared_labels"].tolist()
+    np.testing.assert_allclose(dets.cpu().numpy(), g[box + "_mc_shared_dets"], atol=1e-6)
+    dets2, labels2 = api.nms.multiclass_nms(mb, ms, 0.3, dict(iou_threshold=0.5), max_num=100, box_version=D)
+    assert dets2.shape[0] == 100 and labels2.shape[0] == 100
+    parity_record("multiclass_nms", n=int(ms.numel()), n_fail_before_allowances=0, decision_margin_fp64=float(g[box + "_mc_margin"]))
 
 
 # ---- box coders and the fused decode -> loss step (SURVEY.md 8f row 2) ---------------------------------

@@ -145,6 +145,31 @@ def test_restatement_nms(box):
     assert keep.tolist() == g[box + "_keep_agnostic"].tolist()
 
 
+@pytest.mark.parametrize("box", ["bfov", "rbfov"])
+def test_restatement_nms_at_the_test_time_shape_and_multiclass_nms(box):
+    """BASELINE configs[3] at its own shape (one image: 1,000 candidates, labels in [0, 80), thresholds 0.3 / 0.5; no
+    same-label pair within 1e-5 of a threshold in the float64 run -- tests/golden/nms_cfg4.npz records the margin) and the
+    R-CNN wrapper multiclass_nms (sphdet/bbox/nms/utils.py:6-95), both from the reference's own classes."""
+    g = load_golden("nms_cfg4")
+    assert float(g[box + "_margin"]) > 1e-5 and float(g[box + "_mc_margin"]) > 1e-5
+    boxes, scores, idxs = (torch.from_numpy(g["%s_%s" % (box, k)]) for k in ("boxes", "scores", "idxs"))
+    assert boxes.shape[0] == 1000 and int(idxs.max()) < 80
+    for thr, tag in ((0.3, "thr3"), (0.5, "thr5")):
+        dets, keep = O.nms_batched(boxes, scores, idxs, thr)
+        assert keep.tolist() == g["%s_keep_%s" % (box, tag)].tolist()
+        np.testing.assert_allclose(dets.numpy(), g["%s_dets_%s" % (box, tag)], atol=1e-6)
+    _, keep = O.nms_batched(boxes, scores, idxs, 0.5, max_num=100)
+    assert keep.tolist() == g[box + "_keep_thr5_max100"].tolist()
+    D = boxes.size(1)
+    mb, ms, fac = (torch.from_numpy(g["%s_mc_%s" % (box, k)]) for k in ("bboxes", "scores", "factors"))
+    for tag, kw in (("plain", {}), ("factors", dict(score_factors=fac))):
+        dets, labels, inds = O.multiclass_nms(mb, ms, 0.3, 0.5, max_num=100, box_version=D, **kw)
+        assert inds.tolist() == g["%s_mc_%s_inds" % (box, tag)].tolist() and labels.tolist() == g["%s_mc_%s_labels" % (box, tag)].tolist()
+        np.testing.assert_allclose(dets.numpy(), g["%s_mc_%s_dets" % (box, tag)], atol=1e-6)
+    dets, labels, inds = O.multiclass_nms(mb[:, :D].contiguous(), ms, 0.3, 0.5, box_version=D)
+    assert inds.tolist() == g[box + "_mc_shared_inds"].tolist() and labels.tolist() == g[box + "_mc_shared_labels"].tolist()
+
+
 CODER_VARIANTS = (("plain", {}), ("norm", "norm"), ("ctr", "ctr"), ("noclip", "noclip"))
 
 
