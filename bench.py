@@ -764,6 +764,8 @@ def run_ours(args):
     if args.workload == "sweep":
         from sph_retina_b200.sharded import exchange_route
         exchange_route_name = exchange_route()
+        if exchange_route_name == "peer" and args.exchange == "nccl":
+            exchange_route_name = "nccl"
         exchange_route_name = {"peer": "peer: keys read from the owners' symmetric buffers over NVLink inside the unpack launch "
                                        "(sphk_unpack_peer_keys), no collective", "nccl": "nccl: one all_gather_into_tensor + unpack launch",
                                "single": "single GPU: the unpack launch reads the local block"}[exchange_route_name]

@@ -367,6 +367,22 @@ def test_sharding_emulated_on_one_gpu(api, world):
         for g_, w_, s_ in zip(got, want, (a_max, a_arg, g_max, g_arg)):
             assert torch.equal(g_, w_) and torch.equal(g_, s_)
         assert int(g_arg[5]) == 17
+        # the fused route (sphk_unpack_peer_keys): every "rank" owns a buffer [even block | odd block | flags]; here they
+        # all sit on this GPU, and the flags are pre-set to the step as if every peer had arrived (the handshake itself
+        # needs one process per GPU: bench.py --gpus N --exchange peer).  Step 3 -> the odd block.
+        per, step = cap + G.size(0), 3
+        bufs = []
+        for rank in range(world):
+            buf = torch.zeros(2 * per + 32, dtype=torch.int64, device=DEV)
+            buf[per:2 * per] = blocks[rank]
+            buf[2 * per:2 * per + world] = step
+            bufs.append(buf)
+        table = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=DEV)
+        for rank in range(world):
+            peer = _native.unpack_peer_keys(table.data_ptr(), rank, world, step, per, 2 * per, n, G.size(0), cap, torch.device(DEV))
+            for p_, g_ in zip(peer, got):
+                assert torch.equal(p_, g_)
+            assert int(bufs[(rank + 1) % world][2 * per + rank]) == step       # the rank raised its flag in the peer's buffer
     # "no positive overlap" (key 0) reads as (0.0, index 0) on both sides
     far = torch.tensor([[10.0, 90.0, 0.5, 0.5, 0.0], [190.0, 90.0, 20.0, 20.0, 0.0], [12.0, 40.0, 0.5, 0.5, 0.0]], device=DEV)
     one = torch.tensor([[190.0, 90.0, 20.0, 20.0, 0.0], [300.0, 150.0, 1.0, 1.0, 0.0]], device=DEV)
