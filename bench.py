@@ -709,26 +709,24 @@ def run_ours(args):
         gmax_pin = torch.empty(SWEEP_GTS, dtype=torch.float32).pin_memory()
         garg_pin = torch.empty(SWEEP_GTS, dtype=torch.int64).pin_memory()
 
+        from sph_retina_b200.sharded import HostSweep
+        hs = HostSweep(SWEEP_ANCHORS, n_loc, SWEEP_GTS, 5, dev, exchange=args.exchange)
+
         def e2e_step():
-            # every rank: its shard of the anchors and the GT from pinned host memory -> the sharded call (kernels +
-            # collective + unpack) -> its own slice of the per-anchor result and the per-GT result back to pinned host
-            # memory: across the ranks the host holds the whole result exactly once
-            A_d.copy_(A_pin, non_blocking=True)
-            G_d.copy_(G_pin, non_blocking=True)
-            am, aa, gm, ga = sharded_max_overlaps(A_d, G_d, SWEEP_ANCHORS, lo, anchors_are='bboxes1', exchange=args.exchange)
-            amax_pin.copy_(am[lo:hi], non_blocking=True)
-            aarg_pin.copy_(aa[lo:hi], non_blocking=True)
-            gmax_pin.copy_(gm, non_blocking=True)
-            garg_pin.copy_(ga, non_blocking=True)
+            # every rank: its shard of the anchors and the GT in pinned host memory -> HostSweep (H2D, kernels and D2H
+            # pipelined over row chunks; per-GT keys exchanged between the ranks) -> the per-anchor result of its shard and
+            # the global per-GT result in pinned host memory: across the ranks the host holds the whole result exactly once
+            hs(A_pin, G_pin, lo, amax_pin, aarg_pin, gmax_pin, garg_pin)
         e2e_ms = time_steps(torch, e2e_step, max(5, args.steps // 2), 3, flush, barrier)
         t = max_over_ranks(statistics.mean(e2e_ms))
         e2e = {"value": total_pairs_per_step / (t * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": SWEEP_ANCHORS * 20 + world * SWEEP_GTS * 20,
                "d2h_bytes_per_step": SWEEP_ANCHORS * 12 + world * SWEEP_GTS * 12,
-               "ms_per_step": t, "api": "sph_retina_b200.sharded.sharded_max_overlaps(anchors_shard, gts, n_anchors, offset)",
-               "copies": "per rank and step: H2D of its anchor shard (n/N x 20 B) + the GT (20 kB) from pinned memory; D2H of its "
-                         "slice of the gathered (max fp32, argmax int64) per anchor + the per-GT result into pinned memory; "
-                         "byte counts are whole-job sums over the ranks"}
+               "ms_per_step": t, "api": "sph_retina_b200.sharded.HostSweep(...)(anchors_pinned, gts_pinned, offset, out...)",
+               "chunks_per_rank": hs.chunks,
+               "copies": "per rank and step: H2D of its anchor shard (n/N x 20 B) + the GT (20 kB) from pinned memory; D2H of the "
+                         "(max fp32, argmax int64) of its anchors + the global per-GT result into pinned memory; copies run on "
+                         "a copy stream under the kernels of the neighbouring row chunks; byte counts are whole-job sums over the ranks"}
         if world == 1 and rank == 0:
             # the same result without the fused reduction: the full 4.3 GB matrix does not leave the device in the
             # reference either (MaxIoUAssigner reduces it on the GPU); listed for scale

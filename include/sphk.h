@@ -86,9 +86,11 @@ int sphk_iou_pairwise(int kind, const float* rows, int64_t R, const float* cols,
 /* The fused max/argmax of sphk_iou_pairwise as PACKED keys (no matrix, no unpacking), for reductions across
  * shards: key = float32 bits << 32 | (0xFFFFFFFF - index), 0 = "no positive overlap".  The integer maximum of
  * such keys over shards is (max value, lowest index) -- the single-device tie rule.
- *   row_keys [R]: max over the columns (index = col_base + j);  col_keys [C]: max over the rows (row_base + i) */
+ *   row_keys [R]: max over the columns (index = col_base + j);  col_keys [C]: max over the rows (row_base + i)
+ *   keep: bit 0 / bit 1 = do NOT reset the row / column keys first but raise the ones already there (a sweep processed in
+ *         row chunks accumulates the per-column maxima of all chunks in one key array: keep = 2 from the second chunk on) */
 int sphk_iou_pairwise_keys(int kind, const float* rows, int64_t R, const float* cols, int64_t C, int D, int mode, int edge,
-                           uint64_t* row_keys, uint64_t* col_keys, int32_t row_base, int32_t col_base, void* workspace,
+                           uint64_t* row_keys, uint64_t* col_keys, int32_t row_base, int32_t col_base, int keep, void* workspace,
                            void* stream);
 
 /* Row-sharded N x M across GPUs (BASELINE configs[4]; sph_retina_b200/sharded.py): what follows the all-gather of the

@@ -38,7 +38,7 @@ SIGNATURES = {
                                  _c_float_p, ctypes.c_void_p, _c_float_p, ctypes.c_void_p, _i32, _i32,
                                  ctypes.c_void_p, ctypes.c_void_p]),
     "sphk_iou_pairwise_keys": (_int, [_int, _c_float_p, _i64, _c_float_p, _i64, _int, _int, _int, ctypes.c_void_p, ctypes.c_void_p,
-                                      _i32, _i32, ctypes.c_void_p, ctypes.c_void_p]),
+                                      _i32, _i32, _int, ctypes.c_void_p, ctypes.c_void_p]),
     "sphk_iou_pairwise_ties": (_int, [_int, _c_float_p, _i64, _c_float_p, _i64, _int, _int, _int, _c_float_p, ctypes.c_void_p,
                                       _i32, ctypes.c_void_p, ctypes.c_void_p]),
     "sphk_unpack_gathered_keys": (_int, [ctypes.c_void_p, _i32, _i64, _i64, _i64, _c_float_p, ctypes.c_void_p, _c_float_p,
@@ -241,11 +241,12 @@ def iou_pairwise(kind: str, rows, cols, mode="iou", edge="arc", want_matrix=True
 
 
 def iou_pairwise_keys(kind: str, rows, cols, mode="iou", edge="arc", row_base=0, col_base=0, row_keys_out=None,
-                      col_keys_out=None):
+                      col_keys_out=None, keep_row_keys=False, keep_col_keys=False):
     """Fused max/argmax of the N x M overlaps as the kernel's packed keys, without unpacking:
     (row_keys[R], col_keys[C]) int64 = float32 bits << 32 | (0xFFFFFFFF - index); 0 = no positive overlap.
     Integer MAX over shards of such keys = (max value, lowest index): what the multi-GPU sweep reduces.
-    ``row_keys_out`` / ``col_keys_out``: contiguous int64 CUDA tensors to write into (slices of a communication buffer)."""
+    ``row_keys_out`` / ``col_keys_out``: contiguous int64 CUDA tensors to write into (slices of a communication buffer);
+    ``keep_*_keys``: raise the keys already there instead of resetting them first (row-chunked sweeps)."""
     global launches
     rows, cols = _boxes(rows, "bboxes1"), _boxes(cols, "bboxes2")
     R, C, dev = rows.size(0), cols.size(0), rows.device
@@ -257,23 +258,28 @@ def iou_pairwise_keys(kind: str, rows, cols, mode="iou", edge="arc", row_base=0,
     ws = _workspace(dev, 136 * (R + C) + 32)
     with _on_device(dev):
         _check(lib.sphk_iou_pairwise_keys(KIND[kind], _ptr(rows), R, _ptr(cols), C, rows.size(1), MODE[mode], EDGE[edge],
-                                          _ptr(rk), _ptr(ck), row_base, col_base, _ptr(ws), _stream(rows)))
+                                          _ptr(rk), _ptr(ck), row_base, col_base, (1 if keep_row_keys else 0) | (2 if keep_col_keys else 0),
+                                          _ptr(ws), _stream(rows)))
     launches += 2
     return rk, ck
 
 
-def unpack_gathered_keys(gathered, world: int, n_long: int, n_short: int, cap: int):
+def unpack_gathered_keys(gathered, world: int, n_long: int, n_short: int, cap: int, out=None):
     """Row-sharded N x M: (long_max[n_long], long_arg[n_long] int64, short_max[n_short], short_arg[n_short] int64) from
-    the all-gathered key blocks [world, cap + n_short] (include/sphk.h: sphk_unpack_gathered_keys), one launch."""
+    the all-gathered key blocks [world, cap + n_short] (include/sphk.h: sphk_unpack_gathered_keys), one launch.
+    ``out``: optional 4-tuple of preallocated CUDA tensors to write into."""
     global launches
     if not (gathered.is_cuda and gathered.dtype == torch.int64 and gathered.is_contiguous()
             and gathered.numel() == world * (cap + n_short)):
         raise SphkError("gathered must be a contiguous int64 CUDA tensor of world * (cap + n_short) keys")
     dev = gathered.device
-    lmax = torch.empty(n_long, dtype=torch.float32, device=dev)
-    larg = torch.empty(n_long, dtype=torch.int64, device=dev)
-    smax = torch.empty(n_short, dtype=torch.float32, device=dev)
-    sarg = torch.empty(n_short, dtype=torch.int64, device=dev)
+    if out is None:
+        out = (torch.empty(n_long, dtype=torch.float32, device=dev), torch.empty(n_long, dtype=torch.int64, device=dev),
+               torch.empty(n_short, dtype=torch.float32, device=dev), torch.empty(n_short, dtype=torch.int64, device=dev))
+    lmax, larg, smax, sarg = out
+    for t, n, dt in ((lmax, n_long, torch.float32), (larg, n_long, torch.int64), (smax, n_short, torch.float32), (sarg, n_short, torch.int64)):
+        if not (t.is_cuda and t.dtype == dt and t.is_contiguous() and t.numel() == n):
+            raise SphkError("unpack_gathered_keys: output tensors must be contiguous CUDA tensors of the result shapes")
     with _on_device(dev):
         _check(lib.sphk_unpack_gathered_keys(_ptr(gathered), world, n_long, n_short, cap, _ptr(lmax), _ptr(larg), _ptr(smax),
                                              _ptr(sarg), _stream(gathered)))
@@ -282,15 +288,15 @@ def unpack_gathered_keys(gathered, world: int, n_long: int, n_short: int, cap: i
 
 
 def unpack_peer_keys(peer_bufs_dev: int, rank: int, world: int, step: int, block_offset: int, flag_offset: int, n_long: int,
-                     n_short: int, cap: int, device):
+                     n_short: int, cap: int, device, out=None):
     """Row-sharded N x M with the gather fused into the unpack launch (include/sphk.h: sphk_unpack_peer_keys): the keys of
     every shard are read from its owner's symmetric buffer over NVLink.  ``peer_bufs_dev``: device address of the array
-    of the ranks' buffer base pointers (``_SymmetricMemory.buffer_ptrs_dev``)."""
+    of the ranks' buffer base pointers (``_SymmetricMemory.buffer_ptrs_dev``); ``out``: optional preallocated outputs."""
     global launches
-    lmax = torch.empty(n_long, dtype=torch.float32, device=device)
-    larg = torch.empty(n_long, dtype=torch.int64, device=device)
-    smax = torch.empty(n_short, dtype=torch.float32, device=device)
-    sarg = torch.empty(n_short, dtype=torch.int64, device=device)
+    if out is None:
+        out = (torch.empty(n_long, dtype=torch.float32, device=device), torch.empty(n_long, dtype=torch.int64, device=device),
+               torch.empty(n_short, dtype=torch.float32, device=device), torch.empty(n_short, dtype=torch.int64, device=device))
+    lmax, larg, smax, sarg = out
     with _on_device(device):
         _check(lib.sphk_unpack_peer_keys(peer_bufs_dev, rank, world, step, block_offset, flag_offset, n_long, n_short, cap,
                                          _ptr(lmax), _ptr(larg), _ptr(smax), _ptr(sarg), _raw_stream(device.index)))

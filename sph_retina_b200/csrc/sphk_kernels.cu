@@ -1960,13 +1960,15 @@ static int launch_pairwise2(int kind, const float* rows, int64_t R, const float*
                             float4* rec, float4* cull, float* out, int64_t ld, unsigned long long* rkey,
                             unsigned long long* ckey, int32_t row_base, int32_t col_base, const float* row_target,
                             int* col_tie, const int32_t* row_offsets, int64_t col_stride, int batch, int64_t max_rows,
-                            cudaStream_t s, bool zero_keys = false, float* tile_rmax = nullptr, bool records_ready = false) {
+                            cudaStream_t s, bool zero_keys = false, float* tile_rmax = nullptr, bool records_ready = false,
+                            int keep_keys = 0) {
     const int64_t col_tiles = (C + kThreads - 1) / kThreads;
     // long-row calls (sweeps: the long operand is bboxes1): the row records are computed inside k_iou_pairwise2
     const bool rows_inline = !g_no_rows_inline && batch == 1 && row_offsets == nullptr && R >= 4 * C;
     // single-image calls: the key arrays have one entry per box and are zeroed by k_box_pre (zero_keys)
-    unsigned long long* zr = (zero_keys && batch == 1) ? rkey : nullptr;
-    unsigned long long* zc = (zero_keys && batch == 1) ? ckey : nullptr;
+    // (keep_keys bit 0 / 1: the caller accumulates into the row / column keys of an earlier call -- chunked sweeps)
+    unsigned long long* zr = (zero_keys && batch == 1 && !(keep_keys & 1)) ? rkey : nullptr;
+    unsigned long long* zc = (zero_keys && batch == 1 && !(keep_keys & 2)) ? ckey : nullptr;
     if ((g_probe & 1) || records_ready) {      // (records_ready: a second pass over the operands of the previous launch)
     } else if (D == 4) k_box_pre<4><<<blocks_for(R + C), kThreads, 0, s>>>(rows, R, cols, C, edge, rec, cull, aligned16(rows), aligned16(cols), zr, zc, rows_inline);
     else k_box_pre<5><<<blocks_for(R + C), kThreads, 0, s>>>(rows, R, cols, C, edge, rec, cull, false, false, zr, zc, rows_inline);
@@ -2042,7 +2044,7 @@ static int pairwise_impl(int kind, const float* rows, int64_t R, const float* co
                          int angle, float* out, int64_t ld, float* row_max, int32_t* row_arg, float* col_max,
                          int32_t* col_arg, int32_t row_base, int32_t col_base, void* workspace, void* stream,
                          const float* row_target, int* col_tie, unsigned long long* ext_rkey = nullptr,
-                         unsigned long long* ext_ckey = nullptr) {
+                         unsigned long long* ext_ckey = nullptr, int keep_keys = 0) {
     if (R < 0 || C < 0 || (D != 4 && D != 5)) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: bad R, C or D");
     if (kind < 0 || kind > SPHK_KIND_SPH2POB_LEGACY) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: unknown kind");
     if (kind == SPHK_KIND_SPH2POB_LEGACY && D != 4)
@@ -2078,8 +2080,8 @@ static int pairwise_impl(int kind, const float* rows, int64_t R, const float* co
     unsigned long long* rkey = ext_rkey ? ext_rkey : (want_row ? (unsigned long long*)workspace : nullptr);
     unsigned long long* ckey = ext_ckey ? ext_ckey : (want_col ? (unsigned long long*)workspace + R : nullptr);
     const bool pre_zeroes_keys = !approx && R > 0 && C > 0;      // k_box_pre of the same call does it
-    if (want_row && R > 0 && !pre_zeroes_keys) k_fill_keys<<<blocks_for(R), kThreads, 0, s>>>(rkey, R);
-    if (want_col && C > 0 && !pre_zeroes_keys) k_fill_keys<<<blocks_for(C), kThreads, 0, s>>>(ckey, C);
+    if (want_row && R > 0 && !pre_zeroes_keys && !(keep_keys & 1)) k_fill_keys<<<blocks_for(R), kThreads, 0, s>>>(rkey, R);
+    if (want_col && C > 0 && !pre_zeroes_keys && !(keep_keys & 2)) k_fill_keys<<<blocks_for(C), kThreads, 0, s>>>(ckey, C);
     if (R > 0 && C > 0) {
         if (!rows || !cols) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: null box pointer");
         const int64_t col_tiles = (C + kThreads - 1) / kThreads;
@@ -2118,7 +2120,7 @@ static int pairwise_impl(int kind, const float* rows, int64_t R, const float* co
             float4* rec = (float4*)((char*)workspace + keys_bytes(R, C));       // [R + C][4] rows first
             float4* cull = rec + (R + C) * 4;                                    // [R + C][4]
             const int rc = launch_pairwise2(kind, rows, R, cols, C, D, mode, edge, rec, cull, out, ld, rkey, ckey, row_base,
-                                            col_base, row_target, col_tie, nullptr, 0, 1, R, s, true);
+                                            col_base, row_target, col_tie, nullptr, 0, 1, R, s, true, nullptr, false, keep_keys);
             if (rc != SPHK_OK) return rc;
         }
         SPHK_LAUNCH_CHECK("k_iou_pairwise");
@@ -2141,14 +2143,15 @@ int sphk_iou_pairwise(int kind, const float* rows, int64_t R, const float* cols,
 }
 
 int sphk_iou_pairwise_keys(int kind, const float* rows, int64_t R, const float* cols, int64_t C, int D, int mode, int edge,
-                           uint64_t* row_keys, uint64_t* col_keys, int32_t row_base, int32_t col_base, void* workspace,
+                           uint64_t* row_keys, uint64_t* col_keys, int32_t row_base, int32_t col_base, int keep, void* workspace,
                            void* stream) {
     if (kind != SPHK_KIND_SPH2POB_EFFICIENT && kind != SPHK_KIND_SPH2POB_STANDARD)
         return fail(SPHK_ERR_UNSUPPORTED, "sphk_iou_pairwise_keys: kind must be a Sph2Pob transform");
     if (!row_keys || !col_keys) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise_keys: null key pointer");
+    if (keep < 0 || keep > 3) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise_keys: keep must be 0..3");
     return pairwise_impl(kind, rows, R, cols, C, D, mode, edge, SPHK_ANGLE_EQUATOR, nullptr, C, nullptr, nullptr, nullptr, nullptr,
                          row_base, col_base, workspace, stream, nullptr, nullptr, (unsigned long long*)row_keys,
-                         (unsigned long long*)col_keys);
+                         (unsigned long long*)col_keys, keep);
 }
 
 int sphk_iou_pairwise_ties(int kind, const float* rows, int64_t R, const float* cols, int64_t C, int D, int mode, int edge,

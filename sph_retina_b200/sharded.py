@@ -115,11 +115,11 @@ class PeerExchange:
         off = (self.step & 1) * self.per
         return self.buf[off:off + self.per]
 
-    def finish(self):
+    def finish(self, out=None):
         """-> (anchor_max, anchor_arg, gt_max, gt_arg) of the step whose block was handed out last."""
         from . import _native
         return _native.unpack_peer_keys(self.ptrs_dev, self.rank, self.world, self.step, (self.step & 1) * self.per, 2 * self.per,
-                                        self.n_anchors, self.n_gt, self.cap, self.buf.device)
+                                        self.n_anchors, self.n_gt, self.cap, self.buf.device, out=out)
 
 
 _peer_exchanges = {}
@@ -210,3 +210,78 @@ def sharded_max_overlaps(anchors_local, gts, n_anchors, anchor_offset, backend='
     if ex is not None:
         return ex.finish()
     return gather_assignment(block, n_anchors, n_gt, group)
+
+
+class HostSweep:
+    """The sharded sweep for callers whose boxes and results live in HOST memory (pinned): copies and kernels of a step
+    are pipelined over row chunks instead of running one after the other.
+
+        hs = HostSweep(n_anchors, n_local, n_gt, D, device)            # once: staging buffers, a copy stream, events
+        hs(anchors_pinned, gts_pinned, anchor_offset, out_anchor_max, out_anchor_arg, out_gt_max, out_gt_arg)
+
+    Per chunk of the rank's anchors: H2D on the copy stream -> the fused max/argmax kernel on the caller's stream (its
+    per-GT keys accumulate over the chunks: keep_col_keys) -> unpack of the chunk's per-anchor keys (final: every chunk
+    sees all ground truths) -> D2H on the copy stream, under the next chunk's kernel.  Then the per-GT keys are reduced
+    over the ranks (the same 'peer' / 'nccl' routes as sharded_max_overlaps, on 8 B x G per rank) and copied back.
+    Every rank ends up with the per-anchor result of ITS anchors and the global per-GT result -- the data-parallel
+    consumer's view; the all-ranks per-anchor gather of sharded_max_overlaps is not part of it.  All calls are
+    asynchronous: the outputs are valid once the caller's stream has been synchronised (``hs.done`` is recorded last)."""
+
+    def __init__(self, n_anchors, n_local, n_gt, D, device, group=None, min_chunk_rows=65536, max_chunks=8, exchange='auto'):
+        self.n_anchors, self.n_local, self.n_gt, self.D = n_anchors, n_local, n_gt, D
+        self.device, self.group = torch.device(device), group
+        self.world = _world(group)
+        self.chunks = max(1, min(max_chunks, n_local // max(1, min_chunk_rows)))
+        self.bounds = [shard_bounds(n_local, self.chunks, j) for j in range(self.chunks)]
+        dev = self.device
+        self.a_d = torch.empty((n_local, D), dtype=torch.float32, device=dev)
+        self.g_d = torch.empty((n_gt, D), dtype=torch.float32, device=dev)
+        self.akeys = torch.zeros(n_local, dtype=torch.int64, device=dev)
+        self.amax_d = torch.empty(n_local, dtype=torch.float32, device=dev)
+        self.aarg_d = torch.empty(n_local, dtype=torch.int64, device=dev)
+        self.gmax_d = torch.empty(n_gt, dtype=torch.float32, device=dev)
+        self.garg_d = torch.empty(n_gt, dtype=torch.int64, device=dev)
+        self.none_f = torch.empty(0, dtype=torch.float32, device=dev)
+        self.none_i = torch.empty(0, dtype=torch.int64, device=dev)
+        self.copy_stream = torch.cuda.Stream(dev)
+        self.ev_in = [torch.cuda.Event() for _ in range(self.chunks)]
+        self.ev_out = [torch.cuda.Event() for _ in range(self.chunks)]
+        self.done = torch.cuda.Event()
+        # the per-GT keys of this rank: one block [0 anchor slots | n_gt], in symmetric memory where that route is available
+        self.ex = peer_exchange(0, n_gt, dev, group) if (self.world > 1 and exchange in ('auto', 'peer')) else None
+        self.gblock = None if self.ex is not None else torch.zeros(n_gt, dtype=torch.int64, device=dev)
+
+    def __call__(self, anchors_host, gts_host, anchor_offset, out_anchor_max, out_anchor_arg, out_gt_max, out_gt_arg,
+                 backend='sph2pob_efficient_iou', mode='iou'):
+        from . import _native
+        kind = _KINDS[backend]
+        cur, cp = torch.cuda.current_stream(self.device), self.copy_stream
+        cp.wait_stream(cur)                                   # the previous step's consumers of the staging buffers are done
+        with torch.cuda.stream(cp):
+            for j, (lo, hi) in enumerate(self.bounds):
+                self.a_d[lo:hi].copy_(anchors_host[lo:hi], non_blocking=True)
+                self.ev_in[j].record(cp)
+        self.g_d.copy_(gts_host, non_blocking=True)
+        gkeys = self.ex.next_block() if self.ex is not None else self.gblock
+        with torch.no_grad():
+            for j, (lo, hi) in enumerate(self.bounds):
+                cur.wait_event(self.ev_in[j])
+                _native.iou_pairwise_keys(kind, self.a_d[lo:hi], self.g_d, mode, row_base=anchor_offset + lo,
+                                          row_keys_out=self.akeys[lo:hi], col_keys_out=gkeys, keep_col_keys=j > 0)
+                _native.unpack_gathered_keys(self.akeys[lo:hi], 1, hi - lo, 0, hi - lo,
+                                             out=(self.amax_d[lo:hi], self.aarg_d[lo:hi], self.none_f, self.none_i))
+                self.ev_out[j].record(cur)
+                with torch.cuda.stream(cp):
+                    cp.wait_event(self.ev_out[j])
+                    out_anchor_max[lo:hi].copy_(self.amax_d[lo:hi], non_blocking=True)
+                    out_anchor_arg[lo:hi].copy_(self.aarg_d[lo:hi], non_blocking=True)
+        res = (self.none_f, self.none_i, self.gmax_d, self.garg_d)
+        if self.ex is not None:
+            self.ex.finish(out=res)
+        else:
+            _native.unpack_gathered_keys(exchange_blocks(gkeys, self.group).view(-1), self.world, 0, self.n_gt, 0, out=res)
+        out_gt_max.copy_(self.gmax_d, non_blocking=True)
+        out_gt_arg.copy_(self.garg_d, non_blocking=True)
+        cur.wait_stream(cp)                                   # the chunk results are on their way: the step ends when they have landed
+        self.done.record(cur)
+        return out_anchor_max, out_anchor_arg, out_gt_max, out_gt_arg

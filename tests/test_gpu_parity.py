@@ -391,6 +391,30 @@ def test_sharding_emulated_on_one_gpu(api, world):
     assert a_arg.tolist() == [0, 0, 0] and g_arg.tolist() == [1, 0] and g_max.tolist()[1] == 0.0
 
 
+@pytest.mark.parametrize("chunks", [1, 3])
+def test_host_sweep_pipeline_equals_the_device_call(api, chunks):
+    """HostSweep (pinned host in / out, H2D + kernels + D2H pipelined over row chunks, per-GT keys accumulated over the
+    chunks) returns what sharded_max_overlaps returns for device-resident boxes."""
+    from sph_retina_b200.sharded import HostSweep, sharded_max_overlaps
+    n, G = 7001, 300
+    A = O.generate_boxes(n, alpha_range=(1, 100), beta_range=(1, 100), box="rbfov", seed=5)
+    Gt = O.generate_boxes(G, alpha_range=(1, 100), beta_range=(1, 100), box="rbfov", seed=6)
+    A[6000] = A[11] = Gt[7]                                   # a tie across chunks: lowest index wins
+    want = sharded_max_overlaps(A.to(DEV), Gt.to(DEV), n, 0)
+    hs = HostSweep(n, n, G, 5, DEV, min_chunk_rows=n // chunks, max_chunks=chunks)
+    assert hs.chunks == chunks
+    outs = (torch.empty(n).pin_memory(), torch.empty(n, dtype=torch.int64).pin_memory(),
+            torch.empty(G).pin_memory(), torch.empty(G, dtype=torch.int64).pin_memory())
+    for _ in range(2):                                        # the second step re-uses every staging buffer
+        for o in outs:
+            o.fill_(-7)
+        hs(A.pin_memory(), Gt.pin_memory(), 0, *outs)
+        torch.cuda.synchronize()
+        for got, w in zip(outs, want):
+            assert torch.equal(got, w.cpu())
+    assert int(outs[3][7]) == 11
+
+
 def test_config2_slice_vs_c_oracle(api, c_oracle):
     """Assignment orientation (GT rows x anchor cols) on a strided sample of the real 512x1024 anchor grid."""
     g = load_golden("pairwise")
