@@ -710,7 +710,7 @@ def run_ours(args):
         garg_pin = torch.empty(SWEEP_GTS, dtype=torch.int64).pin_memory()
 
         from sph_retina_b200.sharded import HostSweep
-        hs = HostSweep(SWEEP_ANCHORS, n_loc, SWEEP_GTS, 5, dev, exchange=args.exchange)
+        hs = HostSweep(SWEEP_ANCHORS, n_loc, SWEEP_GTS, 5, dev, exchange=args.exchange, **({'max_chunks': args.e2e_chunks, 'min_chunk_rows': 1} if args.e2e_chunks else {}))
 
         def e2e_step():
             # every rank: its shard of the anchors and the GT in pinned host memory -> HostSweep (H2D, kernels and D2H
@@ -823,6 +823,7 @@ def main():
     ap.add_argument("--workload", default="sweep", choices=["sweep", "assign"])
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
                     help="sweep, N > 1: how the ranks' keys are exchanged (sph_retina_b200/sharded.py)")
+    ap.add_argument("--e2e-chunks", type=int, default=0, help="sweep e2e leg: row chunks per rank of the copy / compute pipeline (0 = HostSweep's default)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configs and keep the run short (ncu)")

@@ -231,8 +231,19 @@ class HostSweep:
         self.n_anchors, self.n_local, self.n_gt, self.D = n_anchors, n_local, n_gt, D
         self.device, self.group = torch.device(device), group
         self.world = _world(group)
-        self.chunks = max(1, min(max_chunks, n_local // max(1, min_chunk_rows)))
-        self.bounds = [shard_bounds(n_local, self.chunks, j) for j in range(self.chunks)]
+        # chunk plan: what stays exposed is the H2D of the FIRST chunk and the D2H of the LAST one, while every extra
+        # launch costs one more kernel tail (~15 us): a short first and last chunk (1/8 of the rows, at most 32,768)
+        # around one or two long ones; equal chunks when the caller fixes their number (min_chunk_rows = 1)
+        if min_chunk_rows <= 1:
+            self.chunks = max(1, min(max_chunks, n_local))
+            self.bounds = [shard_bounds(n_local, self.chunks, j) for j in range(self.chunks)]
+        elif n_local < 2 * min_chunk_rows:
+            self.chunks, self.bounds = 1, [(0, n_local)]
+        else:
+            edge = min(32768, n_local // 8)
+            cuts = [0, edge] + ([n_local // 2] if n_local >= 4 * min_chunk_rows else []) + [n_local - edge, n_local]
+            self.bounds = list(zip(cuts[:-1], cuts[1:]))
+            self.chunks = len(self.bounds)
         dev = self.device
         self.a_d = torch.empty((n_local, D), dtype=torch.float32, device=dev)
         self.g_d = torch.empty((n_gt, D), dtype=torch.float32, device=dev)

@@ -401,8 +401,10 @@ def test_host_sweep_pipeline_equals_the_device_call(api, chunks):
     Gt = O.generate_boxes(G, alpha_range=(1, 100), beta_range=(1, 100), box="rbfov", seed=6)
     A[6000] = A[11] = Gt[7]                                   # a tie across chunks: lowest index wins
     want = sharded_max_overlaps(A.to(DEV), Gt.to(DEV), n, 0)
-    hs = HostSweep(n, n, G, 5, DEV, min_chunk_rows=n // chunks, max_chunks=chunks)
+    hs = HostSweep(n, n, G, 5, DEV, min_chunk_rows=1, max_chunks=chunks)
     assert hs.chunks == chunks
+    assert [b for b in HostSweep(1 << 20, 1 << 20, G, 5, DEV).bounds] == [(0, 32768), (32768, 524288), (524288, 1015808), (1015808, 1048576)]
+    assert HostSweep(1 << 20, 1 << 17, G, 5, DEV).bounds == [(0, 16384), (16384, 114688), (114688, 131072)]
     outs = (torch.empty(n).pin_memory(), torch.empty(n, dtype=torch.int64).pin_memory(),
             torch.empty(G).pin_memory(), torch.empty(G, dtype=torch.int64).pin_memory())
     for _ in range(2):                                        # the second step re-uses every staging buffer
