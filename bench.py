@@ -665,6 +665,12 @@ def run_ours(args):
     # throughput are printed next to it; the HBM view -- 8 B of keys per anchor, or 4 B per pair for the matrix -- is
     # in roofline_hbm and says nothing about this kernel)
     kernel_ms = statistics.median(time_steps(torch, kernel_call, 10, 3, flush, lambda: None))
+    kernel_ms_ranks = [kernel_ms]
+    if world > 1:       # the step ends when the slowest rank's kernel does: how far apart are they?
+        t = torch.zeros(world, dtype=torch.float64, device=dev)
+        t[rank] = kernel_ms
+        dist.all_reduce(t)
+        kernel_ms_ranks = [float(x) for x in t.tolist()]
     if rank == 0:
         peak_tf = fp32_peak(torch, native, dev)
         tf = pairs_per_kernel * FLOP_PER_PAIR / (kernel_ms * 1e-3) / 1e12
@@ -677,6 +683,7 @@ def run_ours(args):
         result["roofline"] = {
             "bound": "fp32", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
             "traffic": prof.get("dram_bytes_per_launch"), "kernel": kernel_name, "kernel_ms": kernel_ms,
+            "kernel_ms_per_rank": kernel_ms_ranks,
             "kernels_per_step": kernels_per_step, "kernel_share_of_step": kernel_ms * kernels_per_step / statistics.mean(ms),
             "flop_per_pair": FLOP_PER_PAIR, "pairs_per_launch": pairs_per_kernel,
             "peak_source": "FMA-chain probe (sphk_probe_fp32) on this GPU in this run; nominal 148 SM x 128 lanes x 2 x %.0f MHz = %.1f"
