@@ -46,6 +46,43 @@ for k in kernels:
         hot = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_hotspots.py"), rep,
                               os.path.join(ROOT, "sph_retina_b200", "_lib", "libsphk.so"), kern, "--top", "45"], capture_output=True, text=True).stdout
         open(os.path.join(dst, "ncu_%s_%s_hotspots.txt" % (k, tag)), "w").write(hot)
+# roofline_ncu.json: what bench.py's roofline object quotes from the committed capture of the dominant kernel
+rpath = os.path.join(dst, "roofline_ncu.json")
+roof = json.load(open(rpath)) if os.path.isfile(rpath) else {}
+for k in ("sweep", "assign", "aligned"):
+    spath = os.path.join(dst, "ncu_%s_%s_summary.txt" % (k, tag))
+    if not os.path.isfile(spath) or k not in traffic:
+        continue
+    vals = {}
+    for line in open(spath):
+        parts = line.split()
+        if len(parts) >= 2 and ("__" in parts[0]):
+            try:
+                vals[parts[0]] = float(parts[1].replace(",", ""))
+                if parts[0] == "gpu__time_duration.sum" and len(parts) > 2:
+                    vals[parts[0]] *= {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(parts[2], 1.0)      # -> microseconds
+            except ValueError:
+                pass
+    el, act = vals.get("sm__cycles_elapsed.max"), vals.get("sm__cycles_active.avg")
+    roof[k] = {
+        "dram_bytes_per_launch": traffic[k],
+        "counters": {
+            "issue_active_pct_of_active_cycles": vals.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+            "sm_active_frac_of_elapsed": (act / el) if el and act else None,
+            "pipe_fma_pct": vals.get("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+            "pipe_alu_pct": vals.get("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active"),
+            "pipe_xu_pct": vals.get("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"),
+            "pipe_lsu_pct": vals.get("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"),
+            "warps_active_pct": vals.get("sm__warps_active.avg.pct_of_peak_sustained_active"),
+            "warp_instructions": vals.get("smsp__inst_executed.sum"),
+            "threads_per_instruction": vals.get("smsp__thread_inst_executed_per_inst_executed.ratio"),
+            "registers_per_thread": vals.get("launch__registers_per_thread"),
+            "kernel_us_under_ncu": vals.get("gpu__time_duration.sum"),
+            "shared_bank_conflicts": vals.get("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"),
+        },
+        "source": "profiles/ncu_%s_%s_summary.txt (ncu --set full --clock-control none, one launch)" % (k, tag),
+    }
+json.dump(roof, open(rpath, "w"), indent=1)
 traffic["source"] = ("ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, one launch "
                      "(profiles/ncu_*_%s_details.csv)" % tag)
 json.dump(traffic, open(os.path.join(dst, "traffic.json"), "w"), indent=1)
