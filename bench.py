@@ -769,10 +769,13 @@ def run_ours(args):
     if args.workload == "sweep":
         from sph_retina_b200.sharded import exchange_route
         exchange_route_name = exchange_route()
-        if exchange_route_name == "peer" and args.exchange == "nccl":
-            exchange_route_name = "nccl"
-        exchange_route_name = {"peer": "peer: keys read from the owners' symmetric buffers over NVLink inside the unpack launch "
-                                       "(sphk_unpack_peer_keys), no collective", "nccl": "nccl: one all_gather_into_tensor + unpack launch",
+        if exchange_route_name == "peer" and args.exchange in ("nccl", "peer-pull"):
+            exchange_route_name = args.exchange
+        exchange_route_name = {"peer": "peer: the compute kernel stores its anchors' keys into the peers' symmetric buffers over NVLink "
+                                       "while it runs (sphk_iou_pairwise_keys_push); flag handshake + local unpack in one launch "
+                                       "(sphk_unpack_peer_keys); no collective",
+                               "peer-pull": "peer-pull: keys read from the owners' symmetric buffers over NVLink inside the unpack launch "
+                                            "(sphk_unpack_peer_keys), no collective", "nccl": "nccl: one all_gather_into_tensor + unpack launch",
                                "single": "single GPU: the unpack launch reads the local block"}[exchange_route_name]
     if rank == 0:
         line = {
@@ -828,7 +831,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="sweep", choices=["sweep", "assign"])
-    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "peer-pull", "nccl"],
                     help="sweep, N > 1: how the ranks' keys are exchanged (sph_retina_b200/sharded.py)")
     ap.add_argument("--e2e-chunks", type=int, default=0, help="sweep e2e leg: row chunks per rank of the copy / compute pipeline (0 = HostSweep's default)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SPHK_ABI_VERSION 6
+#define SPHK_ABI_VERSION 7
 
 enum sphk_status {
     SPHK_OK = 0,
@@ -106,19 +106,39 @@ int sphk_iou_pairwise_keys(int kind, const float* rows, int64_t R, const float* 
 int sphk_unpack_gathered_keys(const uint64_t* gathered, int32_t world, int64_t n_long, int64_t n_short, int64_t cap,
                               float* long_max, int64_t* long_arg, float* short_max, int64_t* short_arg, void* stream);
 
-/* The same unpacking with the gather FUSED into the launch: no NCCL collective, the keys are read from the owners' buffers
- * by peer loads over NVLink.  Every rank owns a symmetric buffer of identical layout (uint64 elements)
- *     [ block of parity 0 : cap + n_short | block of parity 1 : cap + n_short | flags : >= world ]
- * mapped into all processes of the node (torch.distributed._symmetric_memory); peer_bufs is a DEVICE array of the
- * `world` base pointers (the handle's buffer_ptrs_dev).  The rank's compute kernel of step s writes the block at
- * block_offset (= parity (s & 1) times (cap + n_short)); this launch, enqueued after it on the same stream, raises
- * flags[rank] = s in every peer's buffer, waits until all flags of the local buffer have reached s, then reads every
- * shard's keys from its owner and writes the same outputs as sphk_unpack_gathered_keys.  `step` counts from 1 and must
- * advance by one per call on every rank; the flags must be zero before the first step.  A peer that does not arrive
- * within ~5 s makes the kernel trap (the job fails instead of hanging). */
+/* The sharded sweep WITHOUT a collective: the exchange is fused into the compute launch (stores into the peers' buffers
+ * over NVLink while the launch runs) and into the unpack launch (flag handshake + reads).  Every rank owns a symmetric
+ * buffer of identical layout (uint64 elements), mapped into all processes of the node
+ * (torch.distributed._symmetric_memory):
+ *     [ parity 0: world slots | parity 1: world slots | flags : >= world ]
+ *     slot s = the block of rank s = [ `parts` arrays of cap keys of its rows | its n_short keys of the short operand ]
+ * peer_bufs is a DEVICE array of the `world` base pointers (the handle's buffer_ptrs_dev).
+ *
+ * sphk_iou_pairwise_keys_push: the fused max / argmax sweep of sphk_iou_pairwise_keys for rows = the rank's shard of the
+ * long operand.  The column keys go to col_keys (the short-operand part of the rank's own slot) as before; the row keys
+ * are NOT merged over the column tiles: every CTA stores the 32 keys of its (row tile, column tile) as partial array
+ * t = column tile (0 <= t < sphk_key_push_parts(C) = ceil(C / 256)) at element push_offset + t * part_stride + i of the
+ * buffer of EVERY rank, its own included (plain 8-byte stores while the launch runs; part_stride >= R, normally cap).
+ * The maximum over the partial arrays is the row key.  Needs no zero-fill: every partial entry of rows [0, R) is written.
+ * Replaces: nothing in the reference (it is single-device on this path); the contract reproduced is the
+ * single-device overlaps.max(dim=0/1) of mmdet/core/bbox/assigners/max_iou_assigner.py:173-176. */
+int32_t sphk_key_push_parts(int64_t C);
+int sphk_iou_pairwise_keys_push(int kind, const float* rows, int64_t R, const float* cols, int64_t C, int D, int mode, int edge,
+                                uint64_t* col_keys, int32_t row_base, int32_t col_base, uint64_t* const* peer_bufs, int32_t world,
+                                int64_t push_offset, int64_t part_stride, void* workspace, void* stream);
+
+/* The exchange step after the rank's compute kernel of step s (same stream): raises flags[rank] = s in every peer's
+ * buffer, waits until all flags of the local buffer have reached s, then writes the same outputs as
+ * sphk_unpack_gathered_keys.  block_offset = the step's parity (s & 1) times world * (long_parts * cap + n_short).
+ * long_pushed != 0: the long operand's keys are the maximum over the long_parts partial arrays of the LOCAL slots (filled
+ * by every rank's sphk_iou_pairwise_keys_push); long_pushed == 0 (long_parts = 1): they are read from slot s of rank s's
+ * buffer by peer loads (filled by sphk_iou_pairwise_keys).  The short operand's keys (final only when the owner's kernel
+ * has ended) always come from their owners' slots.  `step` counts from 1 and must advance by one per call on every rank;
+ * the flags must be zero before the first step.  A peer that does not arrive within ~5 s makes the kernel trap (the job
+ * fails instead of hanging). */
 int sphk_unpack_peer_keys(const uint64_t* const* peer_bufs, int32_t rank, int32_t world, uint64_t step, int64_t block_offset,
-                          int64_t flag_offset, int64_t n_long, int64_t n_short, int64_t cap, float* long_max, int64_t* long_arg,
-                          float* short_max, int64_t* short_arg, void* stream);
+                          int64_t flag_offset, int64_t n_long, int64_t n_short, int64_t cap, int32_t long_parts, int32_t long_pushed,
+                          float* long_max, int64_t* long_arg, float* short_max, int64_t* short_arg, void* stream);
 
 /* Second pass of MaxIoUAssigner's low-quality matching with gt_max_assign_all=True
  * (mmdet/core/bbox/assigners/max_iou_assigner.py:201-205: for each GT i in ascending order,

@@ -20,7 +20,7 @@ EDGE = {"arc": 0, "chord": 1, "tangent": 2}
 ANGLE = {"equator": 0, "project": 1}
 
 SPHK_OK = 0
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 _c_float_p = ctypes.c_void_p  # raw device addresses
 _i64 = ctypes.c_int64
@@ -43,8 +43,11 @@ SIGNATURES = {
                                       _i32, ctypes.c_void_p, ctypes.c_void_p]),
     "sphk_unpack_gathered_keys": (_int, [ctypes.c_void_p, _i32, _i64, _i64, _i64, _c_float_p, ctypes.c_void_p, _c_float_p,
                                          ctypes.c_void_p, ctypes.c_void_p]),
-    "sphk_unpack_peer_keys": (_int, [ctypes.c_void_p, _i32, _i32, ctypes.c_uint64, _i64, _i64, _i64, _i64, _i64, _c_float_p, ctypes.c_void_p,
-                                     _c_float_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "sphk_key_push_parts": (_i32, [_i64]),
+    "sphk_iou_pairwise_keys_push": (_int, [_int, _c_float_p, _i64, _c_float_p, _i64, _int, _int, _int, ctypes.c_void_p, _i32, _i32,
+                                           ctypes.c_void_p, _i32, _i64, _i64, ctypes.c_void_p, ctypes.c_void_p]),
+    "sphk_unpack_peer_keys": (_int, [ctypes.c_void_p, _i32, _i32, ctypes.c_uint64, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _c_float_p,
+                                     ctypes.c_void_p, _c_float_p, ctypes.c_void_p, ctypes.c_void_p]),
     "sphk_max_iou_assign_workspace_bytes": (_i64, [_i64, _i64, _i32]),
     "sphk_max_iou_assign": (_int, [_int, _c_float_p, ctypes.POINTER(_i32), _i32, _c_float_p, _i64, _int, ctypes.c_float,
                                    ctypes.c_float, ctypes.c_float, ctypes.c_float, _int, _int, ctypes.c_void_p, ctypes.c_void_p,
@@ -264,6 +267,32 @@ def iou_pairwise_keys(kind: str, rows, cols, mode="iou", edge="arc", row_base=0,
     return rk, ck
 
 
+def key_push_parts(C: int) -> int:
+    """Partial arrays per row key that iou_pairwise_keys_push writes: one per column tile of the compute kernel."""
+    return int(lib.sphk_key_push_parts(C))
+
+
+def iou_pairwise_keys_push(kind: str, rows, cols, col_keys_out, peer_bufs_dev: int, world: int, push_offset: int, part_stride: int,
+                           mode="iou", edge="arc", row_base=0, col_base=0):
+    """The fused max / argmax sweep with the row keys stored into EVERY rank's symmetric buffer from inside the launch
+    (include/sphk.h: sphk_iou_pairwise_keys_push): partial array t (one per column tile, key_push_parts(C) of them) at
+    element ``push_offset + t * part_stride`` of each buffer; the column keys go to ``col_keys_out``.
+    ``peer_bufs_dev``: device address of the array of the ranks' buffer base pointers."""
+    global launches
+    rows, cols = _boxes(rows, "bboxes1"), _boxes(cols, "bboxes2")
+    R, C, dev = rows.size(0), cols.size(0), rows.device
+    k = col_keys_out
+    if not (k.is_cuda and k.dtype == torch.int64 and k.is_contiguous() and k.numel() == C and k.device == dev):
+        raise SphkError("col_keys_out must be a contiguous int64 CUDA tensor of %d elements on %s" % (C, dev))
+    ws = _workspace(dev, 136 * (R + C) + 32)
+    with _on_device(dev):
+        _check(lib.sphk_iou_pairwise_keys_push(KIND[kind], _ptr(rows), R, _ptr(cols), C, rows.size(1), MODE[mode], EDGE[edge],
+                                               _ptr(k), row_base, col_base, peer_bufs_dev, world, push_offset, part_stride,
+                                               _ptr(ws), _stream(rows)))
+    launches += 2
+    return k
+
+
 def unpack_gathered_keys(gathered, world: int, n_long: int, n_short: int, cap: int, out=None):
     """Row-sharded N x M: (long_max[n_long], long_arg[n_long] int64, short_max[n_short], short_arg[n_short] int64) from
     the all-gathered key blocks [world, cap + n_short] (include/sphk.h: sphk_unpack_gathered_keys), one launch.
@@ -288,10 +317,12 @@ def unpack_gathered_keys(gathered, world: int, n_long: int, n_short: int, cap: i
 
 
 def unpack_peer_keys(peer_bufs_dev: int, rank: int, world: int, step: int, block_offset: int, flag_offset: int, n_long: int,
-                     n_short: int, cap: int, device, out=None):
-    """Row-sharded N x M with the gather fused into the unpack launch (include/sphk.h: sphk_unpack_peer_keys): the keys of
-    every shard are read from its owner's symmetric buffer over NVLink.  ``peer_bufs_dev``: device address of the array
-    of the ranks' buffer base pointers (``_SymmetricMemory.buffer_ptrs_dev``); ``out``: optional preallocated outputs."""
+                     n_short: int, cap: int, device, out=None, long_parts=1, long_pushed=False):
+    """The exchange step of the row-sharded N x M without a collective (include/sphk.h: sphk_unpack_peer_keys): flag
+    handshake over the ranks' symmetric buffers, then the keys of the long operand from the local slots (``long_pushed``:
+    every rank's compute kernel stored ``long_parts`` partial arrays there) or from their owners' buffers over NVLink, the
+    short operand's from their owners.  ``peer_bufs_dev``: device address of the array of the ranks' buffer base pointers
+    (``_SymmetricMemory.buffer_ptrs_dev``); ``out``: optional preallocated outputs."""
     global launches
     if out is None:
         out = (torch.empty(n_long, dtype=torch.float32, device=device), torch.empty(n_long, dtype=torch.int64, device=device),
@@ -299,7 +330,8 @@ def unpack_peer_keys(peer_bufs_dev: int, rank: int, world: int, step: int, block
     lmax, larg, smax, sarg = out
     with _on_device(device):
         _check(lib.sphk_unpack_peer_keys(peer_bufs_dev, rank, world, step, block_offset, flag_offset, n_long, n_short, cap,
-                                         _ptr(lmax), _ptr(larg), _ptr(smax), _ptr(sarg), _raw_stream(device.index)))
+                                         long_parts, 1 if long_pushed else 0, _ptr(lmax), _ptr(larg), _ptr(smax), _ptr(sarg),
+                                         _raw_stream(device.index)))
     launches += 1
     return lmax, larg, smax, sarg
 

@@ -449,6 +449,7 @@ struct PairTile {
     unsigned short ring[kThreads / 32][2][kRing];
     float rtgt[TR];      // tie pass: the row maxima to compare with
     int ctie[kTC];       // tie pass: per column, the largest (row index + 1) that ties its row maximum
+    unsigned long long* peer[16];   // push route: the ranks' buffers (fetched during phase 0, used in the epilogue)
 };
 
 __device__ __forceinline__ void put_rec(float* base, int i, const BoxRec& b) {
@@ -570,6 +571,19 @@ __device__ unsigned long long g_tl[16384 * 2];
 __device__ unsigned g_tl_sm[16384];
 #endif
 
+// Sharded sweeps (sph_retina_b200/sharded.py, route 'peer'): the row keys leave for the peers from inside the compute
+// kernel.  Instead of merging the column tiles' maxima of a row into one global key (atomicMax), every CTA stores the 32
+// keys of ITS tile -- the maximum over its 256 columns, global argmax index included -- as one of ceil(C / 256) partial
+// arrays, into the buffer of EVERY rank (its own included): plain 8-byte stores, one per thread for up to 8 ranks, over
+// NVLink for the peers, fire-and-forget.  No atomics, no zero-fill, no arrival counting, no fence: the transfer runs
+// under the rest of the launch, and the exchange step that follows takes the maximum over the partials from local memory.
+struct KeyPush {
+    unsigned long long* const* bufs;   // device array of the ranks' buffer base pointers; nullptr: nothing is pushed
+    long long off;                     // element offset, in EVERY rank's buffer, of partial array 0 of this rank's rows
+    long long part_stride;             // elements between the partial arrays of successive column tiles
+    int world;
+};
+
 template <int D, int TR, bool BOX>
 __global__ void __launch_bounds__(kThreads, 4)      // 4 CTAs per SM (64 registers): 3 cost 22 % of the throughput
 k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restrict__ cols, int64_t C,
@@ -577,7 +591,7 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
                 float* __restrict__ out, int64_t ld, unsigned long long* __restrict__ row_key,
                 unsigned long long* __restrict__ col_key, uint32_t row_base, uint32_t col_base, int flags,
                 const float* __restrict__ row_target, int* __restrict__ col_tie,
-                const int32_t* __restrict__ row_offsets, int64_t col_stride, float* __restrict__ tile_rmax) {
+                const int32_t* __restrict__ row_offsets, int64_t col_stride, float* __restrict__ tile_rmax, const KeyPush push) {
     __shared__ __align__(16) PairTile<TR> T;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool dense = (flags & 1) != 0;                               // sphk_set_dense (measurement)
@@ -603,7 +617,7 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
     }
     PairOut o;
     o.out = out; o.ld = ld; o.r0 = r_begin + (int64_t)rt * TR; o.c0 = (int64_t)ct * kTC;
-    o.want_row = row_key != nullptr; o.want_col = col_key != nullptr; o.tie = col_tie != nullptr;
+    o.want_row = row_key != nullptr || push.bufs != nullptr; o.want_col = col_key != nullptr; o.tie = col_tie != nullptr;
     o.row_base = row_base; o.col_base = col_base;
     const int nr = (int)min((int64_t)TR, r_end - o.r0);
     const bool col_ok = o.c0 + tid < C;
@@ -620,8 +634,10 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
         }
     }
     // Programmatic dependent launch: everything above overlaps the tail of k_box_pre; its records are
-    // needed from here on.
+    // needed from here on.  A dependent of THIS launch (the exchange step of the sharded sweep) may take the slots the
+    // last CTAs free; it waits for the completion of this grid itself before it touches anything.
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (o.tie && tile_rmax) {
         // Tie pass of the assigner: an entry can equal its row's maximum only inside a tile whose own maximum of that
         // row IS the maximum.  The max / argmax pass left every tile's row maxima in tile_rmax[column tile][row]: all
@@ -663,6 +679,7 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
         T.rtgt[tid] = (o.tie && ok) ? __ldg(row_target + o.r0 + tid) : -1.0f;
     }
     T.ctie[tid] = 0;
+    if (push.bufs && tid >= kThreads - 16 && tid - (kThreads - 16) < push.world) T.peer[tid - (kThreads - 16)] = push.bufs[tid - (kThreads - 16)];
     __syncthreads();
     // ---- phase 1: prefilter + compaction.  This thread's column is tid (= warp * 32 + lane).
     // Out-of-range columns and the dense (measurement) mode are folded into the bias term of the test.
@@ -731,7 +748,14 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
     if (o.want_row || o.want_col || o.tie) {
         __syncthreads();
         if (o.tie && col_ok && T.ctie[tid] > 0) atomicMax(&col_tie[o.c0 + tid], T.ctie[tid]);
-        if (o.want_row && tid < nr) {
+        if (push.bufs) {
+            // this tile's row keys as partial array `ct`, into every rank's buffer (thread -> (rank, row))
+            const long long at = push.off + (long long)ct * push.part_stride + o.r0;
+            for (int j = tid; j < TR * push.world; j += kThreads) {
+                const int d = j / TR, i = j % TR;
+                if (i < nr) T.peer[d][at + i] = T.rkey[i];
+            }
+        } else if (o.want_row && tid < nr) {
             const unsigned long long key = T.rkey[tid];
             if (key != 0ull && key > row_key[o.r0 + tid]) atomicMax(&row_key[o.r0 + tid], key);
             if (tile_rmax) tile_rmax[(int64_t)ct * R + o.r0 + tid] = __uint_as_float((uint32_t)(key >> 32));
@@ -1022,20 +1046,27 @@ k_unpack_gathered(const unsigned long long* __restrict__ gathered, int world, in
     }
 }
 
-// ---- the same, with the gather fused into the launch: peer loads over NVLink instead of an NCCL all-gather -----------
-// Every rank keeps its key blocks in a SYMMETRIC buffer (same layout on every GPU of the node, mapped into every
-// process: torch.distributed._symmetric_memory): [parity 0 block | parity 1 block | flags[world]].  A step is
-//   compute kernel (writes this rank's block of the step's parity)  ->  this kernel:
-//     1. block 0 tells every peer "my block of step s is complete" (a release store of s into flags[rank] of the peer's
-//        buffer: the compute kernel precedes this launch in the stream, so its writes are visible before the flag is);
+// ---- the same, with the gather fused into the compute and unpack launches: peer stores / loads over NVLink, no NCCL ------
+// Every rank keeps the key blocks of ALL ranks in a SYMMETRIC buffer (same layout on every GPU of the node, mapped into
+// every process: torch.distributed._symmetric_memory):
+//     [ parity 0: world slots | parity 1: world slots | flags[world] ],   slot s = the block of rank s =
+//     [ `parts` arrays of cap anchor keys | n_short ground-truth keys ]
+// A step is
+//   compute kernel of rank r:  'push' (sphk_iou_pairwise_keys_push, parts = column tiles): every CTA stores the keys of its
+//       tile into slot r of EVERY rank's buffer while the launch is still running (KeyPush in k_iou_pairwise2);
+//       'pull' (sphk_iou_pairwise_keys into slot r of the rank's OWN buffer, parts = 1): nothing leaves the GPU yet;
+//   ->  this kernel:
+//     1. block 0 tells every peer "my step s is complete" (a release store of s into flags[rank] of the peer's buffer:
+//        the compute kernel precedes this launch in the stream, so its local and remote writes are visible before the
+//        flag is);
 //     2. every CTA waits until the flags of all peers in the LOCAL buffer have reached s (acquire loads);
-//     3. the keys of the whole anchor set are read straight from the owners' buffers (coalesced 8-byte peer loads,
-//        7/8 of them over NVLink) and unpacked exactly as k_unpack_gathered does.
-// No collective kernel, no staging copy, no second launch: what is exposed after the compute kernel is the skew between
-// the ranks plus ~10 us of peer reads.  The blocks alternate between two parities: a rank that runs ahead by one step
-// writes the other parity, and it cannot run ahead by two (its step s + 1 waits for every peer's flag s + 1, which a
-// peer raises only after its own step-s reads).  A rank that never shows up would leave the others spinning: after
-// ~5 s the kernel traps, so a broken job fails instead of hanging the GPUs.
+//     3. the anchors' keys are read from the local slots (push: maximum over the partial arrays) or straight from their
+//        owners' buffers (pull: coalesced 8-byte peer loads), the ground truths' keys (8 B x n_short per rank, final only
+//        when the owner's kernel has ended) from the owners' slots, and everything is unpacked as k_unpack_gathered does.
+// No collective kernel, no staging copy, no second launch.  The parities alternate: a rank that runs ahead by one step
+// writes (and pushes into) the other parity, and it cannot run ahead by two (its step s + 1 waits for every peer's flag
+// s + 1, which a peer raises only after its own step-s reads).  A rank that never shows up would leave the others
+// spinning: after ~5 s the kernel traps, so a broken job fails instead of hanging the GPUs.
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
     unsigned long long v;
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -1047,13 +1078,17 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
 
 __global__ void __launch_bounds__(kThreads)
 k_unpack_peers(unsigned long long* const* __restrict__ peer_bufs, int rank, int world, unsigned long long step,
-               int64_t block_offset, int64_t flag_offset, int64_t n_long, int64_t n_short, int64_t cap,
+               int64_t block_offset, int64_t flag_offset, int64_t n_long, int64_t n_short, int64_t cap, int parts, bool long_pushed,
                float* __restrict__ long_max, int64_t* __restrict__ long_arg, float* __restrict__ short_max,
                int64_t* __restrict__ short_arg) {
-    __shared__ const unsigned long long* s_blk[16];
+    __shared__ const unsigned long long* s_blk[16];     // slot s in the buffer of rank s
+    const int64_t stride = parts * cap + n_short;
+    // launched with programmatic stream serialization: the CTAs may be resident while the compute kernel drains; nothing
+    // of this step is read, written or signalled before that kernel and its memory operations are complete
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (threadIdx.x < world) {
         unsigned long long* const peer = peer_bufs[threadIdx.x];
-        s_blk[threadIdx.x] = peer + block_offset;
+        s_blk[threadIdx.x] = peer + block_offset + threadIdx.x * stride;
         if (blockIdx.x == 0) {
             __threadfence_system();
             st_release_sys(peer + flag_offset + rank, step);
@@ -1072,24 +1107,33 @@ k_unpack_peers(unsigned long long* const* __restrict__ peer_bufs, int rank, int 
         }
     }
     __syncthreads();
-    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    unsigned long long k = 0ull;
-    if (i < n_long) {
-        const int64_t base = n_long / world, extra = n_long % world;
-        const int64_t cut = extra * (base + 1);
-        const int64_t s = (i < cut) ? i / (base + 1) : extra + (i - cut) / (base > 0 ? base : 1);
-        const int64_t lo = s * base + (s < extra ? s : extra);
-        k = __ldcg(s_blk[s] + (i - lo));
-        long_max[i] = (k == 0ull) ? 0.0f : __uint_as_float((uint32_t)(k >> 32));
-        long_arg[i] = (k == 0ull) ? 0 : (int64_t)(0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull));
-    } else if (i < n_long + n_short) {
-        const int64_t j = i - n_long;
-        for (int s = 0; s < world; ++s) {
-            const unsigned long long v = __ldcg(s_blk[s] + cap + j);
-            k = v > k ? v : k;
+    // bounded grid (the flags are polled once per CTA, not once per 256 keys), grid-stride over the keys
+    const int64_t base = n_long / world, extra = n_long % world;
+    const int64_t cut = extra * (base + 1);
+    const unsigned long long* const local = peer_bufs[rank] + block_offset;
+#pragma unroll 4
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n_long + n_short; i += (int64_t)gridDim.x * kThreads) {
+        unsigned long long k = 0ull;
+        if (i < n_long) {
+            const int64_t s = (i < cut) ? i / (base + 1) : extra + (i - cut) / (base > 0 ? base : 1);
+            const int64_t lo = s * base + (s < extra ? s : extra);
+            const unsigned long long* src = (long_pushed ? local + s * stride : s_blk[s]) + (i - lo);
+            k = __ldcg(src);
+            for (int t = 1; t < parts; ++t) {                       // push: one partial array per column tile of the compute kernel
+                const unsigned long long v = __ldcg(src + t * cap);
+                k = v > k ? v : k;
+            }
+            long_max[i] = (k == 0ull) ? 0.0f : __uint_as_float((uint32_t)(k >> 32));
+            long_arg[i] = (k == 0ull) ? 0 : (int64_t)(0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull));
+        } else {
+            const int64_t j = i - n_long;
+            for (int s = 0; s < world; ++s) {
+                const unsigned long long v = __ldcg(s_blk[s] + parts * cap + j);
+                k = v > k ? v : k;
+            }
+            short_max[j] = (k == 0ull) ? 0.0f : __uint_as_float((uint32_t)(k >> 32));
+            short_arg[j] = (k == 0ull) ? 0 : (int64_t)(0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull));
         }
-        short_max[j] = (k == 0ull) ? 0.0f : __uint_as_float((uint32_t)(k >> 32));
-        short_arg[j] = (k == 0ull) ? 0 : (int64_t)(0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull));
     }
 }
 
@@ -1961,7 +2005,7 @@ static int launch_pairwise2(int kind, const float* rows, int64_t R, const float*
                             unsigned long long* ckey, int32_t row_base, int32_t col_base, const float* row_target,
                             int* col_tie, const int32_t* row_offsets, int64_t col_stride, int batch, int64_t max_rows,
                             cudaStream_t s, bool zero_keys = false, float* tile_rmax = nullptr, bool records_ready = false,
-                            int keep_keys = 0) {
+                            int keep_keys = 0, const KeyPush* push = nullptr) {
     const int64_t col_tiles = (C + kThreads - 1) / kThreads;
     // long-row calls (sweeps: the long operand is bboxes1): the row records are computed inside k_iou_pairwise2
     const bool rows_inline = !g_no_rows_inline && batch == 1 && row_offsets == nullptr && R >= 4 * C;
@@ -1997,10 +2041,11 @@ static int launch_pairwise2(int kind, const float* rows, int64_t R, const float*
     const int dn = (g_dense != 0 ? 1 : 0) | (rows_inline ? 4 : 0);
     // which instance: with the box-frame prefilter test (rows = the short, large-box operand: ground truths x anchors) or without
     const bool box = !g_no_boxcull && box_test_pays(max_rows, C);
+    const KeyPush kp = push ? *push : KeyPush{nullptr, 0, 0, 1};
     cudaError_t le;
 #define SPHK_PW2(DD, TR, BX)                                                                                               \
     le = cudaLaunchKernelEx(&cfg, k_iou_pairwise2<DD, TR, BX>, rows, R, cols, C, crec, ccull, kind, mode, edge, out, ld, rkey, \
-                            ckey, (uint32_t)row_base, (uint32_t)col_base, dn, row_target, col_tie, row_offsets, col_stride, tile_rmax)
+                            ckey, (uint32_t)row_base, (uint32_t)col_base, dn, row_target, col_tie, row_offsets, col_stride, tile_rmax, kp)
     if (box) {
         if (D == 4 && tr == 32) SPHK_PW2(4, 32, true);
         else if (D == 4) SPHK_PW2(4, 8, true);
@@ -2044,7 +2089,7 @@ static int pairwise_impl(int kind, const float* rows, int64_t R, const float* co
                          int angle, float* out, int64_t ld, float* row_max, int32_t* row_arg, float* col_max,
                          int32_t* col_arg, int32_t row_base, int32_t col_base, void* workspace, void* stream,
                          const float* row_target, int* col_tie, unsigned long long* ext_rkey = nullptr,
-                         unsigned long long* ext_ckey = nullptr, int keep_keys = 0) {
+                         unsigned long long* ext_ckey = nullptr, int keep_keys = 0, const KeyPush* push = nullptr) {
     if (R < 0 || C < 0 || (D != 4 && D != 5)) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: bad R, C or D");
     if (kind < 0 || kind > SPHK_KIND_SPH2POB_LEGACY) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise: unknown kind");
     if (kind == SPHK_KIND_SPH2POB_LEGACY && D != 4)
@@ -2120,7 +2165,7 @@ static int pairwise_impl(int kind, const float* rows, int64_t R, const float* co
             float4* rec = (float4*)((char*)workspace + keys_bytes(R, C));       // [R + C][4] rows first
             float4* cull = rec + (R + C) * 4;                                    // [R + C][4]
             const int rc = launch_pairwise2(kind, rows, R, cols, C, D, mode, edge, rec, cull, out, ld, rkey, ckey, row_base,
-                                            col_base, row_target, col_tie, nullptr, 0, 1, R, s, true, nullptr, false, keep_keys);
+                                            col_base, row_target, col_tie, nullptr, 0, 1, R, s, true, nullptr, false, keep_keys, push);
             if (rc != SPHK_OK) return rc;
         }
         SPHK_LAUNCH_CHECK("k_iou_pairwise");
@@ -2154,6 +2199,22 @@ int sphk_iou_pairwise_keys(int kind, const float* rows, int64_t R, const float* 
                          (unsigned long long*)col_keys, keep);
 }
 
+int32_t sphk_key_push_parts(int64_t C) { return C <= 0 ? 1 : (int32_t)((C + kThreads - 1) / kThreads); }
+
+int sphk_iou_pairwise_keys_push(int kind, const float* rows, int64_t R, const float* cols, int64_t C, int D, int mode, int edge,
+                                uint64_t* col_keys, int32_t row_base, int32_t col_base, uint64_t* const* peer_bufs, int32_t world,
+                                int64_t push_offset, int64_t part_stride, void* workspace, void* stream) {
+    if (kind != SPHK_KIND_SPH2POB_EFFICIENT && kind != SPHK_KIND_SPH2POB_STANDARD)
+        return fail(SPHK_ERR_UNSUPPORTED, "sphk_iou_pairwise_keys_push: kind must be a Sph2Pob transform");
+    if (!col_keys || !peer_bufs) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise_keys_push: null pointer");
+    if (world < 1 || world > 16 || push_offset < 0 || part_stride < R)
+        return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_iou_pairwise_keys_push: bad world (1..16), offset or part_stride < R");
+    // (R == 0 or C == 0 launches no tile kernel: nothing is stored, the callers' buffers start zeroed = "no overlap")
+    const KeyPush kp = {(unsigned long long* const*)peer_bufs, (long long)push_offset, (long long)part_stride, world};
+    return pairwise_impl(kind, rows, R, cols, C, D, mode, edge, SPHK_ANGLE_EQUATOR, nullptr, C, nullptr, nullptr, nullptr, nullptr,
+                         row_base, col_base, workspace, stream, nullptr, nullptr, nullptr, (unsigned long long*)col_keys, 0, &kp);
+}
+
 int sphk_iou_pairwise_ties(int kind, const float* rows, int64_t R, const float* cols, int64_t C, int D, int mode, int edge,
                            const float* row_target, int32_t* col_tie, int32_t row_base, void* workspace, void* stream) {
     if (kind != SPHK_KIND_SPH2POB_EFFICIENT && kind != SPHK_KIND_SPH2POB_STANDARD)
@@ -2182,8 +2243,10 @@ int sphk_unpack_gathered_keys(const uint64_t* gathered, int32_t world, int64_t n
 }
 
 int sphk_unpack_peer_keys(const uint64_t* const* peer_bufs, int32_t rank, int32_t world, uint64_t step, int64_t block_offset,
-                          int64_t flag_offset, int64_t n_long, int64_t n_short, int64_t cap, float* long_max, int64_t* long_arg,
-                          float* short_max, int64_t* short_arg, void* stream) {
+                          int64_t flag_offset, int64_t n_long, int64_t n_short, int64_t cap, int32_t long_parts, int32_t long_pushed,
+                          float* long_max, int64_t* long_arg, float* short_max, int64_t* short_arg, void* stream) {
+    if (long_parts < 1 || long_parts > 64 || (!long_pushed && long_parts != 1))
+        return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_unpack_peer_keys: long_parts must be 1..64, and 1 unless the keys were pushed");
     if (world < 1 || world > 16 || rank < 0 || rank >= world || n_long < 0 || n_short < 0 || cap < 0 || block_offset < 0 || flag_offset < 0)
         return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_unpack_peer_keys: bad rank, world (1..16) or sizes");
     if (cap < (n_long + world - 1) / world) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_unpack_peer_keys: cap < ceil(n_long / world)");
@@ -2191,11 +2254,21 @@ int sphk_unpack_peer_keys(const uint64_t* const* peer_bufs, int32_t rank, int32_
     if (!peer_bufs || (n_long > 0 && (!long_max || !long_arg)) || (n_short > 0 && (!short_max || !short_arg)))
         return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_unpack_peer_keys: null pointer");
     // (at least one CTA even when there is nothing to unpack: the flags must be exchanged every step)
-    const unsigned g = blocks_for(n_long + n_short > 0 ? n_long + n_short : 1);
-    k_unpack_peers<<<g, kThreads, 0, (cudaStream_t)stream>>>((unsigned long long* const*)peer_bufs, rank, world, (unsigned long long)step,
-                                                            block_offset, flag_offset, n_long, n_short, cap, long_max, long_arg,
-                                                            short_max, short_arg);
-    SPHK_LAUNCH_CHECK("k_unpack_peers");
+    const int64_t need = blocks_for(n_long + n_short > 0 ? n_long + n_short : 1), cap_g = 8ll * sm_count();
+    const unsigned g = (unsigned)(need < cap_g ? need : cap_g);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(g, 1, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_no_pdl ? 0 : 1;
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, k_unpack_peers, (unsigned long long* const*)peer_bufs, (int)rank, (int)world,
+                                              (unsigned long long)step, block_offset, flag_offset, n_long, n_short, cap, (int)long_parts,
+                                              long_pushed != 0, long_max, long_arg, short_max, short_arg);
+    if (le != cudaSuccess) return cuda_fail(le, "cudaLaunchKernelEx(k_unpack_peers)");
     return SPHK_OK;
 }
 

@@ -7,9 +7,13 @@ writes its packed keys straight into the rank's communication block
     block = [ keys of the rank's anchors (cap = ceil(n / world) slots) | the rank's keys of the G ground truths ]
 
 and the exchange is ONE kernel launch that writes the per-anchor (max, argmax) of the whole anchor set in global order
-and reduces the per-GT keys over the ranks.  Two routes feed it:
-  * 'peer' (default where available): the blocks live in symmetric memory and the launch itself reads every shard's keys
-    from its owner over NVLink after an in-kernel flag handshake (``sphk_unpack_peer_keys``) -- no collective at all;
+and reduces the per-GT keys over the ranks.  Three routes feed it:
+  * 'peer' (default where available): the blocks live in symmetric memory; the COMPUTE kernel stores the finished keys of
+    its anchors into every peer's buffer while it is still running (``sphk_iou_pairwise_keys_push``: the transfer hides
+    under the math), and the unpack launch does an in-kernel flag handshake, fetches the 8 B x G per peer and reads the
+    anchors' keys locally (``sphk_unpack_peer_keys``) -- no collective at all;
+  * 'peer-pull': the compute kernel writes locally only and the unpack launch reads every shard's keys from its owner
+    over NVLink after the handshake (the first version of the route; kept for A/B timing);
   * 'nccl': ONE ``all_gather_into_tensor`` of the blocks (8 B per anchor + 8 B x G per rank), then
     ``sphk_unpack_gathered_keys``.
 No padding copy, no concatenation, no eager unpacking on either route.
@@ -84,42 +88,59 @@ def gather_assignment(block: torch.Tensor, n_anchors: int, n_gt: int, group=None
     return _native.unpack_gathered_keys(gathered, world, n_anchors, n_gt, block_capacity(n_anchors, world))
 
 
+MAX_PUSH_PARTS = 8      # push route: at most this many partial key arrays per anchor (n_gt <= 2048), else the pull route
+
+
 class PeerExchange:
-    """The exchange without a collective: every rank's key blocks live in a symmetric buffer
-    (torch.distributed._symmetric_memory: the same allocation mapped into every process of the node), and the unpack
-    launch reads each shard's keys from its owner over NVLink after a flag handshake inside the kernel
-    (``sphk_unpack_peer_keys``, csrc/sphk_kernels.cu: k_unpack_peers).  Layout per rank, in int64 elements:
-    [ block of even steps | block of odd steps | flags ]; the compute kernel of step s writes block (s & 1)."""
+    """The exchange without a collective: every rank keeps the key blocks of ALL ranks in a symmetric buffer
+    (torch.distributed._symmetric_memory: the same allocation mapped into every process of the node).  Layout per rank, in
+    int64 elements:  [ even steps: world slots | odd steps: world slots | flags ];  slot s = block of rank s =
+    [ parts x cap anchor keys | n_gt ].
+    parts > 1 or push=True ('peer'): the compute kernel of step t stores the keys of every tile into slot `rank` of parity
+    (t & 1) in EVERY rank's buffer while it runs (``sphk_iou_pairwise_keys_push``; parts = column tiles of the kernel);
+    the unpack launch (``sphk_unpack_peer_keys``) then needs the flag handshake, 8 B x n_gt per peer over NVLink, and
+    local reads.  push=False ('peer-pull', parts = 1): the kernel writes the rank's own slot only and the unpack launch
+    reads every slot from its owner over NVLink."""
     FLAG_SLOTS = 32
 
-    def __init__(self, n_anchors: int, n_gt: int, device, group=None):
+    def __init__(self, n_anchors: int, n_gt: int, device, group=None, parts: int = 1, push: bool = False):
         import torch.distributed._symmetric_memory as symm_mem
         self.group = group if group is not None else dist.group.WORLD
         self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
         if self.world > 16:
             raise RuntimeError("PeerExchange: at most 16 ranks (one node)")
-        self.n_anchors, self.n_gt = n_anchors, n_gt
+        self.n_anchors, self.n_gt, self.parts, self.push = n_anchors, n_gt, parts, push
         self.cap = block_capacity(n_anchors, self.world)
-        self.per = self.cap + n_gt
-        self.buf = symm_mem.empty(2 * self.per + self.FLAG_SLOTS, dtype=torch.int64, device=device)
+        self.per = parts * self.cap + n_gt
+        self.area = self.world * self.per                      # one parity: the blocks of all ranks
+        self.buf = symm_mem.empty(2 * self.area + self.FLAG_SLOTS, dtype=torch.int64, device=device)
         self.hdl = symm_mem.rendezvous(self.buf, self.group)
         self.buf.zero_()                       # padding slots and flags start at zero ...
         torch.cuda.synchronize(device)
-        self.hdl.barrier()                     # ... on every rank before anybody raises a flag
+        self.hdl.barrier()                     # ... on every rank before anybody raises a flag or pushes a key
         self.ptrs_dev = int(self.hdl.buffer_ptrs_dev)
         self.step = 0
 
     def next_block(self) -> torch.Tensor:
-        """The block the compute kernel of the next step writes into ([cap + n_gt] int64 view of the symmetric buffer)."""
+        """The rank's own slot of the next step ([parts * cap + n_gt] int64 view of the symmetric buffer)."""
         self.step += 1
-        off = (self.step & 1) * self.per
+        off = (self.step & 1) * self.area + self.rank * self.per
         return self.buf[off:off + self.per]
+
+    def compute(self, kind, anchors_local, gts, mode, anchor_offset: int):
+        """Push route: the step's fused max / argmax kernel (anchors = bboxes1); its anchors' keys go to every rank."""
+        from . import _native
+        block = self.next_block()
+        off = (self.step & 1) * self.area + self.rank * self.per
+        _native.iou_pairwise_keys_push(kind, anchors_local, gts, block[self.parts * self.cap:], self.ptrs_dev, self.world, off,
+                                       self.cap, mode=mode, row_base=anchor_offset)
 
     def finish(self, out=None):
         """-> (anchor_max, anchor_arg, gt_max, gt_arg) of the step whose block was handed out last."""
         from . import _native
-        return _native.unpack_peer_keys(self.ptrs_dev, self.rank, self.world, self.step, (self.step & 1) * self.per, 2 * self.per,
-                                        self.n_anchors, self.n_gt, self.cap, self.buf.device, out=out)
+        return _native.unpack_peer_keys(self.ptrs_dev, self.rank, self.world, self.step, (self.step & 1) * self.area, 2 * self.area,
+                                        self.n_anchors, self.n_gt, self.cap, self.buf.device, out=out, long_parts=self.parts,
+                                        long_pushed=self.push)
 
 
 _peer_exchanges = {}
@@ -133,10 +154,10 @@ def _all_ranks_ok(ok: bool, device, group) -> bool:
     return bool(int(t.item()))
 
 
-def peer_exchange(n_anchors: int, n_gt: int, device, group=None):
-    """The cached PeerExchange of (shape, device), or None where symmetric memory is not available on EVERY rank (then:
-    NCCL route).  Collective on first use: each step of the set-up is agreed on by all ranks before the next one."""
-    key = (str(device), n_anchors, n_gt, _world(group))
+def peer_exchange(n_anchors: int, n_gt: int, device, group=None, parts: int = 1, push: bool = False):
+    """The cached PeerExchange of (shape, device, route), or None where symmetric memory is not available on EVERY rank
+    (then: NCCL route).  Collective on first use: each step of the set-up is agreed on by all ranks before the next one."""
+    key = (str(device), n_anchors, n_gt, _world(group), parts, push)
     ex = _peer_exchanges.get(key)
     if ex is None and not _peer_failed:
         why = None
@@ -150,7 +171,7 @@ def peer_exchange(n_anchors: int, n_gt: int, device, group=None):
             why = why or "symmetric memory unavailable on another rank"
         else:
             try:
-                ex = PeerExchange(n_anchors, n_gt, device, group)
+                ex = PeerExchange(n_anchors, n_gt, device, group, parts, push)
             except Exception as e:            # pragma: no cover
                 why = repr(e)
             if not _all_ranks_ok(ex is not None, device, group):
@@ -180,7 +201,9 @@ def sharded_max_overlaps(anchors_local, gts, n_anchors, anchor_offset, backend='
     gts           : the replicated short set [G, D]
     anchors_are   : 'bboxes1' -> IoU(anchor, gt) (config #5 call), 'bboxes2' -> IoU(gt, anchor)
                     (the assigner's orientation); the jitters are role-asymmetric, so this matters.
-    exchange      : 'peer' -- keys read from the owners' symmetric buffers inside the unpack launch (no collective);
+    exchange      : 'peer' -- no collective: the compute kernel stores the anchors' keys into every peer's symmetric buffer
+                    while it runs, the unpack launch does the flag handshake and reads locally; 'peer-pull' -- the
+                    compute kernel writes locally only, the unpack launch reads the keys from their owners over NVLink;
                     'nccl' -- one all_gather_into_tensor + the unpack launch; 'auto' -- 'peer' where available.
                     Every rank must make the same choice.
     Returns (anchor_max[n_anchors], anchor_arg -> gt index, gt_max[G], gt_arg -> global anchor index)."""
@@ -194,9 +217,21 @@ def sharded_max_overlaps(anchors_local, gts, n_anchors, anchor_offset, backend='
         raise ValueError("rank %d of %d must hold anchors [%d, %d) of %d, got offset %d and %d rows"
                          % (rank, world, lo, hi, n_anchors, anchor_offset, n_local))
     cap = block_capacity(n_anchors, world)
-    ex = peer_exchange(n_anchors, n_gt, anchors_local.device, group) if (world > 1 and exchange in ('auto', 'peer')) else None
-    if exchange == 'peer' and world > 1 and ex is None:
-        raise RuntimeError("sharded_max_overlaps(exchange='peer'): symmetric memory is not available: %s" % _peer_failed)
+    if exchange not in ('auto', 'peer', 'peer-pull', 'nccl'):
+        raise ValueError("exchange must be 'auto', 'peer', 'peer-pull' or 'nccl'")
+    ex = None
+    if world > 1 and exchange != 'nccl':
+        from . import _native as _nat
+        # push: the anchors must be the kernel's rows (one partial key array per 256 ground truths); else pull
+        parts = _nat.key_push_parts(n_gt)
+        push = exchange != 'peer-pull' and anchors_are == 'bboxes1' and parts <= MAX_PUSH_PARTS
+        ex = peer_exchange(n_anchors, n_gt, anchors_local.device, group, parts if push else 1, push)
+    if exchange in ('peer', 'peer-pull') and world > 1 and ex is None:
+        raise RuntimeError("sharded_max_overlaps(exchange=%r): symmetric memory is not available: %s" % (exchange, _peer_failed))
+    if ex is not None and ex.push:
+        with torch.no_grad():
+            ex.compute(kind, anchors_local, gts, mode, anchor_offset)
+        return ex.finish()
     block = ex.next_block() if ex is not None else key_block(n_anchors, n_gt, world, anchors_local.device)
     a_out, g_out = block[:n_local], block[cap:]
     # the kernel's packed keys go straight into the communication block: no unpack / repack / copy
@@ -259,7 +294,7 @@ class HostSweep:
         self.ev_out = [torch.cuda.Event() for _ in range(self.chunks)]
         self.done = torch.cuda.Event()
         # the per-GT keys of this rank: one block [0 anchor slots | n_gt], in symmetric memory where that route is available
-        self.ex = peer_exchange(0, n_gt, dev, group) if (self.world > 1 and exchange in ('auto', 'peer')) else None
+        self.ex = peer_exchange(0, n_gt, dev, group) if (self.world > 1 and exchange != 'nccl') else None
         self.gblock = None if self.ex is not None else torch.zeros(n_gt, dtype=torch.int64, device=dev)
 
     def __call__(self, anchors_host, gts_host, anchor_offset, out_anchor_max, out_anchor_arg, out_gt_max, out_gt_arg,

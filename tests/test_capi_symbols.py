@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol(built_lib):
     for name in declared_symbols():
         assert hasattr(lib, name), "libsphk.so does not export %s" % name
     lib.sphk_abi_version.restype = ctypes.c_int
-    assert lib.sphk_abi_version() == 6
+    assert lib.sphk_abi_version() == 7
 
 
 def test_binding_covers_the_header(built_lib):
@@ -56,9 +56,12 @@ def test_argument_validation_needs_no_gpu(built_lib):
     assert lib.sphk_unpack_gathered_keys(None, 0, 10, 4, 10, None, None, None, None, None) == -1    # world < 1
     assert lib.sphk_unpack_gathered_keys(None, 2, 10, 4, 4, None, None, None, None, None) == -1     # cap < ceil(n / world)
     assert lib.sphk_unpack_gathered_keys(None, 2, 0, 0, 0, None, None, None, None, None) == 0       # nothing to do
-    assert lib.sphk_unpack_peer_keys(None, 0, 17, 1, 0, 0, 8, 2, 8, None, None, None, None, None) == -1   # more than 16 ranks
-    assert lib.sphk_unpack_peer_keys(None, 0, 2, 0, 0, 0, 8, 2, 4, None, None, None, None, None) == -1    # steps count from 1
-    assert lib.sphk_unpack_peer_keys(None, 2, 2, 1, 0, 0, 8, 2, 4, None, None, None, None, None) == -1    # rank >= world
+    assert lib.sphk_unpack_peer_keys(None, 0, 17, 1, 0, 0, 8, 2, 8, 1, 0, None, None, None, None, None) == -1   # more than 16 ranks
+    assert lib.sphk_unpack_peer_keys(None, 0, 2, 0, 0, 0, 8, 2, 4, 1, 0, None, None, None, None, None) == -1    # steps count from 1
+    assert lib.sphk_unpack_peer_keys(None, 2, 2, 1, 0, 0, 8, 2, 4, 1, 0, None, None, None, None, None) == -1    # rank >= world
+    assert lib.sphk_unpack_peer_keys(None, 0, 2, 1, 0, 0, 8, 2, 4, 4, 0, None, None, None, None, None) == -1    # parts > 1 without push
+    assert lib.sphk_iou_pairwise_keys_push(0, None, 8, None, 8, 5, 0, 0, None, 0, 0, None, 2, 0, 8, None, None) == -1   # null pointers
+    assert lib.sphk_key_push_parts(1024) == 4 and lib.sphk_key_push_parts(1025) == 5 and lib.sphk_key_push_parts(0) == 1
     assert lib.sphk_nms_batched(None, None, None, 3, 9, 0, 4, 1, 0.5, None, None) == -3    # NMS calculator: efficient, naive or unbiased
     assert lib.sphk_iou_aligned(4, None, None, 10, 5, 1, 0, 0, None, None) == -3          # naive_iou: mode 'iou' only
     assert lib.sphk_iou_aligned(5, None, None, 10, 4, 1, 0, 0, None, None) == -3          # unbiased_iou: mode 'iou' only

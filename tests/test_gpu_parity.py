@@ -367,22 +367,45 @@ def test_sharding_emulated_on_one_gpu(api, world):
         for g_, w_, s_ in zip(got, want, (a_max, a_arg, g_max, g_arg)):
             assert torch.equal(g_, w_) and torch.equal(g_, s_)
         assert int(g_arg[5]) == 17
-        # the fused route (sphk_unpack_peer_keys): every "rank" owns a buffer [even block | odd block | flags]; here they
-        # all sit on this GPU, and the flags are pre-set to the step as if every peer had arrived (the handshake itself
-        # needs one process per GPU: bench.py --gpus N --exchange peer).  Step 3 -> the odd block.
-        per, step = cap + G.size(0), 3
-        bufs = []
-        for rank in range(world):
-            buf = torch.zeros(2 * per + 32, dtype=torch.int64, device=DEV)
-            buf[per:2 * per] = blocks[rank]
-            buf[2 * per:2 * per + world] = step
-            bufs.append(buf)
-        table = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=DEV)
-        for rank in range(world):
-            peer = _native.unpack_peer_keys(table.data_ptr(), rank, world, step, per, 2 * per, n, G.size(0), cap, torch.device(DEV))
-            for p_, g_ in zip(peer, got):
-                assert torch.equal(p_, g_)
-            assert int(bufs[(rank + 1) % world][2 * per + rank]) == step       # the rank raised its flag in the peer's buffer
+        # the routes without a collective: every "rank" owns a buffer [even steps: world slots | odd steps: world slots |
+        # flags], slot s = [parts x cap anchor keys | G]; here they all sit on this GPU, and the flags are pre-set to the
+        # step as if every peer had arrived (the handshake itself needs one process per GPU: bench.py --gpus N).
+        # Step 3 -> the odd area.
+        #   pull (parts = 1): every rank has filled its own slot only, the unpack launch reads slot s from rank s's buffer;
+        #   push (anchors = rows): sphk_iou_pairwise_keys_push stores every tile's keys, one partial array per column tile,
+        #         into slot r of EVERY buffer while it runs; the unpack launch takes the maximum over the LOCAL partials.
+        step = 3
+        for pushed in ((False, True) if orient == "bboxes1" else (False,)):
+            parts = _native.key_push_parts(G.size(0)) if pushed else 1
+            assert parts == (2 if pushed else 1)
+            per = parts * cap + G.size(0)
+            area = world * per
+            bufs = [torch.full((2 * area + 32,), 0x7777 if pushed else 0, dtype=torch.int64, device=DEV) for _ in range(world)]
+            table = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=DEV)
+            for rank in range(world):
+                lo, hi = shard_bounds(n, world, rank)
+                off = area + rank * per
+                if not pushed:
+                    bufs[rank][off:off + per] = blocks[rank]
+                else:       # (the buffers start as garbage: the push route needs no zero-fill of the rows it owns)
+                    _native.iou_pairwise_keys_push("sph2pob_efficient", A[lo:hi], G, bufs[rank][off + parts * cap:off + per],
+                                                   table.data_ptr(), world, off, cap, row_base=lo)
+                bufs[rank][2 * area:2 * area + world] = step
+            if pushed:
+                for rank in range(world):               # every buffer holds every rank's partial keys; their maximum = the key
+                    for src in range(world):
+                        lo, hi = shard_bounds(n, world, src)
+                        at = area + src * per
+                        both = torch.maximum(bufs[rank][at:at + hi - lo], bufs[rank][at + cap:at + cap + hi - lo])
+                        assert torch.equal(both, blocks[src][:hi - lo])
+                    at = area + rank * per + parts * cap
+                    assert torch.equal(bufs[rank][at:at + G.size(0)], blocks[rank][cap:])
+            for rank in range(world):
+                peer = _native.unpack_peer_keys(table.data_ptr(), rank, world, step, area, 2 * area, n, G.size(0), cap, torch.device(DEV),
+                                                long_parts=parts, long_pushed=pushed)
+                for p_, g_ in zip(peer, got):
+                    assert torch.equal(p_, g_)
+                assert int(bufs[(rank + 1) % world][2 * area + rank]) == step       # the rank raised its flag in the peer's buffer
     # "no positive overlap" (key 0) reads as (0.0, index 0) on both sides
     far = torch.tensor([[10.0, 90.0, 0.5, 0.5, 0.0], [190.0, 90.0, 20.0, 20.0, 0.0], [12.0, 40.0, 0.5, 0.5, 0.0]], device=DEV)
     one = torch.tensor([[190.0, 90.0, 20.0, 20.0, 0.0], [300.0, 150.0, 1.0, 1.0, 0.0]], device=DEV)
