@@ -336,7 +336,8 @@ int sphk_nms_images(const float* boxes, const float* scores, const int64_t* labe
  * sphk_set_dense: 1 disables the parity-safe "disjoint pair" early-outs of the Sph2Pob kernels so the
  *   dense throughput can be reported next to the real one; returns the previous setting.
  * sphk_prefilter_count: *live_count (device) = number of pairs of rows[R] x cols[C] that survive the prefilter of
- *   the N x M kernels (circumscribed-circle and box-frame tests, csrc/sphk_fast.cuh), i.e. that the expensive
+ *   the N x M kernels (circumscribed-circle test, then the box-frame or the separating-axis test, whichever the kernel
+ *   instance of a call of that shape runs: csrc/sphk_fast.cuh), i.e. that the expensive
  *   transform + clipping code is run for; early-out rate = 1 - live / (R * C).  Workspace as sphk_iou_pairwise. */
 int sphk_probe_fp32(int32_t blocks, int32_t iters, float* sink, void* stream);
 int sphk_set_dense(int on);

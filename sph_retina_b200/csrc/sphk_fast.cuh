@@ -138,6 +138,56 @@ SPHK_HD float rsqrt_f(float x) {
 #endif
 }
 
+// Separating-axis test on the two planar boxes, from the per-box records alone (no arc, no atan2, no sincos).
+// Sph2Pob lays the boxes out along the great circle through their centres: in the frame of box g the centre of p sits
+// at arc * (cos a1, -sin a1), and p is turned by r = a2 - a1 against g, with a1 / a2 the bearings of the partner seen
+// from g / p in the boxes' own frames (internal angle minus gamma).  With the frame axes e (width) and f (height) of the
+// records as 3-D tangent vectors,
+//     A = u_p . e_g = -S cos a1,   B = u_p . f_g = S sin a1,   C = u_g . e_p = S cos a2,   Dd = u_g . f_p = -S sin a2,
+// S = sin(arc): |cos r| = |C A + Dd B| / S^2, |sin r| = |Dd A - C B| / S^2, and the four candidate axes are the boxes'
+// own: along e_g the centres are arc |A| / S apart and the boxes reach hw_g + hw_p |cos r| + hh_p |sin r|, and so on.
+// The arc enters through a series LOWER bound from cos(arc) = u_g . u_p (arc = 2 asin(x), x^2 = (1 - cos) / 2,
+// asin(x) >= x (1 + x^2 / 6 + 3 x^4 / 40)), so a reported gap is a real one.  Margins: the half sizes in the records carry
+// kBoxMargin, kSatMargin more covers what jitter_1 / jitter_2 and the acos clamps can turn both frames by (2 x 1.9e-3 rad
+// x (hw + hh <= pi) of extent, pi x 1.9e-3 of centre offset).  Never fires for S < 0.01 (near-coincident or antipodal
+// centres: the bearings are ill-conditioned there), for flagged boxes (half sizes 10) or NaNs.
+// true => the planar boxes are disjoint for every jitter outcome => IoU is exactly 0 in the reference.  ~60 instructions,
+// run by the N x M kernels on the pairs the circle test leaves alive when the operands are of similar size (1 M x 1,024
+// random boxes: a third of them end here -- 40.5 % -> 27.0 % of all pairs go on to the clipper, 26.2 % overlap).
+constexpr float kSatMargin = 1.2e-2f;
+SPHK_HD float rcp_approx(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
+SPHK_HD bool pre_sat_disjoint(float gux, float guy, float guz, float gex, float gey, float gez, float ghw, float gfx, float gfy,
+                              float gfz, float ghh, float pux, float puy, float puz, float pex, float pey, float pez, float phw,
+                              float pfx, float pfy, float pfz, float phh) {
+    const float dot = fmaf(gux, pux, fmaf(guy, puy, guz * puz));
+    const float A = fmaf(gex, pux, fmaf(gey, puy, gez * puz)), B = fmaf(gfx, pux, fmaf(gfy, puy, gfz * puz));
+    const float C = fmaf(pex, gux, fmaf(pey, guy, pez * guz)), Dd = fmaf(pfx, gux, fmaf(pfy, guy, pfz * guz));
+    const float S2 = fmaf(A, A, B * B);
+    const float x2 = fmaxf(fmaf(-0.5f, dot, 0.5f), 1e-12f);
+    const float x = x2 * rsqrt_f(x2);
+    const float arc = (x + x) * fmaf(x2, fmaf(x2, 0.075f, 0.16666667f), 1.0f);
+    const float rs2 = rcp_approx(S2);
+    const float q = arc * rsqrt_f(S2);                                  // arc / S
+    const float X = fabsf(fmaf(C, A, Dd * B)) * rs2, Y = fabsf(fmaf(Dd, A, -C * B)) * rs2;   // |cos r|, |sin r|
+    const bool t1 = q * fabsf(A) > fmaf(phw, X, fmaf(phh, Y, ghw + kSatMargin));
+    const bool t2 = q * fabsf(B) > fmaf(phw, Y, fmaf(phh, X, ghh + kSatMargin));
+    const bool t3 = q * fabsf(C) > fmaf(ghw, X, fmaf(ghh, Y, phw + kSatMargin));
+    const bool t4 = q * fabsf(Dd) > fmaf(ghw, Y, fmaf(ghh, X, phh + kSatMargin));
+    return (S2 > 1e-4f) & (t1 | t2 | t3 | t4);
+}
+SPHK_HD bool pre_sat_disjoint(const BoxCull& g, const BoxCull& p) {
+    return pre_sat_disjoint(g.ux, g.uy, g.uz, g.ex, g.ey, g.ez, g.hwm, g.fx, g.fy, g.fz, g.hhm, p.ux, p.uy, p.uz, p.ex, p.ey, p.ez,
+                            p.hwm, p.fx, p.fy, p.fz, p.hhm);
+}
+
 // The clipping job a pair boils down to: box 2 (w2 x h2, centre (px, py), rotated by r) against the
 // axis-aligned box 1 (w1 x h1) at the origin.
 struct ClipJob {

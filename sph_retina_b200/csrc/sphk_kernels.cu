@@ -45,12 +45,13 @@ const int g_no_rows32 = tune_env("SPHK_NO_ROWS32");
 const int g_no_approx4 = tune_env("SPHK_NO_APPROX4");
 const int g_no_pdl = tune_env("SPHK_NO_PDL");          // launch k_iou_rows32 / k_iou_pairwise2 without programmatic serialization
 const int g_no_boxcull = tune_env("SPHK_NO_BOXCULL");  // prefilter: circle test only
+const int g_no_sat = tune_env("SPHK_NO_SAT");          // no separating-axis stage (calls that would get it run the circle test alone)
 const int g_no_rows_inline = tune_env("SPHK_NO_ROWS_INLINE");   // long-row calls: row records through the workspace, as for short-row calls
 // bit 0 = do not launch k_box_pre (stale records)
 const int g_probe = tune_env("SPHK_PROBE");
 #else
 constexpr int g_force_ctas = 0, g_force_minb = 0, g_force_tr = 0, g_no_rows32 = 0, g_no_approx4 = 0, g_no_pdl = 0,
-              g_no_boxcull = 0, g_no_rows_inline = 0, g_probe = 0;
+              g_no_boxcull = 0, g_no_sat = 0, g_no_rows_inline = 0, g_probe = 0;
 #endif
 
 int fail(int code, const char* what) {
@@ -439,14 +440,15 @@ k_iou_pairwise(const float* __restrict__ rows, int64_t R, const float* __restric
 // one atomicMax per row / column and CTA.
 constexpr int kTC = 256, kRing = 64, kRecStride = 20;   // record stride 20 words: conflict-free LDS.128 across lanes
 
-template <int TR>
+template <int TR, bool SAT>
 struct PairTile {
     float crec[kTC * kRecStride];
     float rrec[TR * kRecStride];
     float4 rcull[TR][4];
+    float4 ccull[SAT ? kTC : 1][3];      // separating-axis stage: centre, width axis + half width, height axis + half height per column
     unsigned long long rkey[TR];
     unsigned long long ckey[kTC];
-    unsigned short ring[kThreads / 32][2][kRing];
+    unsigned short ring[kThreads / 32][SAT ? 3 : 2][kRing];   // 0: pairs for the clipper, 1: reference-order path, 2: circle-test survivors
     float rtgt[TR];      // tie pass: the row maxima to compare with
     int ctie[kTC];       // tie pass: per column, the largest (row index + 1) that ties its row maximum
     unsigned long long* peer[16];   // push route: the ranks' buffers (fetched during phase 0, used in the epilogue)
@@ -554,8 +556,8 @@ struct PairOut {
     uint32_t row_base, col_base;
 };
 
-template <int TR>
-__device__ __forceinline__ void emit_pair(PairTile<TR>& T, const PairOut& o, int r, int c, float v) {
+template <int TR, bool SAT>
+__device__ __forceinline__ void emit_pair(PairTile<TR, SAT>& T, const PairOut& o, int r, int c, float v) {
     if (o.out) o.out[(o.r0 + r) * o.ld + o.c0 + c] = v;
     if (v > 0.0f) {
         if (o.want_row) atomicMax(&T.rkey[r], pack_key(v, o.col_base + (uint32_t)(o.c0 + c)));
@@ -584,7 +586,11 @@ struct KeyPush {
     int world;
 };
 
-template <int D, int TR, bool BOX>
+// CULL: what proves pairs disjoint before the clipper sees them.  0: the circle test of the scan loop alone; 1: + the
+// box-frame test in the scan loop (ground truths x anchors); 2: + the separating-axis test (pre_sat_disjoint) as a stage
+// of its own between the scan and the clipper -- the circle test's survivors are queued, tested 32 at a time with full
+// warps, and only what is left goes on (operands of similar size: a third of the survivors end there).
+template <int D, int TR, int CULL>
 __global__ void __launch_bounds__(kThreads, 4)      // 4 CTAs per SM (64 registers): 3 cost 22 % of the throughput
 k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restrict__ cols, int64_t C,
                 const float4* __restrict__ rec, const float4* __restrict__ cull, int kind, int mode, int edge,
@@ -592,7 +598,8 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
                 unsigned long long* __restrict__ col_key, uint32_t row_base, uint32_t col_base, int flags,
                 const float* __restrict__ row_target, int* __restrict__ col_tie,
                 const int32_t* __restrict__ row_offsets, int64_t col_stride, float* __restrict__ tile_rmax, const KeyPush push) {
-    __shared__ __align__(16) PairTile<TR> T;
+    constexpr bool BOX = CULL == 1, SAT = CULL == 2;
+    __shared__ __align__(16) PairTile<TR, SAT> T;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool dense = (flags & 1) != 0;                               // sphk_set_dense (measurement)
 #ifdef SPHK_TIMELINE
@@ -652,6 +659,7 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
     if (col_ok) {
         const float4* u = cull + (R + o.c0 + tid) * 4;
         pc0 = __ldg(u); pc1 = __ldg(u + 1);
+        if (SAT) { T.ccull[tid][0] = pc0; T.ccull[tid][1] = __ldg(u + 2); T.ccull[tid][2] = __ldg(u + 3); }
     }
     if (tid < TR) {
         const bool ok = tid < nr;
@@ -670,7 +678,7 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
             if (ok) {
                 const float4* u = cull + (o.r0 + tid) * 4;
                 T.rcull[tid][0] = __ldg(u); T.rcull[tid][1] = __ldg(u + 1);
-                if (BOX) { T.rcull[tid][2] = __ldg(u + 2); T.rcull[tid][3] = __ldg(u + 3); }
+                if (BOX || SAT) { T.rcull[tid][2] = __ldg(u + 2); T.rcull[tid][3] = __ldg(u + 3); }
             } else {
                 put_cull_never(T.rcull[tid]);
             }
@@ -687,22 +695,52 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
     const float pr = dense ? 1e30f : pc1.z;      // dense (measurement) mode: the box-frame test never fires either
     (void)pr;
     int hf = 0, tf = 0, hs = 0, ts = 0;          // ring head / tail counters (fast, slow)
+    int ha = 0, ta = 0;                          // SAT: ring of the circle test's survivors
     const unsigned lt = (1u << lane) - 1u;
     // Alternate between a tight scan phase (prefilter rows until 32 live pairs are queued or the rows are used up)
-    // and ONE batch site (so that the expensive code exists once); the rings are flushed when the rows are done.
+    // and ONE batch site per stage (so that the expensive code exists once); the rings are flushed when the rows are done.
     int r = 0;
 #pragma unroll 1
     for (;;) {
+        if (SAT) {
 #pragma unroll 1
-        while (r < nr && tf - hf < 32) {
-            const bool live = prefilter_live<BOX>(T.rcull[r], pc0, pc1.x, pbias, pr);
-            const unsigned m = __ballot_sync(0xFFFFFFFFu, live);
-            if (live) T.ring[warp][0][(tf + __popc(m & lt)) & (kRing - 1)] = (unsigned short)((r << 5) | lane);
-            tf += __popc(m);
-            ++r;
+            while (r < nr && ta - ha < 32) {
+                const bool live = prefilter_live<false>(T.rcull[r], pc0, pc1.x, pbias, pr);
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, live);
+                if (live) T.ring[warp][SAT ? 2 : 0][(ta + __popc(m & lt)) & (kRing - 1)] = (unsigned short)((r << 5) | lane);
+                ta += __popc(m);
+                ++r;
+            }
+            if (ta > ha) {                         // here: >= 32 candidates, or the rows are done
+                const int cnt = min(ta - ha, 32);
+                __syncwarp();
+                const int e = T.ring[warp][SAT ? 2 : 0][(ha + lane) & (kRing - 1)];
+                __syncwarp();
+                bool live = false;
+                if (lane < cnt) {
+                    const float4* g = T.rcull[e >> 5];
+                    const float4* q = T.ccull[warp * 32 + (e & 31)];
+                    const float4 g0 = g[0], g2 = g[2], g3 = g[3], q0 = q[0], q1 = q[1], q2 = q[2];
+                    live = dense || !pre_sat_disjoint(g0.x, g0.y, g0.z, g2.x, g2.y, g2.z, g2.w, g3.x, g3.y, g3.z, g3.w,
+                                                      q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w);
+                }
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, live);
+                if (live) T.ring[warp][0][(tf + __popc(m & lt)) & (kRing - 1)] = (unsigned short)e;
+                tf += __popc(m);
+                ha += cnt;
+            }
+        } else {
+#pragma unroll 1
+            while (r < nr && tf - hf < 32) {
+                const bool live = prefilter_live<BOX>(T.rcull[r], pc0, pc1.x, pbias, pr);
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, live);
+                if (live) T.ring[warp][0][(tf + __popc(m & lt)) & (kRing - 1)] = (unsigned short)((r << 5) | lane);
+                tf += __popc(m);
+                ++r;
+            }
         }
-        const bool rows_done = r >= nr;
-        if (tf > hf) {                             // here: >= 32 queued, or the rows are done
+        const bool rows_done = r >= nr && ta == ha;        // nothing more can enter the fast ring
+        if (tf - hf >= 32 || (rows_done && tf > hf)) {
             const int cnt = min(tf - hf, 32);
             __syncwarp();
             const int e = T.ring[warp][0][(hf + lane) & (kRing - 1)];
@@ -770,7 +808,7 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
 // ---- measurement: how many pairs of an N x M call survive the prefilter of the scan loops (bench.py reports the
 // early-out rate next to the throughput).  Same records, same prefilter_live() as k_iou_pairwise2.
 __global__ void __launch_bounds__(kThreads)
-k_prefilter_count(int64_t R, int64_t C, const float4* __restrict__ cull, unsigned long long* __restrict__ live_count, bool box) {
+k_prefilter_count(int64_t R, int64_t C, const float4* __restrict__ cull, unsigned long long* __restrict__ live_count, int cull_kind) {
     __shared__ float4 s_rc[32][4];
     const int64_t r0 = (int64_t)blockIdx.x * 32, col = (int64_t)blockIdx.y * kThreads + threadIdx.x;
     const int nr = (int)min((int64_t)32, R - r0);
@@ -781,9 +819,17 @@ k_prefilter_count(int64_t R, int64_t C, const float4* __restrict__ cull, unsigne
     __syncthreads();
     unsigned n = 0;
     if (col < C) {
-        const float4 pc0 = __ldg(cull + (R + col) * 4), pc1 = __ldg(cull + (R + col) * 4 + 1);
-        for (int r = 0; r < nr; ++r)
-            n += (box ? prefilter_live<true>(s_rc[r], pc0, pc1.x, pc1.y, pc1.z) : prefilter_live<false>(s_rc[r], pc0, pc1.x, pc1.y, pc1.z)) ? 1u : 0u;
+        const float4* u = cull + (R + col) * 4;
+        const float4 pc0 = __ldg(u), pc1 = __ldg(u + 1), pc2 = __ldg(u + 2), pc3 = __ldg(u + 3);
+        for (int r = 0; r < nr; ++r) {
+            bool live = cull_kind == 1 ? prefilter_live<true>(s_rc[r], pc0, pc1.x, pc1.y, pc1.z) : prefilter_live<false>(s_rc[r], pc0, pc1.x, pc1.y, pc1.z);
+            if (live && cull_kind == 2) {
+                const float4 g0 = s_rc[r][0], g2 = s_rc[r][2], g3 = s_rc[r][3];
+                live = !pre_sat_disjoint(g0.x, g0.y, g0.z, g2.x, g2.y, g2.z, g2.w, g3.x, g3.y, g3.z, g3.w,
+                                         pc0.x, pc0.y, pc0.z, pc2.x, pc2.y, pc2.z, pc2.w, pc3.x, pc3.y, pc3.z, pc3.w);
+            }
+            n += live ? 1u : 0u;
+        }
     }
     n = __reduce_add_sync(0xFFFFFFFFu, n);
     if ((threadIdx.x & 31) == 0 && n) atomicAdd(live_count, (unsigned long long)n);
@@ -2000,6 +2046,18 @@ static inline bool box_test_pays(int64_t rows_per_image, int64_t C) { return row
 
 // k_box_pre + k_iou_pairwise2 for rows[R] x cols[C] (rows = concatenation of `batch` GT lists when row_offsets is
 // given; max_rows = the longest list).  rec / cull: [R + C] records in the workspace.
+#ifdef SPHK_TUNING
+static void pw2_occupancy_note(const void* fn, const char* what) {      // tools/: resident CTAs per SM of the instance, once
+    static int told = 0;
+    if (told++ > 2) return;
+    int n = -1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, kThreads, 0);
+    fprintf(stderr, "[sphk tuning] k_iou_pairwise2<%s>: %d CTAs / SM\n", what, n);
+}
+#else
+static inline void pw2_occupancy_note(const void*, const char*) {}
+#endif
+
 static int launch_pairwise2(int kind, const float* rows, int64_t R, const float* cols, int64_t C, int D, int mode, int edge,
                             float4* rec, float4* cull, float* out, int64_t ld, unsigned long long* rkey,
                             unsigned long long* ckey, int32_t row_base, int32_t col_base, const float* row_target,
@@ -2039,25 +2097,32 @@ static int launch_pairwise2(int kind, const float* rows, int64_t R, const float*
     const float4* crec = rec;
     const float4* ccull = cull;
     const int dn = (g_dense != 0 ? 1 : 0) | (rows_inline ? 4 : 0);
-    // which instance: with the box-frame prefilter test (rows = the short, large-box operand: ground truths x anchors) or without
-    const bool box = !g_no_boxcull && box_test_pays(max_rows, C);
+    // which instance: with the box-frame prefilter test in the scan loop (rows = the short, large-box operand: ground
+    // truths x anchors), or with the separating-axis stage behind the circle test (everything else: operands of similar size)
+    const int cull_kind = box_test_pays(max_rows, C) ? (g_no_boxcull ? 0 : 1) : (g_no_sat ? 0 : 2);
     const KeyPush kp = push ? *push : KeyPush{nullptr, 0, 0, 1};
     cudaError_t le;
-#define SPHK_PW2(DD, TR, BX)                                                                                               \
-    le = cudaLaunchKernelEx(&cfg, k_iou_pairwise2<DD, TR, BX>, rows, R, cols, C, crec, ccull, kind, mode, edge, out, ld, rkey, \
-                            ckey, (uint32_t)row_base, (uint32_t)col_base, dn, row_target, col_tie, row_offsets, col_stride, tile_rmax, kp)
-    if (box) {
-        if (D == 4 && tr == 32) SPHK_PW2(4, 32, true);
-        else if (D == 4) SPHK_PW2(4, 8, true);
-        else if (tr == 32) SPHK_PW2(5, 32, true);
-        else SPHK_PW2(5, 8, true);
-    } else {
-        if (D == 4 && tr == 32) SPHK_PW2(4, 32, false);
-        else if (D == 4) SPHK_PW2(4, 8, false);
-        else if (tr == 32) SPHK_PW2(5, 32, false);
-        else SPHK_PW2(5, 8, false);
-    }
-#undef SPHK_PW2
+    auto go = [&](auto kernel, const char* what) {
+        // every instance wants four resident CTAs per SM (the separating-axis one holds 43 KB of shared memory per CTA):
+        // ask for the largest shared-memory carveout instead of leaving the split to the driver's heuristic
+        // (once per instance and process: the value never changes)
+        static const cudaError_t carve = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        (void)carve;
+        pw2_occupancy_note((const void*)kernel, what);
+        le = cudaLaunchKernelEx(&cfg, kernel, rows, R, cols, C, crec, ccull, kind, mode, edge, out, ld, rkey, ckey, (uint32_t)row_base,
+                                (uint32_t)col_base, dn, row_target, col_tie, row_offsets, col_stride, tile_rmax, kp);
+    };
+#define SPHK_PW2C(CK)                                                                   \
+    do {                                                                                \
+        if (D == 4 && tr == 32) go(k_iou_pairwise2<4, 32, CK>, "4,32," #CK);            \
+        else if (D == 4) go(k_iou_pairwise2<4, 8, CK>, "4,8," #CK);                     \
+        else if (tr == 32) go(k_iou_pairwise2<5, 32, CK>, "5,32," #CK);                 \
+        else go(k_iou_pairwise2<5, 8, CK>, "5,8," #CK);                                 \
+    } while (0)
+    if (cull_kind == 1) SPHK_PW2C(1);
+    else if (cull_kind == 2) SPHK_PW2C(2);
+    else SPHK_PW2C(0);
+#undef SPHK_PW2C
     if (le != cudaSuccess) return cuda_fail(le, "cudaLaunchKernelEx(k_iou_pairwise2)");
     return SPHK_OK;
 }
@@ -2736,7 +2801,8 @@ int sphk_prefilter_count(const float* rows, int64_t R, const float* cols, int64_
     float4* cull = rec + (R + C) * 4;
     if (D == 4) k_box_pre<4><<<blocks_for(R + C), kThreads, 0, s>>>(rows, R, cols, C, edge, rec, cull, aligned16(rows), aligned16(cols), nullptr, nullptr, false);
     else k_box_pre<5><<<blocks_for(R + C), kThreads, 0, s>>>(rows, R, cols, C, edge, rec, cull, false, false, nullptr, nullptr, false);
-    k_prefilter_count<<<dim3((unsigned)row_tiles, (unsigned)col_tiles), kThreads, 0, s>>>(R, C, cull, (unsigned long long*)live_count, box_test_pays(R, C));
+    k_prefilter_count<<<dim3((unsigned)row_tiles, (unsigned)col_tiles), kThreads, 0, s>>>(R, C, cull, (unsigned long long*)live_count,
+                                                                                          box_test_pays(R, C) ? (g_no_boxcull ? 0 : 1) : (g_no_sat ? 0 : 2));
     SPHK_LAUNCH_CHECK("k_prefilter_count");
     return SPHK_OK;
 }

@@ -63,7 +63,7 @@ void hostsim_iou_aligned_v2(int kind, const float* b1, const float* b2, long P, 
 }
 
 // Prefilter verdicts next to the reference-order IoU computed WITHOUT any early-out (dense = true): cull[i] bit 0 = circle
-// test, bit 1 = box-frame test (row = box 1).  A culled pair must have dense IoU exactly 0.
+// test, bit 1 = box-frame test (row = box 1), bit 2 = separating-axis test.  A culled pair must have dense IoU exactly 0.
 void hostsim_prefilter(int kind, const float* b1, const float* b2, long P, int D, int mode, int edge, float* dense_iou,
                        unsigned char* cull) {
     for (long i = 0; i < P; ++i) {
@@ -72,7 +72,7 @@ void hostsim_prefilter(int kind, const float* b1, const float* b2, long P, int D
         BoxCull gc, pc;
         box_pre(x, 1, D, edge, &gr, &gc);
         box_pre(y, 2, D, edge, &pr, &pc);
-        cull[i] = (pre_disjoint(gc, pc) ? 1 : 0) | (pre_outside_box(gc, pc) ? 2 : 0);
+        cull[i] = (pre_disjoint(gc, pc) ? 1 : 0) | (pre_outside_box(gc, pc) ? 2 : 0) | (pre_sat_disjoint(gc, pc) ? 4 : 0);
         dense_iou[i] = sph2pob_iou_pair(x, y, D, kind, mode, edge, true);
     }
 }
