@@ -27,6 +27,9 @@ extern "C" {
 
 #define SPHK_ABI_VERSION 7
 
+/* OR-ed into `kind` of the NMS entry points: suppress iff IoU > threshold (mmcv nms) instead of !(IoU <= threshold) (SphNMS) */
+#define SPHK_NMS_RULE_GT 0x100
+
 enum sphk_status {
     SPHK_OK = 0,
     SPHK_ERR_INVALID_ARGUMENT = -1,
@@ -298,7 +301,10 @@ int sphk_box_format(int fmt, const float* in, int64_t n, int d_in, int d_out, fl
 /* Batched greedy spherical NMS (SphNMS / sph_batched_nms / sph_nms_op,
  * sphdet/bbox/nms/sph_nms.py:22-74).  kind: the IoU SphNMS was built with (sph_nms.py:8-16) -- SPHK_KIND_SPH2POB_EFFICIENT
  * (its default), SPHK_KIND_NAIVE (the reference's indoor360 configs: test_cfg.iou_calculator = 'naive_iou') or
- * SPHK_KIND_UNBIASED (its pandora configs: 'unbiased_iou').
+ * SPHK_KIND_UNBIASED (its pandora configs: 'unbiased_iou').  SPHK_KIND_NAIVE | SPHK_NMS_RULE_GT is mmcv's `nms` on the
+ * sph2pix boxes, i.e. PlanarNMS (sphdet/bbox/nms/planar_nms.py:7-18): same IoU, but suppression iff IoU > threshold, so
+ * that a NaN IoU (two zero-area boxes) KEEPS the box as mmcv's `inter > thr * union` does, where SphNMS's
+ * `ious <= thr` (:70) drops it.
  *   boxes       [M, D]
  *   order       [M]    int32 indices into boxes, grouped by segment (one segment = one
  *                      (image, class) group), score-descending inside a segment (:65)

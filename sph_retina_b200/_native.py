@@ -676,7 +676,8 @@ def riou_fwd_bwd(o1, o2, grad_iou=None, want1=False, want2=False):
     return iou, g1, g2
 
 
-NMS_KIND = {"sph2pob_efficient": 0, "naive_iou": 4, "unbiased_iou": 5}      # SphNMS's iou_calculator names (sph_nms.py:8-16)
+# SphNMS's iou_calculator names (sph_nms.py:8-16); 'planar' = naive_iou with mmcv nms's rule (SPHK_NMS_RULE_GT: a NaN IoU keeps)
+NMS_KIND = {"sph2pob_efficient": 0, "naive_iou": 4, "unbiased_iou": 5, "planar": 4 | 0x100}
 
 
 def nms_batched(boxes, order, seg_offsets, max_seg_len: int, iou_threshold: float, typical_seg_len: int = 0,

@@ -16,6 +16,8 @@
 // The per-pair arithmetic lives in sphk_math.cuh (reference-order path, clipper), sphk_fast.cuh (records,
 // prefilter, fast path) and sphk_grad.cuh (analytic backward).
 #include <cuda_runtime.h>
+
+#include <atomic>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -61,6 +63,23 @@ int fail(int code, const char* what) {
 int cuda_fail(cudaError_t e, const char* where) {
     snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
     return SPHK_ERR_CUDA;
+}
+
+// Dynamic shared memory above 48 KB needs an opt-in per kernel (and device).  It is raised ONCE to the architecture's
+// maximum instead of to the size of the call at hand: two host threads launching the same kernel with different sizes
+// can then never lower each other's limit between the attribute call and the launch.  TAG tells instances of one
+// function-pointer type apart.
+constexpr int kMaxDynamicSmem = 227 * 1024;
+template <int TAG, typename K>
+cudaError_t allow_max_dynamic_smem(K kernel) {
+    static std::atomic<unsigned long long> done{0ull};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynamicSmem);
+    if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+    return e;
 }
 #define SPHK_LAUNCH_CHECK(where)                                  \
     do {                                                          \
@@ -1650,7 +1669,12 @@ __device__ __noinline__ float naive_pair_outofline(const RawBox& x, const RawBox
 __device__ __noinline__ float unbiased_pair_outofline(const RawBox& x, const RawBox& y, int D) { return unbiased_iou_pair(x, y, D); }
 __device__ __forceinline__ bool nms_suppresses(const float* __restrict__ boxes, int bi, int bj, const RawBox& x, const RawBox& y,
                                                int D, int kind, float thr) {
-    if (kind == KIND_NAIVE) return !(naive_pair_outofline(x, y, D) <= thr);
+    // SphNMS keeps what passes `ious <= thr` (sph_nms.py:70): a NaN IoU suppresses.  mmcv's nms -- PlanarNMS, planar_nms.py:16 --
+    // suppresses on `inter > thr * union`: a NaN IoU (two zero-area boxes) keeps the box (SPHK_NMS_RULE_GT).
+    if ((kind & 0xFF) == KIND_NAIVE) {
+        const float v = naive_pair_outofline(x, y, D);
+        return (kind & SPHK_NMS_RULE_GT) ? v > thr : !(v <= thr);
+    }
     if (kind == KIND_UNBIASED) return !(unbiased_pair_outofline(x, y, D) <= thr);
     return pair_iou_any(boxes, bi, boxes, bj, x, y, D, KIND_SPH2POB_EFFICIENT, MODE_IOU, EDGE_ARC) > thr;
 }
@@ -2667,8 +2691,8 @@ int sphk_decode_loss_reduce(const float* anchors, const float* deltas, const flo
 int sphk_nms_batched(const float* boxes, const int32_t* order, const int32_t* seg_offsets, int32_t S, int32_t max_seg_len,
                      int32_t typical_seg_len, int D, int kind, float iou_threshold, uint8_t* keep, void* stream) {
     if (S < 0 || max_seg_len < 0 || (D != 4 && D != 5)) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_nms_batched: bad S, max_seg_len or D");
-    if (kind != SPHK_KIND_SPH2POB_EFFICIENT && kind != SPHK_KIND_NAIVE && kind != SPHK_KIND_UNBIASED)
-        return fail(SPHK_ERR_UNSUPPORTED, "sphk_nms_batched: kind must be sph2pob_efficient, naive or unbiased (SphNMS, sph_nms.py:8-16)");
+    if (kind != SPHK_KIND_SPH2POB_EFFICIENT && kind != SPHK_KIND_NAIVE && kind != SPHK_KIND_UNBIASED && kind != (SPHK_KIND_NAIVE | SPHK_NMS_RULE_GT))
+        return fail(SPHK_ERR_UNSUPPORTED, "sphk_nms_batched: kind must be sph2pob_efficient, naive[ | SPHK_NMS_RULE_GT] or unbiased (SphNMS, sph_nms.py:8-16)");
     if (S == 0 || max_seg_len == 0) return SPHK_OK;
     if (!boxes || !order || !seg_offsets || !keep) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_nms_batched: null pointer");
     const int max_words = (max_seg_len + 31) / 32;
@@ -2682,11 +2706,11 @@ int sphk_nms_batched(const float* boxes, const int32_t* order, const int32_t* se
     const int nt = tl <= 64 ? 128 : (tl <= 256 ? 256 : (tl <= 512 ? 512 : 1024));
     cudaError_t e;
     if (D == 4) {
-        e = cudaFuncSetAttribute(k_nms<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = allow_max_dynamic_smem<4>(k_nms<4>);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_nms)");
         k_nms<4><<<S, nt, smem, s>>>(boxes, const_cast<int32_t*>(order), seg_offsets, nullptr, nullptr, 0, nullptr, 1, iou_threshold, keep, max_words, v, kind);
     } else {
-        e = cudaFuncSetAttribute(k_nms<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = allow_max_dynamic_smem<5>(k_nms<5>);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_nms)");
         k_nms<5><<<S, nt, smem, s>>>(boxes, const_cast<int32_t*>(order), seg_offsets, nullptr, nullptr, 0, nullptr, 1, iou_threshold, keep, max_words, v, kind);
     }
@@ -2706,8 +2730,8 @@ int sphk_nms_images(const float* boxes, const float* scores, const int64_t* labe
                     int32_t* out_count, void* workspace, void* stream) {
     if (num_images < 0 || per_image < 0 || num_classes <= 0 || max_out < 0 || (D != 4 && D != 5))
         return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_nms_images: bad sizes or D");
-    if (kind != SPHK_KIND_SPH2POB_EFFICIENT && kind != SPHK_KIND_NAIVE && kind != SPHK_KIND_UNBIASED)
-        return fail(SPHK_ERR_UNSUPPORTED, "sphk_nms_images: kind must be sph2pob_efficient, naive or unbiased (SphNMS, sph_nms.py:8-16)");
+    if (kind != SPHK_KIND_SPH2POB_EFFICIENT && kind != SPHK_KIND_NAIVE && kind != SPHK_KIND_UNBIASED && kind != (SPHK_KIND_NAIVE | SPHK_NMS_RULE_GT))
+        return fail(SPHK_ERR_UNSUPPORTED, "sphk_nms_images: kind must be sph2pob_efficient, naive[ | SPHK_NMS_RULE_GT] or unbiased (SphNMS, sph_nms.py:8-16)");
     if (num_images == 0) return SPHK_OK;
     if (!out_idx || !out_count) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_nms_images: null output pointer");
     cudaStream_t s = (cudaStream_t)stream;
@@ -2734,8 +2758,10 @@ int sphk_nms_images(const float* boxes, const float* scores, const int64_t* labe
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(keep)");
     const int nt_img = Kp >= 1024 ? 1024 : Kp;
     const size_t smem_sc = (size_t)num_classes * 4, smem_col = (size_t)Kp * 8;
-    e = cudaFuncSetAttribute(k_img_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sc);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_img_collect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_col);
+    if (smem_sc > (size_t)kMaxDynamicSmem || smem_col > (size_t)kMaxDynamicSmem)
+        return fail(SPHK_ERR_UNSUPPORTED, "sphk_nms_images: more than 58,000 classes; use sphk_nms_batched");
+    e = allow_max_dynamic_smem<0>(k_img_scatter);
+    if (e == cudaSuccess) e = allow_max_dynamic_smem<1>(k_img_collect);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_img_scatter)");
     k_img_scatter<<<num_images, nt_img, smem_sc, s>>>(labels, valid, per_image, num_classes, order, seg_start, seg_len, bad);
     SPHK_LAUNCH_CHECK("k_img_scatter");
@@ -2750,11 +2776,11 @@ int sphk_nms_images(const float* boxes, const float* scores, const int64_t* labe
     const int nt = num_classes >= 512 ? 512 : (tl <= 16 ? 128 : (tl <= 64 ? 256 : (tl <= 256 ? 512 : 1024)));   // >= 512: a cap, not a count
     const bool v = aligned16(boxes);
     if (D == 4) {
-        e = cudaFuncSetAttribute(k_nms<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = allow_max_dynamic_smem<4>(k_nms<4>);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_nms)");
         k_nms<4><<<(unsigned)S, nt, smem, s>>>(boxes, order, seg_start, seg_len, scores, sort_cap, bad, num_classes, iou_threshold, keep, max_words, v, kind);
     } else {
-        e = cudaFuncSetAttribute(k_nms<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = allow_max_dynamic_smem<5>(k_nms<5>);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_nms)");
         k_nms<5><<<(unsigned)S, nt, smem, s>>>(boxes, order, seg_start, seg_len, scores, sort_cap, bad, num_classes, iou_threshold, keep, max_words, v, kind);
     }

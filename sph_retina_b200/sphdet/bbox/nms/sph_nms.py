@@ -37,7 +37,7 @@ def _keep_indices(boxes, scores, seg_ids, iou_threshold, desc=None, iou_calculat
     """Indices (into boxes) that survive the per-segment greedy NMS, unordered."""
     order, offsets, longest = _segments(scores, seg_ids, desc)
     flags = _native.nms_batched(boxes, order, offsets, longest, iou_threshold, iou_calculator=iou_calculator)
-    return order[flags.bool()]
+    return order[flags == 1]            # (no segment is refused here: the kernel is sized for the longest one)
 
 
 def sph_batched_nms(boxes, scores, idxs, nms_cfg, iou_calculator='sph2pob_efficient', class_agnostic=False):
@@ -79,7 +79,9 @@ def sph_batched_nms_images(boxes, scores, labels, image_ids, iou_threshold=0.5, 
     With the three hints (batch size, number of classes, an upper bound of the boxes per (image, class) segment, e.g.
     nms_pre) the segment table is built densely on the device and the only host synchronisation left is the final
     compaction of the kept indices.  ``valid`` (bool [M], needs the hints): boxes to leave out -- padded candidate lists
-    go in as they are; the invalid ones are parked behind the last segment and never looked at."""
+    go in as they are; the invalid ones are parked behind the last segment and never looked at.
+    A label outside [0, num_classes) raises; a segment longer than ``max_per_segment`` (which the kernel refuses) sends the
+    call through the exact-length path instead of dropping its boxes."""
     desc = _desc_score_key(scores)
     if num_images is None or num_classes is None or max_per_segment is None:
         if valid is not None:
@@ -97,7 +99,19 @@ def sph_batched_nms_images(boxes, scores, labels, image_ids, iou_threshold=0.5, 
         offsets[1:] = counts.cumsum(0)
         typical = max(1, (2 * boxes.size(0)) // max(1, counts.numel()))     # twice the mean segment length
         flags = _native.nms_batched(boxes, order, offsets, int(max_per_segment), iou_threshold, typical, iou_calculator)
-        keep = order[flags == 1]          # a refused (too long) segment is flagged 0xFF and drops out: size the hint right
+        # one more scalar next to the compaction's synchronisation: labels in range, no segment refused (flag 0xFF)
+        in_range = (labels >= 0) & (labels < int(num_classes))
+        if valid is not None:
+            in_range = in_range | ~valid
+        problems = torch.stack([(~in_range).any(), (flags == 0xFF).any()])
+        keep = order[flags == 1]
+        bad_label, refused = problems.tolist()
+        if bad_label:
+            raise ValueError("sph_batched_nms_images: a label lies outside [0, num_classes = %d)" % int(num_classes))
+        if refused:        # the hint was too small: same result through the exact-length path, nothing is dropped
+            sel = torch.arange(boxes.size(0), device=boxes.device) if valid is None else valid.nonzero(as_tuple=False).view(-1)
+            seg = (image_ids[sel].long() << 20) | labels[sel].long()
+            keep = sel[_keep_indices(boxes[sel], scores[sel], seg, iou_threshold, desc[sel], iou_calculator)]
     return keep[torch.argsort((image_ids[keep].long() << 32) | desc[keep])]
 
 
@@ -135,7 +149,8 @@ class PlanarNMS:
     """sphdet/bbox/nms/planar_nms.py:7-18 -- what the head uses when ``test_cfg.iou_calculator == 'planar'``
     (sph_retina_head.py:89-90): the boxes read as planar (x1, y1, x2, y2) boxes of the 512 x 1024 image
     (``Sph2PlanarBoxTransform('sph2pix')``) and mmcv's ``batched_nms`` of type 'nms' on them.  That is the suppression rule
-    of ``SphNMS('naive_iou')`` for BFoV boxes (IoU = inter / (a1 + a2 - inter), suppress iff IoU > thr), class-agnostic by
+    of ``SphNMS('naive_iou')`` for BFoV boxes (IoU = inter / (a1 + a2 - inter), suppress iff IoU > thr -- a NaN IoU of
+    two zero-area boxes keeps the box, as mmcv's ``inter > thr * union`` does, where SphNMS would drop it), class-agnostic by
     default (planar_nms.py:11) -- so it runs in the same NMS kernel with one segment per image, or one per label when
     ``class_agnostic`` is False (mmcv's coordinate-offset trick separates the classes exactly)."""
 
@@ -166,7 +181,7 @@ class PlanarNMS:
         inner = dict(iou_threshold=thr)
         if max_num > 0:
             inner['max_num'] = max_num
-        dets, keep = sph_batched_nms(boxes, scores, labels, inner, 'naive_iou')
+        dets, keep = sph_batched_nms(boxes, scores, labels, inner, 'planar')      # naive IoU, mmcv's `>` rule (NaN keeps)
         return dets, (keep if index is None else index[keep])
 
 

@@ -95,7 +95,12 @@ def get_bboxes_batch(cls_scores, bbox_preds, mlvl_priors, bbox_coder, cfg, box_v
     order of equal scores, which is unspecified in the reference as well)."""
     nms_pre = _cfg_get(cfg, 'nms_pre', -1)
     score_thr = float(_cfg_get(cfg, 'score_thr', 0.0))
-    nms_cfg = _cfg_get(cfg, 'nms') or {}
+    nms_cfg = _cfg_get(cfg, 'nms')
+    if nms_cfg is None:
+        raise ValueError("test_cfg.nms is None: the reference aborts the process here (sph_nms.py:24-29)")
+    unknown = set(nms_cfg) - {'type', 'iou_threshold', 'max_num', 'class_agnostic', 'split_thr'}
+    if unknown:
+        raise ValueError("get_bboxes_batch: unsupported test_cfg.nms keys %s" % sorted(unknown))
     iou_thr = float(nms_cfg.get('iou_threshold', 0.5))
     iou_calc = _cfg_get(cfg, 'iou_calculator', 'sph2pob_efficient')      # test_cfg.iou_calculator (sph_retina_head.py:89-90)
     if iou_calc == 'planar':                   # class-agnostic planar NMS per image: the per-image contract covers it
@@ -122,7 +127,8 @@ def get_bboxes_batch(cls_scores, bbox_preds, mlvl_priors, bbox_coder, cfg, box_v
     K = scores.size(1)
     boxes = bbox_coder.decode(torch.cat(pr, 1).reshape(-1, D), torch.cat(dl, 1).reshape(-1, D))     # one launch
     scores, labels = scores.reshape(-1), labels.reshape(-1)
-    max_per_img = min(int(_cfg_get(cfg, 'max_per_img', K)), K)
+    # per-image cap: nms.max_num is applied by sph_batched_nms (sph_nms.py:46-53) before the head's max_per_img
+    max_per_img = min(int(_cfg_get(cfg, 'max_per_img', K)), int(nms_cfg.get('max_num', K)), K)
     counts = None
     if K <= 16384:
         # sort, suppression and per-image ordering on the device; the one host synchronisation is reading the counts

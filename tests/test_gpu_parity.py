@@ -740,6 +740,47 @@ def test_planar_nms_golden_keep_sets(api):
     assert torch.equal(scores[keep], scores.sort(descending=True)[0])
 
 
+def test_planar_nms_zero_area_boxes_follow_mmcv(api):
+    """Two zero-area boxes on the same spot have IoU 0 / 0: mmcv's nms (`inter > thr * union`; PlanarNMS, planar_nms.py:16)
+    keeps both, SphNMS('naive_iou') (`ious <= thr` keeps, sph_nms.py:70) drops the later one.  Both rules live in the NMS
+    kernel (SPHK_NMS_RULE_GT); the planar one is checked against the oracle's restatement of mmcv's nms."""
+    from sph_retina_b200.sphdet.bbox.nms import PlanarNMS, SphNMS
+    boxes = O.generate_boxes(60, alpha_range=(5, 60), beta_range=(5, 60), box="bfov", seed=21)
+    boxes[10:20, 2:] = 0.0                          # zero-area boxes ...
+    boxes[15:20, :2] = boxes[10:15, :2]             # ... five of them on top of five others
+    boxes[30] = boxes[31]                           # and an ordinary duplicate
+    scores = torch.linspace(0.95, 0.05, 60)
+    idxs = torch.zeros(60, dtype=torch.long)
+    cfg = dict(type="nms", iou_threshold=0.5)
+    want_dets, want_keep = O.planar_nms(boxes, scores, idxs, cfg)
+    dets, keep = PlanarNMS()(boxes.to(DEV), scores.to(DEV), idxs.to(DEV), cfg)
+    assert keep.cpu().tolist() == want_keep.tolist() and set(range(10, 20)) <= set(keep.cpu().tolist()) and 31 not in keep.cpu().tolist()
+    assert torch.equal(dets.cpu(), want_dets)
+    _, keep_sph = SphNMS("naive_iou")(boxes.to(DEV), scores.to(DEV), idxs.to(DEV), dict(iou_threshold=0.5))
+    assert not (set(range(15, 20)) & set(keep_sph.cpu().tolist())) and set(range(10, 15)) <= set(keep_sph.cpu().tolist())
+
+
+def test_batched_nms_images_hint_checks(api):
+    """The hinted path of sph_batched_nms_images: a segment longer than max_per_segment is NOT dropped (the call falls back
+    to the exact-length path), and a label outside [0, num_classes) raises instead of aliasing into the next image."""
+    B, n = 3, 300
+    boxes = O.generate_boxes(B * n, alpha_range=(5, 60), beta_range=(5, 60), box="bfov", seed=12).to(DEV)
+    scores = torch.rand(B * n, device=DEV)
+    labels = torch.randint(0, 4, (B * n,), device=DEV)
+    image_ids = torch.arange(B, device=DEV).repeat_interleave(n)
+    want = api.nms.sph_batched_nms_images(boxes, scores, labels, image_ids, 0.5)
+    short = api.nms.sph_batched_nms_images(boxes, scores, labels, image_ids, 0.5, num_images=B, num_classes=4, max_per_segment=40)
+    assert torch.equal(want, short)
+    valid = scores > 0.3
+    want_v = api.nms.sph_batched_nms_images(boxes, scores, labels, image_ids, 0.5, num_images=B, num_classes=4, max_per_segment=n, valid=valid)
+    short_v = api.nms.sph_batched_nms_images(boxes, scores, labels, image_ids, 0.5, num_images=B, num_classes=4, max_per_segment=40, valid=valid)
+    assert torch.equal(want_v, short_v) and bool(valid[want_v].all())
+    bad = labels.clone()
+    bad[5] = 4
+    with pytest.raises(ValueError):
+        api.nms.sph_batched_nms_images(boxes, scores, bad, image_ids, 0.5, num_images=B, num_classes=4, max_per_segment=n)
+
+
 # ---- unbiased_iou (the exact spherical IoU; SphOverlaps2D's default backend) and SphNMS('unbiased_iou') ---------------
 @pytest.mark.parametrize("box", ["bfov", "rbfov"])
 def test_unbiased_iou_golden(api, box):
