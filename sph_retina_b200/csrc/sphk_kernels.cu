@@ -69,7 +69,7 @@ int cuda_fail(cudaError_t e, const char* where) {
 // maximum instead of to the size of the call at hand: two host threads launching the same kernel with different sizes
 // can then never lower each other's limit between the attribute call and the launch.  TAG tells instances of one
 // function-pointer type apart.
-constexpr int kMaxDynamicSmem = 227 * 1024;
+constexpr int kMaxDynamicSmem = 200 * 1024;       // what the callers size their requests against
 template <int TAG, typename K>
 cudaError_t allow_max_dynamic_smem(K kernel) {
     static std::atomic<unsigned long long> done{0ull};
@@ -77,7 +77,13 @@ cudaError_t allow_max_dynamic_smem(K kernel) {
     cudaGetDevice(&dev);
     const unsigned long long bit = 1ull << (dev & 63);
     if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
-    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynamicSmem);
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
+    int optin = 0;
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e != cudaSuccess) return e;
+    // (the opt-in limit covers static + dynamic shared memory of the kernel)
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
     if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
     return e;
 }
@@ -2759,7 +2765,7 @@ int sphk_nms_images(const float* boxes, const float* scores, const int64_t* labe
     const int nt_img = Kp >= 1024 ? 1024 : Kp;
     const size_t smem_sc = (size_t)num_classes * 4, smem_col = (size_t)Kp * 8;
     if (smem_sc > (size_t)kMaxDynamicSmem || smem_col > (size_t)kMaxDynamicSmem)
-        return fail(SPHK_ERR_UNSUPPORTED, "sphk_nms_images: more than 58,000 classes; use sphk_nms_batched");
+        return fail(SPHK_ERR_UNSUPPORTED, "sphk_nms_images: more than 51,200 classes; use sphk_nms_batched");
     e = allow_max_dynamic_smem<0>(k_img_scatter);
     if (e == cudaSuccess) e = allow_max_dynamic_smem<1>(k_img_collect);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_img_scatter)");
