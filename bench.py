@@ -639,7 +639,7 @@ def run_ours(args):
 
         def kernel_call():      # the step without the exchange: k_box_pre + k_iou_pairwise2 into a communication block
             return native.iou_pairwise_keys("sph2pob_efficient", A_loc, G, row_base=lo, row_keys_out=_blk[:hi - lo], col_keys_out=_blk[_cap:])
-        kernel_name, kernels_per_step, pairs_per_kernel = "k_iou_pairwise2<5,32>", 1, pairs_per_step
+        kernel_name, kernels_per_step, pairs_per_kernel = "k_iou_pairwise2<5,32,2> (RBFoV, 32-row tiles, separating-axis stage)", 1, pairs_per_step
         rows_k, cols_k = A_loc, G
         scaling = "strong"
         hbm_bytes_per_kernel = (A_loc.size(0) + SWEEP_GTS) * (5 * 4 + 8)
@@ -783,7 +783,10 @@ def run_ours(args):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": workload,
-                       "api": "sharded_max_overlaps -> sphk_iou_pairwise_keys + sphk_unpack_gathered_keys (Sph2Pob-efficient, box_version 5)"
+                       "api": ("sharded_max_overlaps -> %s (Sph2Pob-efficient, box_version 5)" % (
+                                   "sphk_iou_pairwise_keys + sphk_unpack_gathered_keys" if world == 1 or exchange_route_name.startswith("nccl")
+                                   else ("sphk_iou_pairwise_keys_push + sphk_unpack_peer_keys" if exchange_route_name.startswith("peer:")
+                                         else "sphk_iou_pairwise_keys + sphk_unpack_peer_keys")))
                               if args.workload == "sweep" else "SphOverlaps2D('sph2pob_efficient_iou', box_version=5)",
                        "pairs_per_step": total_pairs_per_step,
                        "l2": "256 MB written between timed steps (L2 flush)",

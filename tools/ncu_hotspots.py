@@ -30,6 +30,13 @@ def main():
             cur["rows"].append(row)
     base_name = pat.split("<")[0]
     blk = [b for b in blocks if base_name in b["name"]][0]          # (ncu prints template arguments as "(int)5, (int)4")
+    if "<" not in pat and "<" in blk["name"]:
+        # the report names the instance ("k<(int)5, (int)32, (int)2>(...)"): count only that instance's SASS, not every
+        # template instance of the kernel that happens to share instruction offsets
+        args = re.findall(r"\(int\)(\d+)|\(bool\)(\w+)", blk["name"].split("(const")[0].split(">(")[0])
+        ints = [a if a else ("1" if b == "true" else "0") for a, b in args]
+        if ints and all(a for a, _ in args):
+            pat = "%s<%s>" % (pat, ",".join(ints))
     hdr = blk["hdr"]
     ia, ii, isamp = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("# Samples")
     base = int(blk["rows"][0][ia], 16)
