@@ -14,6 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsphk.so")
 TUNING_LIB_PATH = os.path.join(LIB_DIR, "libsphk_tuning.so")   # -DSPHK_TUNING: the A/B hooks of tools/ (never loaded by default)
+CHECKED_LIB_PATH = os.path.join(LIB_DIR, "libsphk_checked.so") # -DSPHK_CHECKED: ring invariants / index ranges become traps (tools/checked_run.sh)
 TIMELINE_LIB_PATH = os.path.join(LIB_DIR, "libsphk_tl.so")     # -DSPHK_TIMELINE: per-CTA / per-warp timestamps (tools/timeline_*.py)
 SOURCES = ["sphk_kernels.cu"]
 HEADERS = ["sphk_math.cuh", "sphk_fast.cuh", "sphk_grad.cuh", "sphk_coder.cuh", "sphk_obbloss.cuh", os.path.join("..", "..", "include", "sphk.h")]
@@ -79,6 +80,15 @@ def build(force: bool = False, verbose: bool = False, tuning: bool = False) -> s
     return target
 
 
+def build_checked() -> str:
+    """The twin whose shared-memory ring invariants and compacted-store index ranges trap (SPHK_CHECK in csrc/): loaded by
+    tools/checked_run.sh through SPHK_PROBE_LIB -- the stand-in for compute-sanitizer where that tool is not available."""
+    os.makedirs(LIB_DIR, exist_ok=True)
+    cmd = [find_nvcc()] + NVCC_FLAGS + ["-DSPHK_CHECKED", "-o", CHECKED_LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    subprocess.run(cmd, check=True)
+    return CHECKED_LIB_PATH
+
+
 def build_timeline() -> str:
     """The timestamp-instrumented twin (tools/timeline_probe.py, tools/timeline_aligned.py)."""
     os.makedirs(LIB_DIR, exist_ok=True)
@@ -88,6 +98,9 @@ def build_timeline() -> str:
 
 
 if __name__ == "__main__":
+    if "--checked" in sys.argv:
+        print(build_checked())
+        sys.exit(0)
     if "--timeline" in sys.argv:
         print(build_timeline())
         sys.exit(0)

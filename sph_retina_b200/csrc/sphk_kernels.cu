@@ -34,6 +34,16 @@ using namespace sphk;
 
 namespace {
 
+// -DSPHK_CHECKED (python -m sph_retina_b200.build --checked; tools/checked_run.sh): the invariants of the shared-memory
+// rings and the index ranges of every compacted store become traps.  compute-sanitizer is closed on the GPU pool this
+// was developed on, so these are the bounds checks "of our own": a violated invariant kills the launch with an error
+// instead of silently overwriting a neighbour's entry.  The product build compiles them away.
+#ifdef SPHK_CHECKED
+#define SPHK_CHECK(cond) do { if (!(cond)) { printf("SPHK_CHECK failed: %s (%s:%d) block %d thread %d\n", #cond, __FILE__, __LINE__, (int)blockIdx.x, (int)threadIdx.x); __trap(); } } while (0)
+#else
+#define SPHK_CHECK(cond) do { } while (0)
+#endif
+
 thread_local char g_err[256] = "";
 int g_dense = 0;   // sphk_set_dense: 1 = no disjoint-pair early-outs (measurement only)
 #ifdef SPHK_TUNING
@@ -320,6 +330,7 @@ k_iou_aligned2(const float* __restrict__ b1, const float* __restrict__ b2, int64
                 e[2] = make_float4(x.g, y.g, __int_as_float((k << 5) | lane), 0.0f);
             }
             tj += __popc(mj);
+            SPHK_CHECK(tj - hj <= kJobRing);
             ++k;
 #ifdef SPHK_TIMELINE
             tl_scan = tl_now();
@@ -344,11 +355,13 @@ k_iou_aligned2(const float* __restrict__ b1, const float* __restrict__ b2, int64
                 if (st == JOB_SLOW) st = pair_stage1_general(x, y, D, edge, !dense, &q);   // similarity mask / upper clamp: hi + lo form
                 if (st == JOB_READY) st = pair_stage2(q, D, kind, &job);
                 slow = st == JOB_SLOW;
+                SPHK_CHECK((((int64_t)(o2 >> 5) * nw + wg) << 5) + (o2 & 31) < P && o2 >= 0);
                 if (!slow) out[(((int64_t)(o2 >> 5) * nw + wg) << 5) + (o2 & 31)] = (st == JOB_DEAD) ? 0.0f : clip_job_iou(job, mode);
             }
             const unsigned ms = __ballot_sync(0xFFFFFFFFu, slow);
             if (slow) T.sidx[warp][(ts + __popc(ms & lt)) & (kSlowRing - 1)] = o2;
             ts += __popc(ms);
+            SPHK_CHECK(ts - hs <= kSlowRing);
             hj += cnt;
         }
         const bool drained = c >= chunks && tj == hj;
@@ -360,6 +373,7 @@ k_iou_aligned2(const float* __restrict__ b1, const float* __restrict__ b2, int64
             __syncwarp();
             if (lane < cnt) {
                 const int64_t p = (((int64_t)(o2 >> 5) * nw + wg) << 5) + (o2 & 31);
+                SPHK_CHECK(p >= 0 && p < P);
                 out[p] = slow_pair_iou(b1, p, b2, p, D, kind, mode, edge, dense);
             }
             hs += cnt;
@@ -734,6 +748,7 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
                 const unsigned m = __ballot_sync(0xFFFFFFFFu, live);
                 if (live) T.ring[warp][SAT ? 2 : 0][(ta + __popc(m & lt)) & (kRing - 1)] = (unsigned short)((r << 5) | lane);
                 ta += __popc(m);
+                SPHK_CHECK(ta - ha <= kRing);
                 ++r;
             }
             if (ta > ha) {                         // here: >= 32 candidates, or the rows are done
@@ -743,6 +758,7 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
                 __syncwarp();
                 bool live = false;
                 if (lane < cnt) {
+                    SPHK_CHECK((e >> 5) < nr);
                     const float4* g = T.rcull[e >> 5];
                     const float4* q = T.ccull[warp * 32 + (e & 31)];
                     const float4 g0 = g[0], g2 = g[2], g3 = g[3], q0 = q[0], q1 = q[1], q2 = q[2];
@@ -752,6 +768,7 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
                 const unsigned m = __ballot_sync(0xFFFFFFFFu, live);
                 if (live) T.ring[warp][0][(tf + __popc(m & lt)) & (kRing - 1)] = (unsigned short)e;
                 tf += __popc(m);
+                SPHK_CHECK(tf - hf <= kRing);
                 ha += cnt;
             }
         } else {
@@ -761,6 +778,7 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
                 const unsigned m = __ballot_sync(0xFFFFFFFFu, live);
                 if (live) T.ring[warp][0][(tf + __popc(m & lt)) & (kRing - 1)] = (unsigned short)((r << 5) | lane);
                 tf += __popc(m);
+                SPHK_CHECK(tf - hf <= kRing);
                 ++r;
             }
         }
@@ -771,8 +789,11 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
             const int e = T.ring[warp][0][(hf + lane) & (kRing - 1)];
             __syncwarp();
             bool slow = false;
-            if (lane < cnt) {
+            // (a row whose box is not finite fails no test of the scan -- NaN compares false -- and queues all 256 columns of
+            //  the tile, those past the end of the operand included: they are dropped here, not evaluated)
+            if (lane < cnt && o.c0 + warp * 32 + (e & 31) < C) {
                 const int rr = e >> 5, c = warp * 32 + (e & 31);
+                SPHK_CHECK(rr < nr && o.c0 + c < C);
                 float v;
                 slow = !pair_fast(load_rec(T.rrec, rr), load_rec(T.crec, c), D, kind, mode, &v);
                 if (!slow) emit_pair(T, o, rr, c, v);
@@ -780,6 +801,7 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
             const unsigned ms = __ballot_sync(0xFFFFFFFFu, slow);
             if (slow) T.ring[warp][1][(ts + __popc(ms & lt)) & (kRing - 1)] = (unsigned short)e;
             ts += __popc(ms);
+            SPHK_CHECK(ts - hs <= kRing);
             hf += cnt;
         }
         const bool drained = rows_done && tf == hf;
@@ -791,6 +813,7 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
             __syncwarp();
             if (lane < cnt) {
                 const int rr = e >> 5, c = warp * 32 + (e & 31);
+                SPHK_CHECK(rr < nr && o.c0 + c < C);
                 emit_pair(T, o, rr, c, slow_pair_iou(rows, o.r0 + rr, cols, o.c0 + c, D, kind, mode, edge, dense));
             }
             hs += cnt;
@@ -816,6 +839,7 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
             const long long at = push.off + (long long)ct * push.part_stride + o.r0;
             for (int j = tid; j < TR * push.world; j += kThreads) {
                 const int d = j / TR, i = j % TR;
+                SPHK_CHECK(d < push.world && (int64_t)ct * push.part_stride + o.r0 + i >= 0);
                 if (i < nr) T.peer[d][at + i] = T.rkey[i];
             }
         } else if (o.want_row && tid < nr) {
@@ -959,6 +983,7 @@ k_iou_rows32(const float* __restrict__ rows, int R, const float* __restrict__ co
             const unsigned m = __ballot_sync(0xFFFFFFFFu, live);
             if (live) T.ring[warp][0][(tf + __popc(m & lt)) & (kRing - 1)] = (unsigned short)((r << 5) | lane);
             tf += __popc(m);
+            SPHK_CHECK(tf - hf <= kRing);
             ++r;
         }
         const bool rows_done = r >= r_hi;
@@ -968,8 +993,9 @@ k_iou_rows32(const float* __restrict__ rows, int R, const float* __restrict__ co
             const int e = T.ring[warp][0][(hf + lane) & (kRing - 1)];
             __syncwarp();
             bool slow = false;
-            if (lane < cnt) {
+            if (lane < cnt && c0 + cg * 32 + (e & 31) < C) {      // (columns past the end, queued by a non-finite row, are dropped)
                 const int rr = e >> 5, c = cg * 32 + (e & 31);
+                SPHK_CHECK(rr >= r_lo && rr < r_hi && c0 + c < C);
                 float v;
                 slow = !pair_fast(load_rec(T.rrec, rr), load_rec(T.crec, c), D, kind, mode, &v);
                 if (!slow) out[rr * ld + c0 + c] = v;
@@ -977,6 +1003,7 @@ k_iou_rows32(const float* __restrict__ rows, int R, const float* __restrict__ co
             const unsigned ms = __ballot_sync(0xFFFFFFFFu, slow);
             if (slow) T.ring[warp][1][(ts + __popc(ms & lt)) & (kRing - 1)] = (unsigned short)e;
             ts += __popc(ms);
+            SPHK_CHECK(ts - hs <= kRing);
             hf += cnt;
         }
         const bool drained = rows_done && tf == hf;
@@ -988,6 +1015,7 @@ k_iou_rows32(const float* __restrict__ rows, int R, const float* __restrict__ co
             __syncwarp();
             if (lane < cnt) {
                 const int rr = e >> 5, c = cg * 32 + (e & 31);
+                SPHK_CHECK(rr >= r_lo && rr < r_hi && c0 + c < C);
                 out[rr * ld + c0 + c] = slow_pair_iou(rows, rr, cols, c0 + c, D, kind, mode, edge, dense);
             }
             hs += cnt;
@@ -1601,6 +1629,7 @@ k_decode_loss(const float* __restrict__ anchors, const float* __restrict__ delta
                 s_w[warp][slot] = w;
             }
             tail += __popc(m);
+            SPHK_CHECK(tail - head <= kLossRing);
             c += nw;
         }
         if (tail == head) break;                 // chunks used up and nothing queued
@@ -1610,6 +1639,7 @@ k_decode_loss(const float* __restrict__ anchors, const float* __restrict__ delta
         const float w = s_w[warp][(head + lane) & (kLossRing - 1)];
         __syncwarp();
         if (lane < cnt) {
+            SPHK_CHECK(row >= 0 && row < n);
             const RawBox roi = load_box<D>(anchors, row, false), dl = load_box<D>(deltas, row, false);
             const RawBox tg = load_box<D>(target, row, false);
             const float d[5] = {dl.t, dl.p, dl.a, dl.b, dl.g};

@@ -214,6 +214,20 @@ def test_non_finite_and_out_of_range_inputs_do_not_poison_neighbours(api):
     assert torch.equal(mat[rows_ok], ref[rows_ok])
     fin = torch.isfinite(mat[~rows_ok])
     assert bool(((mat[~rows_ok][fin] >= 0) & (mat[~rows_ok][fin] <= 1)).all())
+    # A non-finite ROW box fails no test of the N x M scan loops (NaN compares false) and queues every column of its tile,
+    # those past the end of a ragged last tile included: they must be dropped, not evaluated (they would read past the end
+    # of bboxes2 and write into the next row / past the end of the matrix).  Last row = the bad one, both kernels
+    # (k_iou_rows32: R <= 32; k_iou_pairwise2: R > 32), C not a multiple of the tile widths; the checked build
+    # (tools/checked_run.sh, -DSPHK_CHECKED) turns a violation into a trap.
+    for R in (20, 64):
+        bad = b1[:R].clone()
+        bad[R - 1] = float("nan"); bad[3, 1] = float("inf")
+        ok_rows = torch.ones(R, dtype=torch.bool, device=DEV); ok_rows[R - 1] = False; ok_rows[3] = False
+        for C in (600, 601, 1, 257):
+            m = api.iou.sph2pob_efficient_iou(bad, b2[:C])
+            assert m.shape == (R, C) and torch.equal(m[ok_rows], api.iou.sph2pob_efficient_iou(b1[:R], b2[:C])[ok_rows])
+            rmax, rarg, cmax, carg = api.iou.sph_max_overlaps(bad, b2[:C])
+            assert rmax.shape == (R,) and cmax.shape == (C,)
 
 
 # ---- pairwise ----------------------------------------------------------------------------------
