@@ -1131,6 +1131,7 @@ k_unpack_gathered(const unsigned long long* __restrict__ gathered, int world, in
         const int64_t cut = extra * (base + 1);                   // rows owned by the shards that hold base + 1 rows
         const int64_t s = (i < cut) ? i / (base + 1) : extra + (i - cut) / (base > 0 ? base : 1);
         const int64_t lo = s * base + (s < extra ? s : extra);
+        SPHK_CHECK(s >= 0 && s < world && i - lo >= 0 && i - lo < cap);
         k = gathered[s * stride + (i - lo)];
         long_max[i] = (k == 0ull) ? 0.0f : __uint_as_float((uint32_t)(k >> 32));
         long_arg[i] = (k == 0ull) ? 0 : (int64_t)(0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull));
@@ -1216,6 +1217,7 @@ k_unpack_peers(unsigned long long* const* __restrict__ peer_bufs, int rank, int 
         if (i < n_long) {
             const int64_t s = (i < cut) ? i / (base + 1) : extra + (i - cut) / (base > 0 ? base : 1);
             const int64_t lo = s * base + (s < extra ? s : extra);
+            SPHK_CHECK(s >= 0 && s < world && i - lo >= 0 && i - lo < cap);
             const unsigned long long* src = (long_pushed ? local + s * stride : s_blk[s]) + (i - lo);
             k = __ldcg(src);
             for (int t = 1; t < parts; ++t) {                       // push: one partial array per column tile of the compute kernel

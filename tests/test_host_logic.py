@@ -134,6 +134,22 @@ def test_shard_bounds_cover_and_balance():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_sharded_call_validates_its_arguments_before_any_launch():
+    """sharded_max_overlaps refuses a shard that is not the rank's contiguous slice and an unknown exchange route; the
+    push route's partial-array count follows the kernel's 256-column tiles (one key array per column tile)."""
+    from sph_retina_b200 import _native
+    from sph_retina_b200.sharded import MAX_PUSH_PARTS, sharded_max_overlaps
+    a, g = torch.zeros(10, 5), torch.zeros(4, 5)
+    with pytest.raises(ValueError):
+        sharded_max_overlaps(a, g, 10, 3)                          # world = 1: the shard must start at row 0
+    with pytest.raises(ValueError):
+        sharded_max_overlaps(a, g, 12, 0)                          # ... and hold all rows
+    with pytest.raises(ValueError):
+        sharded_max_overlaps(a, g, 10, 0, exchange='smoke-signals')
+    assert [_native.key_push_parts(c) for c in (0, 1, 256, 257, 1024, 2048, 2049)] == [1, 1, 1, 2, 4, 8, 9]
+    assert MAX_PUSH_PARTS == 8
+
+
 def test_weight_reduce_matches_mmdet_rules():
     from sph_retina_b200.sphdet.losses.sph2pob_iou_loss import _weight_reduce_loss
     loss, w = torch.tensor([1.0, 2.0, 3.0]), torch.tensor([1.0, 0.0, 1.0])
