@@ -126,18 +126,6 @@ SPHK_HD bool pre_outside_box(const BoxCull& g, const BoxCull& p) {
     return pre_outside_box(g.ex, g.ey, g.ez, g.hwm, g.fx, g.fy, g.fz, g.hhm, p.ux, p.uy, p.uz, p.r);
 }
 
-// 1/sqrt(x) to ~1 ulp (MUFU.RSQ): used to normalise (cos, sin) pairs and for the conservative cull radius, where
-// a 2e-7 relative error is immaterial (rsqrtf() without fast-math adds a dozen instructions of special-case handling)
-SPHK_HD float rsqrt_f(float x) {
-#if defined(__CUDA_ARCH__)
-    float r;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-#else
-    return 1.0f / sqrtf(x);
-#endif
-}
-
 // Separating-axis test on the two planar boxes, from the per-box records alone (no arc, no atan2, no sincos).
 // Sph2Pob lays the boxes out along the great circle through their centres: in the frame of box g the centre of p sits
 // at arc * (cos a1, -sin a1), and p is turned by r = a2 - a1 against g, with a1 / a2 the bearings of the partner seen

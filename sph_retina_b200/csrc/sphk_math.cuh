@@ -241,7 +241,43 @@ SPHK_HD float signed_clamped_angle(float n, float m, bool* clamped) {
     return n > 0.0f ? c : -c;
 }
 
-SPHK_HD float arc_from_hav(float hav) { return 2.0f * asinf(fminf(sqrtf(hav), 1.0f)); }
+// 1/sqrt(x) to ~1 ulp (MUFU.RSQ): used to normalise (cos, sin) pairs and for the conservative cull radius, where
+// a 2e-7 relative error is immaterial (rsqrtf() without fast-math adds a dozen instructions of special-case handling)
+SPHK_HD float rsqrt_f(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
+
+// arc = 2 asin(sqrt(hav)) for hav = sin^2(arc / 2) in [0, 1], without sqrtf / asinf (IEEE square root + the library
+// arcsine cost 38 instructions per pair, 4 % of the N x M kernels): with z = min(hav, 1 - hav) <= 1/2 (1 - hav is exact
+// for hav > 1/2) and s = sqrt(z) from MUFU.RSQ + one Newton step,
+//     asin(s) = s + s z P(z)      (P: degree-6 minimax fit of (asin(sqrt z) / sqrt z - 1) / z on [0, 1/2], 5e-8 relative),
+// arc = 2 asin(s) for hav <= 1/2, pi - 2 asin(s) above (pi as hi + lo).  Measured against float64 on 3 M values
+// (uniform and log-uniform hav): <= 1.75 ulp, 0.38 ulp on average.  hav a rounding error above 1 gives pi, as
+// min(sqrt(hav), 1) did; NaN stays NaN.
+SPHK_HD float arc_from_hav(float hav) {
+    const bool big = hav > 0.5f;
+    float z = big ? 1.0f - hav : hav;
+    z = (z < 1e-30f) ? 1e-30f : z;
+    const float y = rsqrt_f(z);
+    const float s0 = z * y;
+    const float s = fmaf(fmaf(-s0, s0, z), 0.5f * y, s0);
+    float p = 0.12372123607510499f;
+    p = fmaf(p, z, -0.11530392646856973f);
+    p = fmaf(p, z, 0.09340074622705977f);
+    p = fmaf(p, z, 0.010430741612056323f);
+    p = fmaf(p, z, 0.04762428807115189f);
+    p = fmaf(p, z, 0.07478349097117638f);
+    p = fmaf(p, z, 0.16667234492246794f);
+    const float a = fmaf(s * z, p, s);
+    const float two = a + a;
+    return big ? (3.14159274f - two) + -8.74227766e-8f : two;
+}
 
 struct XformAux {     // what the backward pass needs to know about active clamps
     bool arc_clamped, ag_clamped, ap_clamped, degenerate;
