@@ -254,12 +254,10 @@ SPHK_HD int pair_job(const BoxRec& g, const BoxRec& p, int D, int kind, bool cul
     bool sim = (fabsf(g.t - p.t) < kEps) | (fabsf(g.p - p.p) < kEps) | (fabsf(g.a - p.a) < kEps) | (fabsf(g.b - p.b) < kEps);
     if (D == 5) sim = sim | (fabsf(g.g - p.g) < kEps);
     if (sim) return JOB_SLOW;
-    float sdt, cdt, sdp, cdp;
-    sincos_deg(0.5f * (p.tj - g.tj), 0.0f, &sdt, &cdt);
-    sincos_deg(0.5f * (p.pj - g.pj), 0.0f, &sdp, &cdp);
-    const float hth = sdt * sdt;
-    const float sin_dth = 2.0f * sdt * cdt, sin_dph = 2.0f * sdp * cdp;
-    const float hav = fmaf(g.sp * p.sp, hth, sdp * sdp);
+    float hth, sin_dth, hph, sin_dph;       // sin^2(dtheta / 2), sin(dtheta), sin^2(dphi / 2), sin(dphi)
+    sin2_and_sin_double_deg(0.5f * (p.tj - g.tj), &hth, &sin_dth);
+    sin2_and_sin_double_deg(0.5f * (p.pj - g.pj), &hph, &sin_dph);
+    const float hav = fmaf(g.sp * p.sp, hth, hph);
     const float arc = arc_from_hav(hav);
     // outside: the acos clamp zone of the arc and jitter_2's |x1 - x2| < eps
     if (!(arc > 2e-3f && arc < 3.14f)) return JOB_SLOW;

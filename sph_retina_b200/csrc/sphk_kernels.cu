@@ -477,7 +477,7 @@ k_iou_pairwise(const float* __restrict__ rows, int64_t R, const float* __restric
 // Pairs that need the reference-order path (rare) are compacted once more into a second ring.
 // Row / column max+argmax are reduced in shared memory and merged into the global packed keys with
 // one atomicMax per row / column and CTA.
-constexpr int kTC = 256, kRing = 64, kRecStride = 20;   // record stride 20 words: conflict-free LDS.128 across lanes
+constexpr int kTC = 256, kRing = 64, kCand = 128, kRecStride = 20;   // record stride 20 words: conflict-free LDS.128 across lanes
 
 template <int TR, bool SAT>
 struct PairTile {
@@ -487,7 +487,8 @@ struct PairTile {
     float4 ccull[SAT ? kTC : 1][3];      // separating-axis stage: centre, width axis + half width, height axis + half height per column
     unsigned long long rkey[TR];
     unsigned long long ckey[kTC];
-    unsigned short ring[kThreads / 32][SAT ? 3 : 2][kRing];   // 0: pairs for the clipper, 1: reference-order path, 2: circle-test survivors
+    unsigned short ring[kThreads / 32][2][kRing];             // 0: pairs for the clipper, 1: reference-order path
+    unsigned short cand[SAT ? kThreads / 32 : 1][kCand];      // separating-axis stage: the circle test's survivors (two rows per scan step)
     float rtgt[TR];      // tie pass: the row maxima to compare with
     int ctie[kTC];       // tie pass: per column, the largest (row index + 1) that ties its row maximum
     unsigned long long* peer[16];   // push route: the ranks' buffers (fetched during phase 0, used in the epilogue)
@@ -742,19 +743,31 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
 #pragma unroll 1
     for (;;) {
         if (SAT) {
+            unsigned short* const cand = T.cand[SAT ? warp : 0];
+            // two rows per step (<= 31 queued + 64 pushed <= kCand), then the odd last row
 #pragma unroll 1
-            while (r < nr && ta - ha < 32) {
+            while (r + 1 < nr && ta - ha < 32) {
+                const bool l0 = prefilter_live<false>(T.rcull[r], pc0, pc1.x, pbias, pr);
+                const bool l1 = prefilter_live<false>(T.rcull[r + 1], pc0, pc1.x, pbias, pr);
+                const unsigned m0 = __ballot_sync(0xFFFFFFFFu, l0), m1 = __ballot_sync(0xFFFFFFFFu, l1);
+                const int n0 = __popc(m0);
+                if (l0) cand[(ta + __popc(m0 & lt)) & (kCand - 1)] = (unsigned short)((r << 5) | lane);
+                if (l1) cand[(ta + n0 + __popc(m1 & lt)) & (kCand - 1)] = (unsigned short)(((r + 1) << 5) | lane);
+                ta += n0 + __popc(m1);
+                SPHK_CHECK(ta - ha <= kCand);
+                r += 2;
+            }
+            if (r + 1 == nr && ta - ha < 32) {
                 const bool live = prefilter_live<false>(T.rcull[r], pc0, pc1.x, pbias, pr);
                 const unsigned m = __ballot_sync(0xFFFFFFFFu, live);
-                if (live) T.ring[warp][SAT ? 2 : 0][(ta + __popc(m & lt)) & (kRing - 1)] = (unsigned short)((r << 5) | lane);
+                if (live) cand[(ta + __popc(m & lt)) & (kCand - 1)] = (unsigned short)((r << 5) | lane);
                 ta += __popc(m);
-                SPHK_CHECK(ta - ha <= kRing);
                 ++r;
             }
             if (ta > ha) {                         // here: >= 32 candidates, or the rows are done
                 const int cnt = min(ta - ha, 32);
                 __syncwarp();
-                const int e = T.ring[warp][SAT ? 2 : 0][(ha + lane) & (kRing - 1)];
+                const int e = cand[(ha + lane) & (kCand - 1)];
                 __syncwarp();
                 bool live = false;
                 if (lane < cnt) {

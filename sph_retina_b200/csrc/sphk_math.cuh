@@ -194,6 +194,25 @@ SPHK_HD void sincos_deg(float hi, float lo, float* s, float* c) {
     *c = ((q + 1) & 2) ? -b : b;
 }
 
+// sin^2(x) and sin(2 x) of an angle x given in degrees: what the haversine formulation needs of the HALF differences of
+// the centres (hav = s1 s2 sin^2(dt/2) + sin^2(dp/2); sin dt, sin dp for the bearings).  Same reduction and the same
+// polynomials as sincos_deg, bit-identical to (s * s, (2 s) * c) of its outputs, without assembling the signs of s and c
+// separately: sign(s) sign(c) is negative exactly in the odd quadrants.
+SPHK_HD void sin2_and_sin_double_deg(float x, float* s2, float* sin2x) {
+    const float k = rintf(x * (1.0f / 90.0f));
+    const float y = fmaf(-90.0f, k, x) + 0.0f;
+    const float r = y * kDeg2Rad;
+    const float z = r * r;
+    const float ps = fmaf(fmaf(fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f), z, -1.6666654611e-1f) * z, r, r);
+    const float pc = fmaf(fmaf(fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f), z, 4.166664568298827e-2f),
+                          z * z, fmaf(-0.5f, z, 1.0f));
+    const bool odd = (((int)k) & 1) != 0;
+    const float a = odd ? pc : ps, b = odd ? ps : pc;
+    *s2 = a * a;
+    const float t = (2.0f * a) * b;
+    *sin2x = odd ? -t : t;
+}
+
 // planar edge length of a field-of-view angle (degrees in), sph2pob_efficient.py:100-108.
 // chord/tangent go through the degree-domain sincos so that 2 tan(alpha/2) stays accurate for
 // alpha -> 180 (oversize anchors are clamped to 180 - eps by jitter_1).
