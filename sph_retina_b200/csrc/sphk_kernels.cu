@@ -699,7 +699,12 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
     if (col_ok) {
         const float4* u = cull + (R + o.c0 + tid) * 4;
         pc0 = __ldg(u); pc1 = __ldg(u + 1);
-        if (SAT) { T.ccull[tid][0] = pc0; T.ccull[tid][1] = __ldg(u + 2); T.ccull[tid][2] = __ldg(u + 3); }
+        if (SAT) {
+            // (dense, the measurement mode: half sizes of 10 switch the separating-axis test off, as for flagged boxes)
+            float4 e2 = __ldg(u + 2), f2 = __ldg(u + 3);
+            if (dense) { e2.w = 10.0f; f2.w = 10.0f; }
+            T.ccull[tid][0] = pc0; T.ccull[tid][1] = e2; T.ccull[tid][2] = f2;
+        }
     }
     if (tid < TR) {
         const bool ok = tid < nr;
@@ -775,7 +780,7 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
                     const float4* g = T.rcull[e >> 5];
                     const float4* q = T.ccull[warp * 32 + (e & 31)];
                     const float4 g0 = g[0], g2 = g[2], g3 = g[3], q0 = q[0], q1 = q[1], q2 = q[2];
-                    live = dense || !pre_sat_disjoint(g0.x, g0.y, g0.z, g2.x, g2.y, g2.z, g2.w, g3.x, g3.y, g3.z, g3.w,
+                    live = !pre_sat_disjoint(g0.x, g0.y, g0.z, g2.x, g2.y, g2.z, g2.w, g3.x, g3.y, g3.z, g3.w,
                                                       q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w);
                 }
                 const unsigned m = __ballot_sync(0xFFFFFFFFu, live);
@@ -812,9 +817,11 @@ k_iou_pairwise2(const float* __restrict__ rows, int64_t R, const float* __restri
                 if (!slow) emit_pair(T, o, rr, c, v);
             }
             const unsigned ms = __ballot_sync(0xFFFFFFFFu, slow);
-            if (slow) T.ring[warp][1][(ts + __popc(ms & lt)) & (kRing - 1)] = (unsigned short)e;
-            ts += __popc(ms);
-            SPHK_CHECK(ts - hs <= kRing);
+            if (ms) {                                   // (1 pair in 10^5 on random boxes: keep the push out of the common path)
+                if (slow) T.ring[warp][1][(ts + __popc(ms & lt)) & (kRing - 1)] = (unsigned short)e;
+                ts += __popc(ms);
+                SPHK_CHECK(ts - hs <= kRing);
+            }
             hf += cnt;
         }
         const bool drained = rows_done && tf == hf;
@@ -1014,9 +1021,11 @@ k_iou_rows32(const float* __restrict__ rows, int R, const float* __restrict__ co
                 if (!slow) out[rr * ld + c0 + c] = v;
             }
             const unsigned ms = __ballot_sync(0xFFFFFFFFu, slow);
-            if (slow) T.ring[warp][1][(ts + __popc(ms & lt)) & (kRing - 1)] = (unsigned short)e;
-            ts += __popc(ms);
-            SPHK_CHECK(ts - hs <= kRing);
+            if (ms) {                                   // (1 pair in 10^5 on random boxes: keep the push out of the common path)
+                if (slow) T.ring[warp][1][(ts + __popc(ms & lt)) & (kRing - 1)] = (unsigned short)e;
+                ts += __popc(ms);
+                SPHK_CHECK(ts - hs <= kRing);
+            }
             hf += cnt;
         }
         const bool drained = rows_done && tf == hf;
