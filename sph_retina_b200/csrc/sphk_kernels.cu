@@ -927,7 +927,7 @@ k_iou_rows32(const float* __restrict__ rows, int R, const float* __restrict__ co
              float* __restrict__ out, int64_t ld, int flags, bool rows_vec, bool cols_vec) {
     __shared__ __align__(16) RowsTile T;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool dense = (flags & 1) != 0, boxcull = (flags & 2) == 0;
+    const bool dense = (flags & 1) != 0;
 #ifdef SPHK_TIMELINE
     unsigned long long tl0 = 0;
     if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl0));
