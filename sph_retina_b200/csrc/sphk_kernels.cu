@@ -520,9 +520,12 @@ template <int D>
 __global__ void __launch_bounds__(kThreads)
 k_box_pre(const float* __restrict__ rows, int64_t R, const float* __restrict__ cols, int64_t C, int edge,
           float4* __restrict__ rec, float4* __restrict__ cull, bool rows_vec, bool cols_vec,
-          unsigned long long* __restrict__ zero_rkey, unsigned long long* __restrict__ zero_ckey, bool rows_inline) {
+          unsigned long long* __restrict__ zero_rkey, unsigned long long* __restrict__ zero_ckey, bool rows_inline,
+          int64_t first) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // k_iou_pairwise2 may start its prologue
-    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    // (first = R when the rows need nothing from this launch -- records computed in the tile kernel, keys pushed, not
+    //  merged: the grid then covers the columns only)
+    const int64_t i = first + (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (i >= R + C) return;
     const bool is_row = i < R;
     // the packed max / argmax keys of the same call start from "nothing seen" (one key per box: no launch of its own)
@@ -2156,8 +2159,11 @@ static int launch_pairwise2(int kind, const float* rows, int64_t R, const float*
     unsigned long long* zr = (zero_keys && batch == 1 && !(keep_keys & 1)) ? rkey : nullptr;
     unsigned long long* zc = (zero_keys && batch == 1 && !(keep_keys & 2)) ? ckey : nullptr;
     if ((g_probe & 1) || records_ready) {      // (records_ready: a second pass over the operands of the previous launch)
-    } else if (D == 4) k_box_pre<4><<<blocks_for(R + C), kThreads, 0, s>>>(rows, R, cols, C, edge, rec, cull, aligned16(rows), aligned16(cols), zr, zc, rows_inline);
-    else k_box_pre<5><<<blocks_for(R + C), kThreads, 0, s>>>(rows, R, cols, C, edge, rec, cull, false, false, zr, zc, rows_inline);
+    } else {
+        const int64_t first = (rows_inline && zr == nullptr) ? R : 0;
+        if (D == 4) k_box_pre<4><<<blocks_for(R + C - first), kThreads, 0, s>>>(rows, R, cols, C, edge, rec, cull, aligned16(rows), aligned16(cols), zr, zc, rows_inline, first);
+        else k_box_pre<5><<<blocks_for(R + C - first), kThreads, 0, s>>>(rows, R, cols, C, edge, rec, cull, false, false, zr, zc, rows_inline, first);
+    }
     // row-tile height: 32 when that already yields many CTAs per SM, else 8 so that the heavy
     // (mostly-live) tiles are spread over more warps and the tail of the launch stays short
     const int64_t tiles32 = col_tiles * ((max_rows + 31) / 32) * batch;
@@ -2885,8 +2891,8 @@ int sphk_prefilter_count(const float* rows, int64_t R, const float* cols, int64_
     if (row_tiles > 0x7FFFFFFFll || col_tiles > 65535) return fail(SPHK_ERR_UNSUPPORTED, "sphk_prefilter_count: grid too large; shard the call");
     float4* rec = (float4*)((char*)workspace + keys_bytes(R, C));
     float4* cull = rec + (R + C) * 4;
-    if (D == 4) k_box_pre<4><<<blocks_for(R + C), kThreads, 0, s>>>(rows, R, cols, C, edge, rec, cull, aligned16(rows), aligned16(cols), nullptr, nullptr, false);
-    else k_box_pre<5><<<blocks_for(R + C), kThreads, 0, s>>>(rows, R, cols, C, edge, rec, cull, false, false, nullptr, nullptr, false);
+    if (D == 4) k_box_pre<4><<<blocks_for(R + C), kThreads, 0, s>>>(rows, R, cols, C, edge, rec, cull, aligned16(rows), aligned16(cols), nullptr, nullptr, false, 0);
+    else k_box_pre<5><<<blocks_for(R + C), kThreads, 0, s>>>(rows, R, cols, C, edge, rec, cull, false, false, nullptr, nullptr, false, 0);
     k_prefilter_count<<<dim3((unsigned)row_tiles, (unsigned)col_tiles), kThreads, 0, s>>>(R, C, cull, (unsigned long long*)live_count,
                                                                                           box_test_pays(R, C) ? (g_no_boxcull ? 0 : 1) : (g_no_sat ? 0 : 2));
     SPHK_LAUNCH_CHECK("k_prefilter_count");
