@@ -8,8 +8,13 @@ pairwise Sph2Pob-efficient IoU of 1,048,576 x 1,024 random RBFoV boxes (1.07 G p
 per-GT max/argmax -- the reduction MaxIoUAssigner applies to the matrix (mmdet/core/bbox/assigners/max_iou_assigner.py:
 173-176) -- through ``sph_retina_b200.sharded.sharded_max_overlaps``.  One "step" = the whole sweep.  With N > 1
 (torchrun, one rank per GPU) the anchors are row-sharded over the ranks, the 1,024 GT replicated, and the timed step
-contains the NCCL all_gather of the packed keys and the unpack launch: STRONG scaling, total work fixed.  N = 1 runs the
-very same code path (the collective degenerates to a view).  ``--workload assign`` is configs[1] (16 per-image
+contains the exchange of the packed keys (pushed into the peers' symmetric buffers over NVLink by the compute kernel, or
+one NCCL all_gather where symmetric memory is unavailable) and the unpack launch: STRONG scaling, total work fixed.  N = 1
+runs the very same code path (the exchange degenerates to a view).  Timing: W untimed steps, synchronize + barrier, then
+K timed steps, each with its own CUDA-event pair on the launching stream (the 256 MB L2 flush between steps sits outside
+the spans), synchronize + barrier; the sum over the K steps, maximum over the ranks.  With N > 1 two further untimed steps
+are enqueued between the barrier and the first timed step, so that every host thread is ahead of its GPU before the
+first timed handshake between the GPUs (a rank leaving the barrier late would otherwise be timed by all the others).  ``--workload assign`` is configs[1] (16 per-image
 ``SphOverlaps2D`` calls of 32 GT x 98,208 anchors, full matrices written; replicas, weak scaling); it is also timed
 briefly under ``other_configs`` of the default run, as are configs[0], [2], [3].
 
@@ -174,6 +179,9 @@ print(json.dumps({"sm": sm, "mask": mask, "power": power,
                 "power_w_max": max(self.power) if self.power else None}
 
 
+LEAD_IN = 2      # multi-GPU runs: untimed steps between the barrier and the first timed step (time_steps)
+
+
 def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
@@ -186,13 +194,20 @@ class L2Flusher:
         self.buf.zero_()
 
 
-def time_steps(torch, step, steps, warmup, flush, barrier):
+def time_steps(torch, step, steps, warmup, flush, barrier, lead_in=0):
     """W untimed + K timed steps; each timed step has its own CUDA-event pair on the launching stream, the L2
-    flush between steps sits outside the timed spans.  Returns per-step ms."""
+    flush between steps sits outside the timed spans.  Returns per-step ms.
+    lead_in: untimed steps enqueued AFTER the barrier, back to back with the timed ones.  A multi-rank step ends with a
+    handshake between the GPUs, so a rank whose host thread leaves the barrier a millisecond late would make every other
+    GPU wait inside its first timed step; after the lead-in steps every host is several steps ahead of its GPU and the
+    timed spans hold device work only."""
     for _ in range(warmup):
         step()
     torch.cuda.synchronize()
     barrier()
+    for _ in range(lead_in):
+        flush()
+        step()
     evs = []
     for _ in range(steps):
         flush()
@@ -653,7 +668,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     l0 = native.launches
     sampler.start()
-    ms = time_steps(torch, step, args.steps, 0, flush, barrier)
+    ms = time_steps(torch, step, args.steps, 0, flush, barrier, lead_in=LEAD_IN if world > 1 else 0)
     clocks = sampler.stop()
     gpu_launches = native.launches - l0
     total_ms = max_over_ranks(sum(ms))
@@ -724,7 +739,7 @@ def run_ours(args):
             # pipelined over row chunks; per-GT keys exchanged between the ranks) -> the per-anchor result of its shard and
             # the global per-GT result in pinned host memory: across the ranks the host holds the whole result exactly once
             hs(A_pin, G_pin, lo, amax_pin, aarg_pin, gmax_pin, garg_pin)
-        e2e_ms = time_steps(torch, e2e_step, max(5, args.steps // 2), 3, flush, barrier)
+        e2e_ms = time_steps(torch, e2e_step, max(5, args.steps // 2), 3, flush, barrier, lead_in=LEAD_IN if world > 1 else 0)
         t = max_over_ranks(statistics.mean(e2e_ms))
         e2e = {"value": total_pairs_per_step / (t * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": SWEEP_ANCHORS * 20 + world * SWEEP_GTS * 20,
@@ -790,7 +805,9 @@ def run_ours(args):
                               if args.workload == "sweep" else "SphOverlaps2D('sph2pob_efficient_iou', box_version=5)",
                        "pairs_per_step": total_pairs_per_step,
                        "l2": "256 MB written between timed steps (L2 flush)",
-                       "timing": "CUDA events per step on the launching stream, sum over K steps, max over ranks",
+                       "timing": "CUDA events per step on the launching stream, sum over K steps, max over ranks"
+                                 + ("; %d untimed lead-in steps follow the barrier (host threads ahead of the GPUs before the first "
+                                    "timed handshake)" % LEAD_IN if world > 1 else ""),
                        "exchange": exchange_route_name,
                        "collectives_per_step": (1 if exchange_route_name == "nccl" else 0)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches,
