@@ -2189,7 +2189,8 @@ static int launch_pairwise2(int kind, const float* rows, int64_t R, const float*
     const int dn = (g_dense != 0 ? 1 : 0) | (rows_inline ? 4 : 0);
     // which instance: with the box-frame prefilter test in the scan loop (rows = the short, large-box operand: ground
     // truths x anchors), or with the separating-axis stage behind the circle test (everything else: operands of similar size)
-    const int cull_kind = box_test_pays(max_rows, C) ? (g_no_boxcull ? 0 : 1) : (g_no_sat ? 0 : 2);
+    // (the measurement mode -- sphk_set_dense: no early-out anywhere -- runs the instance without either stage)
+    const int cull_kind = g_dense ? 0 : (box_test_pays(max_rows, C) ? (g_no_boxcull ? 0 : 1) : (g_no_sat ? 0 : 2));
     const KeyPush kp = push ? *push : KeyPush{nullptr, 0, 0, 1};
     cudaError_t le;
     auto go = [&](auto kernel, const char* what) {
