@@ -62,6 +62,21 @@ void hostsim_iou_aligned_v2(int kind, const float* b1, const float* b2, long P, 
     }
 }
 
+// Scalar building blocks of the fast path: arc = 2 asin(sqrt(hav)) (polynomial, no sqrtf / asinf), and the half-difference
+// terms of pair_job next to what sincos_deg gives for the same angle (they must be the same bits).
+void hostsim_arc_from_hav(const float* hav, long n, float* arc) {
+    for (long i = 0; i < n; ++i) arc[i] = arc_from_hav(hav[i]);
+}
+void hostsim_half_angle_terms(const float* x_deg, long n, float* s2, float* sin2x, float* s2_ref, float* sin2x_ref) {
+    for (long i = 0; i < n; ++i) {
+        sin2_and_sin_double_deg(x_deg[i], &s2[i], &sin2x[i]);
+        float s, c;
+        sincos_deg(x_deg[i], 0.0f, &s, &c);
+        s2_ref[i] = s * s;
+        sin2x_ref[i] = 2.0f * s * c;
+    }
+}
+
 // Prefilter verdicts next to the reference-order IoU computed WITHOUT any early-out (dense = true): cull[i] bit 0 = circle
 // test, bit 1 = box-frame test (row = box 1), bit 2 = separating-axis test.  A culled pair must have dense IoU exactly 0.
 void hostsim_prefilter(int kind, const float* b1, const float* b2, long P, int D, int mode, int edge, float* dense_iou,

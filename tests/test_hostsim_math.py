@@ -348,6 +348,40 @@ def near_sat_border_pairs(n, seed, spread=0.06):
     return b1, b2
 
 
+def test_arc_from_hav_polynomial_against_float64(hostsim):
+    """arc_from_hav (z = min(hav, 1 - hav), rsqrt + one Newton step, degree-6 polynomial; csrc/sphk_math.cuh) against
+    2 asin(sqrt(hav)) in float64: uniform and log-uniform hav, the ends of the range, values a rounding error above 1."""
+    rng = np.random.RandomState(0)
+    hav = np.concatenate([rng.uniform(0, 1, 1_000_000), 10.0 ** rng.uniform(-12, 0, 500_000), 1 - 10.0 ** rng.uniform(-8, 0, 500_000),
+                          [0.0, 1.0, 0.5, np.nextafter(np.float32(0.5), np.float32(1)), 1.0000001, 0.25, 0.75]]).astype(np.float32)
+    arc = np.empty_like(hav)
+    hostsim.hostsim_arc_from_hav(hav.ctypes.data_as(fp), ctypes.c_long(len(hav)), arc.ctypes.data_as(fp))
+    want = 2 * np.arcsin(np.sqrt(np.minimum(hav.astype(np.float64), 1.0)))
+    ulp = np.spacing(np.maximum(want, 1e-30).astype(np.float32)).astype(np.float64)
+    err = np.abs(arc.astype(np.float64) - want) / ulp
+    big = hav > 1e-20                       # (below: the 1e-30 floor of z; such arcs are far inside the clamped-acos zone anyway)
+    assert err[big].max() <= 2.0 and err[big].mean() < 0.5, (err[big].max(), err[big].mean())
+    assert arc[hav == 0].max() < 1e-14 and abs(float(arc[hav >= 1].min()) - np.pi) < 3e-7
+    nan = np.array([np.nan], np.float32)
+    hostsim.hostsim_arc_from_hav(nan.ctypes.data_as(fp), ctypes.c_long(1), nan.ctypes.data_as(fp))
+    assert np.isnan(nan[0])
+
+
+def test_half_difference_terms_are_bit_identical_to_sincos_deg(hostsim):
+    """pair_job takes sin^2(x) and sin(2 x) of the half differences from sin2_and_sin_double_deg; the aligned path takes
+    them from sincos_deg (s * s, 2 s c).  Both kernels must see the same bits (test_pairwise_equals_aligned_on_the_expansion
+    checks that on the device; this is the host twin over every quadrant, the multiples of 45 and 90 degrees, and -0)."""
+    rng = np.random.RandomState(1)
+    x = np.concatenate([rng.uniform(-180, 180, 1_000_000), np.arange(-180, 181, 15, dtype=np.float64), [0.0, -0.0, 1e-30, -1e-30, 44.999996, 45.000004, 134.99999, 179.99998]]).astype(np.float32)
+    n = len(x)
+    out = [np.empty(n, np.float32) for _ in range(4)]
+    hostsim.hostsim_half_angle_terms(x.ctypes.data_as(fp), ctypes.c_long(n), *[o.ctypes.data_as(fp) for o in out])
+    s2, sin2x, s2_ref, sin2x_ref = out
+    assert np.array_equal(s2.view(np.uint32), s2_ref.view(np.uint32))
+    assert np.array_equal(sin2x.view(np.uint32), sin2x_ref.view(np.uint32))
+    assert np.abs(sin2x.astype(np.float64) - np.sin(np.radians(2 * x.astype(np.float64)))).max() < 3e-7
+
+
 def test_separating_axis_cull_is_conservative(hostsim):
     """The separating-axis prefilter of the N x M kernels (sphk_fast.cuh: pre_sat_disjoint) may only fire where the
     reference-order path, run WITHOUT any early-out, returns exactly 0 -- both transforms, both modes, every edge option,
