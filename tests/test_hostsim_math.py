@@ -413,6 +413,28 @@ def test_separating_axis_cull_is_conservative(hostsim):
     assert fired > 0.5 * disjoint and disjoint > 0.5 * total, (fired, disjoint, total)
 
 
+def test_separating_axis_cull_rate_on_the_sweep_distribution(hostsim):
+    """On the box distribution of the bench's sweep (random RBFoV boxes, 1-100 degrees) the circle test leaves ~40 % of
+    the pairs alive and the separating-axis test ends about a third of those: what goes on to the clipper is within a
+    few per cent of the pairs that really overlap.  (The figures DESIGN.md and bench.py's early_out_rate quote.)"""
+    from sph_retina_b200 import synthetic as S
+    ub = ctypes.POINTER(ctypes.c_ubyte)
+    n = 400_000
+    b1 = np.ascontiguousarray(S.generate_boxes(n, alpha_range=(1, 100), beta_range=(1, 100), box="rbfov", seed=0).numpy())
+    b2 = np.ascontiguousarray(S.generate_boxes(n, alpha_range=(1, 100), beta_range=(1, 100), box="rbfov", seed=1).numpy())
+    dense, cull = np.empty(n, np.float32), np.empty(n, np.uint8)
+    hostsim.hostsim_prefilter(0, b1.ctypes.data_as(fp), b2.ctypes.data_as(fp), ctypes.c_long(n), 5, 0, 0, dense.ctypes.data_as(fp),
+                              cull.ctypes.data_as(ub))
+    circle_live = (cull & 1) == 0
+    sat = (cull & 4) != 0
+    assert not (((cull & 5) != 0) & (dense != 0)).any()                 # neither test ever fires on an overlapping pair
+    live = circle_live & ~sat
+    positive = dense > 0
+    assert 0.38 < circle_live.mean() < 0.43, circle_live.mean()
+    assert 0.29 < (circle_live & sat).sum() / circle_live.sum() < 0.38
+    assert 0.25 < positive.mean() < 0.28 and live.mean() - positive.mean() < 0.015, (live.mean(), positive.mean())
+
+
 def test_box_frame_cull_is_conservative(hostsim):
     """The second prefilter test of the N x M scan loops (sphk_fast.cuh: pre_outside_box) may only fire where the
     reference-order path, run WITHOUT any early-out, returns exactly 0 -- for both transforms, every edge option and
