@@ -413,24 +413,27 @@ def other_configs(torch, native, dev, flush, hbm_peak_gbs=6544.3, fp32_peak_tf=6
     out["loss_200k_rbfov"] = {"fwd_ms": ms_f, "fwd_bwd_ms": ms_fb, "pairs_per_s_fwd_bwd": 200_000 / ms_fb * 1e3}
     # the same forward + backward captured in a CUDA graph (the step a training loop replays): what the device needs for
     # it once the ~10 eager autograd / allocator steps of the host are out of the way
-    try:
+    def graph_ms(loss_module):
         p_static = pred.detach().clone().requires_grad_(True)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(3):
                 p_static.grad = None
-                L(p_static, target).backward()
+                loss_module(p_static, target).backward()
         torch.cuda.current_stream().wait_stream(side)
         p_static.grad = None
         gl = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gl):
-            loss_static = L(p_static, target)
+            loss_static = loss_module(p_static, target)
             loss_static.backward()
-        ms_g = quick(torch, gl.replay, flush=flush)
+        ms_ = quick(torch, gl.replay, flush=flush)
+        del gl
+        return ms_
+    try:
+        ms_g = graph_ms(L)
         out["loss_200k_rbfov"].update({"fwd_bwd_graph_ms": ms_g, "pairs_per_s_fwd_bwd_graph": 200_000 / ms_g * 1e3,
                                        "fp32_frac_graph": 200_000 * 3 * FLOP_PER_PAIR / (ms_g * 1e-3) / 1e12 / fp32_peak_tf})
-        del gl
     except Exception as e:      # capture is an extra: never lose the line over it
         out["loss_200k_rbfov"]["fwd_bwd_graph_error"] = repr(e)
     # the other losses on the same OBBs: one launch each for loss + both gradients
@@ -443,6 +446,10 @@ def other_configs(torch, native, dev, flush, hbm_peak_gbs=6544.3, fp32_peak_tf=6
             Lo(p, target).backward()
         ms = quick(torch, fb, flush=flush)
         other[name] = {"fwd_bwd_ms": ms, "pairs_per_s_fwd_bwd": 200_000 / ms * 1e3}
+        try:        # the device's share of the step: the same forward + backward replayed from a CUDA graph
+            other[name]["fwd_bwd_graph_ms"] = graph_ms(Lo)
+        except Exception as e:
+            other[name]["fwd_bwd_graph_error"] = repr(e)
     out["other_losses_200k_rbfov"] = other
     # training targets of the head for the 16 images (assign -> PseudoSampler -> labels / weights / box targets): two C-ABI calls
     from sph_retina_b200.sphdet.assigners import SphMaxIoUAssigner

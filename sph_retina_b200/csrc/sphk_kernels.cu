@@ -1432,7 +1432,7 @@ k_riou_fwd_bwd(const float* __restrict__ obb1, const float* __restrict__ obb2, i
 //   partial [grid]  per-block sums of sum_j up[i, j] * loss[i, j] (without `scale`; NULL to skip)
 //   grad_b1 / grad_b2 [n, D]  scale * sum_j up[i, j] * d(loss[i, j]) / d(box)
 template <int D, typename T>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 k_obb_loss(LossParams lp, int xkind, const float* __restrict__ b1, const float* __restrict__ b2, int64_t n,
            const float* __restrict__ up, int up_cols, float scale, float* __restrict__ loss, float* __restrict__ partial,
            float* __restrict__ grad_b1, float* __restrict__ grad_b2, bool vec_ok) {

@@ -33,54 +33,76 @@ struct LossParams {
 
 SPHK_HD int loss_columns(int kind) { return kind == LOSS_L1 ? 5 : 1; }
 
-// ---- forward-mode dual numbers --------------------------------------------------------------------------------
-constexpr int kNV = 10;   // x1 y1 w1 h1 a1 x2 y2 w2 h2 a2
-template <typename T>
+// ---- forward-mode dual numbers with a compile-time sparsity mask ---------------------------------------------
+// Dual<T, M> carries the value and d/d(variable k) for the variables k named in the bit mask M only (x1 y1 w1 h1 a1 x2 y2 w2
+// h2 a2 = bits 0..9).  The mask is part of the type and propagates through every operation (union of the operands'
+// masks), so the covariance of the predicted box carries three partials, the centre offsets two, and only the last few
+// operations of a loss carry all ten: the partials that are structurally zero are neither stored nor multiplied (the first
+// version carried all ten through everything: 216 registers and ~3 x the FP64 work).  Entries of d[] outside M are never
+// written or read; with the loops unrolled they do not exist.
+constexpr int kNV = 10;
+constexpr unsigned kAllVars = (1u << kNV) - 1u;
+template <typename T, unsigned M>
 struct Dual {
+    static constexpr unsigned mask = M;
     T v;
     T d[kNV];
 };
 
-template <typename T> SPHK_HD Dual<T> dconst(T c) {
-    Dual<T> r; r.v = c;
-#pragma unroll
-    for (int k = 0; k < kNV; ++k) r.d[k] = (T)0;
+template <typename T> SPHK_HD Dual<T, 0u> dconst(T c) {
+    Dual<T, 0u> r; r.v = c;
     return r;
 }
-template <typename T> SPHK_HD Dual<T> dvar(T x, int idx) {
-    Dual<T> r = dconst<T>(x);
-    r.d[idx] = (T)1;
+template <int IDX, typename T> SPHK_HD Dual<T, (1u << IDX)> dvar(T x) {
+    Dual<T, (1u << IDX)> r; r.v = x;
+    r.d[IDX] = (T)1;
+    return r;
+}
+// the same number with more (zero) partials named: where branches of different sparsity meet
+template <unsigned MW, typename T, unsigned M> SPHK_HD Dual<T, MW> dwiden(const Dual<T, M>& a) {
+    static_assert((M & ~MW) == 0u, "dwiden: the wider mask must contain the narrower one");
+    Dual<T, MW> r; r.v = a.v;
+#pragma unroll
+    for (int k = 0; k < kNV; ++k)
+        if ((MW >> k) & 1u) r.d[k] = ((M >> k) & 1u) ? a.d[k] : (T)0;
     return r;
 }
 // r = f(a) with f'(a) = fa
-template <typename T> SPHK_HD Dual<T> dchain(const Dual<T>& a, T fv, T fa) {
-    Dual<T> r; r.v = fv;
+template <typename T, unsigned M> SPHK_HD Dual<T, M> dchain(const Dual<T, M>& a, T fv, T fa) {
+    Dual<T, M> r; r.v = fv;
 #pragma unroll
-    for (int k = 0; k < kNV; ++k) r.d[k] = fa * a.d[k];
+    for (int k = 0; k < kNV; ++k)
+        if ((M >> k) & 1u) r.d[k] = fa * a.d[k];
     return r;
 }
 // r = f(a, b)
-template <typename T> SPHK_HD Dual<T> dchain2(const Dual<T>& a, const Dual<T>& b, T fv, T fa, T fb) {
-    Dual<T> r; r.v = fv;
+template <typename T, unsigned MA, unsigned MB>
+SPHK_HD Dual<T, (MA | MB)> dchain2(const Dual<T, MA>& a, const Dual<T, MB>& b, T fv, T fa, T fb) {
+    Dual<T, (MA | MB)> r; r.v = fv;
 #pragma unroll
-    for (int k = 0; k < kNV; ++k) r.d[k] = fa * a.d[k] + fb * b.d[k];
+    for (int k = 0; k < kNV; ++k) {
+        const bool ia = (MA >> k) & 1u, ib = (MB >> k) & 1u;
+        if (ia && ib) r.d[k] = fa * a.d[k] + fb * b.d[k];
+        else if (ia) r.d[k] = fa * a.d[k];
+        else if (ib) r.d[k] = fb * b.d[k];
+    }
     return r;
 }
-template <typename T> SPHK_HD Dual<T> operator+(const Dual<T>& a, const Dual<T>& b) { return dchain2(a, b, a.v + b.v, (T)1, (T)1); }
-template <typename T> SPHK_HD Dual<T> operator-(const Dual<T>& a, const Dual<T>& b) { return dchain2(a, b, a.v - b.v, (T)1, (T)-1); }
-template <typename T> SPHK_HD Dual<T> operator*(const Dual<T>& a, const Dual<T>& b) { return dchain2(a, b, a.v * b.v, b.v, a.v); }
-template <typename T> SPHK_HD Dual<T> operator/(const Dual<T>& a, const Dual<T>& b) {
+template <typename T, unsigned MA, unsigned MB> SPHK_HD Dual<T, (MA | MB)> operator+(const Dual<T, MA>& a, const Dual<T, MB>& b) { return dchain2(a, b, a.v + b.v, (T)1, (T)1); }
+template <typename T, unsigned MA, unsigned MB> SPHK_HD Dual<T, (MA | MB)> operator-(const Dual<T, MA>& a, const Dual<T, MB>& b) { return dchain2(a, b, a.v - b.v, (T)1, (T)-1); }
+template <typename T, unsigned MA, unsigned MB> SPHK_HD Dual<T, (MA | MB)> operator*(const Dual<T, MA>& a, const Dual<T, MB>& b) { return dchain2(a, b, a.v * b.v, b.v, a.v); }
+template <typename T, unsigned MA, unsigned MB> SPHK_HD Dual<T, (MA | MB)> operator/(const Dual<T, MA>& a, const Dual<T, MB>& b) {
     const T q = a.v / b.v;
     return dchain2(a, b, q, (T)1 / b.v, -q / b.v);
 }
-template <typename T> SPHK_HD Dual<T> operator-(const Dual<T>& a) { return dchain(a, -a.v, (T)-1); }
-template <typename T> SPHK_HD Dual<T> operator+(const Dual<T>& a, T c) { return dchain(a, a.v + c, (T)1); }
-template <typename T> SPHK_HD Dual<T> operator-(const Dual<T>& a, T c) { return dchain(a, a.v - c, (T)1); }
-template <typename T> SPHK_HD Dual<T> operator*(const Dual<T>& a, T c) { return dchain(a, a.v * c, c); }
-template <typename T> SPHK_HD Dual<T> operator*(T c, const Dual<T>& a) { return dchain(a, a.v * c, c); }
-template <typename T> SPHK_HD Dual<T> operator/(const Dual<T>& a, T c) { return dchain(a, a.v / c, (T)1 / c); }
-template <typename T> SPHK_HD Dual<T> operator-(T c, const Dual<T>& a) { return dchain(a, c - a.v, (T)-1); }
-template <typename T> SPHK_HD Dual<T> operator/(T c, const Dual<T>& a) {
+template <typename T, unsigned M> SPHK_HD Dual<T, M> operator-(const Dual<T, M>& a) { return dchain(a, -a.v, (T)-1); }
+template <typename T, unsigned M> SPHK_HD Dual<T, M> operator+(const Dual<T, M>& a, T c) { return dchain(a, a.v + c, (T)1); }
+template <typename T, unsigned M> SPHK_HD Dual<T, M> operator-(const Dual<T, M>& a, T c) { return dchain(a, a.v - c, (T)1); }
+template <typename T, unsigned M> SPHK_HD Dual<T, M> operator*(const Dual<T, M>& a, T c) { return dchain(a, a.v * c, c); }
+template <typename T, unsigned M> SPHK_HD Dual<T, M> operator*(T c, const Dual<T, M>& a) { return dchain(a, a.v * c, c); }
+template <typename T, unsigned M> SPHK_HD Dual<T, M> operator/(const Dual<T, M>& a, T c) { return dchain(a, a.v / c, (T)1 / c); }
+template <typename T, unsigned M> SPHK_HD Dual<T, M> operator-(T c, const Dual<T, M>& a) { return dchain(a, c - a.v, (T)-1); }
+template <typename T, unsigned M> SPHK_HD Dual<T, M> operator/(T c, const Dual<T, M>& a) {
     const T q = c / a.v;
     return dchain(a, q, -q / a.v);
 }
@@ -93,151 +115,178 @@ SPHK_HD float m_sin(float x) { return sinf(x); }       SPHK_HD double m_sin(doub
 SPHK_HD float m_cos(float x) { return cosf(x); }       SPHK_HD double m_cos(double x) { return cos(x); }
 SPHK_HD float m_floor(float x) { return floorf(x); }   SPHK_HD double m_floor(double x) { return floor(x); }
 
-template <typename T> SPHK_HD Dual<T> dsqrt(const Dual<T>& a) { const T s = m_sqrt(a.v); return dchain(a, s, (T)0.5 / s); }
-template <typename T> SPHK_HD Dual<T> dlog(const Dual<T>& a) { return dchain(a, m_log(a.v), (T)1 / a.v); }
-template <typename T> SPHK_HD Dual<T> dlog1p(const Dual<T>& a) { return dchain(a, m_log1p(a.v), (T)1 / ((T)1 + a.v)); }
-template <typename T> SPHK_HD Dual<T> dexp(const Dual<T>& a) { const T e = m_exp(a.v); return dchain(a, e, e); }
-template <typename T> SPHK_HD Dual<T> dabs(const Dual<T>& a) {
+template <typename T, unsigned M> SPHK_HD Dual<T, M> dsqrt(const Dual<T, M>& a) { const T s = m_sqrt(a.v); return dchain(a, s, (T)0.5 / s); }
+template <typename T, unsigned M> SPHK_HD Dual<T, M> dlog(const Dual<T, M>& a) { return dchain(a, m_log(a.v), (T)1 / a.v); }
+template <typename T, unsigned M> SPHK_HD Dual<T, M> dlog1p(const Dual<T, M>& a) { return dchain(a, m_log1p(a.v), (T)1 / ((T)1 + a.v)); }
+template <typename T, unsigned M> SPHK_HD Dual<T, M> dexp(const Dual<T, M>& a) { const T e = m_exp(a.v); return dchain(a, e, e); }
+template <typename T, unsigned M> SPHK_HD Dual<T, M> dabs(const Dual<T, M>& a) {
     const T av = a.v;
     return dchain(a, (av < (T)0) ? -av : av, (av > (T)0) ? (T)1 : ((av < (T)0) ? (T)-1 : (T)0));
 }
 // torch.clamp(min=lo[, max=hi]): NaN stays NaN; the gradient passes where lo <= x <= hi
-template <typename T> SPHK_HD Dual<T> dclamp_min(const Dual<T>& a, T lo) {
+template <typename T, unsigned M> SPHK_HD Dual<T, M> dclamp_min(const Dual<T, M>& a, T lo) {
     return dchain(a, (a.v < lo) ? lo : a.v, (a.v >= lo) ? (T)1 : (T)0);
 }
-template <typename T> SPHK_HD Dual<T> dclamp(const Dual<T>& a, T lo, T hi) {
+template <typename T, unsigned M> SPHK_HD Dual<T, M> dclamp(const Dual<T, M>& a, T lo, T hi) {
     return dchain(a, (a.v < lo) ? lo : ((a.v > hi) ? hi : a.v), (a.v >= lo && a.v <= hi) ? (T)1 : (T)0);
 }
 // torch.max / torch.min of two tensors: equal values share the gradient
-template <typename T> SPHK_HD Dual<T> dmax(const Dual<T>& a, const Dual<T>& b) {
+template <typename T, unsigned MA, unsigned MB> SPHK_HD Dual<T, (MA | MB)> dmax(const Dual<T, MA>& a, const Dual<T, MB>& b) {
     const T wa = (a.v > b.v) ? (T)1 : ((a.v == b.v) ? (T)0.5 : (T)0);
     return dchain2(a, b, (a.v > b.v) ? a.v : b.v, wa, (T)1 - wa);
 }
-template <typename T> SPHK_HD Dual<T> dmin(const Dual<T>& a, const Dual<T>& b) {
+template <typename T, unsigned MA, unsigned MB> SPHK_HD Dual<T, (MA | MB)> dmin(const Dual<T, MA>& a, const Dual<T, MB>& b) {
     const T wa = (a.v < b.v) ? (T)1 : ((a.v == b.v) ? (T)0.5 : (T)0);
     return dchain2(a, b, (a.v < b.v) ? a.v : b.v, wa, (T)1 - wa);
 }
 
 // ---- mmrotate gaussian_dist_loss.py: xy_wh_r_2_xy_sigma -----------------------------------------------------------
-template <typename T>
-struct Sigma2 { Dual<T> s11, s12, s22; };
+template <typename T, unsigned M>
+struct Sigma2 { Dual<T, M> s11, s12, s22; };
 
-template <typename T>
-SPHK_HD Sigma2<T> obb_sigma(const Dual<T>& w, const Dual<T>& h, const Dual<T>& r) {
-    const Dual<T> wc = dclamp(w, (T)1e-7, (T)1e7), hc = dclamp(h, (T)1e-7, (T)1e7);
-    const Dual<T> a = wc * wc * (T)0.25, b = hc * hc * (T)0.25;          // (0.5 diag(wh))^2
+template <typename T, unsigned MW, unsigned MH, unsigned MR>
+SPHK_HD Sigma2<T, (MW | MH | MR)> obb_sigma(const Dual<T, MW>& w, const Dual<T, MH>& h, const Dual<T, MR>& r) {
+    const auto wc = dclamp(w, (T)1e-7, (T)1e7);
+    const auto hc = dclamp(h, (T)1e-7, (T)1e7);
+    const auto a = wc * wc * (T)0.25;
+    const auto b = hc * hc * (T)0.25;          // (0.5 diag(wh))^2
     const T cv = m_cos(r.v), sv = m_sin(r.v);
-    const Dual<T> c = dchain(r, cv, -sv), s = dchain(r, sv, cv);
-    Sigma2<T> S;
+    const auto c = dchain(r, cv, -sv);
+    const auto s = dchain(r, sv, cv);
+    Sigma2<T, (MW | MH | MR)> S;
     S.s11 = c * c * a + s * s * b;
     S.s12 = c * s * (a - b);
     S.s22 = s * s * a + c * c * b;
     return S;
 }
-template <typename T> SPHK_HD Dual<T> sigma_det(const Sigma2<T>& S) { return S.s11 * S.s22 - S.s12 * S.s12; }
+template <typename T, unsigned M> SPHK_HD Dual<T, M> sigma_det(const Sigma2<T, M>& S) { return S.s11 * S.s22 - S.s12 * S.s12; }
 
-template <typename T>
-SPHK_HD Dual<T> gd_postprocess(Dual<T> distance, int fun, T tau) {
+template <typename T, unsigned M>
+SPHK_HD Dual<T, M> gd_postprocess(Dual<T, M> distance, int fun, T tau) {
     if (fun == FUN_LOG1P) distance = dlog1p(distance);
     else if (fun == FUN_SQRT) distance = dsqrt(dclamp_min(distance, (T)1e-7));
     if (tau >= (T)1) return (T)1 - (T)1 / (distance + tau);
     return distance;
 }
 
-template <typename T>
-SPHK_HD Dual<T> gwd_distance(const Dual<T>& dx, const Dual<T>& dy, const Sigma2<T>& P, const Sigma2<T>& Q, T alpha, bool normalize) {
-    const Dual<T> xy = dx * dx + dy * dy;
-    Dual<T> whr = (P.s11 + P.s22) + (Q.s11 + Q.s22);
-    const Dual<T> t_tr = P.s11 * Q.s11 + (T)2 * (P.s12 * Q.s12) + P.s22 * Q.s22;       // trace(Sigma_p Sigma_t)
-    const Dual<T> t_det_sqrt = dsqrt(dclamp_min(sigma_det(P) * sigma_det(Q), (T)1e-7));
-    whr = whr + (T)-2 * dsqrt(dclamp_min(t_tr + (T)2 * t_det_sqrt, (T)1e-7));
-    Dual<T> distance = dsqrt(dclamp_min(xy + (alpha * alpha) * whr, (T)1e-7));
+template <typename T, unsigned MX, unsigned MY, unsigned MP, unsigned MQ>
+SPHK_HD Dual<T, (MX | MY | MP | MQ)> gwd_distance(const Dual<T, MX>& dx, const Dual<T, MY>& dy, const Sigma2<T, MP>& P,
+                                                  const Sigma2<T, MQ>& Q, T alpha, bool normalize) {
+    const auto xy = dx * dx + dy * dy;
+    const auto whr0 = (P.s11 + P.s22) + (Q.s11 + Q.s22);
+    const auto t_tr = P.s11 * Q.s11 + (T)2 * (P.s12 * Q.s12) + P.s22 * Q.s22;       // trace(Sigma_p Sigma_t)
+    const auto t_det_sqrt = dsqrt(dclamp_min(sigma_det(P) * sigma_det(Q), (T)1e-7));
+    const auto whr = whr0 + (T)-2 * dsqrt(dclamp_min(t_tr + (T)2 * t_det_sqrt, (T)1e-7));
+    auto distance = dsqrt(dclamp_min(xy + (alpha * alpha) * whr, (T)1e-7));
     if (normalize) {
-        const Dual<T> scale = (T)2 * dclamp_min(dsqrt(dclamp_min(dsqrt(dclamp_min(t_det_sqrt, (T)1e-7)), (T)1e-7)), (T)1e-7);
+        const auto scale = (T)2 * dclamp_min(dsqrt(dclamp_min(dsqrt(dclamp_min(t_det_sqrt, (T)1e-7)), (T)1e-7)), (T)1e-7);
         distance = distance / scale;
     }
     return distance;
 }
 
 // KL(N_p || N_t) as mmrotate's kld_loss writes it (the inverse is taken of Sigma_p)
-template <typename T>
-SPHK_HD Dual<T> kld_distance(const Dual<T>& dx, const Dual<T>& dy, const Sigma2<T>& P, const Sigma2<T>& Q, T alpha, bool sqrt_) {
-    const Dual<T> det_p = sigma_det(P), det_t = sigma_det(Q);
-    const Dual<T> i11 = P.s22 / det_p, i12 = -P.s12 / det_p, i22 = P.s11 / det_p;
-    const Dual<T> xy = (T)0.5 * (dx * dx * i11 + (T)2 * (dx * dy * i12) + dy * dy * i22);
-    Dual<T> whr = (T)0.5 * (i11 * Q.s11 + (T)2 * (i12 * Q.s12) + i22 * Q.s22);
-    whr = whr + (T)0.5 * (dlog(det_p) - dlog(det_t));
-    whr = whr - (T)1;
-    Dual<T> distance = xy / (alpha * alpha) + whr;
+template <typename T, unsigned MX, unsigned MY, unsigned MP, unsigned MQ>
+SPHK_HD Dual<T, (MX | MY | MP | MQ)> kld_distance(const Dual<T, MX>& dx, const Dual<T, MY>& dy, const Sigma2<T, MP>& P,
+                                                  const Sigma2<T, MQ>& Q, T alpha, bool sqrt_) {
+    const auto det_p = sigma_det(P);
+    const auto det_t = sigma_det(Q);
+    const auto i11 = P.s22 / det_p;
+    const auto i12 = -P.s12 / det_p;
+    const auto i22 = P.s11 / det_p;
+    const auto xy = (T)0.5 * (dx * dx * i11 + (T)2 * (dx * dy * i12) + dy * dy * i22);
+    const auto whr0 = (T)0.5 * (i11 * Q.s11 + (T)2 * (i12 * Q.s12) + i22 * Q.s22);
+    const auto whr = whr0 + (T)0.5 * (dlog(det_p) - dlog(det_t)) - (T)1;
+    auto distance = xy / (alpha * alpha) + whr;
     if (sqrt_) distance = dsqrt(dclamp_min(distance, (T)1e-7));
     return distance;
 }
 
+// the ten OBB parameters as dual variables, each with its own partial
 template <typename T>
-SPHK_HD Dual<T> gd_loss_row(const Dual<T>* q, const LossParams& P) {
-    // q[0..4] = pred OBB (x y w h a), q[5..9] = target OBB
-    const Sigma2<T> Sp = obb_sigma(q[2], q[3], q[4]), St = obb_sigma(q[7], q[8], q[9]);
-    const Dual<T> dx = q[0] - q[5], dy = q[1] - q[6];
+struct ObbVars {
+    Dual<T, (1u << 0)> x1; Dual<T, (1u << 1)> y1; Dual<T, (1u << 2)> w1; Dual<T, (1u << 3)> h1; Dual<T, (1u << 4)> a1;   // pred OBB
+    Dual<T, (1u << 5)> x2; Dual<T, (1u << 6)> y2; Dual<T, (1u << 7)> w2; Dual<T, (1u << 8)> h2; Dual<T, (1u << 9)> a2;   // target OBB
+};
+
+template <typename T>
+SPHK_HD Dual<T, kAllVars> gd_loss_row(const ObbVars<T>& q, const LossParams& P) {
+    const auto Sp = obb_sigma(q.w1, q.h1, q.a1);
+    const auto St = obb_sigma(q.w2, q.h2, q.a2);
+    const auto dx = q.x1 - q.x2;
+    const auto dy = q.y1 - q.y2;
     const T alpha = (T)P.alpha;
     const bool opt = (P.flags & LF_NORMALIZE_OR_SQRT) != 0;
-    Dual<T> dist;
+    Dual<T, kAllVars> dist;
     if (P.kind == LOSS_GWD) {
         dist = gwd_distance(dx, dy, Sp, St, alpha, opt);
     } else if (P.kind == LOSS_KLD) {
         dist = kld_distance(dx, dy, Sp, St, alpha, opt);
     } else {
-        const Dual<T> mdx = -dx, mdy = -dy;
+        const auto mdx = -dx;
+        const auto mdy = -dy;
         if (P.kind == LOSS_JD) {
             dist = (kld_distance(dx, dy, Sp, St, alpha, false) + kld_distance(mdx, mdy, St, Sp, alpha, false)) * (T)0.5;
             if (opt) dist = dsqrt(dclamp_min(dist, (T)1e-7));
         } else {
-            const Dual<T> a = kld_distance(dx, dy, Sp, St, alpha, opt), b = kld_distance(mdx, mdy, St, Sp, alpha, opt);
+            const auto a = kld_distance(dx, dy, Sp, St, alpha, opt);
+            const auto b = kld_distance(mdx, mdy, St, Sp, alpha, opt);
             dist = (P.kind == LOSS_KLD_SYMMAX) ? dmax(a, b) : dmin(a, b);
         }
     }
     return gd_postprocess(dist, P.fun, (T)P.tau);
 }
 
+// smooth-L1 of one centre coordinate as mmrotate's kfiou_loss writes it
+template <typename T, unsigned MA, unsigned MB>
+SPHK_HD Dual<T, (MA | MB)> kf_center_term(const Dual<T, MA>& a, const Dual<T, MB>& b, T beta) {
+    const auto diff = dabs(a - b);
+    return (diff.v < beta) ? ((T)0.5 * diff * diff / beta) : (diff - (T)0.5 * beta);
+}
+
 // mmrotate kf_iou_loss.py: kfiou_loss(pred, target, pred_decode, targets_decode).  The reference's subclass passes
 // pred_decode = TARGET OBB and targets_decode = PRED OBB (sph2pob_kf_loss.py:26).
 template <typename T>
-SPHK_HD Dual<T> kf_loss_row(const Dual<T>* q, const LossParams& P) {
+SPHK_HD Dual<T, kAllVars> kf_loss_row(const ObbVars<T>& q, const LossParams& P) {
     const T beta = (T)P.beta, eps = (T)P.eps;
-    Dual<T> xy_loss = dconst<T>((T)0);
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        const Dual<T> diff = dabs(q[k] - q[5 + k]);
-        xy_loss = xy_loss + ((diff.v < beta) ? ((T)0.5 * diff * diff / beta) : (diff - (T)0.5 * beta));
-    }
-    const Sigma2<T> Sp = obb_sigma(q[7], q[8], q[9]);      // "pred_decode"    = target OBB
-    const Sigma2<T> St = obb_sigma(q[2], q[3], q[4]);      // "targets_decode" = pred OBB
-    const Dual<T> Vb_p = (T)4 * dsqrt(sigma_det(Sp)), Vb_t = (T)4 * dsqrt(sigma_det(St));
+    const auto xy_loss = kf_center_term(q.x1, q.x2, beta) + kf_center_term(q.y1, q.y2, beta);
+    const auto Sp = obb_sigma(q.w2, q.h2, q.a2);      // "pred_decode"    = target OBB
+    const auto St = obb_sigma(q.w1, q.h1, q.a1);      // "targets_decode" = pred OBB
+    const auto Vb_p = (T)4 * dsqrt(sigma_det(Sp));
+    const auto Vb_t = (T)4 * dsqrt(sigma_det(St));
     // K = Sigma_p (Sigma_p + Sigma_t)^-1 ;  Sigma = Sigma_p - K Sigma_p
-    const Dual<T> m11 = Sp.s11 + St.s11, m12 = Sp.s12 + St.s12, m22 = Sp.s22 + St.s22;
-    const Dual<T> md = m11 * m22 - m12 * m12;
-    const Dual<T> n11 = m22 / md, n12 = -m12 / md, n22 = m11 / md;
-    const Dual<T> k11 = Sp.s11 * n11 + Sp.s12 * n12, k12 = Sp.s11 * n12 + Sp.s12 * n22;
-    const Dual<T> k21 = Sp.s12 * n11 + Sp.s22 * n12, k22 = Sp.s12 * n12 + Sp.s22 * n22;
-    const Dual<T> e11 = Sp.s11 - (k11 * Sp.s11 + k12 * Sp.s12), e12 = Sp.s12 - (k11 * Sp.s12 + k12 * Sp.s22);
-    const Dual<T> e21 = Sp.s12 - (k21 * Sp.s11 + k22 * Sp.s12), e22 = Sp.s22 - (k21 * Sp.s12 + k22 * Sp.s22);
-    Dual<T> Vb = (T)4 * dsqrt(e11 * e22 - e12 * e21);
-    if (!(Vb.v == Vb.v)) Vb = dconst<T>((T)0);             // torch.where(isnan(Vb), 0, Vb)
-    const Dual<T> kfiou = Vb / (Vb_p + Vb_t - Vb + eps);
-    Dual<T> kf;
+    const auto m11 = Sp.s11 + St.s11;
+    const auto m12 = Sp.s12 + St.s12;
+    const auto m22 = Sp.s22 + St.s22;
+    const auto md = m11 * m22 - m12 * m12;
+    const auto n11 = m22 / md;
+    const auto n12 = -m12 / md;
+    const auto n22 = m11 / md;
+    const auto k11 = Sp.s11 * n11 + Sp.s12 * n12;
+    const auto k12 = Sp.s11 * n12 + Sp.s12 * n22;
+    const auto k21 = Sp.s12 * n11 + Sp.s22 * n12;
+    const auto k22 = Sp.s12 * n12 + Sp.s22 * n22;
+    const auto e11 = Sp.s11 - (k11 * Sp.s11 + k12 * Sp.s12);
+    const auto e12 = Sp.s12 - (k11 * Sp.s12 + k12 * Sp.s22);
+    const auto e21 = Sp.s12 - (k21 * Sp.s11 + k22 * Sp.s12);
+    const auto e22 = Sp.s22 - (k21 * Sp.s12 + k22 * Sp.s22);
+    auto Vb = (T)4 * dsqrt(e11 * e22 - e12 * e21);
+    if (!(Vb.v == Vb.v)) Vb = dwiden<decltype(Vb)::mask>(dconst<T>((T)0));       // torch.where(isnan(Vb), 0, Vb)
+    const auto kfiou = Vb / (Vb_p + Vb_t - Vb + eps);
+    const auto k1 = (T)1 - kfiou;
+    auto kf = k1;
     if (P.fun == 1) kf = -dlog(kfiou + eps);
-    else if (P.fun == 2) kf = dexp((T)1 - kfiou) - (T)1;
-    else kf = (T)1 - kfiou;
+    else if (P.fun == 2) kf = dexp(k1) - (T)1;
     return dclamp_min(xy_loss + kf, (T)0);
 }
 
 // One row of a GD / KF loss: returns the loss, adds up * d(loss)/d(OBBs) to go1 / go2 (x y w h a each).
 template <typename T>
 SPHK_HD float obb_scalar_loss_row(const ObbPair& o, const LossParams& P, float up, float* go1, float* go2) {
-    Dual<T> q[kNV];
-    const float raw[kNV] = {o.x1, o.y1, o.w1, o.h1, o.a1, o.x2, o.y2, o.w2, o.h2, o.a2};
-#pragma unroll
-    for (int k = 0; k < kNV; ++k) q[k] = dvar<T>((T)raw[k], k);
-    const Dual<T> L = (P.kind == LOSS_KFIOU) ? kf_loss_row<T>(q, P) : gd_loss_row<T>(q, P);
+    ObbVars<T> q;
+    q.x1 = dvar<0>((T)o.x1); q.y1 = dvar<1>((T)o.y1); q.w1 = dvar<2>((T)o.w1); q.h1 = dvar<3>((T)o.h1); q.a1 = dvar<4>((T)o.a1);
+    q.x2 = dvar<5>((T)o.x2); q.y2 = dvar<6>((T)o.y2); q.w2 = dvar<7>((T)o.w2); q.h2 = dvar<8>((T)o.h2); q.a2 = dvar<9>((T)o.a2);
+    const Dual<T, kAllVars> L = (P.kind == LOSS_KFIOU) ? kf_loss_row<T>(q, P) : gd_loss_row<T>(q, P);
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
         go1[k] += up * (float)L.d[k];
