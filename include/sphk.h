@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SPHK_ABI_VERSION 7
+#define SPHK_ABI_VERSION 8
 
 /* OR-ed into `kind` of the NMS entry points: suppress iff IoU > threshold (mmcv nms) instead of !(IoU <= threshold) (SphNMS) */
 #define SPHK_NMS_RULE_GT 0x100
@@ -254,6 +254,15 @@ int sphk_riou_fwd_bwd(const float* obb1, const float* obb2, int64_t n, float* io
 int sphk_obb_loss(int loss_kind, int fun, int flags, float tau, float alpha, float beta, float eps, int transform,
                   const float* pred, const float* target, int64_t n, int D, const float* upstream, int up_cols, float scale,
                   float* loss, float* partial, float* grad_pred, float* grad_target, void* stream);
+
+/* The reduced loss of sphk_obb_loss finished on the device: *total = scale * sum_i sum_j upstream[i, j] * loss[i, j] as one
+ * float written by the launch itself (the block that draws the last ticket adds the per-block sums in index order, as
+ * sphk_loss_reduce_total does), next to the gradients of that total -- the forward of a training step is ONE launch, no
+ * reduction op on the host side.  scratch: sphk_loss_total_scratch_bytes(n) bytes, 16-byte aligned, its first 16 bytes
+ * zero before the first call (every call hands the ticket counter back at zero). */
+int sphk_obb_loss_total(int loss_kind, int fun, int flags, float tau, float alpha, float beta, float eps, int transform,
+                        const float* pred, const float* target, int64_t n, int D, const float* upstream, int up_cols, float scale,
+                        float* total, void* scratch, float* grad_pred, float* grad_target, void* stream);
 
 /* The spherical delta box coders: DeltaXYWHSphBBoxCoder (D = 4) and DeltaXYWHASphBBoxCoder (D = 5)
  * (sphdet/bbox/coder/delta_xywh_sph_bbox_coder.py:45-115,117-262; delta_xywha_rsph_bbox_coder.py:45-115,117-268).

@@ -20,7 +20,7 @@ EDGE = {"arc": 0, "chord": 1, "tangent": 2}
 ANGLE = {"equator": 0, "project": 1}
 
 SPHK_OK = 0
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 _c_float_p = ctypes.c_void_p  # raw device addresses
 _i64 = ctypes.c_int64
@@ -71,6 +71,9 @@ SIGNATURES = {
     "sphk_obb_loss": (_int, [_int, _int, _int, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, _int, _c_float_p,
                              _c_float_p, _i64, _int, _c_float_p, _int, ctypes.c_float, _c_float_p, _c_float_p, _c_float_p,
                              _c_float_p, ctypes.c_void_p]),
+    "sphk_obb_loss_total": (_int, [_int, _int, _int, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, _int, _c_float_p,
+                                   _c_float_p, _i64, _int, _c_float_p, _int, ctypes.c_float, _c_float_p, ctypes.c_void_p, _c_float_p,
+                                   _c_float_p, ctypes.c_void_p]),
     "sphk_coder_decode": (_int, [_c_float_p, _c_float_p, _i64, _int, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float),
                                  ctypes.c_float, _int, _int, ctypes.c_float, _c_float_p, ctypes.c_void_p]),
     "sphk_coder_decode_bwd": (_int, [_c_float_p, _c_float_p, _c_float_p, _i64, _int, ctypes.POINTER(ctypes.c_float),
@@ -530,6 +533,44 @@ def obb_loss(loss_kind, pred, target, upstream=None, scale=1.0, fun=0, flags=0, 
                                  _ptr(partial), _ptr(gp), _ptr(gt), _stream(pred)))
     launches += 1
     return loss, partial, gp, gt
+
+
+def obb_loss_total(loss_kind, pred, target, upstream=None, scale=1.0, fun=0, flags=0, tau=0.0, alpha=1.0, beta=1.0 / 9.0, eps=1e-6,
+                   transform="sph2pob_standard", want_grad_pred=False, want_grad_target=False):
+    """(total, grad_pred, grad_target): total = scale * sum(upstream * loss rows) as a 0-dim tensor written by the launch
+    itself (sphk_obb_loss_total: one launch, no reduction op afterwards) and the gradients of that total.  Scratch buffer as
+    loss_reduce_total: per (device, stream), the kernel hands the ticket counter back at zero."""
+    global launches
+    pred, target = _boxes(pred, "pred"), _boxes(target, "target")
+    if pred.shape != target.shape:
+        raise SphkError("pred/target shapes differ: %s vs %s" % (tuple(pred.shape), tuple(target.shape)))
+    n, dev = pred.size(0), pred.device
+    kind = LOSS_KIND[loss_kind]
+    L = 5 if kind == 6 else 1
+    up_cols = 0
+    if upstream is not None:
+        upstream = upstream.to(device=dev, dtype=torch.float32).contiguous()
+        if upstream.numel() == n * L and L > 1:
+            up_cols = L
+        elif upstream.numel() == n:
+            up_cols = 1
+        else:
+            raise SphkError("upstream has %d elements for %d rows of %d loss columns" % (upstream.numel(), n, L))
+    need = int(lib.sphk_loss_total_scratch_bytes(n))
+    key = (dev.index, _raw_stream(dev.index))
+    scratch = _loss_scratch.get(key)
+    if scratch is None or scratch.numel() < need:
+        scratch = torch.zeros(max(need * 2, 1 << 12), dtype=torch.uint8, device=dev)
+        _loss_scratch[key] = scratch
+    total = torch.empty((), dtype=torch.float32, device=dev)
+    gp = torch.empty_like(pred) if want_grad_pred else None
+    gt = torch.empty_like(target) if want_grad_target else None
+    with _on_device(dev):
+        _check(lib.sphk_obb_loss_total(kind, int(fun), int(flags), float(tau), float(alpha), float(beta), float(eps), KIND[transform],
+                                       _ptr(pred), _ptr(target), n, pred.size(1), _ptr(upstream), up_cols, float(scale), _ptr(total),
+                                       _ptr(scratch), _ptr(gp), _ptr(gt), _stream(pred)))
+    launches += 1
+    return total, gp, gt
 
 
 def _host5(values, D, default):

@@ -1435,8 +1435,10 @@ template <int D, typename T>
 __global__ void __launch_bounds__(kThreads, 2)
 k_obb_loss(LossParams lp, int xkind, const float* __restrict__ b1, const float* __restrict__ b2, int64_t n,
            const float* __restrict__ up, int up_cols, float scale, float* __restrict__ loss, float* __restrict__ partial,
-           float* __restrict__ grad_b1, float* __restrict__ grad_b2, bool vec_ok) {
+           float* __restrict__ grad_b1, float* __restrict__ grad_b2, bool vec_ok, float* __restrict__ total,
+           unsigned* __restrict__ ticket) {
     __shared__ float s_sum[kThreads / 32];
+    __shared__ bool s_last;
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     const int L = loss_columns(lp.kind);
     float li = 0.0f;
@@ -1494,6 +1496,31 @@ k_obb_loss(LossParams lp, int xkind, const float* __restrict__ b1, const float* 
 #pragma unroll
         for (int k = 0; k < kThreads / 32; ++k) t += s_sum[k];
         partial[blockIdx.x] = t;
+        s_last = false;
+        if (total) {
+            // as k_loss_reduce: the block that draws the last ticket adds the partials up in index order (the sum does not
+            // depend on which block that is) and hands the ticket counter back at zero for the next call
+            __threadfence();
+            s_last = atomicAdd(ticket, 1u) == gridDim.x - 1u;
+        }
+    }
+    if (!total) return;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    float acc = 0.0f;
+    for (unsigned k = threadIdx.x; k < gridDim.x; k += kThreads) acc += __ldcg(partial + k);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.0f;
+#pragma unroll
+        for (int k = 0; k < kThreads / 32; ++k) t += s_sum[k];
+        *total = t * scale;
+        *ticket = 0u;
     }
 }
 
@@ -2592,9 +2619,10 @@ int sphk_riou_fwd_bwd(const float* obb1, const float* obb2, int64_t n, float* io
     return SPHK_OK;
 }
 
-int sphk_obb_loss(int loss_kind, int fun, int flags, float tau, float alpha, float beta, float eps, int transform,
-                  const float* pred, const float* target, int64_t n, int D, const float* upstream, int up_cols, float scale,
-                  float* loss, float* partial, float* grad_pred, float* grad_target, void* stream) {
+static int obb_loss_impl(int loss_kind, int fun, int flags, float tau, float alpha, float beta, float eps, int transform,
+                         const float* pred, const float* target, int64_t n, int D, const float* upstream, int up_cols, float scale,
+                         float* loss, float* partial, float* grad_pred, float* grad_target, float* total, unsigned* ticket,
+                         void* stream) {
     if (n < 0 || (D != 4 && D != 5)) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_obb_loss: n < 0 or D not in {4,5}");
     if (loss_kind < SPHK_LOSS_GWD || loss_kind > SPHK_LOSS_L1) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_obb_loss: unknown loss kind");
     if (fun < 0 || fun > 2) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_obb_loss: unknown fun");
@@ -2612,10 +2640,31 @@ int sphk_obb_loss(int loss_kind, int fun, int flags, float tau, float alpha, flo
     cudaStream_t s = (cudaStream_t)stream;
     const bool v = aligned16(pred) && aligned16(target) && (!grad_pred || aligned16(grad_pred)) &&
                    (!grad_target || aligned16(grad_target));
-    if (D == 4) k_obb_loss<4, SPHK_LOSS_SCALAR><<<blocks_for(n), kThreads, 0, s>>>(lp, transform, pred, target, n, upstream, up_cols, scale, loss, partial, grad_pred, grad_target, v);
-    else k_obb_loss<5, SPHK_LOSS_SCALAR><<<blocks_for(n), kThreads, 0, s>>>(lp, transform, pred, target, n, upstream, up_cols, scale, loss, partial, grad_pred, grad_target, v);
+    if (D == 4) k_obb_loss<4, SPHK_LOSS_SCALAR><<<blocks_for(n), kThreads, 0, s>>>(lp, transform, pred, target, n, upstream, up_cols, scale, loss, partial, grad_pred, grad_target, v, total, ticket);
+    else k_obb_loss<5, SPHK_LOSS_SCALAR><<<blocks_for(n), kThreads, 0, s>>>(lp, transform, pred, target, n, upstream, up_cols, scale, loss, partial, grad_pred, grad_target, v, total, ticket);
     SPHK_LAUNCH_CHECK("k_obb_loss");
     return SPHK_OK;
+}
+
+int sphk_obb_loss(int loss_kind, int fun, int flags, float tau, float alpha, float beta, float eps, int transform,
+                  const float* pred, const float* target, int64_t n, int D, const float* upstream, int up_cols, float scale,
+                  float* loss, float* partial, float* grad_pred, float* grad_target, void* stream) {
+    return obb_loss_impl(loss_kind, fun, flags, tau, alpha, beta, eps, transform, pred, target, n, D, upstream, up_cols, scale, loss,
+                         partial, grad_pred, grad_target, nullptr, nullptr, stream);
+}
+
+int sphk_obb_loss_total(int loss_kind, int fun, int flags, float tau, float alpha, float beta, float eps, int transform,
+                        const float* pred, const float* target, int64_t n, int D, const float* upstream, int up_cols, float scale,
+                        float* total, void* scratch, float* grad_pred, float* grad_target, void* stream) {
+    if (!total) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_obb_loss_total: null pointer");
+    if (n == 0) {
+        const cudaError_t e = cudaMemsetAsync(total, 0, sizeof(float), (cudaStream_t)stream);
+        return e == cudaSuccess ? SPHK_OK : cuda_fail(e, "cudaMemsetAsync(total)");
+    }
+    if (!scratch || !aligned16(scratch)) return fail(SPHK_ERR_INVALID_ARGUMENT, "sphk_obb_loss_total: null or unaligned scratch");
+    // scratch as for sphk_loss_reduce_total: the ticket counter (zero between calls) in its first 16 bytes, then the per-block sums
+    return obb_loss_impl(loss_kind, fun, flags, tau, alpha, beta, eps, transform, pred, target, n, D, upstream, up_cols, scale, nullptr,
+                         (float*)((char*)scratch + 16), grad_pred, grad_target, total, (unsigned*)scratch, stream);
 }
 
 static int coder_params(const char* who, int D, const float* means, const float* stds, float wh_ratio_clip, int clip_border,

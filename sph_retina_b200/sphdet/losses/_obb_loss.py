@@ -15,20 +15,20 @@ class _ObbLossReduced(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pred, target, weight, scale, kind, cfg):
         need_p, need_t = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        _, partial, gp, gt = _native.obb_loss(kind, pred.detach(), target.detach(), None if weight is None else weight.detach(),
-                                              scale, want_loss=False, want_partial=True, want_grad_pred=need_p,
-                                              want_grad_target=need_t, **cfg)
+        # the kernel writes the finished scalar: the forward of a training step is this one launch, no reduction op
+        total, gp, gt = _native.obb_loss_total(kind, pred.detach(), target.detach(), None if weight is None else weight.detach(),
+                                               scale, want_grad_pred=need_p, want_grad_target=need_t, **cfg)
         ctx.save_for_backward(*[g for g in (gp, gt) if g is not None])
         ctx.have = (need_p, need_t)
         ctx.in_dtypes = (pred.dtype, target.dtype)
-        return (partial.sum() * scale).to(pred.dtype)
+        return total if pred.dtype == torch.float32 else total.to(pred.dtype)
 
     @staticmethod
     def backward(ctx, grad_loss):
         saved = list(ctx.saved_tensors)
         gp = saved.pop(0) if ctx.have[0] else None
         gt = saved.pop(0) if ctx.have[1] else None
-        g = grad_loss.float()
+        g = grad_loss if grad_loss.dtype == torch.float32 else grad_loss.float()
         return (None if gp is None else (gp * g).to(ctx.in_dtypes[0]),
                 None if gt is None else (gt * g).to(ctx.in_dtypes[1]), None, None, None, None)
 

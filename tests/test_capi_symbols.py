@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol(built_lib):
     for name in declared_symbols():
         assert hasattr(lib, name), "libsphk.so does not export %s" % name
     lib.sphk_abi_version.restype = ctypes.c_int
-    assert lib.sphk_abi_version() == 7
+    assert lib.sphk_abi_version() == 8
 
 
 def test_binding_covers_the_header(built_lib):
